@@ -1,0 +1,35 @@
+import gzip
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_cases():
+    with open(os.path.join(GOLDEN, "cases.json")) as f:
+        return json.load(f)
+
+
+def golden_json(name):
+    with gzip.open(os.path.join(GOLDEN, name + ".json.gz"), "rb") as f:
+        return json.loads(f.read().decode())
+
+
+def golden_trace_path(name):
+    return os.path.join(GOLDEN, name + ".trace")
+
+
+@pytest.fixture(scope="session")
+def cases():
+    return golden_cases()
