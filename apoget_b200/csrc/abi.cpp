@@ -1,0 +1,378 @@
+// extern "C" boundary of libapt_b200.so (declarations and contracts: include/apt_b200.h).
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+#include "engine.h"
+
+using namespace apt;
+
+namespace {
+thread_local std::string g_error;
+
+template <typename F>
+int guarded (F f) {
+  try { f(); g_error.clear(); return APT_OK; }
+  catch (const ApiError &e) { g_error = e.what(); return e.status; }
+  catch (const std::bad_alloc &) { g_error = "out of host memory"; return APT_ERR_NOMEM; }
+  catch (const std::exception &e) { g_error = e.what(); return APT_ERR_STATE; }
+}
+
+void need (bool ok, const char *what) { if (!ok) throw ApiError(APT_ERR_ARGUMENT, what); }
+
+void requireDevice (int device) {
+  int count = 0;
+  cudaCheck(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+  if (device < 0 || device >= count) throw ApiError(APT_ERR_CUDA, "no such CUDA device");
+  cudaCheck(cudaSetDevice(device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  cudaCheck(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  if (prop.major != 10) throw ApiError(APT_ERR_CUDA, "libapt_b200 holds sm_100a code only");
+}
+
+template <typename T>
+struct Tmp {             // device scratch for the host-pointer variants of the stateless kernels
+  T *p = nullptr;
+  explicit Tmp (size_t n) { if (n) cudaCheck(cudaMalloc(&p, n * sizeof(T)), "cudaMalloc"); }
+  ~Tmp (void) { if (p) cudaFree(p); }
+  void up (const T *h, size_t n) { if (n) cudaCheck(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice), "H2D"); }
+  void down (T *h, size_t n) { if (n) cudaCheck(cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost), "D2H"); }
+};
+}
+
+struct apt_tree { Engine engine; explicit apt_tree (const apt_params &p) : engine(p) {} };
+
+/// Stand-alone enveloppe pool for the stateless kernels
+struct apt_pool {
+  apt_params prm;
+  uint32_t K, W, wp, nSpecies, lutStride;
+  bool lut;
+  uint32_t *payload = nullptr;  float4 *meta = nullptr;  uint32_t *fill = nullptr;  double *dlut = nullptr;
+  std::vector<float> classes;       // triples, class id = index
+  ~apt_pool (void) { cudaFree(payload); cudaFree(meta); cudaFree(fill); cudaFree(dlut); }
+  uint32_t classOf (float mu, float sin, float sout) {
+    for (size_t i = 0; i < classes.size(); i += 3)
+      if (classes[i] == mu && classes[i + 1] == sin && classes[i + 2] == sout) return uint32_t(i / 3);
+    classes.push_back(mu);  classes.push_back(sin);  classes.push_back(sout);
+    return uint32_t(classes.size() / 3 - 1);
+  }
+  void uploadLut (void) {
+    if (!lut) return;
+    const size_t n = classes.size() / 3;
+    std::vector<double> h (n * lutStride);
+    for (size_t c = 0; c < n; c++)
+      for (uint32_t d = 0; d < lutStride; d++) {
+        const float mu = classes[3 * c];
+        const double dd = d, sigma = dd < mu ? classes[3 * c + 1] : classes[3 * c + 2];
+        h[c * lutStride + d] = std::exp(-((dd - mu) * (dd - mu)) / (2. * sigma * sigma));   // crossover.h:89-92
+      }
+    cudaFree(dlut);  dlut = nullptr;
+    cudaCheck(cudaMalloc(&dlut, h.size() * sizeof(double)), "cudaMalloc");
+    cudaCheck(cudaMemcpy(dlut, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice), "LUT upload");
+  }
+  PoolView view (void) const { return PoolView { payload, meta, fill, K, wp, nSpecies }; }
+  ScoreCfg cfg (void) const {
+    return ScoreCfg { int(prm.kind), prm.full_continuous, lut ? 1 : 0, prm.compat_thr, prm.sim_thr, prm.avg_thr, dlut, lutStride };
+  }
+  /// pads + packs host births into device buffers
+  void packBirths (uint32_t n, const uint32_t *pl, const float *compat, Tmp<uint32_t> &dB, Tmp<float4> &dM) {
+    std::vector<uint32_t> hb (size_t(n) * wp, 0u);
+    std::vector<float4> hm (n);
+    const size_t before = classes.size();
+    for (uint32_t i = 0; i < n; i++) {
+      memcpy(&hb[size_t(i) * wp], pl + size_t(i) * W, W * 4);
+      const uint32_t cls = lut ? classOf(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2]) : 0;
+      float fc;  memcpy(&fc, &cls, 4);
+      hm[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], fc);
+    }
+    if (classes.size() != before) uploadLut();
+    dB.up(hb.data(), hb.size());
+    dM.up(hm.data(), n);
+  }
+};
+
+extern "C" {
+
+void apt_params_default (apt_params *p) {
+  memset(p, 0, sizeof *p);
+  p->kind = APT_BITS;  p->words = 8;
+  p->rset_size = 5;  p->full_continuous = 1;  p->env_crit = 1;         // ptreeconfig.cpp:10, 18, 19
+  p->compat_thr = .1;  p->sim_thr = .5;  p->avg_thr = .25;             // ptreeconfig.cpp:7-9
+  p->trim_period = 100;  p->trim_thr = .25f;  p->trim_delay = 4.f;  p->trim_min_delay = 200;   // :13-16
+}
+
+const char* apt_last_error (void) { return g_error.c_str(); }
+
+int apt_device_available (void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  for (int d = 0; d < count; d++) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) return 1;
+  }
+  return 0;
+}
+
+int apt_tree_create (const apt_params *params, apt_tree **out) {
+  return guarded([&] {
+    need(params && out, "null argument");
+    *out = new apt_tree(*params);
+  });
+}
+
+void apt_tree_destroy (apt_tree *t) { delete t; }
+
+int apt_tree_add_genomes (apt_tree *t, uint32_t n, const uint32_t *payload, const float *compat,
+                          const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                          const uint32_t *fgid, const uint32_t *fsid,
+                          uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced, uint32_t *n_done) {
+  return guarded([&] {
+    need(t && (n == 0 || (payload && compat && gid && mgid && msid && fgid && fsid)), "null argument");
+    t->engine.addGenomes(n, payload, compat, false, nullptr, gid, mgid, msid, fgid, fsid,
+                         out_sid, out_slot, out_replaced, n_done);
+  });
+}
+
+int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload, const float *d_compat, void *stream,
+                              const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                              const uint32_t *fgid, const uint32_t *fsid,
+                              uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced, uint32_t *n_done) {
+  return guarded([&] {
+    need(t && (n == 0 || (d_payload && d_compat && gid && mgid && msid && fgid && fsid)), "null argument");
+    t->engine.addGenomes(n, d_payload, d_compat, true, static_cast<cudaStream_t>(stream), gid, mgid, msid, fgid, fsid,
+                         out_sid, out_slot, out_replaced, n_done);
+  });
+}
+
+int apt_tree_del_genome (apt_tree *t, uint32_t sid) { return guarded([&] { need(t, "null tree"); t->engine.delGenome(sid); }); }
+
+int apt_tree_register_candidate (apt_tree *t, uint32_t msid, uint32_t fsid, int dir) {
+  return guarded([&] { need(t && (dir == 1 || dir == -1), "bad argument"); t->engine.candidacy(msid, fsid, dir); });
+}
+
+int apt_tree_set_step (apt_tree *t, uint32_t step) { return guarded([&] { need(t, "null tree"); t->engine.setStep(step); }); }
+
+int apt_tree_step (apt_tree *t, uint32_t step, const uint32_t *alive, uint32_t n) {
+  return guarded([&] { need(t && (n == 0 || alive), "null argument"); t->engine.doStep(step, alive, n); });
+}
+
+int apt_tree_stats (apt_tree *t, uint32_t out[8]) { return guarded([&] { need(t && out, "null argument"); t->engine.stats(out); }); }
+int apt_tree_reset_stats (apt_tree *t) { return guarded([&] { need(t, "null tree"); t->engine.resetStats(); }); }
+
+uint32_t apt_tree_event_count (apt_tree *t) { return t ? uint32_t(t->engine.events().size()) : 0; }
+
+uint32_t apt_tree_events (apt_tree *t, apt_event *out, uint32_t cap, int drain) {
+  if (!t) return 0;
+  auto &ev = t->engine.events();
+  const uint32_t n = uint32_t(std::min<size_t>(cap, ev.size()));
+  if (out && n) memcpy(out, ev.data(), n * sizeof(apt_event));
+  if (drain) ev.erase(ev.begin(), ev.begin() + n);
+  return n;
+}
+
+uint64_t apt_tree_to_json (apt_tree *t, char *out, uint64_t cap) {
+  if (!t) return 0;
+  const std::string s = t->engine.toJson();
+  if (out && cap) memcpy(out, s.data(), std::min<uint64_t>(cap, s.size()));
+  return s.size();
+}
+
+int apt_tree_node_info (apt_tree *t, uint32_t sid, apt_node_info *out) {
+  return guarded([&] {
+    need(t && out, "null argument");
+    const Species *s = t->engine.nodeAt(sid);
+    out->sid = s->sid;  out->parent_sid = s->parent ? s->parent->sid : APT_INVALID;
+    out->data[0] = s->first; out->data[1] = s->last; out->data[2] = s->count; out->data[3] = s->alive; out->data[4] = s->pending;
+    out->fill = s->k;  out->n_children = uint32_t(s->children.size());  out->n_contributors = uint32_t(s->contribs.size());
+  });
+}
+
+int apt_tree_node_children (apt_tree *t, uint32_t sid, uint32_t *out, uint32_t cap) {
+  return guarded([&] {
+    need(t && out, "null argument");
+    const Species *s = t->engine.nodeAt(sid);
+    for (size_t i = 0; i < s->children.size() && i < cap; i++) out[i] = s->children[i]->sid;
+  });
+}
+
+int apt_tree_node_contributors (apt_tree *t, uint32_t sid, uint32_t *out, uint32_t cap) {
+  return guarded([&] {
+    need(t && out, "null argument");
+    const Species *s = t->engine.nodeAt(sid);
+    for (size_t i = 0; i < s->contribs.size() && i < cap; i++) {
+      out[3 * i] = s->contribs[i].sid;  out[3 * i + 1] = s->contribs[i].count;  out[3 * i + 2] = s->contribs[i].elligible;
+    }
+  });
+}
+
+int apt_tree_node_rep_gids (apt_tree *t, uint32_t sid, uint32_t *out, uint32_t cap) {
+  return guarded([&] {
+    need(t && out, "null argument");
+    const Species *s = t->engine.nodeAt(sid);
+    for (uint32_t r = 0; r < s->k && r < cap; r++) out[r] = s->reps[r].gid;
+  });
+}
+
+int apt_tree_node_distances (apt_tree *t, uint32_t sid, float *out) {
+  return guarded([&] {
+    need(t && out, "null argument");
+    const Species *s = t->engine.nodeAt(sid);
+    const uint32_t K = t->engine.params().rset_size;
+    for (uint32_t i = 0; i < K; i++)
+      for (uint32_t j = 0; j < K; j++)
+        out[i * K + j] = (i != j && i < s->k && j < s->k) ? s->dist[i * K + j] : std::numeric_limits<float>::quiet_NaN();
+  });
+}
+
+int apt_tree_root (apt_tree *t, uint32_t *out) {
+  return guarded([&] { need(t && out, "null argument"); *out = t->engine.root() ? t->engine.root()->sid : APT_INVALID; });
+}
+
+int apt_tree_alive_species (apt_tree *t, uint32_t *out, uint32_t cap, uint32_t *n) {
+  return guarded([&] {
+    need(t && n, "null argument");
+    const auto &a = t->engine.aliveSpecies();
+    *n = uint32_t(a.size());
+    uint32_t i = 0;
+    for (uint32_t s: a) { if (i >= cap || !out) break; out[i++] = s; }
+  });
+}
+
+int apt_tree_counters (apt_tree *t, uint64_t out[8]) {
+  return guarded([&] { need(t && out, "null argument"); memcpy(out, t->engine.counters, sizeof t->engine.counters); });
+}
+
+int apt_tree_timers (apt_tree *t, double out[4]) {
+  return guarded([&] { need(t && out, "null argument"); memcpy(out, t->engine.timers, sizeof t->engine.timers); });
+}
+
+// ---- stateless kernels ----------------------------------------------------------------------------
+
+int apt_pool_create (const apt_params *params, uint32_t n_species, const uint32_t *rep_payload,
+                     const float *rep_compat, const uint32_t *fill, apt_pool **out) {
+  return guarded([&] {
+    need(params && out && (n_species == 0 || (rep_payload && rep_compat && fill)), "null argument");
+    need(params->kind <= APT_F32 && params->words >= 1 && params->words <= 1024, "bad genome shape");
+    need(params->rset_size >= 1 && params->rset_size <= KMAX, "rset_size must be in 1..32");
+    requireDevice(params->device);
+    std::unique_ptr<apt_pool> p (new apt_pool);
+    p->prm = *params;  p->K = params->rset_size;  p->W = params->words;  p->wp = (p->W + 3u) & ~3u;
+    p->nSpecies = n_species;  p->lutStride = 32u * p->W + 1u;
+    p->lut = params->kind == APT_BITS && !(params->flags & APT_FLAG_FORCE_GENERIC);
+    const size_t rows = size_t(n_species) * p->K;
+    std::vector<uint32_t> hp (rows * p->wp, 0u);
+    std::vector<float4> hm (rows);
+    for (size_t r = 0; r < rows; r++) {
+      memcpy(&hp[r * p->wp], rep_payload + r * p->W, p->W * 4);
+      const bool used = (r % p->K) < fill[r / p->K];
+      const uint32_t cls = (p->lut && used) ? p->classOf(rep_compat[3 * r], rep_compat[3 * r + 1], rep_compat[3 * r + 2]) : 0;
+      float fc;  memcpy(&fc, &cls, 4);
+      hm[r] = make_float4(rep_compat[3 * r], rep_compat[3 * r + 1], rep_compat[3 * r + 2], fc);
+    }
+    cudaCheck(cudaMalloc(&p->payload, std::max<size_t>(hp.size(), 4) * 4), "cudaMalloc");
+    cudaCheck(cudaMalloc(&p->meta, std::max<size_t>(rows, 1) * sizeof(float4)), "cudaMalloc");
+    cudaCheck(cudaMalloc(&p->fill, std::max<size_t>(n_species, 1) * 4), "cudaMalloc");
+    if (rows) {
+      cudaCheck(cudaMemcpy(p->payload, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice), "pool upload");
+      cudaCheck(cudaMemcpy(p->meta, hm.data(), rows * sizeof(float4), cudaMemcpyHostToDevice), "pool upload");
+      cudaCheck(cudaMemcpy(p->fill, fill, size_t(n_species) * 4, cudaMemcpyHostToDevice), "pool upload");
+    }
+    p->uploadLut();
+    *out = p.release();
+  });
+}
+
+void apt_pool_destroy (apt_pool *p) { delete p; }
+
+int apt_score_pairs (apt_pool *p, uint32_t n_births, const uint32_t *payload, const float *compat,
+                     uint32_t n_pairs, const uint32_t *pair_birth, const uint32_t *pair_species,
+                     float *out_score, float *out_dist) {
+  return guarded([&] {
+    need(p && out_score && out_dist && (n_pairs == 0 || (payload && compat && pair_birth && pair_species)), "null argument");
+    for (uint32_t i = 0; i < n_pairs; i++)
+      need(pair_birth[i] < n_births && pair_species[i] < p->nSpecies, "pair index out of range");
+    cudaCheck(cudaSetDevice(p->prm.device), "cudaSetDevice");
+    Tmp<uint32_t> dB (size_t(n_births) * p->wp + 4);  Tmp<float4> dM (n_births + 1);
+    p->packBirths(n_births, payload, compat, dB, dM);
+    Tmp<uint32_t> dPb (n_pairs), dPs (n_pairs);  Tmp<float> dS (n_pairs), dD (size_t(n_pairs) * p->K);
+    dPb.up(pair_birth, n_pairs);  dPs.up(pair_species, n_pairs);
+    launch_score_pairs(p->view(), p->cfg(), dB.p, dM.p, n_pairs, dPb.p, dPs.p, dS.p, dD.p, nullptr);
+    cudaCheck(cudaGetLastError(), "score_pairs launch");
+    cudaCheck(cudaDeviceSynchronize(), "score_pairs");
+    dS.down(out_score, n_pairs);  dD.down(out_dist, size_t(n_pairs) * p->K);
+  });
+}
+
+int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_payload, const float *d_compat,
+                            uint32_t *d_best, float *d_best_score, uint32_t *d_first, uint32_t *d_count, void *stream) {
+  return guarded([&] {
+    need(p && d_payload && d_compat && d_best && d_best_score && d_first && d_count, "null argument");
+    need(!p->lut || p->classes.size() <= 3, "device-resident births need a single compatibility class (or APT_FLAG_FORCE_GENERIC)");
+    cudaCheck(cudaSetDevice(p->prm.device), "cudaSetDevice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t *dB = nullptr;  float4 *dM = nullptr;
+    cudaCheck(cudaMallocAsync(&dB, (size_t(n_births) * p->wp + 4) * 4, st), "cudaMallocAsync");
+    cudaCheck(cudaMallocAsync(&dM, (size_t(n_births) + 1) * sizeof(float4), st), "cudaMallocAsync");
+    launch_pack_births(d_payload, d_compat, nullptr, n_births, p->W, p->wp, dB, dM, st);
+    launch_classify_dense(p->view(), p->cfg(), dB, dM, n_births, d_best, d_best_score, d_first, d_count, st);
+    cudaCheck(cudaGetLastError(), "classify_dense launch");
+    cudaCheck(cudaFreeAsync(dB, st), "cudaFreeAsync");
+    cudaCheck(cudaFreeAsync(dM, st), "cudaFreeAsync");
+  });
+}
+
+int apt_classify_dense (apt_pool *p, uint32_t n_births, const uint32_t *payload, const float *compat,
+                        uint32_t *out_best, float *out_best_score, uint32_t *out_first, uint32_t *out_count) {
+  return guarded([&] {
+    need(p && (n_births == 0 || (payload && compat && out_best && out_best_score && out_first && out_count)), "null argument");
+    cudaCheck(cudaSetDevice(p->prm.device), "cudaSetDevice");
+    Tmp<uint32_t> dB (size_t(n_births) * p->wp + 4);  Tmp<float4> dM (n_births + 1);
+    p->packBirths(n_births, payload, compat, dB, dM);
+    Tmp<uint32_t> dBest (n_births), dFirst (n_births), dCount (n_births);  Tmp<float> dScore (n_births);
+    launch_classify_dense(p->view(), p->cfg(), dB.p, dM.p, n_births, dBest.p, dScore.p, dFirst.p, dCount.p, nullptr);
+    cudaCheck(cudaGetLastError(), "classify_dense launch");
+    cudaCheck(cudaDeviceSynchronize(), "classify_dense");
+    dBest.down(out_best, n_births);  dScore.down(out_best_score, n_births);
+    dFirst.down(out_first, n_births);  dCount.down(out_count, n_births);
+  });
+}
+
+int apt_env_contribution (const apt_params *params, uint32_t n, const float *edist, const float *gdist,
+                          uint8_t *out_better, uint32_t *out_than, float *out_value) {
+  return guarded([&] {
+    need(params && (n == 0 || (edist && gdist && out_better && out_than && out_value)), "null argument");
+    need(params->env_crit == 0 || params->env_crit == 1, "only criteria 0 and 1 run on the device");
+    need(params->rset_size >= 1 && params->rset_size <= KMAX, "rset_size must be in 1..32");
+    requireDevice(params->device);
+    const uint32_t K = params->rset_size;
+    Tmp<float> dE (size_t(n) * K * K), dG (size_t(n) * K), dV (n);
+    Tmp<uint8_t> dBt (n);  Tmp<uint32_t> dT (n);
+    dE.up(edist, size_t(n) * K * K);  dG.up(gdist, size_t(n) * K);
+    launch_env_contribution(params->env_crit, K, n, dE.p, dG.p, dBt.p, dT.p, dV.p, nullptr);
+    cudaCheck(cudaGetLastError(), "env_contribution launch");
+    cudaCheck(cudaDeviceSynchronize(), "env_contribution");
+    dBt.down(out_better, n);  dT.down(out_than, n);  dV.down(out_value, n);
+  });
+}
+
+int apt_pairwise (const apt_params *params, uint32_t n_genomes, const uint32_t *payload, uint32_t n_pairs,
+                  const uint32_t *idx_a, const uint32_t *idx_b, float *out) {
+  return guarded([&] {
+    need(params && (n_pairs == 0 || (payload && idx_a && idx_b && out)), "null argument");
+    need(params->kind <= APT_F32 && params->words >= 1 && params->words <= 1024, "bad genome shape");
+    for (uint32_t i = 0; i < n_pairs; i++) need(idx_a[i] < n_genomes && idx_b[i] < n_genomes, "pair index out of range");
+    requireDevice(params->device);
+    const uint32_t W = params->words, wp = (W + 3u) & ~3u;
+    std::vector<uint32_t> hp (size_t(n_genomes) * wp, 0u);
+    for (uint32_t i = 0; i < n_genomes; i++) memcpy(&hp[size_t(i) * wp], payload + size_t(i) * W, W * 4);
+    Tmp<uint32_t> dP (hp.size() + 4), dA (n_pairs), dB (n_pairs);  Tmp<float> dO (n_pairs);
+    dP.up(hp.data(), hp.size());  dA.up(idx_a, n_pairs);  dB.up(idx_b, n_pairs);
+    launch_pairwise(int(params->kind), wp, dP.p, n_pairs, dA.p, dB.p, dO.p, nullptr);
+    cudaCheck(cudaGetLastError(), "pairwise launch");
+    cudaCheck(cudaDeviceSynchronize(), "pairwise");
+    dO.down(out, n_pairs);
+  });
+}
+
+} // extern "C"

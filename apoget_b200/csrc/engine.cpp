@@ -1,0 +1,883 @@
+// Tree engine: hierarchy bookkeeping + ordered resolution pass (see engine.h).
+// Reference citations are relative to /root/reference/src/core/tree unless a path is given.
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+namespace apt {
+
+namespace {
+constexpr uint32_t INV = APT_INVALID;
+// Scores that were not produced with reference-identical arithmetic (device exp(), tree-order
+// float-vector distances, float-rounded distances) are only acted upon outside this band; inside
+// it the host recomputes them exactly.  The error of those scores is bounded by a few float ulps
+// of a value <= 1 (~1e-7), two orders of magnitude below the band.
+constexpr float GUARD = 1e-5f;
+
+double now (void) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}
+
+void cudaCheck (cudaError_t e, const char *what) {
+  if (e != cudaSuccess)
+    throw ApiError(APT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------------------------
+Engine::Engine (const apt_params &p) : p_(p) {
+  if (p.kind > APT_F32) throw ApiError(APT_ERR_ARGUMENT, "unknown genome kind");
+  if (p.words == 0 || p.words > 1024) throw ApiError(APT_ERR_ARGUMENT, "words must be in 1..1024");
+  if (p.rset_size == 0 || p.rset_size > KMAX) throw ApiError(APT_ERR_ARGUMENT, "rset_size must be in 1..32");
+  if (p.env_crit < 0 || p.env_crit > 3) throw ApiError(APT_ERR_ARGUMENT, "No function for this use case");
+  K_ = p.rset_size;  W_ = p.words;  wp_ = (W_ + 3u) & ~3u;
+  lutMode_ = (p.kind == APT_BITS) && !(p.flags & APT_FLAG_FORCE_GENERIC);
+  lutStride_ = 32u * W_ + 1u;
+
+  int count = 0;
+  cudaCheck(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+  if (p.device < 0 || p.device >= count) throw ApiError(APT_ERR_CUDA, "no such CUDA device");
+  cudaCheck(cudaSetDevice(p.device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  cudaCheck(cudaGetDeviceProperties(&prop, p.device), "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    throw ApiError(APT_ERR_CUDA, "libapt_b200 holds sm_100a code only; device is sm_" +
+                   std::to_string(prop.major) + std::to_string(prop.minor));
+  cudaCheck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  cudaCheck(cudaEventCreateWithFlags(&evUser_, cudaEventDisableTiming), "cudaEventCreate");
+}
+
+Engine::~Engine (void) {
+  for (Species *s: nodes_) delete s;
+  for (Species *s: graveyard_) delete s;
+  if (evUser_) cudaEventDestroy(evUser_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+// phylogenetictree.hpp:168-177
+Species* Engine::nodeAt (uint32_t sid) const {
+  if (sid == INV) throw ApiError(APT_ERR_ARGUMENT, "SID::INVALID is (by definition) invalid");
+  if (sid >= nodes_.size() || !nodes_[sid])
+    throw ApiError(APT_ERR_ARGUMENT, "No node found for species " + std::to_string(sid));
+  return nodes_[sid];
+}
+
+// ---- contributors / parents -------------------------------------------------------------------
+
+// speciescontributors.h:177-197
+bool Engine::elligibile (uint32_t lhs, uint32_t rhs) const {
+  const Species *n = nodes_.at(lhs);
+  if (rhs >= nodes_.size() || !nodes_[rhs]) return false;      // removed species are ignored
+  const Species *q = nodes_[rhs];
+  if (n->first <= q->first) return false;                       // no younger (or same-age) parent
+  while (q && q != n) q = q->parent;                            // not inside n's subtree
+  return q != n;
+}
+
+// speciescontributors.cpp:67-83
+uint32_t Engine::currentMain (Species *n) const {
+  const auto &v = n->contribs;
+  if (v.empty()) return INV;
+  size_t i = 1;
+  Contributor mc = v[0];
+  while (!mc.elligible && i < v.size()) mc = v[i++];
+  return mc.elligible ? mc.sid : INV;
+}
+
+// speciescontributors.cpp:15-65
+uint32_t Engine::contributorsUpdate (Species *n, Contributions ctbs) {
+  auto &v = n->contribs;
+  size_t i = 0, unprocessed = ctbs.size();
+  ctbs.erase(std::remove_if(ctbs.begin(), ctbs.end(), [] (const Contribution &c) { return c.species == INV; }),
+             ctbs.end());
+  while (i < v.size() && unprocessed > 0) {
+    const uint32_t sid = v[i].sid;
+    auto it = std::find_if(ctbs.begin(), ctbs.end(), [sid] (const Contribution &c) { return c.species == sid; });
+    if (it != ctbs.end()) {
+      v[i].count += it->count;
+      unprocessed--;
+      ctbs.erase(it);
+    }
+    i++;
+  }
+  for (const Contribution &c: ctbs) v.push_back({c.species, c.count, elligibile(n->sid, c.species)});
+  std::stable_sort(v.begin(), v.end(), [] (const Contributor &l, const Contributor &r) { return l.count > r.count; });
+  return currentMain(n);
+}
+
+// node.hpp:239-241
+Species* Engine::updateParent (Species *n, uint32_t sid) {
+  if (sid == INV) return n->parent = nullptr;
+  if (sid >= nodes_.size() || !nodes_[sid])     // std::map::at would throw in the reference
+    throw ApiError(APT_ERR_STATE, "major contributor " + std::to_string(sid) + " no longer exists");
+  return n->parent = nodes_[sid];
+}
+
+// node.hpp:182-185
+Species* Engine::nodeUpdate (Species *n, const Contributions &c) { return updateParent(n, contributorsUpdate(n, c)); }
+
+// phylogenetictree.hpp:773-783 with node.hpp:191-194 and speciescontributors.cpp:85-90
+void Engine::updateElligibilities (void) {
+  for (Species *n: nodes_) {
+    if (!n) continue;
+    for (Contributor &c: n->contribs) c.elligible = elligibile(n->sid, c.sid);
+    updateParent(n, currentMain(n));
+  }
+}
+
+uint32_t Engine::allocSlot (void) {
+  uint32_t slot;
+  if (!freeSlots_.empty()) { slot = freeSlots_.back(); freeSlots_.pop_back(); }
+  else {
+    slot = nSlots_++;
+    hPayload_.resize(size_t(nSlots_) * K_ * wp_, 0u);
+  }
+  return slot;
+}
+
+// phylogenetictree.hpp:398-426
+Species* Engine::makeNode (const Contributions &contrib) {
+  Species *n = new Species;
+  n->sid = nextNodeID_++;
+  n->slot = allocSlot();
+  n->reps.resize(K_);
+  n->dist.assign(size_t(K_) * K_, 0.f);
+  n->first = n->last = step_;
+  if (nodes_.size() <= n->sid) nodes_.resize(std::max<size_t>(n->sid + 1, nodes_.size() * 2), nullptr);
+  nodes_[n->sid] = n;
+  width_++;
+  nodeUpdate(n, contrib);
+  if (n->parent) n->parent->children.push_back(n);
+  emit(APT_EV_NEW_SPECIES, n->parent ? n->parent->sid : INV, n->sid, 0);
+  return n;
+}
+
+// phylogenetictree.hpp:741-769
+void Engine::updateContributions (Species *s, const Contributions &contrib) {
+  Species *oldMC = s->parent, *newMC = nodeUpdate(s, contrib);
+  if (oldMC != newMC) {
+    if (!newMC) throw ApiError(APT_ERR_STATE, "species lost its major contributor");   // assert(newMC), :751
+    if (oldMC) {
+      auto &c = oldMC->children;
+      c.erase(std::remove(c.begin(), c.end(), s), c.end());
+    }
+    newMC->children.push_back(s);
+    updateElligibilities();
+    // the reference dereferences a null oldMC here (:765-766); INVALID is reported instead
+    emit(APT_EV_MAJOR_CONTRIBUTOR, s->sid, oldMC ? oldMC->sid : INV, newMC->sid);
+  }
+}
+
+// phylogenetictree.hpp:816-860
+void Engine::performStillbornTrimming (void) {
+  const float T = p_.trim_thr, D = p_.trim_delay, MD = float(p_.trim_min_delay);
+  for (size_t i = 0; i < nodes_.size(); i++) {
+    Species *s = nodes_[i];
+    if (!s || !s->children.empty() || !s->extinct()) continue;
+    const bool underfilled = (s->k < T * K_);
+    const uint32_t liveTime = s->last - s->first, deadTime = step_ - s->last;
+    if (underfilled && std::max(MD, liveTime * D) < deadTime) {
+      if (s->parent) {
+        auto &c = s->parent->children;
+        c.erase(std::remove(c.begin(), c.end(), s), c.end());
+      }
+      stillborns_++;
+      nodes_[i] = nullptr;
+      width_--;
+      freeSlots_.push_back(s->slot);
+      fillUpdates_.push_back(s->slot);  fillUpdates_.push_back(0);
+      s->trimmed = true;  s->stale_mask = 0;                // nothing left to refresh
+      graveyard_.push_back(s);                              // `root_` may still point at it, as in the reference
+    }
+  }
+}
+
+// phylogenetictree.hpp:245-262
+void Engine::doStep (uint32_t s, const uint32_t *sids, uint32_t n) {
+  aliveSpecies_.clear();
+  for (uint32_t i = 0; i < n; i++) aliveSpecies_.insert(sids[i]);
+  for (uint32_t sid: aliveSpecies_) nodeAt(sid)->last = s;
+  step_ = s;
+  if (p_.trim_period > 0 && (step_ % p_.trim_period) == 0) performStillbornTrimming();
+  emit(APT_EV_STEPPED, s, uint32_t(aliveSpecies_.size()), 0);
+}
+
+// phylogenetictree.hpp:305-317
+void Engine::delGenome (uint32_t sid) {
+  Species *n = nodeAt(sid);
+  n->last = step_;
+  n->alive--;
+  deletions_++;
+}
+
+// phylogenetictree.hpp:786-792
+void Engine::candidacy (uint32_t msid, uint32_t fsid, int dir) {
+  if (msid != INV) nodeAt(msid)->pending += dir;
+  if (msid != fsid && fsid != INV) nodeAt(fsid)->pending += dir;
+}
+
+void Engine::stats (uint32_t out[8]) const {
+  out[0] = insertions_; out[1] = deletions_; out[2] = comparisons_; out[3] = branching_;
+  out[4] = nextNodeID_; out[5] = width_; out[6] = step_; out[7] = stillborns_;
+}
+
+// ---- exact host arithmetic ----------------------------------------------------------------------
+
+uint32_t Engine::classOf (float mu, float sin, float sout) {
+  if (lastClass_ != INV && lastTriple_.mu == mu && lastTriple_.sin == sin && lastTriple_.sout == sout)
+    return lastClass_;
+  const Triple t { mu, sin, sout };
+  auto it = classIds_.find(t);
+  uint32_t id;
+  if (it != classIds_.end()) id = it->second;
+  else {
+    id = uint32_t(classes_.size());
+    classIds_.emplace(t, id);
+    classes_.push_back(t);
+    if (lutMode_) {
+      // one table row per class, filled by the HOST libm: the device reads back the very doubles
+      // the reference would compute (crossover.h:89-92)
+      if (size_t(id + 1) * lutStride_ * sizeof(double) > (size_t(256) << 20)) {
+        lutMode_ = false;     // too many distinct triples for a table: fall back to device exp() + guard band
+        hLut_.clear();  hLut_.shrink_to_fit();
+      } else {
+        hLut_.resize(size_t(id + 1) * lutStride_);
+        for (uint32_t d = 0; d < lutStride_; d++) {
+          const double dd = d, sigma = dd < mu ? sin : sout;
+          hLut_[size_t(id) * lutStride_ + d] = std::exp(-((dd - mu) * (dd - mu)) / (2. * sigma * sigma));
+        }
+      }
+    }
+  }
+  lastTriple_ = t;  lastClass_ = id;
+  return id;
+}
+
+// crossover.h:89-92
+double Engine::compatOf (uint32_t cls, float mu, float sin, float sout, double d) const {
+  if (lutMode_) return hLut_[size_t(cls) * lutStride_ + uint32_t(d)];
+  const double sigma = d < mu ? sin : sout;
+  return std::exp(-((d - mu) * (d - mu)) / (2. * sigma * sigma));
+}
+
+/// The toy genomes' distance(): Hamming, or L2 accumulated in double in index order
+double Engine::distanceExact (const uint32_t *a, const uint32_t *b) const {
+  if (p_.kind == APT_F32) {
+    double s = 0;
+    for (uint32_t i = 0; i < W_; i++) {
+      float fa, fb;
+      memcpy(&fa, a + i, 4);  memcpy(&fb, b + i, 4);
+      const double t = double(fa) - double(fb);
+      s += t * t;
+    }
+    return std::sqrt(s);
+  }
+  uint32_t s = 0, i = 0;
+  for (; i + 2 <= W_; i += 2) {
+    uint64_t x, y;
+    memcpy(&x, a + i, 8);  memcpy(&y, b + i, 8);
+    s += uint32_t(__builtin_popcountll(x ^ y));
+  }
+  if (i < W_) s += uint32_t(__builtin_popcount(a[i] ^ b[i]));
+  return double(s);
+}
+
+// phylogenetictree.hpp:465-477 / :439-451
+float Engine::scoreFrom (const double *c, uint32_t k) const {
+  if (p_.full_continuous) {
+    float avg = 0;
+    for (uint32_t r = 0; r < k; r++) avg += c[r];
+    return avg / float(k) - p_.avg_thr;
+  }
+  uint32_t matable = 0;
+  for (uint32_t r = 0; r < k; r++) if (c[r] >= p_.compat_thr) matable++;
+  return matable - p_.sim_thr * k;
+}
+
+bool Engine::trusted (float score) const {
+  if (lutMode_) return true;
+  if (!p_.full_continuous) return false;          // vote counts can flip without moving the score
+  return std::fabs(score) > GUARD;
+}
+
+/// speciesMatchingScore (:430-490) entirely on the host, reference-identical arithmetic
+void Engine::evalExact (const uint32_t *w, const RepMeta &g, Species *s, Eval &e) {
+  double c[KMAX];
+  for (uint32_t r = 0; r < s->k; r++) {
+    const RepMeta &m = s->reps[r];
+    const double d = distanceExact(w, repPayload(s, r));
+    c[r] = std::min(compatOf(g.cls, g.mu, g.sin, g.sout, d), compatOf(m.cls, m.mu, m.sin, m.sout, d));
+    e.d[r] = float(d);
+  }
+  counters[5] += s->k;
+  e.score = scoreFrom(c, s->k);
+  e.exact = true;
+}
+
+/// Same score, using what the device computed for this (birth, species) pair wherever the
+/// device's copy of the enveloppe is still current.
+void Engine::evalSpeculated (const uint32_t *w, const RepMeta &g, Species *s, int64_t pair, Eval &e) {
+  comparisons_ += s->k;                                     // stats.comparisons++, :444 / :470
+  if (pair < 0) { counters[3]++; return evalExact(w, g, s, e); }
+  const float *dd = hDist_.p + size_t(pair) * K_;
+  const bool bits = (p_.kind == APT_BITS);
+  if (s->stale_mask == 0 && s->dev_fill == s->k) {
+    const float sc = hScore_.p[pair];
+    if (trusted(sc)) {
+      memcpy(e.d, dd, s->k * sizeof(float));
+      e.score = sc;  e.exact = lutMode_;
+      counters[1]++;
+      return;
+    }
+    counters[6]++;
+    if (!bits) { counters[3]++; return evalExact(w, g, s, e); }
+  } else if (!bits) {
+    // float-vector distances cannot be patched exactly from their float roundings
+    counters[3]++;
+    return evalExact(w, g, s, e);
+  }
+  // bit-strings: device distances are exact integers; re-measure only the changed representatives
+  double c[KMAX];
+  uint32_t measured = 0;
+  for (uint32_t r = 0; r < s->k; r++) {
+    const RepMeta &m = s->reps[r];
+    double d;
+    if (r < s->dev_fill && !((s->stale_mask >> r) & 1u)) d = dd[r];
+    else { d = distanceExact(w, repPayload(s, r)); measured++; }
+    c[r] = std::min(compatOf(g.cls, g.mu, g.sin, g.sout, d), compatOf(m.cls, m.mu, m.sin, m.sout, d));
+    e.d[r] = float(d);
+  }
+  counters[5] += measured;
+  counters[2]++;
+  e.score = scoreFrom(c, s->k);
+  e.exact = true;
+}
+
+void Engine::markStale (Species *s, uint32_t r) {
+  s->stale_mask |= (1u << r);
+  if (!s->queued) { s->queued = true; refresh_.push_back(s); }
+}
+
+// ---- enveloppe criteria (src/core/tree/enveloppecriteria.cpp) on the K x K matrix ---------------
+namespace {
+struct EC { bool better; uint32_t than; float value; };
+
+inline float ninf (void) { return -std::numeric_limits<float>::infinity(); }   // -DBL_MAX into a float, :46/:93
+
+// :87-133
+EC maxMinDist (const float *e, const float *g, uint32_t k, uint32_t K) {
+  EC ec { false, uint32_t(-1), ninf() };
+  for (uint32_t i = 0; i < k; i++) {
+    float minBase = std::numeric_limits<float>::max(), minNew = std::numeric_limits<float>::max();
+    for (uint32_t j = 0; j < k; j++) {
+      if (i == j) continue;
+      minBase = std::min(minBase, e[i * K + j]);
+      minNew = std::min(minNew, g[j]);
+    }
+    const double c = - minBase + minNew;
+    if (ec.value < c) { ec.value = float(c); ec.than = i; }
+  }
+  ec.better = (ec.value > 0);
+  return ec;
+}
+
+// :40-84
+EC maxAverage (const float *e, const float *g, uint32_t k, uint32_t K) {
+  EC ec { false, uint32_t(-1), ninf() };
+  for (uint32_t i = 0; i < k; i++) {
+    double c = 0;
+    for (uint32_t j = 0; j < k; j++) {
+      if (i == j) continue;
+      c += - e[i * K + j] + g[j];
+    }
+    if (ec.value < c) { ec.value = float(c); ec.than = i; }
+  }
+  ec.better = (ec.value > 0);
+  return ec;
+}
+
+// :29-37 over the map's iteration order (keys (i,j), i<j, lexicographic)
+void avgAndStdDev (const float *m, uint32_t k, uint32_t K, double &avg, double &stdDev) {
+  const double n = double(k) * (k - 1) / 2.;
+  avg = 0;
+  for (uint32_t i = 0; i < k; i++) for (uint32_t j = i + 1; j < k; j++) avg += m[i * K + j];
+  avg /= n;
+  stdDev = 0;
+  for (uint32_t i = 0; i < k; i++) for (uint32_t j = i + 1; j < k; j++) stdDev += std::pow(avg - m[i * K + j], 2);
+  stdDev = std::sqrt(stdDev / n);
+}
+
+// :136-202
+EC maxAvgMinStdDev (const float *e, const float *g, uint32_t k, uint32_t K) {
+  EC ec { false, uint32_t(-1), ninf() };
+  double baseAVG, baseStdDev;
+  avgAndStdDev(e, k, K, baseAVG, baseStdDev);
+  std::vector<float> n (size_t(K) * K);
+  for (uint32_t i = 0; i < k; i++) {
+    std::copy(e, e + size_t(K) * K, n.begin());
+    for (uint32_t j = 0; j < k; j++) if (i != j) n[i * K + j] = n[j * K + i] = g[j];
+    double newAVG, newStdDev;
+    avgAndStdDev(n.data(), k, K, newAVG, newStdDev);
+    const double c = - baseAVG + newAVG + baseStdDev - newStdDev;
+    if (ec.value < c) { ec.value = float(c); ec.than = i; }
+  }
+  ec.better = (ec.value > 0);
+  return ec;
+}
+
+// :205-272 with its sizing quirk (vectors built with k zeros, then k-1 values appended, :231, :238-239)
+EC maxWeightedDist2Avg (const float *e, const float *g, uint32_t k, uint32_t K) {
+  EC ec { false, uint32_t(-1), ninf() };
+  double A = 0;
+  for (uint32_t i = 0; i < k; i++) for (uint32_t j = i + 1; j < k; j++) A += e[i * K + j];
+  A /= double(k) * (k - 1) / 2.;
+  auto weight = [A] (double d) { return 1 - exp(- (d-A)*(d-A) / (2. * A * A / 16.)); };
+  for (uint32_t i = 0; i < k; i++) {
+    std::vector<double> d_i (k), d_g (k);
+    for (uint32_t j = 0; j < k; j++) {
+      if (i == j) continue;
+      d_i.push_back(e[i * K + j]);
+      d_g.push_back(g[j]);
+    }
+    std::sort(d_i.begin(), d_i.end(), [] (double a, double b) { return a > b; });
+    std::sort(d_g.begin(), d_g.end(), [] (double a, double b) { return a > b; });
+    double c = 0;
+    for (uint32_t j = 0; j + 1 < k; j++) {
+      const double nc = - d_i[j], pc = + d_g[j];
+      c += weight(pc) * (nc + pc);
+    }
+    if (ec.value < c) { ec.value = float(c); ec.than = i; }
+  }
+  ec.better = (ec.value > 0);
+  return ec;
+}
+
+// :275-289
+EC computeContribution (int crit, const float *e, const float *g, uint32_t k, uint32_t K) {
+  switch (crit) {
+  case 0: return maxAverage(e, g, k, K);
+  case 1: return maxMinDist(e, g, k, K);
+  case 2: return maxAvgMinStdDev(e, g, k, K);
+  default: return maxWeightedDist2Avg(e, g, k, K);
+  }
+}
+} // namespace
+
+// phylogenetictree.hpp:657-726.  Returns the slot the genome now occupies, or -1.
+int32_t Engine::insertInto (const uint32_t *w, const RepMeta &g, Species *s, const Eval &e, bool haveCache,
+                            uint32_t &replaced) {
+  const uint32_t k = s->k;
+  int32_t slot = -1;
+  replaced = INV;
+  auto place = [&] (uint32_t r, uint32_t udata) {
+    RepMeta m = g;
+    m.timestamp = step_;
+    m.udata = udata;
+    s->reps[r] = m;
+    uint32_t *dst = &hPayload_[(size_t(s->slot) * K_ + r) * wp_];
+    memcpy(dst, w, W_ * sizeof(uint32_t));
+    markStale(s, r);
+  };
+  if (k < K_) {
+    if (k && !haveCache) throw ApiError(APT_ERR_STATE, "append without cached distances");
+    place(k, g.gid);
+    s->k = k + 1;
+    emit(APT_EV_ENTERS_ENVELOPPE, s->sid, g.gid, 0);
+    for (uint32_t i = 0; i < k; i++) s->dist[i * K_ + k] = s->dist[k * K_ + i] = e.d[i];
+    slot = int32_t(k);
+  } else {
+    if (K_ == 1) {
+      // a single representative has no pairwise distance: every criterion yields a value <= 0 or
+      // NaN (minima stay at FLT_MAX -> c = 0, :108-117; empty sums; 0/0 averages) -> never better
+    } else {
+      const EC ec = computeContribution(p_.env_crit, s->dist.data(), e.d, k, K_);
+      if (ec.better) {
+        const uint32_t than = ec.than, epId = s->reps[than].gid;
+        emit(APT_EV_LEAVES_ENVELOPPE, s->sid, epId, 0);
+        emit(APT_EV_ENTERS_ENVELOPPE, s->sid, g.gid, 0);
+        place(than, epId);                                   // *ep.userData = UserData(ep_id), :710
+        for (uint32_t i = 0; i < k; i++)
+          if (i != than) s->dist[i * K_ + than] = s->dist[than * K_ + i] = e.d[i];
+        slot = int32_t(than);
+        replaced = epId;
+      }
+    }
+  }
+  s->count++;
+  s->alive++;
+  s->last = step_;
+  return slot;
+}
+
+// One birth, in order: public addGenome (:268-302) + private addGenome (:553-650) +
+// findBestDerived (:493-548) + updateSpeciesContents (:730-738).
+void Engine::walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uint32_t &sid, int32_t &slot,
+                      uint32_t &replaced) {
+  const uint32_t mSID = g.msid, fSID = g.fsid;
+  Species *s0 = nullptr, *s1 = nullptr;
+  if (mSID == INV && fSID == INV) s0 = root_;
+  else if (fSID == INV || mSID == fSID) s0 = nodeAt(mSID);
+  else { s0 = nodeAt(mSID); s1 = nodeAt(fSID); }
+  if (s0->pending > 0) s0->pending--;
+  if (s1 && s1->pending > 0) s1->pending--;
+
+  Eval ev0, ev1, cur, bestEval;
+  Species *best = nullptr;
+  float bestScore = -std::numeric_limits<float>::max();
+
+  Contributions contrib { { mSID, 1u + (mSID == fSID) } };
+  if (s1) contrib.push_back({ fSID, 1 });
+
+  evalSpeculated(w, g, s0, p0, ev0);
+  if (s1) {
+    evalSpeculated(w, g, s1, p1, ev1);
+    // decisions that compare the two scores (:590, :599-602) need them exact when they are close
+    if ((!ev0.exact || !ev1.exact) && std::fabs(ev0.score - ev1.score) <= GUARD) {
+      if (!ev0.exact) evalExact(w, g, s0, ev0);
+      if (!ev1.exact) evalExact(w, g, s1, ev1);
+    }
+  }
+  if (bestScore < ev0.score) { best = s0; bestScore = ev0.score; }
+  if (s1) {
+    if (bestScore < ev1.score) { best = s1; bestScore = ev1.score; }
+    // std::sort with `>=` on two elements (:599-602): the second goes first iff score1 >= score0
+    if (ev1.score >= ev0.score) std::swap(contrib[0], contrib[1]);
+  }
+  if (best) bestEval = (best == s1 && s1) ? ev1 : ev0;
+
+  if (!(bestScore > 0)) {
+    // findBestDerived (:493-548): direct sub-species, newest first, alternating between the lists
+    Species *lists[2] = { s0, s1 };
+    const uint32_t S = s1 ? 2 : 1;
+    size_t left[2] = { s0->children.size(), s1 ? s1->children.size() : 0 };
+    uint32_t done = 0;
+    const uint32_t allDone = (1u << S) - 1;
+    uint32_t k = 0;
+    while (done != allDone) {
+      if (left[k] == 0) done |= (1u << k);
+      else {
+        branching_++;
+        Species *sub = lists[k]->children[left[k] - 1];
+        evalSpeculated(w, g, sub, -1, cur);
+        if (bestScore < cur.score) { best = sub; bestScore = cur.score; bestEval = cur; }
+        if (bestScore > 0) break;
+        left[k]--;
+      }
+      k = (k + 1) % S;
+    }
+  }
+
+  if (bestScore > 0) {
+    slot = insertInto(w, g, best, bestEval, true, replaced);
+    updateContributions(best, contrib);
+    sid = best->sid;
+  } else {
+    Species *sub = makeNode(contrib);                       // simpleNewSpecies, :637-643
+    Eval none;
+    slot = insertInto(w, g, sub, none, false, replaced);
+    sid = sub->sid;
+  }
+  insertions_++;
+}
+
+// ---- device plumbing ----------------------------------------------------------------------------
+
+PoolView Engine::poolView (void) const {
+  return PoolView { dPool_.p, dMeta_.p, dFill_.p, K_, wp_, nSlots_ };
+}
+
+ScoreCfg Engine::scoreCfg (void) const {
+  return ScoreCfg { int(p_.kind), p_.full_continuous, lutMode_ ? 1 : 0, p_.compat_thr, p_.sim_thr, p_.avg_thr,
+                    dLut_.p, lutStride_ };
+}
+
+void Engine::uploadLut (void) {
+  if (!lutMode_ || lutUploaded_ == classes_.size()) return;
+  dLut_.reserve(hLut_.size(), true, stream_);
+  const size_t off = size_t(lutUploaded_) * lutStride_;
+  cudaCheck(cudaMemcpyAsync(dLut_.p + off, hLut_.data() + off, (hLut_.size() - off) * sizeof(double),
+                            cudaMemcpyHostToDevice, stream_), "LUT upload");
+  cudaCheck(cudaStreamSynchronize(stream_), "LUT upload sync");   // hLut_ is pageable and may be resized
+  lutUploaded_ = uint32_t(classes_.size());
+}
+
+/// Brings the device pool up to date with the host state: only rows that changed are staged
+/// (pinned) and scattered by one kernel.
+void Engine::refreshPool (void) {
+  const double t0 = now();
+  dPool_.reserve(size_t(nSlots_) * K_ * wp_, true, stream_);
+  dMeta_.reserve(size_t(nSlots_) * K_, true, stream_);
+  const size_t oldFillCap = dFill_.cap;
+  dFill_.reserve(nSlots_, true, stream_);
+  if (dFill_.cap != oldFillCap)
+    cudaCheck(cudaMemsetAsync(dFill_.p + oldFillCap, 0, (dFill_.cap - oldFillCap) * sizeof(uint32_t), stream_),
+              "fill clear");
+
+  size_t rows = 0;
+  for (Species *s: refresh_) rows += __builtin_popcount(s->stale_mask);
+  hStageRows_.reserve(rows * wp_ + 4);  hStageMeta_.reserve(rows + 1);
+  hStageDst_.reserve(rows + fillUpdates_.size() + 2 * refresh_.size() + 2);
+  size_t i = 0;
+  for (Species *s: refresh_) {
+    s->queued = false;
+    if (s->trimmed) continue;
+    for (uint32_t r = 0; r < s->k; r++) {
+      if (!((s->stale_mask >> r) & 1u)) continue;
+      memcpy(hStageRows_.p + i * wp_, repPayload(s, r), wp_ * sizeof(uint32_t));
+      const RepMeta &m = s->reps[r];
+      float cls;  memcpy(&cls, &m.cls, 4);
+      hStageMeta_.p[i] = make_float4(m.mu, m.sin, m.sout, cls);
+      hStageDst_.p[i] = s->slot * K_ + r;
+      i++;
+    }
+    s->stale_mask = 0;
+    s->dev_fill = s->k;
+    fillUpdates_.push_back(s->slot);  fillUpdates_.push_back(s->k);
+  }
+  refresh_.clear();
+  rows = i;
+  const size_t nFill = fillUpdates_.size() / 2;
+  // fill updates ride behind the row destinations in the same pinned buffer: [rows dst][slot...][fill...]
+  for (size_t j = 0; j < nFill; j++) {
+    hStageDst_.p[rows + j] = fillUpdates_[2 * j];
+    hStageDst_.p[rows + nFill + j] = fillUpdates_[2 * j + 1];
+  }
+  fillUpdates_.clear();
+  if (rows || nFill) {
+    dStageRows_.reserve(rows * wp_ + 4);  dStageMeta_.reserve(rows + 1);  dStageDst_.reserve(rows + 2 * nFill + 2);
+    if (rows) {
+      cudaCheck(cudaMemcpyAsync(dStageRows_.p, hStageRows_.p, rows * wp_ * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_), "stage rows");
+      cudaCheck(cudaMemcpyAsync(dStageMeta_.p, hStageMeta_.p, rows * sizeof(float4), cudaMemcpyHostToDevice, stream_), "stage meta");
+    }
+    cudaCheck(cudaMemcpyAsync(dStageDst_.p, hStageDst_.p, (rows + 2 * nFill) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_), "stage dst");
+    launch_scatter_rows(dStageRows_.p, dStageMeta_.p, dStageDst_.p, uint32_t(rows), wp_, dPool_.p, dMeta_.p, stream_);
+    launch_scatter_u32(dStageDst_.p + rows, dStageDst_.p + rows + nFill, uint32_t(nFill), dFill_.p, stream_);
+    counters[4] += (rows ? 1 : 0) + (nFill ? 1 : 0);
+    // the pinned staging buffers are rewritten by the next refresh: wait for the copies
+    cudaCheck(cudaStreamSynchronize(stream_), "pool refresh");
+  }
+  timers[3] += now() - t0;
+}
+
+void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
+                       const float *dCompat, const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                       const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
+                       uint32_t *outReplaced, uint32_t &done) {
+  double t0 = now();
+  // ---- prepare: classes, candidate pairs ----
+  hCls_.reserve(n);
+  hBMeta_.reserve(n);
+  pair0_.assign(n, -1);  pair1_.assign(n, -1);
+  hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
+  size_t P = 0;
+  auto lookup = [&] (uint32_t sid) -> Species* {
+    return (sid != INV && sid < nodes_.size()) ? nodes_[sid] : nullptr;
+  };
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t cls = classOf(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2]);
+    hCls_.p[i] = cls;
+    float fc;  memcpy(&fc, &cls, 4);
+    hBMeta_.p[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], fc);
+    Species *s0 = nullptr, *s1 = nullptr;
+    const uint32_t m = msid[i], f = fsid[i];
+    if (m == INV && f == INV) s0 = root_;
+    else if (f == INV || m == f) s0 = lookup(m);
+    else { s0 = lookup(m); s1 = lookup(f); }
+    if (s0 && s0->dev_fill) { pair0_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; }
+    if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; }
+  }
+  uploadLut();
+  timers[0] += now() - t0;
+  t0 = now();
+
+  // ---- device: speculative scores of every (birth, parent species) pair ----
+  if (P) {
+    dBirths_.reserve(size_t(n) * wp_);  dBMeta_.reserve(n);
+    dPairBirth_.reserve(P);  dPairSlot_.reserve(P);  dScore_.reserve(P);  dDist_.reserve(P * K_);
+    hScore_.reserve(P);  hDist_.reserve(P * K_);
+    if (dPayload) {
+      dCls_.reserve(n);
+      cudaCheck(cudaMemcpyAsync(dCls_.p, hCls_.p, size_t(n) * 4, cudaMemcpyHostToDevice, stream_), "classes");
+      launch_pack_births(dPayload, dCompat, dCls_.p, n, W_, wp_, dBirths_.p, dBMeta_.p, stream_);
+      counters[4]++;
+    } else {
+      if (wp_ == W_) {
+        cudaCheck(cudaMemcpyAsync(dBirths_.p, payload, size_t(n) * W_ * 4, cudaMemcpyHostToDevice, stream_), "births");
+      } else {
+        hBirths_.reserve(size_t(n) * wp_);
+        for (uint32_t i = 0; i < n; i++) {
+          memcpy(hBirths_.p + size_t(i) * wp_, payload + size_t(i) * W_, W_ * 4);
+          memset(hBirths_.p + size_t(i) * wp_ + W_, 0, (wp_ - W_) * 4);
+        }
+        cudaCheck(cudaMemcpyAsync(dBirths_.p, hBirths_.p, size_t(n) * wp_ * 4, cudaMemcpyHostToDevice, stream_), "births");
+      }
+      cudaCheck(cudaMemcpyAsync(dBMeta_.p, hBMeta_.p, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, stream_), "birth meta");
+    }
+    cudaCheck(cudaMemcpyAsync(dPairBirth_.p, hPairBirth_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
+    cudaCheck(cudaMemcpyAsync(dPairSlot_.p, hPairSlot_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
+    launch_score_pairs(poolView(), scoreCfg(), dBirths_.p, dBMeta_.p, uint32_t(P), dPairBirth_.p, dPairSlot_.p,
+                       dScore_.p, dDist_.p, stream_);
+    counters[4]++;
+    cudaCheck(cudaGetLastError(), "score_pairs launch");
+    cudaCheck(cudaMemcpyAsync(hScore_.p, dScore_.p, P * 4, cudaMemcpyDeviceToHost, stream_), "scores");
+    cudaCheck(cudaMemcpyAsync(hDist_.p, dDist_.p, P * K_ * 4, cudaMemcpyDeviceToHost, stream_), "distances");
+    cudaCheck(cudaStreamSynchronize(stream_), "score_pairs");
+    counters[7] += P;
+  }
+  timers[1] += now() - t0;
+  t0 = now();
+
+  // ---- host: ordered resolution ----
+  curPayload_ = payload;
+  for (uint32_t i = 0; i < n; i++) {
+    RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, hCls_.p[i],
+                compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
+    uint32_t sid = INV, replaced = INV;
+    int32_t slot = -1;
+    walkOne(payload + size_t(i) * W_, g, pair0_[i], pair1_[i], sid, slot, replaced);
+    if (outSid) outSid[i] = sid;
+    if (outSlot) outSlot[i] = slot;
+    if (outReplaced) outReplaced[i] = replaced;
+    done++;
+    counters[0]++;
+  }
+  timers[2] += now() - t0;
+}
+
+void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compat, bool onDevice,
+                         cudaStream_t userStream, const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                         const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
+                         uint32_t *outReplaced, uint32_t *nDone) {
+  uint32_t done = 0;
+  if (nDone) *nDone = 0;
+  if (!n) return;
+  cudaCheck(cudaSetDevice(p_.device), "cudaSetDevice");
+
+  // device-resident inputs: the walk still needs the payloads of births that enter an enveloppe
+  // or need a repair, so a host copy is fetched (it overlaps with the scoring kernel)
+  std::vector<uint32_t> hostPayload;
+  std::vector<float> hostCompat;
+  const uint32_t *dPayload = nullptr;
+  const float *dCompat = nullptr;
+  if (onDevice) {
+    dPayload = payload;  dCompat = compat;
+    cudaCheck(cudaEventRecord(evUser_, userStream), "event record");
+    cudaCheck(cudaStreamWaitEvent(stream_, evUser_, 0), "stream wait");
+    hostPayload.resize(size_t(n) * W_);  hostCompat.resize(size_t(n) * 3);
+    cudaCheck(cudaMemcpyAsync(hostPayload.data(), dPayload, hostPayload.size() * 4, cudaMemcpyDeviceToHost, stream_), "payload fetch");
+    cudaCheck(cudaMemcpyAsync(hostCompat.data(), dCompat, hostCompat.size() * 4, cudaMemcpyDeviceToHost, stream_), "compat fetch");
+    cudaCheck(cudaStreamSynchronize(stream_), "payload fetch");
+    payload = hostPayload.data();  compat = hostCompat.data();
+  }
+
+  try {
+    uint32_t i0 = 0;
+    if (!root_) {
+      // the very first genome founds species 0 (:270-273); Stats::insertions is not bumped there
+      root_ = makeNode({});
+      RepMeta g { gid[0], mgid[0], msid[0], fgid[0], fsid[0], 0, 0, classOf(compat[0], compat[1], compat[2]),
+                  compat[0], compat[1], compat[2] };
+      Eval none;
+      uint32_t replaced;
+      const int32_t slot = insertInto(payload, g, root_, none, false, replaced);
+      if (outSid) outSid[0] = root_->sid;
+      if (outSlot) outSlot[0] = slot;
+      if (outReplaced) outReplaced[0] = replaced;
+      i0 = 1;  done = 1;  counters[0]++;
+    }
+    constexpr uint32_t CHUNK = 1u << 20;
+    while (i0 < n) {
+      const uint32_t m = std::min(CHUNK, n - i0);
+      refreshPool();
+      runChunk(m, payload + size_t(i0) * W_, compat + size_t(i0) * 3,
+               dPayload ? dPayload + size_t(i0) * W_ : nullptr, dCompat ? dCompat + size_t(i0) * 3 : nullptr,
+               gid + i0, mgid + i0, msid + i0, fgid + i0, fsid + i0,
+               outSid ? outSid + i0 : nullptr, outSlot ? outSlot + i0 : nullptr,
+               outReplaced ? outReplaced + i0 : nullptr, done);
+      i0 += m;
+    }
+  } catch (...) {
+    if (nDone) *nDone = done;
+    throw;
+  }
+  if (nDone) *nDone = done;
+}
+
+// ---- JSON dump (layout of phylogenetictree.hpp:887-941) ---------------------
+namespace {
+void num (std::string &o, double v) {
+  char buf[40];
+  snprintf(buf, sizeof buf, "%.17g", v);
+  o += buf;
+}
+void pid (std::string &o, uint32_t g, uint32_t s) {
+  o += "{\"g\":" + std::to_string(g) + ",\"s\":" + std::to_string(s) + "}";
+}
+}
+
+std::string Engine::toJson (void) const {
+  std::string o = "{\"_step\":" + std::to_string(step_) + ",\"_envSize\":" + std::to_string(K_)
+                + ",\"_stillborns\":" + std::to_string(stillborns_) + ",\"alive\":[";
+  bool first = true;
+  for (uint32_t s: aliveSpecies_) { if (!first) o += ","; first = false; o += std::to_string(s); }
+  o += "],\"nextSID\":" + std::to_string(nextNodeID_) + ",\"tree\":";
+  struct Rec {
+    const Engine &e;
+    void node (std::string &o, const Species &n) const {
+      const uint32_t K = e.K_;
+      o += "{\"id\":" + std::to_string(n.sid);
+      o += ",\"data\":[" + std::to_string(n.first) + "," + std::to_string(n.last) + "," + std::to_string(n.count)
+         + "," + std::to_string(n.alive) + "," + std::to_string(n.pending) + "]";
+      o += ",\"envlp\":[";
+      for (uint32_t r = 0; r < n.k; r++) {
+        const RepMeta &m = n.reps[r];
+        if (r) o += ",";
+        o += "[{\"c\":[";  num(o, m.mu);  o += ",";  num(o, m.sin);  o += ",";  num(o, m.sout);
+        o += "],\"g\":{\"f\":";  pid(o, m.fgid, m.fsid);
+        o += ",\"m\":";  pid(o, m.mgid, m.msid);
+        o += ",\"s\":";  pid(o, m.gid, INV);
+        o += "},\"w\":[";
+        const uint32_t *w = e.repPayload(&n, r);
+        for (uint32_t j = 0; j < e.W_; j++) { if (j) o += ","; o += std::to_string(w[j]); }
+        o += "]}," + std::to_string(m.udata) + "]";
+      }
+      o += "],\"contribs\":[";
+      for (size_t i = 0; i < n.contribs.size(); i++) {
+        const Contributor &c = n.contribs[i];
+        if (i) o += ",";
+        o += "[" + std::to_string(c.sid) + "," + std::to_string(c.count) + "," + (c.elligible ? "true" : "false") + "]";
+      }
+      o += "],\"dists\":";
+      if (n.k < 2) o += "null";
+      else {
+        o += "[";
+        bool first = true;
+        for (uint32_t i = 0; i < n.k; i++)
+          for (uint32_t j = i + 1; j < n.k; j++) {
+            if (!first) o += ",";
+            first = false;
+            o += "[" + std::to_string(i) + "," + std::to_string(j) + ",";  num(o, n.dist[i * K + j]);  o += "]";
+          }
+        o += "]";
+      }
+      o += ",\"children\":";
+      if (n.children.empty()) o += "null";
+      else {
+        o += "[";
+        for (size_t i = 0; i < n.children.size(); i++) { if (i) o += ","; node(o, *n.children[i]); }
+        o += "]";
+      }
+      o += "}";
+    }
+  } rec { *this };
+  if (root_) rec.node(o, *root_); else o += "null";
+  o += "}";
+  return o;
+}
+
+} // namespace apt

@@ -1,0 +1,230 @@
+// Tree engine of libapt_b200.so: PhylogeneticTree<GENOME,UDATA> for device-encoded genomes.
+//
+// Split of labour ("Ordered resolution"):
+//   device  K1 scores every birth of a batch against the enveloppes of its parents' species, and
+//           K2 against those species' sub-species, from the pool as it stood when the batch was
+//           submitted (speculation);
+//   host    one ordered walk commits births in arrival order.  A speculative (birth, species)
+//           result is used as is when that enveloppe has not changed since the pool was refreshed,
+//           patched (only the changed representatives are re-measured) when it has, and computed
+//           from scratch for species founded inside the batch -- so every birth sees exactly the
+//           state the reference's sequential addGenome would have shown it.
+// The hierarchy bookkeeping (contributors, parents, trimming) follows the reference line by line;
+// citations are relative to /root/reference/src/core/tree.
+#ifndef APT_B200_ENGINE_H
+#define APT_B200_ENGINE_H
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "apt_b200.h"
+#include "kernels.cuh"
+
+namespace apt {
+
+struct ApiError : std::runtime_error {
+  int status;
+  ApiError (int status, const std::string &what) : std::runtime_error(what), status(status) {}
+};
+
+void cudaCheck (cudaError_t e, const char *what);
+
+/// Grow-only device buffer
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf (void) { if (p) cudaFree(p); }
+  void reserve (size_t n, bool keep = false, cudaStream_t st = nullptr) {
+    if (n <= cap) return;
+    size_t ncap = cap ? cap : 1024;
+    while (ncap < n) ncap *= 2;
+    T *q = nullptr;
+    cudaCheck(cudaMalloc(&q, ncap * sizeof(T)), "cudaMalloc");
+    if (p) {
+      if (keep && cap) {
+        cudaCheck(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st), "pool growth copy");
+        cudaCheck(cudaStreamSynchronize(st), "pool growth sync");
+      }
+      cudaFree(p);
+    }
+    p = q;  cap = ncap;
+  }
+};
+
+/// Grow-only pinned host buffer
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  ~PinBuf (void) { if (p) cudaFreeHost(p); }
+  void reserve (size_t n) {
+    if (n <= cap) return;
+    size_t ncap = cap ? cap : 1024;
+    while (ncap < n) ncap *= 2;
+    T *q = nullptr;
+    cudaCheck(cudaMallocHost(&q, ncap * sizeof(T)), "cudaMallocHost");
+    if (p) cudaFreeHost(p);
+    p = q;  cap = ncap;
+  }
+};
+
+// speciescontributors.h:16-86 / :89-100
+struct Contributor { uint32_t sid, count; bool elligible; };
+struct Contribution { uint32_t species, count; };
+using Contributions = std::vector<Contribution>;
+
+/// Everything the tree keeps about a representative besides its payload (node.hpp:25-85)
+struct RepMeta {
+  uint32_t gid, mgid, msid, fgid, fsid;   // genealogy of the genome in this slot
+  uint32_t timestamp;                     // insertion step, node.hpp:26
+  uint32_t udata;                         // gid the slot's user-data object was last built from (:708-710)
+  uint32_t cls;                           // compatibility class (index of its (mu, s_in, s_out) triple)
+  float mu, sin, sout;
+};
+
+// node.hpp:16-243 + speciesdata.hpp:15-31
+struct Species {
+  uint32_t sid = 0, slot = 0;
+  Species *parent = nullptr;
+  std::vector<Species*> children;
+  uint32_t first = 0, last = 0, count = 0, alive = 0, pending = 0;
+  std::vector<Contributor> contribs;
+  uint32_t k = 0;                         // rset.size()
+  std::vector<RepMeta> reps;              // K entries, k used
+  std::vector<float> dist;                // K x K, symmetric, valid for i != j < k (DistanceMap)
+  // relation between this host state and the copy in the device pool
+  uint32_t dev_fill = 0;                  // representatives the device copy holds
+  uint32_t stale_mask = 0;                // slots whose device copy is out of date
+  bool queued = false;                    // already in the refresh list
+  bool trimmed = false;                   // removed by stillborn trimming
+  uint32_t cand_epoch = 0, cand_rank = 0; // position in the current group's candidate list (K2)
+  bool extinct (void) const { return alive == 0 && pending == 0; }   // node.hpp:157-159
+};
+
+struct Eval {
+  float score;
+  bool exact;                             // computed with reference-identical arithmetic
+  float d[KMAX];
+};
+
+class Engine {
+public:
+  explicit Engine (const apt_params &p);
+  ~Engine (void);
+
+  void addGenomes (uint32_t n, const uint32_t *payload, const float *compat, bool onDevice, cudaStream_t userStream,
+                   const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                   const uint32_t *fgid, const uint32_t *fsid,
+                   uint32_t *outSid, int32_t *outSlot, uint32_t *outReplaced, uint32_t *nDone);
+  void delGenome (uint32_t sid);
+  void candidacy (uint32_t msid, uint32_t fsid, int dir);
+  void setStep (uint32_t s) { step_ = s; }
+  void doStep (uint32_t s, const uint32_t *sids, uint32_t n);
+
+  void stats (uint32_t out[8]) const;
+  void resetStats (void) { insertions_ = deletions_ = comparisons_ = branching_ = 0; }
+  std::vector<apt_event>& events (void) { return events_; }
+  std::string toJson (void) const;
+  Species* nodeAt (uint32_t sid) const;
+  Species* root (void) const { return root_; }
+  const std::set<uint32_t>& aliveSpecies (void) const { return aliveSpecies_; }
+  const apt_params& params (void) const { return p_; }
+  uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double timers[4] = {0, 0, 0, 0};
+
+private:
+  apt_params p_;
+  uint32_t K_, W_, wp_;
+  bool lutMode_;
+  uint32_t lutStride_;
+
+  // ---- tree state (phylogenetictree.hpp:370-389) ----
+  uint32_t nextNodeID_ = 0, stillborns_ = 0, step_ = 0;
+  Species *root_ = nullptr;
+  std::vector<Species*> nodes_;           // indexed by SID; null = never existed or trimmed
+  uint32_t width_ = 0;
+  std::vector<Species*> graveyard_;
+  std::set<uint32_t> aliveSpecies_;
+  uint32_t insertions_ = 0, deletions_ = 0, comparisons_ = 0, branching_ = 0;
+  std::vector<apt_event> events_;
+
+  // ---- host mirror of the pool ----
+  std::vector<uint32_t> hPayload_;        // [slot][K][wp]
+  std::vector<uint32_t> freeSlots_;
+  uint32_t nSlots_ = 0;
+  std::vector<Species*> refresh_;         // species with stale device rows
+  std::vector<uint32_t> fillUpdates_;     // (slot, fill) pairs for the device `fill` array
+
+  // ---- compatibility classes ----
+  struct Triple { float mu, sin, sout; bool operator< (const Triple &o) const {
+    return mu != o.mu ? mu < o.mu : sin != o.sin ? sin < o.sin : sout < o.sout; } };
+  std::map<Triple, uint32_t> classIds_;
+  std::vector<Triple> classes_;
+  std::vector<double> hLut_;              // [class][lutStride_], host libm values
+  uint32_t lutUploaded_ = 0;              // classes already in the device table
+  Triple lastTriple_ { 0, 0, 0 };  uint32_t lastClass_ = 0xFFFFFFFFu;
+
+  // ---- device state ----
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t evUser_ = nullptr;
+  DevBuf<uint32_t> dPool_;  DevBuf<float4> dMeta_;  DevBuf<uint32_t> dFill_;  DevBuf<double> dLut_;
+  DevBuf<uint32_t> dBirths_, dRaw_;  DevBuf<float4> dBMeta_;  DevBuf<float> dRawCompat_;  DevBuf<uint32_t> dCls_;
+  DevBuf<uint32_t> dPairBirth_, dPairSlot_;  DevBuf<float> dScore_, dDist_;
+  DevBuf<uint32_t> dStageRows_, dStageDst_;  DevBuf<float4> dStageMeta_;
+  PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
+  PinBuf<float4> hBMeta_, hStageMeta_;
+  PinBuf<float> hScore_, hDist_;
+
+  // ---- per-chunk scratch ----
+  std::vector<int64_t> pair0_, pair1_;    // pair index of (birth, s0) / (birth, s1) or -1
+  const uint32_t *curPayload_ = nullptr;  // host payload of the chunk being walked (W_ words per row)
+
+  // hierarchy (line-by-line restatements, see engine.cpp)
+  bool elligibile (uint32_t lhs, uint32_t rhs) const;
+  uint32_t currentMain (Species *n) const;
+  uint32_t contributorsUpdate (Species *n, Contributions ctbs);
+  Species* updateParent (Species *n, uint32_t sid);
+  Species* nodeUpdate (Species *n, const Contributions &c);
+  void updateElligibilities (void);
+  Species* makeNode (const Contributions &c);
+  void updateContributions (Species *s, const Contributions &c);
+  void performStillbornTrimming (void);
+  void emit (uint32_t t, uint32_t a, uint32_t b, uint32_t c) {
+    if (!(p_.flags & APT_FLAG_NO_EVENTS)) events_.push_back({t, a, b, c});
+  }
+
+  // scoring on the host (exact) and resolution
+  uint32_t classOf (float mu, float sin, float sout);
+  double compatOf (uint32_t cls, float mu, float sin, float sout, double d) const;
+  double distanceExact (const uint32_t *a, const uint32_t *b) const;
+  const uint32_t* repPayload (const Species *s, uint32_t r) const { return &hPayload_[(size_t(s->slot) * K_ + r) * wp_]; }
+  float scoreFrom (const double *c, uint32_t k) const;
+  void evalExact (const uint32_t *w, const RepMeta &g, Species *s, Eval &e);
+  void evalSpeculated (const uint32_t *w, const RepMeta &g, Species *s, int64_t pair, Eval &e);
+  bool trusted (float score) const;
+  int32_t insertInto (const uint32_t *w, const RepMeta &g, Species *s, const Eval &e, bool haveCache, uint32_t &replaced);
+  void walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uint32_t &sid, int32_t &slot, uint32_t &replaced);
+  void markStale (Species *s, uint32_t r);
+
+  // device plumbing
+  uint32_t allocSlot (void);
+  void refreshPool (void);
+  void uploadLut (void);
+  PoolView poolView (void) const;
+  ScoreCfg scoreCfg (void) const;
+  void runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
+                 const float *dCompat, const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                 const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
+                 uint32_t *outReplaced, uint32_t &done);
+};
+
+} // namespace apt
+
+#endif

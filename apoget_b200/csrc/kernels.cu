@@ -1,0 +1,333 @@
+// CUDA kernels of the species-assignment hot path (sm_100a).
+//
+// What they compute follows the reference's arithmetic exactly (file:line relative to
+// /root/reference/src/core):
+//   score        tree/phylogenetictree.hpp:456-478 (continuous) and :430-452 (semi-continuous)
+//   compat       crossover.h:76-92
+//   criterion    tree/enveloppecriteria.cpp:40-84 (maxAverage), :87-133 (maxMinDist)
+// How they compute it is ours: SoA enveloppe pool with uint4-aligned rows, lanes striding the
+// contiguous enveloppe block (coalesced 16-byte loads), __popc on the integer pipe with
+// shuffle reductions, and the order-sensitive float accumulation (`float avg += double c`,
+// :465-472) kept strictly sequential -- shuffles / shared memory only GATHER the k values.
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace apt {
+
+namespace {
+
+__device__ __forceinline__ uint32_t popc4 (uint4 a, uint4 b) {
+  return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+}
+
+__device__ __forceinline__ double sqdiff4 (uint4 a, uint4 b) {
+  double t0 = double(__uint_as_float(a.x)) - double(__uint_as_float(b.x));
+  double t1 = double(__uint_as_float(a.y)) - double(__uint_as_float(b.y));
+  double t2 = double(__uint_as_float(a.z)) - double(__uint_as_float(b.z));
+  double t3 = double(__uint_as_float(a.w)) - double(__uint_as_float(b.w));
+  return t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+}
+
+// crossover.h:89-92; same operation order as the host (no a*b+c pattern, so nothing to contract)
+__device__ __forceinline__ double compat_generic (float4 m, double d) {
+  const double mu = double(m.x);
+  const double s = d < mu ? double(m.y) : double(m.z);
+  const double t = d - mu;
+  return exp(-(t * t) / (2. * s * s));
+}
+
+template <bool LUT>
+__device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, float4 bm, float4 rm, double d) {
+  if (LUT) {
+    const uint32_t di = uint32_t(d);
+    const double a = __ldg(cfg.lut + size_t(__float_as_uint(bm.w)) * cfg.lut_stride + di);
+    const double b = __ldg(cfg.lut + size_t(__float_as_uint(rm.w)) * cfg.lut_stride + di);
+    return b < a ? b : a;                       // std::min(a, b), :468
+  } else {
+    const double a = compat_generic(bm, d), b = compat_generic(rm, d);
+    return b < a ? b : a;
+  }
+}
+
+/// Sequential tail of the score (phylogenetictree.hpp:465-477 / :439-451) over the k gathered
+/// compatibilities, evaluated redundantly by every lane (broadcast shared-memory reads).
+__device__ __forceinline__ float score_tail (const ScoreCfg &cfg, const double *c, uint32_t k) {
+  if (cfg.full_continuous) {
+    float avg = 0.f;
+    for (uint32_t r = 0; r < k; r++) avg = float(__dadd_rn(double(avg), c[r]));
+    return float(__dsub_rn(double(__fdiv_rn(avg, float(k))), cfg.avg_thr));
+  }
+  uint32_t matable = 0;
+  for (uint32_t r = 0; r < k; r++) matable += (c[r] >= cfg.compat_thr);
+  return float(__dsub_rn(double(matable), __dmul_rn(cfg.sim_thr, double(k))));
+}
+
+/// One (birth, species) score by one warp.  LPR lanes share a representative (each takes every
+/// LPR-th uint4 of the row), 32/LPR representatives are processed per pass.
+template <int LPR, int KIND, bool LUT>
+__device__ __forceinline__ float warp_score (const PoolView &pool, const ScoreCfg &cfg,
+                                             const uint4 *__restrict__ bq, float4 bm, uint32_t slot,
+                                             double *c_smem, float *out_d, int lane) {
+  constexpr int RPI = 32 / LPR;
+  const uint32_t k = min(__ldg(pool.fill + slot), pool.K);
+  const uint32_t wp4 = pool.wp >> 2;
+  const uint4 *rq = reinterpret_cast<const uint4*>(pool.payload) + size_t(slot) * pool.K * wp4;
+  const float4 *rmeta = pool.cmeta + size_t(slot) * pool.K;
+  const int g = lane / LPR, l = lane % LPR;
+
+  for (uint32_t r0 = 0; r0 < k; r0 += RPI) {
+    const uint32_t r = r0 + g;
+    double d;
+    if (KIND == 0) {
+      uint32_t acc = 0;
+      if (r < k)
+        for (uint32_t v = l; v < wp4; v += LPR) acc += popc4(__ldg(rq + size_t(r) * wp4 + v), bq[v]);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      d = double(acc);
+    } else {
+      double acc = 0.;
+      if (r < k)
+        for (uint32_t v = l; v < wp4; v += LPR) acc += sqdiff4(__ldg(rq + size_t(r) * wp4 + v), bq[v]);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      d = sqrt(acc);
+    }
+    if (l == 0 && r < k) {
+      c_smem[r] = pair_compat<LUT>(cfg, bm, __ldg(rmeta + r), d);
+      if (out_d) out_d[r] = float(d);           // DCCache::push_back(float d, ..), treetypes.h:218-220
+    }
+  }
+  __syncwarp();
+  const float score = score_tail(cfg, c_smem, k);
+  __syncwarp();
+  return score;
+}
+
+constexpr int WARPS_PER_CTA = 8;
+
+template <int LPR, int KIND, bool LUT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+score_pairs_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__restrict__ b_payload,
+                    const float4 *__restrict__ b_cmeta, uint32_t n_pairs,
+                    const uint32_t *__restrict__ pair_birth, const uint32_t *__restrict__ pair_slot,
+                    float *__restrict__ out_score, float *__restrict__ out_dist) {
+  __shared__ double c_smem[WARPS_PER_CTA][KMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t p = blockIdx.x * WARPS_PER_CTA + warp;
+  if (p >= n_pairs) return;
+  const uint32_t b = __ldg(pair_birth + p), slot = __ldg(pair_slot + p);
+  const uint4 *bq = reinterpret_cast<const uint4*>(b_payload) + size_t(b) * (pool.wp >> 2);
+  const float s = warp_score<LPR, KIND, LUT>(pool, cfg, bq, __ldg(b_cmeta + b), slot, c_smem[warp],
+                                             out_dist + size_t(p) * pool.K, lane);
+  if (lane == 0) out_score[p] = s;
+}
+
+/// Dense sweep, first version: one warp per birth walking every slot of the pool.
+template <int LPR, int KIND, bool LUT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+classify_dense_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__restrict__ b_payload,
+                       const float4 *__restrict__ b_cmeta, uint32_t n_births,
+                       uint32_t *__restrict__ out_best, float *__restrict__ out_best_score,
+                       uint32_t *__restrict__ out_first, uint32_t *__restrict__ out_count) {
+  __shared__ double c_smem[WARPS_PER_CTA][KMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b = blockIdx.x * WARPS_PER_CTA + warp;
+  if (b >= n_births) return;
+  const uint4 *bq = reinterpret_cast<const uint4*>(b_payload) + size_t(b) * (pool.wp >> 2);
+  const float4 bm = __ldg(b_cmeta + b);
+  uint32_t best = 0xFFFFFFFFu, first = 0xFFFFFFFFu, count = 0;
+  float bestScore = -CUDART_INF_F;
+  for (uint32_t s = 0; s < pool.n_slots; s++) {
+    if (__ldg(pool.fill + s) == 0) continue;
+    const float sc = warp_score<LPR, KIND, LUT>(pool, cfg, bq, bm, s, c_smem[warp], nullptr, lane);
+    if (best == 0xFFFFFFFFu || bestScore < sc) { best = s; bestScore = sc; }
+    if (sc > 0.f) { count++; if (first == 0xFFFFFFFFu) first = s; }
+  }
+  if (lane == 0) {
+    out_best[b] = best;  out_best_score[b] = bestScore;  out_first[b] = first;  out_count[b] = count;
+  }
+}
+
+template <int KIND>
+__global__ void pairwise_kernel (uint32_t wp4, const uint4 *__restrict__ payload, uint32_t n_pairs,
+                                 const uint32_t *__restrict__ ia, const uint32_t *__restrict__ ib,
+                                 float *__restrict__ out) {
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  const uint4 *a = payload + size_t(__ldg(ia + p)) * wp4, *b = payload + size_t(__ldg(ib + p)) * wp4;
+  if (KIND == 0) {
+    uint32_t acc = 0;
+    for (uint32_t v = lane; v < wp4; v += 32) acc += popc4(__ldg(a + v), __ldg(b + v));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[p] = float(acc);
+  } else {
+    double acc = 0.;
+    for (uint32_t v = lane; v < wp4; v += 32) acc += sqdiff4(__ldg(a + v), __ldg(b + v));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[p] = float(sqrt(acc));
+  }
+}
+
+// enveloppecriteria.cpp:40-84 (crit 0) and :87-133 (crit 1); one thread per candidate genome
+__global__ void env_contribution_kernel (int crit, uint32_t K, uint32_t n, const float *__restrict__ edist,
+                                         const float *__restrict__ gdist, uint8_t *__restrict__ out_better,
+                                         uint32_t *__restrict__ out_than, float *__restrict__ out_value) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *e = edist + size_t(i) * K * K, *g = gdist + size_t(i) * K;
+  float value = -CUDART_INF_F;      // -DBL_MAX stored into a float, :46 / :93
+  uint32_t than = 0xFFFFFFFFu;
+  for (uint32_t a = 0; a < K; a++) {
+    double c;
+    if (crit == 1) {
+      float minBase = 3.402823466e+38f, minNew = 3.402823466e+38f;
+      for (uint32_t j = 0; j < K; j++) {
+        if (j == a) continue;
+        minBase = fminf(minBase, e[a * K + j]);
+        minNew = fminf(minNew, g[j]);
+      }
+      c = double(__fadd_rn(-minBase, minNew));                       // :117
+    } else {
+      c = 0.;
+      for (uint32_t j = 0; j < K; j++) {
+        if (j == a) continue;
+        c = __dadd_rn(c, double(__fadd_rn(-e[a * K + j], g[j])));   // :62
+      }
+    }
+    if (double(value) < c) { value = float(c); than = a; }           // :77-80 / :125-128
+  }
+  out_better[i] = value > 0.f;                                        // :83 / :131
+  out_than[i] = than;
+  out_value[i] = value;
+}
+
+__global__ void pack_births_kernel (const uint32_t *__restrict__ src, const float *__restrict__ compat,
+                                    const uint32_t *__restrict__ cls, uint32_t n, uint32_t words, uint32_t wp,
+                                    uint32_t *__restrict__ dst, float4 *__restrict__ meta) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = size_t(n) * wp;
+  if (t < total) {
+    const uint32_t row = uint32_t(t / wp), w = uint32_t(t % wp);
+    dst[t] = w < words ? src[size_t(row) * words + w] : 0u;
+  }
+  if (t < n)
+    meta[t] = make_float4(compat[3 * t], compat[3 * t + 1], compat[3 * t + 2],
+                          __uint_as_float(cls ? cls[t] : 0u));
+}
+
+__global__ void scatter_rows_kernel (const uint4 *__restrict__ sp, const float4 *__restrict__ sm,
+                                     const uint32_t *__restrict__ dst_row, uint32_t n_rows, uint32_t wp4,
+                                     uint4 *__restrict__ pp, float4 *__restrict__ pm) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = size_t(n_rows) * wp4;
+  if (t < total) {
+    const uint32_t row = uint32_t(t / wp4), v = uint32_t(t % wp4);
+    pp[size_t(dst_row[row]) * wp4 + v] = sp[t];
+  }
+  if (t < n_rows) pm[dst_row[t]] = sm[t];
+}
+
+__global__ void scatter_u32_kernel (const uint32_t *__restrict__ idx, const uint32_t *__restrict__ val, uint32_t n,
+                                    uint32_t *__restrict__ dst) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = val[i];
+}
+
+int lanes_per_rep (uint32_t wp) {
+  uint32_t q = wp >> 2, l = 1;
+  while (l < q && l < 32) l <<= 1;
+  return int(l);
+}
+
+template <template <int, int, bool> class Launcher, typename... Args>
+void dispatch (int lpr, int kind, bool lut, Args&&... args) {
+#define APT_CASE(L)                                                                   \
+  case L:                                                                             \
+    if (kind == 0) { if (lut) Launcher<L, 0, true>::run(args...); else Launcher<L, 0, false>::run(args...); } \
+    else Launcher<L, 1, false>::run(args...);                                        \
+    break;
+  switch (lpr) { APT_CASE(1) APT_CASE(2) APT_CASE(4) APT_CASE(8) APT_CASE(16) APT_CASE(32) }
+#undef APT_CASE
+}
+
+template <int LPR, int KIND, bool LUT>
+struct ScorePairsLauncher {
+  static void run (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *bp, const float4 *bm, uint32_t n,
+                   const uint32_t *pb, const uint32_t *ps, float *os, float *od, cudaStream_t st) {
+    const uint32_t grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    score_pairs_kernel<LPR, KIND, LUT><<<grid, WARPS_PER_CTA * 32, 0, st>>>(pool, cfg, bp, bm, n, pb, ps, os, od);
+  }
+};
+
+template <int LPR, int KIND, bool LUT>
+struct DenseLauncher {
+  static void run (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *bp, const float4 *bm, uint32_t n,
+                   uint32_t *ob, float *obs, uint32_t *of, uint32_t *oc, cudaStream_t st) {
+    const uint32_t grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    classify_dense_kernel<LPR, KIND, LUT><<<grid, WARPS_PER_CTA * 32, 0, st>>>(pool, cfg, bp, bm, n, ob, obs, of, oc);
+  }
+};
+
+} // namespace
+
+void launch_score_pairs (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *b_payload,
+                         const float4 *b_cmeta, uint32_t n_pairs, const uint32_t *pair_birth,
+                         const uint32_t *pair_slot, float *out_score, float *out_dist, cudaStream_t stream) {
+  if (!n_pairs) return;
+  dispatch<ScorePairsLauncher>(lanes_per_rep(pool.wp), cfg.kind, cfg.use_lut != 0, pool, cfg, b_payload, b_cmeta,
+                               n_pairs, pair_birth, pair_slot, out_score, out_dist, stream);
+}
+
+void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *b_payload,
+                            const float4 *b_cmeta, uint32_t n_births, uint32_t *out_best_species,
+                            float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
+                            cudaStream_t stream) {
+  if (!n_births) return;
+  dispatch<DenseLauncher>(lanes_per_rep(pool.wp), cfg.kind, cfg.use_lut != 0, pool, cfg, b_payload, b_cmeta,
+                          n_births, out_best_species, out_best_score, out_first_accept, out_n_accept, stream);
+}
+
+void launch_pack_births (const uint32_t *src_payload, const float *src_compat, const uint32_t *cls, uint32_t n,
+                         uint32_t words, uint32_t wp, uint32_t *dst_payload, float4 *dst_cmeta,
+                         cudaStream_t stream) {
+  if (!n) return;
+  const size_t total = size_t(n) * wp;
+  pack_births_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src_payload, src_compat, cls, n, words, wp,
+                                                                       dst_payload, dst_cmeta);
+}
+
+void launch_scatter_rows (const uint32_t *stage_payload, const float4 *stage_cmeta, const uint32_t *dst_row,
+                          uint32_t n_rows, uint32_t wp, uint32_t *pool_payload, float4 *pool_cmeta,
+                          cudaStream_t stream) {
+  if (!n_rows) return;
+  const size_t total = size_t(n_rows) * (wp >> 2);
+  scatter_rows_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(stage_payload), stage_cmeta, dst_row, n_rows, wp >> 2,
+      reinterpret_cast<uint4*>(pool_payload), pool_cmeta);
+}
+
+void launch_scatter_u32 (const uint32_t *idx, const uint32_t *val, uint32_t n, uint32_t *dst, cudaStream_t stream) {
+  if (!n) return;
+  scatter_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(idx, val, n, dst);
+}
+
+void launch_env_contribution (int crit, uint32_t K, uint32_t n, const float *edist, const float *gdist,
+                              uint8_t *out_better, uint32_t *out_than, float *out_value, cudaStream_t stream) {
+  if (!n) return;
+  env_contribution_kernel<<<(n + 127) / 128, 128, 0, stream>>>(crit, K, n, edist, gdist, out_better, out_than, out_value);
+}
+
+void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n_pairs, const uint32_t *idx_a,
+                      const uint32_t *idx_b, float *out, cudaStream_t stream) {
+  if (!n_pairs) return;
+  const uint32_t grid = uint32_t((size_t(n_pairs) * 32 + 255) / 256);
+  if (kind == 0)
+    pairwise_kernel<0><<<grid, 256, 0, stream>>>(wp >> 2, reinterpret_cast<const uint4*>(payload), n_pairs, idx_a, idx_b, out);
+  else
+    pairwise_kernel<1><<<grid, 256, 0, stream>>>(wp >> 2, reinterpret_cast<const uint4*>(payload), n_pairs, idx_a, idx_b, out);
+}
+
+} // namespace apt

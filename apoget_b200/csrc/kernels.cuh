@@ -1,0 +1,73 @@
+// Device-side data views and kernel launchers of libapt_b200.so (sm_100a only).
+#ifndef APT_B200_KERNELS_CUH
+#define APT_B200_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace apt {
+
+constexpr uint32_t KMAX = 32;        // largest supported enveloppe size (rsetSize)
+
+/// Enveloppe pool in HBM.  Representative r of the species in slot s lives at
+/// payload[(s*K + r) * wp .. +wp) (wp = payload words padded to a multiple of 4 so every row is
+/// uint4-aligned; padding words are zero and do not change either distance).
+/// cmeta[s*K + r] = {mu, sigma_in, sigma_out, bits(class id)}.
+struct PoolView {
+  const uint32_t *payload;
+  const float4 *cmeta;
+  const uint32_t *fill;       // representatives present per slot (k <= K)
+  uint32_t K, wp, n_slots;
+};
+
+/// Scoring configuration (config::PTree thresholds + the compatibility table).
+/// With use_lut, lut[cls * lut_stride + d] holds compatibility(d) of class cls as computed by the
+/// HOST libm for every integer distance d in [0, 32*words] -- the device then reproduces the
+/// reference's doubles bit for bit.
+struct ScoreCfg {
+  int kind;                   // APT_BITS / APT_F32
+  int full_continuous;
+  int use_lut;
+  double compat_thr, sim_thr, avg_thr;
+  const double *lut;
+  uint32_t lut_stride;
+};
+
+/// K1: one warp per (birth, species) pair.
+void launch_score_pairs (const PoolView &pool, const ScoreCfg &cfg,
+                         const uint32_t *b_payload, const float4 *b_cmeta,
+                         uint32_t n_pairs, const uint32_t *pair_birth, const uint32_t *pair_slot,
+                         float *out_score, float *out_dist, cudaStream_t stream);
+
+/// Pads n rows of `words` u32 into rows of `wp` u32 and packs compat triples + class ids into
+/// float4 metadata (device-resident inputs of the *_dev entry points).
+void launch_pack_births (const uint32_t *src_payload, const float *src_compat, const uint32_t *cls,
+                         uint32_t n, uint32_t words, uint32_t wp,
+                         uint32_t *dst_payload, float4 *dst_cmeta, cudaStream_t stream);
+
+/// Scatters staged enveloppe rows into the pool: row i of the staging buffers goes to pool row
+/// dst_row[i] (= slot*K + r).
+void launch_scatter_rows (const uint32_t *stage_payload, const float4 *stage_cmeta, const uint32_t *dst_row,
+                          uint32_t n_rows, uint32_t wp, uint32_t *pool_payload, float4 *pool_cmeta,
+                          cudaStream_t stream);
+
+/// dst[idx[i]] = val[i]
+void launch_scatter_u32 (const uint32_t *idx, const uint32_t *val, uint32_t n, uint32_t *dst, cudaStream_t stream);
+
+/// a8: enveloppe criterion, one thread per candidate (crit 0 = maxAverage, 1 = maxMinDist).
+void launch_env_contribution (int crit, uint32_t K, uint32_t n, const float *edist, const float *gdist,
+                              uint8_t *out_better, uint32_t *out_than, float *out_value, cudaStream_t stream);
+
+/// Births x births distances, one warp per pair.
+void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n_pairs,
+                      const uint32_t *idx_a, const uint32_t *idx_b, float *out, cudaStream_t stream);
+
+/// Dense sweep (every birth x every species), fused score / threshold / argmax.
+void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg,
+                            const uint32_t *b_payload, const float4 *b_cmeta, uint32_t n_births,
+                            uint32_t *out_best_species, float *out_best_score,
+                            uint32_t *out_first_accept, uint32_t *out_n_accept, cudaStream_t stream);
+
+} // namespace apt
+
+#endif

@@ -1,0 +1,209 @@
+/* apt_b200.h -- C ABI of libapt_b200.so, the B200 (sm_100a) species-assignment engine.
+ *
+ * APOGeT (the reference) has no FFI layer: its "operator API" is the C++ template
+ * phylogeny::PhylogeneticTree<GENOME,UDATA> (src/core/tree/phylogenetictree.hpp:44-45) plus the
+ * genome operators distance()/compatibility()/genealogy() (:441-442, :467-468, :276).  This header
+ * is the boundary a reference-side binding would call for genomes that have a fixed-length device
+ * encoding; include/apt/phylogenetictree.hpp is that binding (same class name, members and
+ * semantics as the reference's template) and INTEGRATION.md shows how a host program switches.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * apt_status otherwise, with the message available from apt_last_error() (thread-local);
+ * no exception crosses the boundary.  All calls are synchronous at return unless named *_async.
+ * Pointers are HOST pointers unless the parameter name starts with d_ (device memory of the
+ * tree's CUDA device).  `stream` parameters are CUstream / cudaStream_t handles passed as void*.
+ * One host thread drives one tree (the reference is single-threaded and non re-entrant).
+ *
+ * Genome encoding: `words` 32-bit words of payload per genome and three floats
+ * (mu, sigma_in, sigma_out) = the BOC compatibility genes of src/core/crossover.h:43-49.
+ *   APT_BITS: payload is a bit-string, distance = Hamming distance (integer, exact);
+ *   APT_F32 : payload is `words` IEEE floats, distance = L2 norm of the difference.
+ * compatibility(d) = exp(-(d-mu)^2 / (2 sigma^2)), sigma = sigma_in if d < mu else sigma_out
+ * (crossover.h:76-92).
+ */
+#ifndef APT_B200_H
+#define APT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APT_INVALID 0xFFFFFFFFu      /* SID::INVALID / GID::INVALID, treetypes.h:24-26, 74-76 */
+
+enum apt_kind { APT_BITS = 0, APT_F32 = 1 };
+
+enum apt_status {
+  APT_OK = 0,
+  APT_ERR_ARGUMENT = 1,     /* bad parameter (also: unknown species id, as utils::Thrower at :169-174) */
+  APT_ERR_CUDA = 2,         /* CUDA runtime failure, or no sm_100 device */
+  APT_ERR_STATE = 3,        /* reference invariant violated (the reference asserts or crashes there) */
+  APT_ERR_NOMEM = 4
+};
+
+/* Event stream = the reference's Callbacks_t hooks (callbacks.hpp:16-45), in firing order. */
+enum apt_event_type {
+  APT_EV_STEPPED = 0,            /* a = step, b = number of alive species          (:261) */
+  APT_EV_NEW_SPECIES = 1,        /* a = parent sid or APT_INVALID, b = new sid       (:422-423) */
+  APT_EV_ENTERS_ENVELOPPE = 2,   /* a = sid, b = gid                                 (:674, :705) */
+  APT_EV_LEAVES_ENVELOPPE = 3,   /* a = sid, b = gid                                 (:704) */
+  APT_EV_MAJOR_CONTRIBUTOR = 4   /* a = sid, b = old parent sid, c = new parent sid  (:765) */
+};
+typedef struct apt_event { uint32_t type, a, b, c; } apt_event;
+
+/* config::PTree (src/core/ptreeconfig.h:17-69, defaults ptreeconfig.cpp:7-19) + device choice. */
+typedef struct apt_params {
+  uint32_t kind;               /* apt_kind */
+  uint32_t words;              /* payload words per genome (1..1024) */
+  uint32_t rset_size;          /* rsetSize, enveloppe size K (1..32), default 5 */
+  int32_t  full_continuous;    /* DEBUG_FULL_CONTINUOUS: 1 = avg-compat score (:456-478), 0 = vote count (:430-452) */
+  int32_t  env_crit;           /* DEBUG_ENV_CRIT: 0 maxAverage, 1 maxMinDist (default), 2 maxAvgMinStdDev, 3 maxWeightedDist2Avg */
+  double   compat_thr;         /* compatibilityThreshold    .1  */
+  double   sim_thr;            /* similarityThreshold       .5  */
+  double   avg_thr;            /* avgCompatibilityThreshold .25 */
+  uint32_t trim_period;        /* stillbornTrimmingPeriod   100 */
+  float    trim_thr;           /* stillbornTrimmingThreshold .25 */
+  float    trim_delay;         /* stillbornTrimmingDelay    4   */
+  uint32_t trim_min_delay;     /* stillbornTrimmingMinDelay 200 */
+  int32_t  device;             /* CUDA device ordinal */
+  uint32_t flags;              /* apt_flags */
+} apt_params;
+
+enum apt_flags {
+  APT_FLAG_NO_EVENTS = 1u,       /* do not record the event stream */
+  APT_FLAG_NO_CHILD_KERNEL = 2u, /* debug: sub-species candidates are scored by the host repair path only */
+  APT_FLAG_FORCE_GENERIC = 4u    /* debug: never use the compatibility look-up table */
+};
+
+/* Fills *p with the reference's compiled-in defaults (ptreeconfig.cpp:7-19). */
+void apt_params_default (apt_params *p);
+
+const char* apt_last_error (void);
+
+/* 1 when a CUDA device with compute capability 10.x is visible, else 0 (never fails). */
+int apt_device_available (void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tree engine: PhylogeneticTree<GENOME,UDATA> for device-encoded genomes.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct apt_tree apt_tree;
+
+/* PhylogeneticTree() (:88-95).  Allocates the device pool and streams on params->device. */
+int  apt_tree_create (const apt_params *params, apt_tree **out);
+void apt_tree_destroy (apt_tree *t);
+
+/* Batched addGenome (:268-302, :553-650, :657-738): the result is DEFINED as identical to calling
+ * the reference's addGenome once per birth, in order.  Per birth i: payload[i*words ..],
+ * compat[i*3 ..], gid[i] = genealogy().self.gid, mother/father gid and sid = genealogy().mother /
+ * .father (APT_INVALID where absent).  Outputs (each may be NULL): out_sid[i] = InsertionResult.sid;
+ * out_slot[i] = enveloppe slot the genome now occupies or -1 (InsertionResult.udata != nullptr iff
+ * >= 0); out_replaced_gid[i] = gid of the representative it replaced, APT_INVALID when it was
+ * appended or did not enter.  On error, births before the failing one stay committed
+ * (as when the reference throws out of addGenome) and *n_done, when given, says how many. */
+int apt_tree_add_genomes (apt_tree *t, uint32_t n, const uint32_t *payload, const float *compat,
+                          const uint32_t *gid, const uint32_t *mother_gid, const uint32_t *mother_sid,
+                          const uint32_t *father_gid, const uint32_t *father_sid,
+                          uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced_gid,
+                          uint32_t *n_done);
+
+/* Same, with payload and compat already resident in device memory (d_payload: n*words u32,
+ * d_compat: n*3 f32), ordered after `stream`. */
+int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload, const float *d_compat,
+                              void *stream,
+                              const uint32_t *gid, const uint32_t *mother_gid, const uint32_t *mother_sid,
+                              const uint32_t *father_gid, const uint32_t *father_sid,
+                              uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced_gid,
+                              uint32_t *n_done);
+
+int apt_tree_del_genome (apt_tree *t, uint32_t sid);                                  /* :305-317 */
+int apt_tree_register_candidate (apt_tree *t, uint32_t mother_sid, uint32_t father_sid, int dir); /* :320-329, :786-792; dir = +1 / -1 */
+int apt_tree_set_step (apt_tree *t, uint32_t step);                                   /* :219-221 */
+int apt_tree_step (apt_tree *t, uint32_t step, const uint32_t *alive_sids, uint32_t n); /* :245-262 (incl. stillborn trimming :816-860) */
+
+/* out[8] = Stats{insertions, deletions, comparisons, branching} (:343-355), nextNodeID (:195),
+ * width() (:163), step() (:190), _stillborns. */
+int apt_tree_stats (apt_tree *t, uint32_t out[8]);
+int apt_tree_reset_stats (apt_tree *t);                                               /* :358-360 */
+
+/* Recorded callbacks since the last drain.  apt_tree_events copies min(cap, count) events and,
+ * when `drain` is non-zero, removes them. */
+uint32_t apt_tree_event_count (apt_tree *t);
+uint32_t apt_tree_events (apt_tree *t, apt_event *out, uint32_t cap, int drain);
+
+/* Tree dump with the layout of toJson (:887-941); genomes are written as
+ * {"c":[mu,sigma_in,sigma_out],"g":{"f":{"g","s"},"m":{..},"s":{..}},"w":[payload words]}, user data
+ * as the gid the slot object was last built from (:708-710).  Returns the length; copies at most cap. */
+uint64_t apt_tree_to_json (apt_tree *t, char *out, uint64_t cap);
+
+/* Node accessors used by the C++ binding (include/apt/phylogenetictree.hpp). */
+typedef struct apt_node_info {
+  uint32_t sid, parent_sid;           /* parent_sid = APT_INVALID for parentless nodes */
+  uint32_t data[5];                   /* SpeciesData: first, last, count, currentlyAlive, pendingCandidates (speciesdata.hpp:15-31) */
+  uint32_t fill;                      /* rset.size() */
+  uint32_t n_children, n_contributors;
+} apt_node_info;
+int apt_tree_node_info (apt_tree *t, uint32_t sid, apt_node_info *out);               /* nodeAt(sid), :168-177 */
+int apt_tree_node_children (apt_tree *t, uint32_t sid, uint32_t *out_sids, uint32_t cap);
+int apt_tree_node_contributors (apt_tree *t, uint32_t sid, uint32_t *out_sid_count_elligible, uint32_t cap); /* triples */
+int apt_tree_node_rep_gids (apt_tree *t, uint32_t sid, uint32_t *out_gids, uint32_t cap);
+int apt_tree_node_distances (apt_tree *t, uint32_t sid, float *out_kxk);              /* K*K floats, row-major, NaN where absent */
+int apt_tree_root (apt_tree *t, uint32_t *out_sid);                                   /* APT_INVALID when empty */
+int apt_tree_alive_species (apt_tree *t, uint32_t *out_sids, uint32_t cap, uint32_t *n);
+
+/* Counters of the resolution pass since creation: out[0] births, [1] (birth,species) scores taken
+ * from the device, [2] scores repaired on the host (some representatives changed in-batch),
+ * [3] scores fully recomputed on the host, [4] kernel launches, [5] host-side distance evaluations,
+ * [6] guard-band rechecks, [7] device pairs submitted. */
+int apt_tree_counters (apt_tree *t, uint64_t out[8]);
+
+/* Time spent (seconds, cumulative) : out[0] host prepare, [1] device (H2D+kernels+D2H, as waited for
+ * by the host), [2] ordered resolution walk, [3] pool refresh. */
+int apt_tree_timers (apt_tree *t, double out[4]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stateless kernels (the pieces of the hot path, individually testable against the oracle).
+ * A pool holds `n_species` enveloppes of up to K representatives; all pointers below are DEVICE
+ * pointers when the function name ends in _dev, HOST pointers otherwise (the host variants stage
+ * through device memory and run the same kernels).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct apt_pool apt_pool;
+
+/* Device-resident enveloppe pool.  rep_payload: n_species*K*words u32 (slot-major, representative r
+ * of species s at (s*K+r)*words); rep_compat: n_species*K*3 f32; fill: n_species u32 (k <= K). */
+int  apt_pool_create (const apt_params *params, uint32_t n_species, const uint32_t *rep_payload,
+                      const float *rep_compat, const uint32_t *fill, apt_pool **out);
+void apt_pool_destroy (apt_pool *p);
+
+/* a1/a2 over explicit (birth, species) pairs: out_score[p] (f32) and out_dist[p*K + r] (f32, r < fill).
+ * Arithmetic of speciesMatchingScoreContinuous / Simicontinuous (:430-478). */
+int apt_score_pairs (apt_pool *p, uint32_t n_births, const uint32_t *payload, const float *compat,
+                     uint32_t n_pairs, const uint32_t *pair_birth, const uint32_t *pair_species,
+                     float *out_score, float *out_dist);
+
+/* Dense sweep: every birth against every species of the pool, scoring fused with the acceptance
+ * test; nothing but per-birth winners leaves the chip.  out_best_species / out_best_score: species
+ * with the strictly greatest score (lowest index on ties); out_first_accept: lowest species index
+ * with score > 0 or APT_INVALID; out_n_accept: number of species with score > 0. */
+int apt_classify_dense (apt_pool *p, uint32_t n_births, const uint32_t *payload, const float *compat,
+                        uint32_t *out_best_species, float *out_best_score,
+                        uint32_t *out_first_accept, uint32_t *out_n_accept);
+int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_payload, const float *d_compat,
+                            uint32_t *d_out_best_species, float *d_out_best_score,
+                            uint32_t *d_out_first_accept, uint32_t *d_out_n_accept, void *stream);
+
+/* a8, enveloppe criterion (enveloppecriteria.cpp:87-133, 275-289) for n candidates: edist
+ * n*K*K f32 (full symmetric matrices), gdist n*K f32 -> better (u8), than (u32), value (f32).
+ * Only crit 0 and 1 run on the device. */
+int apt_env_contribution (const apt_params *params, uint32_t n, const float *edist, const float *gdist,
+                          uint8_t *out_better, uint32_t *out_than, float *out_value);
+
+/* Births x births distances for in-batch entrants: out[p] = distance(payload[a[p]], payload[b[p]]). */
+int apt_pairwise (const apt_params *params, uint32_t n_genomes, const uint32_t *payload,
+                  uint32_t n_pairs, const uint32_t *idx_a, const uint32_t *idx_b, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* APT_B200_H */

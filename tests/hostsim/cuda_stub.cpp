@@ -1,0 +1,151 @@
+// TEST DOUBLE -- lets the HOST logic of the engine (hierarchy bookkeeping, ordered resolution,
+// pool refresh planning) run in the GPU-less build container.
+//
+// tests/hostsim/build.py links apoget_b200/csrc/engine.cpp + abi.cpp against this file INSTEAD of
+// kernels.cu / dense.cu and the CUDA runtime: "device" memory is host memory, streams are
+// synchronous, and each launch_* below is a plain-loop stand-in for the kernel of the same name.
+// Nothing here is part of libapt_b200.so, and nothing here is timed or shipped; GPU parity of the
+// real kernels is established by the -m gpu tests through the real library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "kernels.cuh"
+
+extern "C" {
+cudaError_t cudaGetDeviceCount (int *c) { *c = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice (int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties_v2 (cudaDeviceProp *p, int) { memset(p, 0, sizeof *p); p->major = 10; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags (cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventDestroy (cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord (cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaMalloc (void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMallocAsync (void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+cudaError_t cudaFree (void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeAsync (void *p, cudaStream_t) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost (void **p, size_t n) { return cudaMalloc(p, n); }
+cudaError_t cudaHostAlloc (void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost (void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy (void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync (void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync (void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize (void) { return cudaSuccess; }
+cudaError_t cudaGetLastError (void) { return cudaSuccess; }
+const char* cudaGetErrorString (cudaError_t) { return "stub"; }
+}
+
+namespace apt {
+
+namespace {
+double dist (int kind, uint32_t wp, const uint32_t *a, const uint32_t *b) {
+  if (kind == 1) {
+    // pairwise (tree-like) order on purpose: the real kernel does not accumulate sequentially either
+    double s0 = 0, s1 = 0;
+    for (uint32_t i = 0; i < wp; i += 2) {
+      float fa, fb;
+      memcpy(&fa, a + i, 4);  memcpy(&fb, b + i, 4);
+      s0 += (double(fa) - double(fb)) * (double(fa) - double(fb));
+      if (i + 1 < wp) {
+        memcpy(&fa, a + i + 1, 4);  memcpy(&fb, b + i + 1, 4);
+        s1 += (double(fa) - double(fb)) * (double(fa) - double(fb));
+      }
+    }
+    return std::sqrt(s0 + s1);
+  }
+  uint32_t s = 0;
+  for (uint32_t i = 0; i < wp; i++) s += __builtin_popcount(a[i] ^ b[i]);
+  return s;
+}
+
+double compat (const ScoreCfg &cfg, float4 m, double d) {
+  if (cfg.use_lut) {
+    uint32_t cls;  memcpy(&cls, &m.w, 4);
+    return cfg.lut[size_t(cls) * cfg.lut_stride + uint32_t(d)];
+  }
+  const double mu = m.x, s = d < mu ? m.y : m.z;
+  // perturbed by one ulp now and then: the real device exp() is not bit-identical to libm either
+  double c = std::exp(-((d - mu) * (d - mu)) / (2. * s * s));
+  return (uint64_t(d * 7919) & 3) == 0 ? std::nextafter(c, 2.) : c;
+}
+
+float score (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *b, float4 bm, uint32_t slot, float *outD) {
+  const uint32_t k = pool.fill[slot] < pool.K ? pool.fill[slot] : pool.K;
+  float avg = 0;  uint32_t matable = 0;
+  for (uint32_t r = 0; r < k; r++) {
+    const size_t row = size_t(slot) * pool.K + r;
+    const double d = dist(cfg.kind, pool.wp, b, pool.payload + row * pool.wp);
+    const double ca = compat(cfg, bm, d), cb = compat(cfg, pool.cmeta[row], d), c = cb < ca ? cb : ca;
+    avg += c;  matable += (c >= cfg.compat_thr);
+    if (outD) outD[r] = float(d);
+  }
+  return cfg.full_continuous ? float(avg / float(k) - cfg.avg_thr) : float(matable - cfg.sim_thr * k);
+}
+}
+
+void launch_score_pairs (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *bp, const float4 *bm,
+                         uint32_t n, const uint32_t *pb, const uint32_t *ps, float *os, float *od, cudaStream_t) {
+  for (uint32_t p = 0; p < n; p++)
+    os[p] = score(pool, cfg, bp + size_t(pb[p]) * pool.wp, bm[pb[p]], ps[p], od + size_t(p) * pool.K);
+}
+
+void launch_classify_children (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *bp, const float4 *bm,
+                               uint32_t nItems, const uint32_t *itemBirth, const uint32_t *itemOff,
+                               const uint32_t *candSlot, uint32_t *outFirst, float *outScore, float *outDist,
+                               uint32_t *outMask, uint32_t maskWords, float guard, cudaStream_t) {
+  for (uint32_t i = 0; i < nItems; i++) {
+    const uint32_t b = itemBirth[i], c0 = itemOff[2 * i], nc = itemOff[2 * i + 1];
+    uint32_t first = 0xFFFFFFFFu;
+    for (uint32_t w = 0; w < maskWords; w++) outMask[size_t(i) * maskWords + w] = 0;
+    float d[KMAX];
+    for (uint32_t c = 0; c < nc; c++) {
+      const float s = score(pool, cfg, bp + size_t(b) * pool.wp, bm[b], candSlot[c0 + c], d);
+      const bool sure = cfg.use_lut || std::fabs(s) > guard;
+      if (!sure) outMask[size_t(i) * maskWords + (2 * c + 1) / 32] |= 1u << ((2 * c + 1) % 32);
+      if (s > 0) outMask[size_t(i) * maskWords + (2 * c) / 32] |= 1u << ((2 * c) % 32);
+      if ((s > 0 || !sure) && first == 0xFFFFFFFFu) {
+        first = c;  outScore[i] = s;
+        memcpy(outDist + size_t(i) * pool.K, d, pool.K * sizeof(float));
+      }
+    }
+    outFirst[i] = first;
+  }
+}
+
+void launch_pack_births (const uint32_t *src, const float *compat, const uint32_t *cls, uint32_t n, uint32_t words,
+                         uint32_t wp, uint32_t *dst, float4 *meta, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) {
+    memset(dst + size_t(i) * wp, 0, wp * 4);
+    memcpy(dst + size_t(i) * wp, src + size_t(i) * words, words * 4);
+    float fc = 0;  if (cls) memcpy(&fc, cls + i, 4);
+    meta[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], fc);
+  }
+}
+
+void launch_scatter_rows (const uint32_t *sp, const float4 *sm, const uint32_t *dst, uint32_t n, uint32_t wp,
+                          uint32_t *pp, float4 *pm, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) {
+    memcpy(pp + size_t(dst[i]) * wp, sp + size_t(i) * wp, wp * 4);
+    pm[dst[i]] = sm[i];
+  }
+}
+
+void launch_scatter_u32 (const uint32_t *idx, const uint32_t *val, uint32_t n, uint32_t *dst, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) dst[idx[i]] = val[i];
+}
+
+void launch_env_contribution (int, uint32_t, uint32_t, const float*, const float*, uint8_t*, uint32_t*, float*, cudaStream_t) {}
+void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n, const uint32_t *a, const uint32_t *b,
+                      float *out, cudaStream_t) {
+  for (uint32_t p = 0; p < n; p++) out[p] = float(dist(kind, wp, payload + size_t(a[p]) * wp, payload + size_t(b[p]) * wp));
+}
+void launch_classify_dense (const PoolView&, const ScoreCfg&, const uint32_t*, const float4*, uint32_t, uint32_t*, float*,
+                            uint32_t*, uint32_t*, cudaStream_t) {}
+
+} // namespace apt

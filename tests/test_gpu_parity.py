@@ -1,0 +1,192 @@
+"""GPU parity tests (-m gpu): the CUDA path, through the C ABI, against the oracle.
+
+* tree level: every golden trace replayed through libapt_b200.so must reproduce the UNMODIFIED
+  reference (per-birth species ids, enveloppe entries, callback stream, Stats, JSON dump).
+  Bit-exact for bit-string genomes; float-vector genomes: identical structure and assignments,
+  distances within 1e-5 relative (north_star tolerance; measured error is ~1e-7, one float ulp).
+* kernel level: the stateless kernels against oracle/apt_oracle.cpp on seeded random inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from apoget_b200 import synth
+from conftest import golden_cases, golden_json, golden_trace_path, GOLDEN
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(golden_cases())
+F32_RTOL = 1e-5
+
+
+def _json_close(a, b, rtol):
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and a.keys() == b.keys()
+        for k in a:
+            _json_close(a[k], b[k], rtol)
+    elif isinstance(a, list):
+        assert isinstance(b, list) and len(a) == len(b)
+        for x, y in zip(a, b):
+            _json_close(x, y, rtol)
+    elif isinstance(a, float) or isinstance(b, float):
+        assert abs(a - b) <= rtol * max(abs(a), abs(b)), (a, b)
+    else:
+        assert a == b, (a, b)
+
+
+def _compare(name, flags=0):
+    from apoget_b200.tree import PhylogeneticTree
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    tree = PhylogeneticTree(t.kind, t.words, flags=flags, **cfg)
+    sids, slots = tree.replay(t)
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"]), "per-birth species ids"
+    assert np.array_equal(slots >= 0, ref["entered"] > 0), "enveloppe entries"
+    st = tree.stats()
+    for k, v in ref["stats"].items():
+        assert st[k] == v, f"Stats::{k}"
+    assert np.array_equal(tree.events(), ref["events"]), "callback stream"
+    if t.kind == synth.BITS:
+        assert tree.to_json() == golden_json(name), "tree dump"
+    else:
+        _json_close(tree.to_json(), golden_json(name), F32_RTOL)
+    c = tree.counters()
+    assert c["kernel_launches"] > 0 and c["device_scores"] > 0, "the CUDA path did not run"
+    return tree
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tree_matches_unmodified_reference(name):
+    _compare(name)
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c4_b4096_k10"])
+def test_tree_generic_compat_path(name):
+    """Device exp() instead of the libm-built table: decisions must still be identical."""
+    _compare(name, flags=4)
+
+
+def _random_pool(rng, kind, words, S, K, sigma):
+    if kind == synth.BITS:
+        base = rng.integers(0, 2**32, size=(S, 1, words), dtype=np.uint32)
+        flips = np.zeros((S, K, words), dtype=np.uint32)
+        for _ in range(6):
+            pos = rng.integers(0, words * 32, size=(S, K))
+            np.put_along_axis(flips, (pos >> 5)[..., None],
+                              np.take_along_axis(flips, (pos >> 5)[..., None], 2)
+                              ^ (np.uint32(1) << (pos & 31).astype(np.uint32))[..., None], 2)
+        reps = base ^ flips
+    else:
+        base = rng.standard_normal((S, 1, words)).astype(np.float32)
+        reps = (base + 0.05 * rng.standard_normal((S, K, words)).astype(np.float32)).view(np.uint32)
+    fill = rng.integers(1, K + 1, size=S).astype(np.uint32)
+    compat = np.zeros((S, K, 3), dtype=np.float32)
+    compat[..., 1] = sigma
+    compat[..., 2] = sigma * 1.25
+    compat[::3, :, 1] = sigma * 0.75          # a second compatibility class
+    return reps, compat, fill
+
+
+@pytest.mark.parametrize("kind,words,K,sigma,full", [
+    (synth.BITS, 8, 10, 8.0, True), (synth.BITS, 8, 5, 8.0, False), (synth.BITS, 128, 10, 60.0, True),
+    (synth.BITS, 3, 7, 4.0, True), (synth.BITS, 1, 1, 2.0, True), (synth.BITS, 40, 32, 20.0, True),
+    (synth.F32, 64, 10, 0.4, True), (synth.F32, 5, 4, 0.2, True)])
+def test_score_pairs_kernel(kind, words, K, sigma, full):
+    from apoget_b200.kernels import Pool
+    rng = np.random.default_rng(7 + words)
+    S, B = 37, 211
+    reps, rc, fill = _random_pool(rng, kind, words, S, K, sigma)
+    pool = Pool(kind, words, reps, rc, fill, K=K, full_continuous=full)
+    src = rng.integers(0, S, size=B)
+    if kind == synth.BITS:
+        births = reps[src, 0].copy()
+        births[np.arange(B), rng.integers(0, words, size=B)] ^= rng.integers(0, 2**32, size=B, dtype=np.uint32) \
+            & np.uint32(0x0101)
+    else:
+        births = (reps[src, 0].view(np.float32) + 0.05 * rng.standard_normal((B, words)).astype(np.float32)).view(np.uint32)
+    bc = rc[src, 0].copy()
+    pb = np.repeat(np.arange(B), 2).astype(np.uint32)
+    ps = np.stack([src, rng.integers(0, S, size=B)], 1).reshape(-1).astype(np.uint32)
+    score, dist = pool.score_pairs(births, bc, pb, ps)
+    for p in range(pb.size):
+        b, s = int(pb[p]), int(ps[p])
+        k = int(fill[s])
+        so, do = oracle.score(kind, births[b], bc[b], reps[s, :k], rc[s, :k], full_continuous=full)
+        if kind == synth.BITS:
+            assert np.array_equal(dist[p, :k], do), "Hamming distances must be exact"
+            assert score[p] == np.float32(so), "score must be bit-exact (libm-built compat table)"
+        else:
+            assert np.allclose(dist[p, :k], do, rtol=F32_RTOL, atol=0)
+            assert abs(score[p] - so) <= 1e-5
+
+
+def test_score_pairs_empty_and_bad_indices():
+    from apoget_b200.kernels import Pool
+    from apoget_b200._lib import AptError
+    rng = np.random.default_rng(1)
+    reps, rc, fill = _random_pool(rng, synth.BITS, 8, 4, 5, 8.0)
+    pool = Pool(synth.BITS, 8, reps, rc, fill, K=5)
+    s, d = pool.score_pairs(reps[:, 0], rc[:, 0], [], [])
+    assert s.size == 0 and d.shape == (0, 5)
+    with pytest.raises(AptError):
+        pool.score_pairs(reps[:, 0], rc[:, 0], [0], [99])
+
+
+@pytest.mark.parametrize("kind,words,K,sigma", [(synth.BITS, 8, 10, 8.0), (synth.BITS, 128, 10, 60.0),
+                                                (synth.BITS, 3, 4, 4.0), (synth.F32, 64, 10, 0.4)])
+def test_dense_sweep_kernel(kind, words, K, sigma):
+    from apoget_b200.kernels import Pool
+    rng = np.random.default_rng(11 + words)
+    S, B = 53, 97
+    reps, rc, fill = _random_pool(rng, kind, words, S, K, sigma)
+    fill[5] = 0                                    # a free slot must be skipped
+    pool = Pool(kind, words, reps, rc, fill, K=K)
+    src = rng.integers(0, S, size=B)
+    births = reps[src, 0].copy()
+    bc = rc[src, 0].copy()
+    best, best_score, first, count = pool.classify_dense(births, bc)
+    for b in range(B):
+        scores = np.full(S, -np.inf, dtype=np.float32)
+        for s in range(S):
+            if fill[s]:
+                scores[s] = oracle.score(kind, births[b], bc[b], reps[s, :fill[s]], rc[s, :fill[s]])[0]
+        if kind == synth.BITS:
+            assert best[b] == int(np.argmax(scores)) and best_score[b] == scores.max()
+            acc = np.nonzero(scores > 0)[0]
+            assert count[b] == acc.size
+            assert first[b] == (acc[0] if acc.size else 0xFFFFFFFF)
+        else:
+            assert abs(best_score[b] - scores.max()) <= 1e-5
+            sure = np.abs(scores) > 1e-5
+            assert abs(int(count[b]) - int((scores > 0).sum())) <= int((~sure).sum())
+
+
+@pytest.mark.parametrize("crit", [0, 1])
+def test_env_contribution_kernel(crit):
+    from apoget_b200.kernels import env_contribution
+    rng = np.random.default_rng(3)
+    K, n = 10, 300
+    e = rng.integers(1, 40, size=(n, K, K)).astype(np.float32)
+    e = np.triu(e, 1) + np.transpose(np.triu(e, 1), (0, 2, 1))
+    g = rng.integers(0, 40, size=(n, K)).astype(np.float32)
+    better, than, value = env_contribution(K, e, g, crit=crit)
+    for i in range(n):
+        assert (bool(better[i]), int(than[i]), float(value[i])) == oracle.env_contribution(crit, e[i], g[i])
+
+
+@pytest.mark.parametrize("kind,words", [(synth.BITS, 8), (synth.BITS, 128), (synth.BITS, 5), (synth.F32, 64)])
+def test_pairwise_kernel(kind, words):
+    from apoget_b200.kernels import pairwise
+    rng = np.random.default_rng(words)
+    n = 64
+    pl = rng.integers(0, 2**32, size=(n, words), dtype=np.uint32) if kind == synth.BITS else \
+        rng.standard_normal((n, words)).astype(np.float32).view(np.uint32)
+    a, b = rng.integers(0, n, size=500), rng.integers(0, n, size=500)
+    out = pairwise(kind, pl, a, b)
+    exp = np.float32([oracle.distance(kind, pl[i], pl[j]) for i, j in zip(a, b)])
+    if kind == synth.BITS:
+        assert np.array_equal(out, exp)
+    else:
+        assert np.allclose(out, exp, rtol=F32_RTOL, atol=0)

@@ -1,0 +1,114 @@
+"""CPU-side checks: the C-ABI library exports what include/apt_b200.h declares, and the engine's
+HOST logic (hierarchy bookkeeping + ordered resolution) reproduces the reference's results when
+driven through a stubbed CUDA runtime (tests/hostsim).  The real kernels are covered by -m gpu."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from apoget_b200 import _lib, build as apt_build, synth
+from conftest import golden_cases, golden_json, golden_trace_path, GOLDEN, ROOT
+
+CASES = sorted(golden_cases())
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = apt_build.build()
+    header = open(os.path.join(ROOT, "include", "apt_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(apt_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    L = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared but not exported"
+
+
+def test_product_fails_loudly_without_a_device():
+    L = _lib.load(apt_build.build())
+    if L.apt_device_available():
+        pytest.skip("a B200 is visible")
+    p = _lib.AptParams()
+    L.apt_params_default(ctypes.byref(p))
+    h = ctypes.c_void_p()
+    assert L.apt_tree_create(ctypes.byref(p), ctypes.byref(h)) == 2      # APT_ERR_CUDA, no fallback
+    assert L.apt_last_error()
+
+
+@pytest.fixture(scope="module")
+def hostsim(monkeypatch_module):
+    from hostsim import build as hb
+    monkeypatch_module.setattr(_lib, "_lib", _lib.load(hb.build()))
+    from apoget_b200 import tree
+    return tree
+
+
+@pytest.fixture(scope="module")
+def monkeypatch_module():
+    mp = pytest.MonkeyPatch()
+    yield mp
+    mp.undo()
+
+
+def _compare(tree_mod, name, flags=0):
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    tree = tree_mod.PhylogeneticTree(t.kind, t.words, flags=flags, **cfg)
+    sids, slots = tree.replay(t)
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"])
+    assert np.array_equal(slots >= 0, ref["entered"] > 0)
+    st = tree.stats()
+    for k, v in ref["stats"].items():
+        assert st[k] == v, k
+    assert np.array_equal(tree.events(), ref["events"])
+    assert tree.to_json() == golden_json(name)
+    return tree
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_resolution_logic_matches_reference(hostsim, name):
+    _compare(hostsim, name)
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "founders_orphans_classes"])
+def test_host_resolution_logic_generic_compat(hostsim, name):
+    """Device exp() path (stub perturbs it by an ulp): the guard band must hide it."""
+    _compare(hostsim, name, flags=4)
+
+
+def test_one_birth_per_call_equals_batches(hostsim):
+    name = "hybrids_b256_k5"
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sid_of = np.full(t.n_births, synth.NONE, dtype=np.uint32)
+    N = synth.NONE
+    for g in range(t.n_gens):
+        for b in t.births_of(g):
+            m, f = int(t.mother[b]), int(t.father[b])
+            s, _, _ = tree.add_genomes(t.payload[b], t.compat[b], [b + 1], [N if m == N else m + 1],
+                                       [N if m == N else sid_of[m]], [N if f == N else f + 1],
+                                       [N if f == N else sid_of[f]])
+            sid_of[b] = s[0]
+        for d in t.deaths_of(g):
+            tree.del_genome(int(sid_of[d]))
+        tree.step(g + 1, sid_of[t.alive_of(g)])
+    assert tree.to_json() == golden_json(name)
+
+
+def test_unknown_species_is_an_error_and_commits_the_prefix(hostsim):
+    t = synth.read_trace(golden_trace_path("k1_b64"))
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, K=1)
+    n = 5
+    gid = np.arange(1, n + 1, dtype=np.uint32)
+    inv = np.full(n, synth.NONE, dtype=np.uint32)
+    msid = inv.copy()
+    msid[3] = 77                                   # no such species: nodeAt throws (:169-174)
+    with pytest.raises(_lib.AptError) as e:
+        tree.add_genomes(t.payload[:n], t.compat[:n], gid, gid, msid, inv, inv)
+    assert e.value.status == 1 and "No node found for species 77" in str(e.value)
+    assert tree.stats()["insertions"] == 2         # root bootstrap is not counted (:270-273)
