@@ -147,6 +147,13 @@ int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload
 
 int apt_tree_del_genome (apt_tree *t, uint32_t sid) { return guarded([&] { need(t, "null tree"); t->engine.delGenome(sid); }); }
 
+int apt_tree_del_genomes (apt_tree *t, uint32_t n, const uint32_t *sids) {
+  return guarded([&] {
+    need(t && (n == 0 || sids), "null argument");
+    for (uint32_t i = 0; i < n; i++) t->engine.delGenome(sids[i]);
+  });
+}
+
 int apt_tree_register_candidate (apt_tree *t, uint32_t msid, uint32_t fsid, int dir) {
   return guarded([&] { need(t && (dir == 1 || dir == -1), "bad argument"); t->engine.candidacy(msid, fsid, dir); });
 }
@@ -239,11 +246,11 @@ int apt_tree_alive_species (apt_tree *t, uint32_t *out, uint32_t cap, uint32_t *
   });
 }
 
-int apt_tree_counters (apt_tree *t, uint64_t out[8]) {
+int apt_tree_counters (apt_tree *t, uint64_t out[16]) {
   return guarded([&] { need(t && out, "null argument"); memcpy(out, t->engine.counters, sizeof t->engine.counters); });
 }
 
-int apt_tree_timers (apt_tree *t, double out[4]) {
+int apt_tree_timers (apt_tree *t, double out[8]) {
   return guarded([&] { need(t && out, "null argument"); memcpy(out, t->engine.timers, sizeof t->engine.timers); });
 }
 

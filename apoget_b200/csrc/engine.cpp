@@ -50,12 +50,16 @@ Engine::Engine (const apt_params &p) : p_(p) {
                    std::to_string(prop.major) + std::to_string(prop.minor));
   cudaCheck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
   cudaCheck(cudaEventCreateWithFlags(&evUser_, cudaEventDisableTiming), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&evK0_), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&evK1_), "cudaEventCreate");
 }
 
 Engine::~Engine (void) {
   for (Species *s: nodes_) delete s;
   for (Species *s: graveyard_) delete s;
   if (evUser_) cudaEventDestroy(evUser_);
+  if (evK0_) cudaEventDestroy(evK0_);
+  if (evK1_) cudaEventDestroy(evK1_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -641,6 +645,7 @@ void Engine::refreshPool (void) {
   }
   refresh_.clear();
   rows = i;
+  counters[10] += rows;
   const size_t nFill = fillUpdates_.size() / 2;
   // fill updates ride behind the row destinations in the same pinned buffer: [rows dst][slot...][fill...]
   for (size_t j = 0; j < nFill; j++) {
@@ -675,6 +680,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   pair0_.assign(n, -1);  pair1_.assign(n, -1);
   hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
   size_t P = 0;
+  touchEpoch_++;
+  auto touch = [&] (Species *s) {
+    if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
+  };
   auto lookup = [&] (uint32_t sid) -> Species* {
     return (sid != INV && sid < nodes_.size()) ? nodes_[sid] : nullptr;
   };
@@ -688,8 +697,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (m == INV && f == INV) s0 = root_;
     else if (f == INV || m == f) s0 = lookup(m);
     else { s0 = lookup(m); s1 = lookup(f); }
-    if (s0 && s0->dev_fill) { pair0_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; }
-    if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; }
+    if (s0 && s0->dev_fill) { pair0_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
+    if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
   }
   uploadLut();
   timers[0] += now() - t0;
@@ -720,13 +729,18 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     }
     cudaCheck(cudaMemcpyAsync(dPairBirth_.p, hPairBirth_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
     cudaCheck(cudaMemcpyAsync(dPairSlot_.p, hPairSlot_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
+    cudaCheck(cudaEventRecord(evK0_, stream_), "event record");
     launch_score_pairs(poolView(), scoreCfg(), dBirths_.p, dBMeta_.p, uint32_t(P), dPairBirth_.p, dPairSlot_.p,
                        dScore_.p, dDist_.p, stream_);
-    counters[4]++;
+    cudaCheck(cudaEventRecord(evK1_, stream_), "event record");
+    counters[4]++;  counters[9]++;
     cudaCheck(cudaGetLastError(), "score_pairs launch");
     cudaCheck(cudaMemcpyAsync(hScore_.p, dScore_.p, P * 4, cudaMemcpyDeviceToHost, stream_), "scores");
     cudaCheck(cudaMemcpyAsync(hDist_.p, dDist_.p, P * K_ * 4, cudaMemcpyDeviceToHost, stream_), "distances");
     cudaCheck(cudaStreamSynchronize(stream_), "score_pairs");
+    float ms = 0.f;
+    cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed");
+    timers[4] += ms;
     counters[7] += P;
   }
   timers[1] += now() - t0;

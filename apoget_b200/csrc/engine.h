@@ -105,6 +105,7 @@ struct Species {
   bool queued = false;                    // already in the refresh list
   bool trimmed = false;                   // removed by stillborn trimming
   uint32_t cand_epoch = 0, cand_rank = 0; // position in the current group's candidate list (K2)
+  uint32_t touch_epoch = 0;               // last scoring launch that read this enveloppe
   bool extinct (void) const { return alive == 0 && pending == 0; }   // node.hpp:157-159
 };
 
@@ -136,8 +137,8 @@ public:
   Species* root (void) const { return root_; }
   const std::set<uint32_t>& aliveSpecies (void) const { return aliveSpecies_; }
   const apt_params& params (void) const { return p_; }
-  uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  double timers[4] = {0, 0, 0, 0};
+  uint64_t counters[16] = {};
+  double timers[8] = {};
 
 private:
   apt_params p_;
@@ -173,7 +174,8 @@ private:
 
   // ---- device state ----
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t evUser_ = nullptr;
+  cudaEvent_t evUser_ = nullptr, evK0_ = nullptr, evK1_ = nullptr;
+  uint32_t touchEpoch_ = 0;
   DevBuf<uint32_t> dPool_;  DevBuf<float4> dMeta_;  DevBuf<uint32_t> dFill_;  DevBuf<double> dLut_;
   DevBuf<uint32_t> dBirths_, dRaw_;  DevBuf<float4> dBMeta_;  DevBuf<float> dRawCompat_;  DevBuf<uint32_t> dCls_;
   DevBuf<uint32_t> dPairBirth_, dPairSlot_;  DevBuf<float> dScore_, dDist_;

@@ -95,20 +95,28 @@ def read_trace(path: str) -> Trace:
     return Trace(kind, words, gbo, gdo, gao, mother, father, compat, payload, deaths, alive)
 
 
-def _flip_bits(rng: np.random.Generator, payload: np.ndarray, flips: int) -> None:
-    """XOR ``flips`` uniformly chosen bit positions (with replacement) into every row."""
+def _flip_bits(rng: np.random.Generator, payload: np.ndarray, flips: float) -> None:
+    """XOR ``flips`` uniformly chosen bit positions (with replacement) into every row; a fractional
+    part is the probability of one more flip."""
     n, words = payload.shape
     rows = np.arange(n)
-    for _ in range(flips):
+    whole = int(flips)
+    for _ in range(whole):
         pos = rng.integers(0, words * 32, size=n)
         payload[rows, pos >> 5] ^= (np.uint32(1) << (pos & 31).astype(np.uint32))
+    frac = float(flips) - whole
+    if frac > 0:
+        pos = rng.integers(0, words * 32, size=n)
+        bit = np.where(rng.random(n) < frac, np.uint32(1) << (pos & 31).astype(np.uint32), np.uint32(0))
+        payload[rows, pos >> 5] ^= bit.astype(np.uint32)
 
 
 def generate(kind: int = BITS, words: int = 8, pop: int = 1000, gens: int = 100, seed: int = 42,
-             flips: int = 2, init_flips: int = 0, hybrid: float = 0.0, survive: float = 0.0,
+             flips: float = 2, init_flips: int = 0, hybrid: float = 0.0, survive: float = 0.0,
              mu: float = 0.0, sigma: float = 8.0, compat_classes: int = 1,
              noise: float = 0.05, noise_coords: int = 8, founders: int = 1,
-             parent_skew: float = 0.0) -> Trace:
+             parent_skew: float = 0.0, burst_levels: int = 0, burst_fanout: int = 10,
+             burst_bits: int = 48, burst_scale: float = 1.0, hybrid_far: float = -1.0) -> Trace:
     """Generational toy simulation.
 
     Generation 0 holds ``pop`` primordial genomes (no parents) derived from ``founders`` random
@@ -120,6 +128,13 @@ def generate(kind: int = BITS, words: int = 8, pop: int = 1000, gens: int = 100,
     ``1 - survive`` of the previous population dies.  ``parent_skew`` > 0 draws parents with
     probability proportional to rank^-skew (a few prolific lineages).  With ``compat_classes`` > 1
     each founder lineage gets its own (mu, sigma_in, sigma_out) triple, inherited from the mother.
+    ``burst_levels`` > 0 adds an adaptive radiation: in each of the generations 1..burst_levels every
+    child jumps to one of ``burst_fanout`` niches (XOR of a ``burst_bits``-bit mask, or a shift of
+    ``burst_scale`` sigma for float genomes), which grows a tree of fanout^levels well separated
+    species below the root before the steady regime starts.  Fathers are drawn from the mother's own
+    lineage/niche (mates must be compatible, cf. the bail-out crossover of crossover.h:222-248); a
+    fraction ``hybrid_far`` of the hybrids (default: all of them when no bursts/founders are used)
+    takes a father from anywhere in the population.
     """
     rng = np.random.default_rng(seed)
     B = pop * gens
@@ -148,6 +163,10 @@ def generate(kind: int = BITS, words: int = 8, pop: int = 1000, gens: int = 100,
         f = payload[:pop].view(np.float32)
         f += (rng.standard_normal(f.shape) * noise).astype(np.float32)
     compat[:pop] = classes[lineage % classes.shape[0]]
+    cluster = np.zeros(B, dtype=np.int64)       # lineage / niche path of every individual
+    cluster[:pop] = lineage
+    if hybrid_far < 0:
+        hybrid_far = 1.0 if (burst_levels == 0 and founders == 1) else 0.0
     alive = np.arange(pop, dtype=np.uint32)
     gbo.append(pop)
     gdo.append(0)
@@ -167,11 +186,30 @@ def generate(kind: int = BITS, words: int = 8, pop: int = 1000, gens: int = 100,
             f_idx = rng.integers(0, n_al, size=pop)
         m = alive[m_idx]
         f = alive[f_idx]
+        if hybrid > 0 and hybrid_far < 1.0:
+            # same-cluster father: a random member of the mother's cluster
+            order = np.argsort(cluster[alive], kind="stable")
+            sorted_cl = cluster[alive][order]
+            lo = np.searchsorted(sorted_cl, cluster[m], side="left")
+            hi = np.searchsorted(sorted_cl, cluster[m], side="right")
+            near = alive[order[lo + (rng.random(pop) * (hi - lo)).astype(np.int64)]]
+            f = np.where(rng.random(pop) < hybrid_far, f, near)
         is_h = (rng.random(pop) < hybrid) & (f != m)
         child = payload[m].copy()
         if is_h.any():
             mask = rng.integers(0, 2, size=(pop, words)).astype(bool) & is_h[:, None]
             child = np.where(mask, payload[f], child)
+        cluster[b0:b0 + pop] = cluster[m]
+        if g <= burst_levels:
+            niche = rng.integers(0, burst_fanout, size=pop)
+            cluster[b0:b0 + pop] = cluster[m] * burst_fanout + niche
+            if kind == BITS:
+                masks = np.zeros((burst_fanout, words), dtype=np.uint32)
+                _flip_bits(rng, masks, burst_bits)
+                child ^= masks[niche]
+            else:
+                shifts = (rng.standard_normal((burst_fanout, words)) * burst_scale).astype(np.float32)
+                child = (child.view(np.float32) + shifts[niche]).view(np.uint32)
         if kind == BITS:
             _flip_bits(rng, child, flips)
         else:

@@ -90,6 +90,10 @@ class PhylogeneticTree:
     def del_genome(self, sid: int):
         check(lib().apt_tree_del_genome(self._h, int(sid)))
 
+    def del_genomes(self, sids):
+        a = _u32(sids)
+        check(lib().apt_tree_del_genomes(self._h, a.size, _ptr(a)))
+
     def register_candidate(self, mother_sid: int, father_sid: int):
         check(lib().apt_tree_register_candidate(self._h, mother_sid, father_sid, +1))
 
@@ -127,16 +131,17 @@ class PhylogeneticTree:
         return json.loads(buf.raw[:n].decode())
 
     def counters(self) -> dict:
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(16, dtype=np.uint64)
         check(lib().apt_tree_counters(self._h, out.ctypes.data_as(_lib.u64p)))
         keys = ["births", "device_scores", "patched_scores", "host_scores", "kernel_launches",
-                "host_distance_evals", "guard_rechecks", "device_pairs"]
+                "host_distance_evals", "guard_rechecks", "device_pairs", "device_reps_read",
+                "score_launches", "refresh_rows"]
         return dict(zip(keys, (int(x) for x in out)))
 
     def timers(self) -> dict:
-        out = np.zeros(4, dtype=np.float64)
+        out = np.zeros(8, dtype=np.float64)
         check(lib().apt_tree_timers(self._h, out.ctypes.data_as(_lib.f64p)))
-        return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s"], (float(x) for x in out)))
+        return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s", "score_kernel_ms"], (float(x) for x in out)))
 
     def node_info(self, sid: int) -> dict:
         info = _lib.AptNodeInfo()
@@ -163,7 +168,6 @@ class PhylogeneticTree:
             gid = np.arange(b0 + 1, b1 + 1, dtype=np.uint32)
             s, sl, _ = self.add_genomes(trace.payload[b0:b1], trace.compat[b0:b1], gid, mgid, msid, fgid, fsid)
             sid_of[b0:b1], slot_of[b0:b1] = s, sl
-            for d in trace.deaths_of(g):
-                self.del_genome(int(sid_of[d]))
+            self.del_genomes(sid_of[trace.deaths_of(g)])
             self.step(g + 1, sid_of[trace.alive_of(g)])
         return sid_of, slot_of

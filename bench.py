@@ -1,0 +1,334 @@
+#!/usr/bin/env python3
+"""Benchmark of the species-assignment hot path (BASELINE.json metric: births classified / s).
+
+Workload (BASELINE.json configs[1], "C2"): 256-bit bit-string genomes, Hamming distance,
+100 000 births per step against ~1 000 live species with enveloppes of K = 10 representatives.
+The synthetic host simulation (apoget_b200.synth, seed 42) first radiates 1 000 species below the
+root in three generations; every later generation is one STEP: 100 000 births whose parents are
+drawn from the previous generation, classified by one batched addGenome
+(reference: src/core/tree/phylogenetictree.hpp:268-302, 553-650, 657-738), with the reference's exact
+sequential semantics.  Timed per step: the add_genomes call only (the hot path); deaths and step()
+bookkeeping run between timed regions, as in oracle/ref_driver.cpp which times the same loop.
+
+  value : births/s with each step's payloads already resident in HBM (apt_tree_add_genomes_dev)
+  e2e   : births/s through apt_tree_add_genomes with pinned HOST buffers (H2D + kernels + D2H + the
+          ordered resolution pass inside the timed region)
+  roofline : the score-pairs kernel, timed with CUDA events on the engine's own stream
+  cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref/apt_ref_driver, one
+          thread -- the reference is single-threaded and the tree is sequential) on the same trace.
+
+N > 1 (torchrun): the candidate-mode tree is one sequential stream, so ranks are independent
+replicas ("islands": rank r simulates seed 42 + r); no data-path collective; weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from apoget_b200 import synth  # noqa: E402
+
+SETUP_GENS = 4          # generations 0..3: root + three 10-way radiations -> 1 000 species (+111 ancestors)
+WORKLOAD = dict(kind=synth.BITS, words=8, flips=0.5, sigma=12.0, hybrid=0.05, burst_levels=3, burst_fanout=10)
+TREE_CFG = dict(K=10)
+METRIC = "births classified/sec (species assignment, reference-exact)"
+UNIT = "births/s"
+
+
+def make_trace(pop: int, steps: int, seed: int) -> synth.Trace:
+    return synth.generate(pop=pop, gens=SETUP_GENS + steps, seed=seed, **WORKLOAD)
+
+
+def peaks() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self) -> dict:
+        self._stop_ev.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference_arm(trace_path: str, pop: int, warmup: int, steps: int, cref: bool = False) -> dict:
+    """Times the reference's own CPU implementation on the same trace (addGenome loop only)."""
+    import oracle
+    if oracle.have_reference(cref):
+        r = oracle.run_reference(trace_path, os.path.join(tempfile.gettempdir(), "apt_bench_ref"), TREE_CFG, cref=cref,
+                                 extra=["--no-json", "--no-res", "--no-events",
+                                        "--max-births", str(pop * (SETUP_GENS + warmup + steps))])
+        gs, kind = r["gen_seconds"], "reference"
+        evals = r["comparisons"]
+    else:           # the reference binary did not travel: time our CPU restatement instead
+        tr = synth.read_trace(trace_path)
+        o = oracle.Oracle(tr.kind, tr.words, **TREE_CFG)
+        o.log_events(False)
+        o.replay(trace_path, max_births=pop * (SETUP_GENS + warmup + steps))
+        gs, kind = list(o.gen_seconds), "port"
+        evals = o.stats()["comparisons"]
+    timed = gs[SETUP_GENS + warmup:SETUP_GENS + warmup + steps]
+    sec = float(sum(timed))
+    return dict(value=pop * len(timed) / sec, seconds=sec, kind=kind, cores=1, gens_timed=len(timed),
+                gen_seconds=[float(x) for x in timed], comparisons=int(evals))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pop", type=int, default=100_000, help="births per step (C2: 100 000)")
+    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                                    # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_steps = args.warmup + args.steps
+    config = {"workload": "C2: 256-bit Hamming genomes, 100k births/step, ~1k species x enveloppe K=10 "
+                          "(candidate mode, reference-exact sequential semantics)",
+              "births_per_step": args.pop, "species": "1000 live (+111 ancestors)", "K": TREE_CFG["K"],
+              "genome_bits": 256, "seed": 42, "l2": "payload+outputs of each step are new data (never re-read); "
+              "256 MiB L2 flush between timed steps", "parallelism": f"replicas x{world}" if world > 1 else "single GPU"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        trace = make_trace(args.pop, n_steps, 42)
+        path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
+        synth.write_trace(path, trace)
+        t0 = time.time()
+        r = run_reference_arm(path, args.pop, args.warmup, args.steps)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, r["gens_timed"]),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount + f64 compat",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                 "sample": f"{r['gens_timed']} timed steps x {args.pop} births after "
+                                           f"{SETUP_GENS}+{args.warmup} untimed generations, addGenome loop only; "
+                                           f"unmodified reference, -O2 -DNDEBUG, 1 thread (single-threaded code)"},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.time() - t0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm (B200)
+    import torch
+    import torch.distributed as dist
+    from apoget_b200.tree import PhylogeneticTree, INVALID, FLAG_NO_EVENTS
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    trace = make_trace(args.pop, n_steps, 42 + rank)
+    pop, W = args.pop, trace.words
+    B = trace.n_births
+
+    def fresh_tree():
+        t = PhylogeneticTree(trace.kind, W, device=local_rank, flags=FLAG_NO_EVENTS, **TREE_CFG)
+        sid_of = np.full(B, INVALID, dtype=np.uint32)
+        return t, sid_of
+
+    def ids_for(g, sid_of):
+        b0, b1 = g * pop, (g + 1) * pop
+        m, f = trace.mother[b0:b1], trace.father[b0:b1]
+        hm, hf = m != INVALID, f != INVALID
+        return [np.arange(b0 + 1, b1 + 1, dtype=np.uint32),
+                np.where(hm, m + 1, INVALID).astype(np.uint32),
+                np.where(hm, sid_of[np.where(hm, m, 0)], INVALID).astype(np.uint32),
+                np.where(hf, f + 1, INVALID).astype(np.uint32),
+                np.where(hf, sid_of[np.where(hf, f, 0)], INVALID).astype(np.uint32)]
+
+    def finish_gen(t, g, sid_of):
+        t.del_genomes(sid_of[trace.deaths_of(g)])
+        t.step(g + 1, sid_of[trace.alive_of(g)])
+
+    tree_h, sid_h = fresh_tree()       # fed from pinned host memory (e2e)
+    tree_d, sid_d = fresh_tree()       # fed from device-resident payloads (value)
+
+    # untimed setup: grow both trees through the radiation generations (same product path)
+    for g in range(SETUP_GENS):
+        for t, sid_of in ((tree_h, sid_h), (tree_d, sid_d)):
+            b0, b1 = g * pop, (g + 1) * pop
+            s, _, _ = t.add_genomes(trace.payload[b0:b1], trace.compat[b0:b1], *ids_for(g, sid_of))
+            sid_of[b0:b1] = s
+            finish_gen(t, g, sid_of)
+
+    pin_payload = torch.empty((pop, W), dtype=torch.int32).pin_memory()
+    pin_compat = torch.empty((pop, 3), dtype=torch.float32).pin_memory()
+    pin_sid = torch.empty(pop, dtype=torch.int32).pin_memory()
+    pin_slot = torch.empty(pop, dtype=torch.int32).pin_memory()
+    pin_rep = torch.empty(pop, dtype=torch.int32).pin_memory()
+    dev_payload = torch.empty((pop, W), dtype=torch.int32, device="cuda")
+    dev_compat = torch.empty((pop, 3), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    vp = ctypes.c_void_p
+    stream = torch.cuda.current_stream()
+
+    def timed_step(g, timed):
+        b0, b1 = g * pop, (g + 1) * pop
+        out = {}
+        # --- e2e: host buffers through the public C ABI -------------------------------------------
+        pin_payload.numpy()[:] = trace.payload[b0:b1].view(np.int32)
+        pin_compat.numpy()[:] = trace.compat[b0:b1]
+        ids = ids_for(g, sid_h)
+        flush.fill_(g & 0xFF)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        tree_h.add_genomes_raw(pop, vp(pin_payload.data_ptr()), vp(pin_compat.data_ptr()),
+                               [vp(x.ctypes.data) for x in ids],
+                               vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        out["e2e_ms"] = e0.elapsed_time(e1)
+        sid_h[b0:b1] = pin_sid.numpy().view(np.uint32)
+        finish_gen(tree_h, g, sid_h)
+        # --- value: payloads already resident in HBM ------------------------------------------------
+        dev_payload.copy_(pin_payload, non_blocking=True)
+        dev_compat.copy_(pin_compat, non_blocking=True)
+        ids = ids_for(g, sid_d)
+        flush.fill_((g + 1) & 0xFF)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        tree_d.add_genomes_dev(pop, vp(dev_payload.data_ptr()), vp(dev_compat.data_ptr()), vp(stream.cuda_stream),
+                               [vp(x.ctypes.data) for x in ids],
+                               vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
+        d1.record(stream)
+        torch.cuda.synchronize()
+        out["dev_ms"] = d0.elapsed_time(d1)
+        sid_d[b0:b1] = pin_sid.numpy().view(np.uint32)
+        finish_gen(tree_d, g, sid_d)
+        assert np.array_equal(sid_h[b0:b1], sid_d[b0:b1]), "host-fed and device-fed trees diverged"
+        return out
+
+    for w in range(args.warmup):
+        timed_step(SETUP_GENS + w, False)
+
+    c0, t0 = tree_h.counters(), tree_h.timers()
+    cd0 = tree_d.counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    per_step = [timed_step(SETUP_GENS + args.warmup + k, True) for k in range(args.steps)]
+    clocks = sampler.stop()
+    c1, t1 = tree_h.counters(), tree_h.timers()
+    cd1 = tree_d.counters()
+
+    e2e_ms = sum(s["e2e_ms"] for s in per_step)
+    dev_ms = sum(s["dev_ms"] for s in per_step)
+    if world > 1:
+        tt = torch.tensor([e2e_ms, dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms, dev_ms = float(tt[0]), float(tt[1])
+    births = pop * args.steps * world
+
+    # ---- roofline of the dominant kernel (score_pairs), from the engine's own CUDA events --------
+    dc = {k: c1[k] - c0[k] for k in c1}
+    launches = max(1, dc["score_launches"])
+    kernel_ms = (t1["score_kernel_ms"] - t0["score_kernel_ms"]) / launches
+    G = 4 * W
+    K = TREE_CFG["K"]
+    pairs, reps = dc["device_pairs"] / launches, dc["device_reps_read"] / launches
+    # algorithmic bytes per launch: births once (payload + 16 B compat meta), every
+    # touched representative once (payload + 16 B meta), one 8-byte pair descriptor and one
+    # (4 + 4K)-byte result per pair
+    alg_bytes = pop * (G + 16) + reps * (G + 16) + pairs * (8 + 4 + 4 * K)
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+
+    h2d = pop * (G + 12) + pop * 16 + int(pairs) * 8
+    d2h = int(pairs) * (4 + 4 * K)
+    line = {
+        "metric": METRIC, "value": births / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 popcount + f64 compat (bit-exact)", "data": "synthetic", "config": config,
+        "e2e": {"value": births / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int((c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])),
+        "roofline": {"bound": "hbm", "kernel": "score_pairs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "pairs_per_launch": pairs, "evals_per_s_kernel": pairs * K / (kernel_ms * 1e-3) if kernel_ms else 0},
+        "clocks": clocks,
+        "breakdown_e2e_ms_per_step": {
+            "prepare": 1e3 * (t1["prepare_s"] - t0["prepare_s"]) / args.steps,
+            "device_wait": 1e3 * (t1["device_s"] - t0["device_s"]) / args.steps,
+            "ordered_resolution": 1e3 * (t1["walk_s"] - t0["walk_s"]) / args.steps,
+            "pool_refresh": 1e3 * (t1["refresh_s"] - t0["refresh_s"]) / args.steps},
+        "resolution": {k: dc[k] / args.steps for k in ("device_scores", "patched_scores", "host_scores",
+                                                         "host_distance_evals", "guard_rechecks")},
+        "species": tree_h.stats()["width"],
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
+        synth.write_trace(path, trace)
+        n = max(1, min(args.cpu_sample_steps, args.steps))
+        r = run_reference_arm(path, pop, args.warmup, n)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                "sample": f"first {n} timed steps ({n * pop} births) of the same trace after the same "
+                                          f"{SETUP_GENS}+{args.warmup} untimed generations; addGenome loop only; "
+                                          f"1 thread (the reference is single-threaded); host has {os.cpu_count()} cores"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -151,15 +151,21 @@ int apt_tree_node_distances (apt_tree *t, uint32_t sid, float *out_kxk);        
 int apt_tree_root (apt_tree *t, uint32_t *out_sid);                                   /* APT_INVALID when empty */
 int apt_tree_alive_species (apt_tree *t, uint32_t *out_sids, uint32_t cap, uint32_t *n);
 
+/* delGenome for n genomes at once (same effect as n calls of apt_tree_del_genome, in order). */
+int apt_tree_del_genomes (apt_tree *t, uint32_t n, const uint32_t *sids);
+
 /* Counters of the resolution pass since creation: out[0] births, [1] (birth,species) scores taken
  * from the device, [2] scores repaired on the host (some representatives changed in-batch),
  * [3] scores fully recomputed on the host, [4] kernel launches, [5] host-side distance evaluations,
- * [6] guard-band rechecks, [7] device pairs submitted. */
-int apt_tree_counters (apt_tree *t, uint64_t out[8]);
+ * [6] guard-band rechecks, [7] device pairs submitted to the scoring kernel, [8] representatives
+ * those pairs read (distinct enveloppe rows per launch, summed), [9] scoring-kernel launches,
+ * [10] rows uploaded by pool refreshes, [11..15] reserved. */
+int apt_tree_counters (apt_tree *t, uint64_t out[16]);
 
-/* Time spent (seconds, cumulative) : out[0] host prepare, [1] device (H2D+kernels+D2H, as waited for
- * by the host), [2] ordered resolution walk, [3] pool refresh. */
-int apt_tree_timers (apt_tree *t, double out[4]);
+/* Time spent (cumulative): out[0] host prepare (s), [1] device H2D+kernels+D2H as waited for by the
+ * host (s), [2] ordered resolution walk (s), [3] pool refresh (s), [4] scoring kernel alone,
+ * CUDA events on the engine stream (ms), [5..7] reserved. */
+int apt_tree_timers (apt_tree *t, double out[8]);
 
 /* ------------------------------------------------------------------------------------------------
  * Stateless kernels (the pieces of the hot path, individually testable against the oracle).

@@ -61,7 +61,8 @@ def lib() -> ctypes.CDLL:
         L.apto_to_json.restype = ctypes.c_uint64
         L.apto_to_json.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64]
         L.apto_replay.restype = ctypes.c_double
-        L.apto_replay.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, _u32p, _u8p, _u32p]
+        L.apto_replay.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, _u32p, _u8p, _u32p,
+                                  ctypes.POINTER(ctypes.c_double)]
         L.apto_distance.restype = ctypes.c_double
         L.apto_distance.argtypes = [ctypes.c_uint32, ctypes.c_uint32, _u32p, _u32p]
         L.apto_compatibility.restype = ctypes.c_double
@@ -152,14 +153,15 @@ class Oracle:
     def replay(self, trace_path: str, max_births: int = 0, n_births: int | None = None):
         """Replays a trace file with the loop of oracle/ref_driver.cpp.
         Returns (sids, entered, seconds spent in the addGenome loop)."""
-        if n_births is None:
-            from apoget_b200.synth import read_trace
-            n_births = read_trace(trace_path).n_births
+        from apoget_b200.synth import read_trace
+        tr = read_trace(trace_path)
+        n_births = tr.n_births
+        self.gen_seconds = np.zeros(tr.n_gens, dtype=np.float64)
         sids = np.full(n_births, 0xFFFFFFFF, dtype=np.uint32)
         ent = np.zeros(n_births, dtype=np.uint8)
         done = ctypes.c_uint32()
         sec = lib().apto_replay(self._h, trace_path.encode(), max_births, _p(sids, _u32p), _p(ent, _u8p),
-                                ctypes.byref(done))
+                                ctypes.byref(done), _p(self.gen_seconds, ctypes.POINTER(ctypes.c_double)))
         if sec < 0:
             raise RuntimeError(lib().apto_error(self._h).decode())
         return sids[:done.value], ent[:done.value], sec

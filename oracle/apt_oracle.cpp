@@ -711,7 +711,7 @@ uint64_t apto_to_json (void *h, char *out, uint64_t cap) {
 /// addGenome loop (negative on error). maxBirths == 0 replays everything, otherwise stops after
 /// the generation that crosses it. nDone receives the number of births replayed.
 double apto_replay (void *h, const char *path, uint32_t maxBirths, uint32_t *outSid,
-                    uint8_t *outEntered, uint32_t *nDone) {
+                    uint8_t *outEntered, uint32_t *nDone, double *genSeconds) {
   Tree *t = static_cast<Tree*>(h);
   double seconds = 0;
   int rc = guarded(t, [&] {
@@ -733,7 +733,9 @@ double apto_replay (void *h, const char *path, uint32_t maxBirths, uint32_t *out
         if (outSid) outSid[b] = sidOf[b];
         if (outEntered) outEntered[b] = entered;
       }
-      seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+      const double gs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+      seconds += gs;
+      if (genSeconds) genSeconds[gen] = gs;
       for (uint32_t i = tr.gen_death_off[gen]; i < tr.gen_death_off[gen+1]; i++)
         t->delGenome(sidOf[tr.deaths[i]]);
       std::vector<uint32_t> sids;

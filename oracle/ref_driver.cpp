@@ -168,6 +168,7 @@ int run (const apt_trace::Trace &t, const Options &o) {
   };
 
   double seconds = 0;
+  std::vector<double> genSeconds;
   uint32_t done = 0, gens = 0;
   std::vector<G> batch;
   for (uint32_t gen = 0; gen < t.h.n_gens; gen++) {
@@ -181,7 +182,8 @@ int run (const apt_trace::Trace &t, const Options &o) {
       sidOf[b] = uint32_t(r.sid);
       entered[b] = (r.udata != nullptr);
     }
-    seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    genSeconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count());
+    seconds += genSeconds.back();
 
     for (uint32_t i = t.gen_death_off[gen]; i < t.gen_death_off[gen+1]; i++)
       tree.delGenome(makeGenome(t.deaths[i]));
@@ -230,7 +232,7 @@ int run (const apt_trace::Trace &t, const Options &o) {
   printf("{\"impl\": \"%s\", \"births\": %u, \"gens\": %u, \"seconds\": %.6f, "
          "\"births_per_s\": %.1f, \"evals_per_s\": %.1f, \"insertions\": %u, \"deletions\": %u, "
          "\"comparisons\": %u, \"branching\": %u, \"next_sid\": %u, \"width\": %u, "
-         "\"roundtrip_ok\": %s}\n",
+         "\"roundtrip_ok\": %s, \"gen_seconds\": [",
 #ifdef APT_REF_CREF_PATCH
          "reference+cref",
 #else
@@ -239,6 +241,8 @@ int run (const apt_trace::Trace &t, const Options &o) {
          done, gens, seconds, done / seconds, st.comparisons / seconds,
          st.insertions, st.deletions, st.comparisons, st.branching,
          uint32_t(std::as_const(tree).nextNodeID()), tree.width(), roundtripOk ? "true" : "false");
+  for (size_t i = 0; i < genSeconds.size(); i++) printf("%s%.6f", i ? ", " : "", genSeconds[i]);
+  printf("]}\n");
   return 0;   // roundtrip_ok is reported, not enforced: re-parented children may be re-ordered by fromJson
 }
 

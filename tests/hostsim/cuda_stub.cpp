@@ -23,6 +23,8 @@ cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) { *s = nullptr
 cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags (cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
 cudaError_t cudaEventDestroy (cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate (cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventElapsedTime (float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 cudaError_t cudaEventRecord (cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaMalloc (void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
