@@ -1,0 +1,447 @@
+// apt/phylogenetictree.hpp -- drop-in for APOGeT's phylogeny::PhylogeneticTree<GENOME,UDATA>
+// (reference: src/core/tree/phylogenetictree.hpp) whose species-assignment hot path runs on a
+// B200 through libapt_b200.so (C ABI: include/apt_b200.h).
+//
+// Same class name, member names, argument meaning and callback order as the reference; the types
+// below mirror src/core/tree/treetypes.h (GID, SID, PID, Genealogy, InsertionResult),
+// callbacks.hpp (Callbacks_t) and ptreeconfig.h (config::PTree).  A host program switches by
+// including this header, using namespace `apt` instead of `phylogeny`, and describing how its
+// genome is laid out on the device:
+//
+//   template <> struct apt::DeviceEncoding<MyGenome> {
+//     static constexpr apt_kind kind = APT_BITS;      // or APT_F32
+//     static constexpr uint32_t words = 8;            // 32-bit payload words
+//     static void encode (const MyGenome &g, uint32_t *payload, float compat[3]);
+//   };
+//
+// where payload/compat must be consistent with the genome's own distance() / compatibility()
+// (Hamming or L2 over the payload; the two-sided gaussian of src/core/crossover.h:76-92 with
+// compat = {optimalDistance, inbreedTolerance, outbreedTolerance}).  New with respect to the
+// reference: addGenomes(first, last, out), whose result is defined as that of calling addGenome on
+// every element in order.  Not provided ("out of scope"): copy construction /
+// assignment (:98-118), fromJson / readFrom (:946-967, :1004-1016) and logTo (:874-879).
+// toJson / saveTo need nlohmann::json: define APT_WITH_JSON before including.
+#ifndef APT_PHYLOGENETICTREE_HPP
+#define APT_PHYLOGENETICTREE_HPP
+
+#include <cstdint>
+#include <limits>
+#include <map>
+#include <memory>
+#include <ostream>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../apt_b200.h"
+
+#ifdef APT_WITH_JSON
+#include <fstream>
+#include <nlohmann/json.hpp>
+#endif
+
+namespace apt {
+
+using uint = unsigned int;
+
+// ---- treetypes.h ----------------------------------------------------------------------------
+enum class GID : uint { INVALID = uint(-1) };                        // treetypes.h:24-26
+enum class SID : uint { INVALID = uint(-1) };                        // treetypes.h:74-76
+inline std::ostream& operator<< (std::ostream &os, GID g) { return os << uint(g); }
+inline std::ostream& operator<< (std::ostream &os, SID s) { return os << uint(s); }
+using LivingSet = std::set<SID>;                                     // treetypes.h:82
+
+/// treetypes.h:32-71
+class GIDManager {
+  uint next;
+public:
+  GIDManager (void) { setNext(GID(0)); }
+  void setNext (GID n) { next = uint(n) + 1; }
+  GID operator() (void) {
+    if (next == std::numeric_limits<uint>::max())
+      throw std::out_of_range("Exhausted all possible identifers for the underlying type");
+    return GID(next++);
+  }
+  explicit operator GID (void) const { return GID(next); }
+};
+
+/// treetypes.h:85-119
+struct PID {
+  GID gid;
+  SID sid;
+  explicit PID (void) : PID(GID::INVALID) {}
+  explicit PID (GID gid) : gid(gid), sid(SID::INVALID) {}
+  bool valid (void) const { return gid != GID::INVALID; }
+  friend bool operator== (const PID &l, const PID &r) { return l.gid == r.gid && l.sid == r.sid; }
+};
+
+/// treetypes.h:122-188
+struct Genealogy {
+  PID mother, father, self;
+  uint generation = 0;
+  void setSID (SID sid) { self.sid = sid; }
+  void updateAfterCloning (GIDManager &m) { mother = self; father = PID(); self = PID(m()); generation++; }
+  void updateAfterCrossing (const Genealogy &mo, const Genealogy &fa, GIDManager &m) {
+    mother = mo.self;  father = fa.self;  self = PID(m());
+    generation = std::max(mo.generation, fa.generation) + 1;
+  }
+  void setAsPrimordial (GIDManager &m) { self = PID(m()); mother = PID(); father = PID(); generation = 0; }
+};
+
+/// treetypes.h:191-195
+template <typename UserData>
+struct InsertionResult {
+  SID sid;
+  UserData *udata;
+};
+
+/// phylogenetictree.hpp:28-34
+struct NoUserData {
+  NoUserData (void) {}
+  NoUserData (GID) {}
+  void removedFromEnveloppe (void) const {}
+};
+
+/// callbacks.hpp:16-45 -- specialise for your tree type to receive the events
+template <typename PT>
+struct Callbacks_t {
+  void onStepped (uint, const LivingSet &) {}
+  void onNewSpecies (SID, SID) {}
+  void onGenomeEntersEnveloppe (SID, GID) {}
+  void onGenomeLeavesEnveloppe (SID, GID) {}
+  void onMajorContributorChanged (SID, SID, SID) {}
+};
+
+namespace config {
+/// ptreeconfig.h:17-69 with the defaults of ptreeconfig.cpp:7-19.  Values are read when a tree is
+/// constructed (the reference latches rsetSize there too, phylogenetictree.hpp:90).
+struct PTree {
+#define APT_PARAM(TYPE, NAME, VALUE) static TYPE& NAME (void) { static TYPE v = VALUE; return v; }
+  APT_PARAM(double, compatibilityThreshold, .1)
+  APT_PARAM(double, similarityThreshold, .5)
+  APT_PARAM(double, avgCompatibilityThreshold, .25)
+  APT_PARAM(uint, rsetSize, 5)
+  APT_PARAM(bool, simpleNewSpecies, true)
+  APT_PARAM(uint, stillbornTrimmingPeriod, 100)
+  APT_PARAM(float, stillbornTrimmingThreshold, .25f)
+  APT_PARAM(float, stillbornTrimmingDelay, 4.f)
+  APT_PARAM(uint, stillbornTrimmingMinDelay, 200)
+  APT_PARAM(bool, DEBUG_FULL_CONTINUOUS, true)
+  APT_PARAM(int, DEBUG_ENV_CRIT, 1)
+#undef APT_PARAM
+};
+} // namespace config
+
+/// How a genome is laid out for the device; specialise per genome type (see the file header).
+template <typename GENOME> struct DeviceEncoding;
+
+// ---- phylogenetictree.hpp ------------------------------------------------------------------------
+template <typename GENOME, typename UDATA = NoUserData>
+class PhylogeneticTree {
+public:
+  using Genome = GENOME;
+  using UserData = UDATA;
+  using Callbacks = Callbacks_t<PhylogeneticTree<Genome, UserData>>;
+  using Config = config::PTree;
+  using InsertionResult = apt::InsertionResult<UserData>;
+  using Encoding = DeviceEncoding<GENOME>;
+
+  /// node.hpp:25-85
+  struct Representative {
+    uint timestamp;
+    Genome genome;
+    std::unique_ptr<UserData> userData;
+  };
+
+  /// What the reference exposes through nodeAt(sid)-> : id, parent, children, data, rset
+  struct Node {
+    SID id, parent;                                  ///< parent == SID::INVALID for parentless nodes
+    struct { uint firstAppearance, lastAppearance, count, currentlyAlive, pendingCandidates; } data;
+    std::vector<SID> children;
+    const std::vector<Representative> *rset;
+  };
+
+  /// phylogenetictree.hpp:343-355
+  struct Stats {
+    uint insertions = 0, deletions = 0, comparisons = 0, branching = 0;
+    friend std::ostream& operator<< (std::ostream &os, const Stats &s) {
+      return os << " " << s.insertions << " " << s.deletions << " " << s.comparisons << " " << s.branching;
+    }
+  };
+  struct StatsHeader {
+    friend std::ostream& operator<< (std::ostream &os, const StatsHeader&) {
+      return os << " PTInsertions PTDeletions PTComparisons PTBranching";
+    }
+  };
+
+  /// Create an empty PTree (:88-95) on CUDA device `device`
+  explicit PhylogeneticTree (int device = 0) : _callbacks(nullptr) {
+    apt_params p;
+    apt_params_default(&p);
+    p.kind = Encoding::kind;  p.words = Encoding::words;
+    p.rset_size = Config::rsetSize();
+    p.full_continuous = Config::DEBUG_FULL_CONTINUOUS();  p.env_crit = Config::DEBUG_ENV_CRIT();
+    p.compat_thr = Config::compatibilityThreshold();  p.sim_thr = Config::similarityThreshold();
+    p.avg_thr = Config::avgCompatibilityThreshold();
+    p.trim_period = Config::stillbornTrimmingPeriod();  p.trim_thr = Config::stillbornTrimmingThreshold();
+    p.trim_delay = Config::stillbornTrimmingDelay();  p.trim_min_delay = Config::stillbornTrimmingMinDelay();
+    p.device = device;
+    _rsetSize = p.rset_size;
+    check(apt_tree_create(&p, &_tree));
+  }
+
+  ~PhylogeneticTree (void) { if (_tree) apt_tree_destroy(_tree); }
+  PhylogeneticTree (const PhylogeneticTree&) = delete;
+  PhylogeneticTree& operator= (const PhylogeneticTree&) = delete;
+
+  // == Accessors (:155-202) ==
+  Callbacks* callbacks (void) { return _callbacks; }
+  uint width (void) const { return st(5); }
+  uint step (void) const { return st(6); }
+  SID nextNodeID (void) const { return SID(st(4)); }
+  const LivingSet& aliveSpecies (void) const { return _aliveSpecies; }
+  SID root (void) const { uint32_t r; check(apt_tree_root(_tree, &r)); return SID(r); }
+
+  /// \return a view of the node with \p sid (throws like :168-177 when it does not exist)
+  Node nodeAt (SID sid) const {
+    apt_node_info i;
+    check(apt_tree_node_info(_tree, uint32_t(sid), &i));
+    Node n;
+    n.id = SID(i.sid);  n.parent = SID(i.parent_sid);
+    n.data = { i.data[0], i.data[1], i.data[2], i.data[3], i.data[4] };
+    std::vector<uint32_t> c (i.n_children);
+    if (!c.empty()) check(apt_tree_node_children(_tree, uint32_t(sid), c.data(), uint32_t(c.size())));
+    for (uint32_t s: c) n.children.push_back(SID(s));
+    static const std::vector<Representative> empty;
+    auto it = _rsets.find(sid);
+    n.rset = it == _rsets.end() ? &empty : &it->second;
+    return n;
+  }
+
+  /// :181-187
+  UserData* getUserData (const PID &pid) const {
+    nodeAt(pid.sid);                                           // throws for unknown species
+    auto it = _rsets.find(pid.sid);
+    if (it != _rsets.end())
+      for (const Representative &ep: it->second)
+        if (ep.genome.genealogy().self.gid == pid.gid) return ep.userData.get();
+    return nullptr;
+  }
+
+  // == Modifiers (:216-221) ==
+  void setCallbacks (Callbacks *c) const { _callbacks = c; }
+  void setStep (uint step) { check(apt_tree_set_step(_tree, step)); }
+
+  // == Core API ==
+  /// :245-262
+  template <typename IT, typename F>
+  void step (uint step, IT begin, IT end, F sidExtractor) {
+    _aliveSpecies.clear();
+    std::vector<uint32_t> sids;
+    for (IT it = begin; it != end; ++it) {
+      SID s = sidExtractor(*it);
+      _aliveSpecies.insert(s);
+      sids.push_back(uint32_t(s));
+    }
+    check(apt_tree_step(_tree, step, sids.data(), uint32_t(sids.size())));
+    dropTrimmed();
+    replayEvents(nullptr, nullptr, 0);
+  }
+
+  /// :268-302
+  InsertionResult addGenome (const Genome &g) {
+    InsertionResult r;
+    addGenomes(&g, &g + 1, &r);
+    return r;
+  }
+
+  /// Batched insertion: identical, by definition, to addGenome on each element of [first, last)
+  /// in order (results, callbacks and their order included).  `out` may be null.
+  template <typename IT>
+  void addGenomes (IT first, IT last, InsertionResult *out) {
+    _pl.clear();  _cp.clear();  _ids.clear();
+    std::vector<const Genome*> gs;
+    for (IT it = first; it != last; ++it) gs.push_back(&*it);
+    const size_t n = gs.size();
+    if (!n) return;
+    _pl.resize(n * Encoding::words);  _cp.resize(n * 3);  _ids.resize(n * 5);
+    for (size_t i = 0; i < n; i++) {
+      Encoding::encode(*gs[i], &_pl[i * Encoding::words], &_cp[i * 3]);
+      const Genealogy &ge = gs[i]->genealogy();
+      _ids[i] = uint32_t(ge.self.gid);
+      _ids[n + i] = uint32_t(ge.mother.gid);      _ids[2 * n + i] = uint32_t(ge.mother.sid);
+      _ids[3 * n + i] = uint32_t(ge.father.gid);  _ids[4 * n + i] = uint32_t(ge.father.sid);
+    }
+    _sid.assign(n, APT_INVALID);  _slot.assign(n, -1);  _rep.assign(n, APT_INVALID);
+    uint32_t done = 0;
+    const int rc = apt_tree_add_genomes(_tree, uint32_t(n), _pl.data(), _cp.data(), &_ids[0], &_ids[n], &_ids[2 * n],
+                                        &_ids[3 * n], &_ids[4 * n], _sid.data(), _slot.data(), _rep.data(), &done);
+    // births committed before an error stay committed, exactly as when the reference throws
+    replayEvents(gs.data(), out, done);
+    check(rc);
+  }
+
+  /// :305-317
+  void delGenome (const Genome &g) { check(apt_tree_del_genome(_tree, uint32_t(g.genealogy().self.sid))); }
+
+  /// :320-329
+  void registerCandidate (const Genealogy &g) { check(apt_tree_register_candidate(_tree, uint32_t(g.mother.sid), uint32_t(g.father.sid), +1)); }
+  void unregisterCandidate (const Genealogy &g) { check(apt_tree_register_candidate(_tree, uint32_t(g.mother.sid), uint32_t(g.father.sid), -1)); }
+
+  // == Stats (:335-365) ==
+  void resetStats (void) { check(apt_tree_reset_stats(_tree)); }
+  const Stats& stats (void) const {
+    uint32_t s[8];
+    check(apt_tree_stats(_tree, s));
+    _stats.insertions = s[0]; _stats.deletions = s[1]; _stats.comparisons = s[2]; _stats.branching = s[3];
+    return _stats;
+  }
+
+  /// The engine behind this tree (counters, timers, node accessors of apt_b200.h)
+  apt_tree* handle (void) const { return _tree; }
+
+#ifdef APT_WITH_JSON
+  using json = nlohmann::json;
+
+  /// :934-941 / :887-904; genomes and user data are serialised by the user's own to_json
+  static void toJson (json &j, const PhylogeneticTree &pt) {
+    uint32_t s[8];
+    check(apt_tree_stats(pt._tree, s));
+    j["_step"] = s[6];
+    j["_envSize"] = pt._rsetSize;
+    j["_stillborns"] = s[7];
+    json alive = json::array();
+    for (SID a: pt._aliveSpecies) alive.push_back(uint(a));
+    j["alive"] = alive;
+    const SID r = pt.root();
+    j["tree"] = r == SID::INVALID ? json() : pt.nodeJson(r);
+    j["nextSID"] = s[4];
+  }
+
+  /// :984-1001
+  bool saveTo (const std::string &filename) const {
+    std::ofstream ofs (filename);
+    if (!ofs) return false;
+    saveTo(ofs, -1);
+    return true;
+  }
+  void saveTo (std::ostream &os, int indent = 2) const {
+    json j;
+    toJson(j, *this);
+    os << j.dump(indent);
+  }
+#endif
+
+private:
+  apt_tree *_tree = nullptr;
+  uint _rsetSize;
+  LivingSet _aliveSpecies;
+  mutable Callbacks *_callbacks;
+  mutable Stats _stats;
+  std::map<SID, std::vector<Representative>> _rsets;       ///< host-side genome objects per enveloppe slot
+  std::vector<uint32_t> _pl, _ids, _sid, _rep;
+  std::vector<float> _cp;
+  std::vector<int32_t> _slot;
+
+  static void check (int rc) {
+    if (rc == APT_OK) return;
+    const std::string msg = apt_last_error();
+    if (rc == APT_ERR_ARGUMENT) throw std::invalid_argument(msg);   // utils::Thrower's default (:169-174)
+    throw std::runtime_error(msg);
+  }
+
+  uint st (int i) const { uint32_t s[8]; check(apt_tree_stats(_tree, s)); return s[i]; }
+
+  /// Forget the genome objects of species removed by stillborn trimming (:816-860)
+  void dropTrimmed (void) {
+    for (auto it = _rsets.begin(); it != _rsets.end(); ) {
+      apt_node_info i;
+      if (apt_tree_node_info(_tree, uint32_t(it->first), &i) != APT_OK) it = _rsets.erase(it);
+      else ++it;
+    }
+  }
+
+  /// Fires the recorded callbacks in the reference's order and mirrors enveloppe changes into the
+  /// host-side genome / user-data objects (:657-726): for each committed birth, its events first,
+  /// then the slot update, so handlers observe the state the reference would show them.
+  void replayEvents (const Genome *const *gs, InsertionResult *out, uint32_t n) {
+    const uint32_t ne = apt_tree_event_count(_tree);
+    std::vector<apt_event> ev (ne);
+    if (ne) apt_tree_events(_tree, ev.data(), ne, 1);
+    size_t e = 0;
+    auto fire = [&] (const apt_event &x) {
+      if (!_callbacks) return;
+      switch (x.type) {
+      case APT_EV_STEPPED: _callbacks->onStepped(x.a, _aliveSpecies); break;
+      case APT_EV_NEW_SPECIES: _callbacks->onNewSpecies(SID(x.a), SID(x.b)); break;
+      case APT_EV_ENTERS_ENVELOPPE: _callbacks->onGenomeEntersEnveloppe(SID(x.a), GID(x.b)); break;
+      case APT_EV_LEAVES_ENVELOPPE: _callbacks->onGenomeLeavesEnveloppe(SID(x.a), GID(x.b)); break;
+      case APT_EV_MAJOR_CONTRIBUTOR: _callbacks->onMajorContributorChanged(SID(x.a), SID(x.b), SID(x.c)); break;
+      }
+    };
+    for (uint32_t i = 0; i < n; i++) {
+      const SID sid = SID(_sid[i]);
+      const uint32_t gid = _ids[i];
+      if (e < ne && ev[e].type == APT_EV_NEW_SPECIES && ev[e].b == _sid[i]) fire(ev[e++]);
+      UserData *ud = nullptr;
+      if (_slot[i] >= 0) {
+        auto &rset = _rsets[sid];
+        if (_rep[i] != APT_INVALID) {
+          if (e < ne && ev[e].type == APT_EV_LEAVES_ENVELOPPE) fire(ev[e++]);
+          if (e < ne && ev[e].type == APT_EV_ENTERS_ENVELOPPE && ev[e].b == gid) fire(ev[e++]);
+          Representative &ep = rset[size_t(_slot[i])];
+          ep.userData->removedFromEnveloppe();               // :708
+          ud = ep.userData.get();
+          *ep.userData = UserData(GID(_rep[i]));             // rebuilt from the OUTGOING genome's id, :710
+          ep.genome = *gs[i];
+          ep.timestamp = step();
+        } else {
+          if (e < ne && ev[e].type == APT_EV_ENTERS_ENVELOPPE && ev[e].b == gid) fire(ev[e++]);
+          Representative ep;
+          ep.timestamp = step();
+          ep.genome = *gs[i];
+          ep.userData = std::make_unique<UserData>(GID(gid));
+          rset.push_back(std::move(ep));
+          ud = rset.back().userData.get();
+        }
+      }
+      if (e < ne && ev[e].type == APT_EV_MAJOR_CONTRIBUTOR && ev[e].a == _sid[i]) fire(ev[e++]);
+      if (out) out[i] = InsertionResult{ sid, ud };
+    }
+    while (e < ne) fire(ev[e++]);
+  }
+
+#ifdef APT_WITH_JSON
+  json nodeJson (SID sid) const {
+    apt_node_info i;
+    check(apt_tree_node_info(_tree, uint32_t(sid), &i));
+    json j, jd, jc, je = json::array(), jct = json::array();
+    auto it = _rsets.find(sid);
+    if (it != _rsets.end())
+      for (const Representative &r: it->second) je.push_back({ r.genome, *r.userData });
+    std::vector<uint32_t> ct (size_t(i.n_contributors) * 3);
+    if (!ct.empty()) check(apt_tree_node_contributors(_tree, uint32_t(sid), ct.data(), i.n_contributors));
+    for (uint32_t c = 0; c < i.n_contributors; c++) jct.push_back({ ct[3 * c], ct[3 * c + 1], bool(ct[3 * c + 2]) });
+    std::vector<float> d (size_t(_rsetSize) * _rsetSize);
+    check(apt_tree_node_distances(_tree, uint32_t(sid), d.data()));
+    for (uint32_t a = 0; a < i.fill; a++)
+      for (uint32_t b = a + 1; b < i.fill; b++) jd.push_back({ a, b, d[a * _rsetSize + b] });
+    std::vector<uint32_t> ch (i.n_children);
+    if (!ch.empty()) check(apt_tree_node_children(_tree, uint32_t(sid), ch.data(), i.n_children));
+    for (uint32_t c: ch) jc.push_back(nodeJson(SID(c)));
+    j["id"] = i.sid;
+    j["data"] = { i.data[0], i.data[1], i.data[2], i.data[3], i.data[4] };
+    j["envlp"] = je;
+    j["contribs"] = jct;
+    j["dists"] = jd;
+    j["children"] = jc;
+    return j;
+  }
+#endif
+};
+
+} // namespace apt
+
+#endif // APT_PHYLOGENETICTREE_HPP

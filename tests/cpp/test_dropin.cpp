@@ -1,0 +1,147 @@
+// Test program for the C++ drop-in (include/apt/phylogenetictree.hpp): replays a birth trace the way
+// a host simulation written against the reference's API would -- user genome type, user data,
+// specialised Callbacks_t -- and writes the same .res / .json artefacts as oracle/ref_driver.cpp so
+// the Python tests can diff them against the golden files produced by the unmodified reference.
+#define APT_WITH_JSON
+#include "apt/phylogenetictree.hpp"
+
+#include <array>
+#include <cstdio>
+#include <cstring>
+
+#include "../../oracle/trace.h"     // trace reader only (test infrastructure)
+
+using namespace apt;
+using json = nlohmann::json;
+
+namespace apt {
+void to_json (json &j, const PID &p) { j["g"] = uint(p.gid); j["s"] = uint(p.sid); }
+void to_json (json &j, const Genealogy &g) { j["m"] = g.mother; j["f"] = g.father; j["s"] = g.self; }
+}
+
+template <uint32_t W>
+struct Genome {
+  Genealogy gen;
+  std::array<uint32_t, W> w;
+  float mu, sin, sout;
+  const Genealogy& genealogy (void) const { return gen; }
+  friend void to_json (json &j, const Genome &g) { j["g"] = g.gen; j["c"] = {g.mu, g.sin, g.sout}; j["w"] = g.w; }
+};
+
+template <uint32_t W, apt_kind KIND>
+struct Tagged : Genome<W> {};
+
+namespace apt {
+template <uint32_t W, apt_kind KIND>
+struct DeviceEncoding<Tagged<W, KIND>> {
+  static constexpr apt_kind kind = KIND;
+  static constexpr uint32_t words = W;
+  static void encode (const Tagged<W, KIND> &g, uint32_t *payload, float compat[3]) {
+    memcpy(payload, g.w.data(), W * 4);
+    compat[0] = g.mu;  compat[1] = g.sin;  compat[2] = g.sout;
+  }
+};
+}
+
+struct UD {
+  uint32_t gid = uint32_t(-1);
+  int removed = 0;
+  UD (void) {}
+  UD (GID g) : gid(uint32_t(g)) {}
+  void removedFromEnveloppe (void) { removed++; }
+  friend void to_json (json &j, const UD &u) { j = u.gid; }
+};
+
+struct Event { uint32_t type, a, b, c; };
+static std::vector<Event> g_events;
+
+namespace apt {
+template <uint32_t W, apt_kind KIND>
+struct Callbacks_t<PhylogeneticTree<Tagged<W, KIND>, UD>> {
+  void onStepped (uint step, const LivingSet &living) { g_events.push_back({0, step, uint32_t(living.size()), 0}); }
+  void onNewSpecies (SID pid, SID sid) { g_events.push_back({1, uint32_t(pid), uint32_t(sid), 0}); }
+  void onGenomeEntersEnveloppe (SID sid, GID gid) { g_events.push_back({2, uint32_t(sid), uint32_t(gid), 0}); }
+  void onGenomeLeavesEnveloppe (SID sid, GID gid) { g_events.push_back({3, uint32_t(sid), uint32_t(gid), 0}); }
+  void onMajorContributorChanged (SID sid, SID o, SID n) { g_events.push_back({4, uint32_t(sid), uint32_t(o), uint32_t(n)}); }
+};
+}
+
+template <uint32_t W, apt_kind KIND>
+int run (const apt_trace::Trace &t, const std::string &prefix, bool oneByOne) {
+  using G = Tagged<W, KIND>;
+  using PT = PhylogeneticTree<G, UD>;
+  PT tree;
+  typename PT::Callbacks cb;
+  tree.setCallbacks(&cb);
+
+  const uint32_t B = t.h.n_births;
+  std::vector<uint32_t> sidOf (B, uint32_t(-1));
+  std::vector<uint8_t> entered (B, 0);
+  auto make = [&] (uint32_t b) {
+    G g;
+    memcpy(g.w.data(), &t.payload[size_t(b) * W], W * 4);
+    g.mu = t.compat[3*b];  g.sin = t.compat[3*b+1];  g.sout = t.compat[3*b+2];
+    g.gen.self = PID(GID(b + 1));  g.gen.self.sid = SID(sidOf[b]);
+    const uint32_t m = t.mother[b], f = t.father[b];
+    if (m != apt_trace::NONE) { g.gen.mother = PID(GID(m + 1)); g.gen.mother.sid = SID(sidOf[m]); }
+    if (f != apt_trace::NONE) { g.gen.father = PID(GID(f + 1)); g.gen.father.sid = SID(sidOf[f]); }
+    return g;
+  };
+  int bad = 0;
+  for (uint32_t gen = 0; gen < t.h.n_gens; gen++) {
+    const uint32_t b0 = t.gen_birth_off[gen], b1 = t.gen_birth_off[gen+1];
+    std::vector<G> batch;
+    for (uint32_t b = b0; b < b1; b++) batch.push_back(make(b));
+    std::vector<typename PT::InsertionResult> res (b1 - b0);
+    if (oneByOne) for (uint32_t b = b0; b < b1; b++) res[b - b0] = tree.addGenome(batch[b - b0]);
+    else tree.addGenomes(batch.begin(), batch.end(), res.data());
+    for (uint32_t b = b0; b < b1; b++) {
+      sidOf[b] = uint32_t(res[b - b0].sid);
+      entered[b] = res[b - b0].udata != nullptr;
+      // InsertionResult.udata must be the enveloppe slot's own object (:665-725)
+      PID pid (GID(b + 1));  pid.sid = res[b - b0].sid;
+      UD *ud = tree.getUserData(pid);
+      if (b + 1 == b1 && entered[b] && ud != res[b - b0].udata) bad++;
+    }
+    for (uint32_t i = t.gen_death_off[gen]; i < t.gen_death_off[gen+1]; i++) tree.delGenome(make(t.deaths[i]));
+    const uint32_t *a0 = t.alive.data() + t.gen_alive_off[gen], *a1 = t.alive.data() + t.gen_alive_off[gen+1];
+    tree.step(gen + 1, a0, a1, [&] (uint32_t b) { return SID(sidOf[b]); });
+  }
+  const auto &st = tree.stats();
+  { std::ofstream ofs (prefix + ".json");  tree.saveTo(ofs, -1); }
+  FILE *f = fopen((prefix + ".res").c_str(), "wb");
+  if (!f) return 2;
+  uint32_t n = B, ne = uint32_t(g_events.size());
+  uint32_t tail[8] = { st.insertions, st.deletions, st.comparisons, st.branching, uint32_t(tree.nextNodeID()),
+                       tree.width(), tree.step(), 0 };
+  fwrite(&n, 4, 1, f);  fwrite(sidOf.data(), 4, n, f);  fwrite(entered.data(), 1, n, f);
+  fwrite(&ne, 4, 1, f);  fwrite(g_events.data(), sizeof(Event), ne, f);  fwrite(tail, 4, 8, f);
+  fclose(f);
+  // error contract: unknown species -> std::invalid_argument, like utils::Thrower (:169-174)
+  try { tree.nodeAt(SID(0x7FFFFFFF)); bad++; } catch (const std::invalid_argument &) {}
+  printf("{\"births\": %u, \"species\": %u, \"bad\": %d}\n", B, uint32_t(tree.nextNodeID()), bad);
+  return bad ? 3 : 0;
+}
+
+int main (int argc, char **argv) {
+  if (argc < 4) { fprintf(stderr, "usage: %s <trace> <out-prefix> <rset> [--one-by-one] [--crit N] [--semi]\n", argv[0]); return 2; }
+  bool one = false;
+  config::PTree::rsetSize() = std::stoul(argv[3]);
+  for (int i = 4; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "--one-by-one") one = true;
+    else if (a == "--semi") config::PTree::DEBUG_FULL_CONTINUOUS() = false;
+    else if (a == "--crit" && i + 1 < argc) config::PTree::DEBUG_ENV_CRIT() = std::stoi(argv[++i]);
+  }
+  try {
+    apt_trace::Trace t = apt_trace::load(argv[1]);
+    if (t.h.kind == apt_trace::BITS && t.h.words == 8) return run<8, APT_BITS>(t, argv[2], one);
+    if (t.h.kind == apt_trace::BITS && t.h.words == 128) return run<128, APT_BITS>(t, argv[2], one);
+    if (t.h.kind == apt_trace::F32 && t.h.words == 64) return run<64, APT_F32>(t, argv[2], one);
+    fprintf(stderr, "unsupported trace shape\n");
+    return 2;
+  } catch (const std::exception &e) {
+    fprintf(stderr, "drop-in test failed: %s\n", e.what());
+    return 1;
+  }
+}

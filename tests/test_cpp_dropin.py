@@ -1,0 +1,48 @@
+"""The C++ drop-in (include/apt/phylogenetictree.hpp) driven like a reference host program:
+user genome type + DeviceEncoding, user data, specialised Callbacks_t, toJson through the user's
+own to_json.  CPU: linked against the host simulation; GPU (-m gpu): against libapt_b200.so."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_cases, GOLDEN
+
+CASES = [("c2_b256_k10", []), ("hybrids_b256_k5", ["--one-by-one"]), ("c4_b4096_k10", []),
+         ("semicontinuous_b256", ["--semi"]), ("crit0_b256", ["--crit", "0"])]
+
+
+def _run(exe, name, extra, tmp_path, f32=False):
+    cfg = golden_cases()[name]["cfg"]
+    prefix = str(tmp_path / name)
+    r = subprocess.run([exe, os.path.join(GOLDEN, name + ".trace"), prefix, str(cfg.get("K", 5))] + extra,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    a, b = oracle.read_res(prefix + ".res"), oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(a["sids"], b["sids"])
+    assert np.array_equal(a["entered"], b["entered"])
+    assert np.array_equal(a["events"], b["events"]), "callbacks must fire in the reference's order"
+    assert a["stats"] == b["stats"]
+    ja = json.load(open(prefix + ".json"))
+    jb = json.loads(gzip.open(os.path.join(GOLDEN, name + ".json.gz")).read())
+    if not f32:
+        assert ja == jb
+
+
+@pytest.mark.parametrize("name,extra", CASES)
+def test_dropin_host_logic(name, extra, tmp_path):
+    from hostsim import build as hb
+    from cpp import build as cb
+    _run(cb.build(hb.build(), "hostsim"), name, extra, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra", CASES + [("c3_f32x64_k10", [])])
+def test_dropin_on_gpu(name, extra, tmp_path):
+    from apoget_b200 import build as apt_build
+    from cpp import build as cb
+    _run(cb.build(apt_build.build(), "cuda"), name, extra, tmp_path, f32=name.startswith("c3"))
