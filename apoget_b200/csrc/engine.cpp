@@ -52,6 +52,12 @@ Engine::Engine (const apt_params &p) : p_(p) {
   cudaCheck(cudaEventCreateWithFlags(&evUser_, cudaEventDisableTiming), "cudaEventCreate");
   cudaCheck(cudaEventCreate(&evK0_), "cudaEventCreate");
   cudaCheck(cudaEventCreate(&evK1_), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&evS0_), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&evS1_), "cudaEventCreate");
+  // the device resolves streams for the default criteria; vote-count scoring needs the exact table
+  // (a flipped vote cannot be seen from the score, so no guard band protects it)
+  streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
+              && (p.full_continuous || lutMode_);
 }
 
 Engine::~Engine (void) {
@@ -60,6 +66,8 @@ Engine::~Engine (void) {
   if (evUser_) cudaEventDestroy(evUser_);
   if (evK0_) cudaEventDestroy(evK0_);
   if (evK1_) cudaEventDestroy(evK1_);
+  if (evS0_) cudaEventDestroy(evS0_);
+  if (evS1_) cudaEventDestroy(evS1_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -152,6 +160,7 @@ Species* Engine::makeNode (const Contributions &contrib) {
   n->reps.resize(K_);
   n->dist.assign(size_t(K_) * K_, 0.f);
   n->first = n->last = step_;
+  touchSnap(n);                                              // k = 0: nothing of it is on the device
   if (nodes_.size() <= n->sid) nodes_.resize(std::max<size_t>(n->sid + 1, nodes_.size() * 2), nullptr);
   nodes_[n->sid] = n;
   width_++;
@@ -324,13 +333,14 @@ void Engine::evalExact (const uint32_t *w, const RepMeta &g, Species *s, Eval &e
 }
 
 /// Same score, using what the device computed for this (birth, species) pair wherever the
-/// device's copy of the enveloppe is still current.
+/// enveloppe still is what the device saw when the chunk was submitted.
 void Engine::evalSpeculated (const uint32_t *w, const RepMeta &g, Species *s, int64_t pair, Eval &e) {
   comparisons_ += s->k;                                     // stats.comparisons++, :444 / :470
+  touchSnap(s);
   if (pair < 0) { counters[3]++; return evalExact(w, g, s, e); }
   const float *dd = hDist_.p + size_t(pair) * K_;
   const bool bits = (p_.kind == APT_BITS);
-  if (s->stale_mask == 0 && s->dev_fill == s->k) {
+  if (s->snap_mask == 0 && s->snap_fill == s->k) {
     const float sc = hScore_.p[pair];
     if (trusted(sc)) {
       memcpy(e.d, dd, s->k * sizeof(float));
@@ -351,7 +361,7 @@ void Engine::evalSpeculated (const uint32_t *w, const RepMeta &g, Species *s, in
   for (uint32_t r = 0; r < s->k; r++) {
     const RepMeta &m = s->reps[r];
     double d;
-    if (r < s->dev_fill && !((s->stale_mask >> r) & 1u)) d = dd[r];
+    if (r < s->snap_fill && !((s->snap_mask >> r) & 1u)) d = dd[r];
     else { d = distanceExact(w, repPayload(s, r)); measured++; }
     c[r] = std::min(compatOf(g.cls, g.mu, g.sin, g.sout, d), compatOf(m.cls, m.mu, m.sin, m.sout, d));
     e.d[r] = float(d);
@@ -362,9 +372,33 @@ void Engine::evalSpeculated (const uint32_t *w, const RepMeta &g, Species *s, in
   e.exact = true;
 }
 
+/// First use of a species in the current chunk: remember what the device snapshot holds of it
+void Engine::touchSnap (Species *s) {
+  if (s->snap_epoch != chunkEpoch_) {
+    s->snap_epoch = chunkEpoch_;
+    s->snap_mask = 0;
+    s->snap_fill = s->k;
+  }
+}
+
+/// The host changed representative r: the device row is out of date, and a device-resolved stream
+/// of this species (if any) no longer describes what happens to its later births.
 void Engine::markStale (Species *s, uint32_t r) {
+  touchSnap(s);
+  s->snap_mask |= (1u << r);
   s->stale_mask |= (1u << r);
-  if (!s->queued) { s->queued = true; refresh_.push_back(s); }
+  queueRefresh(s);
+  if (s->grp_epoch == chunkEpoch_) diverge(s);
+}
+
+/// The host takes the stream of s over: device results for its remaining births are discarded and
+/// what the kernel wrote back for it is overwritten at the next refresh.
+void Engine::diverge (Species *s) {
+  if (s->div_epoch == chunkEpoch_) return;
+  s->div_epoch = chunkEpoch_;
+  s->full_upload = true;
+  queueRefresh(s);
+  counters[11]++;
 }
 
 // ---- enveloppe criteria (src/core/tree/enveloppecriteria.cpp) on the K x K matrix ---------------
@@ -518,7 +552,48 @@ int32_t Engine::insertInto (const uint32_t *w, const RepMeta &g, Species *s, con
   return slot;
 }
 
-// One birth, in order: public addGenome (:268-302) + private addGenome (:553-650) +
+/// findBestDerived (:493-548): direct sub-species, newest first, alternating between the lists;
+/// the first score > 0 wins.
+void Engine::resolveBelow (const uint32_t *w, const RepMeta &g, Species *s0, Species *s1, Species *&best,
+                           float &bestScore, Eval &bestEval) {
+  Species *lists[2] = { s0, s1 };
+  const uint32_t S = s1 ? 2 : 1;
+  size_t left[2] = { s0->children.size(), s1 ? s1->children.size() : 0 };
+  uint32_t done = 0;
+  const uint32_t allDone = (1u << S) - 1;
+  uint32_t k = 0;
+  Eval cur;
+  while (done != allDone) {
+    if (left[k] == 0) done |= (1u << k);
+    else {
+      branching_++;
+      Species *sub = lists[k]->children[left[k] - 1];
+      evalSpeculated(w, g, sub, -1, cur);
+      if (bestScore < cur.score) { best = sub; bestScore = cur.score; bestEval = cur; }
+      if (bestScore > 0) return;
+      left[k]--;
+    }
+    k = (k + 1) % S;
+  }
+}
+
+/// :612-643: insert into the best species, or found a new one
+void Engine::finishBirth (const uint32_t *w, RepMeta &g, Species *best, float bestScore, const Eval &bestEval,
+                          const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced) {
+  if (bestScore > 0) {
+    slot = insertInto(w, g, best, bestEval, true, replaced);
+    updateContributions(best, contrib);
+    sid = best->sid;
+  } else {
+    Species *sub = makeNode(contrib);                       // simpleNewSpecies, :637-643
+    Eval none;
+    slot = insertInto(w, g, sub, none, false, replaced);
+    sid = sub->sid;
+  }
+  insertions_++;
+}
+
+// One birth on the host, in order: public addGenome (:268-302) + private addGenome (:553-650) +
 // findBestDerived (:493-548) + updateSpeciesContents (:730-738).
 void Engine::walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uint32_t &sid, int32_t &slot,
                       uint32_t &replaced) {
@@ -530,7 +605,7 @@ void Engine::walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uin
   if (s0->pending > 0) s0->pending--;
   if (s1 && s1->pending > 0) s1->pending--;
 
-  Eval ev0, ev1, cur, bestEval;
+  Eval ev0, ev1, bestEval;
   Species *best = nullptr;
   float bestScore = -std::numeric_limits<float>::max();
 
@@ -554,38 +629,73 @@ void Engine::walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uin
   }
   if (best) bestEval = (best == s1 && s1) ? ev1 : ev0;
 
-  if (!(bestScore > 0)) {
-    // findBestDerived (:493-548): direct sub-species, newest first, alternating between the lists
-    Species *lists[2] = { s0, s1 };
-    const uint32_t S = s1 ? 2 : 1;
-    size_t left[2] = { s0->children.size(), s1 ? s1->children.size() : 0 };
-    uint32_t done = 0;
-    const uint32_t allDone = (1u << S) - 1;
-    uint32_t k = 0;
-    while (done != allDone) {
-      if (left[k] == 0) done |= (1u << k);
-      else {
-        branching_++;
-        Species *sub = lists[k]->children[left[k] - 1];
-        evalSpeculated(w, g, sub, -1, cur);
-        if (bestScore < cur.score) { best = sub; bestScore = cur.score; bestEval = cur; }
-        if (bestScore > 0) break;
-        left[k]--;
-      }
-      k = (k + 1) % S;
-    }
-  }
+  if (!(bestScore > 0)) resolveBelow(w, g, s0, s1, best, bestScore, bestEval);
+  finishBirth(w, g, best, bestScore, bestEval, contrib, sid, slot, replaced);
+}
 
-  if (bestScore > 0) {
-    slot = insertInto(w, g, best, bestEval, true, replaced);
-    updateContributions(best, contrib);
-    sid = best->sid;
-  } else {
-    Species *sub = makeNode(contrib);                       // simpleNewSpecies, :637-643
-    Eval none;
-    slot = insertInto(w, g, sub, none, false, replaced);
-    sid = sub->sid;
+/// Contributors::update (speciescontributors.cpp:15-65) for the commonest case, a species
+/// contributing `count` to ITSELF: its own entry is never eligible (:186-187), so moving it cannot
+/// change the major contributor; stable_sort after one increment = bubble past strictly smaller counts.
+void Engine::selfContribution (Species *s, uint32_t count) {
+  auto &v = s->contribs;
+  size_t i = 0;
+  while (i < v.size() && v[i].sid != s->sid) i++;
+  if (i == v.size()) { updateContributions(s, { { s->sid, count } }); return; }
+  v[i].count += count;
+  while (i > 0 && v[i - 1].count < v[i].count) { std::swap(v[i - 1], v[i]); i--; }
+}
+
+// One birth whose top-level decision was taken by the device (resolve_streams_kernel): the host
+// mirrors the decision into the tree (counters, representative metadata, distance rows,
+// contributions, events), exactly as insertInto (:657-726) + updateContributions (:741-769) would.
+void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t act, uint32_t &sid, int32_t &slot,
+                         uint32_t &replaced) {
+  if (s0->pending > 0) s0->pending--;
+  touchSnap(s0);
+  comparisons_ += s0->k;
+  const uint32_t code = act & ACT_CODE_MASK;
+  if (code == ACT_FALLTHROUGH) {
+    Species *best = nullptr;
+    Eval bestEval;
+    float bestScore = 0.f;          // any value <= 0: the actual top-level score only matters by its sign (:612, :534)
+    resolveBelow(w, g, s0, nullptr, best, bestScore, bestEval);
+    Contributions contrib { { g.msid, 1u + (g.msid == g.fsid) } };
+    finishBirth(w, g, best, bestScore, bestEval, contrib, sid, slot, replaced);
+    return;
   }
+  counters[1]++;
+  slot = -1;  replaced = INV;
+  if (code == ACT_ENTERED) {
+    const uint32_t r = (act >> ACT_SLOT_SHIFT) & 31u, k = s0->k;
+    const float *d = hRows_.p + size_t(act >> ACT_ROW_SHIFT) * K_;
+    RepMeta m = g;
+    m.timestamp = step_;
+    if (act & ACT_REPLACED) {
+      const uint32_t epId = s0->reps[r].gid;
+      emit(APT_EV_LEAVES_ENVELOPPE, s0->sid, epId, 0);
+      emit(APT_EV_ENTERS_ENVELOPPE, s0->sid, g.gid, 0);
+      m.udata = epId;                                       // :710
+      replaced = epId;
+    } else {
+      if (r != k) throw ApiError(APT_ERR_STATE, "device/host enveloppe fill mismatch");
+      emit(APT_EV_ENTERS_ENVELOPPE, s0->sid, g.gid, 0);
+      m.udata = g.gid;
+      s0->k = k + 1;
+    }
+    s0->reps[r] = m;
+    memcpy(&hPayload_[(size_t(s0->slot) * K_ + r) * wp_], w, W_ * sizeof(uint32_t));
+    for (uint32_t i = 0; i < k; i++)
+      if (i != r) s0->dist[i * K_ + r] = s0->dist[r * K_ + i] = d[i];
+    s0->snap_mask |= (1u << r);
+    s0->dev_fill = s0->k;                                   // the kernel wrote the same change to the pool
+    slot = int32_t(r);
+  }
+  s0->count++;
+  s0->alive++;
+  s0->last = step_;
+  if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));
+  // (a primordial birth contributes (INVALID, 2), which Contributors::update discards, :27-28)
+  sid = s0->sid;
   insertions_++;
 }
 
@@ -610,59 +720,76 @@ void Engine::uploadLut (void) {
   lutUploaded_ = uint32_t(classes_.size());
 }
 
-/// Brings the device pool up to date with the host state: only rows that changed are staged
-/// (pinned) and scattered by one kernel.
+/// Brings the device pool up to date with the host state: only what changed is staged (pinned)
+/// and scattered by three small kernels (rows+metadata, distance matrices, fills).
 void Engine::refreshPool (void) {
   const double t0 = now();
   dPool_.reserve(size_t(nSlots_) * K_ * wp_, true, stream_);
   dMeta_.reserve(size_t(nSlots_) * K_, true, stream_);
+  dPoolDist_.reserve(size_t(nSlots_) * K_ * K_, true, stream_);
   const size_t oldFillCap = dFill_.cap;
   dFill_.reserve(nSlots_, true, stream_);
   if (dFill_.cap != oldFillCap)
     cudaCheck(cudaMemsetAsync(dFill_.p + oldFillCap, 0, (dFill_.cap - oldFillCap) * sizeof(uint32_t), stream_),
               "fill clear");
 
-  size_t rows = 0;
-  for (Species *s: refresh_) rows += __builtin_popcount(s->stale_mask);
-  hStageRows_.reserve(rows * wp_ + 4);  hStageMeta_.reserve(rows + 1);
-  hStageDst_.reserve(rows + fillUpdates_.size() + 2 * refresh_.size() + 2);
-  size_t i = 0;
+  size_t rows = 0, mats = 0;
+  for (Species *s: refresh_) {
+    if (s->trimmed) continue;
+    if (s->full_upload) s->stale_mask = s->k >= 32 ? 0xFFFFFFFFu : ((1u << s->k) - 1u);
+    rows += __builtin_popcount(s->stale_mask);
+    mats++;
+  }
+  const size_t KK = size_t(K_) * K_;
+  hStageRows_.reserve(rows * wp_ + 4);  hStageMeta_.reserve(rows + 1);  hStageDist_.reserve(mats * KK + 1);
+  hStageDst_.reserve(rows + mats + fillUpdates_.size() + 2 * refresh_.size() + 4);
+  size_t i = 0, m = 0;
+  std::vector<uint32_t> matSlots;
   for (Species *s: refresh_) {
     s->queued = false;
     if (s->trimmed) continue;
     for (uint32_t r = 0; r < s->k; r++) {
       if (!((s->stale_mask >> r) & 1u)) continue;
       memcpy(hStageRows_.p + i * wp_, repPayload(s, r), wp_ * sizeof(uint32_t));
-      const RepMeta &m = s->reps[r];
-      float cls;  memcpy(&cls, &m.cls, 4);
-      hStageMeta_.p[i] = make_float4(m.mu, m.sin, m.sout, cls);
+      const RepMeta &mm = s->reps[r];
+      float cls;  memcpy(&cls, &mm.cls, 4);
+      hStageMeta_.p[i] = make_float4(mm.mu, mm.sin, mm.sout, cls);
       hStageDst_.p[i] = s->slot * K_ + r;
       i++;
     }
+    memcpy(hStageDist_.p + m * KK, s->dist.data(), KK * sizeof(float));
+    matSlots.push_back(s->slot);
+    m++;
     s->stale_mask = 0;
+    s->full_upload = false;
     s->dev_fill = s->k;
     fillUpdates_.push_back(s->slot);  fillUpdates_.push_back(s->k);
   }
   refresh_.clear();
-  rows = i;
+  rows = i;  mats = m;
   counters[10] += rows;
   const size_t nFill = fillUpdates_.size() / 2;
-  // fill updates ride behind the row destinations in the same pinned buffer: [rows dst][slot...][fill...]
+  // destinations share one pinned buffer: [row dst][matrix slots][fill slots][fill values]
+  for (size_t j = 0; j < mats; j++) hStageDst_.p[rows + j] = matSlots[j];
   for (size_t j = 0; j < nFill; j++) {
-    hStageDst_.p[rows + j] = fillUpdates_[2 * j];
-    hStageDst_.p[rows + nFill + j] = fillUpdates_[2 * j + 1];
+    hStageDst_.p[rows + mats + j] = fillUpdates_[2 * j];
+    hStageDst_.p[rows + mats + nFill + j] = fillUpdates_[2 * j + 1];
   }
   fillUpdates_.clear();
-  if (rows || nFill) {
-    dStageRows_.reserve(rows * wp_ + 4);  dStageMeta_.reserve(rows + 1);  dStageDst_.reserve(rows + 2 * nFill + 2);
+  if (rows || mats || nFill) {
+    dStageRows_.reserve(rows * wp_ + 4);  dStageMeta_.reserve(rows + 1);  dStageDist_.reserve(mats * KK + 1);
+    dStageDst_.reserve(rows + mats + 2 * nFill + 4);
     if (rows) {
       cudaCheck(cudaMemcpyAsync(dStageRows_.p, hStageRows_.p, rows * wp_ * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_), "stage rows");
       cudaCheck(cudaMemcpyAsync(dStageMeta_.p, hStageMeta_.p, rows * sizeof(float4), cudaMemcpyHostToDevice, stream_), "stage meta");
     }
-    cudaCheck(cudaMemcpyAsync(dStageDst_.p, hStageDst_.p, (rows + 2 * nFill) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_), "stage dst");
+    if (mats)
+      cudaCheck(cudaMemcpyAsync(dStageDist_.p, hStageDist_.p, mats * KK * sizeof(float), cudaMemcpyHostToDevice, stream_), "stage dist");
+    cudaCheck(cudaMemcpyAsync(dStageDst_.p, hStageDst_.p, (rows + mats + 2 * nFill) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_), "stage dst");
     launch_scatter_rows(dStageRows_.p, dStageMeta_.p, dStageDst_.p, uint32_t(rows), wp_, dPool_.p, dMeta_.p, stream_);
-    launch_scatter_u32(dStageDst_.p + rows, dStageDst_.p + rows + nFill, uint32_t(nFill), dFill_.p, stream_);
-    counters[4] += (rows ? 1 : 0) + (nFill ? 1 : 0);
+    launch_scatter_blocks_f32(dStageDist_.p, dStageDst_.p + rows, uint32_t(mats), uint32_t(KK), dPoolDist_.p, stream_);
+    launch_scatter_u32(dStageDst_.p + rows + mats, dStageDst_.p + rows + mats + nFill, uint32_t(nFill), dFill_.p, stream_);
+    counters[4] += (rows ? 1 : 0) + (mats ? 1 : 0) + (nFill ? 1 : 0);
     // the pinned staging buffers are rewritten by the next refresh: wait for the copies
     cudaCheck(cudaStreamSynchronize(stream_), "pool refresh");
   }
@@ -674,12 +801,16 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
                        const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
                        uint32_t *outReplaced, uint32_t &done) {
   double t0 = now();
-  // ---- prepare: classes, candidate pairs ----
+  chunkEpoch_++;
+  // ---- prepare: classes; births with a single parent species join that species' stream, the
+  //      others get (birth, species) pairs for the speculative scoring kernel ----
   hCls_.reserve(n);
   hBMeta_.reserve(n);
   pair0_.assign(n, -1);  pair1_.assign(n, -1);
+  birthGroup_.assign(n, -1);
+  grpSpecies_.clear();  grpCount_.clear();
   hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
-  size_t P = 0;
+  size_t P = 0, nStream = 0;
   touchEpoch_++;
   auto touch = [&] (Species *s) {
     if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
@@ -697,18 +828,37 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (m == INV && f == INV) s0 = root_;
     else if (f == INV || m == f) s0 = lookup(m);
     else { s0 = lookup(m); s1 = lookup(f); }
+    if (streamOk_ && s0 && !s1 && s0->dev_fill) {
+      if (s0->grp_epoch != chunkEpoch_) {
+        s0->grp_epoch = chunkEpoch_;
+        s0->grp_index = uint32_t(grpSpecies_.size());
+        grpSpecies_.push_back(s0);  grpCount_.push_back(0);
+      }
+      grpCount_[s0->grp_index]++;
+      birthGroup_[i] = int32_t(s0->grp_index);
+      nStream++;
+      touch(s0);
+      continue;
+    }
     if (s0 && s0->dev_fill) { pair0_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
     if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
+  }
+  const uint32_t G = uint32_t(grpSpecies_.size());
+  if (G) {
+    hGrpSlot_.reserve(G);  hGrpOff_.reserve(G + 1);  hOrder_.reserve(nStream);
+    uint32_t off = 0;
+    for (uint32_t g = 0; g < G; g++) { hGrpSlot_.p[g] = grpSpecies_[g]->slot; hGrpOff_.p[g] = off; off += grpCount_[g]; grpCount_[g] = 0; }
+    hGrpOff_.p[G] = off;
+    for (uint32_t i = 0; i < n; i++)
+      if (birthGroup_[i] >= 0) { const uint32_t g = uint32_t(birthGroup_[i]); hOrder_.p[hGrpOff_.p[g] + grpCount_[g]++] = i; }
   }
   uploadLut();
   timers[0] += now() - t0;
   t0 = now();
 
-  // ---- device: speculative scores of every (birth, parent species) pair ----
-  if (P) {
+  // ---- device ----
+  if (P || G) {
     dBirths_.reserve(size_t(n) * wp_);  dBMeta_.reserve(n);
-    dPairBirth_.reserve(P);  dPairSlot_.reserve(P);  dScore_.reserve(P);  dDist_.reserve(P * K_);
-    hScore_.reserve(P);  hDist_.reserve(P * K_);
     if (dPayload) {
       dCls_.reserve(n);
       cudaCheck(cudaMemcpyAsync(dCls_.p, hCls_.p, size_t(n) * 4, cudaMemcpyHostToDevice, stream_), "classes");
@@ -727,6 +877,11 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       cudaCheck(cudaMemcpyAsync(dBMeta_.p, hBMeta_.p, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, stream_), "birth meta");
     }
+  }
+  if (P) {
+    // speculative scores of every (birth, parent species) pair of the two-parent births
+    dPairBirth_.reserve(P);  dPairSlot_.reserve(P);  dScore_.reserve(P);  dDist_.reserve(P * K_);
+    hScore_.reserve(P);  hDist_.reserve(P * K_);
     cudaCheck(cudaMemcpyAsync(dPairBirth_.p, hPairBirth_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
     cudaCheck(cudaMemcpyAsync(dPairSlot_.p, hPairSlot_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
     cudaCheck(cudaEventRecord(evK0_, stream_), "event record");
@@ -737,23 +892,71 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaGetLastError(), "score_pairs launch");
     cudaCheck(cudaMemcpyAsync(hScore_.p, dScore_.p, P * 4, cudaMemcpyDeviceToHost, stream_), "scores");
     cudaCheck(cudaMemcpyAsync(hDist_.p, dDist_.p, P * K_ * 4, cudaMemcpyDeviceToHost, stream_), "distances");
-    cudaCheck(cudaStreamSynchronize(stream_), "score_pairs");
-    float ms = 0.f;
-    cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed");
-    timers[4] += ms;
     counters[7] += P;
+  }
+  uint32_t nRows = 0;
+  if (G) {
+    // the ordered resolution of the single-parent births, one warp per species stream; it runs
+    // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
+    dOrder_.reserve(nStream);  dGrpSlot_.reserve(G);  dGrpOff_.reserve(G + 1);  dAct_.reserve(n);
+    dRowCounter_.reserve(1);  dRows_.reserve(size_t(nStream) * K_);
+    hAct_.reserve(n);  hRowCounter_.reserve(1);
+    cudaCheck(cudaMemcpyAsync(dOrder_.p, hOrder_.p, nStream * 4, cudaMemcpyHostToDevice, stream_), "order");
+    cudaCheck(cudaMemcpyAsync(dGrpSlot_.p, hGrpSlot_.p, G * 4, cudaMemcpyHostToDevice, stream_), "groups");
+    cudaCheck(cudaMemcpyAsync(dGrpOff_.p, hGrpOff_.p, (G + 1) * 4, cudaMemcpyHostToDevice, stream_), "groups");
+    cudaCheck(cudaMemsetAsync(dAct_.p, 0, size_t(n) * 4, stream_), "act clear");
+    cudaCheck(cudaMemsetAsync(dRowCounter_.p, 0, 4, stream_), "row counter clear");
+    StreamArgs a;
+    a.pool = poolView();
+    a.pool_payload_w = dPool_.p;  a.pool_cmeta_w = dMeta_.p;  a.pool_fill_w = dFill_.p;  a.pool_dist = dPoolDist_.p;
+    a.cfg = scoreCfg();  a.crit = p_.env_crit;  a.guard = GUARD;
+    a.b_payload = dBirths_.p;  a.b_cmeta = dBMeta_.p;
+    a.n_groups = G;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
+    a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dRowCounter_.p;
+    cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
+    launch_resolve_streams(a, stream_);
+    cudaCheck(cudaEventRecord(evS1_, stream_), "event record");
+    counters[4]++;  counters[12]++;  counters[13] += nStream;
+    cudaCheck(cudaGetLastError(), "resolve_streams launch");
+    cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
+    cudaCheck(cudaMemcpyAsync(hRowCounter_.p, dRowCounter_.p, 4, cudaMemcpyDeviceToHost, stream_), "row counter");
+  }
+  if (P || G) {
+    cudaCheck(cudaStreamSynchronize(stream_), "device pass");
+    float ms = 0.f;
+    if (P) { cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed"); timers[4] += ms; }
+    if (G) {
+      cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
+      nRows = hRowCounter_.p[0];
+      if (nRows) {
+        hRows_.reserve(size_t(nRows) * K_);
+        cudaCheck(cudaMemcpyAsync(hRows_.p, dRows_.p, size_t(nRows) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "rows");
+        cudaCheck(cudaStreamSynchronize(stream_), "rows");
+      }
+      counters[14] += nRows;
+    }
   }
   timers[1] += now() - t0;
   t0 = now();
 
-  // ---- host: ordered resolution ----
+  // ---- host: ordered walk (device-resolved births are mirrored, the others resolved here) ----
   curPayload_ = payload;
   for (uint32_t i = 0; i < n; i++) {
     RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, hCls_.p[i],
                 compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
     uint32_t sid = INV, replaced = INV;
     int32_t slot = -1;
-    walkOne(payload + size_t(i) * W_, g, pair0_[i], pair1_[i], sid, slot, replaced);
+    const uint32_t *w = payload + size_t(i) * W_;
+    bool viaStream = false;
+    if (birthGroup_[i] >= 0) {
+      Species *s0 = grpSpecies_[size_t(birthGroup_[i])];
+      if (s0->div_epoch != chunkEpoch_) {
+        const uint32_t act = hAct_.p[i];
+        if ((act & ACT_UNCERTAIN) || (act & ACT_CODE_MASK) == ACT_UNPROCESSED) diverge(s0);
+        else { walkStream(w, g, s0, act, sid, slot, replaced); viaStream = true; }
+      }
+    }
+    if (!viaStream) walkOne(w, g, pair0_[i], pair1_[i], sid, slot, replaced);
     if (outSid) outSid[i] = sid;
     if (outSlot) outSlot[i] = slot;
     if (outReplaced) outReplaced[i] = replaced;

@@ -105,6 +105,11 @@ struct Species {
   bool queued = false;                    // already in the refresh list
   bool trimmed = false;                   // removed by stillborn trimming
   uint32_t cand_epoch = 0, cand_rank = 0; // position in the current group's candidate list (K2)
+  // per-chunk state (valid when the epoch field equals the engine's chunk epoch)
+  uint32_t grp_epoch = 0, grp_index = 0;  // this species has a device-resolved stream in the current chunk
+  uint32_t div_epoch = 0;                 // ... and the host took that stream over (device results discarded)
+  uint32_t snap_epoch = 0, snap_mask = 0, snap_fill = 0;  // slots changed since the chunk's device snapshot
+  bool full_upload = false;               // the device copy (rows, matrix, fill) must be rewritten entirely
   uint32_t touch_epoch = 0;               // last scoring launch that read this enveloppe
   bool extinct (void) const { return alive == 0 && pending == 0; }   // node.hpp:157-159
 };
@@ -180,6 +185,14 @@ private:
   DevBuf<uint32_t> dBirths_, dRaw_;  DevBuf<float4> dBMeta_;  DevBuf<float> dRawCompat_;  DevBuf<uint32_t> dCls_;
   DevBuf<uint32_t> dPairBirth_, dPairSlot_;  DevBuf<float> dScore_, dDist_;
   DevBuf<uint32_t> dStageRows_, dStageDst_;  DevBuf<float4> dStageMeta_;
+  DevBuf<float> dPoolDist_, dStageDist_, dRows_;  DevBuf<uint32_t> dOrder_, dGrpSlot_, dGrpOff_, dAct_, dRowCounter_;
+  PinBuf<float> hStageDist_, hRows_;  PinBuf<uint32_t> hOrder_, hGrpSlot_, hGrpOff_, hAct_, hRowCounter_;
+  std::vector<int32_t> birthGroup_;       // stream index of each birth of the chunk, -1 = host/K1 path
+  std::vector<Species*> grpSpecies_;
+  std::vector<uint32_t> grpCount_;
+  uint32_t chunkEpoch_ = 0;
+  bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
+  cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
   PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
   PinBuf<float4> hBMeta_, hStageMeta_;
   PinBuf<float> hScore_, hDist_;
@@ -214,6 +227,14 @@ private:
   int32_t insertInto (const uint32_t *w, const RepMeta &g, Species *s, const Eval &e, bool haveCache, uint32_t &replaced);
   void walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uint32_t &sid, int32_t &slot, uint32_t &replaced);
   void markStale (Species *s, uint32_t r);
+  void touchSnap (Species *s);
+  void diverge (Species *s);
+  void queueRefresh (Species *s) { if (!s->queued) { s->queued = true; refresh_.push_back(s); } }
+  void walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t act, uint32_t &sid, int32_t &slot, uint32_t &replaced);
+  void resolveBelow (const uint32_t *w, const RepMeta &g, Species *s0, Species *s1, Species *&best, float &bestScore, Eval &bestEval);
+  void finishBirth (const uint32_t *w, RepMeta &g, Species *best, float bestScore, const Eval &bestEval,
+                    const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced);
+  void selfContribution (Species *s, uint32_t count);
 
   // device plumbing
   uint32_t allocSlot (void);

@@ -236,6 +236,12 @@ __global__ void scatter_u32_kernel (const uint32_t *__restrict__ idx, const uint
   if (i < n) dst[idx[i]] = val[i];
 }
 
+__global__ void scatter_blocks_f32_kernel (const float *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n,
+                                           uint32_t len, float *__restrict__ dst) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < size_t(n) * len) dst[size_t(idx[t / len]) * len + t % len] = src[t];
+}
+
 int lanes_per_rep (uint32_t wp) {
   uint32_t q = wp >> 2, l = 1;
   while (l < q && l < 32) l <<= 1;
@@ -312,6 +318,13 @@ void launch_scatter_rows (const uint32_t *stage_payload, const float4 *stage_cme
 void launch_scatter_u32 (const uint32_t *idx, const uint32_t *val, uint32_t n, uint32_t *dst, cudaStream_t stream) {
   if (!n) return;
   scatter_u32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(idx, val, n, dst);
+}
+
+void launch_scatter_blocks_f32 (const float *src, const uint32_t *idx, uint32_t n, uint32_t len, float *dst,
+                                cudaStream_t stream) {
+  if (!n) return;
+  const size_t total = size_t(n) * len;
+  scatter_blocks_f32_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src, idx, n, len, dst);
 }
 
 void launch_env_contribution (int crit, uint32_t K, uint32_t n, const float *edist, const float *gdist,

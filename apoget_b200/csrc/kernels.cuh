@@ -62,6 +62,43 @@ void launch_env_contribution (int crit, uint32_t K, uint32_t n, const float *edi
 void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n_pairs,
                       const uint32_t *idx_a, const uint32_t *idx_b, float *out, cudaStream_t stream);
 
+/// Per-birth result word of the stream kernel
+enum : uint32_t {
+  ACT_UNPROCESSED = 0u,       ///< the warp stopped before this birth (host takes over)
+  ACT_FALLTHROUGH = 1u,       ///< score <= 0 at top level: the host walks the sub-species
+  ACT_ACCEPTED = 2u,          ///< accepted, enveloppe unchanged
+  ACT_ENTERED = 3u,           ///< accepted and now a representative
+  ACT_CODE_MASK = 3u,
+  ACT_REPLACED = 4u,          ///< (with ACT_ENTERED) took the place of an older representative
+  ACT_UNCERTAIN = 8u,         ///< decision needs exact arithmetic (guard band): host takes over from here
+  ACT_SLOT_SHIFT = 4u,        ///< 5 bits: enveloppe slot
+  ACT_ROW_SHIFT = 9u          ///< 23 bits: index of the birth's distance row in `rows`
+};
+
+/// Arguments of resolve_streams_kernel (stream.cu): one warp per species stream.
+struct StreamArgs {
+  PoolView pool;              ///< state at submission; the kernel writes the final state back through:
+  uint32_t *pool_payload_w;  float4 *pool_cmeta_w;  uint32_t *pool_fill_w;
+  float *pool_dist;           ///< [slot][K][K] intra-enveloppe distances (DistanceMap, treetypes.h:259)
+  ScoreCfg cfg;
+  int crit;                   ///< 0 maxAverage, 1 maxMinDist
+  float guard;                ///< |score| below which a non-table score is not trusted
+  const uint32_t *b_payload;  const float4 *b_cmeta;
+  uint32_t n_groups;
+  const uint32_t *grp_slot;   ///< [n_groups] pool slot of the stream's species
+  const uint32_t *grp_off;    ///< [n_groups+1] offsets into order
+  const uint32_t *order;      ///< birth indices grouped by stream, arrival order inside a stream
+  uint32_t *act;              ///< [n_births] result words (zero-initialised by the caller)
+  float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
+  uint32_t *row_counter;      ///< zero-initialised
+};
+bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
+void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream);
+
+/// dst[idx[i]*len .. +len) = src[i*len .. +len)
+void launch_scatter_blocks_f32 (const float *src, const uint32_t *idx, uint32_t n, uint32_t len, float *dst,
+                                cudaStream_t stream);
+
 /// Dense sweep (every birth x every species), fused score / threshold / argmax.
 void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg,
                             const uint32_t *b_payload, const float4 *b_cmeta, uint32_t n_births,

@@ -1,0 +1,317 @@
+// resolve_streams_kernel -- the ordered resolution pass on the device.
+//
+// A "stream" is the ordered list of the births of one batch whose only top-level candidate is one
+// given species (no second parent species).  For those births the reference's sequential
+// addGenome (phylogenetictree.hpp:268-302, 553-650) reads and writes nothing but that species'
+// enveloppe as long as the birth is accepted at top level (:612-613) -- so streams of different
+// species are independent, and one warp owns one stream:
+//
+//   * the enveloppe (representatives, compat metadata, K x K distance matrix, per-row minima)
+//     lives in shared memory for the whole stream;
+//   * 32 births are scored at once, one lane per birth (:456-478 / :430-452), each lane keeping
+//     its k distances and compatibilities in shared memory;
+//   * in-chunk dependencies are then resolved exactly: every lane decides under the current
+//     state (accept :612; append :668-677 or criterion enveloppecriteria.cpp:87-133); the FIRST
+//     lane (= earliest birth) whose decision changes the enveloppe commits -- all earlier lanes are
+//     final -- and the later lanes re-measure only the slot that changed and re-sum their score in
+//     the reference's order.  Repeat until the chunk is final.
+//
+// Births rejected at top level (score <= 0) do not touch the enveloppe; they are flagged and the
+// host walks the sub-species for them (:623).  When a decision cannot be taken with
+// reference-identical arithmetic (device exp() inside the guard band) the warp stops and hands the
+// rest of the stream to the host.  At the end the warp writes the enveloppe back to the pool.
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace apt {
+
+namespace {
+
+constexpr int SWARPS = 4;                 // warps (streams) per CTA
+constexpr float FMAX = 3.402823466e+38f;  // std::numeric_limits<float>::max()
+
+__device__ __forceinline__ uint32_t popc4 (uint4 a, uint4 b) {
+  return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+}
+
+__device__ __forceinline__ double sqdiff4 (uint4 a, uint4 b) {
+  double t0 = double(__uint_as_float(a.x)) - double(__uint_as_float(b.x));
+  double t1 = double(__uint_as_float(a.y)) - double(__uint_as_float(b.y));
+  double t2 = double(__uint_as_float(a.z)) - double(__uint_as_float(b.z));
+  double t3 = double(__uint_as_float(a.w)) - double(__uint_as_float(b.w));
+  return t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+}
+
+__device__ __forceinline__ double compat_generic (float4 m, double d) {     // crossover.h:89-92
+  const double mu = double(m.x);
+  const double s = d < mu ? double(m.y) : double(m.z);
+  const double t = d - mu;
+  return exp(-(t * t) / (2. * s * s));
+}
+
+template <bool LUT>
+__device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, float4 bm, float4 rm, double d) {
+  double a, b;
+  if (LUT) {
+    const uint32_t di = uint32_t(d);
+    a = __ldg(cfg.lut + size_t(__float_as_uint(bm.w)) * cfg.lut_stride + di);
+    b = __ldg(cfg.lut + size_t(__float_as_uint(rm.w)) * cfg.lut_stride + di);
+  } else {
+    a = compat_generic(bm, d);
+    b = compat_generic(rm, d);
+  }
+  return b < a ? b : a;
+}
+
+/// Per-warp view of its slice of dynamic shared memory
+struct WarpState {
+  uint4 *reps;        // [K][WQ]
+  float4 *rmeta;      // [K]
+  float *D;           // [K][K]
+  float *minBase;     // [K]
+  float *d;           // [K][32]   distances of lane l to representative r at d[r*32 + l]
+  double *c;          // [K][32]   compatibilities
+};
+
+/// distance + compatibility of this lane's birth to representative r, stored in the lane's column
+template <int WQ, int KIND, bool LUT>
+__device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
+                                         const WarpState &ws, uint32_t r, int lane) {
+  double d;
+  if (KIND == 0) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int v = 0; v < WQ; v++) acc += popc4(bw[v], ws.reps[r * WQ + v]);
+    d = double(acc);
+  } else {
+    double acc = 0.;
+#pragma unroll
+    for (int v = 0; v < WQ; v++) acc += sqdiff4(bw[v], ws.reps[r * WQ + v]);
+    d = sqrt(acc);
+  }
+  ws.d[r * 32 + lane] = float(d);
+  ws.c[r * 32 + lane] = pair_compat<LUT>(cfg, bm, ws.rmeta[r], d);
+}
+
+/// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities
+__device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws, uint32_t k, int lane) {
+  if (cfg.full_continuous) {
+    float avg = 0.f;
+    for (uint32_t r = 0; r < k; r++) avg = float(__dadd_rn(double(avg), ws.c[r * 32 + lane]));
+    return float(__dsub_rn(double(__fdiv_rn(avg, float(k))), cfg.avg_thr));
+  }
+  uint32_t matable = 0;
+  for (uint32_t r = 0; r < k; r++) matable += (ws.c[r * 32 + lane] >= cfg.compat_thr);
+  return float(__dsub_rn(double(matable), __dmul_rn(cfg.sim_thr, double(k))));
+}
+
+/// maxMinDist (enveloppecriteria.cpp:87-133) for this lane's distances against a FULL enveloppe
+__device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, uint32_t K, int lane, uint32_t &than) {
+  float m1 = FMAX, m2 = FMAX;
+  uint32_t i1 = 0xFFFFFFFFu;
+  for (uint32_t r = 0; r < K; r++) {
+    const float x = ws.d[r * 32 + lane];
+    if (x < m1) { m2 = m1; m1 = x; i1 = r; }
+    else if (x < m2) m2 = x;
+  }
+  float value = -CUDART_INF_F;
+  than = 0xFFFFFFFFu;
+  for (uint32_t i = 0; i < K; i++) {
+    const float minNew = (i == i1) ? m2 : m1;                    // min over j != i of gdist[j]
+    const double c = double(__fadd_rn(-ws.minBase[i], minNew));  // :117
+    if (double(value) < c) { value = float(c); than = i; }      // :125-128, first index wins ties
+  }
+  return value > 0.f;                                            // :131
+}
+
+/// maxAverage (enveloppecriteria.cpp:40-84)
+__device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, uint32_t K, int lane, uint32_t &than) {
+  float value = -CUDART_INF_F;
+  than = 0xFFFFFFFFu;
+  for (uint32_t i = 0; i < K; i++) {
+    double c = 0.;
+    for (uint32_t j = 0; j < K; j++) {
+      if (i == j) continue;
+      c = __dadd_rn(c, double(__fadd_rn(-ws.D[i * K + j], ws.d[j * 32 + lane])));   // :62
+    }
+    if (double(value) < c) { value = float(c); than = i; }
+  }
+  return value > 0.f;
+}
+
+template <int WQ, int KIND, bool LUT>
+__global__ void __launch_bounds__(SWARPS * 32)
+resolve_streams_kernel (StreamArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * SWARPS + warp;
+  if (g >= a.n_groups) return;
+
+  const uint32_t K = a.pool.K;
+  // carve this warp's slice: doubles first (8-byte aligned), then 16-byte items, then floats
+  const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * WQ * 16 + size_t(K) * 16 + size_t(K) * K * 4
+                       + size_t(K) * 4 + size_t(K) * 32 * 4;
+  unsigned char *base = smem + ((perWarp + 15) & ~size_t(15)) * warp;
+  WarpState ws;
+  ws.c = reinterpret_cast<double*>(base);            base += size_t(K) * 32 * 8;
+  ws.reps = reinterpret_cast<uint4*>(base);          base += size_t(K) * WQ * 16;
+  ws.rmeta = reinterpret_cast<float4*>(base);        base += size_t(K) * 16;
+  ws.D = reinterpret_cast<float*>(base);             base += size_t(K) * K * 4;
+  ws.minBase = reinterpret_cast<float*>(base);       base += size_t(K) * 4;
+  ws.d = reinterpret_cast<float*>(base);
+
+  const uint32_t slot = a.grp_slot[g];
+  const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
+  uint32_t k = min(a.pool.fill[slot], K);
+  const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
+
+  // ---- load the enveloppe ----
+  for (uint32_t i = lane; i < k * WQ; i += 32) ws.reps[i] = poolRows[i];
+  for (uint32_t i = lane; i < k; i += 32) ws.rmeta[i] = a.pool.cmeta[size_t(slot) * K + i];
+  for (uint32_t i = lane; i < K * K; i += 32) ws.D[i] = a.pool_dist[size_t(slot) * K * K + i];
+  __syncwarp();
+  auto refreshMinBase = [&] (void) {
+    for (uint32_t r = lane; r < k; r += 32) {
+      float m = FMAX;
+      for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, ws.D[r * K + j]);
+      ws.minBase[r] = m;
+    }
+    __syncwarp();
+  };
+  refreshMinBase();
+
+  uint32_t changed = 0;         // slots to write back
+  bool aborted = false;
+
+  for (uint32_t cb = g0; cb < g1 && !aborted; cb += 32) {
+    const uint32_t nb = min(32u, g1 - cb);
+    const bool active = uint32_t(lane) < nb;
+    const uint32_t b = active ? a.order[cb + lane] : 0u;
+    uint4 bw[WQ];
+    float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
+    if (active) {
+      const uint4 *bq = reinterpret_cast<const uint4*>(a.b_payload) + size_t(b) * WQ;
+#pragma unroll
+      for (int v = 0; v < WQ; v++) bw[v] = __ldg(bq + v);
+      bm = __ldg(a.b_cmeta + b);
+    } else {
+#pragma unroll
+      for (int v = 0; v < WQ; v++) bw[v] = make_uint4(0, 0, 0, 0);
+    }
+    float score = 0.f;
+    if (active) {
+      for (uint32_t r = 0; r < k; r++) measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, lane);
+      score = resum(a.cfg, ws, k, lane);
+    }
+    uint32_t unresolved = __ballot_sync(0xffffffffu, active);
+
+    while (unresolved) {
+      const bool mine = (unresolved >> lane) & 1u;
+      const bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
+      const bool accept = mine && score > 0.f;
+      bool modifies = false;
+      uint32_t than = 0xFFFFFFFFu;
+      if (accept) {
+        if (k < K) { modifies = true; than = k; }                       // :668-677
+        else if (K > 1)
+          modifies = a.crit == 1 ? criterion_maxMinDist(ws, K, lane, than) : criterion_maxAverage(ws, K, lane, than);
+      }
+      const uint32_t umask = __ballot_sync(0xffffffffu, uncertain);
+      const uint32_t mmask = __ballot_sync(0xffffffffu, modifies);
+      const int firstU = umask ? __ffs(umask) - 1 : 32, firstM = mmask ? __ffs(mmask) - 1 : 32;
+      const int stop = min(firstU, firstM);
+      if (mine && lane < stop) a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
+      if (stop == 32) break;
+      if (firstU <= firstM) {
+        // the decision of this birth needs exact arithmetic: the host takes the stream over from here
+        if (lane == stop) a.act[b] = ACT_UNCERTAIN;
+        aborted = true;
+        break;
+      }
+      // ---- lane `stop` enters the enveloppe at slot `sl` ----
+      const uint32_t sl = __shfl_sync(0xffffffffu, than, stop);
+      const bool append = (k < K);
+      uint32_t row = 0;
+      if (lane == stop) row = atomicAdd(a.row_counter, 1u);
+      row = __shfl_sync(0xffffffffu, row, stop);
+      // its k distances are the new matrix row (and what the host needs to mirror it), :676-677 / :712-715
+      for (uint32_t r = lane; r < k; r += 32) {
+        const float dr = ws.d[r * 32 + stop];
+        a.rows[size_t(row) * K + r] = dr;
+        if (r != sl) { ws.D[r * K + sl] = dr; ws.D[sl * K + r] = dr; }
+      }
+      if (lane == stop) {
+        a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
+#pragma unroll
+        for (int v = 0; v < WQ; v++) ws.reps[sl * WQ + v] = bw[v];
+        ws.rmeta[sl] = bm;
+      }
+      if (append) k++;
+      changed |= 1u << sl;
+      __syncwarp();
+      refreshMinBase();
+      unresolved &= ~((2u << stop) - 1u);
+      // later births see the new representative: re-measure that slot only, re-sum in order
+      if ((unresolved >> lane) & 1u) {
+        measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, sl, lane);
+        score = resum(a.cfg, ws, k, lane);
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+
+  // ---- write the enveloppe back (the host mirrors the same changes from act/rows) ----
+  if (changed && !aborted) {
+    uint4 *outRows = reinterpret_cast<uint4*>(a.pool_payload_w) + size_t(slot) * K * WQ;
+    for (uint32_t r = 0; r < k; r++) {
+      if (!((changed >> r) & 1u)) continue;
+      for (uint32_t v = lane; v < uint32_t(WQ); v += 32) outRows[r * WQ + v] = ws.reps[r * WQ + v];
+      if (lane == 0) a.pool_cmeta_w[size_t(slot) * K + r] = ws.rmeta[r];
+    }
+    for (uint32_t i = lane; i < K * K; i += 32) a.pool_dist[size_t(slot) * K * K + i] = ws.D[i];
+    if (lane == 0) a.pool_fill_w[slot] = k;
+  }
+}
+
+template <int WQ>
+void launchWQ (const StreamArgs &a, cudaStream_t st) {
+  const uint32_t K = a.pool.K;
+  const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * WQ * 16 + size_t(K) * 16 + size_t(K) * K * 4
+                       + size_t(K) * 4 + size_t(K) * 32 * 4;
+  const size_t smem = ((perWarp + 15) & ~size_t(15)) * SWARPS;
+  const uint32_t grid = (a.n_groups + SWARPS - 1) / SWARPS;
+  auto go = [&] (auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    kernel<<<grid, SWARPS * 32, smem, st>>>(a);
+  };
+  if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true>); else go(resolve_streams_kernel<WQ, 0, false>); }
+  else go(resolve_streams_kernel<WQ, 1, false>);
+}
+
+} // namespace
+
+bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit) {
+  const uint32_t wq = wp >> 2;
+  if (!(wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32)) return false;
+  if (crit != 0 && crit != 1) return false;
+  const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4
+                       + size_t(K) * 4 + size_t(K) * 32 * 4;
+  return ((perWarp + 15) & ~size_t(15)) * SWARPS <= size_t(200) << 10;
+}
+
+void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream) {
+  if (!a.n_groups) return;
+  switch (a.pool.wp >> 2) {
+  case 1: launchWQ<1>(a, stream); break;
+  case 2: launchWQ<2>(a, stream); break;
+  case 4: launchWQ<4>(a, stream); break;
+  case 8: launchWQ<8>(a, stream); break;
+  case 16: launchWQ<16>(a, stream); break;
+  case 32: launchWQ<32>(a, stream); break;
+  default: break;     // callers check stream_kernel_supports()
+  }
+}
+
+} // namespace apt

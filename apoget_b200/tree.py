@@ -17,7 +17,7 @@ from ._lib import AptParams, check, lib
 
 INVALID = 0xFFFFFFFF
 BITS, F32 = 0, 1
-FLAG_NO_EVENTS, FLAG_NO_CHILD_KERNEL, FLAG_FORCE_GENERIC = 1, 2, 4
+FLAG_NO_EVENTS, FLAG_NO_CHILD_KERNEL, FLAG_FORCE_GENERIC, FLAG_NO_STREAM_KERNEL = 1, 2, 4, 8
 
 # config::PTree defaults, src/core/ptreeconfig.cpp:7-19
 DEFAULTS = dict(K=5, full_continuous=True, env_crit=1, compat_thr=.1, sim_thr=.5, avg_thr=.25,
@@ -135,13 +135,15 @@ class PhylogeneticTree:
         check(lib().apt_tree_counters(self._h, out.ctypes.data_as(_lib.u64p)))
         keys = ["births", "device_scores", "patched_scores", "host_scores", "kernel_launches",
                 "host_distance_evals", "guard_rechecks", "device_pairs", "device_reps_read",
-                "score_launches", "refresh_rows"]
+                "score_launches", "refresh_rows", "streams_taken_over", "stream_launches", "stream_births",
+                "stream_entries"]
         return dict(zip(keys, (int(x) for x in out)))
 
     def timers(self) -> dict:
         out = np.zeros(8, dtype=np.float64)
         check(lib().apt_tree_timers(self._h, out.ctypes.data_as(_lib.f64p)))
-        return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s", "score_kernel_ms"], (float(x) for x in out)))
+        return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s", "score_kernel_ms", "stream_kernel_ms"],
+                        (float(x) for x in out)))
 
     def node_info(self, sid: int) -> dict:
         info = _lib.AptNodeInfo()

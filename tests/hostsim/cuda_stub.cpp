@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -97,29 +98,6 @@ void launch_score_pairs (const PoolView &pool, const ScoreCfg &cfg, const uint32
     os[p] = score(pool, cfg, bp + size_t(pb[p]) * pool.wp, bm[pb[p]], ps[p], od + size_t(p) * pool.K);
 }
 
-void launch_classify_children (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *bp, const float4 *bm,
-                               uint32_t nItems, const uint32_t *itemBirth, const uint32_t *itemOff,
-                               const uint32_t *candSlot, uint32_t *outFirst, float *outScore, float *outDist,
-                               uint32_t *outMask, uint32_t maskWords, float guard, cudaStream_t) {
-  for (uint32_t i = 0; i < nItems; i++) {
-    const uint32_t b = itemBirth[i], c0 = itemOff[2 * i], nc = itemOff[2 * i + 1];
-    uint32_t first = 0xFFFFFFFFu;
-    for (uint32_t w = 0; w < maskWords; w++) outMask[size_t(i) * maskWords + w] = 0;
-    float d[KMAX];
-    for (uint32_t c = 0; c < nc; c++) {
-      const float s = score(pool, cfg, bp + size_t(b) * pool.wp, bm[b], candSlot[c0 + c], d);
-      const bool sure = cfg.use_lut || std::fabs(s) > guard;
-      if (!sure) outMask[size_t(i) * maskWords + (2 * c + 1) / 32] |= 1u << ((2 * c + 1) % 32);
-      if (s > 0) outMask[size_t(i) * maskWords + (2 * c) / 32] |= 1u << ((2 * c) % 32);
-      if ((s > 0 || !sure) && first == 0xFFFFFFFFu) {
-        first = c;  outScore[i] = s;
-        memcpy(outDist + size_t(i) * pool.K, d, pool.K * sizeof(float));
-      }
-    }
-    outFirst[i] = first;
-  }
-}
-
 void launch_pack_births (const uint32_t *src, const float *compat, const uint32_t *cls, uint32_t n, uint32_t words,
                          uint32_t wp, uint32_t *dst, float4 *meta, cudaStream_t) {
   for (uint32_t i = 0; i < n; i++) {
@@ -140,6 +118,85 @@ void launch_scatter_rows (const uint32_t *sp, const float4 *sm, const uint32_t *
 
 void launch_scatter_u32 (const uint32_t *idx, const uint32_t *val, uint32_t n, uint32_t *dst, cudaStream_t) {
   for (uint32_t i = 0; i < n; i++) dst[idx[i]] = val[i];
+}
+
+void launch_scatter_blocks_f32 (const float *src, const uint32_t *idx, uint32_t n, uint32_t len, float *dst, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) memcpy(dst + size_t(idx[i]) * len, src + size_t(i) * len, len * sizeof(float));
+}
+
+bool stream_kernel_supports (uint32_t wp, uint32_t, int crit) {
+  const uint32_t wq = wp >> 2;
+  return (wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32) && (crit == 0 || crit == 1);
+}
+
+// Plain sequential stand-in for resolve_streams_kernel (same inputs, outputs and write-back)
+void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
+  const uint32_t K = a.pool.K, wp = a.pool.wp;
+  const float FMAX = std::numeric_limits<float>::max();
+  for (uint32_t g = 0; g < a.n_groups; g++) {
+    const uint32_t slot = a.grp_slot[g];
+    uint32_t k = a.pool.fill[slot] < K ? a.pool.fill[slot] : K;
+    std::vector<uint32_t> reps (a.pool.payload + size_t(slot) * K * wp, a.pool.payload + size_t(slot + 1) * K * wp);
+    std::vector<float4> meta (a.pool.cmeta + size_t(slot) * K, a.pool.cmeta + size_t(slot + 1) * K);
+    std::vector<float> D (a.pool_dist + size_t(slot) * K * K, a.pool_dist + size_t(slot + 1) * K * K);
+    uint32_t changed = 0;
+    bool aborted = false;
+    for (uint32_t t = a.grp_off[g]; t < a.grp_off[g + 1]; t++) {
+      const uint32_t b = a.order[t];
+      const uint32_t *bw = a.b_payload + size_t(b) * wp;
+      const float4 bm = a.b_cmeta[b];
+      float d[KMAX];
+      float avg = 0;  uint32_t matable = 0;
+      for (uint32_t r = 0; r < k; r++) {
+        const double dd = dist(a.cfg.kind, wp, bw, &reps[size_t(r) * wp]);
+        const double ca = compat(a.cfg, bm, dd), cb = compat(a.cfg, meta[r], dd), c = cb < ca ? cb : ca;
+        avg += c;  matable += (c >= a.cfg.compat_thr);
+        d[r] = float(dd);
+      }
+      const float score = a.cfg.full_continuous ? float(avg / float(k) - a.cfg.avg_thr) : float(matable - a.cfg.sim_thr * k);
+      if (!a.cfg.use_lut && std::fabs(score) <= a.guard) { a.act[b] = ACT_UNCERTAIN; aborted = true; break; }
+      if (!(score > 0)) { a.act[b] = ACT_FALLTHROUGH; continue; }
+      uint32_t than = 0xFFFFFFFFu;
+      bool modifies = false, append = false;
+      if (k < K) { modifies = append = true; than = k; }
+      else if (K > 1) {
+        float value = -std::numeric_limits<float>::infinity();
+        for (uint32_t i = 0; i < K; i++) {
+          double c;
+          if (a.crit == 1) {
+            float minBase = FMAX, minNew = FMAX;
+            for (uint32_t j = 0; j < K; j++) { if (i == j) continue; minBase = std::min(minBase, D[i * K + j]); minNew = std::min(minNew, d[j]); }
+            c = - minBase + minNew;
+          } else {
+            c = 0;
+            for (uint32_t j = 0; j < K; j++) { if (i == j) continue; c += - D[i * K + j] + d[j]; }
+          }
+          if (value < c) { value = float(c); than = i; }
+        }
+        modifies = value > 0;
+      }
+      if (!modifies) { a.act[b] = ACT_ACCEPTED; continue; }
+      const uint32_t row = (*a.row_counter)++;
+      for (uint32_t r = 0; r < k; r++) {
+        a.rows[size_t(row) * K + r] = d[r];
+        if (r != than) D[r * K + than] = D[than * K + r] = d[r];
+      }
+      memcpy(&reps[size_t(than) * wp], bw, wp * 4);
+      meta[than] = bm;
+      a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (than << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
+      if (append) k++;
+      changed |= 1u << than;
+    }
+    if (changed && !aborted) {
+      for (uint32_t r = 0; r < k; r++) {
+        if (!((changed >> r) & 1u)) continue;
+        memcpy(a.pool_payload_w + (size_t(slot) * K + r) * wp, &reps[size_t(r) * wp], wp * 4);
+        a.pool_cmeta_w[size_t(slot) * K + r] = meta[r];
+      }
+      memcpy(a.pool_dist + size_t(slot) * K * K, D.data(), size_t(K) * K * sizeof(float));
+      a.pool_fill_w[slot] = k;
+    }
+  }
 }
 
 void launch_env_contribution (int, uint32_t, uint32_t, const float*, const float*, uint8_t*, uint32_t*, float*, cudaStream_t) {}
