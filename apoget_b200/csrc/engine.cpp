@@ -638,11 +638,15 @@ void Engine::walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uin
 /// change the major contributor; stable_sort after one increment = bubble past strictly smaller counts.
 void Engine::selfContribution (Species *s, uint32_t count) {
   auto &v = s->contribs;
-  size_t i = 0;
-  while (i < v.size() && v[i].sid != s->sid) i++;
-  if (i == v.size()) { updateContributions(s, { { s->sid, count } }); return; }
+  size_t i = s->self_idx;
+  if (i >= v.size() || v[i].sid != s->sid) {
+    i = 0;
+    while (i < v.size() && v[i].sid != s->sid) i++;
+    if (i == v.size()) { updateContributions(s, { { s->sid, count } }); return; }
+  }
   v[i].count += count;
   while (i > 0 && v[i - 1].count < v[i].count) { std::swap(v[i - 1], v[i]); i--; }
+  s->self_idx = uint32_t(i);
 }
 
 // One birth whose top-level decision was taken by the device (resolve_streams_kernel): the host
@@ -806,8 +810,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   //      others get (birth, species) pairs for the speculative scoring kernel ----
   hCls_.reserve(n);
   hBMeta_.reserve(n);
-  pair0_.assign(n, -1);  pair1_.assign(n, -1);
-  birthGroup_.assign(n, -1);
+  pair0_.resize(n);  pair1_.resize(n);  birthGroup_.resize(n);
   grpSpecies_.clear();  grpCount_.clear();
   hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
   size_t P = 0, nStream = 0;
@@ -836,10 +839,12 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       grpCount_[s0->grp_index]++;
       birthGroup_[i] = int32_t(s0->grp_index);
+      pair0_[i] = pair1_[i] = -1;               // no speculative pair: a taken-over stream is scored on the host
       nStream++;
       touch(s0);
       continue;
     }
+    birthGroup_[i] = -1;  pair0_[i] = pair1_[i] = -1;
     if (s0 && s0->dev_fill) { pair0_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
     if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
   }
@@ -942,20 +947,37 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   // ---- host: ordered walk (device-resolved births are mirrored, the others resolved here) ----
   curPayload_ = payload;
   for (uint32_t i = 0; i < n; i++) {
+    Species *s0 = nullptr;
+    uint32_t act = 0;
+    if (birthGroup_[i] >= 0) {
+      s0 = grpSpecies_[size_t(birthGroup_[i])];
+      if (s0->div_epoch == chunkEpoch_) s0 = nullptr;
+      else {
+        act = hAct_.p[i];
+        if (act == ACT_ACCEPTED) {
+          // by far the commonest outcome: accepted at top level, enveloppe untouched (:687-691, :721-723)
+          if (s0->pending > 0) s0->pending--;
+          comparisons_ += s0->k;
+          s0->count++;  s0->alive++;  s0->last = step_;
+          if (msid[i] != INV) selfContribution(s0, 1u + (msid[i] == fsid[i]));
+          insertions_++;
+          counters[1]++;  counters[0]++;
+          if (outSid) outSid[i] = s0->sid;
+          if (outSlot) outSlot[i] = -1;
+          if (outReplaced) outReplaced[i] = INV;
+          done++;
+          continue;
+        }
+        if ((act & ACT_UNCERTAIN) || (act & ACT_CODE_MASK) == ACT_UNPROCESSED) { diverge(s0); s0 = nullptr; }
+      }
+    }
     RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, hCls_.p[i],
                 compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
     uint32_t sid = INV, replaced = INV;
     int32_t slot = -1;
     const uint32_t *w = payload + size_t(i) * W_;
     bool viaStream = false;
-    if (birthGroup_[i] >= 0) {
-      Species *s0 = grpSpecies_[size_t(birthGroup_[i])];
-      if (s0->div_epoch != chunkEpoch_) {
-        const uint32_t act = hAct_.p[i];
-        if ((act & ACT_UNCERTAIN) || (act & ACT_CODE_MASK) == ACT_UNPROCESSED) diverge(s0);
-        else { walkStream(w, g, s0, act, sid, slot, replaced); viaStream = true; }
-      }
-    }
+    if (s0) { walkStream(w, g, s0, act, sid, slot, replaced); viaStream = true; }
     if (!viaStream) walkOne(w, g, pair0_[i], pair1_[i], sid, slot, replaced);
     if (outSid) outSid[i] = sid;
     if (outSlot) outSlot[i] = slot;

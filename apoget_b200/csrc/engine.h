@@ -109,6 +109,7 @@ struct Species {
   uint32_t grp_epoch = 0, grp_index = 0;  // this species has a device-resolved stream in the current chunk
   uint32_t div_epoch = 0;                 // ... and the host took that stream over (device results discarded)
   uint32_t snap_epoch = 0, snap_mask = 0, snap_fill = 0;  // slots changed since the chunk's device snapshot
+  uint32_t self_idx = 0;                  // where this species' own entry sits in contribs (hint)
   bool full_upload = false;               // the device copy (rows, matrix, fill) must be rewritten entirely
   uint32_t touch_epoch = 0;               // last scoring launch that read this enveloppe
   bool extinct (void) const { return alive == 0 && pending == 0; }   // node.hpp:157-159

@@ -43,6 +43,8 @@ from apoget_b200 import synth  # noqa: E402
 SETUP_GENS = 4          # generations 0..3: root + three 10-way radiations -> 1 000 species (+111 ancestors)
 WORKLOAD = dict(kind=synth.BITS, words=8, flips=0.5, sigma=12.0, hybrid=0.05, burst_levels=3, burst_fanout=10)
 TREE_CFG = dict(K=10)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/)
+TRAFFIC = {"score_pairs_kernel": 6.10e6}
 METRIC = "births classified/sec (species assignment, reference-exact)"
 UNIT = "births/s"
 
@@ -277,22 +279,33 @@ def main() -> None:
         e2e_ms, dev_ms = float(tt[0]), float(tt[1])
     births = pop * args.steps * world
 
-    # ---- roofline of the dominant kernel (score_pairs), from the engine's own CUDA events --------
+    # ---- roofline of the dominant kernel, timed by the engine's own CUDA events on its stream ------
     dc = {k: c1[k] - c0[k] for k in c1}
-    launches = max(1, dc["score_launches"])
-    kernel_ms = (t1["score_kernel_ms"] - t0["score_kernel_ms"]) / launches
     G = 4 * W
     K = TREE_CFG["K"]
-    pairs, reps = dc["device_pairs"] / launches, dc["device_reps_read"] / launches
-    # algorithmic bytes per launch: births once (payload + 16 B compat meta), every
-    # touched representative once (payload + 16 B meta), one 8-byte pair descriptor and one
-    # (4 + 4K)-byte result per pair
-    alg_bytes = pop * (G + 16) + reps * (G + 16) + pairs * (8 + 4 + 4 * K)
     peak, peak_src = peaks()
+    stream_ms, score_ms = t1["stream_kernel_ms"] - t0["stream_kernel_ms"], t1["score_kernel_ms"] - t0["score_kernel_ms"]
+    pairs = dc["device_pairs"] / max(1, dc["score_launches"])
+    if stream_ms >= score_ms:
+        kname, launches = "resolve_streams_kernel", max(1, dc["stream_launches"])
+        kernel_ms = stream_ms / launches
+        nb, reps, ent = dc["stream_births"] / launches, dc["device_reps_read"] / launches, dc["stream_entries"] / launches
+        # algorithmic bytes per launch: every stream birth once (payload + 16 B compat meta + 4 B order
+        # entry), every touched enveloppe once (rows + 16 B meta per representative + K*K*4 B matrix),
+        # the write-back of the representatives that changed (row + meta + matrix), a 4-byte result word
+        # per birth and one 4K-byte distance row per enveloppe entry
+        alg_bytes = nb * (G + 16 + 4) + reps * (G + 16 + 4 * K) + ent * (G + 16 + 4 * K * K) + nb * 4 + ent * 4 * K
+        units = nb
+    else:
+        kname, launches = "score_pairs_kernel", max(1, dc["score_launches"])
+        kernel_ms = score_ms / launches
+        reps = dc["device_reps_read"] / launches
+        alg_bytes = pop * (G + 16) + reps * (G + 16) + pairs * (8 + 4 + 4 * K)
+        units = pairs
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
 
-    h2d = pop * (G + 12) + pop * 16 + int(pairs) * 8
-    d2h = int(pairs) * (4 + 4 * K)
+    h2d = pop * (G + 16) + pop * 4 + int(pairs) * 8
+    d2h = pop * 4 + int(dc["stream_entries"] / args.steps) * 4 * K + int(pairs) * (4 + 4 * K)
     line = {
         "metric": METRIC, "value": births / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -300,10 +313,11 @@ def main() -> None:
         "e2e": {"value": births / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int((c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])),
-        "roofline": {"bound": "hbm", "kernel": "score_pairs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": TRAFFIC.get(kname), "peak_source": peak_src,
                      "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                     "pairs_per_launch": pairs, "evals_per_s_kernel": pairs * K / (kernel_ms * 1e-3) if kernel_ms else 0},
+                     "births_per_launch": units, "evals_per_s_kernel": units * K / (kernel_ms * 1e-3) if kernel_ms else 0,
+                     "births_per_s_kernel": units / (kernel_ms * 1e-3) if kernel_ms else 0},
         "clocks": clocks,
         "breakdown_e2e_ms_per_step": {
             "prepare": 1e3 * (t1["prepare_s"] - t0["prepare_s"]) / args.steps,
@@ -311,7 +325,8 @@ def main() -> None:
             "ordered_resolution": 1e3 * (t1["walk_s"] - t0["walk_s"]) / args.steps,
             "pool_refresh": 1e3 * (t1["refresh_s"] - t0["refresh_s"]) / args.steps},
         "resolution": {k: dc[k] / args.steps for k in ("device_scores", "patched_scores", "host_scores",
-                                                         "host_distance_evals", "guard_rechecks")},
+                                                         "host_distance_evals", "guard_rechecks", "stream_births",
+                                                         "stream_entries", "streams_taken_over")},
         "species": tree_h.stats()["width"],
     }
 
