@@ -67,6 +67,7 @@ SYMBOLS = {
     "apt_classify_dense": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp]),
     "apt_classify_dense_dev": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp]),
     "apt_env_contribution": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, vp, vp, vp, vp]),
+    "apt_microbench": (ctypes.c_int, [ctypes.c_int, f64p]),
     "apt_pairwise": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, ctypes.c_uint32, vp, vp, vp]),
 }
 

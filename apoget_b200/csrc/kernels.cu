@@ -292,6 +292,11 @@ void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg, const uin
                             float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
                             cudaStream_t stream) {
   if (!n_births) return;
+  if (dense_tiled_supports(pool.wp, pool.K)) {
+    launch_classify_dense_tiled(pool, cfg, b_payload, b_cmeta, n_births, out_best_species, out_best_score,
+                                out_first_accept, out_n_accept, stream);
+    return;
+  }
   dispatch<DenseLauncher>(lanes_per_rep(pool.wp), cfg.kind, cfg.use_lut != 0, pool, cfg, b_payload, b_cmeta,
                           n_births, out_best_species, out_best_score, out_first_accept, out_n_accept, stream);
 }

@@ -105,6 +105,13 @@ void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg,
                             uint32_t *out_best_species, float *out_best_score,
                             uint32_t *out_first_accept, uint32_t *out_n_accept, cudaStream_t stream);
 
+/// Register-tiled dense sweep (dense.cu); launch_classify_dense picks it whenever it fits.
+bool dense_tiled_supports (uint32_t wp, uint32_t K);
+void launch_classify_dense_tiled (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *b_payload,
+                                  const float4 *b_cmeta, uint32_t n_births, uint32_t *out_best_species,
+                                  float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
+                                  cudaStream_t stream);
+
 } // namespace apt
 
 #endif

@@ -210,6 +210,11 @@ int apt_env_contribution (const apt_params *params, uint32_t n, const float *edi
 int apt_pairwise (const apt_params *params, uint32_t n_genomes, const uint32_t *payload,
                   uint32_t n_pairs, const uint32_t *idx_a, const uint32_t *idx_b, float *out);
 
+/* Pipe-throughput micro-benchmarks (roofline denominators not in MEASURED_PEAKS.json), best of 5:
+ * out[0] popc32/s (XOR + POPC per op, as in a Hamming distance), out[1] LOP3/s, out[2] DFMA/s,
+ * out[3] FFMA/s, chip-wide. */
+int apt_microbench (int device, double out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,171 @@
+#!/usr/bin/env python3
+"""Dense sweep benchmark (BASELINE.json configs[3] / north_star: 1 M births x 100 k enveloppe members).
+
+Every birth is scored against every species of a synthetic pool by classify_dense_tiled_kernel
+(apt_classify_dense_dev, inputs and outputs resident in HBM); the kernel is integer-pipe bound, so the
+roofline denominator is the popc32 rate measured on this GPU by apt_microbench.
+With torchrun (N ranks) the species are sharded across the GPUs, every rank sweeps ALL births against
+its shard, and the per-birth partial winners are combined by one NCCL all-gather.
+
+    python tools/bench_dense.py --config c4 [--births N] [--species S]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_dense.py --config c4
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {  # name: (kind, words, K, species, births, sigma)
+    "c2": (0, 8, 10, 1_000, 100_000, 12.0),
+    "c2x": (0, 8, 10, 10_000, 1_000_000, 12.0),
+    "c3": (1, 64, 10, 10_000, 65_536, 0.4),
+    "c4": (0, 128, 10, 10_000, 1_000_000, 60.0),
+}
+
+
+def make_pool(rng, kind, words, S, K, sigma):
+    if kind == 0:
+        base = rng.integers(0, 2**32, size=(S, 1, words), dtype=np.uint32)
+        noise = rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) \
+            & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) \
+            & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32)      # ~3 % of the bits differ
+        reps = base ^ noise
+    else:
+        base = rng.standard_normal((S, 1, words)).astype(np.float32)
+        reps = (base + 0.03 * rng.standard_normal((S, K, words)).astype(np.float32)).view(np.uint32)
+    compat = np.zeros((S, K, 3), dtype=np.float32)
+    compat[..., 1:] = sigma
+    fill = np.full(S, K, dtype=np.uint32)
+    return np.ascontiguousarray(reps), compat, fill
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--births", type=int, default=0)
+    ap.add_argument("--species", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--check", type=int, default=24, help="births verified against the CPU oracle")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from apoget_b200 import _lib
+    from apoget_b200.kernels import Pool
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kind, words, K, S, B, sigma = CONFIGS[args.config]
+    S, B = args.species or S, args.births or B
+    rng = np.random.default_rng(44)
+    reps, rc, fill = make_pool(rng, kind, words, S, K, sigma)
+    # births: mutated copies of random representatives (so that some species accept them)
+    src = rng.integers(0, S, size=B)
+    if kind == 0:
+        births = reps[src, rng.integers(0, K, size=B)].copy()
+        births[np.arange(B), rng.integers(0, words, size=B)] ^= rng.integers(0, 2**32, size=B, dtype=np.uint32) & np.uint32(0x00010101)
+    else:
+        births = (reps[src, 0].view(np.float32) + 0.03 * rng.standard_normal((B, words)).astype(np.float32)).view(np.uint32)
+    bc = np.zeros((B, 3), dtype=np.float32)
+    bc[:, 1:] = sigma
+
+    # species shard of this rank
+    s_lo, s_hi = rank * S // world, (rank + 1) * S // world
+    pool = Pool(kind, words, reps[s_lo:s_hi], rc[s_lo:s_hi], fill[s_lo:s_hi], device=local, K=K)
+
+    peaks = np.zeros(4, dtype=np.float64)
+    _lib.check(_lib.lib().apt_microbench(local, peaks.ctypes.data_as(_lib.f64p)))
+
+    d_births = torch.from_numpy(births.view(np.int32)).cuda()
+    d_compat = torch.from_numpy(bc).cuda()
+    d_best = torch.empty(B, dtype=torch.int32, device="cuda")
+    d_score = torch.empty(B, dtype=torch.float32, device="cuda")
+    d_first = torch.empty(B, dtype=torch.int32, device="cuda")
+    d_count = torch.empty(B, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+    vp = ctypes.c_void_p
+
+    def sweep():
+        pool.classify_dense_dev(B, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), vp(d_best.data_ptr()),
+                                vp(d_score.data_ptr()), vp(d_first.data_ptr()), vp(d_count.data_ptr()),
+                                vp(stream.cuda_stream))
+
+    def combine():
+        """All-gather the per-shard winners and reduce them identically on every rank."""
+        if world == 1:
+            return d_best, d_score, d_first, d_count
+        # species indices become global before the exchange
+        rec = torch.stack([torch.where(d_best >= 0, d_best + s_lo, d_best).to(torch.float64), d_score.to(torch.float64),
+                           torch.where(d_first >= 0, d_first + s_lo, d_first).to(torch.float64), d_count.to(torch.float64)], 1)
+        allrec = torch.empty((world,) + rec.shape, dtype=rec.dtype, device="cuda")
+        dist.all_gather_into_tensor(allrec, rec)
+        score = allrec[:, :, 1]
+        # strictly greatest score, lowest species index on ties = first rank holding the maximum
+        win = torch.argmax(score, 0)
+        best = allrec[:, :, 0].gather(0, win[None]).squeeze(0).to(torch.int64)
+        first = allrec[:, :, 2]
+        first = torch.where(first < 0, torch.full_like(first, 2.0**40), first).amin(0)
+        first = torch.where(first >= 2.0**40, torch.full_like(first, -1.0), first).to(torch.int64)
+        return best, score.amax(0).to(torch.float32), first, allrec[:, :, 3].sum(0).to(torch.int64)
+
+    sweep(); combine()                                    # warm-up
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(args.iters):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sweep()
+        res = combine()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = min(times)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+
+    best, score, first, count = [x.cpu().numpy() for x in res]
+    # ---- verification against the CPU oracle on a sample of births (all species) ----
+    bad = 0
+    if rank == 0 and args.check:
+        import oracle
+        for b in rng.choice(B, size=min(args.check, B), replace=False):
+            sc = np.array([oracle.score(kind, births[b], bc[b], reps[s], rc[s])[0] for s in range(S)], dtype=np.float32)
+            if kind == 0:
+                ok = (int(best[b]) == int(np.argmax(sc)) and np.float32(score[b]) == sc.max()
+                      and int(count[b]) == int((sc > 0).sum())
+                      and int(first[b]) == (int(np.nonzero(sc > 0)[0][0]) if (sc > 0).any() else -1))
+            else:
+                ok = abs(float(score[b]) - float(sc.max())) <= 1e-5
+            bad += (not ok)
+    evals = float(B) * S * K
+    ops = evals * (words if kind == 0 else 3 * words)
+    peak = peaks[0] if kind == 0 else peaks[3] * 2
+    if rank == 0:
+        print(json.dumps({
+            "bench": "dense sweep", "config": args.config, "n_gpus": world, "births": B, "species": S, "K": K,
+            "genome_words": words, "kind": "bits/hamming" if kind == 0 else "f32/l2", "ms": ms,
+            "births_per_s": B / (ms * 1e-3), "evals_per_s": evals / (ms * 1e-3),
+            "pipe_ops_per_s": ops / (ms * 1e-3), "pipe": "popc32 (+xor)" if kind == 0 else "fp32 flop (sub, fma)",
+            "pipe_peak_measured": peak, "frac_of_pipe_peak": ops / (ms * 1e-3) / (peak * world),
+            "microbench": {"popc32_per_s": peaks[0], "lop3_per_s": peaks[1], "dfma_per_s": peaks[2], "ffma_per_s": peaks[3]},
+            "accepting_births_frac": float((count > 0).mean()), "oracle_checked_births": int(min(args.check, B)),
+            "oracle_mismatches": int(bad)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
