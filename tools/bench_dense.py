@@ -25,7 +25,7 @@ CONFIGS = {  # name: (kind, words, K, species, births, sigma)
     "c2": (0, 8, 10, 1_000, 100_000, 12.0),
     "c2x": (0, 8, 10, 10_000, 1_000_000, 12.0),
     "c3": (1, 64, 10, 10_000, 65_536, 0.4),
-    "c4": (0, 128, 10, 10_000, 1_000_000, 60.0),
+    "c4": (0, 128, 10, 10_000, 1_000_000, 100.0),
 }
 
 
@@ -57,6 +57,7 @@ def main():
     import torch.distributed as dist
     from apoget_b200 import _lib
     from apoget_b200.kernels import Pool
+    from apoget_b200 import shard
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -78,7 +79,7 @@ def main():
     bc[:, 1:] = sigma
 
     # species shard of this rank
-    s_lo, s_hi = rank * S // world, (rank + 1) * S // world
+    s_lo, s_hi = shard.shard_range(S, rank, world)
     pool = Pool(kind, words, reps[s_lo:s_hi], rc[s_lo:s_hi], fill[s_lo:s_hi], device=local, K=K)
 
     peaks = np.zeros(4, dtype=np.float64)
@@ -99,22 +100,7 @@ def main():
                                 vp(stream.cuda_stream))
 
     def combine():
-        """All-gather the per-shard winners and reduce them identically on every rank."""
-        if world == 1:
-            return d_best, d_score, d_first, d_count
-        # species indices become global before the exchange
-        rec = torch.stack([torch.where(d_best >= 0, d_best + s_lo, d_best).to(torch.float64), d_score.to(torch.float64),
-                           torch.where(d_first >= 0, d_first + s_lo, d_first).to(torch.float64), d_count.to(torch.float64)], 1)
-        allrec = torch.empty((world,) + rec.shape, dtype=rec.dtype, device="cuda")
-        dist.all_gather_into_tensor(allrec, rec)
-        score = allrec[:, :, 1]
-        # strictly greatest score, lowest species index on ties = first rank holding the maximum
-        win = torch.argmax(score, 0)
-        best = allrec[:, :, 0].gather(0, win[None]).squeeze(0).to(torch.int64)
-        first = allrec[:, :, 2]
-        first = torch.where(first < 0, torch.full_like(first, 2.0**40), first).amin(0)
-        first = torch.where(first >= 2.0**40, torch.full_like(first, -1.0), first).to(torch.int64)
-        return best, score.amax(0).to(torch.float32), first, allrec[:, :, 3].sum(0).to(torch.int64)
+        return shard.combine(d_best, d_score, d_first, d_count, s_lo)
 
     sweep(); combine()                                    # warm-up
     torch.cuda.synchronize()
