@@ -399,6 +399,61 @@ void Engine::diverge (Species *s) {
   s->full_upload = true;
   queueRefresh(s);
   counters[11]++;
+  if (s->grp_epoch == chunkEpoch_ && !grpState_.empty()) settleStream(s->grp_index, true, curBirth_, &requeue_);
+}
+
+/// Credits to s's own contributor entry what its accepted-unchanged stream births with index
+/// < `before` contribute to it.  Needed right before ANOTHER species' contribution to s is
+/// recorded: the stable sort of Contributors::update (speciescontributors.cpp:62) orders equal
+/// counts by history, so the own entry must hold exactly the count it would have at that time.
+void Engine::catchUpSelf (Species *s, uint32_t before) {
+  if (s->grp_epoch != chunkEpoch_ || s->div_epoch == chunkEpoch_ || grpState_.empty()) return;
+  const uint32_t g = s->grp_index;
+  GroupState &st = grpState_[g];
+  const uint32_t end = hGrpOff_.p[g + 1];
+  uint32_t pos = hGrpOff_.p[g] + st.cursor;
+  for (; pos < end; pos++) {
+    const uint32_t ord = hOrder_.p[pos], b = ord & ORDER_INDEX_MASK;
+    if (b >= before) break;
+    if (hAct_.p[b] == ACT_ACCEPTED) st.scanned[ord >> ORDER_CLASS_SHIFT]++;
+  }
+  st.cursor = pos - hGrpOff_.p[g];
+  const uint32_t due = st.scanned[1] + 2 * st.scanned[2];
+  if (due > st.selfApplied) { selfContribution(s, due - st.selfApplied); st.selfApplied = due; }
+}
+
+/// Books the accepted-unchanged births of stream g that the host never looks at individually
+/// (:687-691 nothing to do for the enveloppe; :721-723 counters; :741-769 own contribution).
+/// At the end of a chunk: all of them (totals from the kernel).  When the host takes the stream
+/// over at birth `before`: only those before it; the later ones are handed back through `requeue`.
+void Engine::settleStream (uint32_t g, bool diverging, uint32_t before, std::vector<uint32_t> *requeue) {
+  Species *s = grpSpecies_[g];
+  GroupState &st = grpState_[g];
+  uint32_t n[3];
+  if (diverging) {
+    const uint32_t end = hGrpOff_.p[g + 1];
+    uint32_t pos = hGrpOff_.p[g] + st.cursor;
+    for (; pos < end; pos++) {
+      const uint32_t ord = hOrder_.p[pos], b = ord & ORDER_INDEX_MASK;
+      if (hAct_.p[b] != ACT_ACCEPTED) continue;
+      if (b < before) st.scanned[ord >> ORDER_CLASS_SHIFT]++;
+      else if (requeue) requeue->push_back(b);
+    }
+    st.cursor = end - hGrpOff_.p[g];
+    n[0] = st.scanned[0];  n[1] = st.scanned[1];  n[2] = st.scanned[2];
+  } else {
+    const uint4 sum = hGrpSum_.p[g];
+    n[0] = sum.x;  n[1] = sum.y;  n[2] = sum.z;
+  }
+  const uint32_t total = n[0] + n[1] + n[2];
+  if (!total) return;
+  s->pending = s->pending > total ? s->pending - total : 0;          // :293
+  s->count += total;  s->alive += total;  s->last = step_;            // :721-723
+  comparisons_ += total * K_;                   // an accepted birth leaves the enveloppe alone only when it is full
+  insertions_ += total;
+  counters[0] += total;  counters[1] += total;
+  const uint32_t due = n[1] + 2 * n[2];
+  if (due > st.selfApplied) { selfContribution(s, due - st.selfApplied); st.selfApplied = due; }
 }
 
 // ---- enveloppe criteria (src/core/tree/enveloppecriteria.cpp) on the K x K matrix ---------------
@@ -582,6 +637,7 @@ void Engine::finishBirth (const uint32_t *w, RepMeta &g, Species *best, float be
                           const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced) {
   if (bestScore > 0) {
     slot = insertInto(w, g, best, bestEval, true, replaced);
+    catchUpSelf(best, curBirth_);
     updateContributions(best, contrib);
     sid = best->sid;
   } else {
@@ -815,6 +871,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
   size_t P = 0, nStream = 0;
   touchEpoch_++;
+  for (uint32_t sid: sidTouched_) if (sid < sidGroup_.size()) sidGroup_[sid] = -2;
+  sidTouched_.clear();
+  if (sidGroup_.size() < nodes_.size()) sidGroup_.resize(nodes_.size(), -2);
   auto touch = [&] (Species *s) {
     if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
   };
@@ -828,6 +887,29 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     hBMeta_.p[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], fc);
     Species *s0 = nullptr, *s1 = nullptr;
     const uint32_t m = msid[i], f = fsid[i];
+    if (streamOk_ && (f == INV || m == f) && m != INV && m < sidGroup_.size()) {
+      // single-parent birth: the per-chunk table answers without touching the species record
+      int32_t gidx = sidGroup_[m];
+      if (gidx == -2) {
+        Species *sp = nodes_[m];
+        if (sp && sp->dev_fill) {
+          sp->grp_epoch = chunkEpoch_;
+          sp->grp_index = uint32_t(grpSpecies_.size());
+          gidx = int32_t(sp->grp_index);
+          grpSpecies_.push_back(sp);  grpCount_.push_back(0);
+          touch(sp);
+        } else gidx = -1;
+        sidGroup_[m] = gidx;
+        sidTouched_.push_back(m);
+      }
+      if (gidx >= 0) {
+        grpCount_[size_t(gidx)]++;
+        birthGroup_[i] = gidx;
+        pair0_[i] = pair1_[i] = -1;             // no speculative pair: a taken-over stream is scored on the host
+        nStream++;
+        continue;
+      }
+    }
     if (m == INV && f == INV) s0 = root_;
     else if (f == INV || m == f) s0 = lookup(m);
     else { s0 = lookup(m); s1 = lookup(f); }
@@ -836,10 +918,11 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         s0->grp_epoch = chunkEpoch_;
         s0->grp_index = uint32_t(grpSpecies_.size());
         grpSpecies_.push_back(s0);  grpCount_.push_back(0);
+        if (s0->sid < sidGroup_.size() && sidGroup_[s0->sid] == -2) { sidGroup_[s0->sid] = int32_t(s0->grp_index); sidTouched_.push_back(s0->sid); }
       }
       grpCount_[s0->grp_index]++;
       birthGroup_[i] = int32_t(s0->grp_index);
-      pair0_[i] = pair1_[i] = -1;               // no speculative pair: a taken-over stream is scored on the host
+      pair0_[i] = pair1_[i] = -1;
       nStream++;
       touch(s0);
       continue;
@@ -852,10 +935,18 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   if (G) {
     hGrpSlot_.reserve(G);  hGrpOff_.reserve(G + 1);  hOrder_.reserve(nStream);
     uint32_t off = 0;
-    for (uint32_t g = 0; g < G; g++) { hGrpSlot_.p[g] = grpSpecies_[g]->slot; hGrpOff_.p[g] = off; off += grpCount_[g]; grpCount_[g] = 0; }
+    hGrpSid_.reserve(G);
+    for (uint32_t g = 0; g < G; g++) {
+      hGrpSlot_.p[g] = grpSpecies_[g]->slot;  hGrpSid_.p[g] = grpSpecies_[g]->sid;
+      hGrpOff_.p[g] = off;  off += grpCount_[g];  grpCount_[g] = 0;
+    }
     hGrpOff_.p[G] = off;
     for (uint32_t i = 0; i < n; i++)
-      if (birthGroup_[i] >= 0) { const uint32_t g = uint32_t(birthGroup_[i]); hOrder_.p[hGrpOff_.p[g] + grpCount_[g]++] = i; }
+      if (birthGroup_[i] >= 0) {
+        const uint32_t g = uint32_t(birthGroup_[i]);
+        const uint32_t ccls = msid[i] == INV ? 0u : (msid[i] == fsid[i] ? 2u : 1u);     // :576-577
+        hOrder_.p[hGrpOff_.p[g] + grpCount_[g]++] = i | (ccls << ORDER_CLASS_SHIFT);
+      }
   }
   uploadLut();
   timers[0] += now() - t0;
@@ -905,7 +996,11 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
     dOrder_.reserve(nStream);  dGrpSlot_.reserve(G);  dGrpOff_.reserve(G + 1);  dAct_.reserve(n);
     dRowCounter_.reserve(1);  dRows_.reserve(size_t(nStream) * K_);
-    hAct_.reserve(n);  hRowCounter_.reserve(1);
+    dGrpSid_.reserve(G);  dOutSid_.reserve(n);  dOutSlot_.reserve(n);  dGrpSum_.reserve(G);
+    hAct_.reserve(n);  hRowCounter_.reserve(1);  hOutSid_.reserve(n);  hOutSlot_.reserve(n);  hGrpSum_.reserve(G);
+    cudaCheck(cudaMemcpyAsync(dGrpSid_.p, hGrpSid_.p, G * 4, cudaMemcpyHostToDevice, stream_), "groups");
+    cudaCheck(cudaMemsetAsync(dOutSid_.p, 0xFF, size_t(n) * 4, stream_), "sid clear");
+    cudaCheck(cudaMemsetAsync(dOutSlot_.p, 0xFF, size_t(n) * 4, stream_), "slot clear");
     cudaCheck(cudaMemcpyAsync(dOrder_.p, hOrder_.p, nStream * 4, cudaMemcpyHostToDevice, stream_), "order");
     cudaCheck(cudaMemcpyAsync(dGrpSlot_.p, hGrpSlot_.p, G * 4, cudaMemcpyHostToDevice, stream_), "groups");
     cudaCheck(cudaMemcpyAsync(dGrpOff_.p, hGrpOff_.p, (G + 1) * 4, cudaMemcpyHostToDevice, stream_), "groups");
@@ -918,6 +1013,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.b_payload = dBirths_.p;  a.b_cmeta = dBMeta_.p;
     a.n_groups = G;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
     a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dRowCounter_.p;
+    a.grp_sid = dGrpSid_.p;  a.out_sid = dOutSid_.p;  a.out_slot = dOutSlot_.p;  a.grp_sum = dGrpSum_.p;
     cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
     launch_resolve_streams(a, stream_);
     cudaCheck(cudaEventRecord(evS1_, stream_), "event record");
@@ -925,6 +1021,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaGetLastError(), "resolve_streams launch");
     cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
     cudaCheck(cudaMemcpyAsync(hRowCounter_.p, dRowCounter_.p, 4, cudaMemcpyDeviceToHost, stream_), "row counter");
+    cudaCheck(cudaMemcpyAsync(hOutSid_.p, dOutSid_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
+    cudaCheck(cudaMemcpyAsync(hOutSlot_.p, dOutSlot_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "slots");
+    cudaCheck(cudaMemcpyAsync(hGrpSum_.p, dGrpSum_.p, size_t(G) * sizeof(uint4), cudaMemcpyDeviceToHost, stream_), "sums");
   }
   if (P || G) {
     cudaCheck(cudaStreamSynchronize(stream_), "device pass");
@@ -944,47 +1043,80 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   timers[1] += now() - t0;
   t0 = now();
 
-  // ---- host: ordered walk (device-resolved births are mirrored, the others resolved here) ----
-  curPayload_ = payload;
-  for (uint32_t i = 0; i < n; i++) {
-    Species *s0 = nullptr;
-    uint32_t act = 0;
-    if (birthGroup_[i] >= 0) {
-      s0 = grpSpecies_[size_t(birthGroup_[i])];
-      if (s0->div_epoch == chunkEpoch_) s0 = nullptr;
-      else {
-        act = hAct_.p[i];
-        if (act == ACT_ACCEPTED) {
-          // by far the commonest outcome: accepted at top level, enveloppe untouched (:687-691, :721-723)
-          if (s0->pending > 0) s0->pending--;
-          comparisons_ += s0->k;
-          s0->count++;  s0->alive++;  s0->last = step_;
-          if (msid[i] != INV) selfContribution(s0, 1u + (msid[i] == fsid[i]));
-          insertions_++;
-          counters[1]++;  counters[0]++;
-          if (outSid) outSid[i] = s0->sid;
-          if (outSlot) outSlot[i] = -1;
-          if (outReplaced) outReplaced[i] = INV;
-          done++;
-          continue;
-        }
-        if ((act & ACT_UNCERTAIN) || (act & ACT_CODE_MASK) == ACT_UNPROCESSED) { diverge(s0); s0 = nullptr; }
-      }
-    }
-    RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, hCls_.p[i],
-                compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
-    uint32_t sid = INV, replaced = INV;
-    int32_t slot = -1;
-    const uint32_t *w = payload + size_t(i) * W_;
-    bool viaStream = false;
-    if (s0) { walkStream(w, g, s0, act, sid, slot, replaced); viaStream = true; }
-    if (!viaStream) walkOne(w, g, pair0_[i], pair1_[i], sid, slot, replaced);
-    if (outSid) outSid[i] = sid;
-    if (outSlot) outSlot[i] = slot;
-    if (outReplaced) outReplaced[i] = replaced;
-    done++;
-    counters[0]++;
+  // ---- host: ordered commit.  Births the device accepted without touching an enveloppe need no
+  //      individual attention: their outputs were written by the kernel and their counters are
+  //      booked per stream (settleStream).  Everything else -- enveloppe entries, births rejected at
+  //      top level, two-parent births, streams handed back -- is committed here in arrival order. ----
+  curPayload_ = payload;  curMsid_ = msid;  curFsid_ = fsid;
+  grpState_.assign(G, GroupState{});
+  slow_.clear();  requeue_.clear();
+  if (G) {
+    if (outSid) memcpy(outSid, hOutSid_.p, size_t(n) * 4);
+    if (outSlot) memcpy(outSlot, hOutSlot_.p, size_t(n) * 4);
+    if (outReplaced) memset(outReplaced, 0xFF, size_t(n) * 4);
+    for (uint32_t i = 0; i < n; i++)
+      if (birthGroup_[i] < 0 || hAct_.p[i] != ACT_ACCEPTED) slow_.push_back(i);
+  } else {
+    slow_.resize(n);
+    for (uint32_t i = 0; i < n; i++) slow_[i] = i;
   }
+  size_t si = 0;
+  std::vector<uint32_t> heap;       // births handed back by a taken-over stream (min-heap)
+  auto heapCmp = [] (uint32_t a, uint32_t b) { return a > b; };
+  uint32_t walked = 0;
+  try {
+    for (;;) {
+      for (uint32_t b: requeue_) { heap.push_back(b); std::push_heap(heap.begin(), heap.end(), heapCmp); }
+      requeue_.clear();
+      uint32_t i;
+      if (!heap.empty() && (si >= slow_.size() || heap.front() < slow_[si])) {
+        std::pop_heap(heap.begin(), heap.end(), heapCmp);
+        i = heap.back();  heap.pop_back();
+      } else if (si < slow_.size()) i = slow_[si++];
+      else break;
+      curBirth_ = i;
+      Species *s0 = nullptr;
+      uint32_t act = 0;
+      if (birthGroup_[i] >= 0) {
+        s0 = grpSpecies_[size_t(birthGroup_[i])];
+        if (s0->div_epoch == chunkEpoch_) s0 = nullptr;
+        else {
+          act = hAct_.p[i];
+          if ((act & ACT_UNCERTAIN) || (act & ACT_CODE_MASK) == ACT_UNPROCESSED) { diverge(s0); s0 = nullptr; }
+        }
+      }
+      RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, hCls_.p[i],
+                  compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
+      uint32_t sid = INV, replaced = INV;
+      int32_t slot = -1;
+      const uint32_t *w = payload + size_t(i) * W_;
+      if (s0) walkStream(w, g, s0, act, sid, slot, replaced);
+      else walkOne(w, g, pair0_[i], pair1_[i], sid, slot, replaced);
+      if (outSid) outSid[i] = sid;
+      if (outSlot) outSlot[i] = slot;
+      if (outReplaced) outReplaced[i] = replaced;
+      counters[0]++;
+      walked++;
+    }
+    for (uint32_t g = 0; g < G; g++)
+      if (grpSpecies_[g]->div_epoch != chunkEpoch_) settleStream(g, false, 0, nullptr);
+  } catch (...) {
+    // a birth failed (unknown species, :169-174): everything before it stays committed, as when the
+    // reference throws out of addGenome; streams are settled up to that birth
+    const uint32_t failed = curBirth_;
+    curBirth_ = failed;
+    for (uint32_t g = 0; g < G; g++)
+      if (grpSpecies_[g]->div_epoch != chunkEpoch_) {
+        grpSpecies_[g]->div_epoch = chunkEpoch_;  grpSpecies_[g]->full_upload = true;  queueRefresh(grpSpecies_[g]);
+        settleStream(g, true, failed, nullptr);
+      }
+    done += failed;
+    grpState_.clear();
+    timers[2] += now() - t0;
+    throw;
+  }
+  grpState_.clear();
+  done += n;
   timers[2] += now() - t0;
 }
 

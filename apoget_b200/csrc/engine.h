@@ -191,6 +191,20 @@ private:
   std::vector<int32_t> birthGroup_;       // stream index of each birth of the chunk, -1 = host/K1 path
   std::vector<Species*> grpSpecies_;
   std::vector<uint32_t> grpCount_;
+  /// Host view of one device-resolved stream while the chunk is being committed
+  struct GroupState {
+    uint32_t cursor = 0;                  // position in the stream's order list reached by catch-up scans
+    uint32_t scanned[3] = {0, 0, 0};      // accepted-unchanged births seen by those scans, per contribution class
+    uint32_t selfApplied = 0;             // self-contribution already credited to the species' own entry
+  };
+  std::vector<GroupState> grpState_;
+  std::vector<int32_t> sidGroup_;         // per-chunk cache: sid -> stream index, -1 not streamable, -2 not looked up yet
+  std::vector<uint32_t> sidTouched_;
+  DevBuf<uint32_t> dGrpSid_, dOutSid_;  DevBuf<int32_t> dOutSlot_;  DevBuf<uint4> dGrpSum_;
+  PinBuf<uint32_t> hGrpSid_, hOutSid_;  PinBuf<int32_t> hOutSlot_;  PinBuf<uint4> hGrpSum_;
+  std::vector<uint32_t> slow_, requeue_;  // births the host has to look at (ascending) / handed back by a taken-over stream
+  uint32_t curBirth_ = 0;                 // index (in the chunk) of the birth being committed
+  const uint32_t *curMsid_ = nullptr, *curFsid_ = nullptr;
   uint32_t chunkEpoch_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
@@ -236,6 +250,8 @@ private:
   void finishBirth (const uint32_t *w, RepMeta &g, Species *best, float bestScore, const Eval &bestEval,
                     const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced);
   void selfContribution (Species *s, uint32_t count);
+  void catchUpSelf (Species *s, uint32_t before);
+  void settleStream (uint32_t g, bool diverging, uint32_t before, std::vector<uint32_t> *requeue);
 
   // device plumbing
   uint32_t allocSlot (void);

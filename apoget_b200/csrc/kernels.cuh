@@ -8,6 +8,8 @@
 namespace apt {
 
 constexpr uint32_t KMAX = 32;        // largest supported enveloppe size (rsetSize)
+constexpr uint32_t ORDER_INDEX_MASK = 0x3FFFFFFFu;   // StreamArgs::order: birth index bits
+constexpr uint32_t ORDER_CLASS_SHIFT = 30;
 
 /// Enveloppe pool in HBM.  Representative r of the species in slot s lives at
 /// payload[(s*K + r) * wp .. +wp) (wp = payload words padded to a multiple of 4 so every row is
@@ -87,7 +89,13 @@ struct StreamArgs {
   uint32_t n_groups;
   const uint32_t *grp_slot;   ///< [n_groups] pool slot of the stream's species
   const uint32_t *grp_off;    ///< [n_groups+1] offsets into order
-  const uint32_t *order;      ///< birth indices grouped by stream, arrival order inside a stream
+  const uint32_t *order;      ///< births grouped by stream, arrival order inside a stream: low 30 bits = birth
+                              ///< index, high 2 bits = what the birth contributes to its own species
+                              ///< (0 primordial: nothing, 1 one parent, 2 both parents; :576-577)
+  const uint32_t *grp_sid;    ///< [n_groups] species id of the stream's species
+  uint32_t *out_sid;          ///< [n_births] InsertionResult.sid of accepted births (pre-set to APT_INVALID)
+  int32_t *out_slot;          ///< [n_births] enveloppe slot of entered births (pre-set to -1)
+  uint4 *grp_sum;             ///< [n_groups] {accepted-unchanged births contributing 0, 1, 2; stopped early}
   uint32_t *act;              ///< [n_births] result words (zero-initialised by the caller)
   float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
   uint32_t *row_counter;      ///< zero-initialised

@@ -161,8 +161,9 @@ resolve_streams_kernel (StreamArgs a) {
   ws.minBase = reinterpret_cast<float*>(base);       base += size_t(K) * 4;
   ws.d = reinterpret_cast<float*>(base);
 
-  const uint32_t slot = a.grp_slot[g];
+  const uint32_t slot = a.grp_slot[g], sid = a.grp_sid[g];
   const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
+  uint32_t nAcc0 = 0, nAcc1 = 0, nAcc2 = 0;     // accepted, enveloppe unchanged, by contribution class
   uint32_t k = min(a.pool.fill[slot], K);
   const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
 
@@ -187,7 +188,8 @@ resolve_streams_kernel (StreamArgs a) {
   for (uint32_t cb = g0; cb < g1 && !aborted; cb += 32) {
     const uint32_t nb = min(32u, g1 - cb);
     const bool active = uint32_t(lane) < nb;
-    const uint32_t b = active ? a.order[cb + lane] : 0u;
+    const uint32_t ord = active ? a.order[cb + lane] : 0u;
+    const uint32_t b = ord & ORDER_INDEX_MASK, ccls = ord >> ORDER_CLASS_SHIFT;
     uint4 bw[WQ];
     float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
     if (active) {
@@ -221,7 +223,14 @@ resolve_streams_kernel (StreamArgs a) {
       const uint32_t mmask = __ballot_sync(0xffffffffu, modifies);
       const int firstU = umask ? __ffs(umask) - 1 : 32, firstM = mmask ? __ffs(mmask) - 1 : 32;
       const int stop = min(firstU, firstM);
-      if (mine && lane < stop) a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
+      const bool fin = mine && lane < stop;
+      if (fin) {
+        a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
+        if (accept) a.out_sid[b] = sid;
+      }
+      nAcc0 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 0));
+      nAcc1 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 1));
+      nAcc2 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 2));
       if (stop == 32) break;
       if (firstU <= firstM) {
         // the decision of this birth needs exact arithmetic: the host takes the stream over from here
@@ -243,6 +252,8 @@ resolve_streams_kernel (StreamArgs a) {
       }
       if (lane == stop) {
         a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
+        a.out_sid[b] = sid;
+        a.out_slot[b] = int32_t(sl);
 #pragma unroll
         for (int v = 0; v < WQ; v++) ws.reps[sl * WQ + v] = bw[v];
         ws.rmeta[sl] = bm;
@@ -261,6 +272,8 @@ resolve_streams_kernel (StreamArgs a) {
     }
     __syncwarp();
   }
+
+  if (lane == 0) a.grp_sum[g] = make_uint4(nAcc0, nAcc1, nAcc2, aborted ? 1u : 0u);
 
   // ---- write the enveloppe back (the host mirrors the same changes from act/rows) ----
   if (changed && !aborted) {

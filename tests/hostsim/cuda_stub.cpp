@@ -141,10 +141,10 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
     std::vector<uint32_t> reps (a.pool.payload + size_t(slot) * K * wp, a.pool.payload + size_t(slot + 1) * K * wp);
     std::vector<float4> meta (a.pool.cmeta + size_t(slot) * K, a.pool.cmeta + size_t(slot + 1) * K);
     std::vector<float> D (a.pool_dist + size_t(slot) * K * K, a.pool_dist + size_t(slot + 1) * K * K);
-    uint32_t changed = 0;
+    uint32_t changed = 0, nAcc[3] = {0, 0, 0};
     bool aborted = false;
     for (uint32_t t = a.grp_off[g]; t < a.grp_off[g + 1]; t++) {
-      const uint32_t b = a.order[t];
+      const uint32_t b = a.order[t] & ORDER_INDEX_MASK, ccls = a.order[t] >> ORDER_CLASS_SHIFT;
       const uint32_t *bw = a.b_payload + size_t(b) * wp;
       const float4 bm = a.b_cmeta[b];
       float d[KMAX];
@@ -177,7 +177,9 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
         }
         modifies = value > 0;
       }
-      if (!modifies) { a.act[b] = ACT_ACCEPTED; continue; }
+      a.out_sid[b] = a.grp_sid[g];
+      if (!modifies) { a.act[b] = ACT_ACCEPTED; nAcc[ccls]++; continue; }
+      a.out_slot[b] = int32_t(than);
       const uint32_t row = (*a.row_counter)++;
       for (uint32_t r = 0; r < k; r++) {
         a.rows[size_t(row) * K + r] = d[r];
@@ -189,6 +191,7 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       if (append) k++;
       changed |= 1u << than;
     }
+    a.grp_sum[g] = make_uint4(nAcc[0], nAcc[1], nAcc[2], aborted ? 1u : 0u);
     if (changed && !aborted) {
       for (uint32_t r = 0; r < k; r++) {
         if (!((changed >> r) & 1u)) continue;

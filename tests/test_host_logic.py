@@ -112,3 +112,30 @@ def test_unknown_species_is_an_error_and_commits_the_prefix(hostsim):
         tree.add_genomes(t.payload[:n], t.compat[:n], gid, gid, msid, inv, inv)
     assert e.value.status == 1 and "No node found for species 77" in str(e.value)
     assert tree.stats()["insertions"] == 2         # root bootstrap is not counted (:270-273)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_traces_against_oracle(hostsim, seed, tmp_path):
+    """Fresh seeded traces with many far hybrids, overlapping generations and small enveloppes: the
+    regime where streams get taken over, contributions interleave and parents change."""
+    rng = np.random.default_rng(1000 + seed)
+    K = int(rng.integers(1, 7))
+    t = synth.generate(kind=synth.BITS, words=int(rng.choice([1, 2, 4, 8])), pop=int(rng.integers(30, 160)),
+                       gens=int(rng.integers(8, 30)), seed=seed, flips=float(rng.uniform(0.3, 3.0)),
+                       sigma=float(rng.uniform(2.0, 9.0)), hybrid=float(rng.uniform(0.0, 0.6)), hybrid_far=1.0,
+                       survive=float(rng.uniform(0.0, 0.7)), compat_classes=int(rng.integers(1, 4)),
+                       founders=int(rng.integers(1, 3)))
+    cfg = dict(K=K, full_continuous=bool(seed % 3), env_crit=int(seed % 2), trim_period=5, trim_min_delay=3,
+               trim_delay=1.0, trim_thr=0.6)
+    path = str(tmp_path / "t.trace")
+    synth.write_trace(path, t)
+    o = oracle.Oracle(t.kind, t.words, **cfg)
+    osid, oent, _ = o.replay(path, n_births=t.n_births)
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, slots = tree.replay(t)
+    assert np.array_equal(sids, osid)
+    assert np.array_equal(slots >= 0, oent > 0)
+    ost, st = o.stats(), tree.stats()
+    assert st == ost
+    assert np.array_equal(tree.events(), o.events())
+    assert tree.to_json() == o.to_json()
