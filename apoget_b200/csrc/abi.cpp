@@ -73,7 +73,7 @@ struct apt_pool {
   }
   PoolView view (void) const { return PoolView { payload, meta, fill, K, wp, nSpecies }; }
   ScoreCfg cfg (void) const {
-    return ScoreCfg { int(prm.kind), prm.full_continuous, lut ? 1 : 0, prm.compat_thr, prm.sim_thr, prm.avg_thr, dlut, lutStride };
+    return ScoreCfg { int(prm.kind), prm.full_continuous, lut ? 1 : 0, prm.compat_thr, prm.sim_thr, prm.avg_thr, dlut, lutStride, uint32_t(classes.size() / 3) };
   }
   /// pads + packs host births into device buffers
   void packBirths (uint32_t n, const uint32_t *pl, const float *compat, Tmp<uint32_t> &dB, Tmp<float4> &dM) {
@@ -134,13 +134,13 @@ int apt_tree_add_genomes (apt_tree *t, uint32_t n, const uint32_t *payload, cons
   });
 }
 
-int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload, const float *d_compat, void *stream,
+int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload, const float *compat, void *stream,
                               const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                               const uint32_t *fgid, const uint32_t *fsid,
                               uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced, uint32_t *n_done) {
   return guarded([&] {
-    need(t && (n == 0 || (d_payload && d_compat && gid && mgid && msid && fgid && fsid)), "null argument");
-    t->engine.addGenomes(n, d_payload, d_compat, true, static_cast<cudaStream_t>(stream), gid, mgid, msid, fgid, fsid,
+    need(t && (n == 0 || (d_payload && compat && gid && mgid && msid && fgid && fsid)), "null argument");
+    t->engine.addGenomes(n, d_payload, compat, true, static_cast<cudaStream_t>(stream), gid, mgid, msid, fgid, fsid,
                          out_sid, out_slot, out_replaced, n_done);
   });
 }

@@ -726,6 +726,7 @@ void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t ac
   counters[1]++;
   slot = -1;  replaced = INV;
   if (code == ACT_ENTERED) {
+    counters[14]++;
     const uint32_t r = (act >> ACT_SLOT_SHIFT) & 31u, k = s0->k;
     const float *d = hRows_.p + size_t(act >> ACT_ROW_SHIFT) * K_;
     RepMeta m = g;
@@ -759,6 +760,17 @@ void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t ac
   insertions_++;
 }
 
+/// Payload of birth i of the current chunk as the host sees it
+const uint32_t* Engine::payloadOf (uint32_t i) {
+  if (curPayload_) return curPayload_ + size_t(i) * W_;
+  auto it = std::lower_bound(slow_.begin(), slow_.end(), i);
+  if (it != slow_.end() && *it == i) return hSlowRows_.p + size_t(it - slow_.begin()) * W_;
+  // a birth handed back by a taken-over stream: fetched on demand
+  lateRows_.emplace_back(W_);
+  cudaCheck(cudaMemcpy(lateRows_.back().data(), curDevPayload_ + size_t(i) * W_, W_ * 4, cudaMemcpyDeviceToHost), "late row");
+  return lateRows_.back().data();
+}
+
 // ---- device plumbing ----------------------------------------------------------------------------
 
 PoolView Engine::poolView (void) const {
@@ -767,7 +779,7 @@ PoolView Engine::poolView (void) const {
 
 ScoreCfg Engine::scoreCfg (void) const {
   return ScoreCfg { int(p_.kind), p_.full_continuous, lutMode_ ? 1 : 0, p_.compat_thr, p_.sim_thr, p_.avg_thr,
-                    dLut_.p, lutStride_ };
+                    dLut_.p, lutStride_, lutUploaded_ };
 }
 
 void Engine::uploadLut (void) {
@@ -857,7 +869,7 @@ void Engine::refreshPool (void) {
 }
 
 void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
-                       const float *dCompat, const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                       const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                        const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
                        uint32_t *outReplaced, uint32_t &done) {
   double t0 = now();
@@ -953,14 +965,20 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   t0 = now();
 
   // ---- device ----
+  const uint32_t *dBirthRows = nullptr;      // [n][wp_] on the device
   if (P || G) {
-    dBirths_.reserve(size_t(n) * wp_);  dBMeta_.reserve(n);
+    dBMeta_.reserve(n);
     if (dPayload) {
-      dCls_.reserve(n);
-      cudaCheck(cudaMemcpyAsync(dCls_.p, hCls_.p, size_t(n) * 4, cudaMemcpyHostToDevice, stream_), "classes");
-      launch_pack_births(dPayload, dCompat, dCls_.p, n, W_, wp_, dBirths_.p, dBMeta_.p, stream_);
-      counters[4]++;
+      // payloads are already resident: used in place when rows need no padding
+      if (wp_ == W_) dBirthRows = dPayload;
+      else {
+        dBirths_.reserve(size_t(n) * wp_);
+        launch_pad_rows(dPayload, n, W_, wp_, dBirths_.p, stream_);
+        counters[4]++;
+        dBirthRows = dBirths_.p;
+      }
     } else {
+      dBirths_.reserve(size_t(n) * wp_);
       if (wp_ == W_) {
         cudaCheck(cudaMemcpyAsync(dBirths_.p, payload, size_t(n) * W_ * 4, cudaMemcpyHostToDevice, stream_), "births");
       } else {
@@ -971,8 +989,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         }
         cudaCheck(cudaMemcpyAsync(dBirths_.p, hBirths_.p, size_t(n) * wp_ * 4, cudaMemcpyHostToDevice, stream_), "births");
       }
-      cudaCheck(cudaMemcpyAsync(dBMeta_.p, hBMeta_.p, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, stream_), "birth meta");
+      dBirthRows = dBirths_.p;
     }
+    cudaCheck(cudaMemcpyAsync(dBMeta_.p, hBMeta_.p, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, stream_), "birth meta");
   }
   if (P) {
     // speculative scores of every (birth, parent species) pair of the two-parent births
@@ -981,7 +1000,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaMemcpyAsync(dPairBirth_.p, hPairBirth_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
     cudaCheck(cudaMemcpyAsync(dPairSlot_.p, hPairSlot_.p, P * 4, cudaMemcpyHostToDevice, stream_), "pairs");
     cudaCheck(cudaEventRecord(evK0_, stream_), "event record");
-    launch_score_pairs(poolView(), scoreCfg(), dBirths_.p, dBMeta_.p, uint32_t(P), dPairBirth_.p, dPairSlot_.p,
+    launch_score_pairs(poolView(), scoreCfg(), dBirthRows, dBMeta_.p, uint32_t(P), dPairBirth_.p, dPairSlot_.p,
                        dScore_.p, dDist_.p, stream_);
     cudaCheck(cudaEventRecord(evK1_, stream_), "event record");
     counters[4]++;  counters[9]++;
@@ -995,7 +1014,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     // the ordered resolution of the single-parent births, one warp per species stream; it runs
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
     dOrder_.reserve(nStream);  dGrpSlot_.reserve(G);  dGrpOff_.reserve(G + 1);  dAct_.reserve(n);
-    dRowCounter_.reserve(1);  dRows_.reserve(size_t(nStream) * K_);
+    dRowCounter_.reserve(1);  dRows_.reserve((size_t(nStream) + 8 * size_t(G)) * K_);
     dGrpSid_.reserve(G);  dOutSid_.reserve(n);  dOutSlot_.reserve(n);  dGrpSum_.reserve(G);
     hAct_.reserve(n);  hRowCounter_.reserve(1);  hOutSid_.reserve(n);  hOutSlot_.reserve(n);  hGrpSum_.reserve(G);
     cudaCheck(cudaMemcpyAsync(dGrpSid_.p, hGrpSid_.p, G * 4, cudaMemcpyHostToDevice, stream_), "groups");
@@ -1010,7 +1029,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.pool = poolView();
     a.pool_payload_w = dPool_.p;  a.pool_cmeta_w = dMeta_.p;  a.pool_fill_w = dFill_.p;  a.pool_dist = dPoolDist_.p;
     a.cfg = scoreCfg();  a.crit = p_.env_crit;  a.guard = GUARD;
-    a.b_payload = dBirths_.p;  a.b_cmeta = dBMeta_.p;
+    a.b_payload = dBirthRows;  a.b_cmeta = dBMeta_.p;
     a.n_groups = G;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
     a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dRowCounter_.p;
     a.grp_sid = dGrpSid_.p;  a.out_sid = dOutSid_.p;  a.out_slot = dOutSlot_.p;  a.grp_sum = dGrpSum_.p;
@@ -1037,7 +1056,6 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         cudaCheck(cudaMemcpyAsync(hRows_.p, dRows_.p, size_t(nRows) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "rows");
         cudaCheck(cudaStreamSynchronize(stream_), "rows");
       }
-      counters[14] += nRows;
     }
   }
   timers[1] += now() - t0;
@@ -1047,7 +1065,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   //      individual attention: their outputs were written by the kernel and their counters are
   //      booked per stream (settleStream).  Everything else -- enveloppe entries, births rejected at
   //      top level, two-parent births, streams handed back -- is committed here in arrival order. ----
-  curPayload_ = payload;  curMsid_ = msid;  curFsid_ = fsid;
+  curPayload_ = payload;
   grpState_.assign(G, GroupState{});
   slow_.clear();  requeue_.clear();
   if (G) {
@@ -1059,6 +1077,19 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   } else {
     slow_.resize(n);
     for (uint32_t i = 0; i < n; i++) slow_[i] = i;
+  }
+  curDevPayload_ = payload ? nullptr : dPayload;
+  lateRows_.clear();
+  if (!payload && !slow_.empty()) {
+    // device-resident births: only the births the host has to look at are fetched (gathered on the device)
+    const size_t ns = slow_.size();
+    hSlowIdx_.reserve(ns);  dSlowIdx_.reserve(ns);  dSlowRows_.reserve(ns * W_);  hSlowRows_.reserve(ns * W_);
+    memcpy(hSlowIdx_.p, slow_.data(), ns * 4);
+    cudaCheck(cudaMemcpyAsync(dSlowIdx_.p, hSlowIdx_.p, ns * 4, cudaMemcpyHostToDevice, stream_), "slow list");
+    launch_gather_rows(dPayload, dSlowIdx_.p, uint32_t(ns), W_, dSlowRows_.p, stream_);
+    counters[4]++;
+    cudaCheck(cudaMemcpyAsync(hSlowRows_.p, dSlowRows_.p, ns * W_ * 4, cudaMemcpyDeviceToHost, stream_), "slow rows");
+    cudaCheck(cudaStreamSynchronize(stream_), "slow rows");
   }
   size_t si = 0;
   std::vector<uint32_t> heap;       // births handed back by a taken-over stream (min-heap)
@@ -1089,7 +1120,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
                   compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
       uint32_t sid = INV, replaced = INV;
       int32_t slot = -1;
-      const uint32_t *w = payload + size_t(i) * W_;
+      const uint32_t *w = payloadOf(i);
       if (s0) walkStream(w, g, s0, act, sid, slot, replaced);
       else walkOne(w, g, pair0_[i], pair1_[i], sid, slot, replaced);
       if (outSid) outSid[i] = sid;
@@ -1129,21 +1160,13 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
   if (!n) return;
   cudaCheck(cudaSetDevice(p_.device), "cudaSetDevice");
 
-  // device-resident inputs: the walk still needs the payloads of births that enter an enveloppe
-  // or need a repair, so a host copy is fetched (it overlaps with the scoring kernel)
-  std::vector<uint32_t> hostPayload;
-  std::vector<float> hostCompat;
+  // device-resident payloads stay where they are: the kernels read them in place and the host only
+  // fetches the rows of the births it has to look at (runChunk)
   const uint32_t *dPayload = nullptr;
-  const float *dCompat = nullptr;
   if (onDevice) {
-    dPayload = payload;  dCompat = compat;
+    dPayload = payload;  payload = nullptr;
     cudaCheck(cudaEventRecord(evUser_, userStream), "event record");
     cudaCheck(cudaStreamWaitEvent(stream_, evUser_, 0), "stream wait");
-    hostPayload.resize(size_t(n) * W_);  hostCompat.resize(size_t(n) * 3);
-    cudaCheck(cudaMemcpyAsync(hostPayload.data(), dPayload, hostPayload.size() * 4, cudaMemcpyDeviceToHost, stream_), "payload fetch");
-    cudaCheck(cudaMemcpyAsync(hostCompat.data(), dCompat, hostCompat.size() * 4, cudaMemcpyDeviceToHost, stream_), "compat fetch");
-    cudaCheck(cudaStreamSynchronize(stream_), "payload fetch");
-    payload = hostPayload.data();  compat = hostCompat.data();
   }
 
   try {
@@ -1155,7 +1178,10 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
                   compat[0], compat[1], compat[2] };
       Eval none;
       uint32_t replaced;
-      const int32_t slot = insertInto(payload, g, root_, none, false, replaced);
+      std::vector<uint32_t> first (W_);
+      if (dPayload) cudaCheck(cudaMemcpy(first.data(), dPayload, W_ * 4, cudaMemcpyDeviceToHost), "first row");
+      else memcpy(first.data(), payload, W_ * 4);
+      const int32_t slot = insertInto(first.data(), g, root_, none, false, replaced);
       if (outSid) outSid[0] = root_->sid;
       if (outSlot) outSlot[0] = slot;
       if (outReplaced) outReplaced[0] = replaced;
@@ -1165,8 +1191,8 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
     while (i0 < n) {
       const uint32_t m = std::min(CHUNK, n - i0);
       refreshPool();
-      runChunk(m, payload + size_t(i0) * W_, compat + size_t(i0) * 3,
-               dPayload ? dPayload + size_t(i0) * W_ : nullptr, dCompat ? dCompat + size_t(i0) * 3 : nullptr,
+      runChunk(m, payload ? payload + size_t(i0) * W_ : nullptr, compat + size_t(i0) * 3,
+               dPayload ? dPayload + size_t(i0) * W_ : nullptr,
                gid + i0, mgid + i0, msid + i0, fgid + i0, fsid + i0,
                outSid ? outSid + i0 : nullptr, outSlot ? outSlot + i0 : nullptr,
                outReplaced ? outReplaced + i0 : nullptr, done);

@@ -204,7 +204,9 @@ private:
   PinBuf<uint32_t> hGrpSid_, hOutSid_;  PinBuf<int32_t> hOutSlot_;  PinBuf<uint4> hGrpSum_;
   std::vector<uint32_t> slow_, requeue_;  // births the host has to look at (ascending) / handed back by a taken-over stream
   uint32_t curBirth_ = 0;                 // index (in the chunk) of the birth being committed
-  const uint32_t *curMsid_ = nullptr, *curFsid_ = nullptr;
+  const uint32_t *curDevPayload_ = nullptr;
+  DevBuf<uint32_t> dSlowIdx_, dSlowRows_;  PinBuf<uint32_t> hSlowIdx_, hSlowRows_;
+  std::vector<std::vector<uint32_t>> lateRows_;
   uint32_t chunkEpoch_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
@@ -259,8 +261,9 @@ private:
   void uploadLut (void);
   PoolView poolView (void) const;
   ScoreCfg scoreCfg (void) const;
+  const uint32_t* payloadOf (uint32_t i);
   void runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
-                 const float *dCompat, const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                 const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                  const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
                  uint32_t *outReplaced, uint32_t &done);
 };

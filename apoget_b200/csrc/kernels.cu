@@ -218,6 +218,21 @@ __global__ void pack_births_kernel (const uint32_t *__restrict__ src, const floa
                           __uint_as_float(cls ? cls[t] : 0u));
 }
 
+__global__ void pad_rows_kernel (const uint32_t *__restrict__ src, uint32_t n, uint32_t words, uint32_t wp,
+                                 uint32_t *__restrict__ dst) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < size_t(n) * wp) {
+    const uint32_t row = uint32_t(t / wp), w = uint32_t(t % wp);
+    dst[t] = w < words ? src[size_t(row) * words + w] : 0u;
+  }
+}
+
+__global__ void gather_rows_kernel (const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n,
+                                    uint32_t words, uint32_t *__restrict__ dst) {
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < size_t(n) * words) dst[t] = src[size_t(idx[t / words]) * words + t % words];
+}
+
 __global__ void scatter_rows_kernel (const uint4 *__restrict__ sp, const float4 *__restrict__ sm,
                                      const uint32_t *__restrict__ dst_row, uint32_t n_rows, uint32_t wp4,
                                      uint4 *__restrict__ pp, float4 *__restrict__ pm) {
@@ -308,6 +323,19 @@ void launch_pack_births (const uint32_t *src_payload, const float *src_compat, c
   const size_t total = size_t(n) * wp;
   pack_births_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src_payload, src_compat, cls, n, words, wp,
                                                                        dst_payload, dst_cmeta);
+}
+
+void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t wp, uint32_t *dst, cudaStream_t stream) {
+  if (!n) return;
+  const size_t total = size_t(n) * wp;
+  pad_rows_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src, n, words, wp, dst);
+}
+
+void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t words, uint32_t *dst,
+                         cudaStream_t stream) {
+  if (!n) return;
+  const size_t total = size_t(n) * words;
+  gather_rows_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src, idx, n, words, dst);
 }
 
 void launch_scatter_rows (const uint32_t *stage_payload, const float4 *stage_cmeta, const uint32_t *dst_row,

@@ -33,6 +33,7 @@ struct ScoreCfg {
   double compat_thr, sim_thr, avg_thr;
   const double *lut;
   uint32_t lut_stride;
+  uint32_t lut_classes;       // rows of the table
 };
 
 /// K1: one warp per (birth, species) pair.
@@ -46,6 +47,13 @@ void launch_score_pairs (const PoolView &pool, const ScoreCfg &cfg,
 void launch_pack_births (const uint32_t *src_payload, const float *src_compat, const uint32_t *cls,
                          uint32_t n, uint32_t words, uint32_t wp,
                          uint32_t *dst_payload, float4 *dst_cmeta, cudaStream_t stream);
+
+/// dst[i][0..wp) = src[i][0..words) padded with zeros
+void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t wp, uint32_t *dst, cudaStream_t stream);
+
+/// dst[i][0..words) = src[idx[i]][0..words)
+void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t words, uint32_t *dst,
+                         cudaStream_t stream);
 
 /// Scatters staged enveloppe rows into the pool: row i of the staging buffers goes to pool row
 /// dst_row[i] (= slot*K + r).
@@ -98,7 +106,8 @@ struct StreamArgs {
   uint4 *grp_sum;             ///< [n_groups] {accepted-unchanged births contributing 0, 1, 2; stopped early}
   uint32_t *act;              ///< [n_births] result words (zero-initialised by the caller)
   float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
-  uint32_t *row_counter;      ///< zero-initialised
+  uint32_t *row_counter;      ///< zero-initialised; rows are claimed in blocks of 8 per stream
+  int lut_in_smem = 0;        ///< set by the launcher
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream);

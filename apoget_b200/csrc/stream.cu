@@ -51,12 +51,12 @@ __device__ __forceinline__ double compat_generic (float4 m, double d) {     // c
 }
 
 template <bool LUT>
-__device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, float4 bm, float4 rm, double d) {
+__device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, const double *lut, float4 bm, float4 rm, double d) {
   double a, b;
   if (LUT) {
     const uint32_t di = uint32_t(d);
-    a = __ldg(cfg.lut + size_t(__float_as_uint(bm.w)) * cfg.lut_stride + di);
-    b = __ldg(cfg.lut + size_t(__float_as_uint(rm.w)) * cfg.lut_stride + di);
+    a = lut[size_t(__float_as_uint(bm.w)) * cfg.lut_stride + di];
+    b = lut[size_t(__float_as_uint(rm.w)) * cfg.lut_stride + di];
   } else {
     a = compat_generic(bm, d);
     b = compat_generic(rm, d);
@@ -72,6 +72,7 @@ struct WarpState {
   float *minBase;     // [K]
   float *d;           // [K][32]   distances of lane l to representative r at d[r*32 + l]
   double *c;          // [K][32]   compatibilities
+  const double *lut;  // compatibility table: shared-memory copy when it fits, else global
 };
 
 /// distance + compatibility of this lane's birth to representative r, stored in the lane's column
@@ -91,7 +92,7 @@ __device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[
     d = sqrt(acc);
   }
   ws.d[r * 32 + lane] = float(d);
-  ws.c[r * 32 + lane] = pair_compat<LUT>(cfg, bm, ws.rmeta[r], d);
+  ws.c[r * 32 + lane] = pair_compat<LUT>(cfg, ws.lut, bm, ws.rmeta[r], d);
 }
 
 /// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities
@@ -146,8 +147,6 @@ resolve_streams_kernel (StreamArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t g = blockIdx.x * SWARPS + warp;
-  if (g >= a.n_groups) return;
-
   const uint32_t K = a.pool.K;
   // carve this warp's slice: doubles first (8-byte aligned), then 16-byte items, then floats
   const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * WQ * 16 + size_t(K) * 16 + size_t(K) * K * 4
@@ -160,6 +159,16 @@ resolve_streams_kernel (StreamArgs a) {
   ws.D = reinterpret_cast<float*>(base);             base += size_t(K) * K * 4;
   ws.minBase = reinterpret_cast<float*>(base);       base += size_t(K) * 4;
   ws.d = reinterpret_cast<float*>(base);
+  // the compatibility table is read twice per (birth, representative): keep it next to the SM
+  ws.lut = a.cfg.lut;
+  if (LUT && a.lut_in_smem) {
+    double *lut_s = reinterpret_cast<double*>(smem + ((perWarp + 15) & ~size_t(15)) * SWARPS);
+    const uint32_t nd = a.cfg.lut_classes * a.cfg.lut_stride;
+    for (uint32_t i = threadIdx.x; i < nd; i += SWARPS * 32) lut_s[i] = __ldg(a.cfg.lut + i);
+    ws.lut = lut_s;
+    __syncthreads();
+  }
+  if (g >= a.n_groups) return;
 
   const uint32_t slot = a.grp_slot[g], sid = a.grp_sid[g];
   const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
@@ -184,6 +193,7 @@ resolve_streams_kernel (StreamArgs a) {
 
   uint32_t changed = 0;         // slots to write back
   bool aborted = false;
+  uint32_t rowNext = 0, rowLeft = 0;   // rows of the output buffer are claimed 8 at a time (one atomic per 8 entries)
 
   for (uint32_t cb = g0; cb < g1 && !aborted; cb += 32) {
     const uint32_t nb = min(32u, g1 - cb);
@@ -241,9 +251,13 @@ resolve_streams_kernel (StreamArgs a) {
       // ---- lane `stop` enters the enveloppe at slot `sl` ----
       const uint32_t sl = __shfl_sync(0xffffffffu, than, stop);
       const bool append = (k < K);
-      uint32_t row = 0;
-      if (lane == stop) row = atomicAdd(a.row_counter, 1u);
-      row = __shfl_sync(0xffffffffu, row, stop);
+      if (rowLeft == 0) {
+        if (lane == 0) rowNext = atomicAdd(a.row_counter, 8u);
+        rowNext = __shfl_sync(0xffffffffu, rowNext, 0);
+        rowLeft = 8;
+      }
+      const uint32_t row = rowNext++;
+      rowLeft--;
       // its k distances are the new matrix row (and what the host needs to mirror it), :676-677 / :712-715
       for (uint32_t r = lane; r < k; r += 32) {
         const float dr = ws.d[r * 32 + stop];
@@ -293,11 +307,15 @@ void launchWQ (const StreamArgs &a, cudaStream_t st) {
   const uint32_t K = a.pool.K;
   const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * WQ * 16 + size_t(K) * 16 + size_t(K) * K * 4
                        + size_t(K) * 4 + size_t(K) * 32 * 4;
-  const size_t smem = ((perWarp + 15) & ~size_t(15)) * SWARPS;
+  size_t smem = ((perWarp + 15) & ~size_t(15)) * SWARPS;
+  StreamArgs b = a;
+  const size_t lutBytes = size_t(a.cfg.lut_classes) * a.cfg.lut_stride * sizeof(double);
+  b.lut_in_smem = a.cfg.use_lut && lutBytes > 0 && lutBytes <= (size_t(48) << 10) && smem + lutBytes <= (size_t(200) << 10);
+  if (b.lut_in_smem) smem += lutBytes;
   const uint32_t grid = (a.n_groups + SWARPS - 1) / SWARPS;
   auto go = [&] (auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kernel<<<grid, SWARPS * 32, smem, st>>>(a);
+    kernel<<<grid, SWARPS * 32, smem, st>>>(b);
   };
   if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true>); else go(resolve_streams_kernel<WQ, 0, false>); }
   else go(resolve_streams_kernel<WQ, 1, false>);

@@ -82,9 +82,10 @@ class PhylogeneticTree:
         check(lib().apt_tree_add_genomes(self._h, n, payload_ptr, compat_ptr, *ids, sid, slot, rep,
                                          ctypes.byref(done)))
 
-    def add_genomes_dev(self, n, d_payload_ptr, d_compat_ptr, stream, ids, sid, slot, rep):
+    def add_genomes_dev(self, n, d_payload_ptr, compat_ptr, stream, ids, sid, slot, rep):
+        """Payloads resident in device memory (raw pointer), everything else host pointers."""
         done = ctypes.c_uint32()
-        check(lib().apt_tree_add_genomes_dev(self._h, n, d_payload_ptr, d_compat_ptr, stream, *ids, sid, slot,
+        check(lib().apt_tree_add_genomes_dev(self._h, n, d_payload_ptr, compat_ptr, stream, *ids, sid, slot,
                                              rep, ctypes.byref(done)))
 
     def del_genome(self, sid: int):
@@ -152,7 +153,7 @@ class PhylogeneticTree:
                     n_children=info.n_children, n_contributors=info.n_contributors)
 
     # -- trace replay (same loop as oracle/ref_driver.cpp) -----------------------------------------
-    def replay(self, trace, max_gens: int | None = None):
+    def replay(self, trace, max_gens: int | None = None, to_device=None):
         """Feeds a synth.Trace generation by generation: one add_genomes batch per generation, then
         the deaths, then step().  Returns (sid per birth, slot per birth)."""
         B = trace.n_births
@@ -168,7 +169,18 @@ class PhylogeneticTree:
             msid = np.where(hm, sid_of[np.where(hm, m, 0)], INVALID).astype(np.uint32)
             fsid = np.where(hf, sid_of[np.where(hf, f, 0)], INVALID).astype(np.uint32)
             gid = np.arange(b0 + 1, b1 + 1, dtype=np.uint32)
-            s, sl, _ = self.add_genomes(trace.payload[b0:b1], trace.compat[b0:b1], gid, mgid, msid, fgid, fsid)
+            if to_device is None:
+                s, sl, _ = self.add_genomes(trace.payload[b0:b1], trace.compat[b0:b1], gid, mgid, msid, fgid, fsid)
+            else:
+                # payloads handed over as a device pointer: to_device(ndarray) -> (keep-alive object, pointer, stream)
+                keep, dptr, stream = to_device(np.ascontiguousarray(trace.payload[b0:b1]))
+                compat = np.ascontiguousarray(trace.compat[b0:b1], dtype=np.float32)
+                s = np.full(b1 - b0, INVALID, dtype=np.uint32)
+                sl = np.full(b1 - b0, -1, dtype=np.int32)
+                rp = np.full(b1 - b0, INVALID, dtype=np.uint32)
+                self.add_genomes_dev(b1 - b0, ctypes.c_void_p(dptr), _ptr(compat), ctypes.c_void_p(stream),
+                                     [_ptr(x) for x in (gid, mgid, msid, fgid, fsid)], _ptr(s), _ptr(sl), _ptr(rp))
+                del keep
             sid_of[b0:b1], slot_of[b0:b1] = s, sl
             self.del_genomes(sid_of[trace.deaths_of(g)])
             self.step(g + 1, sid_of[trace.alive_of(g)])

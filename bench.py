@@ -212,7 +212,6 @@ def main() -> None:
     pin_slot = torch.empty(pop, dtype=torch.int32).pin_memory()
     pin_rep = torch.empty(pop, dtype=torch.int32).pin_memory()
     dev_payload = torch.empty((pop, W), dtype=torch.int32, device="cuda")
-    dev_compat = torch.empty((pop, 3), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     vp = ctypes.c_void_p
     stream = torch.cuda.current_stream()
@@ -240,7 +239,6 @@ def main() -> None:
         finish_gen(tree_h, g, sid_h)
         # --- value: payloads already resident in HBM ------------------------------------------------
         dev_payload.copy_(pin_payload, non_blocking=True)
-        dev_compat.copy_(pin_compat, non_blocking=True)
         ids = ids_for(g, sid_d)
         flush.fill_((g + 1) & 0xFF)
         if world > 1:
@@ -248,7 +246,7 @@ def main() -> None:
         torch.cuda.synchronize()
         d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d0.record(stream)
-        tree_d.add_genomes_dev(pop, vp(dev_payload.data_ptr()), vp(dev_compat.data_ptr()), vp(stream.cuda_stream),
+        tree_d.add_genomes_dev(pop, vp(dev_payload.data_ptr()), vp(pin_compat.data_ptr()), vp(stream.cuda_stream),
                                [vp(x.ctypes.data) for x in ids],
                                vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
         d1.record(stream)

@@ -108,9 +108,10 @@ int apt_tree_add_genomes (apt_tree *t, uint32_t n, const uint32_t *payload, cons
                           uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced_gid,
                           uint32_t *n_done);
 
-/* Same, with payload and compat already resident in device memory (d_payload: n*words u32,
- * d_compat: n*3 f32), ordered after `stream`. */
-int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload, const float *d_compat,
+/* Same, with the payloads already resident in device memory (d_payload: n*words u32, ordered after
+ * `stream`); compat and the id arrays are host arrays as above.  The kernels read the payloads in
+ * place; only the rows of births that change something are copied back for the host mirror. */
+int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload, const float *compat,
                               void *stream,
                               const uint32_t *gid, const uint32_t *mother_gid, const uint32_t *mother_sid,
                               const uint32_t *father_gid, const uint32_t *father_sid,

@@ -110,6 +110,17 @@ void launch_pack_births (const uint32_t *src, const float *compat, const uint32_
   }
 }
 
+void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t wp, uint32_t *dst, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) {
+    memset(dst + size_t(i) * wp, 0, wp * 4);
+    memcpy(dst + size_t(i) * wp, src + size_t(i) * words, words * 4);
+  }
+}
+
+void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t words, uint32_t *dst, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) memcpy(dst + size_t(i) * words, src + size_t(idx[i]) * words, words * 4);
+}
+
 void launch_scatter_rows (const uint32_t *sp, const float4 *sm, const uint32_t *dst, uint32_t n, uint32_t wp,
                           uint32_t *pp, float4 *pm, cudaStream_t) {
   for (uint32_t i = 0; i < n; i++) {

@@ -190,3 +190,24 @@ def test_pairwise_kernel(kind, words):
         assert np.array_equal(out, exp)
     else:
         assert np.allclose(out, exp, rtol=F32_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "ragged_b96_k3", "c4_b4096_k10"])
+def test_tree_device_resident_payloads(name):
+    """apt_tree_add_genomes_dev: payloads stay in HBM, the host fetches only the rows it needs."""
+    import torch
+    from apoget_b200.tree import PhylogeneticTree
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    tree = PhylogeneticTree(t.kind, t.words, **cfg)
+
+    def to_device(a):
+        d = torch.from_numpy(a.view(np.int32)).cuda()
+        torch.cuda.synchronize()
+        return d, d.data_ptr(), torch.cuda.current_stream().cuda_stream
+
+    sids, _ = tree.replay(t, to_device=to_device)
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"])
+    assert np.array_equal(tree.events(), ref["events"])
+    assert tree.to_json() == golden_json(name)

@@ -139,3 +139,17 @@ def test_randomised_traces_against_oracle(hostsim, seed, tmp_path):
     assert st == ost
     assert np.array_equal(tree.events(), o.events())
     assert tree.to_json() == o.to_json()
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "ragged_b96_k3", "c5_speciation_trimming"])
+def test_device_resident_payload_entry_point(hostsim, name):
+    """apt_tree_add_genomes_dev (payload rows fetched lazily for the births the host looks at); in the
+    host simulation "device" memory is host memory."""
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, _ = tree.replay(t, to_device=lambda a: (a, a.ctypes.data, 0))
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"])
+    assert np.array_equal(tree.events(), ref["events"])
+    assert tree.to_json() == golden_json(name)
