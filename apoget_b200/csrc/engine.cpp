@@ -56,6 +56,7 @@ Engine::Engine (const apt_params &p) : p_(p) {
   cudaCheck(cudaEventCreate(&evS1_), "cudaEventCreate");
   // the device resolves streams for the default criteria; vote-count scoring needs the exact table
   // (a flipped vote cannot be seen from the score, so no guard band protects it)
+  childKernel_ = !(p.flags & APT_FLAG_NO_CHILD_KERNEL);
   streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
               && (p.full_continuous || lutMode_);
 }
@@ -178,8 +179,10 @@ void Engine::updateContributions (Species *s, const Contributions &contrib) {
     if (oldMC) {
       auto &c = oldMC->children;
       c.erase(std::remove(c.begin(), c.end(), s), c.end());
+      oldMC->child_change_epoch = chunkEpoch_;
     }
     newMC->children.push_back(s);
+    newMC->child_change_epoch = chunkEpoch_;
     updateElligibilities();
     // the reference dereferences a null oldMC here (:765-766); INVALID is reported instead
     emit(APT_EV_MAJOR_CONTRIBUTOR, s->sid, oldMC ? oldMC->sid : INV, newMC->sid);
@@ -632,6 +635,50 @@ void Engine::resolveBelow (const uint32_t *w, const RepMeta &g, Species *s0, Spe
   }
 }
 
+/// findBestDerived for a birth a device stream rejected at top level: the sub-species kernel already
+/// walked the sub-species its species had when the chunk was submitted (newest first, stopping at
+/// the first acceptance).  Its verdict on a sub-species is used when that enveloppe is, at this
+/// point of the ordered commit, exactly what the kernel saw: untouched by the host, and not entered
+/// by any later birth of its own stream.  Sub-species founded inside the chunk come first (:506) and
+/// are scored here, as are those the kernel's view is not valid for.
+void Engine::resolveBelowStream (const uint32_t *w, const RepMeta &g, Species *s0, int64_t ft, Species *&best,
+                                 float &bestScore, Eval &bestEval) {
+  const GroupState &st = grpState_[s0->grp_index];
+  const bool dev = ft >= 0 && s0->child_change_epoch != chunkEpoch_;
+  const size_t snapN = st.snapChildren;
+  const uint32_t firstRank = dev ? hFtFirst_.p[ft] : 0u;
+  const bool firstUnsure = dev && (hFtFlags_.p[ft] & 1u);
+  Eval cur;
+  size_t idx = s0->children.size();
+  while (idx-- > 0) {
+    Species *sub = s0->children[idx];
+    branching_++;
+    bool decided = false;
+    if (dev && idx < snapN) {
+      const uint32_t rank = uint32_t(snapN - 1 - idx);
+      const bool known = rank < firstRank || (rank == firstRank && !firstUnsure);
+      if (known && sub->stale_mask == 0 && !sub->full_upload && sub->div_epoch != chunkEpoch_ &&
+          (sub->grp_epoch != chunkEpoch_ || grpState_[sub->grp_index].lastEnter < int64_t(curBirth_))) {
+        touchSnap(sub);
+        comparisons_ += sub->k;
+        counters[1]++;
+        decided = true;
+        if (rank == firstRank) {                            // first acceptance: done (:540-541)
+          best = sub;  bestScore = hFtScore_.p[ft];
+          memcpy(bestEval.d, hFtDist_.p + size_t(ft) * K_, sub->k * sizeof(float));
+          bestEval.score = bestScore;  bestEval.exact = lutMode_;
+          return;
+        }
+      }
+    }
+    if (!decided) {
+      evalSpeculated(w, g, sub, -1, cur);
+      if (bestScore < cur.score) { best = sub; bestScore = cur.score; bestEval = cur; }
+      if (bestScore > 0) return;
+    }
+  }
+}
+
 /// :612-643: insert into the best species, or found a new one
 void Engine::finishBirth (const uint32_t *w, RepMeta &g, Species *best, float bestScore, const Eval &bestEval,
                           const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced) {
@@ -718,7 +765,7 @@ void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t ac
     Species *best = nullptr;
     Eval bestEval;
     float bestScore = 0.f;          // any value <= 0: the actual top-level score only matters by its sign (:612, :534)
-    resolveBelow(w, g, s0, nullptr, best, bestScore, bestEval);
+    resolveBelowStream(w, g, s0, curFt_, best, bestScore, bestEval);
     Contributions contrib { { g.msid, 1u + (g.msid == g.fsid) } };
     finishBirth(w, g, best, bestScore, bestEval, contrib, sid, slot, replaced);
     return;
@@ -960,6 +1007,23 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         hOrder_.p[hGrpOff_.p[g] + grpCount_[g]++] = i | (ccls << ORDER_CLASS_SHIFT);
       }
   }
+  // sub-species of every stream's species, in the reference's visiting order (newest first, :506)
+  size_t nChild = 0;
+  const bool useChildKernel = G && childKernel_;
+  if (useChildKernel) {
+    size_t total = 0;
+    for (uint32_t g = 0; g < G; g++) total += grpSpecies_[g]->children.size();
+    hChildOff_.reserve(G + 1);  hChildSlot_.reserve(total + 1);
+    for (uint32_t g = 0; g < G; g++) {
+      hChildOff_.p[g] = uint32_t(nChild);
+      const auto &ch = grpSpecies_[g]->children;
+      for (size_t idx = ch.size(); idx-- > 0; ) {
+        const Species *c = ch[idx];
+        hChildSlot_.p[nChild++] = (c->dev_fill && c->dev_fill == c->k && !c->stale_mask && !c->full_upload) ? c->slot : INV;
+      }
+    }
+    hChildOff_.p[G] = uint32_t(nChild);
+  }
   uploadLut();
   timers[0] += now() - t0;
   t0 = now();
@@ -1010,6 +1074,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     counters[7] += P;
   }
   uint32_t nRows = 0;
+  nFt_ = 0;
   if (G) {
     // the ordered resolution of the single-parent births, one warp per species stream; it runs
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
@@ -1033,11 +1098,35 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.n_groups = G;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
     a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dRowCounter_.p;
     a.grp_sid = dGrpSid_.p;  a.out_sid = dOutSid_.p;  a.out_slot = dOutSlot_.p;  a.grp_sum = dGrpSum_.p;
+    a.ft_list = nullptr;  a.ft_counter = nullptr;
+    if (useChildKernel) {
+      dFtList_.reserve(2 * nStream);  dFtCounter_.reserve(1);  hFtCounter_.reserve(1);
+      cudaCheck(cudaMemsetAsync(dFtCounter_.p, 0, 4, stream_), "ft counter clear");
+      a.ft_list = dFtList_.p;  a.ft_counter = dFtCounter_.p;
+    }
     cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
     launch_resolve_streams(a, stream_);
     cudaCheck(cudaEventRecord(evS1_, stream_), "event record");
     counters[4]++;  counters[12]++;  counters[13] += nStream;
     cudaCheck(cudaGetLastError(), "resolve_streams launch");
+    if (useChildKernel && nChild) {
+      // the births the streams rejected walk the sub-species on the device too (pool as the streams left it)
+      dChildOff_.reserve(G + 1);  dChildSlot_.reserve(nChild);
+      dFtFirst_.reserve(nStream);  dFtFlags_.reserve(nStream);  dFtScore_.reserve(nStream);  dFtDist_.reserve(nStream * K_);
+      cudaCheck(cudaMemcpyAsync(dChildOff_.p, hChildOff_.p, (G + 1) * 4, cudaMemcpyHostToDevice, stream_), "children");
+      cudaCheck(cudaMemcpyAsync(dChildSlot_.p, hChildSlot_.p, nChild * 4, cudaMemcpyHostToDevice, stream_), "children");
+      ChildArgs c;
+      c.pool = poolView();  c.cfg = scoreCfg();  c.guard = GUARD;
+      c.b_payload = dBirthRows;  c.b_cmeta = dBMeta_.p;
+      c.ft_list = dFtList_.p;  c.ft_counter = dFtCounter_.p;  c.max_ft = uint32_t(nStream);
+      c.child_off = dChildOff_.p;  c.child_slot = dChildSlot_.p;
+      c.out_first = dFtFirst_.p;  c.out_flags = dFtFlags_.p;  c.out_score = dFtScore_.p;  c.out_dist = dFtDist_.p;
+      launch_classify_children(c, stream_);
+      counters[4]++;
+      cudaCheck(cudaGetLastError(), "classify_children launch");
+    }
+    if (useChildKernel)
+      cudaCheck(cudaMemcpyAsync(hFtCounter_.p, dFtCounter_.p, 4, cudaMemcpyDeviceToHost, stream_), "ft counter");
     cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
     cudaCheck(cudaMemcpyAsync(hRowCounter_.p, dRowCounter_.p, 4, cudaMemcpyDeviceToHost, stream_), "row counter");
     cudaCheck(cudaMemcpyAsync(hOutSid_.p, dOutSid_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
@@ -1051,11 +1140,21 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (G) {
       cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
       nRows = hRowCounter_.p[0];
+      nFt_ = (useChildKernel && nChild) ? hFtCounter_.p[0] : 0u;
       if (nRows) {
         hRows_.reserve(size_t(nRows) * K_);
         cudaCheck(cudaMemcpyAsync(hRows_.p, dRows_.p, size_t(nRows) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "rows");
-        cudaCheck(cudaStreamSynchronize(stream_), "rows");
       }
+      if (nFt_) {
+        hFtList_.reserve(2 * size_t(nFt_));  hFtFirst_.reserve(nFt_);  hFtFlags_.reserve(nFt_);
+        hFtScore_.reserve(nFt_);  hFtDist_.reserve(size_t(nFt_) * K_);
+        cudaCheck(cudaMemcpyAsync(hFtList_.p, dFtList_.p, 2 * size_t(nFt_) * 4, cudaMemcpyDeviceToHost, stream_), "ft list");
+        cudaCheck(cudaMemcpyAsync(hFtFirst_.p, dFtFirst_.p, size_t(nFt_) * 4, cudaMemcpyDeviceToHost, stream_), "ft first");
+        cudaCheck(cudaMemcpyAsync(hFtFlags_.p, dFtFlags_.p, size_t(nFt_) * 4, cudaMemcpyDeviceToHost, stream_), "ft flags");
+        cudaCheck(cudaMemcpyAsync(hFtScore_.p, dFtScore_.p, size_t(nFt_) * 4, cudaMemcpyDeviceToHost, stream_), "ft score");
+        cudaCheck(cudaMemcpyAsync(hFtDist_.p, dFtDist_.p, size_t(nFt_) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "ft dist");
+      }
+      if (nRows || nFt_) cudaCheck(cudaStreamSynchronize(stream_), "rows");
     }
   }
   timers[1] += now() - t0;
@@ -1072,11 +1171,20 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (outSid) memcpy(outSid, hOutSid_.p, size_t(n) * 4);
     if (outSlot) memcpy(outSlot, hOutSlot_.p, size_t(n) * 4);
     if (outReplaced) memset(outReplaced, 0xFF, size_t(n) * 4);
-    for (uint32_t i = 0; i < n; i++)
-      if (birthGroup_[i] < 0 || hAct_.p[i] != ACT_ACCEPTED) slow_.push_back(i);
+    for (uint32_t i = 0; i < n; i++) {
+      if (birthGroup_[i] >= 0 && hAct_.p[i] == ACT_ACCEPTED) continue;
+      slow_.push_back(i);
+      if (birthGroup_[i] >= 0 && (hAct_.p[i] & ACT_CODE_MASK) == ACT_ENTERED) grpState_[size_t(birthGroup_[i])].lastEnter = i;
+    }
+    for (uint32_t g = 0; g < G; g++) grpState_[g].snapChildren = uint32_t(grpSpecies_[g]->children.size());
   } else {
     slow_.resize(n);
     for (uint32_t i = 0; i < n; i++) slow_[i] = i;
+  }
+  ftOfSlow_.assign(slow_.size(), -1);
+  for (uint32_t e = 0; e < nFt_; e++) {
+    auto it = std::lower_bound(slow_.begin(), slow_.end(), hFtList_.p[2 * e]);
+    if (it != slow_.end() && *it == hFtList_.p[2 * e]) ftOfSlow_[size_t(it - slow_.begin())] = int32_t(e);
   }
   curDevPayload_ = payload ? nullptr : dPayload;
   lateRows_.clear();
@@ -1103,7 +1211,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       if (!heap.empty() && (si >= slow_.size() || heap.front() < slow_[si])) {
         std::pop_heap(heap.begin(), heap.end(), heapCmp);
         i = heap.back();  heap.pop_back();
-      } else if (si < slow_.size()) i = slow_[si++];
+        curFt_ = -1;
+      } else if (si < slow_.size()) { curFt_ = ftOfSlow_[si]; i = slow_[si++]; }
       else break;
       curBirth_ = i;
       Species *s0 = nullptr;

@@ -110,6 +110,7 @@ struct Species {
   uint32_t div_epoch = 0;                 // ... and the host took that stream over (device results discarded)
   uint32_t snap_epoch = 0, snap_mask = 0, snap_fill = 0;  // slots changed since the chunk's device snapshot
   uint32_t self_idx = 0;                  // where this species' own entry sits in contribs (hint)
+  uint32_t child_change_epoch = 0;        // chunk in which a sub-species was moved into / out of this node
   bool full_upload = false;               // the device copy (rows, matrix, fill) must be rewritten entirely
   uint32_t touch_epoch = 0;               // last scoring launch that read this enveloppe
   bool extinct (void) const { return alive == 0 && pending == 0; }   // node.hpp:157-159
@@ -196,6 +197,8 @@ private:
     uint32_t cursor = 0;                  // position in the stream's order list reached by catch-up scans
     uint32_t scanned[3] = {0, 0, 0};      // accepted-unchanged births seen by those scans, per contribution class
     uint32_t selfApplied = 0;             // self-contribution already credited to the species' own entry
+    uint32_t snapChildren = 0;            // sub-species the stream's species had when the chunk was submitted
+    int64_t lastEnter = -1;               // last birth of the chunk the device let into this enveloppe
   };
   std::vector<GroupState> grpState_;
   std::vector<int32_t> sidGroup_;         // per-chunk cache: sid -> stream index, -1 not streamable, -2 not looked up yet
@@ -207,6 +210,13 @@ private:
   const uint32_t *curDevPayload_ = nullptr;
   DevBuf<uint32_t> dSlowIdx_, dSlowRows_;  PinBuf<uint32_t> hSlowIdx_, hSlowRows_;
   std::vector<std::vector<uint32_t>> lateRows_;
+  // sub-species kernel (K2)
+  bool childKernel_ = true;
+  DevBuf<uint32_t> dChildOff_, dChildSlot_, dFtList_, dFtCounter_, dFtFirst_, dFtFlags_;  DevBuf<float> dFtScore_, dFtDist_;
+  PinBuf<uint32_t> hChildOff_, hChildSlot_, hFtList_, hFtCounter_, hFtFirst_, hFtFlags_;  PinBuf<float> hFtScore_, hFtDist_;
+  std::vector<int32_t> ftOfSlow_;         // entry of the sub-species results for slow_[i], -1 = none
+  uint32_t nFt_ = 0;
+  int64_t curFt_ = -1;                    // sub-species result entry of the birth being committed
   uint32_t chunkEpoch_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
@@ -249,6 +259,7 @@ private:
   void queueRefresh (Species *s) { if (!s->queued) { s->queued = true; refresh_.push_back(s); } }
   void walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t act, uint32_t &sid, int32_t &slot, uint32_t &replaced);
   void resolveBelow (const uint32_t *w, const RepMeta &g, Species *s0, Species *s1, Species *&best, float &bestScore, Eval &bestEval);
+  void resolveBelowStream (const uint32_t *w, const RepMeta &g, Species *s0, int64_t ft, Species *&best, float &bestScore, Eval &bestEval);
   void finishBirth (const uint32_t *w, RepMeta &g, Species *best, float bestScore, const Eval &bestEval,
                     const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced);
   void selfContribution (Species *s, uint32_t count);

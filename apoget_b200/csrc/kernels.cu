@@ -124,6 +124,32 @@ score_pairs_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__restrict__ b_
   if (lane == 0) out_score[p] = s;
 }
 
+/// K2: sub-species walk of one rejected birth per warp (see ChildArgs)
+template <int LPR, int KIND, bool LUT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+classify_children_kernel (ChildArgs a) {
+  __shared__ double c_smem[WARPS_PER_CTA][KMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t e = blockIdx.x * WARPS_PER_CTA + warp;
+  if (e >= min(__ldg(a.ft_counter), a.max_ft)) return;
+  const uint32_t b = __ldg(a.ft_list + 2 * e), g = __ldg(a.ft_list + 2 * e + 1);
+  const uint32_t c0 = __ldg(a.child_off + g), c1 = __ldg(a.child_off + g + 1);
+  const uint4 *bq = reinterpret_cast<const uint4*>(a.b_payload) + size_t(b) * (a.pool.wp >> 2);
+  const float4 bm = __ldg(a.b_cmeta + b);
+  float *od = a.out_dist + size_t(e) * a.pool.K;
+  uint32_t first = 0xFFFFFFFFu, flags = 0;
+  float score = 0.f;
+  for (uint32_t c = c0; c < c1; c++) {
+    const uint32_t slot = __ldg(a.child_slot + c);
+    if (slot == 0xFFFFFFFFu) { first = c - c0; flags = 1u; break; }          // the host knows this one only
+    score = warp_score<LPR, KIND, LUT>(a.pool, a.cfg, bq, bm, slot, c_smem[warp], od, lane);
+    const bool unsure = !LUT && (fabsf(score) <= a.guard || !a.cfg.full_continuous);
+    if (unsure) { first = c - c0; flags = 1u; break; }
+    if (score > 0.f) { first = c - c0; break; }                              // :540-541
+  }
+  if (lane == 0) { a.out_first[e] = first;  a.out_flags[e] = flags;  a.out_score[e] = score; }
+}
+
 /// Dense sweep, first version: one warp per birth walking every slot of the pool.
 template <int LPR, int KIND, bool LUT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -284,6 +310,14 @@ struct ScorePairsLauncher {
 };
 
 template <int LPR, int KIND, bool LUT>
+struct ChildrenLauncher {
+  static void run (const ChildArgs &a, cudaStream_t st) {
+    const uint32_t grid = (a.max_ft + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    classify_children_kernel<LPR, KIND, LUT><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
+  }
+};
+
+template <int LPR, int KIND, bool LUT>
 struct DenseLauncher {
   static void run (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *bp, const float4 *bm, uint32_t n,
                    uint32_t *ob, float *obs, uint32_t *of, uint32_t *oc, cudaStream_t st) {
@@ -300,6 +334,11 @@ void launch_score_pairs (const PoolView &pool, const ScoreCfg &cfg, const uint32
   if (!n_pairs) return;
   dispatch<ScorePairsLauncher>(lanes_per_rep(pool.wp), cfg.kind, cfg.use_lut != 0, pool, cfg, b_payload, b_cmeta,
                                n_pairs, pair_birth, pair_slot, out_score, out_dist, stream);
+}
+
+void launch_classify_children (const ChildArgs &a, cudaStream_t stream) {
+  if (!a.max_ft) return;
+  dispatch<ChildrenLauncher>(lanes_per_rep(a.pool.wp), a.cfg.kind, a.cfg.use_lut != 0, a, stream);
 }
 
 void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *b_payload,

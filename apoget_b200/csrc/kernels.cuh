@@ -106,11 +106,33 @@ struct StreamArgs {
   uint4 *grp_sum;             ///< [n_groups] {accepted-unchanged births contributing 0, 1, 2; stopped early}
   uint32_t *act;              ///< [n_births] result words (zero-initialised by the caller)
   float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
+  uint32_t *ft_list;          ///< births rejected at top level, appended as (birth, stream) pairs ...
+  uint32_t *ft_counter;       ///< ... counted here (zero-initialised)
   uint32_t *row_counter;      ///< zero-initialised; rows are claimed in blocks of 8 per stream
   int lut_in_smem = 0;        ///< set by the launcher
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream);
+
+/// K2 -- findBestDerived (phylogenetictree.hpp:493-548) for the births a stream rejected at top level:
+/// one warp per rejected birth walks the sub-species of its species in the reference's visiting
+/// order (newest first) and stops at the first score > 0 (:540-541).
+struct ChildArgs {
+  PoolView pool;
+  ScoreCfg cfg;
+  float guard;
+  const uint32_t *b_payload;  const float4 *b_cmeta;
+  const uint32_t *ft_list;    ///< (birth, stream) pairs written by the stream kernel
+  const uint32_t *ft_counter; ///< how many
+  uint32_t max_ft;            ///< capacity (grid is sized for it; surplus warps exit)
+  const uint32_t *child_off;  ///< [n_groups+1] offsets into child_slot
+  const uint32_t *child_slot; ///< sub-species slots per stream, visiting order; APT_INVALID = not on the device
+  uint32_t *out_first;        ///< [max_ft] rank of the first accepting sub-species, or APT_INVALID
+  uint32_t *out_flags;        ///< [max_ft] bit 0: the walk stopped at out_first because its score needs the host
+  float *out_score;           ///< [max_ft] score at out_first
+  float *out_dist;            ///< [max_ft][K] distances to the representatives of out_first
+};
+void launch_classify_children (const ChildArgs &a, cudaStream_t stream);
 
 /// dst[idx[i]*len .. +len) = src[i*len .. +len)
 void launch_scatter_blocks_f32 (const float *src, const uint32_t *idx, uint32_t n, uint32_t len, float *dst,

@@ -238,6 +238,17 @@ resolve_streams_kernel (StreamArgs a) {
         a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
         if (accept) a.out_sid[b] = sid;
       }
+      // births rejected at top level queue up for the sub-species kernel (one atomic per warp step)
+      const uint32_t ftm = __ballot_sync(0xffffffffu, fin && !accept);
+      if (ftm && a.ft_list) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.ft_counter, uint32_t(__popc(ftm)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (fin && !accept) {
+          const uint32_t at = base + __popc(ftm & ((1u << lane) - 1u));
+          a.ft_list[2 * at] = b;  a.ft_list[2 * at + 1] = g;
+        }
+      }
       nAcc0 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 0));
       nAcc1 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 1));
       nAcc2 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 2));

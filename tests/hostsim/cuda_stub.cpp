@@ -168,7 +168,11 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       }
       const float score = a.cfg.full_continuous ? float(avg / float(k) - a.cfg.avg_thr) : float(matable - a.cfg.sim_thr * k);
       if (!a.cfg.use_lut && std::fabs(score) <= a.guard) { a.act[b] = ACT_UNCERTAIN; aborted = true; break; }
-      if (!(score > 0)) { a.act[b] = ACT_FALLTHROUGH; continue; }
+      if (!(score > 0)) {
+        a.act[b] = ACT_FALLTHROUGH;
+        if (a.ft_list) { const uint32_t at = (*a.ft_counter)++; a.ft_list[2 * at] = b; a.ft_list[2 * at + 1] = g; }
+        continue;
+      }
       uint32_t than = 0xFFFFFFFFu;
       bool modifies = false, append = false;
       if (k < K) { modifies = append = true; than = k; }
@@ -212,6 +216,23 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       memcpy(a.pool_dist + size_t(slot) * K * K, D.data(), size_t(K) * K * sizeof(float));
       a.pool_fill_w[slot] = k;
     }
+  }
+}
+
+void launch_classify_children (const ChildArgs &a, cudaStream_t) {
+  const uint32_t n = *a.ft_counter < a.max_ft ? *a.ft_counter : a.max_ft;
+  for (uint32_t e = 0; e < n; e++) {
+    const uint32_t b = a.ft_list[2 * e], g = a.ft_list[2 * e + 1];
+    uint32_t first = 0xFFFFFFFFu, flags = 0;
+    float sc = 0;
+    for (uint32_t c = a.child_off[g]; c < a.child_off[g + 1]; c++) {
+      const uint32_t slot = a.child_slot[c], rank = c - a.child_off[g];
+      if (slot == 0xFFFFFFFFu) { first = rank; flags = 1; break; }
+      sc = score(a.pool, a.cfg, a.b_payload + size_t(b) * a.pool.wp, a.b_cmeta[b], slot, a.out_dist + size_t(e) * a.pool.K);
+      if (!a.cfg.use_lut && (std::fabs(sc) <= a.guard || !a.cfg.full_continuous)) { first = rank; flags = 1; break; }
+      if (sc > 0) { first = rank; break; }
+    }
+    a.out_first[e] = first;  a.out_flags[e] = flags;  a.out_score[e] = sc;
   }
 }
 
