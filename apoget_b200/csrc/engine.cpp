@@ -732,7 +732,13 @@ void Engine::walkOne (const uint32_t *w, RepMeta &g, int64_t p0, int64_t p1, uin
   }
   if (best) bestEval = (best == s1 && s1) ? ev1 : ev0;
 
-  if (!(bestScore > 0)) resolveBelow(w, g, s0, s1, best, bestScore, bestEval);
+  if (!(bestScore > 0)) {
+    // a single-parent birth whose stream was handed back may still have a sub-species verdict from the
+    // device (it depends on the birth and on the sub-species only, not on what became of the stream)
+    if (!s1 && curFt_ >= 0 && s0->grp_epoch == chunkEpoch_ && !grpState_.empty())
+      resolveBelowStream(w, g, s0, curFt_, best, bestScore, bestEval);
+    else resolveBelow(w, g, s0, s1, best, bestScore, bestEval);
+  }
   finishBirth(w, g, best, bestScore, bestEval, contrib, sid, slot, replaced);
 }
 
