@@ -10,10 +10,11 @@ drawn from the previous generation, classified by one batched addGenome
 sequential semantics.  Timed per step: the add_genomes call only (the hot path); deaths and step()
 bookkeeping run between timed regions, as in oracle/ref_driver.cpp which times the same loop.
 
-  value : births/s with each step's payloads already resident in HBM (apt_tree_add_genomes_dev)
+  value : births/s with each step's payloads already resident in HBM (apt_tree_add_genomes_dev, read in place)
   e2e   : births/s through apt_tree_add_genomes with pinned HOST buffers (H2D + kernels + D2H + the
-          ordered resolution pass inside the timed region)
-  roofline : the score-pairs kernel, timed with CUDA events on the engine's own stream
+          ordered commit on the host inside the timed region)
+  roofline : the dominant kernel (resolve_streams: the ordered resolution on the device), timed with
+          CUDA events on the engine's own stream
   cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref/apt_ref_driver, one
           thread -- the reference is single-threaded and the tree is sequential) on the same trace.
 
@@ -44,7 +45,7 @@ SETUP_GENS = 4          # generations 0..3: root + three 10-way radiations -> 1 
 WORKLOAD = dict(kind=synth.BITS, words=8, flips=0.5, sigma=12.0, hybrid=0.05, burst_levels=3, burst_fanout=10)
 TREE_CFG = dict(K=10)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/)
-TRAFFIC = {"score_pairs_kernel": 6.10e6}
+TRAFFIC = {"score_pairs_kernel": 6.10e6, "resolve_streams_kernel": 6.14e6}
 METRIC = "births classified/sec (species assignment, reference-exact)"
 UNIT = "births/s"
 

@@ -25,16 +25,16 @@ CONFIGS = {  # name: (kind, words, K, species, births, sigma)
     "c2": (0, 8, 10, 1_000, 100_000, 12.0),
     "c2x": (0, 8, 10, 10_000, 1_000_000, 12.0),
     "c3": (1, 64, 10, 10_000, 65_536, 0.4),
-    "c4": (0, 128, 10, 10_000, 1_000_000, 100.0),
+    "c4": (0, 128, 10, 10_000, 1_000_000, 60.0),
 }
 
 
 def make_pool(rng, kind, words, S, K, sigma):
     if kind == 0:
         base = rng.integers(0, 2**32, size=(S, 1, words), dtype=np.uint32)
-        noise = rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) \
-            & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32) \
-            & rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32)      # ~3 % of the bits differ
+        noise = rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32)
+        for _ in range(4 if words <= 8 else 6):     # AND of random words: ~3 % (short genomes) / ~0.8 % of the bits differ
+            noise &= rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32)
         reps = base ^ noise
     else:
         base = rng.standard_normal((S, 1, words)).astype(np.float32)
