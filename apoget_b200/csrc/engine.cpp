@@ -997,13 +997,14 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
   }
   const uint32_t G = uint32_t(grpSpecies_.size());
+  uint32_t maxStream = 0;
   if (G) {
     hGrpSlot_.reserve(G);  hGrpOff_.reserve(G + 1);  hOrder_.reserve(nStream);
     uint32_t off = 0;
     hGrpSid_.reserve(G);
     for (uint32_t g = 0; g < G; g++) {
       hGrpSlot_.p[g] = grpSpecies_[g]->slot;  hGrpSid_.p[g] = grpSpecies_[g]->sid;
-      hGrpOff_.p[g] = off;  off += grpCount_[g];  grpCount_[g] = 0;
+      hGrpOff_.p[g] = off;  off += grpCount_[g];  maxStream = std::max(maxStream, grpCount_[g]);  grpCount_[g] = 0;
     }
     hGrpOff_.p[G] = off;
     for (uint32_t i = 0; i < n; i++)
@@ -1101,7 +1102,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.pool_payload_w = dPool_.p;  a.pool_cmeta_w = dMeta_.p;  a.pool_fill_w = dFill_.p;  a.pool_dist = dPoolDist_.p;
     a.cfg = scoreCfg();  a.crit = p_.env_crit;  a.guard = GUARD;
     a.b_payload = dBirthRows;  a.b_cmeta = dBMeta_.p;
-    a.n_groups = G;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
+    a.n_groups = G;  a.max_stream = maxStream;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
     a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dRowCounter_.p;
     a.grp_sid = dGrpSid_.p;  a.out_sid = dOutSid_.p;  a.out_slot = dOutSlot_.p;  a.grp_sum = dGrpSum_.p;
     a.ft_list = nullptr;  a.ft_counter = nullptr;

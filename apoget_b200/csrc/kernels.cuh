@@ -95,6 +95,7 @@ struct StreamArgs {
   float guard;                ///< |score| below which a non-table score is not trusted
   const uint32_t *b_payload;  const float4 *b_cmeta;
   uint32_t n_groups;
+  uint32_t max_stream;        ///< births in the longest stream (picks the CTA width)
   const uint32_t *grp_slot;   ///< [n_groups] pool slot of the stream's species
   const uint32_t *grp_off;    ///< [n_groups+1] offsets into order
   const uint32_t *order;      ///< births grouped by stream, arrival order inside a stream: low 30 bits = birth

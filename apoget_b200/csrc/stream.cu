@@ -4,17 +4,17 @@
 // given species (no second parent species).  For those births the reference's sequential
 // addGenome (phylogenetictree.hpp:268-302, 553-650) reads and writes nothing but that species'
 // enveloppe as long as the birth is accepted at top level (:612-613) -- so streams of different
-// species are independent, and one warp owns one stream:
+// species are independent, and one CTA (NW warps) owns one stream:
 //
 //   * the enveloppe (representatives, compat metadata, K x K distance matrix, per-row minima)
 //     lives in shared memory for the whole stream;
-//   * 32 births are scored at once, one lane per birth (:456-478 / :430-452), each lane keeping
-//     its k distances and compatibilities in shared memory;
-//   * in-chunk dependencies are then resolved exactly: every lane decides under the current
+//   * NW*32 births are scored at once, one thread per birth (:456-478 / :430-452), each thread
+//     keeping its k distances and compatibilities in shared memory;
+//   * in-chunk dependencies are then resolved exactly: every thread decides under the current
 //     state (accept :612; append :668-677 or criterion enveloppecriteria.cpp:87-133); the FIRST
-//     lane (= earliest birth) whose decision changes the enveloppe commits -- all earlier lanes are
-//     final -- and the later lanes re-measure only the slot that changed and re-sum their score in
-//     the reference's order.  Repeat until the chunk is final.
+//     thread (= earliest birth) whose decision changes the enveloppe commits -- all earlier ones
+//     are final -- and the later ones re-measure only the slot that changed and re-sum their score
+//     in the reference's order.  Repeat until the chunk is final.
 //
 // Births rejected at top level (score <= 0) do not touch the enveloppe; they are flagged and the
 // host walks the sub-species for them (:623).  When a decision cannot be taken with
@@ -28,7 +28,6 @@ namespace apt {
 
 namespace {
 
-constexpr int SWARPS = 4;                 // warps (streams) per CTA
 constexpr float FMAX = 3.402823466e+38f;  // std::numeric_limits<float>::max()
 
 __device__ __forceinline__ uint32_t popc4 (uint4 a, uint4 b) {
@@ -64,15 +63,16 @@ __device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, const double
   return b < a ? b : a;
 }
 
-/// Per-warp view of its slice of dynamic shared memory
+/// The stream's state in dynamic shared memory (T = threads of the CTA = births per step)
 struct WarpState {
   uint4 *reps;        // [K][WQ]
   float4 *rmeta;      // [K]
   float *D;           // [K][K]
   float *minBase;     // [K]
-  float *d;           // [K][32]   distances of lane l to representative r at d[r*32 + l]
-  double *c;          // [K][32]   compatibilities
+  float *d;           // [K][T]   distances of thread t to representative r at d[r*T + t]
+  double *c;          // [K][T]   compatibilities
   const double *lut;  // compatibility table: shared-memory copy when it fits, else global
+  uint32_t T;
 };
 
 /// distance + compatibility of this lane's birth to representative r, stored in the lane's column
@@ -91,19 +91,19 @@ __device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[
     for (int v = 0; v < WQ; v++) acc += sqdiff4(bw[v], ws.reps[r * WQ + v]);
     d = sqrt(acc);
   }
-  ws.d[r * 32 + lane] = float(d);
-  ws.c[r * 32 + lane] = pair_compat<LUT>(cfg, ws.lut, bm, ws.rmeta[r], d);
+  ws.d[r * ws.T + lane] = float(d);
+  ws.c[r * ws.T + lane] = pair_compat<LUT>(cfg, ws.lut, bm, ws.rmeta[r], d);
 }
 
 /// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities
 __device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws, uint32_t k, int lane) {
   if (cfg.full_continuous) {
     float avg = 0.f;
-    for (uint32_t r = 0; r < k; r++) avg = float(__dadd_rn(double(avg), ws.c[r * 32 + lane]));
+    for (uint32_t r = 0; r < k; r++) avg = float(__dadd_rn(double(avg), ws.c[r * ws.T + lane]));
     return float(__dsub_rn(double(__fdiv_rn(avg, float(k))), cfg.avg_thr));
   }
   uint32_t matable = 0;
-  for (uint32_t r = 0; r < k; r++) matable += (ws.c[r * 32 + lane] >= cfg.compat_thr);
+  for (uint32_t r = 0; r < k; r++) matable += (ws.c[r * ws.T + lane] >= cfg.compat_thr);
   return float(__dsub_rn(double(matable), __dmul_rn(cfg.sim_thr, double(k))));
 }
 
@@ -112,7 +112,7 @@ __device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, uint3
   float m1 = FMAX, m2 = FMAX;
   uint32_t i1 = 0xFFFFFFFFu;
   for (uint32_t r = 0; r < K; r++) {
-    const float x = ws.d[r * 32 + lane];
+    const float x = ws.d[r * ws.T + lane];
     if (x < m1) { m2 = m1; m1 = x; i1 = r; }
     else if (x < m2) m2 = x;
   }
@@ -134,71 +134,77 @@ __device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, uint3
     double c = 0.;
     for (uint32_t j = 0; j < K; j++) {
       if (i == j) continue;
-      c = __dadd_rn(c, double(__fadd_rn(-ws.D[i * K + j], ws.d[j * 32 + lane])));   // :62
+      c = __dadd_rn(c, double(__fadd_rn(-ws.D[i * K + j], ws.d[j * ws.T + lane])));   // :62
     }
     if (double(value) < c) { value = float(c); than = i; }
   }
   return value > 0.f;
 }
 
-template <int WQ, int KIND, bool LUT>
-__global__ void __launch_bounds__(SWARPS * 32)
+/// Shared-memory bytes of one stream (without the table)
+__host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T) {
+  return size_t(K) * T * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
+       + size_t(K) * T * 4 + 64 * 4;
+}
+
+template <int WQ, int KIND, bool LUT, int NW>
+__global__ void __launch_bounds__(NW * 32)
 resolve_streams_kernel (StreamArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t g = blockIdx.x * SWARPS + warp;
+  constexpr uint32_t T = NW * 32;
+  constexpr uint32_t NONE = 0xFFFFFFFFu;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t g = blockIdx.x;
   const uint32_t K = a.pool.K;
-  // carve this warp's slice: doubles first (8-byte aligned), then 16-byte items, then floats
-  const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * WQ * 16 + size_t(K) * 16 + size_t(K) * K * 4
-                       + size_t(K) * 4 + size_t(K) * 32 * 4;
-  unsigned char *base = smem + ((perWarp + 15) & ~size_t(15)) * warp;
+  unsigned char *base = smem;
   WarpState ws;
-  ws.c = reinterpret_cast<double*>(base);            base += size_t(K) * 32 * 8;
+  ws.T = T;
+  ws.c = reinterpret_cast<double*>(base);            base += size_t(K) * T * 8;
   ws.reps = reinterpret_cast<uint4*>(base);          base += size_t(K) * WQ * 16;
   ws.rmeta = reinterpret_cast<float4*>(base);        base += size_t(K) * 16;
   ws.D = reinterpret_cast<float*>(base);             base += size_t(K) * K * 4;
   ws.minBase = reinterpret_cast<float*>(base);       base += size_t(K) * 4;
-  ws.d = reinterpret_cast<float*>(base);
-  // the compatibility table is read twice per (birth, representative): keep it next to the SM
+  ws.d = reinterpret_cast<float*>(base);             base += size_t(K) * T * 4;
+  uint32_t *ctl = reinterpret_cast<uint32_t*>(base); base += 64 * 4;
+  // ctl[0..NW): first event thread per warp; ctl[32]: slot entered; ctl[33]: row; ctl[34]: append; ctl[36..39): counters
   ws.lut = a.cfg.lut;
   if (LUT && a.lut_in_smem) {
-    double *lut_s = reinterpret_cast<double*>(smem + ((perWarp + 15) & ~size_t(15)) * SWARPS);
+    double *lut_s = reinterpret_cast<double*>(smem + ((stream_smem(K, WQ, T) + 15) & ~size_t(15)));
     const uint32_t nd = a.cfg.lut_classes * a.cfg.lut_stride;
-    for (uint32_t i = threadIdx.x; i < nd; i += SWARPS * 32) lut_s[i] = __ldg(a.cfg.lut + i);
+    for (uint32_t i = tid; i < nd; i += T) lut_s[i] = __ldg(a.cfg.lut + i);
     ws.lut = lut_s;
-    __syncthreads();
   }
-  if (g >= a.n_groups) return;
 
   const uint32_t slot = a.grp_slot[g], sid = a.grp_sid[g];
   const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
-  uint32_t nAcc0 = 0, nAcc1 = 0, nAcc2 = 0;     // accepted, enveloppe unchanged, by contribution class
   uint32_t k = min(a.pool.fill[slot], K);
   const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
 
   // ---- load the enveloppe ----
-  for (uint32_t i = lane; i < k * WQ; i += 32) ws.reps[i] = poolRows[i];
-  for (uint32_t i = lane; i < k; i += 32) ws.rmeta[i] = a.pool.cmeta[size_t(slot) * K + i];
-  for (uint32_t i = lane; i < K * K; i += 32) ws.D[i] = a.pool_dist[size_t(slot) * K * K + i];
-  __syncwarp();
+  for (uint32_t i = tid; i < k * WQ; i += T) ws.reps[i] = poolRows[i];
+  for (uint32_t i = tid; i < k; i += T) ws.rmeta[i] = a.pool.cmeta[size_t(slot) * K + i];
+  for (uint32_t i = tid; i < K * K; i += T) ws.D[i] = a.pool_dist[size_t(slot) * K * K + i];
+  if (tid < 4) ctl[36 + tid] = 0;
+  __syncthreads();
   auto refreshMinBase = [&] (void) {
-    for (uint32_t r = lane; r < k; r += 32) {
+    for (uint32_t r = tid; r < k; r += T) {
       float m = FMAX;
       for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, ws.D[r * K + j]);
       ws.minBase[r] = m;
     }
-    __syncwarp();
+    __syncthreads();
   };
   refreshMinBase();
 
-  uint32_t changed = 0;         // slots to write back
+  uint32_t changed = 0;         // slots to write back (uniform)
   bool aborted = false;
-  uint32_t rowNext = 0, rowLeft = 0;   // rows of the output buffer are claimed 8 at a time (one atomic per 8 entries)
+  uint32_t rowNext = 0, rowLeft = 0;   // output rows are claimed 8 at a time (one atomic per 8 entries); uniform
+  uint32_t nAcc0 = 0, nAcc1 = 0, nAcc2 = 0;     // per thread: accepted, enveloppe unchanged, by contribution class
 
-  for (uint32_t cb = g0; cb < g1 && !aborted; cb += 32) {
-    const uint32_t nb = min(32u, g1 - cb);
-    const bool active = uint32_t(lane) < nb;
-    const uint32_t ord = active ? a.order[cb + lane] : 0u;
+  for (uint32_t cb = g0; cb < g1 && !aborted; cb += T) {
+    const uint32_t nb = min(T, g1 - cb);
+    const bool active = uint32_t(tid) < nb;
+    const uint32_t ord = active ? a.order[cb + tid] : 0u;
     const uint32_t b = ord & ORDER_INDEX_MASK, ccls = ord >> ORDER_CLASS_SHIFT;
     uint4 bw[WQ];
     float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
@@ -213,123 +219,130 @@ resolve_streams_kernel (StreamArgs a) {
     }
     float score = 0.f;
     if (active) {
-      for (uint32_t r = 0; r < k; r++) measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, lane);
-      score = resum(a.cfg, ws, k, lane);
+      for (uint32_t r = 0; r < k; r++) measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, tid);
+      score = resum(a.cfg, ws, k, tid);
     }
-    uint32_t unresolved = __ballot_sync(0xffffffffu, active);
+    bool mine = active;           // not final yet
 
-    while (unresolved) {
-      const bool mine = (unresolved >> lane) & 1u;
+    for (;;) {
       const bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
       const bool accept = mine && score > 0.f;
       bool modifies = false;
-      uint32_t than = 0xFFFFFFFFu;
+      uint32_t than = NONE;
       if (accept) {
         if (k < K) { modifies = true; than = k; }                       // :668-677
         else if (K > 1)
-          modifies = a.crit == 1 ? criterion_maxMinDist(ws, K, lane, than) : criterion_maxAverage(ws, K, lane, than);
+          modifies = a.crit == 1 ? criterion_maxMinDist(ws, K, tid, than) : criterion_maxAverage(ws, K, tid, than);
       }
-      const uint32_t umask = __ballot_sync(0xffffffffu, uncertain);
-      const uint32_t mmask = __ballot_sync(0xffffffffu, modifies);
-      const int firstU = umask ? __ffs(umask) - 1 : 32, firstM = mmask ? __ffs(mmask) - 1 : 32;
-      const int stop = min(firstU, firstM);
-      const bool fin = mine && lane < stop;
+      // earliest thread of the CTA whose decision is an event (changes the enveloppe / needs the host)
+      const uint32_t em = __ballot_sync(0xffffffffu, uncertain || modifies);
+      if (lane == 0) ctl[warp] = em ? uint32_t(warp * 32 + __ffs(em) - 1) : NONE;
+      __syncthreads();
+      uint32_t stop = NONE;
+#pragma unroll
+      for (int w = 0; w < NW; w++) stop = min(stop, ctl[w]);
+      const bool fin = mine && (stop == NONE || uint32_t(tid) < stop);
       if (fin) {
         a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
-        if (accept) a.out_sid[b] = sid;
+        if (accept) { a.out_sid[b] = sid; nAcc0 += (ccls == 0); nAcc1 += (ccls == 1); nAcc2 += (ccls == 2); }
+        mine = false;
       }
       // births rejected at top level queue up for the sub-species kernel (one atomic per warp step)
       const uint32_t ftm = __ballot_sync(0xffffffffu, fin && !accept);
       if (ftm && a.ft_list) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(a.ft_counter, uint32_t(__popc(ftm)));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t fbase = 0;
+        if (lane == 0) fbase = atomicAdd(a.ft_counter, uint32_t(__popc(ftm)));
+        fbase = __shfl_sync(0xffffffffu, fbase, 0);
         if (fin && !accept) {
-          const uint32_t at = base + __popc(ftm & ((1u << lane) - 1u));
+          const uint32_t at = fbase + __popc(ftm & ((1u << lane) - 1u));
           a.ft_list[2 * at] = b;  a.ft_list[2 * at + 1] = g;
         }
       }
-      nAcc0 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 0));
-      nAcc1 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 1));
-      nAcc2 += __popc(__ballot_sync(0xffffffffu, fin && accept && ccls == 2));
-      if (stop == 32) break;
-      if (firstU <= firstM) {
-        // the decision of this birth needs exact arithmetic: the host takes the stream over from here
-        if (lane == stop) a.act[b] = ACT_UNCERTAIN;
-        aborted = true;
-        break;
+      if (stop == NONE) break;
+      if (uint32_t(tid) == stop) {
+        if (uncertain) { a.act[b] = ACT_UNCERTAIN; ctl[32] = NONE; }   // the host takes the stream over from here
+        else {
+          ctl[32] = than;
+#pragma unroll
+          for (int v = 0; v < WQ; v++) ws.reps[than * WQ + v] = bw[v];
+          ws.rmeta[than] = bm;
+          a.out_sid[b] = sid;
+          a.out_slot[b] = int32_t(than);
+          mine = false;
+        }
       }
-      // ---- lane `stop` enters the enveloppe at slot `sl` ----
-      const uint32_t sl = __shfl_sync(0xffffffffu, than, stop);
-      const bool append = (k < K);
       if (rowLeft == 0) {
-        if (lane == 0) rowNext = atomicAdd(a.row_counter, 8u);
-        rowNext = __shfl_sync(0xffffffffu, rowNext, 0);
-        rowLeft = 8;
+        if (tid == 0) ctl[33] = atomicAdd(a.row_counter, 8u);
       }
+      __syncthreads();
+      const uint32_t sl = ctl[32];
+      if (sl == NONE) { aborted = true; break; }
+      if (rowLeft == 0) { rowNext = ctl[33]; rowLeft = 8; }
       const uint32_t row = rowNext++;
       rowLeft--;
-      // its k distances are the new matrix row (and what the host needs to mirror it), :676-677 / :712-715
-      for (uint32_t r = lane; r < k; r += 32) {
-        const float dr = ws.d[r * 32 + stop];
+      const bool append = (k < K);
+      // the entering birth's k distances are the new matrix row (and what the host mirrors), :676-677 / :712-715
+      for (uint32_t r = tid; r < k; r += T) {
+        const float dr = ws.d[r * T + stop];
         a.rows[size_t(row) * K + r] = dr;
         if (r != sl) { ws.D[r * K + sl] = dr; ws.D[sl * K + r] = dr; }
       }
-      if (lane == stop) {
+      if (uint32_t(tid) == stop)
         a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
-        a.out_sid[b] = sid;
-        a.out_slot[b] = int32_t(sl);
-#pragma unroll
-        for (int v = 0; v < WQ; v++) ws.reps[sl * WQ + v] = bw[v];
-        ws.rmeta[sl] = bm;
-      }
       if (append) k++;
       changed |= 1u << sl;
-      __syncwarp();
+      __syncthreads();
       refreshMinBase();
-      unresolved &= ~((2u << stop) - 1u);
       // later births see the new representative: re-measure that slot only, re-sum in order
-      if ((unresolved >> lane) & 1u) {
-        measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, sl, lane);
-        score = resum(a.cfg, ws, k, lane);
+      if (mine) {
+        measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, sl, tid);
+        score = resum(a.cfg, ws, k, tid);
       }
-      __syncwarp();
     }
-    __syncwarp();
+    __syncthreads();
   }
 
-  if (lane == 0) a.grp_sum[g] = make_uint4(nAcc0, nAcc1, nAcc2, aborted ? 1u : 0u);
+  // ---- per-stream totals ----
+  atomicAdd(&ctl[36], nAcc0);  atomicAdd(&ctl[37], nAcc1);  atomicAdd(&ctl[38], nAcc2);
+  __syncthreads();
+  if (tid == 0) a.grp_sum[g] = make_uint4(ctl[36], ctl[37], ctl[38], aborted ? 1u : 0u);
 
   // ---- write the enveloppe back (the host mirrors the same changes from act/rows) ----
   if (changed && !aborted) {
     uint4 *outRows = reinterpret_cast<uint4*>(a.pool_payload_w) + size_t(slot) * K * WQ;
-    for (uint32_t r = 0; r < k; r++) {
-      if (!((changed >> r) & 1u)) continue;
-      for (uint32_t v = lane; v < uint32_t(WQ); v += 32) outRows[r * WQ + v] = ws.reps[r * WQ + v];
-      if (lane == 0) a.pool_cmeta_w[size_t(slot) * K + r] = ws.rmeta[r];
-    }
-    for (uint32_t i = lane; i < K * K; i += 32) a.pool_dist[size_t(slot) * K * K + i] = ws.D[i];
-    if (lane == 0) a.pool_fill_w[slot] = k;
+    for (uint32_t i = tid; i < k * WQ; i += T)
+      if ((changed >> (i / WQ)) & 1u) outRows[i] = ws.reps[i];
+    for (uint32_t r = tid; r < k; r += T)
+      if ((changed >> r) & 1u) a.pool_cmeta_w[size_t(slot) * K + r] = ws.rmeta[r];
+    for (uint32_t i = tid; i < K * K; i += T) a.pool_dist[size_t(slot) * K * K + i] = ws.D[i];
+    if (tid == 0) a.pool_fill_w[slot] = k;
   }
 }
 
-template <int WQ>
+template <int WQ, int NW>
 void launchWQ (const StreamArgs &a, cudaStream_t st) {
   const uint32_t K = a.pool.K;
-  const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * WQ * 16 + size_t(K) * 16 + size_t(K) * K * 4
-                       + size_t(K) * 4 + size_t(K) * 32 * 4;
-  size_t smem = ((perWarp + 15) & ~size_t(15)) * SWARPS;
+  size_t smem = (stream_smem(K, WQ, NW * 32) + 15) & ~size_t(15);
   StreamArgs b = a;
   const size_t lutBytes = size_t(a.cfg.lut_classes) * a.cfg.lut_stride * sizeof(double);
   b.lut_in_smem = a.cfg.use_lut && lutBytes > 0 && lutBytes <= (size_t(48) << 10) && smem + lutBytes <= (size_t(200) << 10);
   if (b.lut_in_smem) smem += lutBytes;
-  const uint32_t grid = (a.n_groups + SWARPS - 1) / SWARPS;
   auto go = [&] (auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kernel<<<grid, SWARPS * 32, smem, st>>>(b);
+    kernel<<<a.n_groups, NW * 32, smem, st>>>(b);
   };
-  if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true>); else go(resolve_streams_kernel<WQ, 0, false>); }
-  else go(resolve_streams_kernel<WQ, 1, false>);
+  if (a.cfg.kind == 0) {
+    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW>); else go(resolve_streams_kernel<WQ, 0, false, NW>);
+  } else go(resolve_streams_kernel<WQ, 1, false, NW>);
+}
+
+/// Warps per stream: wide CTAs pay off when some stream is long; genomes that fill the register
+/// file (>= 2048 bits per thread) stay at 4 warps.
+template <int WQ>
+void launchNW (const StreamArgs &a, cudaStream_t st) {
+  const bool wide = a.max_stream > 1024 && WQ <= 8
+                    && ((stream_smem(a.pool.K, WQ, 512) + 15) & ~size_t(15)) <= (size_t(150) << 10);
+  if (wide) launchWQ<WQ, 16>(a, st); else launchWQ<WQ, 4>(a, st);
 }
 
 } // namespace
@@ -338,20 +351,18 @@ bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit) {
   const uint32_t wq = wp >> 2;
   if (!(wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32)) return false;
   if (crit != 0 && crit != 1) return false;
-  const size_t perWarp = size_t(K) * 32 * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4
-                       + size_t(K) * 4 + size_t(K) * 32 * 4;
-  return ((perWarp + 15) & ~size_t(15)) * SWARPS <= size_t(200) << 10;
+  return ((stream_smem(K, wq, 128) + 15) & ~size_t(15)) <= size_t(150) << 10;
 }
 
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream) {
   if (!a.n_groups) return;
   switch (a.pool.wp >> 2) {
-  case 1: launchWQ<1>(a, stream); break;
-  case 2: launchWQ<2>(a, stream); break;
-  case 4: launchWQ<4>(a, stream); break;
-  case 8: launchWQ<8>(a, stream); break;
-  case 16: launchWQ<16>(a, stream); break;
-  case 32: launchWQ<32>(a, stream); break;
+  case 1: launchNW<1>(a, stream); break;
+  case 2: launchNW<2>(a, stream); break;
+  case 4: launchNW<4>(a, stream); break;
+  case 8: launchNW<8>(a, stream); break;
+  case 16: launchNW<16>(a, stream); break;
+  case 32: launchNW<32>(a, stream); break;
   default: break;     // callers check stream_kernel_supports()
   }
 }
