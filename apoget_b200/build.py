@@ -12,7 +12,7 @@ SOURCES = ["kernels.cu", "stream.cu", "dense.cu", "microbench.cu", "engine.cpp",
 HEADERS = ["kernels.cuh", "engine.h", os.path.join(ROOT, "include", "apt_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC,-O2,-mpopcnt,-Wall", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-O2,-mpopcnt,-Wall,-pthread", "-shared", "-cudart", "static"]
 
 
 def _stale() -> bool:

@@ -24,6 +24,57 @@ double now (void) {
 }
 }
 
+WorkerPool::WorkerPool (unsigned n) : n_(n ? n : 1) {
+  for (unsigned t = 1; t < n_; t++) threads_.emplace_back([this, t] { loop(t); });
+}
+
+WorkerPool::~WorkerPool (void) {
+  { std::lock_guard<std::mutex> lk (m_); stop_ = true; }
+  wake_.notify_all();
+  for (auto &th: threads_) th.join();
+}
+
+void WorkerPool::loop (unsigned t) {
+  uint64_t seen = 0;
+  for (;;) {
+    // phases of one chunk follow each other within microseconds: spin briefly before sleeping
+    bool got = false;
+    for (int spin = 0; spin < 20000; spin++) {
+      if (gen_.load(std::memory_order_acquire) != seen) { got = true; break; }
+      __builtin_ia32_pause();
+    }
+    if (!got) {
+      std::unique_lock<std::mutex> lk (m_);
+      wake_.wait(lk, [&] { return stop_ || gen_.load(std::memory_order_acquire) != seen; });
+      if (stop_) return;
+    }
+    seen = gen_.load(std::memory_order_acquire);
+    (*fn_)(t);
+    if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+      std::lock_guard<std::mutex> lk (m_);
+      done_.notify_one();
+    }
+  }
+}
+
+void WorkerPool::run (const std::function<void(unsigned)> &fn) {
+  if (n_ == 1) { fn(0); return; }
+  {
+    std::lock_guard<std::mutex> lk (m_);
+    fn_ = &fn;
+    pending_.store(n_ - 1, std::memory_order_release);
+    gen_.fetch_add(1, std::memory_order_acq_rel);
+  }
+  wake_.notify_all();
+  fn(0);
+  for (int spin = 0; spin < 20000; spin++) {
+    if (pending_.load(std::memory_order_acquire) == 0) return;
+    __builtin_ia32_pause();
+  }
+  std::unique_lock<std::mutex> lk (m_);
+  done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+}
+
 void cudaCheck (cudaError_t e, const char *what) {
   if (e != cudaSuccess)
     throw ApiError(APT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -57,6 +108,13 @@ Engine::Engine (const apt_params &p) : p_(p) {
   // the device resolves streams for the default criteria; vote-count scoring needs the exact table
   // (a flipped vote cannot be seen from the score, so no guard band protects it)
   childKernel_ = !(p.flags & APT_FLAG_NO_CHILD_KERNEL);
+  {
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    if (const char *e = getenv("APT_HOST_THREADS")) nt = unsigned(std::max(1, atoi(e)));
+    if (const char *e = getenv("APT_PAR_MIN")) parMin_ = uint32_t(std::max(1, atoi(e)));
+    if (nt > 1) pool_.reset(new WorkerPool(nt));
+  }
   streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
               && (p.full_continuous || lutMode_);
 }
@@ -143,6 +201,12 @@ void Engine::updateElligibilities (void) {
   }
 }
 
+/// sidSlot_ mirrors "the device holds a current copy of this species" (dev_fill > 0)
+void Engine::setStreamable (const Species *s, bool on) {
+  if (sidSlot_.size() <= s->sid) sidSlot_.resize(std::max<size_t>(s->sid + 1, sidSlot_.size() * 2), INV);
+  sidSlot_[s->sid] = on ? s->slot : INV;
+}
+
 uint32_t Engine::allocSlot (void) {
   uint32_t slot;
   if (!freeSlots_.empty()) { slot = freeSlots_.back(); freeSlots_.pop_back(); }
@@ -204,6 +268,7 @@ void Engine::performStillbornTrimming (void) {
       }
       stillborns_++;
       nodes_[i] = nullptr;
+      setStreamable(s, false);
       width_--;
       freeSlots_.push_back(s->slot);
       fillUpdates_.push_back(s->slot);  fillUpdates_.push_back(0);
@@ -888,6 +953,7 @@ void Engine::refreshPool (void) {
     s->stale_mask = 0;
     s->full_upload = false;
     s->dev_fill = s->k;
+    setStreamable(s, s->k > 0);
     fillUpdates_.push_back(s->slot);  fillUpdates_.push_back(s->k);
   }
   refresh_.clear();
@@ -921,38 +987,22 @@ void Engine::refreshPool (void) {
   timers[3] += now() - t0;
 }
 
-void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
-                       const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
-                       const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
-                       uint32_t *outReplaced, uint32_t &done) {
-  double t0 = now();
-  chunkEpoch_++;
-  // ---- prepare: classes; births with a single parent species join that species' stream, the
-  //      others get (birth, species) pairs for the speculative scoring kernel ----
-  hCls_.reserve(n);
-  hBMeta_.reserve(n);
-  pair0_.resize(n);  pair1_.resize(n);  birthGroup_.resize(n);
-  grpSpecies_.clear();  grpCount_.clear();
-  hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
-  size_t P = 0, nStream = 0;
-  touchEpoch_++;
-  for (uint32_t sid: sidTouched_) if (sid < sidGroup_.size()) sidGroup_[sid] = -2;
-  sidTouched_.clear();
-  if (sidGroup_.size() < nodes_.size()) sidGroup_.resize(nodes_.size(), -2);
+/// Groups the births of a chunk into per-species streams (single parent species with a current
+/// device copy) and speculative pairs (everything else).  Serial version.
+void Engine::groupSerial (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream,
+                          uint32_t &maxStream) {
   auto touch = [&] (Species *s) {
     if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
   };
   auto lookup = [&] (uint32_t sid) -> Species* {
     return (sid != INV && sid < nodes_.size()) ? nodes_[sid] : nullptr;
   };
+  // birthGroup_[i]: stream index | contribution class << 30 (what the birth adds to its own species,
+  // :576-577: 0 primordial, 1 one parent, 2 both parents), or -1 for the host / speculative path
   for (uint32_t i = 0; i < n; i++) {
-    const uint32_t cls = classOf(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2]);
-    hCls_.p[i] = cls;
-    float fc;  memcpy(&fc, &cls, 4);
-    hBMeta_.p[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], fc);
     Species *s0 = nullptr, *s1 = nullptr;
     const uint32_t m = msid[i], f = fsid[i];
-    if (streamOk_ && (f == INV || m == f) && m != INV && m < sidGroup_.size()) {
+    if (streamOk_ && (f == INV || m == f) && m < sidGroup_.size()) {
       // single-parent birth: the per-chunk table answers without touching the species record
       int32_t gidx = sidGroup_[m];
       if (gidx == -2) {
@@ -969,8 +1019,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       if (gidx >= 0) {
         grpCount_[size_t(gidx)]++;
-        birthGroup_[i] = gidx;
-        pair0_[i] = pair1_[i] = -1;             // no speculative pair: a taken-over stream is scored on the host
+        birthGroup_[i] = gidx | int32_t((m == f ? 2u : 1u) << ORDER_CLASS_SHIFT);
         nStream++;
         continue;
       }
@@ -986,34 +1035,169 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         if (s0->sid < sidGroup_.size() && sidGroup_[s0->sid] == -2) { sidGroup_[s0->sid] = int32_t(s0->grp_index); sidTouched_.push_back(s0->sid); }
       }
       grpCount_[s0->grp_index]++;
-      birthGroup_[i] = int32_t(s0->grp_index);
-      pair0_[i] = pair1_[i] = -1;
+      const uint32_t ccls = m == INV ? 0u : (m == f ? 2u : 1u);
+      birthGroup_[i] = int32_t(s0->grp_index) | int32_t(ccls << ORDER_CLASS_SHIFT);
       nStream++;
       touch(s0);
       continue;
     }
-    birthGroup_[i] = -1;  pair0_[i] = pair1_[i] = -1;
-    if (s0 && s0->dev_fill) { pair0_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
-    if (s1 && s1->dev_fill) { pair1_[i] = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
+    birthGroup_[i] = -1;
+    PairRef pr { i, -1, -1 };
+    if (s0 && s0->dev_fill) { pr.p0 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
+    if (s1 && s1->dev_fill) { pr.p1 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
+    if (pr.p0 >= 0 || pr.p1 >= 0) pairOf_.push_back(pr);
   }
   const uint32_t G = uint32_t(grpSpecies_.size());
-  uint32_t maxStream = 0;
   if (G) {
     hGrpSlot_.reserve(G);  hGrpOff_.reserve(G + 1);  hOrder_.reserve(nStream);
     uint32_t off = 0;
     hGrpSid_.reserve(G);
     for (uint32_t g = 0; g < G; g++) {
       hGrpSlot_.p[g] = grpSpecies_[g]->slot;  hGrpSid_.p[g] = grpSpecies_[g]->sid;
-      hGrpOff_.p[g] = off;  off += grpCount_[g];  maxStream = std::max(maxStream, grpCount_[g]);  grpCount_[g] = 0;
+      hGrpOff_.p[g] = off;  off += grpCount_[g];  maxStream = std::max(maxStream, grpCount_[g]);  grpCount_[g] = off - grpCount_[g];
     }
     hGrpOff_.p[G] = off;
-    for (uint32_t i = 0; i < n; i++)
-      if (birthGroup_[i] >= 0) {
-        const uint32_t g = uint32_t(birthGroup_[i]);
-        const uint32_t ccls = msid[i] == INV ? 0u : (msid[i] == fsid[i] ? 2u : 1u);     // :576-577
-        hOrder_.p[hGrpOff_.p[g] + grpCount_[g]++] = i | (ccls << ORDER_CLASS_SHIFT);
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t bg = uint32_t(birthGroup_[i]);       // class 2 sets the sign bit: compare with "none" explicitly
+      if (bg != 0xFFFFFFFFu) {
+        const uint32_t g = bg & ORDER_INDEX_MASK;
+        hOrder_.p[grpCount_[g]++] = i | (bg & ~ORDER_INDEX_MASK);
+        birthGroup_[i] = int32_t(g);
       }
+    }
   }
+}
+
+/// Same result as groupSerial for large chunks: a stable parallel counting sort by species id.
+/// Thread t owns a contiguous range of births; per-thread histograms give every thread its own
+/// write cursor inside each stream, so arrival order inside a stream is preserved.
+void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream,
+                            uint32_t &maxStream) {
+  const unsigned T = pool_->size();
+  const size_t NS = nodes_.size();
+  if (sidSlot_.size() < NS) sidSlot_.resize(NS, INV);
+  parCnt_.resize(T);  parRest_.resize(T);
+  birthKey_.resize(n);
+  const uint32_t rootSid = (root_ && root_->sid < NS && nodes_[root_->sid] == root_) ? root_->sid : INV;
+  const bool rootOk = rootSid != INV && sidSlot_[rootSid] != INV;
+  const uint32_t per = (n + T - 1) / T;
+  const double q0 = now();
+  // 1. classify every birth, count per (thread, species)
+  pool_->run([&] (unsigned t) {
+    auto &cnt = parCnt_[t];
+    cnt.assign(NS, 0u);
+    const uint32_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint32_t m = msid[i], f = fsid[i];
+      uint32_t key = INV;
+      if (f == INV || m == f) {
+        if (m == INV) { if (rootOk) key = rootSid; }                                  // primordial: root, contributes nothing (:281-282)
+        else if (m < NS && sidSlot_[m] != INV) key = m | ((m == f ? 2u : 1u) << ORDER_CLASS_SHIFT);
+      }
+      birthKey_[i] = key;
+      if (key != INV) cnt[key & ORDER_INDEX_MASK]++;
+    }
+  });
+  const double q1 = now();
+  // 2. streams in ascending species id; per-thread cursors
+  uint32_t off = 0;
+  for (size_t sid = 0; sid < NS; sid++) {
+    uint32_t total = 0;
+    for (unsigned t = 0; t < T; t++) total += parCnt_[t][sid];
+    if (!total) continue;
+    Species *sp = nodes_[sid];
+    sp->grp_epoch = chunkEpoch_;
+    sp->grp_index = uint32_t(grpSpecies_.size());
+    grpSpecies_.push_back(sp);  grpCount_.push_back(total);
+    if (sp->touch_epoch != touchEpoch_) { sp->touch_epoch = touchEpoch_; counters[8] += sp->dev_fill; }
+    sidGroup_[sid] = int32_t(sp->grp_index);
+    sidTouched_.push_back(uint32_t(sid));
+    for (unsigned t = 0; t < T; t++) { const uint32_t c = parCnt_[t][sid]; parCnt_[t][sid] = off; off += c; }
+    maxStream = std::max(maxStream, total);
+  }
+  nStream = off;
+  const uint32_t G = uint32_t(grpSpecies_.size());
+  hGrpSlot_.reserve(G);  hGrpOff_.reserve(G + 1);  hGrpSid_.reserve(G);  hOrder_.reserve(nStream);
+  uint32_t o2 = 0;
+  for (uint32_t g = 0; g < G; g++) {
+    hGrpSlot_.p[g] = grpSpecies_[g]->slot;  hGrpSid_.p[g] = grpSpecies_[g]->sid;
+    hGrpOff_.p[g] = o2;  o2 += grpCount_[g];
+  }
+  hGrpOff_.p[G] = o2;
+  const double q2 = now();
+  // 3. scatter
+  pool_->run([&] (unsigned t) {
+    auto &cur = parCnt_[t];
+    auto &rest = parRest_[t];
+    rest.clear();
+    const uint32_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    for (uint32_t i = lo; i < hi; i++) {
+      const uint32_t key = birthKey_[i];
+      if (key != INV) {
+        const uint32_t sid = key & ORDER_INDEX_MASK;
+        hOrder_.p[cur[sid]++] = i | (key & ~ORDER_INDEX_MASK);
+        birthGroup_[i] = sidGroup_[sid];
+      } else { birthGroup_[i] = -1; rest.push_back(i); }
+    }
+  });
+  const double q3 = now();
+  if (getenv("APT_PROFILE")) fprintf(stderr, "group: count %.3f assign %.3f scatter %.3f ms\n", 1e3*(q1-q0), 1e3*(q2-q1), 1e3*(q3-q2));
+  // 4. the rest (two parent species, unknown ids, species without a device copy): speculative pairs
+  for (unsigned t = 0; t < T; t++)
+    for (uint32_t i: parRest_[t]) {
+      const uint32_t m = msid[i], f = fsid[i];
+      Species *s0 = nullptr, *s1 = nullptr;
+      auto lookup = [&] (uint32_t sid) -> Species* { return (sid != INV && sid < NS) ? nodes_[sid] : nullptr; };
+      if (m == INV && f == INV) s0 = root_;
+      else if (f == INV || m == f) s0 = lookup(m);
+      else { s0 = lookup(m); s1 = lookup(f); }
+      PairRef pr { i, -1, -1 };
+      auto touch = [&] (Species *s) {
+        if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
+      };
+      if (s0 && s0->dev_fill) { pr.p0 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
+      if (s1 && s1->dev_fill) { pr.p1 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
+      if (pr.p0 >= 0 || pr.p1 >= 0) pairOf_.push_back(pr);
+    }
+}
+
+void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
+                       const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
+                       const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
+                       uint32_t *outReplaced, uint32_t &done) {
+  double t0 = now();
+  chunkEpoch_++;
+  // ---- prepare: classes; births with a single parent species join that species' stream, the
+  //      others get (birth, species) pairs for the speculative scoring kernel ----
+  hCls_.reserve(n);
+  hBMeta_.reserve(n);
+  birthGroup_.resize(n);
+  pairOf_.clear();
+  grpSpecies_.clear();  grpCount_.clear();
+  hPairBirth_.reserve(2 * size_t(n));  hPairSlot_.reserve(2 * size_t(n));
+  size_t P = 0, nStream = 0;
+  touchEpoch_++;
+  for (uint32_t sid: sidTouched_) if (sid < sidGroup_.size()) sidGroup_[sid] = -2;
+  sidTouched_.clear();
+  if (sidGroup_.size() < nodes_.size()) sidGroup_.resize(nodes_.size(), -2);
+  // compatibility classes: one triple for the whole chunk is the common case (array == itself shifted by one triple)
+  chunkUniform_ = n < 2 || memcmp(compat, compat + 3, size_t(n - 1) * 3 * sizeof(float)) == 0;
+  if (chunkUniform_) {
+    chunkCls_ = classOf(compat[0], compat[1], compat[2]);
+  } else {
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t cls = classOf(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2]);
+      hCls_.p[i] = cls;
+      float fc;  memcpy(&fc, &cls, 4);
+      hBMeta_.p[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], fc);
+    }
+  }
+  uint32_t maxStream = 0;
+  if (pool_ && n >= parMin_ && streamOk_ && nodes_.size() <= size_t(2) * n)
+    groupParallel(n, msid, fsid, P, nStream, maxStream);
+  else
+    groupSerial(n, msid, fsid, P, nStream, maxStream);
+  const uint32_t G = uint32_t(grpSpecies_.size());
   // sub-species of every stream's species, in the reference's visiting order (newest first, :506)
   size_t nChild = 0;
   const bool useChildKernel = G && childKernel_;
@@ -1062,7 +1246,12 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       dBirthRows = dBirths_.p;
     }
-    cudaCheck(cudaMemcpyAsync(dBMeta_.p, hBMeta_.p, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, stream_), "birth meta");
+    if (chunkUniform_) {
+      float fc;  memcpy(&fc, &chunkCls_, 4);
+      launch_fill_f4(dBMeta_.p, n, make_float4(compat[0], compat[1], compat[2], fc), stream_);
+      counters[4]++;
+    } else
+      cudaCheck(cudaMemcpyAsync(dBMeta_.p, hBMeta_.p, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, stream_), "birth meta");
   }
   if (P) {
     // speculative scores of every (birth, parent species) pair of the two-parent births
@@ -1232,13 +1421,18 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           if ((act & ACT_UNCERTAIN) || (act & ACT_CODE_MASK) == ACT_UNPROCESSED) { diverge(s0); s0 = nullptr; }
         }
       }
-      RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, hCls_.p[i],
+      RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, chunkUniform_ ? chunkCls_ : hCls_.p[i],
                   compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
       uint32_t sid = INV, replaced = INV;
       int32_t slot = -1;
       const uint32_t *w = payloadOf(i);
       if (s0) walkStream(w, g, s0, act, sid, slot, replaced);
-      else walkOne(w, g, pair0_[i], pair1_[i], sid, slot, replaced);
+      else {
+        int64_t p0 = -1, p1 = -1;
+        auto it = std::lower_bound(pairOf_.begin(), pairOf_.end(), i, [] (const PairRef &p, uint32_t b) { return p.birth < b; });
+        if (it != pairOf_.end() && it->birth == i) { p0 = it->p0; p1 = it->p1; }
+        walkOne(w, g, p0, p1, sid, slot, replaced);
+      }
       if (outSid) outSid[i] = sid;
       if (outSlot) outSlot[i] = slot;
       if (outReplaced) outReplaced[i] = replaced;

@@ -16,8 +16,14 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -73,6 +79,27 @@ struct PinBuf {
     if (p) cudaFreeHost(p);
     p = q;  cap = ncap;
   }
+};
+
+/// Fixed set of worker threads for the O(n) host loops of large chunks (grouping births into
+/// streams).  run(fn) executes fn(t) for t in [0, size) -- t = 0 on the caller -- and returns when
+/// all are done.  No OpenMP on purpose: the library is loaded next to other runtimes.
+class WorkerPool {
+public:
+  explicit WorkerPool (unsigned n);
+  ~WorkerPool (void);
+  unsigned size (void) const { return n_; }
+  void run (const std::function<void(unsigned)> &fn);
+private:
+  void loop (unsigned t);
+  unsigned n_;
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable wake_, done_;
+  const std::function<void(unsigned)> *fn_ = nullptr;
+  std::atomic<uint64_t> gen_ { 0 };
+  std::atomic<unsigned> pending_ { 0 };
+  bool stop_ = false;
 };
 
 // speciescontributors.h:16-86 / :89-100
@@ -201,6 +228,15 @@ private:
     int64_t lastEnter = -1;               // last birth of the chunk the device let into this enveloppe
   };
   std::vector<GroupState> grpState_;
+  // parallel grouping
+  std::unique_ptr<WorkerPool> pool_;
+  uint32_t parMin_ = 32768;               // chunks at least this large are grouped by the worker pool
+  std::vector<uint32_t> sidSlot_;         // sid -> pool slot when the species can be streamed (device copy current), else APT_INVALID
+  std::vector<std::vector<uint32_t>> parCnt_, parRest_;
+  std::vector<uint32_t> birthKey_;
+  void groupSerial (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
+  void groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
+  void setStreamable (const Species *s, bool on);
   std::vector<int32_t> sidGroup_;         // per-chunk cache: sid -> stream index, -1 not streamable, -2 not looked up yet
   std::vector<uint32_t> sidTouched_;
   DevBuf<uint32_t> dGrpSid_, dOutSid_;  DevBuf<int32_t> dOutSlot_;  DevBuf<uint4> dGrpSum_;
@@ -218,6 +254,8 @@ private:
   uint32_t nFt_ = 0;
   int64_t curFt_ = -1;                    // sub-species result entry of the birth being committed
   uint32_t chunkEpoch_ = 0;
+  bool chunkUniform_ = false;             // every birth of the chunk carries the same compatibility triple
+  uint32_t chunkCls_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
   PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
@@ -225,7 +263,8 @@ private:
   PinBuf<float> hScore_, hDist_;
 
   // ---- per-chunk scratch ----
-  std::vector<int64_t> pair0_, pair1_;    // pair index of (birth, s0) / (birth, s1) or -1
+  struct PairRef { uint32_t birth; int64_t p0, p1; };   // speculative pair indices of a two-parent birth
+  std::vector<PairRef> pairOf_;           // ascending by birth
   const uint32_t *curPayload_ = nullptr;  // host payload of the chunk being walked (W_ words per row)
 
   // hierarchy (line-by-line restatements, see engine.cpp)

@@ -244,6 +244,11 @@ __global__ void pack_births_kernel (const uint32_t *__restrict__ src, const floa
                           __uint_as_float(cls ? cls[t] : 0u));
 }
 
+__global__ void fill_f4_kernel (float4 *__restrict__ dst, uint32_t n, float4 value) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = value;
+}
+
 __global__ void pad_rows_kernel (const uint32_t *__restrict__ src, uint32_t n, uint32_t words, uint32_t wp,
                                  uint32_t *__restrict__ dst) {
   const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -362,6 +367,11 @@ void launch_pack_births (const uint32_t *src_payload, const float *src_compat, c
   const size_t total = size_t(n) * wp;
   pack_births_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src_payload, src_compat, cls, n, words, wp,
                                                                        dst_payload, dst_cmeta);
+}
+
+void launch_fill_f4 (float4 *dst, uint32_t n, float4 value, cudaStream_t stream) {
+  if (!n) return;
+  fill_f4_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dst, n, value);
 }
 
 void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t wp, uint32_t *dst, cudaStream_t stream) {

@@ -48,6 +48,9 @@ void launch_pack_births (const uint32_t *src_payload, const float *src_compat, c
                          uint32_t n, uint32_t words, uint32_t wp,
                          uint32_t *dst_payload, float4 *dst_cmeta, cudaStream_t stream);
 
+/// dst[0..n) = value
+void launch_fill_f4 (float4 *dst, uint32_t n, float4 value, cudaStream_t stream);
+
 /// dst[i][0..wp) = src[i][0..words) padded with zeros
 void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t wp, uint32_t *dst, cudaStream_t stream);
 

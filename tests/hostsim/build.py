@@ -16,7 +16,7 @@ def build() -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-mpopcnt", "-Wall", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", cuda_inc,
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-mpopcnt", "-Wall", "-pthread", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", cuda_inc,
            "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", OUT] + srcs
     subprocess.run(cmd, check=True)
     return OUT

@@ -110,6 +110,8 @@ void launch_pack_births (const uint32_t *src, const float *compat, const uint32_
   }
 }
 
+void launch_fill_f4 (float4 *dst, uint32_t n, float4 value, cudaStream_t) { for (uint32_t i = 0; i < n; i++) dst[i] = value; }
+
 void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t wp, uint32_t *dst, cudaStream_t) {
   for (uint32_t i = 0; i < n; i++) {
     memset(dst + size_t(i) * wp, 0, wp * 4);
