@@ -823,6 +823,38 @@ void Engine::selfContribution (Species *s, uint32_t count) {
   s->self_idx = uint32_t(i);
 }
 
+/// Mirrors one enveloppe entry decided by the device (append :668-677 / replacement :694-718) into
+/// the host copy of species s0.  Touches s0 only (safe to run for different species in parallel);
+/// the callbacks to fire are returned in `ev` (at most two, in the reference's order).
+int Engine::mirrorEntry (const uint32_t *w, const RepMeta &g, Species *s0, uint32_t act, int32_t &slot,
+                         uint32_t &replaced, apt_event ev[2]) {
+  int ne = 0;
+  const uint32_t r = (act >> ACT_SLOT_SHIFT) & 31u, k = s0->k;
+  const float *d = hRows_.p + size_t(act >> ACT_ROW_SHIFT) * K_;
+  RepMeta m = g;
+  m.timestamp = step_;
+  if (act & ACT_REPLACED) {
+    const uint32_t epId = s0->reps[r].gid;
+    ev[ne++] = { APT_EV_LEAVES_ENVELOPPE, s0->sid, epId, 0 };
+    ev[ne++] = { APT_EV_ENTERS_ENVELOPPE, s0->sid, g.gid, 0 };
+    m.udata = epId;                                       // :710
+    replaced = epId;
+  } else {
+    if (r != k) throw ApiError(APT_ERR_STATE, "device/host enveloppe fill mismatch");
+    ev[ne++] = { APT_EV_ENTERS_ENVELOPPE, s0->sid, g.gid, 0 };
+    m.udata = g.gid;
+    s0->k = k + 1;
+  }
+  s0->reps[r] = m;
+  memcpy(&hPayload_[(size_t(s0->slot) * K_ + r) * wp_], w, W_ * sizeof(uint32_t));
+  for (uint32_t i = 0; i < k; i++)
+    if (i != r) s0->dist[i * K_ + r] = s0->dist[r * K_ + i] = d[i];
+  s0->snap_mask |= (1u << r);
+  s0->dev_fill = s0->k;                                   // the kernel wrote the same change to the pool
+  slot = int32_t(r);
+  return ne;
+}
+
 // One birth whose top-level decision was taken by the device (resolve_streams_kernel): the host
 // mirrors the decision into the tree (counters, representative metadata, distance rows,
 // contributions, events), exactly as insertInto (:657-726) + updateContributions (:741-769) would.
@@ -845,29 +877,9 @@ void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t ac
   slot = -1;  replaced = INV;
   if (code == ACT_ENTERED) {
     counters[14]++;
-    const uint32_t r = (act >> ACT_SLOT_SHIFT) & 31u, k = s0->k;
-    const float *d = hRows_.p + size_t(act >> ACT_ROW_SHIFT) * K_;
-    RepMeta m = g;
-    m.timestamp = step_;
-    if (act & ACT_REPLACED) {
-      const uint32_t epId = s0->reps[r].gid;
-      emit(APT_EV_LEAVES_ENVELOPPE, s0->sid, epId, 0);
-      emit(APT_EV_ENTERS_ENVELOPPE, s0->sid, g.gid, 0);
-      m.udata = epId;                                       // :710
-      replaced = epId;
-    } else {
-      if (r != k) throw ApiError(APT_ERR_STATE, "device/host enveloppe fill mismatch");
-      emit(APT_EV_ENTERS_ENVELOPPE, s0->sid, g.gid, 0);
-      m.udata = g.gid;
-      s0->k = k + 1;
-    }
-    s0->reps[r] = m;
-    memcpy(&hPayload_[(size_t(s0->slot) * K_ + r) * wp_], w, W_ * sizeof(uint32_t));
-    for (uint32_t i = 0; i < k; i++)
-      if (i != r) s0->dist[i * K_ + r] = s0->dist[r * K_ + i] = d[i];
-    s0->snap_mask |= (1u << r);
-    s0->dev_fill = s0->k;                                   // the kernel wrote the same change to the pool
-    slot = int32_t(r);
+    apt_event ev[2];
+    const int ne = mirrorEntry(w, g, s0, act, slot, replaced, ev);
+    for (int e = 0; e < ne; e++) emit(ev[e].type, ev[e].a, ev[e].b, ev[e].c);
   }
   s0->count++;
   s0->alive++;
@@ -1364,14 +1376,25 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   grpState_.assign(G, GroupState{});
   slow_.clear();  requeue_.clear();
   if (G) {
-    if (outSid) memcpy(outSid, hOutSid_.p, size_t(n) * 4);
-    if (outSlot) memcpy(outSlot, hOutSlot_.p, size_t(n) * 4);
-    if (outReplaced) memset(outReplaced, 0xFF, size_t(n) * 4);
-    for (uint32_t i = 0; i < n; i++) {
-      if (birthGroup_[i] >= 0 && hAct_.p[i] == ACT_ACCEPTED) continue;
-      slow_.push_back(i);
+    // outputs of the births the device settled + the list of births the host has to look at
+    // (one pass over the result words; split over the worker pool for large chunks)
+    const unsigned T = (pool_ && n >= parMin_) ? pool_->size() : 1u;
+    parRest_.resize(std::max<size_t>(parRest_.size(), T));
+    const uint32_t per = (n + T - 1) / T;
+    auto scan = [&] (unsigned t) {
+      const uint32_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+      if (outSid) memcpy(outSid + lo, hOutSid_.p + lo, size_t(hi - lo) * 4);
+      if (outSlot) memcpy(outSlot + lo, hOutSlot_.p + lo, size_t(hi - lo) * 4);
+      if (outReplaced) memset(outReplaced + lo, 0xFF, size_t(hi - lo) * 4);
+      auto &rest = parRest_[t];
+      rest.clear();
+      for (uint32_t i = lo; i < hi; i++)
+        if (!(birthGroup_[i] >= 0 && hAct_.p[i] == ACT_ACCEPTED)) rest.push_back(i);
+    };
+    if (T > 1) pool_->run(scan); else scan(0);
+    for (unsigned t = 0; t < T; t++) slow_.insert(slow_.end(), parRest_[t].begin(), parRest_[t].end());
+    for (uint32_t i: slow_)
       if (birthGroup_[i] >= 0 && (hAct_.p[i] & ACT_CODE_MASK) == ACT_ENTERED) grpState_[size_t(birthGroup_[i])].lastEnter = i;
-    }
     for (uint32_t g = 0; g < G; g++) grpState_[g].snapChildren = uint32_t(grpSpecies_[g]->children.size());
   } else {
     slow_.resize(n);
@@ -1395,7 +1418,65 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaMemcpyAsync(hSlowRows_.p, dSlowRows_.p, ns * W_ * 4, cudaMemcpyDeviceToHost, stream_), "slow rows");
     cudaCheck(cudaStreamSynchronize(stream_), "slow rows");
   }
+  const double w1 = now();
   size_t si = 0;
+  // The leading run of births that are plain enveloppe entries of device streams touches nothing but
+  // each stream's own species: worker t mirrors the entries of the streams it owns (in arrival order),
+  // callbacks are merged back into arrival order afterwards.  Anything else (a birth rejected at top
+  // level, a two-parent birth, a stream handed back) ends the run and is committed serially below.
+  const size_t entryParMin = std::max<size_t>(1, parMin_ / 32);
+  if (pool_ && G && slow_.size() >= entryParMin) {
+    size_t run = 0;
+    while (run < slow_.size()) {
+      const uint32_t i = slow_[run];
+      if (birthGroup_[i] < 0 || (hAct_.p[i] & (ACT_CODE_MASK | ACT_UNCERTAIN)) != ACT_ENTERED) break;
+      run++;
+    }
+    if (run >= entryParMin) {
+      const unsigned T = pool_->size();
+      const bool wantEvents = !(p_.flags & APT_FLAG_NO_EVENTS);
+      struct Local { std::vector<std::pair<uint32_t, apt_event>> ev; uint64_t comparisons = 0, n = 0; std::string error; };
+      std::vector<Local> loc (T);
+      pool_->run([&] (unsigned t) {
+        Local &L = loc[t];
+        try {
+          for (size_t q = 0; q < run; q++) {
+            const uint32_t i = slow_[q];
+            const uint32_t gi = uint32_t(birthGroup_[i]);
+            if (gi % T != t) continue;
+            Species *s0 = grpSpecies_[gi];
+            if (s0->pending > 0) s0->pending--;
+            touchSnap(s0);
+            L.comparisons += s0->k;
+            RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, chunkUniform_ ? chunkCls_ : hCls_.p[i],
+                        compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
+            int32_t slot = -1;
+            uint32_t replaced = INV;
+            apt_event ev[2];
+            const int ne = mirrorEntry(payload ? payload + size_t(i) * W_ : hSlowRows_.p + q * W_, g, s0, hAct_.p[i], slot, replaced, ev);
+            if (wantEvents) for (int e = 0; e < ne; e++) L.ev.emplace_back(i, ev[e]);
+            s0->count++;  s0->alive++;  s0->last = step_;
+            if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));
+            if (outReplaced) outReplaced[i] = replaced;
+            L.n++;
+          }
+        } catch (const std::exception &e) { L.error = e.what(); }
+      });
+      for (const Local &L: loc) if (!L.error.empty()) throw ApiError(APT_ERR_STATE, L.error);
+      uint64_t total = 0;
+      for (const Local &L: loc) { comparisons_ += uint32_t(L.comparisons); total += L.n; }
+      insertions_ += uint32_t(total);
+      counters[0] += total;  counters[1] += total;  counters[14] += total;
+      if (wantEvents) {
+        // per-worker lists are ascending by birth; a birth's events sit in one list, in order
+        std::vector<std::pair<uint32_t, apt_event>> all;
+        for (Local &L: loc) all.insert(all.end(), L.ev.begin(), L.ev.end());
+        std::stable_sort(all.begin(), all.end(), [] (const auto &a, const auto &b) { return a.first < b.first; });
+        for (const auto &e: all) events_.push_back(e.second);
+      }
+      si = run;
+    }
+  }
   std::vector<uint32_t> heap;       // births handed back by a taken-over stream (min-heap)
   auto heapCmp = [] (uint32_t a, uint32_t b) { return a > b; };
   uint32_t walked = 0;
@@ -1411,6 +1492,31 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       } else if (si < slow_.size()) { curFt_ = ftOfSlow_[si]; i = slow_[si++]; }
       else break;
       curBirth_ = i;
+      // the births looked at are sparse: pull what the next ones touch into the cache ahead of time
+      if (si + 12 < slow_.size()) {
+        const uint32_t j = slow_[si + 12];
+        __builtin_prefetch(&birthGroup_[j]);  __builtin_prefetch(&hAct_.p[j]);
+        __builtin_prefetch(&gid[j]);  __builtin_prefetch(&mgid[j]);  __builtin_prefetch(&msid[j]);
+        __builtin_prefetch(&fgid[j]);  __builtin_prefetch(&fsid[j]);  __builtin_prefetch(&compat[3 * size_t(j)]);
+        if (payload) __builtin_prefetch(payload + size_t(j) * W_);
+      }
+      if (si + 6 < slow_.size()) {
+        const int32_t bg = birthGroup_[slow_[si + 6]];
+        if (bg >= 0) {
+          const Species *sp = grpSpecies_[size_t(bg)];
+          __builtin_prefetch(sp);  __builtin_prefetch(reinterpret_cast<const char*>(sp) + 64);
+          __builtin_prefetch(reinterpret_cast<const char*>(sp) + 128);
+        }
+      }
+      if (si + 3 < slow_.size()) {
+        const int32_t bg = birthGroup_[slow_[si + 3]];
+        if (bg >= 0) {
+          const Species *sp = grpSpecies_[size_t(bg)];
+          __builtin_prefetch(sp->reps.data(), 1);  __builtin_prefetch(sp->dist.data(), 1);
+          __builtin_prefetch(sp->contribs.data(), 1);
+          __builtin_prefetch(&hPayload_[size_t(sp->slot) * K_ * wp_], 1);
+        }
+      }
       Species *s0 = nullptr;
       uint32_t act = 0;
       if (birthGroup_[i] >= 0) {
@@ -1439,8 +1545,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       counters[0]++;
       walked++;
     }
+    const double w2 = now();
     for (uint32_t g = 0; g < G; g++)
       if (grpSpecies_[g]->div_epoch != chunkEpoch_) settleStream(g, false, 0, nullptr);
+    if (getenv("APT_PROFILE")) fprintf(stderr, "walk: scan %.3f slow(%zu) %.3f settle %.3f ms\n", 1e3*(w1-t0), slow_.size(), 1e3*(w2-w1), 1e3*(now()-w2));
   } catch (...) {
     // a birth failed (unknown species, :169-174): everything before it stays committed, as when the
     // reference throws out of addGenome; streams are settled up to that birth

@@ -302,6 +302,7 @@ private:
   void finishBirth (const uint32_t *w, RepMeta &g, Species *best, float bestScore, const Eval &bestEval,
                     const Contributions &contrib, uint32_t &sid, int32_t &slot, uint32_t &replaced);
   void selfContribution (Species *s, uint32_t count);
+  int mirrorEntry (const uint32_t *w, const RepMeta &g, Species *s0, uint32_t act, int32_t &slot, uint32_t &replaced, apt_event ev[2]);
   void catchUpSelf (Species *s, uint32_t before);
   void settleStream (uint32_t g, bool diverging, uint32_t before, std::vector<uint32_t> *requeue);
 

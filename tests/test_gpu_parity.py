@@ -211,3 +211,11 @@ def test_tree_device_resident_payloads(name):
     assert np.array_equal(sids, ref["sids"])
     assert np.array_equal(tree.events(), ref["events"])
     assert tree.to_json() == golden_json(name)
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c5_speciation_trimming"])
+def test_tree_parallel_host_paths(name, monkeypatch):
+    """Worker-pool versions of the host loops forced on for the small golden chunks."""
+    monkeypatch.setenv("APT_PAR_MIN", "1")
+    monkeypatch.setenv("APT_HOST_THREADS", "4")
+    _compare(name)

@@ -153,3 +153,12 @@ def test_device_resident_payload_entry_point(hostsim, name):
     assert np.array_equal(sids, ref["sids"])
     assert np.array_equal(tree.events(), ref["events"])
     assert tree.to_json() == golden_json(name)
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c5_speciation_trimming", "founders_orphans_classes"])
+def test_parallel_host_paths(hostsim, name, monkeypatch):
+    """Worker-pool versions of the O(n) host loops (stable parallel grouping, result scan, mirroring of
+    enveloppe entries) forced on for small chunks: results, callback order and dump must not change."""
+    monkeypatch.setenv("APT_PAR_MIN", "1")
+    monkeypatch.setenv("APT_HOST_THREADS", "4")
+    _compare(hostsim, name)
