@@ -126,6 +126,7 @@ def main() -> None:
     ap.add_argument("--pop", type=int, default=100_000, help="births per step (C2: 100 000)")
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-sweep side measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                    # timing rule: W >= 3
@@ -329,6 +330,20 @@ def main() -> None:
         "species": tree_h.stats()["width"],
     }
 
+    if rank == 0 and world == 1 and not args.no_dense:
+        # second headline of BASELINE.json ("genome-distance evals/sec vs int-pipe roofline"): the dense
+        # sweep of configs[3] (4096-bit genomes, 100 k enveloppe members) on a 131 072-birth slice
+        import argparse as _ap
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_dense
+        d = bench_dense.run(_ap.Namespace(config="c4", births=131072, species=0, iters=2, check=8))
+        line["dense_sweep"] = {
+            "workload": "C4: 4096-bit Hamming genomes, every birth x 10 000 species x K=10 (131 072-birth slice of the 1 M batch)",
+            "evals_per_s": d["evals_per_s"], "births_per_s": d["births_per_s"], "ms": d["ms"],
+            "roofline": {"bound": "int_pipe (popc32)", "achieved": d["pipe_ops_per_s"], "peak": d["pipe_peak_measured"],
+                         "unit": "popc32/s", "frac": d["frac_of_pipe_peak"],
+                         "peak_source": "measured on this GPU by apt_microbench (XOR+POPC chains)"},
+            "oracle_checked_births": d["oracle_checked_births"], "oracle_mismatches": d["oracle_mismatches"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
         synth.write_trace(path, trace)

@@ -45,14 +45,8 @@ def make_pool(rng, kind, words, S, K, sigma):
     return np.ascontiguousarray(reps), compat, fill
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
-    ap.add_argument("--births", type=int, default=0)
-    ap.add_argument("--species", type=int, default=0)
-    ap.add_argument("--iters", type=int, default=3)
-    ap.add_argument("--check", type=int, default=24, help="births verified against the CPU oracle")
-    args = ap.parse_args()
+def run(args):
+    """One dense sweep measurement; returns the result dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
     from apoget_b200 import _lib
@@ -62,7 +56,8 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    own_group = world > 1 and not dist.is_initialized()
+    if own_group:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind, words, K, S, B, sigma = CONFIGS[args.config]
     S, B = args.species or S, args.births or B
@@ -139,8 +134,9 @@ def main():
     evals = float(B) * S * K
     ops = evals * (words if kind == 0 else 3 * words)
     peak = peaks[0] if kind == 0 else peaks[3] * 2
+    out = None
     if rank == 0:
-        print(json.dumps({
+        out = ({
             "bench": "dense sweep", "config": args.config, "n_gpus": world, "births": B, "species": S, "K": K,
             "genome_words": words, "kind": "bits/hamming" if kind == 0 else "f32/l2", "ms": ms,
             "births_per_s": B / (ms * 1e-3), "evals_per_s": evals / (ms * 1e-3),
@@ -148,9 +144,22 @@ def main():
             "pipe_peak_measured": peak, "frac_of_pipe_peak": ops / (ms * 1e-3) / (peak * world),
             "microbench": {"popc32_per_s": peaks[0], "lop3_per_s": peaks[1], "dfma_per_s": peaks[2], "ffma_per_s": peaks[3]},
             "accepting_births_frac": float((count > 0).mean()), "oracle_checked_births": int(min(args.check, B)),
-            "oracle_mismatches": int(bad)}))
-    if world > 1:
+            "oracle_mismatches": int(bad)})
+    if own_group:
         dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--births", type=int, default=0)
+    ap.add_argument("--species", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--check", type=int, default=24, help="births verified against the CPU oracle")
+    out = run(ap.parse_args())
+    if out is not None:
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":
