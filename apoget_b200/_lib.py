@@ -52,6 +52,7 @@ SYMBOLS = {
     "apt_tree_event_count": (ctypes.c_uint32, [vp]),
     "apt_tree_events": (ctypes.c_uint32, [vp, vp, ctypes.c_uint32, ctypes.c_int]),
     "apt_tree_to_json": (ctypes.c_uint64, [vp, ctypes.c_char_p, ctypes.c_uint64]),
+    "apt_tree_from_json": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_uint64]),
     "apt_tree_node_info": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.POINTER(AptNodeInfo)]),
     "apt_tree_node_children": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.c_uint32]),
     "apt_tree_node_contributors": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.c_uint32]),
@@ -67,6 +68,7 @@ SYMBOLS = {
     "apt_classify_dense": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp]),
     "apt_classify_dense_dev": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp]),
     "apt_env_contribution": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, vp, vp, vp, vp]),
+    "apt_mate_compat": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, vp, ctypes.c_uint32, vp, vp, vp, vp]),
     "apt_microbench": (ctypes.c_int, [ctypes.c_int, f64p]),
     "apt_pairwise": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, ctypes.c_uint32, vp, vp, vp]),
 }

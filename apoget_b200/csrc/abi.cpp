@@ -185,6 +185,13 @@ uint64_t apt_tree_to_json (apt_tree *t, char *out, uint64_t cap) {
   return s.size();
 }
 
+int apt_tree_from_json (apt_tree *t, const char *text, uint64_t len) {
+  return guarded([&] {
+    need(t && text, "null argument");
+    t->engine.fromJson(std::string(text, size_t(len)));
+  });
+}
+
 int apt_tree_node_info (apt_tree *t, uint32_t sid, apt_node_info *out) {
   return guarded([&] {
     need(t && out, "null argument");
@@ -379,6 +386,30 @@ int apt_pairwise (const apt_params *params, uint32_t n_genomes, const uint32_t *
     cudaCheck(cudaGetLastError(), "pairwise launch");
     cudaCheck(cudaDeviceSynchronize(), "pairwise");
     dO.down(out, n_pairs);
+  });
+}
+
+int apt_mate_compat (const apt_params *params, uint32_t n_genomes, const uint32_t *payload, const float *compat,
+                     uint32_t n_pairs, const uint32_t *idx_m, const uint32_t *idx_f, float *out_dist, double *out_compat) {
+  return guarded([&] {
+    need(params && (n_pairs == 0 || (payload && compat && idx_m && idx_f && out_dist && out_compat)), "null argument");
+    need(params->kind <= APT_F32 && params->words >= 1 && params->words <= 1024, "bad genome shape");
+    for (uint32_t i = 0; i < n_pairs; i++) need(idx_m[i] < n_genomes && idx_f[i] < n_genomes, "pair index out of range");
+    requireDevice(params->device);
+    const uint32_t W = params->words, wp = (W + 3u) & ~3u;
+    std::vector<uint32_t> hp (size_t(n_genomes) * wp, 0u);
+    std::vector<float4> hm (n_genomes);
+    for (uint32_t i = 0; i < n_genomes; i++) {
+      memcpy(&hp[size_t(i) * wp], payload + size_t(i) * W, W * 4);
+      hm[i] = make_float4(compat[3 * i], compat[3 * i + 1], compat[3 * i + 2], 0.f);
+    }
+    Tmp<uint32_t> dP (hp.size() + 4), dA (n_pairs), dB (n_pairs);  Tmp<float4> dM (n_genomes + 1);
+    Tmp<float> dD (n_pairs);  Tmp<double> dC (n_pairs);
+    dP.up(hp.data(), hp.size());  dM.up(hm.data(), n_genomes);  dA.up(idx_m, n_pairs);  dB.up(idx_f, n_pairs);
+    launch_mate_compat(int(params->kind), wp, dP.p, dM.p, n_pairs, dA.p, dB.p, dD.p, dC.p, nullptr);
+    cudaCheck(cudaGetLastError(), "mate_compat launch");
+    cudaCheck(cudaDeviceSynchronize(), "mate_compat");
+    dD.down(out_dist, n_pairs);  dC.down(out_compat, n_pairs);
   });
 }
 

@@ -1696,3 +1696,169 @@ std::string Engine::toJson (void) const {
 }
 
 } // namespace apt
+
+// ---- JSON load (phylogenetictree.hpp:908-927, :946-967) ------------------------------------------------
+namespace apt {
+namespace {
+
+/// Minimal JSON value + recursive-descent parser (objects, arrays, numbers, true/false/null, strings)
+struct JVal {
+  enum Type { NUL, BOOL, NUM, STR, ARR, OBJ } type = NUL;
+  double num = 0;
+  bool b = false;
+  std::string str;
+  std::vector<JVal> arr;
+  std::vector<std::pair<std::string, JVal>> obj;
+  const JVal& at (const char *key) const {
+    for (const auto &kv: obj) if (kv.first == key) return kv.second;
+    throw ApiError(APT_ERR_ARGUMENT, std::string("JSON: missing key '") + key + "'");
+  }
+  const JVal& idx (size_t i) const {
+    if (type != ARR || i >= arr.size()) throw ApiError(APT_ERR_ARGUMENT, "JSON: bad array access");
+    return arr[i];
+  }
+  uint32_t u32 (void) const {
+    if (type != NUM) throw ApiError(APT_ERR_ARGUMENT, "JSON: number expected");
+    return uint32_t(num);
+  }
+  size_t size (void) const { return type == ARR ? arr.size() : 0; }
+};
+
+struct JParser {
+  const char *p, *end;
+  [[noreturn]] void fail (const char *what) const { throw ApiError(APT_ERR_ARGUMENT, std::string("JSON: ") + what); }
+  void ws (void) { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+  bool lit (const char *s) { const size_t n = strlen(s); if (size_t(end - p) >= n && !memcmp(p, s, n)) { p += n; return true; } return false; }
+  std::string string (void) {
+    if (p >= end || *p != '"') fail("string expected");
+    p++;
+    std::string s;
+    while (p < end && *p != '"') { if (*p == '\\' && p + 1 < end) p++; s += *p++; }
+    if (p >= end) fail("unterminated string");
+    p++;
+    return s;
+  }
+  JVal value (void) {
+    ws();
+    if (p >= end) fail("unexpected end");
+    JVal v;
+    if (*p == '{') {
+      v.type = JVal::OBJ;  p++;  ws();
+      if (p < end && *p == '}') { p++; return v; }
+      for (;;) {
+        ws();
+        std::string k = string();
+        ws();
+        if (p >= end || *p != ':') fail("':' expected");
+        p++;
+        v.obj.emplace_back(std::move(k), value());
+        ws();
+        if (p < end && *p == ',') { p++; continue; }
+        if (p < end && *p == '}') { p++; return v; }
+        fail("',' or '}' expected");
+      }
+    }
+    if (*p == '[') {
+      v.type = JVal::ARR;  p++;  ws();
+      if (p < end && *p == ']') { p++; return v; }
+      for (;;) {
+        v.arr.push_back(value());
+        ws();
+        if (p < end && *p == ',') { p++; continue; }
+        if (p < end && *p == ']') { p++; return v; }
+        fail("',' or ']' expected");
+      }
+    }
+    if (*p == '"') { v.type = JVal::STR; v.str = string(); return v; }
+    if (lit("null")) return v;
+    if (lit("true")) { v.type = JVal::BOOL; v.b = true; return v; }
+    if (lit("false")) { v.type = JVal::BOOL; v.b = false; return v; }
+    char *e = nullptr;
+    v.num = strtod(p, &e);
+    if (e == p) fail("value expected");
+    v.type = JVal::NUM;  p = e;
+    return v;
+  }
+};
+
+} // namespace
+
+/// fromJson (:946-967): rebuilds the hierarchy (:908-927), then re-derives every node's parent from its
+/// stored contributors in ascending species id (updateContributions(n, {}, true), :961-962) -- which,
+/// as in the reference, re-attaches sub-species in THAT order.  The device pool is rebuilt from the
+/// loaded enveloppes at the next insertion.  The tree must be empty.
+void Engine::fromJson (const std::string &text) {
+  if (root_ || nextNodeID_ || width_) throw ApiError(APT_ERR_STATE, "fromJson needs an empty tree");
+  JParser ps { text.data(), text.data() + text.size() };
+  const JVal j = ps.value();
+  const uint32_t envSize = j.at("_envSize").u32();
+  if (envSize != K_)
+    throw ApiError(APT_ERR_ARGUMENT, "Current configuration file specifies an enveloppe size of " + std::to_string(K_)
+                   + " whereas the provided PTree was built with " + std::to_string(envSize));     // :949-954
+  step_ = j.at("_step").u32();
+  stillborns_ = j.at("_stillborns").u32();
+
+  struct Rec {
+    Engine &e;
+    Species* node (const JVal &jn) {                                        // rebuildHierarchy, :908-927
+      Species *n = new Species;
+      n->sid = jn.at("id").u32();
+      n->slot = e.allocSlot();
+      n->reps.resize(e.K_);
+      n->dist.assign(size_t(e.K_) * e.K_, 0.f);
+      for (const JVal &c: jn.at("contribs").arr)
+        n->contribs.push_back({ c.idx(0).u32(), c.idx(1).u32(), c.idx(2).type == JVal::BOOL ? c.idx(2).b : c.idx(2).num != 0 });
+      const JVal &d = jn.at("data");
+      n->first = d.idx(0).u32();  n->last = d.idx(1).u32();  n->count = d.idx(2).u32();
+      n->alive = d.idx(3).u32();  n->pending = d.idx(4).u32();
+      const JVal &env = jn.at("envlp");
+      if (env.size() > e.K_) throw ApiError(APT_ERR_ARGUMENT, "JSON: enveloppe larger than rsetSize");
+      for (size_t r = 0; r < env.size(); r++) {
+        const JVal &g = env.idx(r).idx(0);
+        RepMeta &m = n->reps[r];
+        m.mu = float(g.at("c").idx(0).num);  m.sin = float(g.at("c").idx(1).num);  m.sout = float(g.at("c").idx(2).num);
+        m.cls = e.classOf(m.mu, m.sin, m.sout);
+        const JVal &ge = g.at("g");
+        m.fgid = ge.at("f").at("g").u32();  m.fsid = ge.at("f").at("s").u32();
+        m.mgid = ge.at("m").at("g").u32();  m.msid = ge.at("m").at("s").u32();
+        m.gid = ge.at("s").at("g").u32();
+        m.timestamp = 0;                      // not serialised by the reference either (node.hpp:54-63)
+        m.udata = env.idx(r).idx(1).type == JVal::NUM ? env.idx(r).idx(1).u32() : m.gid;
+        const JVal &w = g.at("w");
+        if (w.size() != e.W_) throw ApiError(APT_ERR_ARGUMENT, "JSON: payload width does not match the tree");
+        uint32_t *dst = &e.hPayload_[(size_t(n->slot) * e.K_ + r) * e.wp_];
+        for (uint32_t i = 0; i < e.W_; i++) dst[i] = w.idx(i).u32();
+      }
+      n->k = uint32_t(env.size());
+      for (const JVal &dd: jn.at("dists").arr) {
+        const uint32_t a = dd.idx(0).u32(), b = dd.idx(1).u32();
+        if (a >= e.K_ || b >= e.K_) throw ApiError(APT_ERR_ARGUMENT, "JSON: distance index out of range");
+        n->dist[a * e.K_ + b] = n->dist[b * e.K_ + a] = float(dd.idx(2).num);
+      }
+      if (e.nodes_.size() <= n->sid) e.nodes_.resize(std::max<size_t>(n->sid + 1, e.nodes_.size() * 2), nullptr);
+      if (e.nodes_[n->sid]) throw ApiError(APT_ERR_ARGUMENT, "JSON: duplicate species id");
+      e.nodes_[n->sid] = n;
+      e.width_++;
+      n->full_upload = true;
+      e.queueRefresh(n);
+      for (const JVal &c: jn.at("children").arr) node(c);
+      return n;
+    }
+  } rec { *this };
+  const JVal &jt = j.at("tree");
+  if (jt.type == JVal::OBJ) root_ = rec.node(jt);
+  aliveSpecies_.clear();
+  for (const JVal &a: j.at("alive").arr) aliveSpecies_.insert(a.u32());
+  nextNodeID_ = j.at("nextSID").u32();
+
+  // Ensure correct parenting (:960-962): contributors.update({}) = stable_sort + currentMain on stored flags
+  for (Species *n: nodes_) {
+    if (!n) continue;
+    std::stable_sort(n->contribs.begin(), n->contribs.end(),
+                     [] (const Contributor &l, const Contributor &r) { return l.count > r.count; });
+    Species *newMC = updateParent(n, currentMain(n));
+    if (newMC) newMC->children.push_back(n);
+  }
+}
+
+} // namespace apt

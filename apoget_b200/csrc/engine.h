@@ -167,6 +167,7 @@ public:
   void resetStats (void) { insertions_ = deletions_ = comparisons_ = branching_ = 0; }
   std::vector<apt_event>& events (void) { return events_; }
   std::string toJson (void) const;
+  void fromJson (const std::string &text);
   Species* nodeAt (uint32_t sid) const;
   Species* root (void) const { return root_; }
   const std::set<uint32_t>& aliveSpecies (void) const { return aliveSpecies_; }

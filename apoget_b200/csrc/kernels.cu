@@ -197,6 +197,31 @@ __global__ void pairwise_kernel (uint32_t wp4, const uint4 *__restrict__ payload
   }
 }
 
+// crossover.h:234-240: dist = distance(mother, father); compat = mother.compatibility(dist)
+template <int KIND>
+__global__ void mate_compat_kernel (uint32_t wp4, const uint4 *__restrict__ payload, const float4 *__restrict__ cmeta,
+                                    uint32_t n_pairs, const uint32_t *__restrict__ im, const uint32_t *__restrict__ ifa,
+                                    float *__restrict__ out_dist, double *__restrict__ out_compat) {
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  const uint32_t m = __ldg(im + p);
+  const uint4 *a = payload + size_t(m) * wp4, *b = payload + size_t(__ldg(ifa + p)) * wp4;
+  double d;
+  if (KIND == 0) {
+    uint32_t acc = 0;
+    for (uint32_t v = lane; v < wp4; v += 32) acc += popc4(__ldg(a + v), __ldg(b + v));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    d = double(acc);
+  } else {
+    double acc = 0.;
+    for (uint32_t v = lane; v < wp4; v += 32) acc += sqdiff4(__ldg(a + v), __ldg(b + v));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    d = sqrt(acc);
+  }
+  if (lane == 0) { out_dist[p] = float(d);  out_compat[p] = compat_generic(__ldg(cmeta + m), d); }
+}
+
 // enveloppecriteria.cpp:40-84 (crit 0) and :87-133 (crit 1); one thread per candidate genome
 __global__ void env_contribution_kernel (int crit, uint32_t K, uint32_t n, const float *__restrict__ edist,
                                          const float *__restrict__ gdist, uint8_t *__restrict__ out_better,
@@ -413,6 +438,19 @@ void launch_env_contribution (int crit, uint32_t K, uint32_t n, const float *edi
                               uint8_t *out_better, uint32_t *out_than, float *out_value, cudaStream_t stream) {
   if (!n) return;
   env_contribution_kernel<<<(n + 127) / 128, 128, 0, stream>>>(crit, K, n, edist, gdist, out_better, out_than, out_value);
+}
+
+void launch_mate_compat (int kind, uint32_t wp, const uint32_t *payload, const float4 *cmeta, uint32_t n_pairs,
+                         const uint32_t *idx_mother, const uint32_t *idx_father, float *out_dist, double *out_compat,
+                         cudaStream_t stream) {
+  if (!n_pairs) return;
+  const uint32_t grid = uint32_t((size_t(n_pairs) * 32 + 255) / 256);
+  if (kind == 0)
+    mate_compat_kernel<0><<<grid, 256, 0, stream>>>(wp >> 2, reinterpret_cast<const uint4*>(payload), cmeta, n_pairs,
+                                                    idx_mother, idx_father, out_dist, out_compat);
+  else
+    mate_compat_kernel<1><<<grid, 256, 0, stream>>>(wp >> 2, reinterpret_cast<const uint4*>(payload), cmeta, n_pairs,
+                                                    idx_mother, idx_father, out_dist, out_compat);
 }
 
 void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n_pairs, const uint32_t *idx_a,

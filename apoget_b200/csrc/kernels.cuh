@@ -142,6 +142,12 @@ void launch_classify_children (const ChildArgs &a, cudaStream_t stream);
 void launch_scatter_blocks_f32 (const float *src, const uint32_t *idx, uint32_t n, uint32_t len, float *dst,
                                 cudaStream_t stream);
 
+/// Mate pre-filter (bailOutCrossver, src/core/crossover.h:222-248): per (mother, father) pair the genomic
+/// distance and the compatibility the MOTHER perceives at that distance (femaleBiased default).
+void launch_mate_compat (int kind, uint32_t wp, const uint32_t *payload, const float4 *cmeta, uint32_t n_pairs,
+                         const uint32_t *idx_mother, const uint32_t *idx_father, float *out_dist, double *out_compat,
+                         cudaStream_t stream);
+
 /// Dense sweep (every birth x every species), fused score / threshold / argmax.
 void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg,
                             const uint32_t *b_payload, const float4 *b_cmeta, uint32_t n_births,

@@ -80,3 +80,17 @@ def pairwise(kind, payload, idx_a, idx_b, device=0):
     p = make_params(kind, words, device, 0)
     check(lib().apt_pairwise(ctypes.byref(p), n, _ptr(payload), a.size, _ptr(a), _ptr(b), _ptr(out)))
     return out
+
+
+def mate_compat(kind, payload, compat, idx_mother, idx_father, device=0):
+    """bailOutCrossver's pre-filter: (distance(mother, father), mother.compatibility(distance)) per pair."""
+    payload = _u32(payload)
+    n, words = payload.shape
+    compat = np.ascontiguousarray(compat, dtype=np.float32).reshape(n, 3)
+    a, b = _u32(idx_mother), _u32(idx_father)
+    dist = np.zeros(a.size, dtype=np.float32)
+    comp = np.zeros(a.size, dtype=np.float64)
+    p = make_params(kind, words, device, 0)
+    check(lib().apt_mate_compat(ctypes.byref(p), n, _ptr(payload), _ptr(compat), a.size, _ptr(a), _ptr(b),
+                                _ptr(dist), _ptr(comp)))
+    return dist, comp

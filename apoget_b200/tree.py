@@ -131,6 +131,13 @@ class PhylogeneticTree:
         lib().apt_tree_to_json(self._h, buf, n)
         return json.loads(buf.raw[:n].decode())
 
+    def from_json(self, dump):
+        """fromJson (:946-967) into this (empty) tree; `dump` is a dict as returned by to_json, or its text."""
+        text = dump if isinstance(dump, (str, bytes)) else json.dumps(dump)
+        if isinstance(text, str):
+            text = text.encode()
+        check(lib().apt_tree_from_json(self._h, text, len(text)))
+
     def counters(self) -> dict:
         out = np.zeros(16, dtype=np.uint64)
         check(lib().apt_tree_counters(self._h, out.ctypes.data_as(_lib.u64p)))

@@ -19,8 +19,8 @@
 // compat = {optimalDistance, inbreedTolerance, outbreedTolerance}).  New with respect to the
 // reference: addGenomes(first, last, out), whose result is defined as that of calling addGenome on
 // every element in order.  Not provided ("out of scope"): copy construction /
-// assignment (:98-118), fromJson / readFrom (:946-967, :1004-1016) and logTo (:874-879).
-// toJson / saveTo need nlohmann::json: define APT_WITH_JSON before including.
+// assignment (:98-118; trees are movable) and logTo (:874-879).
+// toJson / saveTo / fromJson / readFrom need nlohmann::json: define APT_WITH_JSON before including.
 #ifndef APT_PHYLOGENETICTREE_HPP
 #define APT_PHYLOGENETICTREE_HPP
 
@@ -195,6 +195,9 @@ public:
   ~PhylogeneticTree (void) { if (_tree) apt_tree_destroy(_tree); }
   PhylogeneticTree (const PhylogeneticTree&) = delete;
   PhylogeneticTree& operator= (const PhylogeneticTree&) = delete;
+  PhylogeneticTree (PhylogeneticTree &&that) noexcept
+    : _tree(that._tree), _rsetSize(that._rsetSize), _aliveSpecies(std::move(that._aliveSpecies)),
+      _callbacks(nullptr), _rsets(std::move(that._rsets)) { that._tree = nullptr; }
 
   // == Accessors (:155-202) ==
   Callbacks* callbacks (void) { return _callbacks; }
@@ -320,6 +323,29 @@ public:
     j["nextSID"] = s[4];
   }
 
+  /// :946-967 -- into an EMPTY tree.  Genomes and user data are rebuilt by the user's own from_json and
+  /// re-encoded for the device; parents are re-derived from the stored contributors as in the reference.
+  static void fromJson (const json &j, PhylogeneticTree &pt) {
+    json e;                                   // the same dump with device-encoded genomes, for the engine
+    e["_step"] = j["_step"];  e["_envSize"] = j["_envSize"];  e["_stillborns"] = j["_stillborns"];
+    e["alive"] = j["alive"].is_null() ? json::array() : j["alive"];
+    e["nextSID"] = j["nextSID"];
+    e["tree"] = j["tree"].is_null() ? json() : pt.loadNode(j["tree"]);
+    const std::string text = e.dump();
+    check(apt_tree_from_json(pt._tree, text.data(), text.size()));
+    pt._aliveSpecies.clear();
+    for (const auto &a: e["alive"]) pt._aliveSpecies.insert(SID(a.get<uint>()));
+  }
+
+  /// :1004-1016
+  static PhylogeneticTree readFrom (const std::string &filename, int device = 0) {
+    std::ifstream ifs (filename);
+    if (!ifs) throw std::invalid_argument("Unable to open '" + filename + "' for reading");
+    PhylogeneticTree pt (device);
+    fromJson(json::parse(ifs), pt);
+    return pt;
+  }
+
   /// :984-1001
   bool saveTo (const std::string &filename) const {
     std::ofstream ofs (filename);
@@ -414,6 +440,40 @@ private:
   }
 
 #ifdef APT_WITH_JSON
+  /// One node of a dump -> the engine's layout (genome as {c, g, w}); fills the host-side enveloppe objects
+  json loadNode (const json &jn) {
+    json out;
+    const SID sid = SID(jn["id"].get<uint>());
+    out["id"] = jn["id"];  out["data"] = jn["data"];  out["contribs"] = jn["contribs"].is_null() ? json::array() : jn["contribs"];
+    out["dists"] = jn["dists"].is_null() ? json::array() : jn["dists"];
+    json env = json::array(), children = json::array();
+    auto &rset = _rsets[sid];
+    if (!jn["envlp"].is_null())
+      for (const auto &jr: jn["envlp"]) {
+        Representative ep;
+        ep.timestamp = 0;
+        ep.genome = jr[0].get<Genome>();
+        ep.userData = std::make_unique<UserData>(GID::INVALID);        // node.hpp:59-63
+        *ep.userData = jr[1].get<UserData>();
+        uint32_t payload[Encoding::words];
+        float compat[3];
+        Encoding::encode(ep.genome, payload, compat);
+        const Genealogy &ge = ep.genome.genealogy();
+        json g;
+        g["c"] = { compat[0], compat[1], compat[2] };
+        g["g"] = { { "f", { { "g", uint(ge.father.gid) }, { "s", uint(ge.father.sid) } } },
+                   { "m", { { "g", uint(ge.mother.gid) }, { "s", uint(ge.mother.sid) } } },
+                   { "s", { { "g", uint(ge.self.gid) }, { "s", uint(ge.self.sid) } } } };
+        g["w"] = std::vector<uint32_t>(payload, payload + Encoding::words);
+        env.push_back({ g, uint(ge.self.gid) });
+        rset.push_back(std::move(ep));
+      }
+    if (!jn["children"].is_null())
+      for (const auto &jc: jn["children"]) children.push_back(loadNode(jc));
+    out["envlp"] = env;  out["children"] = children;
+    return out;
+  }
+
   json nodeJson (SID sid) const {
     apt_node_info i;
     check(apt_tree_node_info(_tree, uint32_t(sid), &i));

@@ -138,6 +138,11 @@ uint32_t apt_tree_events (apt_tree *t, apt_event *out, uint32_t cap, int drain);
  * as the gid the slot object was last built from (:708-710).  Returns the length; copies at most cap. */
 uint64_t apt_tree_to_json (apt_tree *t, char *out, uint64_t cap);
 
+/* fromJson (:946-967) for a dump in the layout of apt_tree_to_json, into an EMPTY tree: rebuilds the
+ * hierarchy (:908-927), re-derives the parents from the stored contributors (:960-962) and schedules
+ * the whole pool for upload.  A dump built with another rsetSize is refused like at :949-954. */
+int apt_tree_from_json (apt_tree *t, const char *text, uint64_t len);
+
 /* Node accessors used by the C++ binding (include/apt/phylogenetictree.hpp). */
 typedef struct apt_node_info {
   uint32_t sid, parent_sid;           /* parent_sid = APT_INVALID for parentless nodes */
@@ -210,6 +215,14 @@ int apt_env_contribution (const apt_params *params, uint32_t n, const float *edi
 /* Births x births distances for in-batch entrants: out[p] = distance(payload[a[p]], payload[b[p]]). */
 int apt_pairwise (const apt_params *params, uint32_t n_genomes, const uint32_t *payload,
                   uint32_t n_pairs, const uint32_t *idx_a, const uint32_t *idx_b, float *out);
+
+/* Mate pre-filter of bailOutCrossver (src/core/crossover.h:222-248) for n_pairs (mother, father) pairs of a
+ * population of n_genomes: out_dist[p] = distance(mother, father) (:234-236), out_compat[p] = the
+ * compatibility the MOTHER perceives at that distance (femaleBiased, the default fcompat, :238-240).
+ * Hamming distances are exact; compat uses the device exp() (<= 1 ulp from the host's). */
+int apt_mate_compat (const apt_params *params, uint32_t n_genomes, const uint32_t *payload, const float *compat,
+                     uint32_t n_pairs, const uint32_t *idx_mother, const uint32_t *idx_father,
+                     float *out_dist, double *out_compat);
 
 /* Pipe-throughput micro-benchmarks (roofline denominators not in MEASURED_PEAKS.json), best of 5:
  * out[0] popc32/s (XOR + POPC per op, as in a Hamming distance), out[1] LOP3/s, out[2] DFMA/s,

@@ -212,6 +212,8 @@ int run (const apt_trace::Trace &t, const Options &o) {
     PT::fromJson(j0, copy);
     PT::toJson(j1, copy);
     roundtripOk = (j0 == j1);
+    std::ofstream ofs (o.prefix + ".rt.json");      // what the reference's own fromJson makes of its dump
+    ofs << j1.dump(-1);
   }
 
   if (o.writeRes) {

@@ -26,6 +26,16 @@ def golden_json(name):
         return json.loads(f.read().decode())
 
 
+def golden_roundtrip_json(name):
+    """What the reference's own toJson -> fromJson -> toJson yields (differs from the dump where
+    re-parented sub-species get re-attached in ascending id, phylogenetictree.hpp:960-962)."""
+    p = os.path.join(GOLDEN, name + ".rt.json.gz")
+    if not os.path.exists(p):
+        return golden_json(name)
+    with gzip.open(p, "rb") as f:
+        return json.loads(f.read().decode())
+
+
 def golden_trace_path(name):
     return os.path.join(GOLDEN, name + ".trace")
 

@@ -16,7 +16,9 @@ using json = nlohmann::json;
 
 namespace apt {
 void to_json (json &j, const PID &p) { j["g"] = uint(p.gid); j["s"] = uint(p.sid); }
+void from_json (const json &j, PID &p) { p.gid = GID(j["g"].get<uint>()); p.sid = SID(j["s"].get<uint>()); }
 void to_json (json &j, const Genealogy &g) { j["m"] = g.mother; j["f"] = g.father; j["s"] = g.self; }
+void from_json (const json &j, Genealogy &g) { from_json(j["m"], g.mother); from_json(j["f"], g.father); from_json(j["s"], g.self); }
 }
 
 template <uint32_t W>
@@ -26,7 +28,15 @@ struct Genome {
   float mu, sin, sout;
   const Genealogy& genealogy (void) const { return gen; }
   friend void to_json (json &j, const Genome &g) { j["g"] = g.gen; j["c"] = {g.mu, g.sin, g.sout}; j["w"] = g.w; }
+  friend void from_json (const json &j, Genome &g) {
+    apt::from_json(j["g"], g.gen);
+    g.mu = j["c"][0];  g.sin = j["c"][1];  g.sout = j["c"][2];
+    g.w = j["w"].get<std::array<uint32_t, W>>();
+  }
 };
+
+template <uint32_t W, apt_kind KIND> struct Tagged;
+template <uint32_t W, apt_kind KIND> void from_json (const json &j, Tagged<W, KIND> &g) { from_json(j, static_cast<Genome<W>&>(g)); }
 
 template <uint32_t W, apt_kind KIND>
 struct Tagged : Genome<W> {};
@@ -50,6 +60,7 @@ struct UD {
   UD (GID g) : gid(uint32_t(g)) {}
   void removedFromEnveloppe (void) { removed++; }
   friend void to_json (json &j, const UD &u) { j = u.gid; }
+  friend void from_json (const json &j, UD &u) { u.gid = j.get<uint32_t>(); }
 };
 
 struct Event { uint32_t type, a, b, c; };
@@ -109,6 +120,13 @@ int run (const apt_trace::Trace &t, const std::string &prefix, bool oneByOne) {
   }
   const auto &st = tree.stats();
   { std::ofstream ofs (prefix + ".json");  tree.saveTo(ofs, -1); }
+  {
+    // saveTo -> readFrom -> saveTo: must equal what the reference's own round trip produces
+    PT copy = PT::readFrom(prefix + ".json");
+    std::ofstream ofs (prefix + ".rt.json");
+    copy.saveTo(ofs, -1);
+    if (copy.width() != tree.width() || copy.nextNodeID() != tree.nextNodeID()) bad++;
+  }
   FILE *f = fopen((prefix + ".res").c_str(), "wb");
   if (!f) return 2;
   uint32_t n = B, ne = uint32_t(g_events.size());

@@ -4,7 +4,8 @@ Run in the build container (needs /root/reference): ``python tests/golden/make_g
 For every case below it writes ``<name>.trace`` (the input, produced by apoget_b200.synth with a
 fixed seed), ``<name>.res`` (per-birth species ids, enveloppe-entry flags, the callback stream and
 Stats as written by oracle/_ref/apt_ref_driver) and ``<name>.json.gz`` (the reference's own
-``saveTo`` dump, phylogenetictree.hpp:934-941, 997-1001).  ``cases.json`` lists the cases with the
+``saveTo`` dump, phylogenetictree.hpp:934-941, 997-1001); ``<name>.rt.json.gz`` is the dump after the
+reference's own toJson -> fromJson -> toJson when that is not a fixed point.  ``cases.json`` lists the cases with the
 PTree configuration each one was run with.
 """
 import gzip
@@ -63,12 +64,21 @@ def main():
             tp = os.path.join(HERE, name + ".trace")
             synth.write_trace(tp, t)
             prefix = os.path.join(tmp, name)
-            summary = oracle.run_reference(tp, prefix, cfg)
+            summary = oracle.run_reference(tp, prefix, cfg, extra=["--roundtrip"])
             shutil.copy(prefix + ".res", os.path.join(HERE, name + ".res"))
             with open(prefix + ".json", "rb") as f, \
                     gzip.GzipFile(os.path.join(HERE, name + ".json.gz"), "wb", mtime=0) as g:
                 g.write(f.read())
-            index[name] = dict(gen=gen, cfg=cfg, births=summary["births"], species=summary["next_sid"],
+            # the reference's fromJson re-attaches sub-species in ascending id (phylogenetictree.hpp:960-962):
+            # where that changes the dump, keep what the reference itself produces
+            rt = os.path.join(HERE, name + ".rt.json.gz")
+            if summary["roundtrip_ok"]:
+                if os.path.exists(rt):
+                    os.remove(rt)
+            else:
+                with open(prefix + ".rt.json", "rb") as f, gzip.GzipFile(rt, "wb", mtime=0) as g:
+                    g.write(f.read())
+            index[name] = dict(roundtrip_fixed_point=bool(summary["roundtrip_ok"]), gen=gen, cfg=cfg, births=summary["births"], species=summary["next_sid"],
                                width=summary["width"], comparisons=summary["comparisons"],
                                branching=summary["branching"])
             print(name, summary)

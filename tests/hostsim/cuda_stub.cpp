@@ -243,6 +243,7 @@ void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n
                       float *out, cudaStream_t) {
   for (uint32_t p = 0; p < n; p++) out[p] = float(dist(kind, wp, payload + size_t(a[p]) * wp, payload + size_t(b[p]) * wp));
 }
+void launch_mate_compat (int, uint32_t, const uint32_t*, const float4*, uint32_t, const uint32_t*, const uint32_t*, float*, double*, cudaStream_t) {}
 void launch_classify_dense (const PoolView&, const ScoreCfg&, const uint32_t*, const float4*, uint32_t, uint32_t*, float*,
                             uint32_t*, uint32_t*, cudaStream_t) {}
 

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import golden_cases, GOLDEN
+from conftest import golden_cases, golden_roundtrip_json, GOLDEN
 
 CASES = [("c2_b256_k10", []), ("hybrids_b256_k5", ["--one-by-one"]), ("c4_b4096_k10", []),
          ("semicontinuous_b256", ["--semi"]), ("crit0_b256", ["--crit", "0"])]
@@ -31,6 +31,7 @@ def _run(exe, name, extra, tmp_path, f32=False):
     jb = json.loads(gzip.open(os.path.join(GOLDEN, name + ".json.gz")).read())
     if not f32:
         assert ja == jb
+        assert json.load(open(prefix + ".rt.json")) == golden_roundtrip_json(name), "readFrom differs from the reference's"
 
 
 @pytest.mark.parametrize("name,extra", CASES)

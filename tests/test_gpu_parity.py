@@ -219,3 +219,29 @@ def test_tree_parallel_host_paths(name, monkeypatch):
     monkeypatch.setenv("APT_PAR_MIN", "1")
     monkeypatch.setenv("APT_HOST_THREADS", "4")
     _compare(name)
+
+
+@pytest.mark.parametrize("kind,words", [(synth.BITS, 8), (synth.BITS, 128), (synth.F32, 64)])
+def test_mate_compat_kernel(kind, words):
+    """bailOutCrossver's pre-filter (crossover.h:234-240): distance + the mother's compatibility."""
+    from apoget_b200.kernels import mate_compat
+    rng = np.random.default_rng(words + 1)
+    n = 80
+    if kind == synth.BITS:
+        pl = rng.integers(0, 2**32, size=(1, words), dtype=np.uint32) ^ \
+            (rng.integers(0, 2**32, size=(n, words), dtype=np.uint32) & np.uint32(0x01010101))
+        cp = np.stack([rng.uniform(0, 20, n), rng.uniform(3, 12, n), rng.uniform(3, 12, n)], 1).astype(np.float32)
+    else:
+        pl = (rng.standard_normal((1, words)) + 0.1 * rng.standard_normal((n, words))).astype(np.float32).view(np.uint32)
+        cp = np.stack([rng.uniform(0, 1, n), rng.uniform(.2, 1, n), rng.uniform(.2, 1, n)], 1).astype(np.float32)
+    m, f = rng.integers(0, n, size=400), rng.integers(0, n, size=400)
+    dist, comp = mate_compat(kind, pl, cp, m, f)
+    for p in range(m.size):
+        d = oracle.distance(kind, pl[m[p]], pl[f[p]])
+        c = oracle.compatibility(*[float(x) for x in cp[m[p]]], d)
+        if kind == synth.BITS:
+            assert dist[p] == np.float32(d)
+            assert abs(comp[p] - c) <= 4e-16 * max(c, 1e-300) + 1e-300 or abs(comp[p] - c) <= 1e-15
+        else:
+            assert abs(dist[p] - d) <= F32_RTOL * d
+            assert abs(comp[p] - c) <= 1e-9

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 from apoget_b200 import _lib, build as apt_build, synth
-from conftest import golden_cases, golden_json, golden_trace_path, GOLDEN, ROOT
+from conftest import golden_cases, golden_json, golden_roundtrip_json, golden_trace_path, GOLDEN, ROOT
 
 CASES = sorted(golden_cases())
 
@@ -162,3 +162,52 @@ def test_parallel_host_paths(hostsim, name, monkeypatch):
     monkeypatch.setenv("APT_PAR_MIN", "1")
     monkeypatch.setenv("APT_HOST_THREADS", "4")
     _compare(hostsim, name)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_json_load_matches_the_references_fromJson(hostsim, name):
+    """fromJson (phylogenetictree.hpp:946-967) of the reference's dump, dumped again, must equal what the
+    reference's own round trip yields -- including the four cases where that is NOT a fixed point."""
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    dump = golden_json(name)
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    tree.from_json(dump)
+    assert tree.to_json() == golden_roundtrip_json(name)
+    assert tree.stats()["next_sid"] == dump["nextSID"]
+
+
+def test_json_checkpoint_resume(hostsim):
+    """Stop after some generations, dump, load into a fresh tree, continue: same final tree as an
+    uninterrupted run (the device pool is rebuilt from the loaded enveloppes)."""
+    name = "c2_b256_k10"
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    half = t.n_gens // 2
+    a = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, _ = a.replay(t, max_gens=half)
+    b = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    b.from_json(a.to_json())
+    # continue the replay on b with the species ids assigned so far
+    from apoget_b200.tree import INVALID
+    for g in range(half, t.n_gens):
+        b0, b1 = int(t.gen_birth_off[g]), int(t.gen_birth_off[g + 1])
+        m, f = t.mother[b0:b1], t.father[b0:b1]
+        hm, hf = m != INVALID, f != INVALID
+        s, _, _ = b.add_genomes(t.payload[b0:b1], t.compat[b0:b1], np.arange(b0 + 1, b1 + 1, dtype=np.uint32),
+                                np.where(hm, m + 1, INVALID), np.where(hm, sids[np.where(hm, m, 0)], INVALID),
+                                np.where(hf, f + 1, INVALID), np.where(hf, sids[np.where(hf, f, 0)], INVALID))
+        sids[b0:b1] = s
+        b.del_genomes(sids[t.deaths_of(g)])
+        b.step(g + 1, sids[t.alive_of(g)])
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"])
+    assert b.to_json() == golden_json(name)
+
+
+def test_json_load_refuses_other_enveloppe_size(hostsim):
+    t = synth.read_trace(golden_trace_path("k1_b64"))
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, K=3)
+    with pytest.raises(_lib.AptError) as e:
+        tree.from_json(golden_json("k1_b64"))
+    assert "enveloppe size" in str(e.value)
