@@ -245,3 +245,30 @@ def test_mate_compat_kernel(kind, words):
         else:
             assert abs(dist[p] - d) <= F32_RTOL * d
             assert abs(comp[p] - c) <= 1e-9
+
+
+def test_tree_json_checkpoint_resume():
+    """Dump after half the generations, load into a fresh tree (pool rebuilt from the dump), continue."""
+    from apoget_b200.tree import PhylogeneticTree, INVALID
+    name = "c2_b256_k10"
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    half = t.n_gens // 2
+    a = PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, _ = a.replay(t, max_gens=half)
+    b = PhylogeneticTree(t.kind, t.words, **cfg)
+    b.from_json(a.to_json())
+    for g in range(half, t.n_gens):
+        b0, b1 = int(t.gen_birth_off[g]), int(t.gen_birth_off[g + 1])
+        m, f = t.mother[b0:b1], t.father[b0:b1]
+        hm, hf = m != INVALID, f != INVALID
+        s, _, _ = b.add_genomes(t.payload[b0:b1], t.compat[b0:b1], np.arange(b0 + 1, b1 + 1, dtype=np.uint32),
+                                np.where(hm, m + 1, INVALID), np.where(hm, sids[np.where(hm, m, 0)], INVALID),
+                                np.where(hf, f + 1, INVALID), np.where(hf, sids[np.where(hf, f, 0)], INVALID))
+        sids[b0:b1] = s
+        b.del_genomes(sids[t.deaths_of(g)])
+        b.step(g + 1, sids[t.alive_of(g)])
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"])
+    assert b.to_json() == golden_json(name)
+    assert b.counters()["stream_births"] > 0
