@@ -223,20 +223,10 @@ resolve_streams_kernel (StreamArgs a) {
       score = resum(a.cfg, ws, k, tid);
     }
     bool mine = active;           // not final yet
-    // With few warps the decision step is taken warp by warp, in order (GATED): a later warp keeps its
-    // distances current after every commit but only re-sums and decides when its turn comes -- deciding
-    // earlier would be thrown away by the next commit of an earlier warp.  Wide CTAs (long streams)
-    // decide speculatively in all warps at once: fewer sequential steps, more redundant work.
-    constexpr bool GATED = NW <= 4;
-    uint32_t turn = 0;
-    bool dirty = false;
 
     for (;;) {
-      const bool myTurn = !GATED || uint32_t(warp) == turn;
-      if (GATED && myTurn && dirty && mine) { score = resum(a.cfg, ws, k, tid); dirty = false; }
-      const bool deciding = mine && myTurn;
-      const bool uncertain = deciding && !LUT && fabsf(score) <= a.guard;
-      const bool accept = deciding && score > 0.f;
+      const bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
+      const bool accept = mine && score > 0.f;
       bool modifies = false;
       uint32_t than = NONE;
       if (accept) {
@@ -251,7 +241,7 @@ resolve_streams_kernel (StreamArgs a) {
       uint32_t stop = NONE;
 #pragma unroll
       for (int w = 0; w < NW; w++) stop = min(stop, ctl[w]);
-      const bool fin = deciding && (stop == NONE || uint32_t(tid) < stop);
+      const bool fin = mine && (stop == NONE || uint32_t(tid) < stop);
       if (fin) {
         a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
         if (accept) { a.out_sid[b] = sid; nAcc0 += (ccls == 0); nAcc1 += (ccls == 1); nAcc2 += (ccls == 2); }
@@ -268,13 +258,7 @@ resolve_streams_kernel (StreamArgs a) {
           a.ft_list[2 * at] = b;  a.ft_list[2 * at + 1] = g;
         }
       }
-      if (stop == NONE) {
-        if (!GATED) break;
-        turn++;                                    // this warp is final: the next one decides
-        if (turn * 32 >= nb) break;
-        __syncthreads();                           // ctl is rewritten in the next step
-        continue;
-      }
+      if (stop == NONE) break;
       if (uint32_t(tid) == stop) {
         if (uncertain) { a.act[b] = ACT_UNCERTAIN; ctl[32] = NONE; }   // the host takes the stream over from here
         else {
@@ -312,7 +296,7 @@ resolve_streams_kernel (StreamArgs a) {
       // later births see the new representative: re-measure that slot only, re-sum in order
       if (mine) {
         measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, sl, tid);
-        if (myTurn) score = resum(a.cfg, ws, k, tid); else dirty = true;
+        score = resum(a.cfg, ws, k, tid);
       }
     }
     __syncthreads();
