@@ -352,6 +352,54 @@ int apt_classify_dense (apt_pool *p, uint32_t n_births, const uint32_t *payload,
   });
 }
 
+int apt_classify_dense_shard_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_payload, const float *d_compat,
+                                  uint32_t species_offset, uint32_t rank, uint32_t world,
+                                  const uint64_t *peer_records, void *stream) {
+  return guarded([&] {
+    need(p && d_payload && d_compat && peer_records, "null argument");
+    need(world >= 1 && world <= MAX_PEERS && rank < world, "bad shard layout (at most 8 shards)");
+    need(!p->lut || p->classes.size() <= 3, "device-resident births need a single compatibility class (or APT_FLAG_FORCE_GENERIC)");
+    cudaCheck(cudaSetDevice(p->prm.device), "cudaSetDevice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ShardSink sink;
+    for (uint32_t q = 0; q < world; q++) {
+      need(peer_records[q] != 0, "null peer buffer");
+      sink.peer[q] = reinterpret_cast<uint4*>(uintptr_t(peer_records[q]));
+    }
+    sink.world = world;  sink.rank = rank;  sink.species_offset = species_offset;
+    uint32_t *dB = nullptr;  float4 *dM = nullptr;
+    cudaCheck(cudaMallocAsync(&dB, (size_t(n_births) * p->wp + 4) * 4, st), "cudaMallocAsync");
+    cudaCheck(cudaMallocAsync(&dM, (size_t(n_births) + 1) * sizeof(float4), st), "cudaMallocAsync");
+    launch_pack_births(d_payload, d_compat, nullptr, n_births, p->W, p->wp, dB, dM, st);
+    if (dense_tiled_supports(p->wp, p->K)) {
+      // the sweep kernel itself stores the records into the peers' buffers
+      launch_classify_dense_tiled(p->view(), p->cfg(), dB, dM, n_births, nullptr, nullptr, nullptr, nullptr, st, &sink);
+    } else {
+      uint32_t *dW = nullptr;
+      cudaCheck(cudaMallocAsync(&dW, size_t(n_births) * 16 + 16, st), "cudaMallocAsync");
+      uint32_t *best = dW, *first = dW + n_births, *count = dW + 2 * size_t(n_births);
+      float *score = reinterpret_cast<float*>(dW + 3 * size_t(n_births));
+      launch_classify_dense(p->view(), p->cfg(), dB, dM, n_births, best, score, first, count, st);
+      launch_publish_records(best, score, first, count, n_births, sink, st);
+      cudaCheck(cudaFreeAsync(dW, st), "cudaFreeAsync");
+    }
+    cudaCheck(cudaGetLastError(), "classify_dense launch");
+    cudaCheck(cudaFreeAsync(dB, st), "cudaFreeAsync");
+    cudaCheck(cudaFreeAsync(dM, st), "cudaFreeAsync");
+  });
+}
+
+int apt_combine_shards_dev (int device, uint32_t n_births, uint32_t world, const void *d_records,
+                            uint32_t *d_best, float *d_best_score, uint32_t *d_first, uint32_t *d_count, void *stream) {
+  return guarded([&] {
+    need(world >= 1 && (n_births == 0 || (d_records && d_best && d_best_score && d_first && d_count)), "null argument");
+    requireDevice(device);
+    launch_combine_shards(static_cast<const uint4*>(d_records), n_births, world, d_best, d_best_score, d_first, d_count,
+                          static_cast<cudaStream_t>(stream));
+    cudaCheck(cudaGetLastError(), "combine_shards launch");
+  });
+}
+
 int apt_env_contribution (const apt_params *params, uint32_t n, const float *edist, const float *gdist,
                           uint8_t *out_better, uint32_t *out_than, float *out_value) {
   return guarded([&] {

@@ -1179,6 +1179,25 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
                        uint32_t *outReplaced, uint32_t &done) {
   double t0 = now();
   chunkEpoch_++;
+  // the births' genomes start their way to the device before the host groups them: the copy
+  // overlaps the grouping below (host buffers only; a chunk that ends up with no device work at
+  // all -- an empty pool -- has paid for a copy nobody reads)
+  bool birthsUploaded = false;
+  auto uploadBirths = [&] (void) {
+    dBirths_.reserve(size_t(n) * wp_);
+    if (wp_ == W_) {
+      cudaCheck(cudaMemcpyAsync(dBirths_.p, payload, size_t(n) * W_ * 4, cudaMemcpyHostToDevice, stream_), "births");
+    } else {
+      hBirths_.reserve(size_t(n) * wp_);
+      for (uint32_t i = 0; i < n; i++) {
+        memcpy(hBirths_.p + size_t(i) * wp_, payload + size_t(i) * W_, W_ * 4);
+        memset(hBirths_.p + size_t(i) * wp_ + W_, 0, (wp_ - W_) * 4);
+      }
+      cudaCheck(cudaMemcpyAsync(dBirths_.p, hBirths_.p, size_t(n) * wp_ * 4, cudaMemcpyHostToDevice, stream_), "births");
+    }
+    birthsUploaded = true;
+  };
+  if (!dPayload && n >= 4096 && nSlots_ > freeSlots_.size()) uploadBirths();
   // ---- prepare: classes; births with a single parent species join that species' stream, the
   //      others get (birth, species) pairs for the speculative scoring kernel ----
   hCls_.reserve(n);
@@ -1245,17 +1264,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         dBirthRows = dBirths_.p;
       }
     } else {
-      dBirths_.reserve(size_t(n) * wp_);
-      if (wp_ == W_) {
-        cudaCheck(cudaMemcpyAsync(dBirths_.p, payload, size_t(n) * W_ * 4, cudaMemcpyHostToDevice, stream_), "births");
-      } else {
-        hBirths_.reserve(size_t(n) * wp_);
-        for (uint32_t i = 0; i < n; i++) {
-          memcpy(hBirths_.p + size_t(i) * wp_, payload + size_t(i) * W_, W_ * 4);
-          memset(hBirths_.p + size_t(i) * wp_ + W_, 0, (wp_ - W_) * 4);
-        }
-        cudaCheck(cudaMemcpyAsync(dBirths_.p, hBirths_.p, size_t(n) * wp_ * 4, cudaMemcpyHostToDevice, stream_), "births");
-      }
+      if (!birthsUploaded) uploadBirths();
       dBirthRows = dBirths_.p;
     }
     if (chunkUniform_) {
@@ -1312,6 +1321,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       cudaCheck(cudaMemsetAsync(dFtCounter_.p, 0, 4, stream_), "ft counter clear");
       a.ft_list = dFtList_.p;  a.ft_counter = dFtCounter_.p;
     }
+    const char *profPath = getenv("APT_STREAM_PROF");
+    if (profPath) { dProf_.reserve(size_t(G) * 8); a.prof = dProf_.p; }
     cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
     launch_resolve_streams(a, stream_);
     cudaCheck(cudaEventRecord(evS1_, stream_), "event record");
@@ -1347,6 +1358,19 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (P) { cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed"); timers[4] += ms; }
     if (G) {
       cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
+      if (const char *profPath = getenv("APT_STREAM_PROF")) {
+        // development aid: one text line per stream {launch, stream, births, 8 timeline words}, appended
+        std::vector<unsigned long long> hp (size_t(G) * 8);
+        cudaCheck(cudaMemcpy(hp.data(), dProf_.p, hp.size() * 8, cudaMemcpyDeviceToHost), "stream profile");
+        if (FILE *f = fopen(profPath, "a")) {
+          for (uint32_t g = 0; g < G; g++) {
+            fprintf(f, "%llu %u %u %.3f", (unsigned long long) counters[12], g, hGrpOff_.p[g + 1] - hGrpOff_.p[g], double(ms));
+            for (int q = 0; q < 8; q++) fprintf(f, " %llu", hp[size_t(g) * 8 + q]);
+            fputc('\n', f);
+          }
+          fclose(f);
+        }
+      }
       nRows = hRowCounter_.p[0];
       nFt_ = (useChildKernel && nChild) ? hFtCounter_.p[0] : 0u;
       if (nRows) {

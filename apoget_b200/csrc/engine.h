@@ -259,6 +259,7 @@ private:
   uint32_t chunkCls_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
+  DevBuf<unsigned long long> dProf_;    // per-stream timelines, only with APT_STREAM_PROF=<file>
   PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
   PinBuf<float4> hBMeta_, hStageMeta_;
   PinBuf<float> hScore_, hDist_;

@@ -385,6 +385,54 @@ void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg, const uin
                           n_births, out_best_species, out_best_score, out_first_accept, out_n_accept, stream);
 }
 
+namespace {
+__global__ void publish_records_kernel (const uint32_t *__restrict__ best, const float *__restrict__ score,
+                                        const uint32_t *__restrict__ first, const uint32_t *__restrict__ count,
+                                        uint32_t n, ShardSink sink) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const uint32_t off = sink.species_offset, be = best[b], fi = first[b];
+  const uint4 rec = make_uint4(be == 0xFFFFFFFFu ? be : be + off, __float_as_uint(score[b]),
+                               fi == 0xFFFFFFFFu ? fi : fi + off, count[b]);
+  #pragma unroll
+  for (uint32_t p = 0; p < MAX_PEERS; p++)
+    if (p < sink.world) sink.peer[p][size_t(sink.rank) * n + b] = rec;
+}
+
+__global__ void combine_shards_kernel (const uint4 *__restrict__ rec, uint32_t n, uint32_t world,
+                                       uint32_t *__restrict__ out_best, float *__restrict__ out_score,
+                                       uint32_t *__restrict__ out_first, uint32_t *__restrict__ out_count) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  uint32_t best = 0xFFFFFFFFu, first = 0xFFFFFFFFu, count = 0;
+  float score = -CUDART_INF_F;
+  for (uint32_t r = 0; r < world; r++) {
+    const uint4 q = rec[size_t(r) * n + b];
+    if (q.x != 0xFFFFFFFFu) {
+      const float s = __uint_as_float(q.y);
+      if (best == 0xFFFFFFFFu || score < s) { best = q.x; score = s; }     // shards hold increasing species ranges
+    }
+    first = min(first, q.z);
+    count += q.w;
+  }
+  out_best[b] = best;  out_score[b] = score;  out_first[b] = first;  out_count[b] = count;
+}
+} // namespace
+
+void launch_publish_records (const uint32_t *best, const float *best_score, const uint32_t *first, const uint32_t *count,
+                             uint32_t n_births, const ShardSink &sink, cudaStream_t stream) {
+  if (!n_births || !sink.world) return;
+  publish_records_kernel<<<(n_births + 255) / 256, 256, 0, stream>>>(best, best_score, first, count, n_births, sink);
+}
+
+void launch_combine_shards (const uint4 *rec, uint32_t n_births, uint32_t world, uint32_t *out_best_species,
+                            float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
+                            cudaStream_t stream) {
+  if (!n_births) return;
+  combine_shards_kernel<<<(n_births + 255) / 256, 256, 0, stream>>>(rec, n_births, world, out_best_species, out_best_score,
+                                                                    out_first_accept, out_n_accept);
+}
+
 void launch_pack_births (const uint32_t *src_payload, const float *src_compat, const uint32_t *cls, uint32_t n,
                          uint32_t words, uint32_t wp, uint32_t *dst_payload, float4 *dst_cmeta,
                          cudaStream_t stream) {

@@ -114,6 +114,7 @@ struct StreamArgs {
   uint32_t *ft_counter;       ///< ... counted here (zero-initialised)
   uint32_t *row_counter;      ///< zero-initialised; rows are claimed in blocks of 8 per stream
   int lut_in_smem = 0;        ///< set by the launcher
+  unsigned long long *prof = nullptr;   ///< optional [n_groups][8] per-stream timeline (APT_STREAM_PROF), see stream.cu
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream);
@@ -154,12 +155,35 @@ void launch_classify_dense (const PoolView &pool, const ScoreCfg &cfg,
                             uint32_t *out_best_species, float *out_best_score,
                             uint32_t *out_first_accept, uint32_t *out_n_accept, cudaStream_t stream);
 
+/// Species-sharded dense sweep: where the per-birth winners of a shard go.  With
+/// world > 0 the sweep writes ONE 16-byte record per birth {best species (pool-wide index), score
+/// bits, first accepting species, accept count} straight into every peer's gather buffer at
+/// peer[p][rank * n_births + birth] -- peer-mapped memory, i.e. NVLink stores from inside the sweep
+/// kernel -- instead of the four local arrays; the exchange needs no separate collective.
+constexpr uint32_t MAX_PEERS = 8;
+struct ShardSink {
+  uint4 *peer[MAX_PEERS];
+  uint32_t world = 0, rank = 0, species_offset = 0;
+};
+
 /// Register-tiled dense sweep (dense.cu); launch_classify_dense picks it whenever it fits.
 bool dense_tiled_supports (uint32_t wp, uint32_t K);
 void launch_classify_dense_tiled (const PoolView &pool, const ScoreCfg &cfg, const uint32_t *b_payload,
                                   const float4 *b_cmeta, uint32_t n_births, uint32_t *out_best_species,
                                   float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, const ShardSink *sink = nullptr);
+
+/// Local winners -> records in every peer's gather buffer (the sweep kernels that do not write
+/// records themselves: genome shapes the tiled kernel does not cover)
+void launch_publish_records (const uint32_t *best, const float *best_score, const uint32_t *first, const uint32_t *count,
+                             uint32_t n_births, const ShardSink &sink, cudaStream_t stream);
+
+/// Pool-wide winners from the gathered records rec[rank * n_births + birth] of `world` shards holding
+/// increasing species ranges: strictly greatest score (lowest species on ties = first shard holding
+/// the maximum), lowest accepting species, total accept count.
+void launch_combine_shards (const uint4 *rec, uint32_t n_births, uint32_t world, uint32_t *out_best_species,
+                            float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
+                            cudaStream_t stream);
 
 } // namespace apt
 

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) pipe_kernel (uint32_t iters, uint32_t see
       a4 = (a4 ^ seed) & a5 | i; a5 = (a5 ^ seed) & a6 | i; a6 = (a6 ^ seed) & a7 | i; a7 = (a7 ^ seed) & a0 | i;
     } else if (WHAT == 2) {   // DFMA
       d0 = fma(d0, 1.0000001, 0.5); d1 = fma(d1, 1.0000001, 0.5); d2 = fma(d2, 1.0000001, 0.5); d3 = fma(d3, 1.0000001, 0.5);
+    } else if (WHAT == 4) {   // F2F: float -> double -> float round trips (the `float avg += double c` of the scoring loop)
+      f0 = float(double(f0) + 0.1); f1 = float(double(f1) + 0.1); f2 = float(double(f2) + 0.1); f3 = float(double(f3) + 0.1);   // 0.1 is no float: the sum cannot be folded into an FADD
     } else {                  // FFMA
       f0 = fmaf(f0, 1.0001f, f1); f1 = fmaf(f1, 1.0001f, f2); f2 = fmaf(f2, 1.0001f, f3); f3 = fmaf(f3, 1.0001f, f4);
       f4 = fmaf(f4, 1.0001f, f5); f5 = fmaf(f5, 1.0001f, f6); f6 = fmaf(f6, 1.0001f, f7); f7 = fmaf(f7, 1.0001f, f0);
@@ -67,4 +69,10 @@ extern "C" int apt_microbench (int device, double out[4]) {
   out[2] = run<2>(4);      // DFMA / s
   out[3] = run<3>(8);      // FFMA / s
   return (out[0] > 0 && out[1] > 0 && out[2] > 0 && out[3] > 0) ? APT_OK : APT_ERR_CUDA;
+}
+
+extern "C" int apt_microbench_cvt (int device, double out[1]) {
+  if (cudaSetDevice(device) != cudaSuccess) return APT_ERR_CUDA;
+  out[0] = run<4>(8);      // F2F conversions / s (4 chains x {f32->f64, f64->f32}; the DADD between them is on another pipe)
+  return out[0] > 0 ? APT_OK : APT_ERR_CUDA;
 }

@@ -71,6 +71,7 @@ struct WarpState {
   float *minBase;     // [K]
   float *d;           // [K][T]   distances of thread t to representative r at d[r*T + t]
   double *c;          // [K][T]   compatibilities
+  float *pre;         // [K+1][T] running average BEFORE representative r is added (pre[k] = the total)
   const double *lut;  // compatibility table: shared-memory copy when it fits, else global
   uint32_t T;
 };
@@ -79,6 +80,18 @@ struct WarpState {
 template <int WQ, int KIND, bool LUT>
 __device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
                                          const WarpState &ws, uint32_t r, int lane) {
+  if (KIND == 0 && LUT) {
+    // Hamming distance stays an integer: it indexes the table directly (no double round trip)
+    uint32_t acc = 0;
+#pragma unroll
+    for (int v = 0; v < WQ; v++) acc += popc4(bw[v], ws.reps[r * WQ + v]);
+    const float4 rm = ws.rmeta[r];
+    const double ca = ws.lut[size_t(__float_as_uint(bm.w)) * cfg.lut_stride + acc];
+    const double cb = ws.lut[size_t(__float_as_uint(rm.w)) * cfg.lut_stride + acc];
+    ws.d[r * ws.T + lane] = float(acc);
+    ws.c[r * ws.T + lane] = cb < ca ? cb : ca;
+    return;
+  }
   double d;
   if (KIND == 0) {
     uint32_t acc = 0;
@@ -95,11 +108,17 @@ __device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[
   ws.c[r * ws.T + lane] = pair_compat<LUT>(cfg, ws.lut, bm, ws.rmeta[r], d);
 }
 
-/// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities
-__device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws, uint32_t k, int lane) {
+/// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities.  The float
+/// accumulation is order sensitive, so it stays sequential -- but representatives before `from` are
+/// unchanged since the last call and their partial sum is kept (pre[from]).
+__device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws, uint32_t k, int lane, uint32_t from) {
   if (cfg.full_continuous) {
-    float avg = 0.f;
-    for (uint32_t r = 0; r < k; r++) avg = float(__dadd_rn(double(avg), ws.c[r * ws.T + lane]));
+    float avg = from ? ws.pre[from * ws.T + lane] : 0.f;
+    for (uint32_t r = from; r < k; r++) {
+      ws.pre[r * ws.T + lane] = avg;
+      avg = float(__dadd_rn(double(avg), ws.c[r * ws.T + lane]));
+    }
+    ws.pre[k * ws.T + lane] = avg;
     return float(__dsub_rn(double(__fdiv_rn(avg, float(k))), cfg.avg_thr));
   }
   uint32_t matable = 0;
@@ -107,7 +126,9 @@ __device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws
   return float(__dsub_rn(double(matable), __dmul_rn(cfg.sim_thr, double(k))));
 }
 
-/// maxMinDist (enveloppecriteria.cpp:87-133) for this lane's distances against a FULL enveloppe
+/// maxMinDist (enveloppecriteria.cpp:87-133) for this lane's distances against a FULL enveloppe.
+/// :117 widens a float difference to double and :125 compares it with the float maximum: the
+/// comparison of the two floats is the same predicate, so it is taken in float.
 __device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, uint32_t K, int lane, uint32_t &than) {
   float m1 = FMAX, m2 = FMAX;
   uint32_t i1 = 0xFFFFFFFFu;
@@ -120,8 +141,8 @@ __device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, uint3
   than = 0xFFFFFFFFu;
   for (uint32_t i = 0; i < K; i++) {
     const float minNew = (i == i1) ? m2 : m1;                    // min over j != i of gdist[j]
-    const double c = double(__fadd_rn(-ws.minBase[i], minNew));  // :117
-    if (double(value) < c) { value = float(c); than = i; }      // :125-128, first index wins ties
+    const float c = __fadd_rn(-ws.minBase[i], minNew);           // :117
+    if (value < c) { value = c; than = i; }                      // :125-128, first index wins ties
   }
   return value > 0.f;                                            // :131
 }
@@ -144,8 +165,13 @@ __device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, uint3
 /// Shared-memory bytes of one stream (without the table)
 __host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T) {
   return size_t(K) * T * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
-       + size_t(K) * T * 4 + 64 * 4;
+       + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + 64 * 4;
 }
+
+__device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// Event word exchanged between the warps of a stream: earliest thread first (high bits), then what it does
+constexpr uint32_t EV_TID_SHIFT = 8, EV_UNCERTAIN = 0x80u, EV_SLOT_MASK = 0x3Fu;
 
 template <int WQ, int KIND, bool LUT, int NW>
 __global__ void __launch_bounds__(NW * 32)
@@ -165,36 +191,59 @@ resolve_streams_kernel (StreamArgs a) {
   ws.D = reinterpret_cast<float*>(base);             base += size_t(K) * K * 4;
   ws.minBase = reinterpret_cast<float*>(base);       base += size_t(K) * 4;
   ws.d = reinterpret_cast<float*>(base);             base += size_t(K) * T * 4;
+  ws.pre = reinterpret_cast<float*>(base);           base += size_t(K + 1) * T * 4;
   uint32_t *ctl = reinterpret_cast<uint32_t*>(base); base += 64 * 4;
-  // ctl[0..NW): first event thread per warp; ctl[32]: slot entered; ctl[33]: row; ctl[34]: append; ctl[36..39): counters
+  // ctl[0..NW): event word per warp; ctl[33]: first row of a claimed block; ctl[36..39): counters
   ws.lut = a.cfg.lut;
+
+  // ---- everything the stream needs first is requested before anything is waited for: the
+  //      stream's extent, then (one round trip later) the enveloppe, the first births' indices and
+  //      the table, then (another one) those births' genomes ----
+  // optional timeline of this stream (development aid, APT_STREAM_PROF): {globaltimer ns at start, SM clock at
+  // start, after the enveloppe is loaded, after the first births are scored, at the end, events, steps, SM id}
+  unsigned long long *prof = a.prof ? a.prof + size_t(g) * 8 : nullptr;
+  uint32_t profEvents = 0, profSteps = 0;
+  if (prof && tid == 0) {
+    unsigned long long gt;  uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    prof[0] = gt;  prof[1] = clock64();  prof[7] = smid;
+  }
+  const uint32_t slot = a.grp_slot[g], sid = a.grp_sid[g];
+  const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
+  const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
+  const uint4 *birthRows = reinterpret_cast<const uint4*>(a.b_payload);
+  uint32_t ordNext = (g0 + tid < g1) ? __ldg(a.order + g0 + tid) : 0u;
+  uint32_t k = min(__ldg(a.pool.fill + slot), K);
+  for (uint32_t i = tid; i < K * WQ; i += T) ws.reps[i] = poolRows[i];          // rows past the fill are never read
+  for (uint32_t i = tid; i < K; i += T) ws.rmeta[i] = a.pool.cmeta[size_t(slot) * K + i];
+  for (uint32_t i = tid; i < K * K; i += T) ws.D[i] = a.pool_dist[size_t(slot) * K * K + i];
   if (LUT && a.lut_in_smem) {
     double *lut_s = reinterpret_cast<double*>(smem + ((stream_smem(K, WQ, T) + 15) & ~size_t(15)));
     const uint32_t nd = a.cfg.lut_classes * a.cfg.lut_stride;
     for (uint32_t i = tid; i < nd; i += T) lut_s[i] = __ldg(a.cfg.lut + i);
     ws.lut = lut_s;
   }
-
-  const uint32_t slot = a.grp_slot[g], sid = a.grp_sid[g];
-  const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
-  uint32_t k = min(a.pool.fill[slot], K);
-  const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
-
-  // ---- load the enveloppe ----
-  for (uint32_t i = tid; i < k * WQ; i += T) ws.reps[i] = poolRows[i];
-  for (uint32_t i = tid; i < k; i += T) ws.rmeta[i] = a.pool.cmeta[size_t(slot) * K + i];
-  for (uint32_t i = tid; i < K * K; i += T) ws.D[i] = a.pool_dist[size_t(slot) * K * K + i];
   if (tid < 4) ctl[36 + tid] = 0;
+  uint4 bw[WQ];
+  float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
+  if (g0 + tid < g1) {
+    const uint32_t b = ordNext & ORDER_INDEX_MASK;
+#pragma unroll
+    for (int v = 0; v < WQ; v++) bw[v] = __ldg(birthRows + size_t(b) * WQ + v);
+    bm = __ldg(a.b_cmeta + b);
+  } else {
+#pragma unroll
+    for (int v = 0; v < WQ; v++) bw[v] = make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
-  auto refreshMinBase = [&] (void) {
-    for (uint32_t r = tid; r < k; r += T) {
-      float m = FMAX;
-      for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, ws.D[r * K + j]);
-      ws.minBase[r] = m;
-    }
-    __syncthreads();
-  };
-  refreshMinBase();
+  for (uint32_t r = tid; r < k; r += T) {
+    float m = FMAX;
+    for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, ws.D[r * K + j]);
+    ws.minBase[r] = m;
+  }
+  __syncthreads();
+  if (prof && tid == 0) prof[2] = clock64();
 
   uint32_t changed = 0;         // slots to write back (uniform)
   bool aborted = false;
@@ -204,44 +253,61 @@ resolve_streams_kernel (StreamArgs a) {
   for (uint32_t cb = g0; cb < g1 && !aborted; cb += T) {
     const uint32_t nb = min(T, g1 - cb);
     const bool active = uint32_t(tid) < nb;
-    const uint32_t ord = active ? a.order[cb + tid] : 0u;
+    const uint32_t ord = ordNext;
     const uint32_t b = ord & ORDER_INDEX_MASK, ccls = ord >> ORDER_CLASS_SHIFT;
-    uint4 bw[WQ];
-    float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
-    if (active) {
-      const uint4 *bq = reinterpret_cast<const uint4*>(a.b_payload) + size_t(b) * WQ;
+    if (cb != g0) {
+      if (active) {
 #pragma unroll
-      for (int v = 0; v < WQ; v++) bw[v] = __ldg(bq + v);
-      bm = __ldg(a.b_cmeta + b);
-    } else {
+        for (int v = 0; v < WQ; v++) bw[v] = __ldg(birthRows + size_t(b) * WQ + v);
+        bm = __ldg(a.b_cmeta + b);
+      } else {
 #pragma unroll
-      for (int v = 0; v < WQ; v++) bw[v] = make_uint4(0, 0, 0, 0);
+        for (int v = 0; v < WQ; v++) bw[v] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    // the next step's births start their way up from HBM while this step is resolved
+    ordNext = 0u;
+    if (cb + T + tid < g1) {
+      ordNext = __ldg(a.order + cb + T + tid);
+      const char *nx = reinterpret_cast<const char*>(birthRows + size_t(ordNext & ORDER_INDEX_MASK) * WQ);
+#pragma unroll
+      for (int o = 0; o < WQ * 16; o += 128) prefetch_l2(nx + o);
+      prefetch_l2(a.b_cmeta + (ordNext & ORDER_INDEX_MASK));
     }
     float score = 0.f;
     if (active) {
       for (uint32_t r = 0; r < k; r++) measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, tid);
-      score = resum(a.cfg, ws, k, tid);
+      score = resum(a.cfg, ws, k, tid, 0);
     }
+    if (prof && tid == 0 && cb == g0) prof[3] = clock64();
+    profSteps++;
     bool mine = active;           // not final yet
 
     for (;;) {
       const bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
       const bool accept = mine && score > 0.f;
       bool modifies = false;
-      uint32_t than = NONE;
-      if (accept) {
+      uint32_t than = 0;
+      if (accept && !uncertain) {
         if (k < K) { modifies = true; than = k; }                       // :668-677
         else if (K > 1)
           modifies = a.crit == 1 ? criterion_maxMinDist(ws, K, tid, than) : criterion_maxAverage(ws, K, tid, than);
       }
-      // earliest thread of the CTA whose decision is an event (changes the enveloppe / needs the host)
+      // earliest thread of the CTA whose decision is an event (changes the enveloppe / needs the host),
+      // published together with what it does: one barrier tells every thread who and where
       const uint32_t em = __ballot_sync(0xffffffffu, uncertain || modifies);
-      if (lane == 0) ctl[warp] = em ? uint32_t(warp * 32 + __ffs(em) - 1) : NONE;
+      if (em) {
+        const int first = __ffs(em) - 1;
+        const uint32_t word = (uint32_t(tid) << EV_TID_SHIFT) | (uncertain ? EV_UNCERTAIN : (than & EV_SLOT_MASK));
+        const uint32_t w0 = __shfl_sync(0xffffffffu, word, first);
+        if (lane == 0) ctl[warp] = w0;
+      } else if (lane == 0) ctl[warp] = NONE;
       __syncthreads();
-      uint32_t stop = NONE;
+      uint32_t event = NONE;
 #pragma unroll
-      for (int w = 0; w < NW; w++) stop = min(stop, ctl[w]);
-      const bool fin = mine && (stop == NONE || uint32_t(tid) < stop);
+      for (int w = 0; w < NW; w++) event = min(event, ctl[w]);
+      const uint32_t stop = event == NONE ? NONE : event >> EV_TID_SHIFT;
+      const bool fin = mine && uint32_t(tid) < stop;
       if (fin) {
         a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
         if (accept) { a.out_sid[b] = sid; nAcc0 += (ccls == 0); nAcc1 += (ccls == 1); nAcc2 += (ccls == 2); }
@@ -258,45 +324,52 @@ resolve_streams_kernel (StreamArgs a) {
           a.ft_list[2 * at] = b;  a.ft_list[2 * at + 1] = g;
         }
       }
-      if (stop == NONE) break;
+      if (event == NONE) break;
+      if (event & EV_UNCERTAIN) {                     // the host takes the stream over from here
+        if (uint32_t(tid) == stop) a.act[b] = ACT_UNCERTAIN;
+        aborted = true;
+        break;
+      }
+      profEvents++;
+      const uint32_t sl = event & EV_SLOT_MASK;
+      const bool append = (k < K);
+      const uint32_t kOld = k;
+      if (append) k++;
       if (uint32_t(tid) == stop) {
-        if (uncertain) { a.act[b] = ACT_UNCERTAIN; ctl[32] = NONE; }   // the host takes the stream over from here
-        else {
-          ctl[32] = than;
 #pragma unroll
-          for (int v = 0; v < WQ; v++) ws.reps[than * WQ + v] = bw[v];
-          ws.rmeta[than] = bm;
-          a.out_sid[b] = sid;
-          a.out_slot[b] = int32_t(than);
-          mine = false;
+        for (int v = 0; v < WQ; v++) ws.reps[sl * WQ + v] = bw[v];
+        ws.rmeta[sl] = bm;
+        a.out_sid[b] = sid;
+        a.out_slot[b] = int32_t(sl);
+        mine = false;
+      }
+      // the entering birth's distances are the new row / column sl of the matrix (:676-677 / :712-715);
+      // thread r owns row r, so its new minimum needs no other thread's writes (row sl = the birth's own distances)
+      for (uint32_t r = tid; r < k; r += T) {
+        float m = FMAX;
+        if (r != sl) {
+          const float dr = ws.d[r * T + stop];
+          ws.D[r * K + sl] = dr;  ws.D[sl * K + r] = dr;
+          for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, j == sl ? dr : ws.D[r * K + j]);
+        } else {
+          for (uint32_t j = 0; j < kOld; j++) if (j != sl) m = fminf(m, ws.d[j * T + stop]);
         }
+        ws.minBase[r] = m;
       }
-      if (rowLeft == 0) {
-        if (tid == 0) ctl[33] = atomicAdd(a.row_counter, 8u);
-      }
+      if (rowLeft == 0 && tid == 0) ctl[33] = atomicAdd(a.row_counter, 8u);
       __syncthreads();
-      const uint32_t sl = ctl[32];
-      if (sl == NONE) { aborted = true; break; }
       if (rowLeft == 0) { rowNext = ctl[33]; rowLeft = 8; }
       const uint32_t row = rowNext++;
       rowLeft--;
-      const bool append = (k < K);
-      // the entering birth's k distances are the new matrix row (and what the host mirrors), :676-677 / :712-715
-      for (uint32_t r = tid; r < k; r += T) {
-        const float dr = ws.d[r * T + stop];
-        a.rows[size_t(row) * K + r] = dr;
-        if (r != sl) { ws.D[r * K + sl] = dr; ws.D[sl * K + r] = dr; }
-      }
+      // what the host mirrors: the birth's kOld cached distances
+      for (uint32_t r = tid; r < kOld; r += T) a.rows[size_t(row) * K + r] = ws.d[r * T + stop];
       if (uint32_t(tid) == stop)
         a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
-      if (append) k++;
       changed |= 1u << sl;
-      __syncthreads();
-      refreshMinBase();
-      // later births see the new representative: re-measure that slot only, re-sum in order
+      // later births see the new representative: re-measure that slot only, re-sum from there in order
       if (mine) {
         measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, sl, tid);
-        score = resum(a.cfg, ws, k, tid);
+        score = resum(a.cfg, ws, k, tid, sl);
       }
     }
     __syncthreads();
@@ -317,6 +390,7 @@ resolve_streams_kernel (StreamArgs a) {
     for (uint32_t i = tid; i < K * K; i += T) a.pool_dist[size_t(slot) * K * K + i] = ws.D[i];
     if (tid == 0) a.pool_fill_w[slot] = k;
   }
+  if (prof && tid == 0) { prof[4] = clock64();  prof[5] = profEvents;  prof[6] = profSteps; }
 }
 
 template <int WQ, int NW>

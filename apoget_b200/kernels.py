@@ -59,6 +59,19 @@ class Pool:
         check(lib().apt_classify_dense_dev(self._h, n, d_payload, d_compat, d_best, d_best_score, d_first,
                                            d_count, stream))
 
+    def classify_dense_shard_dev(self, n, d_payload, d_compat, species_offset, rank, world, peer_records, stream):
+        """Sharded sweep: writes this shard's records into every rank's gather buffer (peer_records: `world`
+        device addresses of world*n 16-byte records each; peer-mapped memory)."""
+        ptrs = np.ascontiguousarray(peer_records, dtype=np.uint64)
+        assert ptrs.size == world
+        check(lib().apt_classify_dense_shard_dev(self._h, n, d_payload, d_compat, species_offset, rank, world,
+                                                 ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), stream))
+
+
+def combine_shards_dev(n, world, d_records, d_best, d_best_score, d_first, d_count, stream, device=0):
+    """Pool-wide winners from the gathered [world][n] records (all arguments raw device pointers)."""
+    check(lib().apt_combine_shards_dev(device, n, world, d_records, d_best, d_best_score, d_first, d_count, stream))
+
 
 def env_contribution(K, edist, gdist, crit=1, device=0):
     e = np.ascontiguousarray(edist, dtype=np.float32).reshape(-1, K, K)

@@ -9,7 +9,17 @@ against it (classify_dense), and the per-birth partial winners are exchanged wit
     first accept  = lowest species index with score > 0
     accept count  = sum
 
-`torch.distributed` is plumbing only (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+Two exchanges exist on the GPUs:
+
+  * `PeerExchange` (the product path on one NVSwitch node): the sweep kernel itself stores every
+    birth's 16-byte record into ALL ranks' gather buffers through peer-mapped memory (torch symmetric
+    memory hands out the peer pointers; the stores travel over NVLink) -- compute and exchange are one
+    kernel, followed by a device-side barrier and our combine kernel.  No collective call, no pack or
+    reduce kernels of torch's.
+  * `combine` (NCCL all-gather + torch reduction): the baseline the above is measured against, and
+    what the gloo CPU tests exercise.
+
+`torch.distributed` is plumbing only (rendezvous, NCCL over NVLink, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -50,3 +60,40 @@ def combine(best, score, first, count, s_lo: int, group=None):
     out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(out, rec, group=group)          # rank-major concatenation
     return reduce_records(out.view(world, rec.shape[0], rec.shape[1]))
+
+
+class PeerExchange:
+    """Fused sweep + exchange of the species-sharded dense sweep over NVLink peer memory.
+
+    One symmetric buffer of [world, n_births, 4] int32 records per rank; rank r's sweep writes its
+    records into slice r of EVERY rank's buffer (apt_classify_dense_shard_dev), a device-side barrier
+    orders the peers' stores before the combine kernel (apt_combine_shards_dev) reads them, and a second
+    barrier keeps a fast peer's next sweep from overwriting records a slow rank is still reading."""
+
+    def __init__(self, n_births: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = n_births
+        self.records = symm_mem.empty((self.world, n_births, 4), dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.handle = symm_mem.rendezvous(self.records, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        dev = self.records.device
+        self.best = torch.empty(n_births, dtype=torch.int32, device=dev)
+        self.score = torch.empty(n_births, dtype=torch.float32, device=dev)
+        self.first = torch.empty(n_births, dtype=torch.int32, device=dev)
+        self.count = torch.empty(n_births, dtype=torch.int32, device=dev)
+
+    def sweep_and_combine(self, pool, d_births: torch.Tensor, d_compat: torch.Tensor, s_lo: int):
+        """pool: this rank's shard (apoget_b200.kernels.Pool); returns pool-wide (best, score, first, count)."""
+        import ctypes
+        from .kernels import combine_shards_dev
+        vp = ctypes.c_void_p
+        stream = vp(torch.cuda.current_stream().cuda_stream)
+        pool.classify_dense_shard_dev(self.n, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), s_lo, self.rank, self.world,
+                                      self.peer_ptrs, stream)
+        self.handle.barrier(channel=0)
+        combine_shards_dev(self.n, self.world, vp(self.records.data_ptr()), vp(self.best.data_ptr()), vp(self.score.data_ptr()),
+                           vp(self.first.data_ptr()), vp(self.count.data_ptr()), stream, device=self.records.device.index)
+        self.handle.barrier(channel=1)
+        return self.best, self.score, self.first, self.count

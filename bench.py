@@ -336,7 +336,7 @@ def main() -> None:
         import argparse as _ap
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_dense
-        d = bench_dense.run(_ap.Namespace(config="c4", births=131072, species=0, iters=2, check=8))
+        d = bench_dense.run(_ap.Namespace(config="c4", births=131072, species=0, iters=2, check=8, exchange="p2p"))
         line["dense_sweep"] = {
             "workload": "C4: 4096-bit Hamming genomes, every birth x 10 000 species x K=10 (131 072-birth slice of the 1 M batch)",
             "evals_per_s": d["evals_per_s"], "births_per_s": d["births_per_s"], "ms": d["ms"],

@@ -206,6 +206,22 @@ int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_pa
                             uint32_t *d_out_best_species, float *d_out_best_score,
                             uint32_t *d_out_first_accept, uint32_t *d_out_n_accept, void *stream);
 
+/* Species-sharded dense sweep (north_star (5)): this rank's pool holds the species
+ * [species_offset, species_offset + n_species) of `world` <= 8 shards with increasing ranges.  The sweep
+ * kernel writes one 16-byte record per birth {best species (pool-wide index), score bits, first
+ * accepting species, accept count} directly into EVERY rank's gather buffer: peer_records[q] (host
+ * array of `world` device addresses, peer-mapped over NVLink, e.g. torch symmetric memory) is rank q's
+ * buffer of world*n_births records, and this rank fills its [rank*n_births, (rank+1)*n_births) --
+ * compute and exchange are one kernel, no collective call.  After a cross-rank barrier,
+ * apt_combine_shards_dev reduces the `world` records of every birth to the pool-wide winners
+ * (strictly greatest score, lowest species on ties; lowest accepting species; total count). */
+int apt_classify_dense_shard_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_payload, const float *d_compat,
+                                  uint32_t species_offset, uint32_t rank, uint32_t world,
+                                  const uint64_t *peer_records, void *stream);
+int apt_combine_shards_dev (int device, uint32_t n_births, uint32_t world, const void *d_records,
+                            uint32_t *d_out_best_species, float *d_out_best_score,
+                            uint32_t *d_out_first_accept, uint32_t *d_out_n_accept, void *stream);
+
 /* a8, enveloppe criterion (enveloppecriteria.cpp:87-133, 275-289) for n candidates: edist
  * n*K*K f32 (full symmetric matrices), gdist n*K f32 -> better (u8), than (u32), value (f32).
  * Only crit 0 and 1 run on the device. */
@@ -228,6 +244,9 @@ int apt_mate_compat (const apt_params *params, uint32_t n_genomes, const uint32_
  * out[0] popc32/s (XOR + POPC per op, as in a Hamming distance), out[1] LOP3/s, out[2] DFMA/s,
  * out[3] FFMA/s, chip-wide. */
 int apt_microbench (int device, double out[4]);
+/* out[0] = float<->double conversions/s (F2F, chip-wide): the rate the reference's `float avg += double c`
+ * (phylogenetictree.hpp:465-472) is limited by when it is evaluated literally on the device. */
+int apt_microbench_cvt (int device, double out[1]);
 
 #ifdef __cplusplus
 }

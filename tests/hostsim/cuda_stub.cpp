@@ -45,6 +45,7 @@ const char* cudaGetErrorString (cudaError_t) { return "stub"; }
 }
 
 extern "C" int apt_microbench (int, double out[4]) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
+extern "C" int apt_microbench_cvt (int, double out[1]) { out[0] = 0; return 0; }
 
 namespace apt {
 
@@ -246,5 +247,10 @@ void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n
 void launch_mate_compat (int, uint32_t, const uint32_t*, const float4*, uint32_t, const uint32_t*, const uint32_t*, float*, double*, cudaStream_t) {}
 void launch_classify_dense (const PoolView&, const ScoreCfg&, const uint32_t*, const float4*, uint32_t, uint32_t*, float*,
                             uint32_t*, uint32_t*, cudaStream_t) {}
+bool dense_tiled_supports (uint32_t, uint32_t) { return false; }
+void launch_classify_dense_tiled (const PoolView&, const ScoreCfg&, const uint32_t*, const float4*, uint32_t, uint32_t*, float*,
+                                  uint32_t*, uint32_t*, cudaStream_t, const ShardSink*) {}
+void launch_publish_records (const uint32_t*, const float*, const uint32_t*, const uint32_t*, uint32_t, const ShardSink&, cudaStream_t) {}
+void launch_combine_shards (const uint4*, uint32_t, uint32_t, uint32_t*, float*, uint32_t*, uint32_t*, cudaStream_t) {}
 
 } // namespace apt

@@ -272,3 +272,47 @@ def test_tree_json_checkpoint_resume():
     assert np.array_equal(sids, ref["sids"])
     assert b.to_json() == golden_json(name)
     assert b.counters()["stream_births"] > 0
+
+
+@pytest.mark.parametrize("kind,words,sigma", [(synth.BITS, 8, 8.0), (synth.BITS, 128, 60.0), (synth.F32, 64, 0.4)])
+def test_sharded_dense_sweep_records_and_combine(kind, words, sigma):
+    """Species-sharded sweep: the sweep kernel writes per-birth records into the gather
+    buffer of every rank and combine_shards reduces them.  Here three shards run one after the other on one
+    GPU into one buffer (peer pointers = the same buffer): the result must equal the unsharded sweep, and
+    the torch reduction of the NCCL path must agree with the combine kernel."""
+    import ctypes
+    import torch
+    from apoget_b200 import shard
+    from apoget_b200.kernels import Pool, combine_shards_dev
+    rng = np.random.default_rng(5 + words)
+    S, B, K, world = 53, 197, 10, 3
+    reps, rc, fill = _random_pool(rng, kind, words, S, K, sigma)
+    rc[...] = rc[1, 0]                              # device-resident births: one compatibility class
+    fill[7] = 0
+    src = rng.integers(0, S, size=B)
+    births, bc = reps[src, 0].copy(), rc[src, 0].copy()
+    whole = Pool(kind, words, reps, rc, fill, K=K)
+    want = whole.classify_dense(births, bc)
+    vp = ctypes.c_void_p
+    d_births = torch.from_numpy(births.view(np.int32)).cuda()
+    d_compat = torch.from_numpy(bc).cuda()
+    rec = torch.full((world, B, 4), 0x55, dtype=torch.int32, device="cuda")
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    for r in range(world):
+        lo, hi = shard.shard_range(S, r, world)
+        part = Pool(kind, words, reps[lo:hi], rc[lo:hi], fill[lo:hi], K=K)
+        part.classify_dense_shard_dev(B, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), lo, r, world,
+                                      [rec.data_ptr()] * world, stream)
+        torch.cuda.synchronize()
+        part.close()
+    out = [torch.empty(B, dtype=dt, device="cuda") for dt in (torch.int32, torch.float32, torch.int32, torch.int32)]
+    combine_shards_dev(B, world, vp(rec.data_ptr()), *[vp(o.data_ptr()) for o in out], stream)
+    torch.cuda.synchronize()
+    got = [o.cpu().numpy() for o in out]
+    assert np.array_equal(got[0].view(np.uint32), want[0]), "best species"
+    assert np.array_equal(got[1], want[1]), "best score"
+    assert np.array_equal(got[2].view(np.uint32), want[2]), "first accepting species"
+    assert np.array_equal(got[3].view(np.uint32), want[3]), "accept count"
+    ref = shard.reduce_records(rec)
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b), "combine kernel and the torch reduction of the all-gather path disagree"

@@ -211,3 +211,14 @@ def test_json_load_refuses_other_enveloppe_size(hostsim):
     with pytest.raises(_lib.AptError) as e:
         tree.from_json(golden_json("k1_b64"))
     assert "enveloppe size" in str(e.value)
+
+
+def test_round_to_float_matches_the_hardware_conversion(tmp_path):
+    """apt::round_to_float (csrc/round24.h) is what the dense sweep uses instead of the two conversions of the
+    reference's `float avg += double c` (phylogenetictree.hpp:465-472): it must equal double(float(s)) bit for bit."""
+    import subprocess
+    exe = str(tmp_path / "round24_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "apoget_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "round24_check.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe, "3000000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

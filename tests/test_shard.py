@@ -81,3 +81,21 @@ def test_shard_ranges_partition():
         for w in (1, 2, 3, 8):
             r = [shard.shard_range(S, i, w) for i in range(w)]
             assert r[0][0] == 0 and r[-1][1] == S and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+@pytest.mark.gpu
+def test_peer_memory_exchange_matches_allgather_on_two_gpus():
+    """The fused sweep + exchange (records stored into the peers' buffers over NVLink by the sweep kernel) against
+    the NCCL all-gather path, on 2 GPUs; tools/bench_dense.py asserts that both give identical winners."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                        os.path.join(root, "tools", "bench_dense.py"), "--config", "c2", "--births", "8192",
+                        "--species", "301", "--exchange", "p2p", "--check", "6"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert '"oracle_mismatches": 0' in r.stdout and "peer-memory" in r.stdout

@@ -79,6 +79,8 @@ def run(args):
 
     peaks = np.zeros(4, dtype=np.float64)
     _lib.check(_lib.lib().apt_microbench(local, peaks.ctypes.data_as(_lib.f64p)))
+    cvt = np.zeros(1, dtype=np.float64)
+    _lib.check(_lib.lib().apt_microbench_cvt(local, cvt.ctypes.data_as(_lib.f64p)))
 
     d_births = torch.from_numpy(births.view(np.int32)).cuda()
     d_compat = torch.from_numpy(bc).cuda()
@@ -96,6 +98,20 @@ def run(args):
 
     def combine():
         return shard.combine(d_best, d_score, d_first, d_count, s_lo)
+
+    p2p = None
+    if world > 1 and args.exchange == "p2p":
+        # fused sweep + exchange over NVLink peer memory; checked against the NCCL all-gather path first
+        p2p = shard.PeerExchange(B)
+        sweep()
+        ref = [x.clone() for x in combine()]
+        got = p2p.sweep_and_combine(pool, d_births, d_compat, s_lo)
+        torch.cuda.synchronize()
+        for a, b, name in zip(got, ref, ("best", "score", "first", "count")):
+            assert torch.equal(a, b), f"peer-memory exchange differs from the all-gather path: {name}"
+        _sweep, _combine = sweep, combine
+        sweep = lambda: None                                       # noqa: E731
+        combine = lambda: p2p.sweep_and_combine(pool, d_births, d_compat, s_lo)   # noqa: E731
 
     sweep(); combine()                                    # warm-up
     torch.cuda.synchronize()
@@ -137,12 +153,15 @@ def run(args):
     out = None
     if rank == 0:
         out = ({
-            "bench": "dense sweep", "config": args.config, "n_gpus": world, "births": B, "species": S, "K": K,
+            "bench": "dense sweep", "config": args.config, "n_gpus": world,
+            "exchange": ("peer-memory stores from the sweep kernel + device barrier + combine kernel" if p2p is not None
+                         else ("NCCL all-gather + torch reduction" if world > 1 else "none")), "births": B, "species": S, "K": K,
             "genome_words": words, "kind": "bits/hamming" if kind == 0 else "f32/l2", "ms": ms,
             "births_per_s": B / (ms * 1e-3), "evals_per_s": evals / (ms * 1e-3),
             "pipe_ops_per_s": ops / (ms * 1e-3), "pipe": "popc32 (+xor)" if kind == 0 else "fp32 flop (sub, fma)",
             "pipe_peak_measured": peak, "frac_of_pipe_peak": ops / (ms * 1e-3) / (peak * world),
-            "microbench": {"popc32_per_s": peaks[0], "lop3_per_s": peaks[1], "dfma_per_s": peaks[2], "ffma_per_s": peaks[3]},
+            "microbench": {"popc32_per_s": peaks[0], "lop3_per_s": peaks[1], "dfma_per_s": peaks[2], "ffma_per_s": peaks[3],
+                           "f2f_cvt_per_s": cvt[0]},
             "accepting_births_frac": float((count > 0).mean()), "oracle_checked_births": int(min(args.check, B)),
             "oracle_mismatches": int(bad)})
     if own_group:
@@ -157,6 +176,8 @@ def main():
     ap.add_argument("--species", type=int, default=0)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--check", type=int, default=24, help="births verified against the CPU oracle")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: records stored into the peers' buffers by the sweep kernel (p2p) or NCCL all-gather")
     out = run(ap.parse_args())
     if out is not None:
         print(json.dumps(out))
