@@ -1322,7 +1322,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       a.ft_list = dFtList_.p;  a.ft_counter = dFtCounter_.p;
     }
     const char *profPath = getenv("APT_STREAM_PROF");
-    if (profPath) { dProf_.reserve(size_t(G) * 8); a.prof = dProf_.p; }
+    if (profPath) { dProf_.reserve(size_t(G) * 16); a.prof = dProf_.p; }
     cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
     launch_resolve_streams(a, stream_);
     cudaCheck(cudaEventRecord(evS1_, stream_), "event record");
@@ -1359,13 +1359,13 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (G) {
       cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
       if (const char *profPath = getenv("APT_STREAM_PROF")) {
-        // development aid: one text line per stream {launch, stream, births, 8 timeline words}, appended
-        std::vector<unsigned long long> hp (size_t(G) * 8);
+        // development aid: one text line per stream {launch, stream, births, kernel ms, 10 timeline words}, appended
+        std::vector<unsigned long long> hp (size_t(G) * 16);
         cudaCheck(cudaMemcpy(hp.data(), dProf_.p, hp.size() * 8, cudaMemcpyDeviceToHost), "stream profile");
         if (FILE *f = fopen(profPath, "a")) {
           for (uint32_t g = 0; g < G; g++) {
             fprintf(f, "%llu %u %u %.3f", (unsigned long long) counters[12], g, hGrpOff_.p[g + 1] - hGrpOff_.p[g], double(ms));
-            for (int q = 0; q < 8; q++) fprintf(f, " %llu", hp[size_t(g) * 8 + q]);
+            for (int q = 0; q < 14; q++) fprintf(f, " %llu", hp[size_t(g) * 16 + q]);
             fputc('\n', f);
           }
           fclose(f);

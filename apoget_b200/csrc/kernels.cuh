@@ -112,9 +112,9 @@ struct StreamArgs {
   float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
   uint32_t *ft_list;          ///< births rejected at top level, appended as (birth, stream) pairs ...
   uint32_t *ft_counter;       ///< ... counted here (zero-initialised)
-  uint32_t *row_counter;      ///< zero-initialised; rows are claimed in blocks of 8 per stream
+  uint32_t *row_counter;      ///< zero-initialised; a stream claims the rows of a step (its enveloppe entries) with one add
   int lut_in_smem = 0;        ///< set by the launcher
-  unsigned long long *prof = nullptr;   ///< optional [n_groups][8] per-stream timeline (APT_STREAM_PROF), see stream.cu
+  unsigned long long *prof = nullptr;   ///< optional [n_groups][12] per-stream timeline (APT_STREAM_PROF), see stream.cu
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream);

@@ -49,13 +49,13 @@ __device__ __forceinline__ double compat_generic (float4 m, double d) {     // c
   return exp(-(t * t) / (2. * s * s));
 }
 
-template <bool LUT>
-__device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, const double *lut, float4 bm, float4 rm, double d) {
+template <bool LUT, class WS>
+__device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, const WS &ws, float4 bm, float4 rm, double d) {
   double a, b;
   if (LUT) {
     const uint32_t di = uint32_t(d);
-    a = lut[size_t(__float_as_uint(bm.w)) * cfg.lut_stride + di];
-    b = lut[size_t(__float_as_uint(rm.w)) * cfg.lut_stride + di];
+    a = ws.lut(size_t(__float_as_uint(bm.w)) * cfg.lut_stride + di);
+    b = ws.lut(size_t(__float_as_uint(rm.w)) * cfg.lut_stride + di);
   } else {
     a = compat_generic(bm, d);
     b = compat_generic(rm, d);
@@ -63,99 +63,157 @@ __device__ __forceinline__ double pair_compat (const ScoreCfg &cfg, const double
   return b < a ? b : a;
 }
 
-/// The stream's state in dynamic shared memory (T = threads of the CTA = births per step)
+/// Dynamic shared memory of the CTA.  Every access goes through this symbol (plus a byte offset), so the
+/// compiler knows the address space: generic pointers kept in a struct made it re-derive the shared
+/// window from SR_CgaCtaId in front of every access (57 S2R in the event loop, ~1.3 us per event).
+extern __shared__ __align__(16) unsigned char apt_smem[];
+
+/// Shared-window address of apt_smem, laundered through a shuffle so that it is a plain register value:
+/// otherwise ptxas re-derives it (S2R SR_CgaCtaId + LEA) in front of accesses instead of keeping it live.
+__device__ __forceinline__ uint32_t smem_window (void) {
+  return __shfl_sync(0xffffffffu, uint32_t(__cvta_generic_to_shared(apt_smem)), 0);
+}
+/// Unconditional shared-memory accesses by window address (a load inside a C++ conditional is turned into a branch)
+__device__ __forceinline__ float lds_f32 (uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+/// The stream's state in shared memory (T = threads of the CTA = births per step): byte offsets
 struct WarpState {
-  uint4 *reps;        // [K][WQ]
-  float4 *rmeta;      // [K]
-  float *D;           // [K][K]
-  float *minBase;     // [K]
-  float *d;           // [K][T]   distances of thread t to representative r at d[r*T + t]
-  double *c;          // [K][T]   compatibilities
-  float *pre;         // [K+1][T] running average BEFORE representative r is added (pre[k] = the total)
-  const double *lut;  // compatibility table: shared-memory copy when it fits, else global
+  uint32_t oReps, oRmeta, oD, oMinBase, od, oc, oPre, oEv, oCtl, oLut;
+  const double *lutG;   // compatibility table in global memory (used when it does not fit in shared memory)
+  bool lutS;            // table staged in shared memory at oLut
   uint32_t T;
+  uint32_t sb;          // shared-window address of apt_smem (smem_window)
+  __device__ __forceinline__ uint4& reps (uint32_t i) const { return reinterpret_cast<uint4*>(apt_smem + oReps)[i]; }        // [K][WQ]
+  __device__ __forceinline__ float4& rmeta (uint32_t i) const { return reinterpret_cast<float4*>(apt_smem + oRmeta)[i]; }    // [K]
+  __device__ __forceinline__ float& D (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + oD)[i]; }              // [K][K]
+  __device__ __forceinline__ float& minBase (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + oMinBase)[i]; }  // [K]
+  __device__ __forceinline__ float& d (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + od)[i]; }              // [K][T] distance of thread t to representative r at r*T + t
+  __device__ __forceinline__ double& c (uint32_t i) const { return reinterpret_cast<double*>(apt_smem + oc)[i]; }            // [K][T] compatibilities (only when K is not a compile-time constant)
+  __device__ __forceinline__ float& pre (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + oPre)[i]; }          // [K+1][T] running average BEFORE representative r is added (pre[k] = the total)
+  __device__ __forceinline__ uint32_t& ev (uint32_t i) const { return reinterpret_cast<uint32_t*>(apt_smem + oEv)[i]; }      // [T] per event of a step: thread << 8 | distances
+  __device__ __forceinline__ uint32_t& ctl (uint32_t i) const { return reinterpret_cast<uint32_t*>(apt_smem + oCtl)[i]; }    // [64] exchange words
+  __device__ __forceinline__ double lut (size_t i) const {
+    return lutS ? reinterpret_cast<const double*>(apt_smem + oLut)[i] : __ldg(lutG + i);
+  }
 };
 
-/// distance + compatibility of this lane's birth to representative r, stored in the lane's column
+/// A thread's distances and compatibilities to the k representatives.  With the enveloppe size known
+/// at compile time (KT > 0) they live in registers and every loop over them is unrolled -- the
+/// per-event critical path (criterion, re-sum) then has no shared-memory round trips in it; the
+/// distances are mirrored to shared memory because the OTHER threads need the entering birth's row.
+template <int KT>
+struct Lane {
+  float d[KT ? KT : 1];
+  double c[KT ? KT : 1];
+};
+
+#define APT_FOR_K(r, k) _Pragma("unroll") for (uint32_t r = 0; r < (KT ? uint32_t(KT) : (k)); r++) if (KT == 0 || r < (k))
+
+/// distance + compatibility of this lane's birth to representative r
 template <int WQ, int KIND, bool LUT>
-__device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
-                                         const WarpState &ws, uint32_t r, int lane) {
+__device__ __forceinline__ void measure_one (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
+                                             const WarpState &ws, uint32_t r, float &df, double &c) {
   if (KIND == 0 && LUT) {
     // Hamming distance stays an integer: it indexes the table directly (no double round trip)
     uint32_t acc = 0;
 #pragma unroll
-    for (int v = 0; v < WQ; v++) acc += popc4(bw[v], ws.reps[r * WQ + v]);
-    const float4 rm = ws.rmeta[r];
-    const double ca = ws.lut[size_t(__float_as_uint(bm.w)) * cfg.lut_stride + acc];
-    const double cb = ws.lut[size_t(__float_as_uint(rm.w)) * cfg.lut_stride + acc];
-    ws.d[r * ws.T + lane] = float(acc);
-    ws.c[r * ws.T + lane] = cb < ca ? cb : ca;
+    for (int v = 0; v < WQ; v++) acc += popc4(bw[v], ws.reps(r * WQ + v));
+    const float4 rm = ws.rmeta(r);
+    const double ca = ws.lut(size_t(__float_as_uint(bm.w)) * cfg.lut_stride + acc);
+    const double cb = ws.lut(size_t(__float_as_uint(rm.w)) * cfg.lut_stride + acc);
+    df = float(acc);
+    c = cb < ca ? cb : ca;
     return;
   }
   double d;
   if (KIND == 0) {
     uint32_t acc = 0;
 #pragma unroll
-    for (int v = 0; v < WQ; v++) acc += popc4(bw[v], ws.reps[r * WQ + v]);
+    for (int v = 0; v < WQ; v++) acc += popc4(bw[v], ws.reps(r * WQ + v));
     d = double(acc);
   } else {
     double acc = 0.;
 #pragma unroll
-    for (int v = 0; v < WQ; v++) acc += sqdiff4(bw[v], ws.reps[r * WQ + v]);
+    for (int v = 0; v < WQ; v++) acc += sqdiff4(bw[v], ws.reps(r * WQ + v));
     d = sqrt(acc);
   }
-  ws.d[r * ws.T + lane] = float(d);
-  ws.c[r * ws.T + lane] = pair_compat<LUT>(cfg, ws.lut, bm, ws.rmeta[r], d);
+  df = float(d);
+  c = pair_compat<LUT>(cfg, ws, bm, ws.rmeta(r), d);
+}
+
+/// (re-)measures representative r and stores the result in the lane's column
+template <int WQ, int KIND, bool LUT, int KT>
+__device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
+                                         const WarpState &ws, Lane<KT> &ln, uint32_t r, int lane) {
+  float df;  double c;
+  measure_one<WQ, KIND, LUT>(cfg, bw, bm, ws, r, df, c);
+  ws.d(r * ws.T + lane) = df;
+  if (KT > 0) {
+#pragma unroll
+    for (int q = 0; q < (KT ? KT : 1); q++) if (uint32_t(q) == r) { ln.d[q] = df; ln.c[q] = c; }
+  } else ws.c(r * ws.T + lane) = c;
 }
 
 /// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities.  The float
 /// accumulation is order sensitive, so it stays sequential -- but representatives before `from` are
 /// unchanged since the last call and their partial sum is kept (pre[from]).
-__device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws, uint32_t k, int lane, uint32_t from) {
+template <int KT>
+__device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws, const Lane<KT> &ln, uint32_t k,
+                                        int lane, uint32_t from) {
   if (cfg.full_continuous) {
-    float avg = from ? ws.pre[from * ws.T + lane] : 0.f;
-    for (uint32_t r = from; r < k; r++) {
-      ws.pre[r * ws.T + lane] = avg;
-      avg = float(__dadd_rn(double(avg), ws.c[r * ws.T + lane]));
+    float avg = from ? ws.pre(from * ws.T + lane) : 0.f;
+    APT_FOR_K(r, k) {
+      if (r >= from) {
+        ws.pre(r * ws.T + lane) = avg;
+        avg = float(__dadd_rn(double(avg), KT ? ln.c[KT ? r : 0] : ws.c(r * ws.T + lane)));
+      }
     }
-    ws.pre[k * ws.T + lane] = avg;
+    ws.pre(k * ws.T + lane) = avg;
     return float(__dsub_rn(double(__fdiv_rn(avg, float(k))), cfg.avg_thr));
   }
   uint32_t matable = 0;
-  for (uint32_t r = 0; r < k; r++) matable += (ws.c[r * ws.T + lane] >= cfg.compat_thr);
+  APT_FOR_K(r, k) matable += ((KT ? ln.c[KT ? r : 0] : ws.c(r * ws.T + lane)) >= cfg.compat_thr);
   return float(__dsub_rn(double(matable), __dmul_rn(cfg.sim_thr, double(k))));
 }
 
 /// maxMinDist (enveloppecriteria.cpp:87-133) for this lane's distances against a FULL enveloppe.
 /// :117 widens a float difference to double and :125 compares it with the float maximum: the
 /// comparison of the two floats is the same predicate, so it is taken in float.
-__device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, uint32_t K, int lane, uint32_t &than) {
+template <int KT>
+__device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, const Lane<KT> &ln, uint32_t K, int lane,
+                                                      uint32_t &than) {
   float m1 = FMAX, m2 = FMAX;
   uint32_t i1 = 0xFFFFFFFFu;
-  for (uint32_t r = 0; r < K; r++) {
-    const float x = ws.d[r * ws.T + lane];
+  APT_FOR_K(r, K) {
+    const float x = KT ? ln.d[KT ? r : 0] : ws.d(r * ws.T + lane);
     if (x < m1) { m2 = m1; m1 = x; i1 = r; }
     else if (x < m2) m2 = x;
   }
   float value = -CUDART_INF_F;
   than = 0xFFFFFFFFu;
-  for (uint32_t i = 0; i < K; i++) {
+  APT_FOR_K(i, K) {
     const float minNew = (i == i1) ? m2 : m1;                    // min over j != i of gdist[j]
-    const float c = __fadd_rn(-ws.minBase[i], minNew);           // :117
+    const float c = __fadd_rn(-ws.minBase(i), minNew);           // :117
     if (value < c) { value = c; than = i; }                      // :125-128, first index wins ties
   }
   return value > 0.f;                                            // :131
 }
 
 /// maxAverage (enveloppecriteria.cpp:40-84)
-__device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, uint32_t K, int lane, uint32_t &than) {
+template <int KT>
+__device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, const Lane<KT> &ln, uint32_t K, int lane,
+                                                      uint32_t &than) {
   float value = -CUDART_INF_F;
   than = 0xFFFFFFFFu;
   for (uint32_t i = 0; i < K; i++) {
     double c = 0.;
-    for (uint32_t j = 0; j < K; j++) {
-      if (i == j) continue;
-      c = __dadd_rn(c, double(__fadd_rn(-ws.D[i * K + j], ws.d[j * ws.T + lane])));   // :62
+    APT_FOR_K(j, K) {
+      if (j != i)
+        c = __dadd_rn(c, double(__fadd_rn(-ws.D(i * K + j), KT ? ln.d[KT ? j : 0] : ws.d(j * ws.T + lane))));   // :62
     }
     if (double(value) < c) { value = float(c); than = i; }
   }
@@ -163,9 +221,9 @@ __device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, uint3
 }
 
 /// Shared-memory bytes of one stream (without the table)
-__host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T) {
-  return size_t(K) * T * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
-       + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + 64 * 4;
+__host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T, bool ktConst = false) {
+  return (ktConst ? 0 : size_t(K) * T * 8) + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
+       + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + size_t(T) * 4 + 64 * 4;
 }
 
 __device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
@@ -173,36 +231,42 @@ __device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile("pref
 // Event word exchanged between the warps of a stream: earliest thread first (high bits), then what it does
 constexpr uint32_t EV_TID_SHIFT = 8, EV_UNCERTAIN = 0x80u, EV_SLOT_MASK = 0x3Fu;
 
-template <int WQ, int KIND, bool LUT, int NW>
-__global__ void __launch_bounds__(NW * 32)
+// 7 CTAs of 4 warps per SM keep 1 000 streams in one wave on 148 SMs (register-resident variant: <= 72 registers)
+template <int WQ, int KIND, bool LUT, int NW, int KT>
+__global__ void __launch_bounds__(NW * 32, (NW == 4 && KT > 0 && WQ <= 2) ? 7 : 1)
 resolve_streams_kernel (StreamArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
   constexpr uint32_t T = NW * 32;
   constexpr uint32_t NONE = 0xFFFFFFFFu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t g = blockIdx.x;
-  const uint32_t K = a.pool.K;
-  unsigned char *base = smem;
+  const uint32_t K = KT ? uint32_t(KT) : a.pool.K;
+  uint32_t base = 0;
   WarpState ws;
   ws.T = T;
-  ws.c = reinterpret_cast<double*>(base);            base += size_t(K) * T * 8;
-  ws.reps = reinterpret_cast<uint4*>(base);          base += size_t(K) * WQ * 16;
-  ws.rmeta = reinterpret_cast<float4*>(base);        base += size_t(K) * 16;
-  ws.D = reinterpret_cast<float*>(base);             base += size_t(K) * K * 4;
-  ws.minBase = reinterpret_cast<float*>(base);       base += size_t(K) * 4;
-  ws.d = reinterpret_cast<float*>(base);             base += size_t(K) * T * 4;
-  ws.pre = reinterpret_cast<float*>(base);           base += size_t(K + 1) * T * 4;
-  uint32_t *ctl = reinterpret_cast<uint32_t*>(base); base += 64 * 4;
-  // ctl[0..NW): event word per warp; ctl[33]: first row of a claimed block; ctl[36..39): counters
-  ws.lut = a.cfg.lut;
+  ws.oc = base;        if (KT == 0) base += K * T * 8;
+  ws.oReps = base;     base += K * WQ * 16;
+  ws.oRmeta = base;    base += K * 16;
+  ws.oD = base;        base += K * K * 4;
+  ws.oMinBase = base;  base += K * 4;
+  ws.od = base;        base += K * T * 4;
+  ws.oPre = base;      base += (K + 1) * T * 4;
+  ws.oEv = base;       base += T * 4;
+  ws.oCtl = base;      base += 64 * 4;
+  // ws.ctl(0..NW): event word per warp; ws.ctl(33): first output row of the step; ws.ctl(36..39): counters
+  ws.oLut = (base + 15u) & ~15u;
+  ws.lutG = a.cfg.lut;
+  ws.lutS = LUT && a.lut_in_smem;
+  ws.sb = smem_window();
 
   // ---- everything the stream needs first is requested before anything is waited for: the
   //      stream's extent, then (one round trip later) the enveloppe, the first births' indices and
   //      the table, then (another one) those births' genomes ----
   // optional timeline of this stream (development aid, APT_STREAM_PROF): {globaltimer ns at start, SM clock at
-  // start, after the enveloppe is loaded, after the first births are scored, at the end, events, steps, SM id}
-  unsigned long long *prof = a.prof ? a.prof + size_t(g) * 8 : nullptr;
+  // start, after the enveloppe is loaded, after the first births are scored, at the end, events, steps, SM id,
+  // cycles between barriers on the score/decide side, on the enveloppe-update side}
+  unsigned long long *prof = a.prof ? a.prof + size_t(g) * 16 : nullptr;
   uint32_t profEvents = 0, profSteps = 0;
+  long long profA = 0, profB = 0, profT = 0;     // cycles between barriers: score/decide side, enveloppe update side
   if (prof && tid == 0) {
     unsigned long long gt;  uint32_t smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -215,16 +279,21 @@ resolve_streams_kernel (StreamArgs a) {
   const uint4 *birthRows = reinterpret_cast<const uint4*>(a.b_payload);
   uint32_t ordNext = (g0 + tid < g1) ? __ldg(a.order + g0 + tid) : 0u;
   uint32_t k = min(__ldg(a.pool.fill + slot), K);
-  for (uint32_t i = tid; i < K * WQ; i += T) ws.reps[i] = poolRows[i];          // rows past the fill are never read
-  for (uint32_t i = tid; i < K; i += T) ws.rmeta[i] = a.pool.cmeta[size_t(slot) * K + i];
-  for (uint32_t i = tid; i < K * K; i += T) ws.D[i] = a.pool_dist[size_t(slot) * K * K + i];
-  if (LUT && a.lut_in_smem) {
-    double *lut_s = reinterpret_cast<double*>(smem + ((stream_smem(K, WQ, T) + 15) & ~size_t(15)));
+  for (uint32_t i = tid; i < K * WQ; i += T) ws.reps(i) = poolRows[i];          // rows past the fill are never read
+  for (uint32_t i = tid; i < K; i += T) ws.rmeta(i) = a.pool.cmeta[size_t(slot) * K + i];
+  // the matrix is kept with FLT_MAX on the diagonal and in unused rows / columns: a row's minimum over its
+  // other representatives (minBase, enveloppecriteria.cpp:105-113) is then a plain minimum over K entries
+  for (uint32_t i = tid; i < K * K; i += T) {
+    const float v = a.pool_dist[size_t(slot) * K * K + i];
+    const uint32_t row = i / K, col = i - row * K;
+    ws.D(i) = (row < k && col < k && row != col) ? v : FMAX;
+  }
+  if (ws.lutS) {
+    double *lut_s = reinterpret_cast<double*>(apt_smem + ws.oLut);
     const uint32_t nd = a.cfg.lut_classes * a.cfg.lut_stride;
     for (uint32_t i = tid; i < nd; i += T) lut_s[i] = __ldg(a.cfg.lut + i);
-    ws.lut = lut_s;
   }
-  if (tid < 4) ctl[36 + tid] = 0;
+  if (tid < 4) ws.ctl(36 + tid) = 0;
   uint4 bw[WQ];
   float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
   if (g0 + tid < g1) {
@@ -239,15 +308,16 @@ resolve_streams_kernel (StreamArgs a) {
   __syncthreads();
   for (uint32_t r = tid; r < k; r += T) {
     float m = FMAX;
-    for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, ws.D[r * K + j]);
-    ws.minBase[r] = m;
+#pragma unroll (KT ? KT : 1)
+    for (uint32_t j = 0; j < K; j++) m = fminf(m, ws.D(r * K + j));
+    ws.minBase(r) = m;
   }
   __syncthreads();
   if (prof && tid == 0) prof[2] = clock64();
+  Lane<KT> ln;
 
   uint32_t changed = 0;         // slots to write back (uniform)
   bool aborted = false;
-  uint32_t rowNext = 0, rowLeft = 0;   // output rows are claimed 8 at a time (one atomic per 8 entries); uniform
   uint32_t nAcc0 = 0, nAcc1 = 0, nAcc2 = 0;     // per thread: accepted, enveloppe unchanged, by contribution class
 
   for (uint32_t cb = g0; cb < g1 && !aborted; cb += T) {
@@ -276,12 +346,23 @@ resolve_streams_kernel (StreamArgs a) {
     }
     float score = 0.f;
     if (active) {
-      for (uint32_t r = 0; r < k; r++) measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, tid);
-      score = resum(a.cfg, ws, k, tid, 0);
+      APT_FOR_K(r, k) {
+        float df;  double c;
+        measure_one<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, df, c);
+        ws.d(r * T + tid) = df;
+        if (KT > 0) { ln.d[KT ? r : 0] = df; ln.c[KT ? r : 0] = c; } else ws.c(r * T + tid) = c;
+      }
+      score = resum<KT>(a.cfg, ws, ln, k, tid, 0);
     }
     if (prof && tid == 0 && cb == g0) prof[3] = clock64();
     profSteps++;
     bool mine = active;           // not final yet
+    if (prof) profT = clock64();
+    // Nothing leaves the chip inside the event loop: scattered global stores ahead of the shared-memory
+    // traffic of the next event cost ~1.3 us per event (measured with APT_STREAM_PROF; the LDS queue up
+    // behind them).  Each thread keeps its verdict in registers and the step's results are written once.
+    uint32_t myAct = ACT_UNPROCESSED, myEv = 0, nEv = 0;
+    bool rejected = false;
 
     for (;;) {
       const bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
@@ -291,7 +372,7 @@ resolve_streams_kernel (StreamArgs a) {
       if (accept && !uncertain) {
         if (k < K) { modifies = true; than = k; }                       // :668-677
         else if (K > 1)
-          modifies = a.crit == 1 ? criterion_maxMinDist(ws, K, tid, than) : criterion_maxAverage(ws, K, tid, than);
+          modifies = a.crit == 1 ? criterion_maxMinDist<KT>(ws, ln, K, tid, than) : criterion_maxAverage<KT>(ws, ln, K, tid, than);
       }
       // earliest thread of the CTA whose decision is an event (changes the enveloppe / needs the host),
       // published together with what it does: one barrier tells every thread who and where
@@ -300,33 +381,22 @@ resolve_streams_kernel (StreamArgs a) {
         const int first = __ffs(em) - 1;
         const uint32_t word = (uint32_t(tid) << EV_TID_SHIFT) | (uncertain ? EV_UNCERTAIN : (than & EV_SLOT_MASK));
         const uint32_t w0 = __shfl_sync(0xffffffffu, word, first);
-        if (lane == 0) ctl[warp] = w0;
-      } else if (lane == 0) ctl[warp] = NONE;
+        if (lane == 0) ws.ctl(warp) = w0;
+      } else if (lane == 0) ws.ctl(warp) = NONE;
       __syncthreads();
+      if (prof) { const long long t = clock64(); profA += t - profT; profT = t; }
       uint32_t event = NONE;
 #pragma unroll
-      for (int w = 0; w < NW; w++) event = min(event, ctl[w]);
+      for (int w = 0; w < NW; w++) event = min(event, ws.ctl(w));
       const uint32_t stop = event == NONE ? NONE : event >> EV_TID_SHIFT;
-      const bool fin = mine && uint32_t(tid) < stop;
-      if (fin) {
-        a.act[b] = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
-        if (accept) { a.out_sid[b] = sid; nAcc0 += (ccls == 0); nAcc1 += (ccls == 1); nAcc2 += (ccls == 2); }
+      if (mine && uint32_t(tid) < stop) {           // final: every earlier decision stands
+        myAct = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
+        rejected = !accept;
         mine = false;
-      }
-      // births rejected at top level queue up for the sub-species kernel (one atomic per warp step)
-      const uint32_t ftm = __ballot_sync(0xffffffffu, fin && !accept);
-      if (ftm && a.ft_list) {
-        uint32_t fbase = 0;
-        if (lane == 0) fbase = atomicAdd(a.ft_counter, uint32_t(__popc(ftm)));
-        fbase = __shfl_sync(0xffffffffu, fbase, 0);
-        if (fin && !accept) {
-          const uint32_t at = fbase + __popc(ftm & ((1u << lane) - 1u));
-          a.ft_list[2 * at] = b;  a.ft_list[2 * at + 1] = g;
-        }
       }
       if (event == NONE) break;
       if (event & EV_UNCERTAIN) {                     // the host takes the stream over from here
-        if (uint32_t(tid) == stop) a.act[b] = ACT_UNCERTAIN;
+        if (uint32_t(tid) == stop) myAct = ACT_UNCERTAIN;
         aborted = true;
         break;
       }
@@ -337,66 +407,111 @@ resolve_streams_kernel (StreamArgs a) {
       if (append) k++;
       if (uint32_t(tid) == stop) {
 #pragma unroll
-        for (int v = 0; v < WQ; v++) ws.reps[sl * WQ + v] = bw[v];
-        ws.rmeta[sl] = bm;
-        a.out_sid[b] = sid;
-        a.out_slot[b] = int32_t(sl);
+        for (int v = 0; v < WQ; v++) ws.reps(sl * WQ + v) = bw[v];
+        ws.rmeta(sl) = bm;
+        myAct = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT);
+        myEv = nEv;
+        ws.ev(nEv) = (stop << 8) | kOld;             // whose distances are the row, and how many
         mine = false;
       }
-      // the entering birth's distances are the new row / column sl of the matrix (:676-677 / :712-715);
-      // thread r owns row r, so its new minimum needs no other thread's writes (row sl = the birth's own distances)
-      for (uint32_t r = tid; r < k; r += T) {
-        float m = FMAX;
-        if (r != sl) {
-          const float dr = ws.d[r * T + stop];
-          ws.D[r * K + sl] = dr;  ws.D[sl * K + r] = dr;
-          for (uint32_t j = 0; j < k; j++) if (j != r) m = fminf(m, j == sl ? dr : ws.D[r * K + j]);
-        } else {
-          for (uint32_t j = 0; j < kOld; j++) if (j != sl) m = fminf(m, ws.d[j * T + stop]);
+      nEv++;
+      // the entering birth's distances are the new row / column sl of the matrix (:676-677 / :712-715).
+      // Lane r of warp 0 owns row r (only its column sl changes), one lane of warp 1 owns row sl (the birth's
+      // own distances): no thread needs another's writes for its new minimum.  Straight-line code, loads
+      // unconditional -- this sits on the critical path of every event.
+      {
+        const uint32_t aEnt = ws.sb + ws.od + stop * 4;
+        if (uint32_t(tid) < k && uint32_t(tid) != sl) {
+          const uint32_t r = tid, aRow = ws.sb + ws.oD + r * K * 4;
+          const float dr = lds_f32(aEnt + r * T * 4);
+          float m = FMAX;
+#pragma unroll (KT ? KT : 1)
+          for (uint32_t j = 0; j < K; j++) {
+            const float w = lds_f32(aRow + j * 4);
+            m = fminf(m, j == sl ? dr : w);
+          }
+          ws.D(r * K + sl) = dr;
+          ws.minBase(r) = m;
+        } else if (tid == 32) {
+          float m = FMAX;
+#pragma unroll (KT ? KT : 1)
+          for (uint32_t j = 0; j < K; j++) {
+            const float e = lds_f32(aEnt + j * T * 4);          // columns past kOld hold stale values: masked
+            const float v = (j == sl || j >= kOld) ? FMAX : e;
+            ws.D(sl * K + j) = v;
+            m = fminf(m, v);
+          }
+          ws.minBase(sl) = m;
         }
-        ws.minBase[r] = m;
       }
-      if (rowLeft == 0 && tid == 0) ctl[33] = atomicAdd(a.row_counter, 8u);
       __syncthreads();
-      if (rowLeft == 0) { rowNext = ctl[33]; rowLeft = 8; }
-      const uint32_t row = rowNext++;
-      rowLeft--;
-      // what the host mirrors: the birth's kOld cached distances
-      for (uint32_t r = tid; r < kOld; r += T) a.rows[size_t(row) * K + r] = ws.d[r * T + stop];
-      if (uint32_t(tid) == stop)
-        a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
+      if (prof) { const long long t = clock64(); profB += t - profT; profT = t; }
       changed |= 1u << sl;
       // later births see the new representative: re-measure that slot only, re-sum from there in order
       if (mine) {
-        measure<WQ, KIND, LUT>(a.cfg, bw, bm, ws, sl, tid);
-        score = resum(a.cfg, ws, k, tid, sl);
+        measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, sl, tid);
+        score = resum<KT>(a.cfg, ws, ln, k, tid, sl);
       }
+    }
+
+    // ---- the step's results leave the chip: one row claim for all its enveloppe entries, one result
+    //      word per birth, the cached distance row of every entering birth (what the host mirrors),
+    //      and the births rejected at top level queue up for the sub-species kernel ----
+    if (nEv && tid == 0) ws.ctl(33) = atomicAdd(a.row_counter, nEv);
+    const uint32_t ftm = __ballot_sync(0xffffffffu, rejected);
+    if (ftm && a.ft_list) {
+      uint32_t fbase = 0;
+      if (lane == 0) fbase = atomicAdd(a.ft_counter, uint32_t(__popc(ftm)));
+      fbase = __shfl_sync(0xffffffffu, fbase, 0);
+      if (rejected) {
+        const uint32_t at = fbase + __popc(ftm & ((1u << lane) - 1u));
+        a.ft_list[2 * at] = b;  a.ft_list[2 * at + 1] = g;
+      }
+    }
+    __syncthreads();
+    const uint32_t rowBase = nEv ? ws.ctl(33) : 0u;
+    if (active) {
+      const uint32_t code = myAct & ACT_CODE_MASK;
+      if (code == ACT_ENTERED) {
+        myAct |= (rowBase + myEv) << ACT_ROW_SHIFT;
+        a.out_slot[b] = int32_t((myAct >> ACT_SLOT_SHIFT) & 31u);
+      }
+      if (code == ACT_ENTERED || code == ACT_ACCEPTED) a.out_sid[b] = sid;
+      if (code == ACT_ACCEPTED) { nAcc0 += (ccls == 0); nAcc1 += (ccls == 1); nAcc2 += (ccls == 2); }
+      a.act[b] = myAct;
+    }
+    for (uint32_t idx = tid; idx < nEv * K; idx += T) {
+      const uint32_t e = idx / K, r = idx - e * K, info = ws.ev(e);
+      if (r < (info & 0xFFu)) a.rows[size_t(rowBase + e) * K + r] = ws.d(r * T + (info >> 8));
     }
     __syncthreads();
   }
 
   // ---- per-stream totals ----
-  atomicAdd(&ctl[36], nAcc0);  atomicAdd(&ctl[37], nAcc1);  atomicAdd(&ctl[38], nAcc2);
+  atomicAdd(&ws.ctl(36), nAcc0);  atomicAdd(&ws.ctl(37), nAcc1);  atomicAdd(&ws.ctl(38), nAcc2);
   __syncthreads();
-  if (tid == 0) a.grp_sum[g] = make_uint4(ctl[36], ctl[37], ctl[38], aborted ? 1u : 0u);
+  if (tid == 0) a.grp_sum[g] = make_uint4(ws.ctl(36), ws.ctl(37), ws.ctl(38), aborted ? 1u : 0u);
 
   // ---- write the enveloppe back (the host mirrors the same changes from act/rows) ----
   if (changed && !aborted) {
     uint4 *outRows = reinterpret_cast<uint4*>(a.pool_payload_w) + size_t(slot) * K * WQ;
     for (uint32_t i = tid; i < k * WQ; i += T)
-      if ((changed >> (i / WQ)) & 1u) outRows[i] = ws.reps[i];
+      if ((changed >> (i / WQ)) & 1u) outRows[i] = ws.reps(i);
     for (uint32_t r = tid; r < k; r += T)
-      if ((changed >> r) & 1u) a.pool_cmeta_w[size_t(slot) * K + r] = ws.rmeta[r];
-    for (uint32_t i = tid; i < K * K; i += T) a.pool_dist[size_t(slot) * K * K + i] = ws.D[i];
+      if ((changed >> r) & 1u) a.pool_cmeta_w[size_t(slot) * K + r] = ws.rmeta(r);
+    for (uint32_t i = tid; i < K * K; i += T) {
+      const uint32_t row = i / K, col = i - row * K;
+      if (row < k && col < k && row != col) a.pool_dist[size_t(slot) * K * K + i] = ws.D(i);
+    }
     if (tid == 0) a.pool_fill_w[slot] = k;
   }
-  if (prof && tid == 0) { prof[4] = clock64();  prof[5] = profEvents;  prof[6] = profSteps; }
+  if (prof && tid == 0) { prof[4] = clock64();  prof[5] = profEvents;  prof[6] = profSteps;  prof[8] = profA;  prof[9] = profB; }
 }
 
-template <int WQ, int NW>
+template <int WQ, int NW, int KT>
 void launchWQ (const StreamArgs &a, cudaStream_t st) {
   const uint32_t K = a.pool.K;
-  size_t smem = (stream_smem(K, WQ, NW * 32) + 15) & ~size_t(15);
+  size_t smem = (stream_smem(K, WQ, NW * 32, KT > 0) + 15) & ~size_t(15);
   StreamArgs b = a;
   const size_t lutBytes = size_t(a.cfg.lut_classes) * a.cfg.lut_stride * sizeof(double);
   b.lut_in_smem = a.cfg.use_lut && lutBytes > 0 && lutBytes <= (size_t(48) << 10) && smem + lutBytes <= (size_t(200) << 10);
@@ -406,17 +521,23 @@ void launchWQ (const StreamArgs &a, cudaStream_t st) {
     kernel<<<a.n_groups, NW * 32, smem, st>>>(b);
   };
   if (a.cfg.kind == 0) {
-    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW>); else go(resolve_streams_kernel<WQ, 0, false, NW>);
-  } else go(resolve_streams_kernel<WQ, 1, false, NW>);
+    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW, KT>); else go(resolve_streams_kernel<WQ, 0, false, NW, KT>);
+  } else go(resolve_streams_kernel<WQ, 1, false, NW, KT>);
 }
 
 /// Warps per stream: wide CTAs pay off when some stream is long; genomes that fill the register
-/// file (>= 2048 bits per thread) stay at 4 warps.
+/// file (>= 2048 bits per thread) stay at 4 warps.  Enveloppe sizes 5 (the reference's default,
+/// ptreeconfig.cpp:10) and 10 (BASELINE.json) get the register-resident variant for short genomes.
 template <int WQ>
 void launchNW (const StreamArgs &a, cudaStream_t st) {
   const bool wide = a.max_stream > 1024 && WQ <= 8
                     && ((stream_smem(a.pool.K, WQ, 512) + 15) & ~size_t(15)) <= (size_t(150) << 10);
-  if (wide) launchWQ<WQ, 16>(a, st); else launchWQ<WQ, 4>(a, st);
+  if constexpr (WQ <= 4) {
+    if (a.pool.K == 10) { if (wide) launchWQ<WQ, 16, 10>(a, st); else launchWQ<WQ, 4, 10>(a, st); return; }
+    if (a.pool.K == 5) { if (wide) launchWQ<WQ, 16, 5>(a, st); else launchWQ<WQ, 4, 5>(a, st); return; }
+  }
+  if constexpr (WQ <= 8) { if (wide) { launchWQ<WQ, 16, 0>(a, st); return; } }
+  launchWQ<WQ, 4, 0>(a, st);
 }
 
 } // namespace
