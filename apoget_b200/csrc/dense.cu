@@ -50,6 +50,26 @@ __device__ __forceinline__ void cp_async_commit (void) { asm volatile("cp.async.
 __device__ __forceinline__ void cp_async_wait_all (void) { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one (void) { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
+/// Full adder on 32 bit lanes: one LOP3 each (truth tables 0x96 = a ^ b ^ c, 0xE8 = majority)
+__device__ __forceinline__ uint32_t xor3 (uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t maj3 (uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+/// Hamming distance of two 128-bit blocks with THREE population counts instead of four: one carry-save
+/// step, popc(x) + popc(y) + popc(z) = popc(x ^ y ^ z) + 2 popc(maj(x, y, z)), moves a quarter of the
+/// work from the 16-lane POPC pipe (the one this kernel is bound by) to LOP3 on the 64-lane ALU pipe.
+__device__ __forceinline__ uint32_t hamming4 (uint4 a, uint4 b) {
+  const uint32_t x = a.x ^ b.x, y = a.y ^ b.y, z = a.z ^ b.z, w = a.w ^ b.w;
+  return __popc(xor3(x, y, z)) + __popc(w) + 2u * __popc(maj3(x, y, z));
+}
+
 __device__ __forceinline__ double compat_generic (float4 m, double d) {     // crossover.h:89-92
   const double mu = double(m.x);
   const double s = d < mu ? double(m.y) : double(m.z);
@@ -92,7 +112,7 @@ struct Chain {
 };
 
 template <int KIND, bool LUT, bool CONT, int KT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KIND == 1 ? 3 : 2)
 classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__restrict__ b_payload,
                              const float4 *__restrict__ b_cmeta, uint32_t n_births, uint32_t spc, int lut_in_smem, int dbuf,
                              uint32_t *__restrict__ out_best, float *__restrict__ out_best_score,
@@ -180,14 +200,28 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
       const bool same = tid >= int(rows) || __float_as_uint(rmeta_s[tid].w) == c0;
       if (__syncthreads_and(same) && lut_in_smem) chunkCls = c0;
     }
+    // float vectors: same idea on the gaussian's parameters -- when the whole chunk shares them and the birth
+    // has them too, min(c, c) = c and one EX2 per representative is enough
+    bool chunkUni = false;
+    float4 chunkMeta = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KIND == 1) {
+      __syncthreads();                                   // rmeta_s was just rewritten in place
+      chunkMeta = rmeta_s[0];
+      const float4 m = rmeta_s[tid < int(rows) ? tid : 0];
+      chunkUni = __syncthreads_and(m.x == chunkMeta.x && m.y == chunkMeta.y && m.z == chunkMeta.z) != 0;
+    }
 
     // ---- 4 x 4 register tile of distances ----
     if (KIND == 0) {
-      uint32_t acc[BT][RT];
+      // carry-save accumulation: per (birth, representative) pair a running word of weight-1 bits (`ones`) absorbs
+      // the four XOR words of every 128-bit step through two full-adder steps; only the two carry words (weight 2)
+      // are population-counted.  Two POPC + eight LOP3 per step instead of four POPC + four LOP3: the 16-lane POPC
+      // pipe and the 64-lane ALU pipe end up evenly loaded.  dist = 2 * acc + popc(ones).
+      uint32_t acc[BT][RT], ones[BT][RT];
 #pragma unroll
       for (int i = 0; i < BT; i++)
 #pragma unroll
-        for (int j = 0; j < RT; j++) acc[i][j] = 0;
+        for (int j = 0; j < RT; j++) { acc[i][j] = 0; ones[i][j] = 0; }
       for (uint32_t v = 0; v < wp4; v++) {
         uint4 bq[BT], rq[RT];
 #pragma unroll
@@ -197,14 +231,18 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
 #pragma unroll
         for (int i = 0; i < BT; i++)
 #pragma unroll
-          for (int j = 0; j < RT; j++)
-            acc[i][j] += __popc(bq[i].x ^ rq[j].x) + __popc(bq[i].y ^ rq[j].y)
-                       + __popc(bq[i].z ^ rq[j].z) + __popc(bq[i].w ^ rq[j].w);
+          for (int j = 0; j < RT; j++) {
+            const uint32_t x = bq[i].x ^ rq[j].x, y = bq[i].y ^ rq[j].y, z = bq[i].z ^ rq[j].z, w = bq[i].w ^ rq[j].w;
+            const uint32_t s1 = xor3(x, y, z), c1 = maj3(x, y, z);
+            const uint32_t o = ones[i][j], c2 = maj3(s1, w, o);
+            ones[i][j] = xor3(s1, w, o);
+            acc[i][j] += __popc(c1) + __popc(c2);
+          }
       }
 #pragma unroll
       for (int i = 0; i < BT; i++)
 #pragma unroll
-        for (int j = 0; j < RT; j++) dist_s[(tx + 16 * j) * DPAD + ty + 16 * i] = acc[i][j];
+        for (int j = 0; j < RT; j++) dist_s[(tx + 16 * j) * DPAD + ty + 16 * i] = 2u * acc[i][j] + __popc(ones[i][j]);
     } else {
       // packed FP32 (FADD2 / FFMA2, sm_100): two coordinates per instruction -- this loop is bound by issue
       // slots, not by the FMA datapath; births are stored negated, so t = rep - birth is one add
@@ -243,11 +281,12 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
     const float4 bm = bmeta_s[eb];
     const uint32_t bcls = __float_as_uint(bm.w);
     const double *lutB = LUT ? lut + size_t(bcls) * cfg.lut_stride : nullptr;
+    const bool sameMeta = KIND == 1 && chunkUni && bm.x == chunkMeta.x && bm.y == chunkMeta.y && bm.z == chunkMeta.z;
     auto step = [&] (Chain<KIND> &ch, uint32_t sl, uint32_t r) {
       const uint32_t dw = dist_s[(sl * K + r) * DPAD + eb];
       if (KIND == 1) {
         const float df = __uint_as_float(dw);
-        const float c = fminf(compat_fast(bm, df), compat_fast(rmeta_s[sl * K + r], df));
+        const float c = sameMeta ? compat_fast(bm, df) : fminf(compat_fast(bm, df), compat_fast(rmeta_s[sl * K + r], df));
         if (CONT) ch.favg += c; else ch.matable += (double(c) >= cfg.compat_thr);
         return;
       }

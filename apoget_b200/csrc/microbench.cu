@@ -18,9 +18,15 @@ __global__ void __launch_bounds__(256) pipe_kernel (uint32_t iters, uint32_t see
     if (WHAT == 0) {          // POPC (+ the XOR that feeds it, as in a Hamming distance)
       a0 = __popc(a0 ^ seed) + i; a1 = __popc(a1 ^ seed) + i; a2 = __popc(a2 ^ seed) + i; a3 = __popc(a3 ^ seed) + i;
       a4 = __popc(a4 ^ seed) + i; a5 = __popc(a5 ^ seed) + i; a6 = __popc(a6 ^ seed) + i; a7 = __popc(a7 ^ seed) + i;
-    } else if (WHAT == 1) {   // LOP3 only
-      a0 = (a0 ^ seed) & a1 | i; a1 = (a1 ^ seed) & a2 | i; a2 = (a2 ^ seed) & a3 | i; a3 = (a3 ^ seed) & a4 | i;
-      a4 = (a4 ^ seed) & a5 | i; a5 = (a5 ^ seed) & a6 | i; a6 = (a6 ^ seed) & a7 | i; a7 = (a7 ^ seed) & a0 | i;
+    } else if (WHAT == 1) {   // LOP3 only (one three-input instruction per operation: a ^ b ^ c)
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a0) : "r"(a1), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a1) : "r"(a2), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a2) : "r"(a3), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a3) : "r"(a4), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a4) : "r"(a5), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a5) : "r"(a6), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a6) : "r"(a7), "r"(i));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a7) : "r"(a0), "r"(i));
     } else if (WHAT == 2) {   // DFMA
       d0 = fma(d0, 1.0000001, 0.5); d1 = fma(d1, 1.0000001, 0.5); d2 = fma(d2, 1.0000001, 0.5); d3 = fma(d3, 1.0000001, 0.5);
     } else if (WHAT == 4) {   // F2F: float -> double -> float round trips (the `float avg += double c` of the scoring loop)

@@ -150,6 +150,16 @@ def run(args):
     evals = float(B) * S * K
     ops = evals * (words if kind == 0 else 3 * words)
     peak = peaks[0] if kind == 0 else peaks[3] * 2
+    # Integer-pipe model of the bit-string tile (dense.cu): per 128-bit step of a (birth, representative) pair the
+    # carry-save accumulation issues 2 POPC (16-lane pipe) and 9 ALU operations (8 LOP3 + 1 IADD3, 64-lane pipe);
+    # the slower of the two pipes bounds the sweep.  The algorithmic count (one popc32 per word) can therefore exceed
+    # the measured POPC peak.
+    model = None
+    if kind == 0:
+        steps = evals * ((words + 3) // 4)
+        t_popc, t_alu = 2 * steps / peaks[0], 9 * steps / peaks[1]
+        model = {"popc_per_step": 2, "alu_ops_per_step": 9, "bound": "alu (lop3/iadd3)" if t_alu >= t_popc else "popc",
+                 "min_ms": 1e3 * max(t_popc, t_alu) / world, "frac": max(t_popc, t_alu) / world / (ms * 1e-3)}
     out = None
     if rank == 0:
         out = ({
@@ -160,6 +170,7 @@ def run(args):
             "births_per_s": B / (ms * 1e-3), "evals_per_s": evals / (ms * 1e-3),
             "pipe_ops_per_s": ops / (ms * 1e-3), "pipe": "popc32 (+xor)" if kind == 0 else "fp32 flop (sub, fma)",
             "pipe_peak_measured": peak, "frac_of_pipe_peak": ops / (ms * 1e-3) / (peak * world),
+            "int_pipe_model": model,
             "microbench": {"popc32_per_s": peaks[0], "lop3_per_s": peaks[1], "dfma_per_s": peaks[2], "ffma_per_s": peaks[3],
                            "f2f_cvt_per_s": cvt[0]},
             "accepting_births_frac": float((count > 0).mean()), "oracle_checked_births": int(min(args.check, B)),
