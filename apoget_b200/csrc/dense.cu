@@ -35,7 +35,7 @@ namespace {
 constexpr int TB = 64;          // births per CTA
 constexpr int TR = 64;          // representative rows per chunk
 constexpr int BT = 4, RT = 4;   // register tile
-constexpr int DPAD = TB + 1;    // distance tile row pitch (words)
+constexpr int DPAD = TB + 4;    // distance tile row pitch (words): a warp's 8 x 4 tile corners land in 32 different banks
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void cp_async16 (void *smem, const void *gmem) {
@@ -133,7 +133,10 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
     lut = lut_s;
   }
 
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // thread -> tile corner: a warp covers 8 representative rows x 4 birth rows, so that a 128-bit operand load of a
+  // warp touches 8 (4) distinct rows = one shared-memory wavefront each, the rest being broadcast
+  const int tid = threadIdx.x;
+  const int tx = ((tid >> 5) & 1) * 8 + (tid & 7), ty = (tid >> 6) * 4 + ((tid >> 3) & 3);
   const uint32_t b0 = blockIdx.x * TB;
 
   // ---- stage the birth tile (rows past the end are zero) ----
@@ -325,6 +328,22 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
           }
           fold(win, float(__dsub_rn(double(__fdiv_rn(float(A), float(KT))), cfg.avg_thr)), s0 + sa);
           fold(win, float(__dsub_rn(double(__fdiv_rn(float(B), float(KT))), cfg.avg_thr)), s0 + sb);
+          continue;
+        }
+      }
+      if (KIND == 1 && CONT && KT > 0) {
+        // float vectors, the common case, unrolled: both enveloppes full and one set of gaussian parameters for
+        // the chunk and the birth -- per representative one LDS, five FP32 operations and one EX2
+        if (sameMeta && ka == uint32_t(KT) && kb == uint32_t(KT)) {
+          const uint32_t *da = dist_s + size_t(sa) * KT * DPAD + eb, *db = dist_s + size_t(sb) * KT * DPAD + eb;
+          float A = 0.f, B = 0.f;
+#pragma unroll
+          for (int r = 0; r < (KT ? KT : 1); r++) {
+            A += compat_fast(bm, __uint_as_float(da[r * DPAD]));
+            B += compat_fast(bm, __uint_as_float(db[r * DPAD]));
+          }
+          fold(win, float(__dsub_rn(double(__fdiv_rn(A, float(KT))), cfg.avg_thr)), s0 + sa);
+          fold(win, float(__dsub_rn(double(__fdiv_rn(B, float(KT))), cfg.avg_thr)), s0 + sb);
           continue;
         }
       }

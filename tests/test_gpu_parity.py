@@ -316,3 +316,35 @@ def test_sharded_dense_sweep_records_and_combine(kind, words, sigma):
     ref = shard.reduce_records(rec)
     for a, b in zip(out, ref):
         assert torch.equal(a, b), "combine kernel and the torch reduction of the all-gather path disagree"
+
+
+@pytest.mark.parametrize("kind,words,K,sigma", [(synth.BITS, 8, 10, 8.0), (synth.BITS, 8, 5, 8.0), (synth.BITS, 128, 10, 60.0),
+                                                (synth.F32, 64, 10, 0.4), (synth.F32, 16, 5, 0.3)])
+def test_dense_sweep_full_uniform_pool(kind, words, K, sigma):
+    """The unrolled epilogues of the dense sweep (full enveloppes, one compatibility class, K = 5 / 10): same
+    contract as test_dense_sweep_kernel, plus one partially filled and one foreign-class species that must take
+    the general path inside the same launch."""
+    from apoget_b200.kernels import Pool
+    rng = np.random.default_rng(23 + words + K)
+    S, B = 131, 203
+    reps, rc, fill = _random_pool(rng, kind, words, S, K, sigma)
+    rc[...] = rc[1, 0]
+    fill[:] = K
+    fill[40] = max(1, K - 2)
+    rc[77, :, 1] *= 0.5
+    pool = Pool(kind, words, reps, rc, fill, K=K)
+    src = rng.integers(0, S, size=B)
+    births, bc = reps[src, 0].copy(), rc[np.full(B, 1), 0].copy()
+    best, best_score, first, count = pool.classify_dense(births, bc)
+    for b in range(0, B, 3):
+        scores = np.array([oracle.score(kind, births[b], bc[b], reps[s, :fill[s]], rc[s, :fill[s]])[0] for s in range(S)],
+                          dtype=np.float32)
+        if kind == synth.BITS:
+            assert best[b] == int(np.argmax(scores)) and best_score[b] == scores.max()
+            acc = np.nonzero(scores > 0)[0]
+            assert count[b] == acc.size
+            assert first[b] == (acc[0] if acc.size else 0xFFFFFFFF)
+        else:
+            assert abs(best_score[b] - scores.max()) <= 1e-5
+            sure = np.abs(scores) > 1e-5
+            assert abs(int(count[b]) - int((scores > 0).sum())) <= int((~sure).sum())
