@@ -35,7 +35,7 @@ WorkerPool::~WorkerPool (void) {
 }
 
 void WorkerPool::loop (unsigned t) {
-  uint64_t seen = 0;
+  uint64_t seen = 0, seenHint = 0;
   for (;;) {
     // phases of one chunk follow each other within microseconds: spin briefly before sleeping
     bool got = false;
@@ -45,8 +45,10 @@ void WorkerPool::loop (unsigned t) {
     }
     if (!got) {
       std::unique_lock<std::mutex> lk (m_);
-      wake_.wait(lk, [&] { return stop_ || gen_.load(std::memory_order_acquire) != seen; });
+      wake_.wait(lk, [&] { return stop_ || gen_.load(std::memory_order_acquire) != seen || hint_ != seenHint; });
       if (stop_) return;
+      seenHint = hint_;
+      if (gen_.load(std::memory_order_acquire) == seen) continue;     // woken ahead of the work (wake()): spin for it
     }
     seen = gen_.load(std::memory_order_acquire);
     (*fn_)(t);
@@ -55,6 +57,14 @@ void WorkerPool::loop (unsigned t) {
       done_.notify_one();
     }
   }
+}
+
+/// Work is coming within microseconds: sleeping workers get up now and spin, so that their wake-up latency
+/// (tens of microseconds) overlaps whatever the caller still does before the first run()
+void WorkerPool::wake (void) {
+  if (n_ == 1) return;
+  { std::lock_guard<std::mutex> lk (m_); hint_++; }
+  wake_.notify_all();
 }
 
 void WorkerPool::run (const std::function<void(unsigned)> &fn) {
@@ -1600,6 +1610,7 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
   uint32_t done = 0;
   if (nDone) *nDone = 0;
   if (!n) return;
+  if (pool_ && n >= parMin_) pool_->wake();
   cudaCheck(cudaSetDevice(p_.device), "cudaSetDevice");
 
   // device-resident payloads stay where they are: the kernels read them in place and the host only

@@ -90,6 +90,7 @@ public:
   ~WorkerPool (void);
   unsigned size (void) const { return n_; }
   void run (const std::function<void(unsigned)> &fn);
+  void wake (void);
 private:
   void loop (unsigned t);
   unsigned n_;
@@ -100,6 +101,7 @@ private:
   std::atomic<uint64_t> gen_ { 0 };
   std::atomic<unsigned> pending_ { 0 };
   bool stop_ = false;
+  uint64_t hint_ = 0;
 };
 
 // speciescontributors.h:16-86 / :89-100
