@@ -46,6 +46,25 @@ __device__ __forceinline__ void cp_async4 (void *smem, const void *gmem) {
   const uint32_t s = uint32_t(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(s), "l"(gmem));
 }
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ----
+__device__ __forceinline__ void mbar_init (uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+               :: "r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity) {
+  const uint32_t a = uint32_t(__cvta_generic_to_shared(bar));
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" :: "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s (void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem), "r"(bytes),
+                  "r"(uint32_t(__cvta_generic_to_shared(bar))) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit (void) { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all (void) { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one (void) { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
@@ -114,13 +133,14 @@ struct Chain {
 template <int KIND, bool LUT, bool CONT, int KT>
 __global__ void __launch_bounds__(256, KIND == 1 ? 3 : 2)
 classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__restrict__ b_payload,
-                             const float4 *__restrict__ b_cmeta, uint32_t n_births, uint32_t spc, int lut_in_smem, int dbuf,
+                             const float4 *__restrict__ b_cmeta, uint32_t n_births, uint32_t spc, int lut_in_smem, int dbuf, int bulk,
                              uint32_t *__restrict__ out_best, float *__restrict__ out_best_score,
                              uint32_t *__restrict__ out_first, uint32_t *__restrict__ out_count, ShardSink sink) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t K = KT ? uint32_t(KT) : pool.K, wp4 = pool.wp >> 2, stride4 = wp4 | 1u;    // KT: enveloppe size known at compile time
   // [births][dist][chunk buffer 0][chunk buffer 1 (dbuf)][table (lut_in_smem)]; a chunk buffer = rows + metadata + fills
-  uint4 *births_s = reinterpret_cast<uint4*>(smem);                       // [TB][stride4]
+  uint64_t *bars = reinterpret_cast<uint64_t*>(smem);                     // two mbarriers (bulk-copy staging), one per chunk buffer
+  uint4 *births_s = reinterpret_cast<uint4*>(smem + 16);                  // [TB][stride4]
   float4 *bmeta_s = reinterpret_cast<float4*>(births_s + size_t(TB) * stride4);   // [TB]
   uint32_t *dist_s = reinterpret_cast<uint32_t*>(bmeta_s + TB);           // [TR][DPAD]: u32 (bit-strings) / f32 bits
   unsigned char *chunk0 = reinterpret_cast<unsigned char*>(dist_s + size_t(TR) * DPAD);
@@ -139,12 +159,25 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
   const int tx = ((tid >> 5) & 1) * 8 + (tid & 7), ty = (tid >> 6) * 4 + ((tid >> 3) & 3);
   const uint32_t b0 = blockIdx.x * TB;
 
-  // ---- stage the birth tile (rows past the end are zero) ----
-  for (uint32_t i = tid; i < TB * wp4; i += 256) {
-    const uint32_t row = i / wp4, v = i % wp4;
-    if (b0 + row < n_births)
-      cp_async16(&births_s[row * stride4 + v], reinterpret_cast<const uint4*>(b_payload) + size_t(b0 + row) * wp4 + v);
-    else births_s[row * stride4 + v] = make_uint4(0, 0, 0, 0);
+  // ---- stage the birth tile (rows past the end are zero).  Long genomes: one TMA bulk copy per row (rows are
+  //      contiguous in HBM, padded in shared memory), completing on the first chunk's mbarrier; short ones
+  //      (< 128 B per row) keep 16-byte cp.async ----
+  const uint32_t rowBytes = pool.wp * 4;
+  const uint32_t birthRows = min(uint32_t(TB), n_births - b0);
+  if (bulk) {
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    __syncthreads();
+    if (tid < int(birthRows))
+      bulk_g2s(&births_s[tid * stride4], reinterpret_cast<const uint4*>(b_payload) + size_t(b0 + tid) * wp4, rowBytes, &bars[0]);
+    for (uint32_t i = tid; i < (TB - birthRows) * wp4; i += 256)
+      births_s[(birthRows + i / wp4) * stride4 + i % wp4] = make_uint4(0, 0, 0, 0);
+  } else {
+    for (uint32_t i = tid; i < TB * wp4; i += 256) {
+      const uint32_t row = i / wp4, v = i % wp4;
+      if (b0 + row < n_births)
+        cp_async16(&births_s[row * stride4 + v], reinterpret_cast<const uint4*>(b_payload) + size_t(b0 + row) * wp4 + v);
+      else births_s[row * stride4 + v] = make_uint4(0, 0, 0, 0);
+    }
   }
   if (tid < TB) {
     const float4 m = b0 + tid < n_births ? __ldg(b_cmeta + b0 + tid) : make_float4(0.f, 1.f, 1.f, 0.f);
@@ -165,12 +198,20 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
     uint32_t *fill = reinterpret_cast<uint32_t*>(rmeta + TR);
     const uint32_t ns = min(spc, pool.n_slots - s0), rows = ns * K;
     const uint4 *src = reinterpret_cast<const uint4*>(pool.payload) + size_t(s0) * K * wp4;   // `rows` rows, contiguous
-    for (uint32_t i = tid; i < TR * wp4; i += 256) {
-      const uint32_t row = i / wp4, v = i % wp4;
-      if (row < rows) cp_async16(&reps[row * stride4 + v], src + size_t(row) * wp4 + v);
-      else reps[row * stride4 + v] = make_uint4(0, 0, 0, 0);
+    if (bulk) {
+      // thread 0 announces the bytes of the chunk (plus the birth tile on the very first one), one thread per row issues its copy
+      if (tid == 0) mbar_expect_tx(&bars[buf], rows * (rowBytes + 16u) + (s0 == 0 ? birthRows * rowBytes : 0u));
+      if (tid < int(rows)) bulk_g2s(&reps[tid * stride4], src + size_t(tid) * wp4, rowBytes, &bars[buf]);
+      if (tid == 32) bulk_g2s(rmeta, pool.cmeta + size_t(s0) * K, rows * 16u, &bars[buf]);
+      for (uint32_t i = tid; i < (TR - rows) * wp4; i += 256) reps[(rows + i / wp4) * stride4 + i % wp4] = make_uint4(0, 0, 0, 0);
+    } else {
+      for (uint32_t i = tid; i < TR * wp4; i += 256) {
+        const uint32_t row = i / wp4, v = i % wp4;
+        if (row < rows) cp_async16(&reps[row * stride4 + v], src + size_t(row) * wp4 + v);
+        else reps[row * stride4 + v] = make_uint4(0, 0, 0, 0);
+      }
+      if (tid < int(rows)) cp_async16(&rmeta[tid], pool.cmeta + size_t(s0) * K + tid);
     }
-    if (tid < int(rows)) cp_async16(&rmeta[tid], pool.cmeta + size_t(s0) * K + tid);
     if (tid < int(ns)) cp_async4(&fill[tid], pool.fill + s0 + tid);
     cp_async_commit();
   };
@@ -180,6 +221,7 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
     const uint32_t buf = dbuf ? (c & 1u) : 0u;
     if (dbuf && s0 + spc < pool.n_slots) { stage(s0 + spc, buf ^ 1u); cp_async_wait_but_one(); }
     else cp_async_wait_all();
+    if (bulk) mbar_wait(&bars[buf], (dbuf ? (c >> 1) : c) & 1u);      // the buffer's mbarrier flips phase once per use
     __syncthreads();
     uint4 *reps_s = reinterpret_cast<uint4*>(chunk0 + buf * chunkBytes);
     float4 *rmeta_s = reinterpret_cast<float4*>(reps_s + size_t(TR) * stride4);
@@ -397,7 +439,7 @@ size_t dense_chunk_bytes (uint32_t wp) {
 }
 size_t dense_smem (uint32_t wp) {
   const size_t stride4 = (wp >> 2) | 1u;
-  return size_t(TB) * stride4 * 16 + size_t(TB) * 16 + size_t(TR) * DPAD * 4 + dense_chunk_bytes(wp);
+  return 16 + size_t(TB) * stride4 * 16 + size_t(TB) * 16 + size_t(TR) * DPAD * 4 + dense_chunk_bytes(wp);
 }
 
 } // namespace
@@ -421,10 +463,11 @@ void launch_classify_dense_tiled (const PoolView &pool, const ScoreCfg &cfg, con
   const size_t lutBytes = size_t(cfg.lut_classes) * cfg.lut_stride * sizeof(double);
   const int lutInSmem = cfg.use_lut && lutBytes > 0 && lutBytes <= (size_t(32) << 10) && smem + lutBytes <= (size_t(110) << 10);
   if (lutInSmem) smem += lutBytes;
+  const int bulk = pool.wp * 4 >= 128;        // TMA bulk copies for rows of at least 128 bytes
   const uint32_t grid = (n_births + TB - 1) / TB;
   auto go = [&] (auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kernel<<<grid, 256, smem, stream>>>(pool, cfg, b_payload, b_cmeta, n_births, spc, lutInSmem, dbuf, out_best, out_best_score,
+    kernel<<<grid, 256, smem, stream>>>(pool, cfg, b_payload, b_cmeta, n_births, spc, lutInSmem, dbuf, bulk, out_best, out_best_score,
                                         out_first, out_count, snk);
   };
   const bool cont = cfg.full_continuous != 0;
