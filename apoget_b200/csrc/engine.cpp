@@ -1183,6 +1183,7 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
     }
 }
 
+
 void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
                        const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                        const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
@@ -1302,6 +1303,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   }
   uint32_t nRows = 0;
   nFt_ = 0;
+  bool directOut = false;
   if (G) {
     // the ordered resolution of the single-parent births, one warp per species stream; it runs
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
@@ -1358,10 +1360,15 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       cudaCheck(cudaMemcpyAsync(hFtCounter_.p, dFtCounter_.p, 4, cudaMemcpyDeviceToHost, stream_), "ft counter");
     cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
     cudaCheck(cudaMemcpyAsync(hRowCounter_.p, dRowCounter_.p, 4, cudaMemcpyDeviceToHost, stream_), "row counter");
-    cudaCheck(cudaMemcpyAsync(hOutSid_.p, dOutSid_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
-    cudaCheck(cudaMemcpyAsync(hOutSlot_.p, dOutSlot_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "slots");
+    // results go straight into the caller's arrays when those are pinned (no staging copy on the host)
+    directOut = outSid && outSlot && outPinned_;
+    cudaCheck(cudaMemcpyAsync(directOut ? outSid : hOutSid_.p, dOutSid_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
+    cudaCheck(cudaMemcpyAsync(directOut ? reinterpret_cast<uint32_t*>(outSlot) : reinterpret_cast<uint32_t*>(hOutSlot_.p), dOutSlot_.p,
+                              size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "slots");
     cudaCheck(cudaMemcpyAsync(hGrpSum_.p, dGrpSum_.p, size_t(G) * sizeof(uint4), cudaMemcpyDeviceToHost, stream_), "sums");
   }
+  // host work that needs no device result runs under the device pass
+  if (G && outReplaced) memset(outReplaced, 0xFF, size_t(n) * 4);
   if (P || G) {
     cudaCheck(cudaStreamSynchronize(stream_), "device pass");
     float ms = 0.f;
@@ -1417,9 +1424,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     const uint32_t per = (n + T - 1) / T;
     auto scan = [&] (unsigned t) {
       const uint32_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
-      if (outSid) memcpy(outSid + lo, hOutSid_.p + lo, size_t(hi - lo) * 4);
-      if (outSlot) memcpy(outSlot + lo, hOutSlot_.p + lo, size_t(hi - lo) * 4);
-      if (outReplaced) memset(outReplaced + lo, 0xFF, size_t(hi - lo) * 4);
+      if (!directOut) {
+        if (outSid) memcpy(outSid + lo, hOutSid_.p + lo, size_t(hi - lo) * 4);
+        if (outSlot) memcpy(outSlot + lo, hOutSlot_.p + lo, size_t(hi - lo) * 4);
+      }
       auto &rest = parRest_[t];
       rest.clear();
       for (uint32_t i = lo; i < hi; i++)
@@ -1612,6 +1620,13 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
   if (!n) return;
   if (pool_ && n >= parMin_) pool_->wake();
   cudaCheck(cudaSetDevice(p_.device), "cudaSetDevice");
+  outPinned_ = false;
+  if (outSid && outSlot && n >= 4096) {
+    cudaPointerAttributes a0, a1;
+    outPinned_ = cudaPointerGetAttributes(&a0, outSid) == cudaSuccess && a0.type == cudaMemoryTypeHost
+              && cudaPointerGetAttributes(&a1, outSlot) == cudaSuccess && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();        // an unregistered pointer is not an error here
+  }
 
   // device-resident payloads stay where they are: the kernels read them in place and the host only
   // fetches the rows of the births it has to look at (runChunk)

@@ -235,7 +235,8 @@ private:
   std::unique_ptr<WorkerPool> pool_;
   uint32_t parMin_ = 32768;               // chunks at least this large are grouped by the worker pool
   std::vector<uint32_t> sidSlot_;         // sid -> pool slot when the species can be streamed (device copy current), else APT_INVALID
-  std::vector<std::vector<uint32_t>> parCnt_, parRest_;
+  std::vector<std::vector<uint32_t>> parRest_, parCnt_;
+
   std::vector<uint32_t> birthKey_;
   void groupSerial (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
   void groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
@@ -261,6 +262,7 @@ private:
   uint32_t chunkCls_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
+  bool outPinned_ = false;              // the caller's result arrays of the current call are pinned host memory
   DevBuf<unsigned long long> dProf_;    // per-stream timelines, only with APT_STREAM_PROF=<file>
   PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
   PinBuf<float4> hBMeta_, hStageMeta_;

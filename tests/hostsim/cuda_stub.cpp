@@ -41,6 +41,7 @@ cudaError_t cudaMemsetAsync (void *d, int v, size_t n, cudaStream_t) { memset(d,
 cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize (void) { return cudaSuccess; }
 cudaError_t cudaGetLastError (void) { return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes (cudaPointerAttributes *a, const void*) { memset(a, 0, sizeof *a); a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 const char* cudaGetErrorString (cudaError_t) { return "stub"; }
 }
 

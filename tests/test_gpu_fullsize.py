@@ -1,0 +1,131 @@
+"""GPU tests at BASELINE.json's full sizes (-m gpu).
+
+* candidate mode at C2 size (100 000 births per generation, ~1 000 species, K = 10): the whole tree must equal
+  the CPU oracle's (species ids, enveloppe entries, dump), and the result must not depend on how a generation is
+  cut into add_genomes calls (the batched call is DEFINED as n sequential addGenome calls);
+* dense sweep at 1 M births x 100 k enveloppe members: size-independent properties (permutation of the births,
+  shard additivity of the accept counts, argmax merge) plus an oracle check on a sample.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from apoget_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _c2_trace(gens):
+    return synth.generate(kind=synth.BITS, words=8, pop=100_000, gens=gens, seed=42, flips=0.5, sigma=12.0, hybrid=0.05,
+                          burst_levels=3, burst_fanout=10)
+
+
+def test_c2_full_size_tree_equals_oracle_and_is_batch_invariant(tmp_path):
+    from apoget_b200.tree import PhylogeneticTree, INVALID
+    t = _c2_trace(6)
+    path = str(tmp_path / "c2.trace")
+    synth.write_trace(path, t)
+    o = oracle.Oracle(t.kind, t.words, K=10)
+    o.log_events(False)
+    osids, oent, _ = o.replay(path, n_births=t.n_births)
+
+    whole = PhylogeneticTree(t.kind, t.words, K=10)
+    sids, slots = whole.replay(t)
+    assert np.array_equal(sids, osids), "per-birth species ids differ from the oracle at full size"
+    assert np.array_equal(slots >= 0, oent > 0), "enveloppe entries differ from the oracle at full size"
+    assert whole.to_json() == o.to_json(), "tree dump differs from the oracle at full size"
+    c = whole.counters()
+    assert c["stream_births"] >= 200_000 and c["kernel_launches"] > 0, "the stream kernel did not carry the steady generations"
+
+    # the same generations cut into uneven calls (ragged: 1, 7, 33 333, the rest)
+    cut = PhylogeneticTree(t.kind, t.words, K=10)
+    sid_of = np.full(t.n_births, INVALID, dtype=np.uint32)
+    for g in range(t.n_gens):
+        b0, b1 = int(t.gen_birth_off[g]), int(t.gen_birth_off[g + 1])
+        edges = [b0, b0 + 1, b0 + 8, b0 + 33_341, b1]
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            m, f = t.mother[lo:hi], t.father[lo:hi]
+            hm, hf = m != INVALID, f != INVALID
+            s, _, _ = cut.add_genomes(t.payload[lo:hi], t.compat[lo:hi], np.arange(lo + 1, hi + 1, dtype=np.uint32),
+                                      np.where(hm, m + 1, INVALID), np.where(hm, sid_of[np.where(hm, m, 0)], INVALID),
+                                      np.where(hf, f + 1, INVALID), np.where(hf, sid_of[np.where(hf, f, 0)], INVALID))
+            sid_of[lo:hi] = s
+        cut.del_genomes(sid_of[t.deaths_of(g)])
+        cut.step(g + 1, sid_of[t.alive_of(g)])
+    assert np.array_equal(sid_of, sids), "result depends on the batch boundaries"
+    assert cut.to_json() == whole.to_json(), "tree depends on the batch boundaries"
+
+
+@pytest.mark.parametrize("words,sigma", [(8, 12.0), (128, 60.0)])
+def test_dense_sweep_full_size_properties(words, sigma):
+    """1 M births x 10 000 species x K = 10 (256-bit: the whole batch; 4096-bit: a 131 072-birth slice keeps the
+    test under a few seconds -- the properties do not depend on the number of births)."""
+    import torch
+    from apoget_b200 import shard
+    from apoget_b200.kernels import Pool, combine_shards_dev
+    rng = np.random.default_rng(44)
+    S, K = 10_000, 10
+    B = 1_000_000 if words == 8 else 131_072
+    base = rng.integers(0, 2**32, size=(S, 1, words), dtype=np.uint32)
+    noise = rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32)
+    for _ in range(4 if words <= 8 else 6):
+        noise &= rng.integers(0, 2**32, size=(S, K, words), dtype=np.uint32)
+    reps = np.ascontiguousarray(base ^ noise)
+    rc = np.zeros((S, K, 3), dtype=np.float32)
+    rc[..., 1:] = sigma
+    fill = np.full(S, K, dtype=np.uint32)
+    fill[rng.integers(0, S, size=50)] = rng.integers(0, K, size=50)        # ragged and empty enveloppes
+    src = rng.integers(0, S, size=B)
+    births = reps[src, rng.integers(0, K, size=B)].copy()
+    births[np.arange(B), rng.integers(0, words, size=B)] ^= rng.integers(0, 2**32, size=B, dtype=np.uint32) & np.uint32(0x00010101)
+    bc = np.zeros((B, 3), dtype=np.float32)
+    bc[:, 1:] = sigma
+    vp = ctypes.c_void_p
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    d_compat = torch.from_numpy(bc).cuda()
+
+    def sweep(pool, d_births, n):
+        out = [torch.empty(n, dtype=dt, device="cuda") for dt in (torch.int32, torch.float32, torch.int32, torch.int32)]
+        pool.classify_dense_dev(n, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), *[vp(x.data_ptr()) for x in out], stream)
+        torch.cuda.synchronize()
+        return out
+
+    whole = Pool(synth.BITS, words, reps, rc, fill, K=K)
+    d_births = torch.from_numpy(births.view(np.int32)).cuda()
+    best, score, first, count = sweep(whole, d_births, B)
+
+    # 1. permuting the births permutes the results
+    perm = torch.from_numpy(rng.permutation(B)).cuda()
+    pb, ps, pf, pc = sweep(whole, d_births[perm].contiguous(), B)
+    assert torch.equal(pb, best[perm]) and torch.equal(ps, score[perm]) and torch.equal(pf, first[perm]) and torch.equal(pc, count[perm])
+
+    # 2. shard additivity / argmax merge: two species shards into one record buffer, combined on the device
+    world = 2
+    rec = torch.empty((world, B, 4), dtype=torch.int32, device="cuda")
+    for r in range(world):
+        lo, hi = shard.shard_range(S, r, world)
+        part = Pool(synth.BITS, words, reps[lo:hi], rc[lo:hi], fill[lo:hi], K=K)
+        part.classify_dense_shard_dev(B, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), lo, r, world, [rec.data_ptr()] * world, stream)
+        torch.cuda.synchronize()
+        part.close()
+    out = [torch.empty(B, dtype=dt, device="cuda") for dt in (torch.int32, torch.float32, torch.int32, torch.int32)]
+    combine_shards_dev(B, world, vp(rec.data_ptr()), *[vp(o.data_ptr()) for o in out], stream)
+    torch.cuda.synchronize()
+    for a, b, name in zip(out, (best, score, first, count), ("best", "score", "first", "count")):
+        assert torch.equal(a, b), f"sharded sweep differs from the whole pool: {name}"
+
+    # 3. every birth is a near-copy of a representative of species src[b]: nearly all are accepted somewhere
+    cnt = count.cpu().numpy()
+    ok_src = fill[src] == K
+    assert (cnt[ok_src] >= 1).mean() > 0.95
+    # 4. oracle on a sample: all species of 6 births
+    bst, sc, fst = best.cpu().numpy(), score.cpu().numpy(), first.cpu().numpy()
+    for b in rng.choice(B, size=6, replace=False):
+        ref = np.array([oracle.score(synth.BITS, births[b], bc[b], reps[s, :fill[s]], rc[s, :fill[s]])[0] if fill[s] else -np.inf
+                        for s in range(S)], dtype=np.float32)
+        assert int(bst[b]) == int(np.argmax(ref)) and sc[b] == ref.max()
+        acc = np.nonzero(ref > 0)[0]
+        assert cnt[b] == acc.size and int(fst[b]) == (int(acc[0]) if acc.size else -1)
