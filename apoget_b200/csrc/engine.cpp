@@ -123,6 +123,8 @@ Engine::Engine (const apt_params &p) : p_(p) {
     unsigned nt = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
     if (const char *e = getenv("APT_HOST_THREADS")) nt = unsigned(std::max(1, atoi(e)));
     if (const char *e = getenv("APT_PAR_MIN")) parMin_ = uint32_t(std::max(1, atoi(e)));
+    profile_ = getenv("APT_PROFILE") != nullptr;
+    if (const char *e = getenv("APT_STREAM_PROF")) streamProf_ = e;
     if (nt > 1) pool_.reset(new WorkerPool(nt));
   }
   streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
@@ -1103,7 +1105,7 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
   const uint32_t rootSid = (root_ && root_->sid < NS && nodes_[root_->sid] == root_) ? root_->sid : INV;
   const bool rootOk = rootSid != INV && sidSlot_[rootSid] != INV;
   const uint32_t per = (n + T - 1) / T;
-  const double q0 = now();
+  const double q0 = profile_ ? now() : 0.;
   // 1. classify every birth, count per (thread, species)
   pool_->run([&] (unsigned t) {
     auto &cnt = parCnt_[t];
@@ -1120,7 +1122,7 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
       if (key != INV) cnt[key & ORDER_INDEX_MASK]++;
     }
   });
-  const double q1 = now();
+  const double q1 = profile_ ? now() : 0.;
   // 2. streams in ascending species id; per-thread cursors
   uint32_t off = 0;
   for (size_t sid = 0; sid < NS; sid++) {
@@ -1146,7 +1148,7 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
     hGrpOff_.p[g] = o2;  o2 += grpCount_[g];
   }
   hGrpOff_.p[G] = o2;
-  const double q2 = now();
+  const double q2 = profile_ ? now() : 0.;
   // 3. scatter
   pool_->run([&] (unsigned t) {
     auto &cur = parCnt_[t];
@@ -1162,8 +1164,8 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
       } else { birthGroup_[i] = -1; rest.push_back(i); }
     }
   });
-  const double q3 = now();
-  if (getenv("APT_PROFILE")) fprintf(stderr, "group: count %.3f assign %.3f scatter %.3f ms\n", 1e3*(q1-q0), 1e3*(q2-q1), 1e3*(q3-q2));
+  const double q3 = profile_ ? now() : 0.;
+  if (profile_) fprintf(stderr, "group: count %.3f assign %.3f scatter %.3f ms\n", 1e3*(q1-q0), 1e3*(q2-q1), 1e3*(q3-q2));
   // 4. the rest (two parent species, unknown ids, species without a device copy): speculative pairs
   for (unsigned t = 0; t < T; t++)
     for (uint32_t i: parRest_[t]) {
@@ -1333,7 +1335,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       cudaCheck(cudaMemsetAsync(dFtCounter_.p, 0, 4, stream_), "ft counter clear");
       a.ft_list = dFtList_.p;  a.ft_counter = dFtCounter_.p;
     }
-    const char *profPath = getenv("APT_STREAM_PROF");
+    const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str();
     if (profPath) { dProf_.reserve(size_t(G) * 16); a.prof = dProf_.p; }
     cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
     launch_resolve_streams(a, stream_);
@@ -1375,7 +1377,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (P) { cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed"); timers[4] += ms; }
     if (G) {
       cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
-      if (const char *profPath = getenv("APT_STREAM_PROF")) {
+      if (const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str()) {
         // development aid: one text line per stream {launch, stream, births, kernel ms, 10 timeline words}, appended
         std::vector<unsigned long long> hp (size_t(G) * 16);
         cudaCheck(cudaMemcpy(hp.data(), dProf_.p, hp.size() * 8, cudaMemcpyDeviceToHost), "stream profile");
@@ -1460,7 +1462,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaMemcpyAsync(hSlowRows_.p, dSlowRows_.p, ns * W_ * 4, cudaMemcpyDeviceToHost, stream_), "slow rows");
     cudaCheck(cudaStreamSynchronize(stream_), "slow rows");
   }
-  const double w1 = now();
+  const double w1 = profile_ ? now() : 0.;
   size_t si = 0;
   // The leading run of births that are plain enveloppe entries of device streams touches nothing but
   // each stream's own species: worker t mirrors the entries of the streams it owns (in arrival order),
@@ -1587,10 +1589,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       counters[0]++;
       walked++;
     }
-    const double w2 = now();
+    const double w2 = profile_ ? now() : 0.;
     for (uint32_t g = 0; g < G; g++)
       if (grpSpecies_[g]->div_epoch != chunkEpoch_) settleStream(g, false, 0, nullptr);
-    if (getenv("APT_PROFILE")) fprintf(stderr, "walk: scan %.3f slow(%zu) %.3f settle %.3f ms\n", 1e3*(w1-t0), slow_.size(), 1e3*(w2-w1), 1e3*(now()-w2));
+    if (profile_) fprintf(stderr, "walk: scan %.3f slow(%zu) %.3f settle %.3f ms\n", 1e3*(w1-t0), slow_.size(), 1e3*(w2-w1), 1e3*(now()-w2));
   } catch (...) {
     // a birth failed (unknown species, :169-174): everything before it stays committed, as when the
     // reference throws out of addGenome; streams are settled up to that birth
@@ -1655,9 +1657,13 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
       if (outReplaced) outReplaced[0] = replaced;
       i0 = 1;  done = 1;  counters[0]++;
     }
-    constexpr uint32_t CHUNK = 1u << 20;
+    // Adaptive device passes.  Inside one pass the device sees the tree as it was at submission: births that
+    // fall through to sub-species founded or modified earlier in the same pass are scored on the host.  When that
+    // happens a lot (radiations, speciation stress) shorter passes are cheaper -- the next pass sees the new
+    // species on the device -- and when it does not, the whole batch is one pass.  Any cut gives the same result.
     while (i0 < n) {
-      const uint32_t m = std::min(CHUNK, n - i0);
+      const uint32_t m = std::min(adaptChunk_, n - i0);
+      const uint64_t hostScores0 = counters[3];
       refreshPool();
       runChunk(m, payload ? payload + size_t(i0) * W_ : nullptr, compat + size_t(i0) * 3,
                dPayload ? dPayload + size_t(i0) * W_ : nullptr,
@@ -1665,6 +1671,9 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
                outSid ? outSid + i0 : nullptr, outSlot ? outSlot + i0 : nullptr,
                outReplaced ? outReplaced + i0 : nullptr, done);
       i0 += m;
+      const uint64_t hostScores = counters[3] - hostScores0;
+      if (hostScores > m && m > CHUNK_MIN) adaptChunk_ = std::max(CHUNK_MIN, m / 2);
+      else if (hostScores < m / 8 && m == adaptChunk_) adaptChunk_ = std::min(CHUNK_MAX, adaptChunk_ * 2);
     }
   } catch (...) {
     if (nDone) *nDone = done;

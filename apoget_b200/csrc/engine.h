@@ -262,6 +262,10 @@ private:
   uint32_t chunkCls_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
+  static constexpr uint32_t CHUNK_MIN = 1024, CHUNK_MAX = 1u << 20;
+  uint32_t adaptChunk_ = 4096;          // births per device pass, adapted to how much of the last pass fell back to the host
+  bool profile_ = false;                // APT_PROFILE: per-phase host timings on stderr
+  std::string streamProf_;              // APT_STREAM_PROF: file the per-stream kernel timelines are appended to
   bool outPinned_ = false;              // the caller's result arrays of the current call are pinned host memory
   DevBuf<unsigned long long> dProf_;    // per-stream timelines, only with APT_STREAM_PROF=<file>
   PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
