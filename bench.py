@@ -63,58 +63,26 @@ def peaks() -> tuple[float, str]:
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons while the timed region runs: NVML every 5 ms when the
-    bindings are importable (the timed region of the default run is a fraction of a second), else nvidia-smi."""
+    """Samples SM clocks and throttle reasons with nvidia-smi, back to back, while the timed region runs.
+    (Polling NVML from inside the process instead stalled the CUDA driver: device waits of 3-50 ms.)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_ev = index, [], threading.Event()
-        self.nvml = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may renumber the devices: go through the PCI bus id of torch's device
-            import torch
-            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-            if bus is not None:
-                for i in range(pynvml.nvmlDeviceGetCount()):
-                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
-                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
-                        self.handle = h
-            self.nvml = pynvml
-        except Exception:
-            self.nvml = None
-
-    def _sample_nvml(self):
-        n = self.nvml
-        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
-            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-        bits = [getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)]
-        return [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self._stop_ev.is_set():
             try:
-                if self.nvml is not None:
-                    self.samples.append(self._sample_nvml())
-                    self._stop_ev.wait(0.005)
-                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 f = [x.strip() for x in out.stdout.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
             except Exception:
-                if self.nvml is not None:
-                    self.nvml = None        # fall back to nvidia-smi
-            self._stop_ev.wait(0.2)
+                pass
+            self._stop_ev.wait(0.02)
 
     def stop(self) -> dict:
         self._stop_ev.set()
@@ -122,9 +90,10 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         sm = sorted(float(s[0]) for s in self.samples)
-        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "samples": len(sm)}
 
 
 def run_reference_arm(trace_path: str, pop: int, warmup: int, steps: int, cref: bool = False) -> dict:
