@@ -120,7 +120,8 @@ Engine::Engine (const apt_params &p) : p_(p) {
   childKernel_ = !(p.flags & APT_FLAG_NO_CHILD_KERNEL);
   {
     unsigned hw = std::thread::hardware_concurrency();
-    unsigned nt = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);
+    // measured on a 16-core B200 host (bench.py, 100 000 births per call): 4 threads 1.19 ms/step, 8: 1.05, 12: 0.95, 16: 1.18
+    unsigned nt = hw >= 16 ? 12 : (hw >= 8 ? hw / 2 : (hw >= 4 ? 2 : 1));
     if (const char *e = getenv("APT_HOST_THREADS")) nt = unsigned(std::max(1, atoi(e)));
     if (const char *e = getenv("APT_PAR_MIN")) parMin_ = uint32_t(std::max(1, atoi(e)));
     profile_ = getenv("APT_PROFILE") != nullptr;

@@ -62,38 +62,36 @@ def peaks() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi, back to back, while the timed region runs.
-    (Polling NVML from inside the process instead stalled the CUDA driver: device waits of 3-50 ms.)"""
+class ClockSampler:
+    """SM clocks and throttle reasons during the timed region (B200_PROFILING.md's clocks line).  One nvidia-smi query
+    is made BETWEEN timed steps (after the first, the middle and the last one), not concurrently with them: any NVML
+    query that overlapped a timed call -- a polling thread, nvidia-smi -lms, in-process NVML -- stalled the CUDA
+    driver for 2-100 ms on some boxes and wrecked the step it hit."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self._stop_ev = index, [], threading.Event()
+        self.index, self.samples = index, []
 
-    def run(self):
-        while not self._stop_ev.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self._stop_ev.wait(0.02)
+    def sample(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+            f = [x.strip() for x in out.stdout.strip().split(",")]
+            if len(f) >= 6:
+                self.samples.append(f)
+        except Exception:
+            pass
 
     def stop(self) -> dict:
-        self._stop_ev.set()
-        self.join(timeout=6)
-        if not self.samples:
+        samples = self.samples
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
+        sm = sorted(float(s[0]) for s in samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "reasons": reasons, "samples": len(sm),
+                "how": "nvidia-smi between timed steps (first, middle, last)"}
 
 
 def run_reference_arm(trace_path: str, pop: int, warmup: int, steps: int, cref: bool = False) -> dict:
@@ -174,6 +172,8 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the ranks share the host: each engine gets its share of the cores for its grouping / commit workers
+        os.environ.setdefault("APT_HOST_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // world))))
 
     trace = make_trace(args.pop, n_steps, 42 + rank)
     pop, W = args.pop, trace.words
@@ -266,8 +266,11 @@ def main() -> None:
     c0, t0 = tree_h.counters(), tree_h.timers()
     cd0 = tree_d.counters()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    per_step = [timed_step(SETUP_GENS + args.warmup + k, True) for k in range(args.steps)]
+    per_step = []
+    for k in range(args.steps):
+        per_step.append(timed_step(SETUP_GENS + args.warmup + k, True))
+        if k in (0, args.steps // 2, args.steps - 1):
+            sampler.sample()
     clocks = sampler.stop()
     c1, t1 = tree_h.counters(), tree_h.timers()
     cd1 = tree_d.counters()
@@ -309,9 +312,12 @@ def main() -> None:
     d2h = pop * 4 + int(dc["stream_entries"] / args.steps) * 4 * K + int(pairs) * (4 + 4 * K)
     line = {
         "metric": METRIC, "value": births / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "ms_per_step_median": float(np.median([s["dev_ms"] for s in per_step])), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 popcount + f64 compat (bit-exact)", "data": "synthetic", "config": config,
         "e2e": {"value": births / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "ms_per_step_median": float(np.median([s["e2e_ms"] for s in per_step])),
+                "ms_per_step_all": [round(s["e2e_ms"], 4) for s in per_step],
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int((c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
