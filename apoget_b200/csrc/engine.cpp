@@ -1465,63 +1465,65 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   }
   const double w1 = profile_ ? now() : 0.;
   size_t si = 0;
-  // The leading run of births that are plain enveloppe entries of device streams touches nothing but
-  // each stream's own species: worker t mirrors the entries of the streams it owns (in arrival order),
-  // callbacks are merged back into arrival order afterwards.  Anything else (a birth rejected at top
-  // level, a two-parent birth, a stream handed back) ends the run and is committed serially below.
+  // A run of births that are plain enveloppe entries of device streams (not taken over) touches nothing
+  // but each stream's own species: worker t mirrors the entries of the streams it owns (in arrival
+  // order), callbacks are merged back into arrival order afterwards.  Anything else (a birth rejected at
+  // top level, a two-parent birth, a stream handed back) ends the run and is committed serially; the
+  // next run starts behind it.  Returns the number of births it committed from slow_[from...).
   const size_t entryParMin = std::max<size_t>(1, parMin_ / 32);
-  if (pool_ && G && slow_.size() >= entryParMin) {
+  auto parallelRun = [&] (size_t from) -> size_t {
     size_t run = 0;
-    while (run < slow_.size()) {
-      const uint32_t i = slow_[run];
+    while (from + run < slow_.size()) {
+      const uint32_t i = slow_[from + run];
       if (birthGroup_[i] < 0 || (hAct_.p[i] & (ACT_CODE_MASK | ACT_UNCERTAIN)) != ACT_ENTERED) break;
+      if (grpSpecies_[size_t(birthGroup_[i])]->div_epoch == chunkEpoch_) break;
       run++;
     }
-    if (run >= entryParMin) {
-      const unsigned T = pool_->size();
-      const bool wantEvents = !(p_.flags & APT_FLAG_NO_EVENTS);
-      struct Local { std::vector<std::pair<uint32_t, apt_event>> ev; uint64_t comparisons = 0, n = 0; std::string error; };
-      std::vector<Local> loc (T);
-      pool_->run([&] (unsigned t) {
-        Local &L = loc[t];
-        try {
-          for (size_t q = 0; q < run; q++) {
-            const uint32_t i = slow_[q];
-            const uint32_t gi = uint32_t(birthGroup_[i]);
-            if (gi % T != t) continue;
-            Species *s0 = grpSpecies_[gi];
-            if (s0->pending > 0) s0->pending--;
-            touchSnap(s0);
-            L.comparisons += s0->k;
-            RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, chunkUniform_ ? chunkCls_ : hCls_.p[i],
-                        compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
-            int32_t slot = -1;
-            uint32_t replaced = INV;
-            apt_event ev[2];
-            const int ne = mirrorEntry(payload ? payload + size_t(i) * W_ : hSlowRows_.p + q * W_, g, s0, hAct_.p[i], slot, replaced, ev);
-            if (wantEvents) for (int e = 0; e < ne; e++) L.ev.emplace_back(i, ev[e]);
-            s0->count++;  s0->alive++;  s0->last = step_;
-            if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));
-            if (outReplaced) outReplaced[i] = replaced;
-            L.n++;
-          }
-        } catch (const std::exception &e) { L.error = e.what(); }
-      });
-      for (const Local &L: loc) if (!L.error.empty()) throw ApiError(APT_ERR_STATE, L.error);
-      uint64_t total = 0;
-      for (const Local &L: loc) { comparisons_ += uint32_t(L.comparisons); total += L.n; }
-      insertions_ += uint32_t(total);
-      counters[0] += total;  counters[1] += total;  counters[14] += total;
-      if (wantEvents) {
-        // per-worker lists are ascending by birth; a birth's events sit in one list, in order
-        std::vector<std::pair<uint32_t, apt_event>> all;
-        for (Local &L: loc) all.insert(all.end(), L.ev.begin(), L.ev.end());
-        std::stable_sort(all.begin(), all.end(), [] (const auto &a, const auto &b) { return a.first < b.first; });
-        for (const auto &e: all) events_.push_back(e.second);
-      }
-      si = run;
+    if (run < entryParMin) return 0;
+    const unsigned T = pool_->size();
+    const bool wantEvents = !(p_.flags & APT_FLAG_NO_EVENTS);
+    struct Local { std::vector<std::pair<uint32_t, apt_event>> ev; uint64_t comparisons = 0, n = 0; std::string error; };
+    std::vector<Local> loc (T);
+    pool_->run([&] (unsigned t) {
+      Local &L = loc[t];
+      try {
+        for (size_t q = from; q < from + run; q++) {
+          const uint32_t i = slow_[q];
+          const uint32_t gi = uint32_t(birthGroup_[i]);
+          if (gi % T != t) continue;
+          Species *s0 = grpSpecies_[gi];
+          if (s0->pending > 0) s0->pending--;
+          touchSnap(s0);
+          L.comparisons += s0->k;
+          RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, chunkUniform_ ? chunkCls_ : hCls_.p[i],
+                      compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
+          int32_t slot = -1;
+          uint32_t replaced = INV;
+          apt_event ev[2];
+          const int ne = mirrorEntry(payload ? payload + size_t(i) * W_ : hSlowRows_.p + q * W_, g, s0, hAct_.p[i], slot, replaced, ev);
+          if (wantEvents) for (int e = 0; e < ne; e++) L.ev.emplace_back(i, ev[e]);
+          s0->count++;  s0->alive++;  s0->last = step_;
+          if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));
+          if (outReplaced) outReplaced[i] = replaced;
+          L.n++;
+        }
+      } catch (const std::exception &e) { L.error = e.what(); }
+    });
+    for (const Local &L: loc) if (!L.error.empty()) throw ApiError(APT_ERR_STATE, L.error);
+    uint64_t total = 0;
+    for (const Local &L: loc) { comparisons_ += uint32_t(L.comparisons); total += L.n; }
+    insertions_ += uint32_t(total);
+    counters[0] += total;  counters[1] += total;  counters[14] += total;
+    if (wantEvents) {
+      // per-worker lists are ascending by birth; a birth's events sit in one list, in order
+      std::vector<std::pair<uint32_t, apt_event>> all;
+      for (Local &L: loc) all.insert(all.end(), L.ev.begin(), L.ev.end());
+      std::stable_sort(all.begin(), all.end(), [] (const auto &a, const auto &b) { return a.first < b.first; });
+      for (const auto &e: all) events_.push_back(e.second);
     }
-  }
+    return run;
+  };
+  size_t nextTry = 0;                 // first position from which a parallel run is worth looking for again
   std::vector<uint32_t> heap;       // births handed back by a taken-over stream (min-heap)
   auto heapCmp = [] (uint32_t a, uint32_t b) { return a > b; };
   uint32_t walked = 0;
@@ -1529,6 +1531,11 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     for (;;) {
       for (uint32_t b: requeue_) { heap.push_back(b); std::push_heap(heap.begin(), heap.end(), heapCmp); }
       requeue_.clear();
+      if (pool_ && G && heap.empty() && si >= nextTry && slow_.size() - si >= entryParMin) {
+        const size_t done = parallelRun(si);
+        if (done) { si += done; continue; }
+        nextTry = si + entryParMin / 4 + 1;         // a short run: do not rescan at every birth
+      }
       uint32_t i;
       if (!heap.empty() && (si >= slow_.size() || heap.front() < slow_[si])) {
         std::pop_heap(heap.begin(), heap.end(), heapCmp);

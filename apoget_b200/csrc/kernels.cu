@@ -13,6 +13,8 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace apt {
 
 namespace {
@@ -130,24 +132,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 classify_children_kernel (ChildArgs a) {
   __shared__ double c_smem[WARPS_PER_CTA][KMAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t e = blockIdx.x * WARPS_PER_CTA + warp;
-  if (e >= min(__ldg(a.ft_counter), a.max_ft)) return;
-  const uint32_t b = __ldg(a.ft_list + 2 * e), g = __ldg(a.ft_list + 2 * e + 1);
-  const uint32_t c0 = __ldg(a.child_off + g), c1 = __ldg(a.child_off + g + 1);
-  const uint4 *bq = reinterpret_cast<const uint4*>(a.b_payload) + size_t(b) * (a.pool.wp >> 2);
-  const float4 bm = __ldg(a.b_cmeta + b);
-  float *od = a.out_dist + size_t(e) * a.pool.K;
-  uint32_t first = 0xFFFFFFFFu, flags = 0;
-  float score = 0.f;
-  for (uint32_t c = c0; c < c1; c++) {
-    const uint32_t slot = __ldg(a.child_slot + c);
-    if (slot == 0xFFFFFFFFu) { first = c - c0; flags = 1u; break; }          // the host knows this one only
-    score = warp_score<LPR, KIND, LUT>(a.pool, a.cfg, bq, bm, slot, c_smem[warp], od, lane);
-    const bool unsure = !LUT && (fabsf(score) <= a.guard || !a.cfg.full_continuous);
-    if (unsure) { first = c - c0; flags = 1u; break; }
-    if (score > 0.f) { first = c - c0; break; }                              // :540-541
+  // the number of rejected births is only known on the device: a bounded grid strides over the list
+  const uint32_t nft = min(__ldg(a.ft_counter), a.max_ft);
+  for (uint32_t e = blockIdx.x * WARPS_PER_CTA + warp; e < nft; e += gridDim.x * WARPS_PER_CTA) {
+    const uint32_t b = __ldg(a.ft_list + 2 * e), g = __ldg(a.ft_list + 2 * e + 1);
+    const uint32_t c0 = __ldg(a.child_off + g), c1 = __ldg(a.child_off + g + 1);
+    const uint4 *bq = reinterpret_cast<const uint4*>(a.b_payload) + size_t(b) * (a.pool.wp >> 2);
+    const float4 bm = __ldg(a.b_cmeta + b);
+    float *od = a.out_dist + size_t(e) * a.pool.K;
+    uint32_t first = 0xFFFFFFFFu, flags = 0;
+    float score = 0.f;
+    for (uint32_t c = c0; c < c1; c++) {
+      const uint32_t slot = __ldg(a.child_slot + c);
+      if (slot == 0xFFFFFFFFu) { first = c - c0; flags = 1u; break; }          // the host knows this one only
+      score = warp_score<LPR, KIND, LUT>(a.pool, a.cfg, bq, bm, slot, c_smem[warp], od, lane);
+      const bool unsure = !LUT && (fabsf(score) <= a.guard || !a.cfg.full_continuous);
+      if (unsure) { first = c - c0; flags = 1u; break; }
+      if (score > 0.f) { first = c - c0; break; }                              // :540-541
+    }
+    if (lane == 0) { a.out_first[e] = first;  a.out_flags[e] = flags;  a.out_score[e] = score; }
+    __syncwarp();
   }
-  if (lane == 0) { a.out_first[e] = first;  a.out_flags[e] = flags;  a.out_score[e] = score; }
 }
 
 /// Dense sweep, first version: one warp per birth walking every slot of the pool.
@@ -342,7 +347,8 @@ struct ScorePairsLauncher {
 template <int LPR, int KIND, bool LUT>
 struct ChildrenLauncher {
   static void run (const ChildArgs &a, cudaStream_t st) {
-    const uint32_t grid = (a.max_ft + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    // at most 8 CTAs per SM of a B200: an empty list (the common case) costs one small launch, not max_ft warps
+    const uint32_t grid = std::min<uint32_t>((a.max_ft + WARPS_PER_CTA - 1) / WARPS_PER_CTA, 148u * 8u);
     classify_children_kernel<LPR, KIND, LUT><<<grid, WARPS_PER_CTA * 32, 0, st>>>(a);
   }
 };

@@ -41,6 +41,7 @@ if ROOT not in sys.path:
 
 from apoget_b200 import synth  # noqa: E402
 
+EPOCH_STEPS = 5         # timed generations per simulation (the steady window, see main)
 SETUP_GENS = 4          # generations 0..3: root + three 10-way radiations -> 1 000 species (+111 ancestors)
 WORKLOAD = dict(kind=synth.BITS, words=8, flips=0.5, sigma=12.0, hybrid=0.05, burst_levels=3, burst_fanout=10)
 TREE_CFG = dict(K=10)
@@ -137,6 +138,8 @@ def main() -> None:
     config = {"workload": "C2: 256-bit Hamming genomes, 100k births/step, ~1k species x enveloppe K=10 "
                           "(candidate mode, reference-exact sequential semantics)",
               "births_per_step": args.pop, "species": "1000 live (+111 ancestors)", "K": TREE_CFG["K"],
+              "window": f"steady regime: generations 7-11 of each simulation ({EPOCH_STEPS} timed steps per simulation, seeds 42 + 1000 e); "
+                        "the speciation that sets in from generation 12 on is configs[4] (tools/bench_trace.py)",
               "genome_bits": 256, "seed": 42, "l2": "payload+outputs of each step are new data (never re-read); "
               "256 MiB L2 flush between timed steps", "parallelism": f"replicas x{world}" if world > 1 else "single GPU"}
 
@@ -144,11 +147,19 @@ def main() -> None:
     if args.impl == "reference":
         if rank != 0:
             return
-        trace = make_trace(args.pop, n_steps, 42)
-        path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
-        synth.write_trace(path, trace)
         t0 = time.time()
-        r = run_reference_arm(path, args.pop, args.warmup, args.steps)
+        r = None
+        for e in range((args.steps + EPOCH_STEPS - 1) // EPOCH_STEPS):          # the same simulations as our arm
+            n_warm, n_timed = (args.warmup if e == 0 else 3), min(EPOCH_STEPS, args.steps - e * EPOCH_STEPS)
+            trace = make_trace(args.pop, n_warm + n_timed, 42 + 1000 * e)
+            path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
+            synth.write_trace(path, trace)
+            re = run_reference_arm(path, args.pop, n_warm, n_timed)
+            if r is None:
+                r = re
+            else:
+                r["seconds"] += re["seconds"];  r["gens_timed"] += re["gens_timed"];  r["comparisons"] += re["comparisons"]
+        r["value"] = args.pop * r["gens_timed"] / r["seconds"]
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, r["gens_timed"]),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount + f64 compat",
@@ -175,105 +186,133 @@ def main() -> None:
         # the ranks share the host: each engine gets its share of the cores for its grouping / commit workers
         os.environ.setdefault("APT_HOST_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // world))))
 
-    trace = make_trace(args.pop, n_steps, 42 + rank)
-    pop, W = args.pop, trace.words
-    B = trace.n_births
-
-    def fresh_tree():
-        t = PhylogeneticTree(trace.kind, W, device=local_rank, flags=FLAG_NO_EVENTS, **TREE_CFG)
-        sid_of = np.full(B, INVALID, dtype=np.uint32)
-        return t, sid_of
-
-    def ids_for(g, sid_of):
-        b0, b1 = g * pop, (g + 1) * pop
-        m, f = trace.mother[b0:b1], trace.father[b0:b1]
-        hm, hf = m != INVALID, f != INVALID
-        return [np.arange(b0 + 1, b1 + 1, dtype=np.uint32),
-                np.where(hm, m + 1, INVALID).astype(np.uint32),
-                np.where(hm, sid_of[np.where(hm, m, 0)], INVALID).astype(np.uint32),
-                np.where(hf, f + 1, INVALID).astype(np.uint32),
-                np.where(hf, sid_of[np.where(hf, f, 0)], INVALID).astype(np.uint32)]
-
-    def finish_gen(t, g, sid_of):
-        t.del_genomes(sid_of[trace.deaths_of(g)])
-        t.step(g + 1, sid_of[trace.alive_of(g)])
-
-    tree_h, sid_h = fresh_tree()       # fed from pinned host memory (e2e)
-    tree_d, sid_d = fresh_tree()       # fed from device-resident payloads (value)
-
-    # untimed setup: grow both trees through the radiation generations (same product path)
-    for g in range(SETUP_GENS):
-        for t, sid_of in ((tree_h, sid_h), (tree_d, sid_d)):
-            b0, b1 = g * pop, (g + 1) * pop
-            s, _, _ = t.add_genomes(trace.payload[b0:b1], trace.compat[b0:b1], *ids_for(g, sid_of))
-            sid_of[b0:b1] = s
-            finish_gen(t, g, sid_of)
-
-    pin_payload = torch.empty((pop, W), dtype=torch.int32).pin_memory()
-    pin_compat = torch.empty((pop, 3), dtype=torch.float32).pin_memory()
-    pin_sid = torch.empty(pop, dtype=torch.int32).pin_memory()
-    pin_slot = torch.empty(pop, dtype=torch.int32).pin_memory()
-    pin_rep = torch.empty(pop, dtype=torch.int32).pin_memory()
-    dev_payload = torch.empty((pop, W), dtype=torch.int32, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    vp = ctypes.c_void_p
-    stream = torch.cuda.current_stream()
-
-    def timed_step(g, timed):
-        b0, b1 = g * pop, (g + 1) * pop
-        out = {}
-        # --- e2e: host buffers through the public C ABI -------------------------------------------
-        pin_payload.numpy()[:] = trace.payload[b0:b1].view(np.int32)
-        pin_compat.numpy()[:] = trace.compat[b0:b1]
-        ids = ids_for(g, sid_h)
-        flush.fill_(g & 0xFF)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        tree_h.add_genomes_raw(pop, vp(pin_payload.data_ptr()), vp(pin_compat.data_ptr()),
-                               [vp(x.ctypes.data) for x in ids],
-                               vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
-        e1.record(stream)
-        torch.cuda.synchronize()
-        out["e2e_ms"] = e0.elapsed_time(e1)
-        sid_h[b0:b1] = pin_sid.numpy().view(np.uint32)
-        finish_gen(tree_h, g, sid_h)
-        # --- value: payloads already resident in HBM ------------------------------------------------
-        dev_payload.copy_(pin_payload, non_blocking=True)
-        ids = ids_for(g, sid_d)
-        flush.fill_((g + 1) & 0xFF)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(stream)
-        tree_d.add_genomes_dev(pop, vp(dev_payload.data_ptr()), vp(pin_compat.data_ptr()), vp(stream.cuda_stream),
-                               [vp(x.ctypes.data) for x in ids],
-                               vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
-        d1.record(stream)
-        torch.cuda.synchronize()
-        out["dev_ms"] = d0.elapsed_time(d1)
-        sid_d[b0:b1] = pin_sid.numpy().view(np.uint32)
-        finish_gen(tree_d, g, sid_d)
-        assert np.array_equal(sid_h[b0:b1], sid_d[b0:b1]), "host-fed and device-fed trees diverged"
-        return out
-
-    for w in range(args.warmup):
-        timed_step(SETUP_GENS + w, False)
-
-    c0, t0 = tree_h.counters(), tree_h.timers()
-    cd0 = tree_d.counters()
+    # The workload is the STEADY regime of the simulation: generations 7..11 (after 4 set-up and 3 warm-up
+    # generations), where ~1 000 species take 100 000 births each step.  Left running, the drifting population
+    # starts to speciate from generation 12 on -- that is BASELINE.json's configs[4], measured by
+    # tools/bench_trace.py, not this metric -- so more than EPOCH_STEPS timed steps are taken from further
+    # simulations (seeds 42 + 1000 e), each grown through its own untimed set-up and warm-up generations.
+    pop, W = args.pop, 8
+    dc, dt, launches, per_step = {}, {}, [0], []
     sampler = ClockSampler(local_rank)
-    per_step = []
-    for k in range(args.steps):
-        per_step.append(timed_step(SETUP_GENS + args.warmup + k, True))
-        if k in (0, args.steps // 2, args.steps - 1):
-            sampler.sample()
+
+    def run_epoch(e, n_warm, n_timed):
+        trace = make_trace(args.pop, n_warm + n_timed, 42 + rank + 1000 * e)
+        B = trace.n_births
+
+        def fresh_tree():
+            t = PhylogeneticTree(trace.kind, W, device=local_rank, flags=FLAG_NO_EVENTS, **TREE_CFG)
+            sid_of = np.full(B, INVALID, dtype=np.uint32)
+            return t, sid_of
+
+        def ids_for(g, sid_of):
+            b0, b1 = g * pop, (g + 1) * pop
+            m, f = trace.mother[b0:b1], trace.father[b0:b1]
+            hm, hf = m != INVALID, f != INVALID
+            return [np.arange(b0 + 1, b1 + 1, dtype=np.uint32),
+                    np.where(hm, m + 1, INVALID).astype(np.uint32),
+                    np.where(hm, sid_of[np.where(hm, m, 0)], INVALID).astype(np.uint32),
+                    np.where(hf, f + 1, INVALID).astype(np.uint32),
+                    np.where(hf, sid_of[np.where(hf, f, 0)], INVALID).astype(np.uint32)]
+
+        def finish_gen(t, g, sid_of):
+            t.del_genomes(sid_of[trace.deaths_of(g)])
+            t.step(g + 1, sid_of[trace.alive_of(g)])
+
+        tree_h, sid_h = fresh_tree()       # fed from pinned host memory (e2e)
+        tree_d, sid_d = fresh_tree()       # fed from device-resident payloads (value)
+
+        # untimed setup: grow both trees through the radiation generations (same product path)
+        for g in range(SETUP_GENS):
+            for t, sid_of in ((tree_h, sid_h), (tree_d, sid_d)):
+                b0, b1 = g * pop, (g + 1) * pop
+                s, _, _ = t.add_genomes(trace.payload[b0:b1], trace.compat[b0:b1], *ids_for(g, sid_of))
+                sid_of[b0:b1] = s
+                finish_gen(t, g, sid_of)
+
+        pin_payload = torch.empty((pop, W), dtype=torch.int32).pin_memory()
+        pin_compat = torch.empty((pop, 3), dtype=torch.float32).pin_memory()
+        pin_sid = torch.empty(pop, dtype=torch.int32).pin_memory()
+        pin_slot = torch.empty(pop, dtype=torch.int32).pin_memory()
+        pin_rep = torch.empty(pop, dtype=torch.int32).pin_memory()
+        dev_payload = torch.empty((pop, W), dtype=torch.int32, device="cuda")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        vp = ctypes.c_void_p
+        stream = torch.cuda.current_stream()
+
+        def timed_step(g, timed):
+            b0, b1 = g * pop, (g + 1) * pop
+            out = {}
+            # --- e2e: host buffers through the public C ABI -------------------------------------------
+            pin_payload.numpy()[:] = trace.payload[b0:b1].view(np.int32)
+            pin_compat.numpy()[:] = trace.compat[b0:b1]
+            ids = ids_for(g, sid_h)
+            flush.fill_(g & 0xFF)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tm0, cn0 = tree_h.timers(), tree_h.counters()
+            e0.record(stream)
+            tree_h.add_genomes_raw(pop, vp(pin_payload.data_ptr()), vp(pin_compat.data_ptr()),
+                                   [vp(x.ctypes.data) for x in ids],
+                                   vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            out["e2e_ms"] = e0.elapsed_time(e1)
+            tm1, cn1 = tree_h.timers(), tree_h.counters()
+            out["host"] = [round(1e3 * (tm1[k] - tm0[k]), 3) for k in ("prepare_s", "device_s", "walk_s", "refresh_s")] + \
+                          [round(tm1["stream_kernel_ms"] - tm0["stream_kernel_ms"], 3), cn1["kernel_launches"] - cn0["kernel_launches"],
+                           cn1["host_scores"] - cn0["host_scores"], cn1["stream_launches"] - cn0["stream_launches"]]
+            sid_h[b0:b1] = pin_sid.numpy().view(np.uint32)
+            finish_gen(tree_h, g, sid_h)
+            # --- value: payloads already resident in HBM ------------------------------------------------
+            dev_payload.copy_(pin_payload, non_blocking=True)
+            ids = ids_for(g, sid_d)
+            flush.fill_((g + 1) & 0xFF)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record(stream)
+            tree_d.add_genomes_dev(pop, vp(dev_payload.data_ptr()), vp(pin_compat.data_ptr()), vp(stream.cuda_stream),
+                                   [vp(x.ctypes.data) for x in ids],
+                                   vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
+            d1.record(stream)
+            torch.cuda.synchronize()
+            out["dev_ms"] = d0.elapsed_time(d1)
+            sid_d[b0:b1] = pin_sid.numpy().view(np.uint32)
+            finish_gen(tree_d, g, sid_d)
+            assert np.array_equal(sid_h[b0:b1], sid_d[b0:b1]), "host-fed and device-fed trees diverged"
+            return out
+
+        for w in range(n_warm):
+            timed_step(SETUP_GENS + w, False)
+
+        c0, t0 = tree_h.counters(), tree_h.timers()
+        cd0 = tree_d.counters()
+        steps_here = []
+        for k in range(n_timed):
+            steps_here.append(timed_step(SETUP_GENS + n_warm + k, True))
+            if len(per_step) + len(steps_here) in (1, args.steps // 2 + 1, args.steps):
+                sampler.sample()
+        c1, t1 = tree_h.counters(), tree_h.timers()
+        cd1 = tree_d.counters()
+        for k in c1:
+            dc[k] = dc.get(k, 0) + c1[k] - c0[k]
+        for k in t1:
+            dt[k] = dt.get(k, 0.0) + t1[k] - t0[k]
+        launches[0] += (c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])
+        per_step.extend(steps_here)
+        return trace, tree_h.stats()["width"]
+
+
+    trace, width = None, 0
+    for e in range((args.steps + EPOCH_STEPS - 1) // EPOCH_STEPS):
+        n_timed = min(EPOCH_STEPS, args.steps - e * EPOCH_STEPS)
+        tr, width = run_epoch(e, args.warmup if e == 0 else 3, n_timed)
+        if e == 0:
+            trace = tr
     clocks = sampler.stop()
-    c1, t1 = tree_h.counters(), tree_h.timers()
-    cd1 = tree_d.counters()
 
     e2e_ms = sum(s["e2e_ms"] for s in per_step)
     dev_ms = sum(s["dev_ms"] for s in per_step)
@@ -284,11 +323,10 @@ def main() -> None:
     births = pop * args.steps * world
 
     # ---- roofline of the dominant kernel, timed by the engine's own CUDA events on its stream ------
-    dc = {k: c1[k] - c0[k] for k in c1}
     G = 4 * W
     K = TREE_CFG["K"]
     peak, peak_src = peaks()
-    stream_ms, score_ms = t1["stream_kernel_ms"] - t0["stream_kernel_ms"], t1["score_kernel_ms"] - t0["score_kernel_ms"]
+    stream_ms, score_ms = dt["stream_kernel_ms"], dt["score_kernel_ms"]
     pairs = dc["device_pairs"] / max(1, dc["score_launches"])
     if stream_ms >= score_ms:
         kname, launches = "resolve_streams_kernel", max(1, dc["stream_launches"])
@@ -318,8 +356,11 @@ def main() -> None:
         "e2e": {"value": births / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "ms_per_step_median": float(np.median([s["e2e_ms"] for s in per_step])),
                 "ms_per_step_all": [round(s["e2e_ms"], 4) for s in per_step],
+                "per_step_host": {"columns": ["prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms", "stream_kernel_ms",
+                                              "kernel_launches", "host_scores", "device_passes"],
+                                  "rows": [s["host"] for s in per_step]},
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int((c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])),
+        "gpu_launches": int(launches[0]),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC.get(kname), "peak_source": peak_src,
                      "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
@@ -327,14 +368,14 @@ def main() -> None:
                      "births_per_s_kernel": units / (kernel_ms * 1e-3) if kernel_ms else 0},
         "clocks": clocks,
         "breakdown_e2e_ms_per_step": {
-            "prepare": 1e3 * (t1["prepare_s"] - t0["prepare_s"]) / args.steps,
-            "device_wait": 1e3 * (t1["device_s"] - t0["device_s"]) / args.steps,
-            "ordered_resolution": 1e3 * (t1["walk_s"] - t0["walk_s"]) / args.steps,
-            "pool_refresh": 1e3 * (t1["refresh_s"] - t0["refresh_s"]) / args.steps},
+            "prepare": 1e3 * dt["prepare_s"] / args.steps,
+            "device_wait": 1e3 * dt["device_s"] / args.steps,
+            "ordered_resolution": 1e3 * dt["walk_s"] / args.steps,
+            "pool_refresh": 1e3 * dt["refresh_s"] / args.steps},
         "resolution": {k: dc[k] / args.steps for k in ("device_scores", "patched_scores", "host_scores",
                                                          "host_distance_evals", "guard_rechecks", "stream_births",
                                                          "stream_entries", "streams_taken_over")},
-        "species": tree_h.stats()["width"],
+        "species": width,
     }
 
     if rank == 0 and world == 1 and not args.no_dense:
@@ -358,8 +399,8 @@ def main() -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
         synth.write_trace(path, trace)
-        n = max(1, min(args.cpu_sample_steps, args.steps))
-        r = run_reference_arm(path, pop, args.warmup, n)
+        n = max(1, min(args.cpu_sample_steps, args.steps, EPOCH_STEPS))
+        r = run_reference_arm(path, pop, args.warmup, n)         # `trace` = the first simulation (seed 42)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
                                 "sample": f"first {n} timed steps ({n * pop} births) of the same trace after the same "
                                           f"{SETUP_GENS}+{args.warmup} untimed generations; addGenome loop only; "
