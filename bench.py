@@ -192,7 +192,7 @@ def main() -> None:
     # tools/bench_trace.py, not this metric -- so more than EPOCH_STEPS timed steps are taken from further
     # simulations (seeds 42 + 1000 e), each grown through its own untimed set-up and warm-up generations.
     pop, W = args.pop, 8
-    dc, dt, launches, per_step = {}, {}, [0], []
+    dc, dt, n_launches, per_step = {}, {}, [0], []
     sampler = ClockSampler(local_rank)
 
     def run_epoch(e, n_warm, n_timed):
@@ -301,7 +301,7 @@ def main() -> None:
             dc[k] = dc.get(k, 0) + c1[k] - c0[k]
         for k in t1:
             dt[k] = dt.get(k, 0.0) + t1[k] - t0[k]
-        launches[0] += (c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])
+        n_launches[0] += (c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])
         per_step.extend(steps_here)
         return trace, tree_h.stats()["width"]
 
@@ -360,7 +360,7 @@ def main() -> None:
                                               "kernel_launches", "host_scores", "device_passes"],
                                   "rows": [s["host"] for s in per_step]},
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches[0]),
+        "gpu_launches": int(n_launches[0]),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC.get(kname), "peak_source": peak_src,
                      "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
