@@ -903,11 +903,21 @@ void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t ac
   insertions_++;
 }
 
+/// Device-resident births: genome of a birth the stream kernel put into an enveloppe (it came back with the
+/// birth's distance row), or null when the birth is not such an entry
+const uint32_t* Engine::entryRowOf (uint32_t i) const {
+  if (birthGroup_[i] < 0) return nullptr;
+  const uint32_t act = hAct_.p[i];
+  if ((act & (ACT_CODE_MASK | ACT_UNCERTAIN)) != ACT_ENTERED) return nullptr;
+  return hRowPayload_.p + size_t(act >> ACT_ROW_SHIFT) * wp_;
+}
+
 /// Payload of birth i of the current chunk as the host sees it
 const uint32_t* Engine::payloadOf (uint32_t i) {
   if (curPayload_) return curPayload_ + size_t(i) * W_;
-  auto it = std::lower_bound(slow_.begin(), slow_.end(), i);
-  if (it != slow_.end() && *it == i) return hSlowRows_.p + size_t(it - slow_.begin()) * W_;
+  if (const uint32_t *w = entryRowOf(i)) return w;
+  auto it = std::lower_bound(gatherIdx_.begin(), gatherIdx_.end(), i);
+  if (it != gatherIdx_.end() && *it == i) return hSlowRows_.p + size_t(it - gatherIdx_.begin()) * W_;
   // a birth handed back by a taken-over stream: fetched on demand
   lateRows_.emplace_back(W_);
   cudaCheck(cudaMemcpy(lateRows_.back().data(), curDevPayload_ + size_t(i) * W_, W_ * 4, cudaMemcpyDeviceToHost), "late row");
@@ -1329,6 +1339,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.b_payload = dBirthRows;  a.b_cmeta = dBMeta_.p;
     a.n_groups = G;  a.max_stream = maxStream;  a.grp_slot = dGrpSlot_.p;  a.grp_off = dGrpOff_.p;  a.order = dOrder_.p;
     a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dRowCounter_.p;
+    a.row_payload = nullptr;
+    if (!payload) { dRowPayload_.reserve(size_t(nStream) * wp_ + 4); a.row_payload = dRowPayload_.p; }
     a.grp_sid = dGrpSid_.p;  a.out_sid = dOutSid_.p;  a.out_slot = dOutSlot_.p;  a.grp_sum = dGrpSum_.p;
     a.ft_list = nullptr;  a.ft_counter = nullptr;
     if (useChildKernel) {
@@ -1396,6 +1408,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       if (nRows) {
         hRows_.reserve(size_t(nRows) * K_);
         cudaCheck(cudaMemcpyAsync(hRows_.p, dRows_.p, size_t(nRows) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "rows");
+        if (!payload) {
+          hRowPayload_.reserve(size_t(nRows) * wp_);
+          cudaCheck(cudaMemcpyAsync(hRowPayload_.p, dRowPayload_.p, size_t(nRows) * wp_ * 4, cudaMemcpyDeviceToHost, stream_), "row genomes");
+        }
       }
       if (nFt_) {
         hFtList_.reserve(2 * size_t(nFt_));  hFtFirst_.reserve(nFt_);  hFtFlags_.reserve(nFt_);
@@ -1452,16 +1468,22 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   }
   curDevPayload_ = payload ? nullptr : dPayload;
   lateRows_.clear();
+  gatherIdx_.clear();
   if (!payload && !slow_.empty()) {
-    // device-resident births: only the births the host has to look at are fetched (gathered on the device)
-    const size_t ns = slow_.size();
-    hSlowIdx_.reserve(ns);  dSlowIdx_.reserve(ns);  dSlowRows_.reserve(ns * W_);  hSlowRows_.reserve(ns * W_);
-    memcpy(hSlowIdx_.p, slow_.data(), ns * 4);
-    cudaCheck(cudaMemcpyAsync(dSlowIdx_.p, hSlowIdx_.p, ns * 4, cudaMemcpyHostToDevice, stream_), "slow list");
-    launch_gather_rows(dPayload, dSlowIdx_.p, uint32_t(ns), W_, dSlowRows_.p, stream_);
-    counters[4]++;
-    cudaCheck(cudaMemcpyAsync(hSlowRows_.p, dSlowRows_.p, ns * W_ * 4, cudaMemcpyDeviceToHost, stream_), "slow rows");
-    cudaCheck(cudaStreamSynchronize(stream_), "slow rows");
+    // device-resident births: the genomes of the births that entered an enveloppe came back with their distance
+    // rows; the other births the host has to look at (rejected at top level, two parents, handed back) are
+    // gathered on the device and fetched
+    for (uint32_t i: slow_) if (!entryRowOf(i)) gatherIdx_.push_back(i);
+    const size_t ns = gatherIdx_.size();
+    if (ns) {
+      hSlowIdx_.reserve(ns);  dSlowIdx_.reserve(ns);  dSlowRows_.reserve(ns * W_);  hSlowRows_.reserve(ns * W_);
+      memcpy(hSlowIdx_.p, gatherIdx_.data(), ns * 4);
+      cudaCheck(cudaMemcpyAsync(dSlowIdx_.p, hSlowIdx_.p, ns * 4, cudaMemcpyHostToDevice, stream_), "slow list");
+      launch_gather_rows(dPayload, dSlowIdx_.p, uint32_t(ns), W_, dSlowRows_.p, stream_);
+      counters[4]++;
+      cudaCheck(cudaMemcpyAsync(hSlowRows_.p, dSlowRows_.p, ns * W_ * 4, cudaMemcpyDeviceToHost, stream_), "slow rows");
+      cudaCheck(cudaStreamSynchronize(stream_), "slow rows");
+    }
   }
   const double w1 = profile_ ? now() : 0.;
   size_t si = 0;
@@ -1500,7 +1522,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           int32_t slot = -1;
           uint32_t replaced = INV;
           apt_event ev[2];
-          const int ne = mirrorEntry(payload ? payload + size_t(i) * W_ : hSlowRows_.p + q * W_, g, s0, hAct_.p[i], slot, replaced, ev);
+          const int ne = mirrorEntry(payload ? payload + size_t(i) * W_ : entryRowOf(i), g, s0, hAct_.p[i], slot, replaced, ev);
           if (wantEvents) for (int e = 0; e < ne; e++) L.ev.emplace_back(i, ev[e]);
           s0->count++;  s0->alive++;  s0->last = step_;
           if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));

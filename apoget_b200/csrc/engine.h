@@ -248,7 +248,8 @@ private:
   std::vector<uint32_t> slow_, requeue_;  // births the host has to look at (ascending) / handed back by a taken-over stream
   uint32_t curBirth_ = 0;                 // index (in the chunk) of the birth being committed
   const uint32_t *curDevPayload_ = nullptr;
-  DevBuf<uint32_t> dSlowIdx_, dSlowRows_;  PinBuf<uint32_t> hSlowIdx_, hSlowRows_;
+  DevBuf<uint32_t> dSlowIdx_, dSlowRows_, dRowPayload_;  PinBuf<uint32_t> hSlowIdx_, hSlowRows_, hRowPayload_;
+  std::vector<uint32_t> gatherIdx_;     // births of the chunk whose genomes were gathered into hSlowRows_ (ascending)
   std::vector<std::vector<uint32_t>> lateRows_;
   // sub-species kernel (K2)
   bool childKernel_ = true;
@@ -323,6 +324,7 @@ private:
   PoolView poolView (void) const;
   ScoreCfg scoreCfg (void) const;
   const uint32_t* payloadOf (uint32_t i);
+  const uint32_t* entryRowOf (uint32_t i) const;
   void runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
                  const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                  const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,

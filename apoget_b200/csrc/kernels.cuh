@@ -110,6 +110,7 @@ struct StreamArgs {
   uint4 *grp_sum;             ///< [n_groups] {accepted-unchanged births contributing 0, 1, 2; stopped early}
   uint32_t *act;              ///< [n_births] result words (zero-initialised by the caller)
   float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
+  uint32_t *row_payload;      ///< [n_rows][wp] their genomes (device-resident births: what the host mirrors), or null
   uint32_t *ft_list;          ///< births rejected at top level, appended as (birth, stream) pairs ...
   uint32_t *ft_counter;       ///< ... counted here (zero-initialised)
   uint32_t *row_counter;      ///< zero-initialised; a stream claims the rows of a step (its enveloppe entries) with one add

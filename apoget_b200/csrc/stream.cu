@@ -475,6 +475,11 @@ resolve_streams_kernel (StreamArgs a) {
       if (code == ACT_ENTERED) {
         myAct |= (rowBase + myEv) << ACT_ROW_SHIFT;
         a.out_slot[b] = int32_t((myAct >> ACT_SLOT_SHIFT) & 31u);
+        if (a.row_payload) {          // device-resident births: the host mirrors the new representative from here
+          uint4 *dst = reinterpret_cast<uint4*>(a.row_payload) + size_t(rowBase + myEv) * WQ;
+#pragma unroll
+          for (int v = 0; v < WQ; v++) dst[v] = bw[v];
+        }
       }
       if (code == ACT_ENTERED || code == ACT_ACCEPTED) a.out_sid[b] = sid;
       if (code == ACT_ACCEPTED) { nAcc0 += (ccls == 0); nAcc1 += (ccls == 1); nAcc2 += (ccls == 2); }

@@ -192,7 +192,7 @@ def main() -> None:
     # tools/bench_trace.py, not this metric -- so more than EPOCH_STEPS timed steps are taken from further
     # simulations (seeds 42 + 1000 e), each grown through its own untimed set-up and warm-up generations.
     pop, W = args.pop, 8
-    dc, dt, n_launches, per_step = {}, {}, [0], []
+    dc, dt, dtd, n_launches, per_step = {}, {}, {}, [0], []
     sampler = ClockSampler(local_rank)
 
     def run_epoch(e, n_warm, n_timed):
@@ -289,14 +289,16 @@ def main() -> None:
             timed_step(SETUP_GENS + w, False)
 
         c0, t0 = tree_h.counters(), tree_h.timers()
-        cd0 = tree_d.counters()
+        cd0, td0 = tree_d.counters(), tree_d.timers()
         steps_here = []
         for k in range(n_timed):
             steps_here.append(timed_step(SETUP_GENS + n_warm + k, True))
             if len(per_step) + len(steps_here) in (1, args.steps // 2 + 1, args.steps):
                 sampler.sample()
         c1, t1 = tree_h.counters(), tree_h.timers()
-        cd1 = tree_d.counters()
+        cd1, td1 = tree_d.counters(), tree_d.timers()
+        for k in td1:
+            dtd[k] = dtd.get(k, 0.0) + td1[k] - td0[k]
         for k in c1:
             dc[k] = dc.get(k, 0) + c1[k] - c0[k]
         for k in t1:
@@ -372,6 +374,9 @@ def main() -> None:
             "device_wait": 1e3 * dt["device_s"] / args.steps,
             "ordered_resolution": 1e3 * dt["walk_s"] / args.steps,
             "pool_refresh": 1e3 * dt["refresh_s"] / args.steps},
+        "breakdown_resident_ms_per_step": {
+            "prepare": 1e3 * dtd["prepare_s"] / args.steps, "device_wait": 1e3 * dtd["device_s"] / args.steps,
+            "ordered_resolution": 1e3 * dtd["walk_s"] / args.steps, "pool_refresh": 1e3 * dtd["refresh_s"] / args.steps},
         "resolution": {k: dc[k] / args.steps for k in ("device_scores", "patched_scores", "host_scores",
                                                          "host_distance_evals", "guard_rechecks", "stream_births",
                                                          "stream_entries", "streams_taken_over")},

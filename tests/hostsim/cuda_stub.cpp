@@ -205,6 +205,7 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
         if (r != than) D[r * K + than] = D[than * K + r] = d[r];
       }
       memcpy(&reps[size_t(than) * wp], bw, wp * 4);
+      if (a.row_payload) memcpy(a.row_payload + size_t(row) * wp, bw, wp * 4);
       meta[than] = bm;
       a.act[b] = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (than << ACT_SLOT_SHIFT) | (row << ACT_ROW_SHIFT);
       if (append) k++;
