@@ -133,6 +133,10 @@ Engine::Engine (const apt_params &p) : p_(p) {
 }
 
 Engine::~Engine (void) {
+  if (profile_)
+    fprintf(stderr, "serial commit: plain entries %llu in %.3f s, rejected at top level %llu in %.3f s, other %llu in %.3f s\n",
+            (unsigned long long) profWalkN_[0], profWalk_[0], (unsigned long long) profWalkN_[1], profWalk_[1],
+            (unsigned long long) profWalkN_[2], profWalk_[2]);
   for (Species *s: nodes_) delete s;
   for (Species *s: graveyard_) delete s;
   if (evUser_) cudaEventDestroy(evUser_);
@@ -1606,13 +1610,17 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       uint32_t sid = INV, replaced = INV;
       int32_t slot = -1;
       const uint32_t *w = payloadOf(i);
-      if (s0) walkStream(w, g, s0, act, sid, slot, replaced);
+      const double p0t = profile_ ? now() : 0.;
+      int pcat = 0;                       // 0 plain entry, 1 rejected at top level (stream), 2 everything else
+      if (s0) { pcat = (act & ACT_CODE_MASK) == ACT_FALLTHROUGH ? 1 : 0; walkStream(w, g, s0, act, sid, slot, replaced); }
       else {
+        pcat = 2;
         int64_t p0 = -1, p1 = -1;
         auto it = std::lower_bound(pairOf_.begin(), pairOf_.end(), i, [] (const PairRef &p, uint32_t b) { return p.birth < b; });
         if (it != pairOf_.end() && it->birth == i) { p0 = it->p0; p1 = it->p1; }
         walkOne(w, g, p0, p1, sid, slot, replaced);
       }
+      if (profile_) { profWalk_[pcat] += now() - p0t; profWalkN_[pcat]++; }
       if (outSid) outSid[i] = sid;
       if (outSlot) outSlot[i] = slot;
       if (outReplaced) outReplaced[i] = replaced;

@@ -265,6 +265,7 @@ private:
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
   static constexpr uint32_t CHUNK_MIN = 1024, CHUNK_MAX = 1u << 20;
   uint32_t adaptChunk_ = 4096;          // births per device pass, adapted to how much of the last pass fell back to the host
+  double profWalk_[3] = {0, 0, 0};  uint64_t profWalkN_[3] = {0, 0, 0};   // APT_PROFILE: serial commit by category
   bool profile_ = false;                // APT_PROFILE: per-phase host timings on stderr
   std::string streamProf_;              // APT_STREAM_PROF: file the per-stream kernel timelines are appended to
   bool outPinned_ = false;              // the caller's result arrays of the current call are pinned host memory

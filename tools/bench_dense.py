@@ -151,14 +151,15 @@ def run(args):
     ops = evals * (words if kind == 0 else 3 * words)
     peak = peaks[0] if kind == 0 else peaks[3] * 2
     # Integer-pipe model of the bit-string tile (dense.cu): per 128-bit step of a (birth, representative) pair the
-    # carry-save accumulation issues 2 POPC (16-lane pipe) and 9 ALU operations (8 LOP3 + 1 IADD3, 64-lane pipe);
+    # carry-save accumulation issues 2 POPC (16-lane pipe) and 8 ALU operations (LOP3, 64-lane pipe; the two count
+    # additions are IMADs on the otherwise idle FMA pipe);
     # the slower of the two pipes bounds the sweep.  The algorithmic count (one popc32 per word) can therefore exceed
     # the measured POPC peak.
     model = None
     if kind == 0:
         steps = evals * ((words + 3) // 4)
-        t_popc, t_alu = 2 * steps / peaks[0], 9 * steps / peaks[1]
-        model = {"popc_per_step": 2, "alu_ops_per_step": 9, "bound": "alu (lop3/iadd3)" if t_alu >= t_popc else "popc",
+        t_popc, t_alu = 2 * steps / peaks[0], 8 * steps / peaks[1]
+        model = {"popc_per_step": 2, "alu_ops_per_step": 8, "bound": "alu (lop3)" if t_alu >= t_popc else "popc",
                  "min_ms": 1e3 * max(t_popc, t_alu) / world, "frac": max(t_popc, t_alu) / world / (ms * 1e-3)}
     out = None
     if rank == 0:
