@@ -182,6 +182,8 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout, in front of the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         # the ranks share the host: each engine gets its share of the cores for its grouping / commit workers
         os.environ.setdefault("APT_HOST_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // world))))
