@@ -117,6 +117,39 @@ __device__ __forceinline__ float compat_fast (float4 fm, float d) {
   return c;
 }
 
+/// sqrt.approx (1 ulp class): the distances of float-vector genomes carry float rounding already
+__device__ __forceinline__ float sqrt_fast (float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ uint4 lds128 (uint32_t addr, int off) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr + off) : "memory");
+  return v;
+}
+
+/// One 16-byte step of the float tile: 4 x 4 (birth, representative) pairs, two packed adds and two packed FMAs each
+template <int OFF>
+__device__ __forceinline__ void f32_tile_step (const uint32_t (&aB)[BT], const uint32_t (&aR)[RT], float2 (&acc)[BT][RT]) {
+  uint4 bq[BT], rq[RT];
+#pragma unroll
+  for (int i = 0; i < BT; i++) bq[i] = lds128(aB[i], OFF);
+#pragma unroll
+  for (int j = 0; j < RT; j++) rq[j] = lds128(aR[j], OFF);
+#pragma unroll
+  for (int i = 0; i < BT; i++)
+#pragma unroll
+    for (int j = 0; j < RT; j++) {
+      const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(bq[i].x), __uint_as_float(bq[i].y)),
+                                   make_float2(__uint_as_float(rq[j].x), __uint_as_float(rq[j].y)));
+      const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(bq[i].z), __uint_as_float(bq[i].w)),
+                                   make_float2(__uint_as_float(rq[j].z), __uint_as_float(rq[j].w)));
+      acc[i][j] = __ffma2_rn(t1, t1, __ffma2_rn(t0, t0, acc[i][j]));
+    }
+}
+
 struct Winners {
   float bestScore;
   uint32_t best, first, count;
@@ -138,7 +171,7 @@ struct Chain {
 };
 
 template <int KIND, bool LUT, bool CONT, int KT>
-__global__ void __launch_bounds__(256, KIND == 1 ? 3 : 2)
+__global__ void __launch_bounds__(256, 2)
 classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__restrict__ b_payload,
                              const float4 *__restrict__ b_cmeta, uint32_t n_births, uint32_t spc, int lut_in_smem, int dbuf, int bulk,
                              uint32_t *__restrict__ out_best, float *__restrict__ out_best_score,
@@ -306,28 +339,34 @@ classify_dense_tiled_kernel (PoolView pool, ScoreCfg cfg, const uint32_t *__rest
       for (int i = 0; i < BT; i++)
 #pragma unroll
         for (int j = 0; j < RT; j++) acc[i][j] = make_float2(0.f, 0.f);
-      for (uint32_t v = 0; v < wp4; v++) {
-        uint4 bq[BT], rq[RT];
+      // operand rows by shared-window address, four 16-byte steps per iteration with immediate offsets: the FMA
+      // pipe is the one this loop is bound by, so the address arithmetic (IMADs otherwise) is kept off it
+      uint32_t aB[BT], aR[RT];
 #pragma unroll
-        for (int i = 0; i < BT; i++) bq[i] = births_s[(ty + 16 * i) * stride4 + v];
+      for (int i = 0; i < BT; i++) aB[i] = uint32_t(__cvta_generic_to_shared(&births_s[(ty + 16 * i) * stride4]));
 #pragma unroll
-        for (int j = 0; j < RT; j++) rq[j] = reps_s[(tx + 16 * j) * stride4 + v];
+      for (int j = 0; j < RT; j++) aR[j] = uint32_t(__cvta_generic_to_shared(&reps_s[(tx + 16 * j) * stride4]));
+      uint32_t v = 0;
+      for (; v + 4 <= wp4; v += 4) {
+        f32_tile_step<0>(aB, aR, acc);   f32_tile_step<16>(aB, aR, acc);
+        f32_tile_step<32>(aB, aR, acc);  f32_tile_step<48>(aB, aR, acc);
 #pragma unroll
-        for (int i = 0; i < BT; i++)
+        for (int i = 0; i < BT; i++) aB[i] += 64;
 #pragma unroll
-          for (int j = 0; j < RT; j++) {
-            const float2 t0 = __fadd2_rn(make_float2(__uint_as_float(bq[i].x), __uint_as_float(bq[i].y)),
-                                         make_float2(__uint_as_float(rq[j].x), __uint_as_float(rq[j].y)));
-            const float2 t1 = __fadd2_rn(make_float2(__uint_as_float(bq[i].z), __uint_as_float(bq[i].w)),
-                                         make_float2(__uint_as_float(rq[j].z), __uint_as_float(rq[j].w)));
-            acc[i][j] = __ffma2_rn(t1, t1, __ffma2_rn(t0, t0, acc[i][j]));
-          }
+        for (int j = 0; j < RT; j++) aR[j] += 64;
+      }
+      for (; v < wp4; v++) {
+        f32_tile_step<0>(aB, aR, acc);
+#pragma unroll
+        for (int i = 0; i < BT; i++) aB[i] += 16;
+#pragma unroll
+        for (int j = 0; j < RT; j++) aR[j] += 16;
       }
 #pragma unroll
       for (int i = 0; i < BT; i++)
 #pragma unroll
         for (int j = 0; j < RT; j++)
-          dist_s[(tx + 16 * j) * DPAD + ty + 16 * i] = __float_as_uint(sqrtf(acc[i][j].x + acc[i][j].y));
+          dist_s[(tx + 16 * j) * DPAD + ty + 16 * i] = __float_as_uint(sqrt_fast(acc[i][j].x + acc[i][j].y));
     }
     __syncthreads();
 
