@@ -182,11 +182,10 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout, in front of the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / debug lines would go to stdout, in front of the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         # the ranks share the host: each engine gets its share of the cores for its grouping / commit workers
-        os.environ.setdefault("APT_HOST_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // world))))
+        os.environ.setdefault("APT_HOST_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // world - 2))))
 
     # The workload is the STEADY regime of the simulation: generations 7..11 (after 4 set-up and 3 warm-up
     # generations), where ~1 000 species take 100 000 births each step.  Left running, the drifting population
@@ -382,7 +381,7 @@ def main() -> None:
         "resolution": {k: dc[k] / args.steps for k in ("device_scores", "patched_scores", "host_scores",
                                                          "host_distance_evals", "guard_rechecks", "stream_births",
                                                          "stream_entries", "streams_taken_over")},
-        "species": width,
+        "species": width, "host_cores": os.cpu_count(), "host_threads_per_tree": os.environ.get("APT_HOST_THREADS", "default (12 on >= 16 cores)"),
     }
 
     if rank == 0 and world == 1 and not args.no_dense:
