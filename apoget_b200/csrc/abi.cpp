@@ -145,6 +145,16 @@ int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload
   });
 }
 
+int apt_host_alloc (uint64_t bytes, void **out) {
+  return guarded([&] {
+    need(out, "null argument");
+    *out = nullptr;
+    if (bytes) apt::cudaCheck(cudaMallocHost(out, size_t(bytes)), "cudaMallocHost");
+  });
+}
+
+void apt_host_free (void *p) { if (p) cudaFreeHost(p); }
+
 int apt_tree_del_genome (apt_tree *t, uint32_t sid) { return guarded([&] { need(t, "null tree"); t->engine.delGenome(sid); }); }
 
 int apt_tree_del_genomes (apt_tree *t, uint32_t n, const uint32_t *sids) {

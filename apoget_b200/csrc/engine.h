@@ -269,6 +269,9 @@ private:
   bool profile_ = false;                // APT_PROFILE: per-phase host timings on stderr
   std::string streamProf_;              // APT_STREAM_PROF: file the per-stream kernel timelines are appended to
   bool outPinned_ = false;              // the caller's result arrays of the current call are pinned host memory
+  bool payloadPinned_ = false;          // ... and so are its payload rows (else large batches are staged by the workers)
+  size_t stageMin_ = size_t(1) << 20;   // payload bytes from which pageable rows are staged by the worker pool (APT_STAGE_MIN)
+  static constexpr size_t STAGE_SLICE = size_t(256) << 10;
   DevBuf<unsigned long long> dProf_;    // per-stream timelines, only with APT_STREAM_PROF=<file>
   PinBuf<uint32_t> hBirths_, hPairBirth_, hPairSlot_, hStageRows_, hStageDst_, hCls_;
   PinBuf<float4> hBMeta_, hStageMeta_;

@@ -28,6 +28,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <new>
 #include <ostream>
 #include <set>
 #include <stdexcept>
@@ -135,6 +136,24 @@ struct PTree {
 } // namespace config
 
 /// How a genome is laid out for the device; specialise per genome type (see the file header).
+/// Allocator of the staging arrays handed to the engine (encoded genomes, results): page-locked memory
+/// (apt_host_alloc), so the births' copy to the device is one asynchronous DMA and results land in place.
+template <typename T>
+struct PinnedAllocator {
+  using value_type = T;
+  PinnedAllocator (void) = default;
+  template <typename U> PinnedAllocator (const PinnedAllocator<U>&) {}
+  T* allocate (std::size_t n) {
+    void *p = nullptr;
+    if (apt_host_alloc(uint64_t(n) * sizeof(T), &p) != APT_OK || !p) throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate (T *p, std::size_t) { apt_host_free(p); }
+  template <typename U> bool operator== (const PinnedAllocator<U>&) const { return true; }
+  template <typename U> bool operator!= (const PinnedAllocator<U>&) const { return false; }
+};
+template <typename T> using PinnedVector = std::vector<T, PinnedAllocator<T>>;
+
 template <typename GENOME> struct DeviceEncoding;
 
 // ---- phylogenetictree.hpp ------------------------------------------------------------------------
@@ -367,9 +386,10 @@ private:
   mutable Callbacks *_callbacks;
   mutable Stats _stats;
   std::map<SID, std::vector<Representative>> _rsets;       ///< host-side genome objects per enveloppe slot
-  std::vector<uint32_t> _pl, _ids, _sid, _rep;
-  std::vector<float> _cp;
-  std::vector<int32_t> _slot;
+  PinnedVector<uint32_t> _pl, _sid, _rep;
+  std::vector<uint32_t> _ids;
+  PinnedVector<float> _cp;
+  PinnedVector<int32_t> _slot;
 
   static void check (int rc) {
     if (rc == APT_OK) return;

@@ -118,6 +118,14 @@ int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload
                               uint32_t *out_sid, int32_t *out_slot, uint32_t *out_replaced_gid,
                               uint32_t *n_done);
 
+/* Page-locked host memory for the arrays handed to apt_tree_add_genomes (payload, compat, out_*):
+ * the births' copy to the device then runs as one asynchronous DMA underneath the host-side
+ * grouping, and results are written straight into out_sid / out_slot.  Ordinary (pageable) arrays
+ * are accepted everywhere; large ones are staged through pinned memory by the engine's worker
+ * threads.  The reference has no counterpart (its genomes never leave the host). */
+int apt_host_alloc (uint64_t bytes, void **out);
+void apt_host_free (void *p);
+
 int apt_tree_del_genome (apt_tree *t, uint32_t sid);                                  /* :305-317 */
 int apt_tree_register_candidate (apt_tree *t, uint32_t mother_sid, uint32_t father_sid, int dir); /* :320-329, :786-792; dir = +1 / -1 */
 int apt_tree_set_step (apt_tree *t, uint32_t step);                                   /* :219-221 */

@@ -164,6 +164,25 @@ def test_parallel_host_paths(hostsim, name, monkeypatch):
     _compare(hostsim, name)
 
 
+@pytest.mark.parametrize("name", ["c2_b256_k10", "ragged_b96_k3", "c3_f32x64_k10"])
+def test_staged_upload_of_pageable_births(hostsim, name, monkeypatch):
+    """Pageable payload arrays are copied into pinned memory slice by slice by the worker pool (rows padded
+    on the way when the word count is not a multiple of four), each slice leaving for the device on its own."""
+    monkeypatch.setenv("APT_STAGE_MIN", "1")
+    monkeypatch.setenv("APT_HOST_THREADS", "4")
+    _compare(hostsim, name)
+
+
+def test_pinned_host_allocation_round_trip():
+    L = _lib.load(apt_build.build())
+    if not L.apt_device_available():
+        pytest.skip("no device: pinned allocation needs the CUDA runtime")
+    p = ctypes.c_void_p()
+    assert L.apt_host_alloc(1 << 20, ctypes.byref(p)) == 0 and p.value
+    ctypes.memset(p, 0xA5, 1 << 20)
+    L.apt_host_free(p)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_json_load_matches_the_references_fromJson(hostsim, name):
     """fromJson (phylogenetictree.hpp:946-967) of the reference's dump, dumped again, must equal what the

@@ -55,7 +55,7 @@ def main():
     from apoget_b200.tree import PhylogeneticTree, INVALID
     tree = PhylogeneticTree(t.kind, t.words, flags=args.flags, **cfg)
     sid_of = np.full(t.n_births, INVALID, dtype=np.uint32)
-    per_gen = []
+    per_gen, gen_rows = [], []
     for g in range(t.n_gens):
         b0, b1 = int(t.gen_birth_off[g]), int(t.gen_birth_off[g + 1])
         m, f = t.mother[b0:b1], t.father[b0:b1]
@@ -64,9 +64,15 @@ def main():
                np.where(hm, sid_of[np.where(hm, m, 0)], INVALID).astype(np.uint32),
                np.where(hf, f + 1, INVALID).astype(np.uint32),
                np.where(hf, sid_of[np.where(hf, f, 0)], INVALID).astype(np.uint32)]
+        tm0, cn0 = tree.timers(), tree.counters()
         t0 = time.perf_counter()
         s, _, _ = tree.add_genomes(t.payload[b0:b1], t.compat[b0:b1], *ids)
         per_gen.append(time.perf_counter() - t0)
+        tm1, cn1 = tree.timers(), tree.counters()
+        gen_rows.append([round(1e3 * per_gen[-1], 3)] +
+                        [round(1e3 * (tm1[k] - tm0[k]), 3) for k in ("prepare_s", "device_s", "walk_s", "refresh_s")] +
+                        [round(tm1["stream_kernel_ms"] - tm0["stream_kernel_ms"], 3)] +
+                        [cn1[k] - cn0[k] for k in ("stream_launches", "host_scores", "stream_entries")])
         sid_of[b0:b1] = s
         tree.del_genomes(sid_of[t.deaths_of(g)])
         tree.step(g + 1, sid_of[t.alive_of(g)])
@@ -74,7 +80,9 @@ def main():
     out = {"config": args.config, "births": t.n_births, "gens": t.n_gens, "pop": pop, "species": st["next_sid"],
            "width": st["width"], "comparisons": st["comparisons"], "branching": st["branching"],
            "cuda_seconds": sum(per_gen), "cuda_births_per_s": t.n_births / sum(per_gen),
-           "cuda_births_per_s_last_gen": pop / per_gen[-1], "counters": tree.counters(), "timers": tree.timers()}
+           "cuda_births_per_s_last_gen": pop / per_gen[-1], "counters": tree.counters(), "timers": tree.timers(),
+           "per_gen": {"columns": ["call_ms", "prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms", "stream_kernel_ms",
+                                   "device_passes", "host_scores", "stream_entries"], "rows": gen_rows}}
 
     if args.ref_births:
         import oracle
