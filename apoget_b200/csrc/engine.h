@@ -217,8 +217,8 @@ private:
   DevBuf<uint32_t> dBirths_, dRaw_;  DevBuf<float4> dBMeta_;  DevBuf<float> dRawCompat_;  DevBuf<uint32_t> dCls_;
   DevBuf<uint32_t> dPairBirth_, dPairSlot_;  DevBuf<float> dScore_, dDist_;
   DevBuf<uint32_t> dStageRows_, dStageDst_;  DevBuf<float4> dStageMeta_;
-  DevBuf<float> dPoolDist_, dStageDist_, dRows_;  DevBuf<uint32_t> dOrder_, dGrpSlot_, dGrpOff_, dAct_, dRowCounter_;
-  PinBuf<float> hStageDist_, hRows_;  PinBuf<uint32_t> hOrder_, hGrpSlot_, hGrpOff_, hAct_, hRowCounter_;
+  DevBuf<float> dPoolDist_, dStageDist_, dRows_;  DevBuf<uint32_t> dOrder_, dGrpAll_, dAct_, dCtr_, dOut2_;
+  PinBuf<float> hStageDist_, hRows_;  PinBuf<uint32_t> hOrder_, hGrpSlot_, hGrpOff_, hAct_, hGrpAll_, hCtr_;
   std::vector<int32_t> birthGroup_;       // stream index of each birth of the chunk, -1 = host/K1 path
   std::vector<Species*> grpSpecies_;
   std::vector<uint32_t> grpCount_;
@@ -235,7 +235,8 @@ private:
   std::unique_ptr<WorkerPool> pool_;
   uint32_t parMin_ = 32768;               // chunks at least this large are grouped by the worker pool
   std::vector<uint32_t> sidSlot_;         // sid -> pool slot when the species can be streamed (device copy current), else APT_INVALID
-  std::vector<std::vector<uint32_t>> parRest_, parCnt_;
+  std::vector<std::vector<uint32_t>> parRest_, parCnt_, parOrd_, parLoc_;   // per worker: births left to the host path, offsets per species, private order buffer and its cursors
+  std::vector<uint32_t> sidTotal_;        // per species: births of the chunk, then the start of its stream in the order list
 
   std::vector<uint32_t> birthKey_;
   void groupSerial (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
@@ -243,9 +244,12 @@ private:
   void setStreamable (const Species *s, bool on);
   std::vector<int32_t> sidGroup_;         // per-chunk cache: sid -> stream index, -1 not streamable, -2 not looked up yet
   std::vector<uint32_t> sidTouched_;
-  DevBuf<uint32_t> dGrpSid_, dOutSid_;  DevBuf<int32_t> dOutSlot_;  DevBuf<uint4> dGrpSum_;
+  DevBuf<uint4> dGrpSum_;
   PinBuf<uint32_t> hGrpSid_, hOutSid_;  PinBuf<int32_t> hOutSlot_;  PinBuf<uint4> hGrpSum_;
   std::vector<uint32_t> slow_, requeue_;  // births the host has to look at (ascending) / handed back by a taken-over stream
+  std::vector<int32_t> slowGrp_;          // stream index of slow_[q] (-1: none) and ...
+  std::vector<uint32_t> slowAct_;         // ... its result word, kept next to it (sequential passes instead of gathers)
+  std::vector<std::vector<uint32_t>> parMine_;   // per worker: positions in slow_ of the entries it mirrors
   uint32_t curBirth_ = 0;                 // index (in the chunk) of the birth being committed
   const uint32_t *curDevPayload_ = nullptr;
   DevBuf<uint32_t> dSlowIdx_, dSlowRows_, dRowPayload_;  PinBuf<uint32_t> hSlowIdx_, hSlowRows_, hRowPayload_;
@@ -253,13 +257,14 @@ private:
   std::vector<std::vector<uint32_t>> lateRows_;
   // sub-species kernel (K2)
   bool childKernel_ = true;
-  DevBuf<uint32_t> dChildOff_, dChildSlot_, dFtList_, dFtCounter_, dFtFirst_, dFtFlags_;  DevBuf<float> dFtScore_, dFtDist_;
-  PinBuf<uint32_t> hChildOff_, hChildSlot_, hFtList_, hFtCounter_, hFtFirst_, hFtFlags_;  PinBuf<float> hFtScore_, hFtDist_;
+  DevBuf<uint32_t> dChildOff_, dChildSlot_, dFtList_, dFtFirst_, dFtFlags_;  DevBuf<float> dFtScore_, dFtDist_;
+  PinBuf<uint32_t> hChildOff_, hChildSlot_, hFtList_, hFtFirst_, hFtFlags_;  PinBuf<float> hFtScore_, hFtDist_;
   std::vector<int32_t> ftOfSlow_;         // entry of the sub-species results for slow_[i], -1 = none
   uint32_t nFt_ = 0;
   int64_t curFt_ = -1;                    // sub-species result entry of the birth being committed
   uint32_t chunkEpoch_ = 0;
   bool chunkUniform_ = false;             // every birth of the chunk carries the same compatibility triple
+  const float4 *fillPtr_ = nullptr;  uint32_t fillN_ = 0;  float4 fillValue_ {};   // what the births' device meta array was last filled with (uniform chunks)
   uint32_t chunkCls_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
   cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
