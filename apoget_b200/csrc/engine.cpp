@@ -123,6 +123,7 @@ Engine::Engine (const apt_params &p) : p_(p) {
     // measured on a 16-core B200 host (bench.py, 100 000 births per call): 4 threads 1.19 ms/step, 8: 1.05, 12: 0.95, 16: 1.18
     unsigned nt = hw >= 16 ? 12 : (hw >= 8 ? hw / 2 : (hw >= 4 ? 2 : 1));
     if (const char *e = getenv("APT_HOST_THREADS")) nt = unsigned(std::max(1, atoi(e)));
+    nt = std::min(nt, 64u);
     if (const char *e = getenv("APT_PAR_MIN")) parMin_ = uint32_t(std::max(1, atoi(e)));
     if (const char *e = getenv("APT_STAGE_MIN")) stageMin_ = size_t(std::max(1, atoi(e)));
     profile_ = getenv("APT_PROFILE") != nullptr;
@@ -1208,7 +1209,11 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
     uint32_t begin = 0;
     for (size_t sid = 0; sid < NS; sid++) {
       const uint32_t end = loc[sid];
-      if (end != begin) memcpy(hOrder_.p + sidTotal_[sid] + cur[sid], ord.data() + begin, size_t(end - begin) * 4);
+      if (end != begin) {                       // runs are a handful of entries: copied inline, no call
+        uint32_t *dst = hOrder_.p + sidTotal_[sid] + cur[sid];
+        const uint32_t *src = ord.data() + begin;
+        for (uint32_t j = 0; j < end - begin; j++) dst[j] = src[j];
+      }
       begin = end;
     }
   });
@@ -1525,7 +1530,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   //      booked per stream (settleStream).  Everything else -- enveloppe entries, births rejected at
   //      top level, two-parent births, streams handed back -- is committed here in arrival order. ----
   curPayload_ = payload;
-  slow_.clear();  slowGrp_.clear();  slowAct_.clear();  requeue_.clear();
+  slow_.clear();  slowGrp_.clear();  slowAct_.clear();  requeue_.clear();  grpOwner_.clear();
   if (G) {
     // outputs of the births the device settled + the list of births the host has to look at
     // (one pass over the result words; split over the worker pool for large chunks)
@@ -1614,13 +1619,20 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     struct Local { std::vector<std::pair<uint32_t, apt_event>> ev; uint64_t comparisons = 0, n = 0; std::string error; };
     std::vector<Local> loc (T);
     parMine_.resize(std::max<size_t>(parMine_.size(), T));
+    if (grpOwner_.size() != G) {
+      // stream -> worker (a table: no division per entry in the filter below).  Contiguous blocks of streams, i.e. of
+      // species ids: species founded one after the other sit next to each other in memory (records, enveloppe
+      // rows in the host mirror), and a round-robin deal made neighbouring workers share those cache lines
+      grpOwner_.resize(G);
+      for (uint32_t g = 0; g < G; g++) grpOwner_[g] = uint8_t(uint64_t(g) * T / G);
+    }
     pool_->run([&] (unsigned t) {
       Local &L = loc[t];
       // this worker's entries (streams t, t + T, ...), then one pass over them with the lines each one will touch
       // requested a few entries ahead: an entry reads ~15 cache lines nobody has touched since the last generation
       auto &mine = parMine_[t];
       mine.clear();
-      for (size_t q = from; q < from + run; q++) if (uint32_t(slowGrp_[q]) % T == t) mine.push_back(uint32_t(q));
+      for (size_t q = from; q < from + run; q++) if (grpOwner_[size_t(slowGrp_[q])] == t) mine.push_back(uint32_t(q));
       auto prefetchBirth = [&] (size_t q) {
         const uint32_t j = slow_[q];
         __builtin_prefetch(&gid[j]);  __builtin_prefetch(&mgid[j]);  __builtin_prefetch(&msid[j]);
@@ -1640,6 +1652,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         for (size_t o = 0; o < size_t(K_) * K_ * 4; o += 64) __builtin_prefetch(dm + o, 1);
         __builtin_prefetch(&hPayload_[(size_t(sp->slot) * K_ + r) * wp_], 1);
       };
+      uint64_t nDone = 0, nCmp = 0;           // (kept off the shared Local array inside the loop: neighbours share its cache lines)
       try {
         for (size_t a = 0; a < mine.size(); a++) {
           if (a + 6 < mine.size()) prefetchBirth(mine[a + 6]);
@@ -1650,7 +1663,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           Species *s0 = grpSpecies_[gi];
           if (s0->pending > 0) s0->pending--;
           touchSnap(s0);
-          L.comparisons += s0->k;
+          nCmp += s0->k;
           RepMeta g { gid[i], mgid[i], msid[i], fgid[i], fsid[i], 0, 0, chunkUniform_ ? chunkCls_ : hCls_.p[i],
                       compat[3 * i], compat[3 * i + 1], compat[3 * i + 2] };
           int32_t slot = -1;
@@ -1663,9 +1676,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           s0->count++;  s0->alive++;  s0->last = step_;
           if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));
           if (outReplaced) outReplaced[i] = replaced;
-          L.n++;
+          nDone++;
         }
       } catch (const std::exception &e) { L.error = e.what(); }
+      L.comparisons = nCmp;  L.n = nDone;
     });
     for (const Local &L: loc) if (!L.error.empty()) throw ApiError(APT_ERR_STATE, L.error);
     uint64_t total = 0;
