@@ -922,6 +922,7 @@ const uint32_t* Engine::entryRowOf (uint32_t i) const {
 const uint32_t* Engine::payloadOf (uint32_t i) {
   if (curPayload_) return curPayload_ + size_t(i) * W_;
   if (const uint32_t *w = entryRowOf(i)) return w;
+  if (curFtRow_ >= 0 && i == curBirth_) return hFtRows_.p + size_t(curFtRow_) * W_;
   auto it = std::lower_bound(gatherIdx_.begin(), gatherIdx_.end(), i);
   if (it != gatherIdx_.end() && *it == i) return hSlowRows_.p + size_t(it - gatherIdx_.begin()) * W_;
   // a birth handed back by a taken-over stream: fetched on demand
@@ -1290,6 +1291,16 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     birthsUploaded = true;
   };
   if (!dPayload && n >= 4096 && nSlots_ > freeSlots_.size()) uploadBirths();
+  // ... and so do the clears of the result arrays (they depend on n only): the device runs them under the grouping
+  bool earlyClears = false;
+  auto clearResults = [&] (void) {
+    dOut2_.reserve(2 * size_t(n));  dAct_.reserve(n);  dCtr_.reserve(2);
+    cudaCheck(cudaMemsetAsync(dOut2_.p, 0xFF, 2 * size_t(n) * 4, stream_), "sid / slot clear");
+    cudaCheck(cudaMemsetAsync(dAct_.p, 0, size_t(n) * 4, stream_), "act clear");
+    cudaCheck(cudaMemsetAsync(dCtr_.p, 0, 8, stream_), "counter clear");        // [0] rows claimed, [1] births rejected at top level
+    earlyClears = true;
+  };
+  if (streamOk_ && n >= 4096 && nSlots_ > freeSlots_.size()) clearResults();
   mark("upload");
   // ---- prepare: classes; births with a single parent species join that species' stream, the
   //      others get (birth, species) pairs for the speculative scoring kernel ----
@@ -1405,7 +1416,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     counters[7] += P;
   }
   uint32_t nRows = 0;
-  nFt_ = 0;
+  nFt_ = 0;  nFtRows_ = 0;
+  bool ftRows = false;
+  uint32_t specRows = 0, specFt = 0;        // rows / rejected births fetched ahead of knowing their number
   bool directOut = false;
   if (G) {
     // the ordered resolution of the single-parent births, one warp per species stream; it runs
@@ -1423,9 +1436,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     memcpy(hGrpAll_.p + 2 * size_t(G), hGrpOff_.p, (size_t(G) + 1) * 4);
     cudaCheck(cudaMemcpyAsync(dGrpAll_.p, hGrpAll_.p, (3 * size_t(G) + 1) * 4, cudaMemcpyHostToDevice, stream_), "groups");
     cudaCheck(cudaMemcpyAsync(dOrder_.p, hOrder_.p, nStream * 4, cudaMemcpyHostToDevice, stream_), "order");
-    cudaCheck(cudaMemsetAsync(dOut2_.p, 0xFF, 2 * size_t(n) * 4, stream_), "sid / slot clear");
-    cudaCheck(cudaMemsetAsync(dAct_.p, 0, size_t(n) * 4, stream_), "act clear");
-    cudaCheck(cudaMemsetAsync(dCtr_.p, 0, 8, stream_), "counter clear");        // [0] rows claimed, [1] births rejected at top level
+    if (!earlyClears) clearResults();
     StreamArgs a;
     a.pool = poolView();
     a.pool_payload_w = dPool_.p;  a.pool_cmeta_w = dMeta_.p;  a.pool_fill_w = dFill_.p;  a.pool_dist = dPoolDist_.p;
@@ -1464,6 +1475,15 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       counters[4]++;
       cudaCheck(cudaGetLastError(), "classify_children launch");
     }
+    if (!payload && useChildKernel) {
+      // device-resident births: the host will want the genomes of the births the streams rejected (it walks the
+      // sub-species for them); they are gathered from the device-side list right away, so that they come back
+      // with the distance rows instead of costing a round trip of their own
+      dFtRows_.reserve(size_t(nStream) * W_);
+      launch_gather_listed_rows(dPayload, dFtList_.p, dCtr_.p + 1, uint32_t(nStream), W_, dFtRows_.p, stream_);
+      counters[4]++;
+      ftRows = true;
+    }
     cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
     cudaCheck(cudaMemcpyAsync(hCtr_.p, dCtr_.p, 8, cudaMemcpyDeviceToHost, stream_), "counters");
     // results go straight into the caller's arrays when those are pinned (no staging copy on the host)
@@ -1472,6 +1492,23 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaMemcpyAsync(directOut ? reinterpret_cast<uint32_t*>(outSlot) : reinterpret_cast<uint32_t*>(hOutSlot_.p), dOutSlot,
                               size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "slots");
     cudaCheck(cudaMemcpyAsync(hGrpSum_.p, dGrpSum_.p, size_t(G) * sizeof(uint4), cudaMemcpyDeviceToHost, stream_), "sums");
+    // how many distance rows (enveloppe entries) and rejected births there are is only known after the pass; about as
+    // many as last time are fetched right away, so that the usual step needs no second round trip
+    if (estRows_) {
+      specRows = uint32_t(std::min<size_t>(estRows_, nStream));
+      hRows_.reserve(size_t(specRows) * K_);
+      cudaCheck(cudaMemcpyAsync(hRows_.p, dRows_.p, size_t(specRows) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "rows");
+      if (!payload) {
+        hRowPayload_.reserve(size_t(specRows) * wp_);
+        cudaCheck(cudaMemcpyAsync(hRowPayload_.p, dRowPayload_.p, size_t(specRows) * wp_ * 4, cudaMemcpyDeviceToHost, stream_), "row genomes");
+      }
+    }
+    if (ftRows && estFt_) {
+      specFt = uint32_t(std::min<size_t>(estFt_, nStream));
+      hFtRows_.reserve(size_t(specFt) * W_);  hFtList_.reserve(2 * size_t(specFt));
+      cudaCheck(cudaMemcpyAsync(hFtRows_.p, dFtRows_.p, size_t(specFt) * W_ * 4, cudaMemcpyDeviceToHost, stream_), "rejected births' rows");
+      cudaCheck(cudaMemcpyAsync(hFtList_.p, dFtList_.p, 2 * size_t(specFt) * 4, cudaMemcpyDeviceToHost, stream_), "ft list");
+    }
   }
   // host work that needs no device result runs under the device pass
   mark("enqueue");
@@ -1501,7 +1538,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       nRows = hCtr_.p[0];
       nFt_ = (useChildKernel && nChild) ? hCtr_.p[1] : 0u;
-      if (nRows) {
+      if (nRows > specRows) {
         hRows_.reserve(size_t(nRows) * K_);
         cudaCheck(cudaMemcpyAsync(hRows_.p, dRows_.p, size_t(nRows) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "rows");
         if (!payload) {
@@ -1518,7 +1555,18 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         cudaCheck(cudaMemcpyAsync(hFtScore_.p, dFtScore_.p, size_t(nFt_) * 4, cudaMemcpyDeviceToHost, stream_), "ft score");
         cudaCheck(cudaMemcpyAsync(hFtDist_.p, dFtDist_.p, size_t(nFt_) * K_ * 4, cudaMemcpyDeviceToHost, stream_), "ft dist");
       }
-      if (nRows || nFt_) cudaCheck(cudaStreamSynchronize(stream_), "rows");
+      nFtRows_ = ftRows ? std::min(hCtr_.p[1], uint32_t(nStream)) : 0u;
+      if (nFtRows_ > specFt) {
+        hFtRows_.reserve(size_t(nFtRows_) * W_);
+        cudaCheck(cudaMemcpyAsync(hFtRows_.p, dFtRows_.p, size_t(nFtRows_) * W_ * 4, cudaMemcpyDeviceToHost, stream_), "rejected births' rows");
+        if (!nFt_) {
+          hFtList_.reserve(2 * size_t(nFtRows_));
+          cudaCheck(cudaMemcpyAsync(hFtList_.p, dFtList_.p, 2 * size_t(nFtRows_) * 4, cudaMemcpyDeviceToHost, stream_), "ft list");
+        }
+      }
+      if (nRows > specRows || nFt_ || nFtRows_ > specFt) cudaCheck(cudaStreamSynchronize(stream_), "rows");
+      estRows_ = nRows + nRows / 4 + 64;
+      estFt_ = ftRows ? nFtRows_ + nFtRows_ / 4 + 64 : estFt_;
     }
   }
   mark("sync2");
@@ -1556,26 +1604,35 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     mark("commit-init");
     if (T > 1) pool_->run(scan); else scan(0);
     mark("scan");
+    // the workers' lists, concatenated (each worker copies its own to its offset)
     size_t total = 0;
-    for (unsigned t = 0; t < T; t++) total += parRest_[t].size() / 3;
-    slow_.reserve(total);  slowGrp_.reserve(total);  slowAct_.reserve(total);
-    for (unsigned t = 0; t < T; t++) {
+    std::vector<size_t> at (T + 1, 0);
+    for (unsigned t = 0; t < T; t++) { at[t] = total;  total += parRest_[t].size() / 3; }
+    at[T] = total;
+    slow_.resize(total);  slowGrp_.resize(total);  slowAct_.resize(total);
+    auto merge = [&] (unsigned t) {
       const auto &rest = parRest_[t];
-      for (size_t q = 0; q < rest.size(); q += 3) {
-        slow_.push_back(rest[q]);  slowGrp_.push_back(int32_t(rest[q + 1]));  slowAct_.push_back(rest[q + 2]);
-        if (int32_t(rest[q + 1]) >= 0 && (rest[q + 2] & ACT_CODE_MASK) == ACT_ENTERED) grpState_[rest[q + 1]].lastEnter = rest[q];
-      }
-    }
+      size_t o = at[t];
+      for (size_t q = 0; q < rest.size(); q += 3, o++) { slow_[o] = rest[q];  slowGrp_[o] = int32_t(rest[q + 1]);  slowAct_[o] = rest[q + 2]; }
+    };
+    if (T > 1 && total >= 1024) pool_->run(merge); else for (unsigned t = 0; t < T; t++) merge(t);
+    for (size_t q = 0; q < total; q++)
+      if (slowGrp_[q] >= 0 && (slowAct_[q] & ACT_CODE_MASK) == ACT_ENTERED) grpState_[size_t(slowGrp_[q])].lastEnter = slow_[q];
   } else {
     slow_.resize(n);
     slowGrp_.assign(n, -1);  slowAct_.assign(n, 0u);
     for (uint32_t i = 0; i < n; i++) slow_[i] = i;
   }
   mark("slow-list");
+  // entry of the device-side list of rejected births (sub-species verdicts, fetched genomes) for slow_[q]
   ftOfSlow_.assign(slow_.size(), -1);
-  for (uint32_t e = 0; e < nFt_; e++) {
+  ftRowOfSlow_.assign(nFtRows_ ? slow_.size() : 0, -1);
+  for (uint32_t e = 0; e < std::max(nFt_, nFtRows_); e++) {
     auto it = std::lower_bound(slow_.begin(), slow_.end(), hFtList_.p[2 * e]);
-    if (it != slow_.end() && *it == hFtList_.p[2 * e]) ftOfSlow_[size_t(it - slow_.begin())] = int32_t(e);
+    if (it != slow_.end() && *it == hFtList_.p[2 * e]) {
+      if (e < nFt_) ftOfSlow_[size_t(it - slow_.begin())] = int32_t(e);
+      if (e < nFtRows_) ftRowOfSlow_[size_t(it - slow_.begin())] = int32_t(e);
+    }
   }
   curDevPayload_ = payload ? nullptr : dPayload;
   lateRows_.clear();
@@ -1584,7 +1641,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     // device-resident births: the genomes of the births that entered an enveloppe came back with their distance
     // rows; the other births the host has to look at (rejected at top level, two parents, handed back) are
     // gathered on the device and fetched
-    for (uint32_t i: slow_) if (!entryRowOf(i)) gatherIdx_.push_back(i);
+    for (size_t q = 0; q < slow_.size(); q++) {
+      const bool entry = slowGrp_[q] >= 0 && (slowAct_[q] & (ACT_CODE_MASK | ACT_UNCERTAIN)) == ACT_ENTERED;    // = entryRowOf(slow_[q]) != null
+      if (!entry && !(nFtRows_ && ftRowOfSlow_[q] >= 0)) gatherIdx_.push_back(slow_[q]);
+    }
     const size_t ns = gatherIdx_.size();
     if (ns) {
       hSlowIdx_.reserve(ns);  dSlowIdx_.reserve(ns);  dSlowRows_.reserve(ns * W_);  hSlowRows_.reserve(ns * W_);
@@ -1712,8 +1772,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       if (!heap.empty() && (si >= slow_.size() || heap.front() < slow_[si])) {
         std::pop_heap(heap.begin(), heap.end(), heapCmp);
         i = heap.back();  heap.pop_back();
-        curFt_ = -1;
-      } else if (si < slow_.size()) { curFt_ = ftOfSlow_[si]; i = slow_[si++]; }
+        curFt_ = -1;  curFtRow_ = -1;
+      } else if (si < slow_.size()) { curFt_ = ftOfSlow_[si];  curFtRow_ = nFtRows_ ? ftRowOfSlow_[si] : -1;  i = slow_[si++]; }
       else break;
       curBirth_ = i;
       // the births looked at are sparse: pull what the next ones touch into the cache ahead of time

@@ -262,6 +262,11 @@ private:
   PinBuf<uint32_t> hChildOff_, hChildSlot_, hFtList_, hFtFirst_, hFtFlags_;  PinBuf<float> hFtScore_, hFtDist_;
   std::vector<int32_t> ftOfSlow_;         // entry of the sub-species results for slow_[i], -1 = none
   uint32_t nFt_ = 0;
+  uint32_t nFtRows_ = 0;                 // device-resident births: genomes of the rejected births fetched with the rows
+  std::vector<int32_t> ftRowOfSlow_;
+  int64_t curFtRow_ = -1;
+  uint32_t estRows_ = 0, estFt_ = 0;     // enveloppe entries / rejected births of the last device pass (+25 %): fetched speculatively with the results
+  DevBuf<uint32_t> dFtRows_;  PinBuf<uint32_t> hFtRows_;
   int64_t curFt_ = -1;                    // sub-species result entry of the birth being committed
   uint32_t chunkEpoch_ = 0;
   bool chunkUniform_ = false;             // every birth of the chunk carries the same compatibility triple

@@ -459,6 +459,26 @@ void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t 
   pad_rows_kernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(src, n, words, wp, dst);
 }
 
+/// Rows of the births a device-side list names: entry e of `list` is the pair (birth, stream), *count entries
+/// (a device counter: the host does not know it yet); grid-stride over (entry, word).
+__global__ void gather_listed_rows_kernel (const uint32_t *__restrict__ src, const uint32_t *__restrict__ list,
+                                           const uint32_t *__restrict__ count, uint32_t max_entries, uint32_t words,
+                                           uint32_t *__restrict__ dst) {
+  const size_t total = size_t(min(*count, max_entries)) * words;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t e = i / words, w = i - e * words;
+    dst[i] = src[size_t(list[2 * e]) * words + w];
+  }
+}
+
+void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
+                                uint32_t words, uint32_t *dst, cudaStream_t stream) {
+  if (!max_entries) return;
+  const size_t total = size_t(max_entries) * words;
+  const uint32_t blocks = uint32_t(std::min<size_t>((total + 255) / 256, 148 * 8));
+  gather_listed_rows_kernel<<<blocks, 256, 0, stream>>>(src, list, count, max_entries, words, dst);
+}
+
 void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t words, uint32_t *dst,
                          cudaStream_t stream) {
   if (!n) return;

@@ -58,6 +58,10 @@ void launch_pad_rows (const uint32_t *src, uint32_t n, uint32_t words, uint32_t 
 void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, uint32_t words, uint32_t *dst,
                          cudaStream_t stream);
 
+/// dst[e][0..words) = src[list[2e]][0..words) for e < min(*count, max_entries), `count` being a device counter
+void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
+                                uint32_t words, uint32_t *dst, cudaStream_t stream);
+
 /// Scatters staged enveloppe rows into the pool: row i of the staging buffers goes to pool row
 /// dst_row[i] (= slot*K + r).
 void launch_scatter_rows (const uint32_t *stage_payload, const float4 *stage_cmeta, const uint32_t *dst_row,

@@ -125,6 +125,12 @@ void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, u
   for (uint32_t i = 0; i < n; i++) memcpy(dst + size_t(i) * words, src + size_t(idx[i]) * words, words * 4);
 }
 
+void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
+                                uint32_t words, uint32_t *dst, cudaStream_t) {
+  const uint32_t n = *count < max_entries ? *count : max_entries;
+  for (uint32_t e = 0; e < n; e++) memcpy(dst + size_t(e) * words, src + size_t(list[2 * e]) * words, words * 4);
+}
+
 void launch_scatter_rows (const uint32_t *sp, const float4 *sm, const uint32_t *dst, uint32_t n, uint32_t wp,
                           uint32_t *pp, float4 *pm, cudaStream_t) {
   for (uint32_t i = 0; i < n; i++) {

@@ -155,6 +155,22 @@ def test_device_resident_payload_entry_point(hostsim, name):
     assert tree.to_json() == golden_json(name)
 
 
+@pytest.mark.parametrize("name", ["c2_b256_k10", "c5_speciation_trimming"])
+def test_device_resident_payloads_with_parallel_host_paths(hostsim, name, monkeypatch):
+    """Device-resident births + worker-pool commit: entering genomes come back with their distance rows, the
+    genomes of births rejected at top level with the device-side list (no gather round trip)."""
+    monkeypatch.setenv("APT_PAR_MIN", "1")
+    monkeypatch.setenv("APT_HOST_THREADS", "3")
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, _ = tree.replay(t, to_device=lambda a: (a, a.ctypes.data, 0))
+    ref = oracle.read_res(os.path.join(GOLDEN, name + ".res"))
+    assert np.array_equal(sids, ref["sids"])
+    assert np.array_equal(tree.events(), ref["events"])
+    assert tree.to_json() == golden_json(name)
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c5_speciation_trimming", "founders_orphans_classes"])
 def test_parallel_host_paths(hostsim, name, monkeypatch):
     """Worker-pool versions of the O(n) host loops (stable parallel grouping, result scan, mirroring of
