@@ -2,6 +2,8 @@
 // Reference citations are relative to /root/reference/src/core/tree unless a path is given.
 #include "engine.h"
 
+#include <sched.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -39,9 +41,12 @@ void WorkerPool::loop (unsigned t) {
   for (;;) {
     // phases of one chunk follow each other within microseconds: spin briefly before sleeping
     bool got = false;
-    for (int spin = 0; spin < 20000; spin++) {
+    // ... a few microseconds of pure spinning, then yielding between polls: a worker that only spins keeps its core
+    // from the driver's and NCCL's threads when every core of the host has a spinner on it (several ranks per host),
+    // and the thread that loses its time slice (1.5-4 ms) may be the one everybody waits for
+    for (int spin = 0; spin < 6000; spin++) {
       if (gen_.load(std::memory_order_acquire) != seen) { got = true; break; }
-      __builtin_ia32_pause();
+      if (spin < 512) __builtin_ia32_pause(); else sched_yield();
     }
     if (!got) {
       std::unique_lock<std::mutex> lk (m_);
@@ -79,10 +84,17 @@ void WorkerPool::run (const std::function<void(unsigned)> &fn) {
   fn(0);
   for (int spin = 0; spin < 20000; spin++) {
     if (pending_.load(std::memory_order_acquire) == 0) return;
-    __builtin_ia32_pause();
+    if (spin < 4096) __builtin_ia32_pause(); else sched_yield();
   }
   std::unique_lock<std::mutex> lk (m_);
   done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+}
+
+double allocClock (void) { return now(); }
+
+void noteAlloc (const char *kind, size_t bytes, double t0) {
+  static const bool on = getenv("APT_PROFILE") != nullptr;
+  if (on) fprintf(stderr, "alloc: %s %zu bytes in %.3f ms\n", kind, bytes, 1e3 * (now() - t0));
 }
 
 void cudaCheck (cudaError_t e, const char *what) {
@@ -1452,6 +1464,12 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.ft_list = nullptr;  a.ft_counter = nullptr;
     if (useChildKernel) {
       dFtList_.reserve(2 * nStream);
+      // everything the sub-species pass may need is allocated with the first stream pass, not on the step in which the
+      // first sub-species appears (a steady step): page-locking five small arrays there cost 1.5-3 ms on multi-GPU hosts
+      dChildOff_.reserve(G + 1);  dFtFirst_.reserve(nStream);  dFtFlags_.reserve(nStream);  dFtScore_.reserve(nStream);
+      dFtDist_.reserve(nStream * K_);
+      hFtList_.reserve(2 * 2048);  hFtFirst_.reserve(2048);  hFtFlags_.reserve(2048);  hFtScore_.reserve(2048);
+      hFtDist_.reserve(size_t(2048) * K_);
       a.ft_list = dFtList_.p;  a.ft_counter = dCtr_.p + 1;
     }
     const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str();
@@ -1482,6 +1500,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       // sub-species for them); they are gathered from the device-side list right away, so that they come back
       // with the distance rows instead of costing a round trip of their own
       dFtRows_.reserve(size_t(nStream) * W_);
+      // (first-use allocations of the rarely needed host-driven gather, taken here for the same reason as above)
+      hFtRows_.reserve(size_t(2048) * W_);  hSlowIdx_.reserve(1024);  dSlowIdx_.reserve(1024);
+      dSlowRows_.reserve(size_t(1024) * W_);  hSlowRows_.reserve(size_t(1024) * W_);
       launch_gather_listed_rows(dPayload, dFtList_.p, dCtr_.p + 1, uint32_t(nStream), W_, dFtRows_.p, stream_);
       counters[4]++;
       ftRows = true;
@@ -1496,6 +1517,13 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaMemcpyAsync(hGrpSum_.p, dGrpSum_.p, size_t(G) * sizeof(uint4), cudaMemcpyDeviceToHost, stream_), "sums");
     // how many distance rows (enveloppe entries) and rejected births there are is only known after the pass; about as
     // many as last time are fetched right away, so that the usual step needs no second round trip
+    // (page-locked result arrays are sized by the pass -- an eighth of its births may enter an enveloppe, or be rejected,
+    // before anything has to grow -- and not by the counts seen so far: those come from the shorter passes of the
+    // adaptive phase, and a re-allocation would then hit the first full-size steps: 1.5-2 ms each on multi-GPU hosts)
+    const size_t roomy = std::max<size_t>(1024, nStream / 8);
+    hRows_.reserve(roomy * K_);
+    if (!payload) hRowPayload_.reserve(roomy * wp_);
+    if (ftRows) { hFtRows_.reserve(roomy * W_);  hFtList_.reserve(2 * roomy); }
     if (estRows_) {
       specRows = uint32_t(std::min<size_t>(estRows_, nStream));
       hRows_.reserve(size_t(specRows) * K_);
@@ -1568,7 +1596,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       if (nRows > specRows || nFt_ || nFtRows_ > specFt) cudaCheck(cudaStreamSynchronize(stream_), "rows");
       estRows_ = nRows + nRows / 4 + 64;
-      estFt_ = ftRows ? nFtRows_ + nFtRows_ / 4 + 64 : estFt_;
+      estFt_ = ftRows ? nFtRows_ + nFtRows_ / 2 + 256 : estFt_;     // (few, and their number varies more)
     }
   }
   mark("sync2");

@@ -40,6 +40,9 @@ struct ApiError : std::runtime_error {
 };
 
 void cudaCheck (cudaError_t e, const char *what);
+/// APT_PROFILE: every (re)allocation of a grow-only buffer is reported on stderr with the time it took
+void noteAlloc (const char *kind, size_t bytes, double t0);
+double allocClock (void);
 
 /// Grow-only device buffer
 template <typename T>
@@ -52,6 +55,7 @@ struct DevBuf {
     size_t ncap = cap ? cap : 1024;
     while (ncap < n) ncap *= 2;
     T *q = nullptr;
+    const double t0 = allocClock();
     cudaCheck(cudaMalloc(&q, ncap * sizeof(T)), "cudaMalloc");
     if (p) {
       if (keep && cap) {
@@ -61,6 +65,7 @@ struct DevBuf {
       cudaFree(p);
     }
     p = q;  cap = ncap;
+    noteAlloc("device", ncap * sizeof(T), t0);
   }
 };
 
@@ -72,12 +77,16 @@ struct PinBuf {
   ~PinBuf (void) { if (p) cudaFreeHost(p); }
   void reserve (size_t n) {
     if (n <= cap) return;
+    // at least 25 % of headroom: page-locking is slow (1.5 ms per call in a process that sees several GPUs) and
+    // result sizes creep up from step to step
     size_t ncap = cap ? cap : 1024;
-    while (ncap < n) ncap *= 2;
+    while (ncap < n + n / 4) ncap *= 2;
     T *q = nullptr;
+    const double t0 = allocClock();
     cudaCheck(cudaMallocHost(&q, ncap * sizeof(T)), "cudaMallocHost");
     if (p) cudaFreeHost(p);
     p = q;  cap = ncap;
+    noteAlloc("pinned", ncap * sizeof(T), t0);
   }
 };
 

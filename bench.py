@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -255,11 +256,14 @@ def main() -> None:
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             tm0, cn0 = tree_h.timers(), tree_h.counters()
+            w0 = time.perf_counter()
             e0.record(stream)
             tree_h.add_genomes_raw(*args_h)
+            w1 = time.perf_counter()
             e1.record(stream)
             torch.cuda.synchronize()
             out["e2e_ms"] = e0.elapsed_time(e1)
+            out["e2e_wall_ms"] = 1e3 * (w1 - w0)
             tm1, cn1 = tree_h.timers(), tree_h.counters()
             out["host"] = [round(1e3 * (tm1[k] - tm0[k]), 3) for k in ("prepare_s", "device_s", "walk_s", "refresh_s")] + \
                           [round(tm1["stream_kernel_ms"] - tm0["stream_kernel_ms"], 3), cn1["kernel_launches"] - cn0["kernel_launches"],
@@ -276,11 +280,14 @@ def main() -> None:
                 dist.barrier()
             torch.cuda.synchronize()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tmd0 = tree_d.timers()
             d0.record(stream)
             tree_d.add_genomes_dev(*args_d)
             d1.record(stream)
             torch.cuda.synchronize()
             out["dev_ms"] = d0.elapsed_time(d1)
+            tmd1 = tree_d.timers()
+            out["host_dev"] = [round(1e3 * (tmd1[k] - tmd0[k]), 3) for k in ("prepare_s", "device_s", "walk_s", "refresh_s")]
             sid_d[b0:b1] = pin_sid.numpy().view(np.uint32)
             finish_gen(tree_d, g, sid_d)
             assert np.array_equal(sid_h[b0:b1], sid_d[b0:b1]), "host-fed and device-fed trees diverged"
@@ -288,6 +295,7 @@ def main() -> None:
 
         for w in range(n_warm):
             timed_step(SETUP_GENS + w, False)
+        gc.collect()        # nothing is left for the collector to do inside a timed call (it is disabled below, see main)
 
         c0, t0 = tree_h.counters(), tree_h.timers()
         cd0, td0 = tree_d.counters(), tree_d.timers()
@@ -306,11 +314,18 @@ def main() -> None:
             dt[k] = dt.get(k, 0.0) + t1[k] - t0[k]
         n_launches[0] += (c1["kernel_launches"] - c0["kernel_launches"]) + (cd1["kernel_launches"] - cd0["kernel_launches"])
         per_step.extend(steps_here)
-        return trace, tree_h.stats()["width"]
+        width = tree_h.stats()["width"]
+        tree_h.close();  tree_d.close()      # engines (streams, ~70 device / pinned buffers, worker threads) go now, not whenever the collector finds them
+        return trace, width
 
 
+    # Python's cyclic collector runs when allocation counts say so -- also inside a timed call, where freeing an old
+    # simulation's engine (dozens of cudaFree / cudaFreeHost, each a device-wide synchronisation, milliseconds apiece in
+    # a process that sees several GPUs) showed up as a 2-5 ms step.  Collected explicitly between the timed regions instead.
+    gc.disable()
     trace, width = None, 0
     for e in range((args.steps + EPOCH_STEPS - 1) // EPOCH_STEPS):
+        gc.collect()
         n_timed = min(EPOCH_STEPS, args.steps - e * EPOCH_STEPS)
         tr, width = run_epoch(e, args.warmup if e == 0 else 3, n_timed)
         if e == 0:
@@ -354,11 +369,15 @@ def main() -> None:
     line = {
         "metric": METRIC, "value": births / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "ms_per_step_median": float(np.median([s["dev_ms"] for s in per_step])), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step_median": float(np.median([s["dev_ms"] for s in per_step])),
+        "ms_per_step_all": [round(s["dev_ms"], 4) for s in per_step],
+        "per_step_host": {"columns": ["prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms"], "rows": [s["host_dev"] for s in per_step]},
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 popcount + f64 compat (bit-exact)", "data": "synthetic", "config": config,
         "e2e": {"value": births / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "ms_per_step_median": float(np.median([s["e2e_ms"] for s in per_step])),
                 "ms_per_step_all": [round(s["e2e_ms"], 4) for s in per_step],
+                "host_wall_ms_per_step_all": [round(s["e2e_wall_ms"], 4) for s in per_step],
                 "per_step_host": {"columns": ["prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms", "stream_kernel_ms",
                                               "kernel_launches", "host_scores", "device_passes"],
                                   "rows": [s["host"] for s in per_step]},
