@@ -12,12 +12,14 @@ for c in c3 c4 c5; do python tools/bench_trace.py --config $c > gpurun_out/trace
 # launch list of the bench (kernel shares) and full captures of the two top kernels
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dense > /dev/null
-ncu --set full --clock-control none --import-source on -k regex:resolve_streams -s 10 -c 1 -f -o gpurun_out/resolve_streams \
+# (-s 66: the last launches of the run are the steady steps, grid 1000; earlier ones belong to the set-up generations)
+ncu --set full --clock-control none --import-source on -k regex:resolve_streams -s 66 -c 1 -f -o gpurun_out/resolve_streams \
     python bench.py --no-cpu-baseline --no-dense --steps 2 > /dev/null
 for c in c2x c3 c4; do
   ncu --set full --clock-control none --import-source on -k regex:classify_dense_tiled -s 1 -c 1 -f -o gpurun_out/dense_$c \
       python tools/bench_dense.py --config $c --births 65536 --check 0 > /dev/null
 done
+# text summaries as committed under profiles/: python tools/ncu_summary.py launches gpurun_out/launches.csv ; python tools/ncu_summary.py kernel gpurun_out/resolve_streams.ncu-rep
 # per-stream timeline of the stream kernel
 APT_STREAM_PROF=gpurun_out/stream_prof.txt python bench.py --no-cpu-baseline --no-dense --steps 2 > /dev/null
 # multi-GPU (needs 2 / 8 GPUs): fused peer-memory exchange vs NCCL all-gather, replica scaling of the tree bench
