@@ -1706,8 +1706,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (run < entryParMin) return 0;
     const unsigned T = pool_->size();
     const bool wantEvents = !(p_.flags & APT_FLAG_NO_EVENTS);
-    struct Local { std::vector<std::pair<uint32_t, apt_event>> ev; uint64_t comparisons = 0, n = 0; std::string error; };
+    struct Local { uint64_t comparisons = 0, n = 0; std::string error; };
     std::vector<Local> loc (T);
+    // callbacks of the run: at most two per entry, written to the entry's own place and read back in arrival order
+    if (wantEvents) { runEv_.resize(2 * run);  runEvN_.assign(run, 0); }
     parMine_.resize(std::max<size_t>(parMine_.size(), T));
     if (grpOwner_.size() != G) {
       // stream -> worker (a table: no division per entry in the filter below).  Contiguous blocks of streams, i.e. of
@@ -1762,7 +1764,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           const uint32_t act = slowAct_[q];
           const uint32_t *w = payload ? payload + size_t(i) * W_ : hRowPayload_.p + size_t(act >> ACT_ROW_SHIFT) * wp_;
           const int ne = mirrorEntry(w, g, s0, act, slot, replaced, ev);
-          if (wantEvents) for (int e = 0; e < ne; e++) L.ev.emplace_back(i, ev[e]);
+          if (wantEvents) { for (int e = 0; e < ne; e++) runEv_[2 * (q - from) + e] = ev[e];  runEvN_[q - from] = uint8_t(ne); }
           s0->count++;  s0->alive++;  s0->last = step_;
           if (g.msid != INV) selfContribution(s0, 1u + (g.msid == g.fsid));
           if (outReplaced) outReplaced[i] = replaced;
@@ -1776,13 +1778,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     for (const Local &L: loc) { comparisons_ += uint32_t(L.comparisons); total += L.n; }
     insertions_ += uint32_t(total);
     counters[0] += total;  counters[1] += total;  counters[14] += total;
-    if (wantEvents) {
-      // per-worker lists are ascending by birth; a birth's events sit in one list, in order
-      std::vector<std::pair<uint32_t, apt_event>> all;
-      for (Local &L: loc) all.insert(all.end(), L.ev.begin(), L.ev.end());
-      std::stable_sort(all.begin(), all.end(), [] (const auto &a, const auto &b) { return a.first < b.first; });
-      for (const auto &e: all) events_.push_back(e.second);
-    }
+    if (wantEvents)
+      for (size_t q = 0; q < run; q++)
+        for (uint8_t e = 0; e < runEvN_[q]; e++) events_.push_back(runEv_[2 * q + e]);
     return run;
   };
   size_t nextTry = 0;                 // first position from which a parallel run is worth looking for again

@@ -258,6 +258,7 @@ private:
   std::vector<uint32_t> slow_, requeue_;  // births the host has to look at (ascending) / handed back by a taken-over stream
   std::vector<int32_t> slowGrp_;          // stream index of slow_[q] (-1: none) and ...
   std::vector<uint32_t> slowAct_;         // ... its result word, kept next to it (sequential passes instead of gathers)
+  std::vector<apt_event> runEv_;  std::vector<uint8_t> runEvN_;   // callbacks of a parallel run, two places per entry
   std::vector<uint8_t> grpOwner_;         // worker that mirrors the entries of stream g (pool sizes stay far below 256)
   std::vector<std::vector<uint32_t>> parMine_;   // per worker: positions in slow_ of the entries it mirrors
   uint32_t curBirth_ = 0;                 // index (in the chunk) of the birth being committed

@@ -6,6 +6,7 @@
 #include "apt/phylogenetictree.hpp"
 
 #include <array>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 
@@ -99,13 +100,16 @@ int run (const apt_trace::Trace &t, const std::string &prefix, bool oneByOne) {
     return g;
   };
   int bad = 0;
+  std::vector<double> addMs;          // time inside addGenome(s) per generation: encode + engine + callback replay
   for (uint32_t gen = 0; gen < t.h.n_gens; gen++) {
     const uint32_t b0 = t.gen_birth_off[gen], b1 = t.gen_birth_off[gen+1];
     std::vector<G> batch;
     for (uint32_t b = b0; b < b1; b++) batch.push_back(make(b));
     std::vector<typename PT::InsertionResult> res (b1 - b0);
+    const auto c0 = std::chrono::steady_clock::now();
     if (oneByOne) for (uint32_t b = b0; b < b1; b++) res[b - b0] = tree.addGenome(batch[b - b0]);
     else tree.addGenomes(batch.begin(), batch.end(), res.data());
+    addMs.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count());
     for (uint32_t b = b0; b < b1; b++) {
       sidOf[b] = uint32_t(res[b - b0].sid);
       entered[b] = res[b - b0].udata != nullptr;
@@ -137,7 +141,9 @@ int run (const apt_trace::Trace &t, const std::string &prefix, bool oneByOne) {
   fclose(f);
   // error contract: unknown species -> std::invalid_argument, like utils::Thrower (:169-174)
   try { tree.nodeAt(SID(0x7FFFFFFF)); bad++; } catch (const std::invalid_argument &) {}
-  printf("{\"births\": %u, \"species\": %u, \"bad\": %d}\n", B, uint32_t(tree.nextNodeID()), bad);
+  printf("{\"births\": %u, \"species\": %u, \"bad\": %d, \"add_ms_per_generation\": [", B, uint32_t(tree.nextNodeID()), bad);
+  for (size_t i = 0; i < addMs.size(); i++) printf("%s%.3f", i ? ", " : "", addMs[i]);
+  printf("]}\n");
   return bad ? 3 : 0;
 }
 
