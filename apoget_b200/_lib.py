@@ -42,6 +42,7 @@ SYMBOLS = {
     "apt_tree_destroy": (None, [vp]),
     "apt_tree_add_genomes": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32p]),
     "apt_tree_add_genomes_dev": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32p]),
+    "apt_tree_parallel_for": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp]),
     "apt_host_alloc": (ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(vp)]),
     "apt_host_free": (None, [vp]),
     "apt_tree_del_genome": (ctypes.c_int, [vp, ctypes.c_uint32]),

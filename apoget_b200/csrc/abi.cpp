@@ -145,6 +145,11 @@ int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload
   });
 }
 
+int apt_tree_parallel_for (apt_tree *t, uint32_t n, void (*fn)(void *ctx, uint32_t lo, uint32_t hi), void *ctx) {
+  // (an exception escaping fn on a worker thread terminates the process, as it would out of any C callback)
+  return guarded([&] { need(t && fn, "null argument"); t->engine.parallelFor(n, fn, ctx); });
+}
+
 int apt_host_alloc (uint64_t bytes, void **out) {
   return guarded([&] {
     need(out, "null argument");

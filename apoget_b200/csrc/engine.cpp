@@ -320,6 +320,18 @@ void Engine::doStep (uint32_t s, const uint32_t *sids, uint32_t n) {
 }
 
 // phylogenetictree.hpp:305-317
+void Engine::parallelFor (uint32_t n, void (*fn)(void *ctx, uint32_t lo, uint32_t hi), void *ctx) {
+  if (!n) return;
+  if (!pool_ || n < parMin_) { fn(ctx, 0, n); return; }
+  pool_->wake();
+  const unsigned T = pool_->size();
+  const uint32_t per = (n + T - 1) / T;
+  pool_->run([&] (unsigned t) {
+    const uint32_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    if (hi > lo) fn(ctx, lo, hi);
+  });
+}
+
 void Engine::delGenome (uint32_t sid) {
   Species *n = nodeAt(sid);
   n->last = step_;

@@ -169,6 +169,9 @@ public:
                    const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                    const uint32_t *fgid, const uint32_t *fsid,
                    uint32_t *outSid, int32_t *outSlot, uint32_t *outReplaced, uint32_t *nDone);
+  /// fn(ctx, lo, hi) over disjoint slices of [0, n) on the engine's worker threads (the caller's thread included);
+  /// returns when all slices are done.  For the binding's own O(n) loops (encoding genomes, filling results).
+  void parallelFor (uint32_t n, void (*fn)(void *ctx, uint32_t lo, uint32_t hi), void *ctx);
   void delGenome (uint32_t sid);
   void candidacy (uint32_t msid, uint32_t fsid, int dir);
   void setStep (uint32_t s) { step_ = s; }

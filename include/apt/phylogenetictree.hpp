@@ -305,14 +305,28 @@ public:
     const size_t n = gs.size();
     if (!n) return;
     _pl.resize(n * Encoding::words);  _cp.resize(n * 3);  _ids.resize(n * 5);
-    for (size_t i = 0; i < n; i++) {
-      Encoding::encode(*gs[i], &_pl[i * Encoding::words], &_cp[i * 3]);
-      const Genealogy &ge = gs[i]->genealogy();
-      _ids[i] = uint32_t(ge.self.gid);
-      _ids[n + i] = uint32_t(ge.mother.gid);      _ids[2 * n + i] = uint32_t(ge.mother.sid);
-      _ids[3 * n + i] = uint32_t(ge.father.gid);  _ids[4 * n + i] = uint32_t(ge.father.sid);
-    }
-    _sid.assign(n, APT_INVALID);  _slot.assign(n, -1);  _rep.assign(n, APT_INVALID);
+    _sid.resize(n);  _slot.resize(n);  _rep.resize(n);
+    // genome objects -> staging arrays, on the engine's worker threads for large batches: DeviceEncoding::encode is
+    // called concurrently for DIFFERENT genomes (define APT_DROPIN_SERIAL_ENCODE if yours is not a pure function of its genome)
+    struct EncodeCtx { PhylogeneticTree *self; const Genome *const *gs; size_t n; } ectx { this, gs.data(), n };
+    auto encodeSlice = [] (void *c, uint32_t lo, uint32_t hi) {
+      EncodeCtx &x = *static_cast<EncodeCtx*>(c);
+      PhylogeneticTree &t = *x.self;
+      const size_t n = x.n;
+      for (size_t i = lo; i < hi; i++) {
+        Encoding::encode(*x.gs[i], &t._pl[i * Encoding::words], &t._cp[i * 3]);
+        const Genealogy &ge = x.gs[i]->genealogy();
+        t._ids[i] = uint32_t(ge.self.gid);
+        t._ids[n + i] = uint32_t(ge.mother.gid);      t._ids[2 * n + i] = uint32_t(ge.mother.sid);
+        t._ids[3 * n + i] = uint32_t(ge.father.gid);  t._ids[4 * n + i] = uint32_t(ge.father.sid);
+        t._sid[i] = APT_INVALID;  t._slot[i] = -1;  t._rep[i] = APT_INVALID;
+      }
+    };
+#ifdef APT_DROPIN_SERIAL_ENCODE
+    encodeSlice(&ectx, 0, uint32_t(n));
+#else
+    check(apt_tree_parallel_for(_tree, uint32_t(n), +encodeSlice, &ectx));
+#endif
 #ifdef APT_DROPIN_PROFILE
     const auto p1 = std::chrono::steady_clock::now();
 #endif
@@ -454,7 +468,18 @@ private:
       case APT_EV_MAJOR_CONTRIBUTOR: _callbacks->onMajorContributorChanged(SID(x.a), SID(x.b), SID(x.c)); break;
       }
     };
+    // most births neither enter an enveloppe nor fire a callback: their results are filled in bulk (worker threads),
+    // the ordered pass below only stops at the others
+    if (out) {
+      struct FillCtx { const uint32_t *sid; InsertionResult *out; } fctx { _sid.data(), out };
+      auto fillSlice = [] (void *c, uint32_t lo, uint32_t hi) {
+        FillCtx &x = *static_cast<FillCtx*>(c);
+        for (uint32_t i = lo; i < hi; i++) x.out[i] = InsertionResult{ SID(x.sid[i]), nullptr };
+      };
+      check(apt_tree_parallel_for(_tree, n, +fillSlice, &fctx));
+    }
     for (uint32_t i = 0; i < n; i++) {
+      if (_slot[i] < 0 && (e >= ne || (ev[e].b != _sid[i] && ev[e].a != _sid[i]))) continue;      // nothing happens at this birth
       const SID sid = SID(_sid[i]);
       const uint32_t gid = _ids[i];
       if (e < ne && ev[e].type == APT_EV_NEW_SPECIES && ev[e].b == _sid[i]) fire(ev[e++]);
@@ -481,7 +506,7 @@ private:
         }
       }
       if (e < ne && ev[e].type == APT_EV_MAJOR_CONTRIBUTOR && ev[e].a == _sid[i]) fire(ev[e++]);
-      if (out) out[i] = InsertionResult{ sid, ud };
+      if (out && ud) out[i].udata = ud;
     }
     while (e < ne) fire(ev[e++]);
   }

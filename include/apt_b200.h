@@ -124,6 +124,11 @@ int apt_tree_add_genomes_dev (apt_tree *t, uint32_t n, const uint32_t *d_payload
  * are accepted everywhere; large ones are staged through pinned memory by the engine's worker
  * threads.  The reference has no counterpart (its genomes never leave the host). */
 int apt_host_alloc (uint64_t bytes, void **out);
+/* Runs fn(ctx, lo, hi) over disjoint slices covering [0, n) on the tree's host worker threads (and the calling thread)
+ * and returns when all are done: for a binding's own per-genome loops around apt_tree_add_genomes -- encoding genome
+ * objects into the payload array, filling result objects.  fn must be safe to run concurrently on different slices and
+ * must not call back into this tree.  Small n runs inline on the caller. */
+int apt_tree_parallel_for (apt_tree *t, uint32_t n, void (*fn)(void *ctx, uint32_t lo, uint32_t hi), void *ctx);
 void apt_host_free (void *p);
 
 int apt_tree_del_genome (apt_tree *t, uint32_t sid);                                  /* :305-317 */

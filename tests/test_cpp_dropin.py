@@ -16,11 +16,11 @@ CASES = [("c2_b256_k10", []), ("hybrids_b256_k5", ["--one-by-one"]), ("c4_b4096_
          ("semicontinuous_b256", ["--semi"]), ("crit0_b256", ["--crit", "0"])]
 
 
-def _run(exe, name, extra, tmp_path, f32=False):
+def _run(exe, name, extra, tmp_path, f32=False, env=None):
     cfg = golden_cases()[name]["cfg"]
     prefix = str(tmp_path / name)
     r = subprocess.run([exe, os.path.join(GOLDEN, name + ".trace"), prefix, str(cfg.get("K", 5))] + extra,
-                       capture_output=True, text=True)
+                       capture_output=True, text=True, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout + r.stderr
     a, b = oracle.read_res(prefix + ".res"), oracle.read_res(os.path.join(GOLDEN, name + ".res"))
     assert np.array_equal(a["sids"], b["sids"])
@@ -39,6 +39,14 @@ def test_dropin_host_logic(name, extra, tmp_path):
     from hostsim import build as hb
     from cpp import build as cb
     _run(cb.build(hb.build(), "hostsim"), name, extra, tmp_path)
+
+
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5"])
+def test_dropin_encodes_and_fills_results_on_the_worker_threads(name, tmp_path):
+    """apt_tree_parallel_for: the binding's per-genome loops (encode, result fill) split over the engine's workers."""
+    from hostsim import build as hb
+    from cpp import build as cb
+    _run(cb.build(hb.build(), "hostsim"), name, [], tmp_path, env={"APT_PAR_MIN": "1", "APT_HOST_THREADS": "4"})
 
 
 @pytest.mark.gpu
