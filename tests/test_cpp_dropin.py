@@ -55,3 +55,13 @@ def test_dropin_on_gpu(name, extra, tmp_path):
     from apoget_b200 import build as apt_build
     from cpp import build as cb
     _run(cb.build(apt_build.build(), "cuda"), name, extra, tmp_path, f32=name.startswith("c3"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2_b256_k10", "c4_b4096_k10"])
+def test_dropin_worker_thread_paths_on_gpu(name, tmp_path):
+    """Same, through the real library: parallel encode / result fill, staged and pinned uploads, parallel commit."""
+    from apoget_b200 import build as apt_build
+    from cpp import build as cb
+    _run(cb.build(apt_build.build(), "cuda"), name, [], tmp_path,
+         env={"APT_PAR_MIN": "1", "APT_HOST_THREADS": "4", "APT_STAGE_MIN": "1"})
