@@ -142,7 +142,8 @@ def main() -> None:
               "window": f"steady regime: generations 7-11 of each simulation ({EPOCH_STEPS} timed steps per simulation, seeds 42 + 1000 e); "
                         "the speciation that sets in from generation 12 on is configs[4] (tools/bench_trace.py)",
               "genome_bits": 256, "seed": 42, "l2": "payload+outputs of each step are new data (never re-read); "
-              "256 MiB L2 flush between timed steps", "parallelism": f"replicas x{world}" if world > 1 else "single GPU"}
+              "256 MiB L2 flush between timed steps", "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+              "barriers": "in front of each simulation's timed steps + max over ranks at the end (independent replicas)"}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -194,6 +195,10 @@ def main() -> None:
     # tools/bench_trace.py, not this metric -- so more than EPOCH_STEPS timed steps are taken from further
     # simulations (seeds 42 + 1000 e), each grown through its own untimed set-up and warm-up generations.
     pop, W = args.pop, 8
+    # Ranks are independent replicas: they meet at a barrier in front of the timed steps of every simulation and in the
+    # reduction behind the last one, not in front of every timed call (BENCH_STEP_BARRIER=1 does that: it lines up the
+    # host-side bursts of all ranks on the shared cores -- 631 M instead of 765 M births/s on 8 GPUs / 32 cores)
+    step_barrier = os.environ.get("BENCH_STEP_BARRIER", "0") == "1"
     dc, dt, dtd, n_launches, per_step = {}, {}, {}, [0], []
     sampler = ClockSampler(local_rank)
 
@@ -251,7 +256,7 @@ def main() -> None:
             args_h = (pop, vp(pin_payload.data_ptr()), vp(pin_compat.data_ptr()), [vp(x.ctypes.data) for x in ids],
                       vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))      # marshalled outside the timed region
             flush.fill_(g & 0xFF)
-            if world > 1:
+            if world > 1 and step_barrier:
                 dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -276,7 +281,7 @@ def main() -> None:
             args_d = (pop, vp(dev_payload.data_ptr()), vp(pin_compat.data_ptr()), vp(stream.cuda_stream),
                       [vp(x.ctypes.data) for x in ids], vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
             flush.fill_((g + 1) & 0xFF)
-            if world > 1:
+            if world > 1 and step_barrier:
                 dist.barrier()
             torch.cuda.synchronize()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,7 +300,9 @@ def main() -> None:
 
         for w in range(n_warm):
             timed_step(SETUP_GENS + w, False)
-        gc.collect()        # nothing is left for the collector to do inside a timed call (it is disabled below, see main)
+        gc.collect()
+        if world > 1:
+            dist.barrier()                   # all ranks enter the timed steps of this simulation together        # nothing is left for the collector to do inside a timed call (it is disabled below, see main)
 
         c0, t0 = tree_h.counters(), tree_h.timers()
         cd0, td0 = tree_d.counters(), tree_d.timers()
