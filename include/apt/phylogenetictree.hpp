@@ -458,6 +458,7 @@ private:
     std::vector<apt_event> ev (ne);
     if (ne) apt_tree_events(_tree, ev.data(), ne, 1);
     size_t e = 0;
+    const uint stepNow = step();           // (one call: step() goes through the C ABI)
     auto fire = [&] (const apt_event &x) {
       if (!_callbacks) return;
       switch (x.type) {
@@ -478,8 +479,17 @@ private:
       };
       check(apt_tree_parallel_for(_tree, n, +fillSlice, &fctx));
     }
+    const int32_t *slotp = _slot.data();
+    const uint32_t *sidp = _sid.data();
     for (uint32_t i = 0; i < n; i++) {
-      if (_slot[i] < 0 && (e >= ne || (ev[e].b != _sid[i] && ev[e].a != _sid[i]))) continue;      // nothing happens at this birth
+      {
+        // nothing happens at a birth that neither enters an enveloppe nor is the subject of the next pending callback:
+        // runs of those (95 % of a steady generation) are skipped in a loop over two arrays and two constants
+        const bool pending = e < ne;
+        const uint32_t ea = pending ? ev[e].a : 0u, eb = pending ? ev[e].b : 0u;
+        while (i < n && slotp[i] < 0 && !(pending && (sidp[i] == ea || sidp[i] == eb))) i++;
+        if (i == n) break;
+      }
       const SID sid = SID(_sid[i]);
       const uint32_t gid = _ids[i];
       if (e < ne && ev[e].type == APT_EV_NEW_SPECIES && ev[e].b == _sid[i]) fire(ev[e++]);
@@ -494,11 +504,11 @@ private:
           ud = ep.userData.get();
           *ep.userData = UserData(GID(_rep[i]));             // rebuilt from the OUTGOING genome's id, :710
           ep.genome = *gs[i];
-          ep.timestamp = step();
+          ep.timestamp = stepNow;
         } else {
           if (e < ne && ev[e].type == APT_EV_ENTERS_ENVELOPPE && ev[e].b == gid) fire(ev[e++]);
           Representative ep;
-          ep.timestamp = step();
+          ep.timestamp = stepNow;
           ep.genome = *gs[i];
           ep.userData = std::make_unique<UserData>(GID(gid));
           rset.push_back(std::move(ep));
