@@ -25,6 +25,7 @@
 #define APT_PHYLOGENETICTREE_HPP
 
 #include <cstdint>
+#include <deque>
 #ifdef APT_DROPIN_PROFILE
 #include <chrono>
 #include <cstdio>
@@ -38,7 +39,6 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
-#include <unordered_map>
 #include <utility>
 #include <iterator>
 #include <vector>
@@ -249,17 +249,16 @@ public:
     if (!c.empty()) check(apt_tree_node_children(_tree, uint32_t(sid), c.data(), uint32_t(c.size())));
     for (uint32_t s: c) n.children.push_back(SID(s));
     static const std::vector<Representative> empty;
-    auto it = _rsets.find(sid);
-    n.rset = it == _rsets.end() ? &empty : &it->second;
+    const auto *rs = rsetOf(sid);
+    n.rset = rs ? rs : &empty;
     return n;
   }
 
   /// :181-187
   UserData* getUserData (const PID &pid) const {
     nodeAt(pid.sid);                                           // throws for unknown species
-    auto it = _rsets.find(pid.sid);
-    if (it != _rsets.end())
-      for (const Representative &ep: it->second)
+    if (const auto *rs = rsetOf(pid.sid))
+      for (const Representative &ep: *rs)
         if (ep.genome.genealogy().self.gid == pid.gid) return ep.userData.get();
     return nullptr;
   }
@@ -426,8 +425,16 @@ private:
   LivingSet _aliveSpecies;
   mutable Callbacks *_callbacks;
   mutable Stats _stats;
-  struct SidHash { std::size_t operator() (SID s) const { return std::hash<uint32_t>()(uint32_t(s)); } };
-  std::unordered_map<SID, std::vector<Representative>, SidHash> _rsets;       ///< host-side genome objects per enveloppe slot
+  /// host-side genome objects per enveloppe slot, indexed by species id (ids are handed out densely, :195); a deque:
+  /// element addresses survive growth (Node views point at them) and a look-up is two hops instead of a hash chain
+  std::deque<std::vector<Representative>> _rsets;
+  const std::vector<Representative>* rsetOf (SID sid) const {
+    return (uint32_t(sid) < _rsets.size() && !_rsets[uint32_t(sid)].empty()) ? &_rsets[uint32_t(sid)] : nullptr;
+  }
+  std::vector<Representative>& rsetFor (SID sid) {
+    if (uint32_t(sid) >= _rsets.size()) _rsets.resize(size_t(uint32_t(sid)) + 1);
+    return _rsets[uint32_t(sid)];
+  }
   PinnedVector<uint32_t> _pl, _sid, _rep, _ids;
   PinnedVector<float> _cp;
   PinnedVector<int32_t> _slot;
@@ -443,10 +450,10 @@ private:
 
   /// Forget the genome objects of species removed by stillborn trimming (:816-860)
   void dropTrimmed (void) {
-    for (auto it = _rsets.begin(); it != _rsets.end(); ) {
+    for (size_t sid = 0; sid < _rsets.size(); sid++) {
+      if (_rsets[sid].empty()) continue;
       apt_node_info i;
-      if (apt_tree_node_info(_tree, uint32_t(it->first), &i) != APT_OK) it = _rsets.erase(it);
-      else ++it;
+      if (apt_tree_node_info(_tree, uint32_t(sid), &i) != APT_OK) std::vector<Representative>().swap(_rsets[sid]);
     }
   }
 
@@ -495,7 +502,7 @@ private:
       if (e < ne && ev[e].type == APT_EV_NEW_SPECIES && ev[e].b == _sid[i]) fire(ev[e++]);
       UserData *ud = nullptr;
       if (_slot[i] >= 0) {
-        auto &rset = _rsets[sid];
+        auto &rset = rsetFor(sid);
         if (_rep[i] != APT_INVALID) {
           if (e < ne && ev[e].type == APT_EV_LEAVES_ENVELOPPE) fire(ev[e++]);
           if (e < ne && ev[e].type == APT_EV_ENTERS_ENVELOPPE && ev[e].b == gid) fire(ev[e++]);
@@ -529,7 +536,7 @@ private:
     out["id"] = jn["id"];  out["data"] = jn["data"];  out["contribs"] = jn["contribs"].is_null() ? json::array() : jn["contribs"];
     out["dists"] = jn["dists"].is_null() ? json::array() : jn["dists"];
     json env = json::array(), children = json::array();
-    auto &rset = _rsets[sid];
+    auto &rset = rsetFor(sid);
     if (!jn["envlp"].is_null())
       for (const auto &jr: jn["envlp"]) {
         Representative ep;
@@ -560,9 +567,8 @@ private:
     apt_node_info i;
     check(apt_tree_node_info(_tree, uint32_t(sid), &i));
     json j, jd, jc, je = json::array(), jct = json::array();
-    auto it = _rsets.find(sid);
-    if (it != _rsets.end())
-      for (const Representative &r: it->second) je.push_back({ r.genome, *r.userData });
+    if (const auto *rs = rsetOf(sid))
+      for (const Representative &r: *rs) je.push_back({ r.genome, *r.userData });
     std::vector<uint32_t> ct (size_t(i.n_contributors) * 3);
     if (!ct.empty()) check(apt_tree_node_contributors(_tree, uint32_t(sid), ct.data(), i.n_contributors));
     for (uint32_t c = 0; c < i.n_contributors; c++) jct.push_back({ ct[3 * c], ct[3 * c + 1], bool(ct[3 * c + 2]) });
