@@ -192,23 +192,34 @@ uint32_t Engine::currentMain (Species *n) const {
 }
 
 // speciescontributors.cpp:15-65
-uint32_t Engine::contributorsUpdate (Species *n, Contributions ctbs) {
+uint32_t Engine::contributorsUpdate (Species *n, const Contributions &ctbs) {
+  // Same result as the reference's copy / erase / stable_sort, without touching the heap: a contribution list has one
+  // or two entries, a contributor list a handful.  `done` marks the contributions already added to an existing entry
+  // (the reference erases them from its copy); INVALID species are dropped first (:27-28).
   auto &v = n->contribs;
-  size_t i = 0, unprocessed = ctbs.size();
-  ctbs.erase(std::remove_if(ctbs.begin(), ctbs.end(), [] (const Contribution &c) { return c.species == INV; }),
-             ctbs.end());
-  while (i < v.size() && unprocessed > 0) {
+  uint64_t done = 0;
+  size_t unprocessed = ctbs.size();                      // (counted before the INVALID entries are dropped, as in :19-20)
+  if (ctbs.size() > 64) throw ApiError(APT_ERR_STATE, "contribution list too long");
+  for (size_t c = 0; c < ctbs.size(); c++) if (ctbs[c].species == INV) done |= (uint64_t(1) << c);
+  for (size_t i = 0; i < v.size() && unprocessed > 0; i++) {
     const uint32_t sid = v[i].sid;
-    auto it = std::find_if(ctbs.begin(), ctbs.end(), [sid] (const Contribution &c) { return c.species == sid; });
-    if (it != ctbs.end()) {
-      v[i].count += it->count;
-      unprocessed--;
-      ctbs.erase(it);
-    }
-    i++;
+    for (size_t c = 0; c < ctbs.size(); c++)
+      if (!((done >> c) & 1u) && ctbs[c].species == sid) {
+        v[i].count += ctbs[c].count;
+        unprocessed--;
+        done |= (uint64_t(1) << c);
+        break;
+      }
   }
-  for (const Contribution &c: ctbs) v.push_back({c.species, c.count, elligibile(n->sid, c.species)});
-  std::stable_sort(v.begin(), v.end(), [] (const Contributor &l, const Contributor &r) { return l.count > r.count; });
+  for (size_t c = 0; c < ctbs.size(); c++)
+    if (!((done >> c) & 1u)) v.push_back({ctbs[c].species, ctbs[c].count, elligibile(n->sid, ctbs[c].species)});
+  // stable sort by decreasing count (:62): insertion sort keeps equal counts in their order
+  for (size_t i = 1; i < v.size(); i++) {
+    const Contributor x = v[i];
+    size_t j = i;
+    while (j > 0 && v[j - 1].count < x.count) { v[j] = v[j - 1]; j--; }
+    v[j] = x;
+  }
   return currentMain(n);
 }
 

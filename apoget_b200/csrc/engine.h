@@ -309,7 +309,7 @@ private:
   // hierarchy (line-by-line restatements, see engine.cpp)
   bool elligibile (uint32_t lhs, uint32_t rhs) const;
   uint32_t currentMain (Species *n) const;
-  uint32_t contributorsUpdate (Species *n, Contributions ctbs);
+  uint32_t contributorsUpdate (Species *n, const Contributions &ctbs);
   Species* updateParent (Species *n, uint32_t sid);
   Species* nodeUpdate (Species *n, const Contributions &c);
   void updateElligibilities (void);
