@@ -20,6 +20,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <functional>
+#include <initializer_list>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -116,7 +117,23 @@ private:
 // speciescontributors.h:16-86 / :89-100
 struct Contributor { uint32_t sid, count; bool elligible; };
 struct Contribution { uint32_t species, count; };
-using Contributions = std::vector<Contribution>;
+/// What one birth contributes: its mother's and (when different) its father's species -- never more than two entries,
+/// kept inline (the reference's std::vector costs a heap round trip per birth on the commit path)
+struct Contributions {
+  Contribution v[2];
+  uint32_t n = 0;
+  Contributions (void) = default;
+  Contributions (std::initializer_list<Contribution> l) { for (const Contribution &c: l) push_back(c); }
+  void push_back (const Contribution &c) {
+    if (n >= 2) throw ApiError(APT_ERR_STATE, "more than two contributions for one birth");
+    v[n++] = c;
+  }
+  size_t size (void) const { return n; }
+  Contribution& operator[] (size_t i) { return v[i]; }
+  const Contribution& operator[] (size_t i) const { return v[i]; }
+  const Contribution* begin (void) const { return v; }
+  const Contribution* end (void) const { return v + n; }
+};
 
 /// Everything the tree keeps about a representative besides its payload (node.hpp:25-85)
 struct RepMeta {
