@@ -371,8 +371,14 @@ def main() -> None:
         units = pairs
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
 
-    h2d = pop * (G + 16) + pop * 4 + int(pairs) * 8
-    d2h = pop * 4 + int(dc["stream_entries"] / args.steps) * 4 * K + int(pairs) * (4 + 4 * K)
+    # bytes the engine copies per step (engine.cpp, runChunk): genomes, the streams' order list and the three per-stream
+    # tables go up (the births' compat metadata is one triple here and is filled on the device); result word, species id
+    # and slot per birth, the per-stream totals and the speculatively fetched distance rows (last step's count + 25 % + 64)
+    # come back; two-parent births add their pair lists / scores
+    n_streams = int(dc["stream_launches"] and width)
+    ent = int(dc["stream_entries"] / args.steps)
+    h2d = pop * G + pop * 4 + (3 * n_streams + 1) * 4 + int(pairs) * 8
+    d2h = 3 * pop * 4 + n_streams * 16 + 8 + (ent + ent // 4 + 64) * 4 * K + int(pairs) * (4 + 4 * K)
     line = {
         "metric": METRIC, "value": births / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
