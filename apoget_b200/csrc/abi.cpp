@@ -50,7 +50,41 @@ struct apt_pool {
   bool lut;
   uint32_t *payload = nullptr;  float4 *meta = nullptr;  uint32_t *fill = nullptr;  double *dlut = nullptr;
   std::vector<float> classes;       // triples, class id = index
-  ~apt_pool (void) { cudaFree(payload); cudaFree(meta); cudaFree(fill); cudaFree(dlut); }
+  // tensor-core sweep (tc_dense.cu): the pool expanded into tile images + per-tile metadata, built on first use
+  uint8_t *tcImg = nullptr;  uint32_t *tcMeta = nullptr;
+  ~apt_pool (void) { cudaFree(payload); cudaFree(meta); cudaFree(fill); cudaFree(dlut); cudaFree(tcImg); cudaFree(tcMeta); }
+  /// long bit-string genomes with the exact table go through the tensor cores (APT_DENSE_TC=0: popcount sweep)
+  bool tcWanted (void) const {
+    const char *e = getenv("APT_DENSE_TC");
+    const bool off = e && e[0] == '0';      // read per call: tests switch between the two sweeps
+    return !off && nSpecies > 0 && dense_tc_supports(cfg(), wp, K);
+  }
+  void tcEnsure (cudaStream_t st) {
+    if (tcImg) return;
+    cudaCheck(cudaMalloc(&tcImg, tc_pool_image_bytes(nSpecies, K, wp)), "cudaMalloc (expanded pool)");
+    cudaCheck(cudaMalloc(&tcMeta, tc_pool_meta_bytes(nSpecies, K)), "cudaMalloc (tile metadata)");
+    launch_tc_expand_pool(view(), tcImg, tcMeta, st);
+    cudaCheck(cudaGetLastError(), "pool expansion launch");
+  }
+  /// dense sweep of n padded births (dB: n x wp, dM: metadata) on the tensor cores, in slabs of births whose expanded
+  /// image stays below 2 GiB; `matrix` != null: distance-matrix mode
+  void tcSweep (const uint32_t *dB, const float4 *dM, uint32_t n, uint32_t *best, float *score, uint32_t *first, uint32_t *count,
+                uint32_t *matrix, size_t matrixLd, cudaStream_t st, const ShardSink *sink) {
+    tcEnsure(st);
+    const size_t perBirth = tc_births_image_bytes(128, wp) / 128;
+    uint32_t slab = uint32_t(std::min<size_t>(n, std::max<size_t>(128, ((size_t(2) << 30) / perBirth) / (148 * 128) * (148 * 128))));
+    uint8_t *img = nullptr;
+    cudaCheck(cudaMallocAsync(&img, tc_births_image_bytes(slab, wp), st), "cudaMallocAsync (expanded births)");
+    for (uint32_t b0 = 0; b0 < n; b0 += slab) {
+      const uint32_t m = std::min(slab, n - b0);
+      launch_tc_expand_births(dB + size_t(b0) * wp, m, wp, img, st);
+      launch_classify_dense_tc(view(), cfg(), img, tcImg, tcMeta, dM + b0, m, best ? best + b0 : nullptr, score ? score + b0 : nullptr,
+                               first ? first + b0 : nullptr, count ? count + b0 : nullptr,
+                               matrix ? matrix + size_t(b0) * matrixLd : nullptr, st, sink, n, b0);
+    }
+    cudaCheck(cudaGetLastError(), "tensor-core sweep launch");
+    cudaCheck(cudaFreeAsync(img, st), "cudaFreeAsync");
+  }
   uint32_t classOf (float mu, float sin, float sout) {
     for (size_t i = 0; i < classes.size(); i += 3)
       if (classes[i] == mu && classes[i + 1] == sin && classes[i + 2] == sout) return uint32_t(i / 3);
@@ -344,7 +378,8 @@ int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_pa
     cudaCheck(cudaMallocAsync(&dB, (size_t(n_births) * p->wp + 4) * 4, st), "cudaMallocAsync");
     cudaCheck(cudaMallocAsync(&dM, (size_t(n_births) + 1) * sizeof(float4), st), "cudaMallocAsync");
     launch_pack_births(d_payload, d_compat, nullptr, n_births, p->W, p->wp, dB, dM, st);
-    launch_classify_dense(p->view(), p->cfg(), dB, dM, n_births, d_best, d_best_score, d_first, d_count, st);
+    if (p->tcWanted()) p->tcSweep(dB, dM, n_births, d_best, d_best_score, d_first, d_count, nullptr, 0, st, nullptr);
+    else launch_classify_dense(p->view(), p->cfg(), dB, dM, n_births, d_best, d_best_score, d_first, d_count, st);
     cudaCheck(cudaGetLastError(), "classify_dense launch");
     cudaCheck(cudaFreeAsync(dB, st), "cudaFreeAsync");
     cudaCheck(cudaFreeAsync(dM, st), "cudaFreeAsync");
@@ -359,7 +394,8 @@ int apt_classify_dense (apt_pool *p, uint32_t n_births, const uint32_t *payload,
     Tmp<uint32_t> dB (size_t(n_births) * p->wp + 4);  Tmp<float4> dM (n_births + 1);
     p->packBirths(n_births, payload, compat, dB, dM);
     Tmp<uint32_t> dBest (n_births), dFirst (n_births), dCount (n_births);  Tmp<float> dScore (n_births);
-    launch_classify_dense(p->view(), p->cfg(), dB.p, dM.p, n_births, dBest.p, dScore.p, dFirst.p, dCount.p, nullptr);
+    if (p->tcWanted()) p->tcSweep(dB.p, dM.p, n_births, dBest.p, dScore.p, dFirst.p, dCount.p, nullptr, 0, nullptr, nullptr);
+    else launch_classify_dense(p->view(), p->cfg(), dB.p, dM.p, n_births, dBest.p, dScore.p, dFirst.p, dCount.p, nullptr);
     cudaCheck(cudaGetLastError(), "classify_dense launch");
     cudaCheck(cudaDeviceSynchronize(), "classify_dense");
     dBest.down(out_best, n_births);  dScore.down(out_best_score, n_births);
@@ -386,7 +422,10 @@ int apt_classify_dense_shard_dev (apt_pool *p, uint32_t n_births, const uint32_t
     cudaCheck(cudaMallocAsync(&dB, (size_t(n_births) * p->wp + 4) * 4, st), "cudaMallocAsync");
     cudaCheck(cudaMallocAsync(&dM, (size_t(n_births) + 1) * sizeof(float4), st), "cudaMallocAsync");
     launch_pack_births(d_payload, d_compat, nullptr, n_births, p->W, p->wp, dB, dM, st);
-    if (dense_tiled_supports(p->wp, p->K)) {
+    if (p->tcWanted()) {
+      // tensor-core sweep: its epilogue stores the records into the peers' buffers
+      p->tcSweep(dB, dM, n_births, nullptr, nullptr, nullptr, nullptr, nullptr, 0, st, &sink);
+    } else if (dense_tiled_supports(p->wp, p->K)) {
       // the sweep kernel itself stores the records into the peers' buffers
       launch_classify_dense_tiled(p->view(), p->cfg(), dB, dM, n_births, nullptr, nullptr, nullptr, nullptr, st, &sink);
     } else {
@@ -412,6 +451,34 @@ int apt_combine_shards_dev (int device, uint32_t n_births, uint32_t world, const
     launch_combine_shards(static_cast<const uint4*>(d_records), n_births, world, d_best, d_best_score, d_first, d_count,
                           static_cast<cudaStream_t>(stream));
     cudaCheck(cudaGetLastError(), "combine_shards launch");
+  });
+}
+
+int apt_distance_matrix (const apt_params *params, uint32_t n_a, const uint32_t *payload_a, uint32_t n_b,
+                         const uint32_t *payload_b, uint32_t *out) {
+  return guarded([&] {
+    need(params && (n_a == 0 || n_b == 0 || (payload_a && payload_b && out)), "null argument");
+    need(params->kind == APT_BITS && params->words >= 1 && params->words <= 1024, "bit-string genomes only");
+    if (!n_a || !n_b) return;
+    requireDevice(params->device);
+    // a pool of n_b one-representative species: a tile of the expanded pool is then 256 consecutive rows of b
+    apt_params prm = *params;
+    prm.rset_size = 1;  prm.flags &= ~uint32_t(APT_FLAG_FORCE_GENERIC);
+    std::vector<float> compat (size_t(std::max(n_a, n_b)) * 3, 1.f);
+    std::vector<uint32_t> fill (n_b, 1u);
+    apt_pool *raw = nullptr;
+    if (apt_pool_create(&prm, n_b, payload_b, compat.data(), fill.data(), &raw) != APT_OK) throw ApiError(APT_ERR_CUDA, g_error);
+    std::unique_ptr<apt_pool> p (raw);
+    need(dense_tc_supports(p->cfg(), p->wp, 1), "genomes of 1024 to 32768 bits only");
+    Tmp<uint32_t> dB (size_t(n_a) * p->wp + 4);  Tmp<float4> dM (n_a + 1);
+    p->packBirths(n_a, payload_a, compat.data(), dB, dM);
+    const size_t ld = (size_t(n_b) + 255) / 256 * 256;
+    Tmp<uint32_t> dOut (size_t(n_a) * ld);
+    p->tcSweep(dB.p, dM.p, n_a, nullptr, nullptr, nullptr, nullptr, dOut.p, ld, nullptr, nullptr);
+    cudaCheck(cudaDeviceSynchronize(), "distance matrix");
+    std::vector<uint32_t> h (size_t(n_a) * ld);
+    dOut.down(h.data(), h.size());
+    for (uint32_t i = 0; i < n_a; i++) memcpy(out + size_t(i) * n_b, h.data() + size_t(i) * ld, size_t(n_b) * 4);
   });
 }
 

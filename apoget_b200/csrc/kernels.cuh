@@ -178,6 +178,21 @@ void launch_classify_dense_tiled (const PoolView &pool, const ScoreCfg &cfg, con
                                   float *out_best_score, uint32_t *out_first_accept, uint32_t *out_n_accept,
                                   cudaStream_t stream, const ShardSink *sink = nullptr);
 
+/// Tensor-core dense sweep for long bit-string genomes (tc_dense.cu): Hamming distance as an exact int8 GEMM
+/// (tcgen05.mma, accumulators in TMEM) over operands pre-expanded into tile images, same epilogue arithmetic.
+bool dense_tc_supports (const ScoreCfg &cfg, uint32_t wp, uint32_t K);
+size_t tc_pool_image_bytes (uint32_t n_species, uint32_t K, uint32_t wp);
+size_t tc_pool_meta_bytes (uint32_t n_species, uint32_t K);
+size_t tc_births_image_bytes (uint32_t n_births, uint32_t wp);
+void launch_tc_expand_pool (const PoolView &pool, uint8_t *img, uint32_t *meta, cudaStream_t stream);
+void launch_tc_expand_births (const uint32_t *b_payload, uint32_t n_births, uint32_t wp, uint8_t *img, cudaStream_t stream);
+/// out_matrix != null: distance-matrix mode, out_matrix[b * ld + row] = Hamming distance (ld = tiles * 256 pool rows)
+void launch_classify_dense_tc (const PoolView &pool, const ScoreCfg &cfg, const uint8_t *a_img, const uint8_t *b_img,
+                               const uint32_t *tile_meta, const float4 *b_cmeta, uint32_t n_births,
+                               uint32_t *out_best_species, float *out_best_score, uint32_t *out_first_accept,
+                               uint32_t *out_n_accept, uint32_t *out_matrix, cudaStream_t stream,
+                               const ShardSink *sink = nullptr, uint32_t rec_stride = 0, uint32_t rec_offset = 0);
+
 /// Local winners -> records in every peer's gather buffer (the sweep kernels that do not write
 /// records themselves: genome shapes the tiled kernel does not cover)
 void launch_publish_records (const uint32_t *best, const float *best_score, const uint32_t *first, const uint32_t *count,

@@ -85,6 +85,17 @@ def env_contribution(K, edist, gdist, crit=1, device=0):
     return better.astype(bool), than, value
 
 
+def distance_matrix(payload_a, payload_b, device=0):
+    """Hamming distances of every genome of payload_a [n_a, words] to every genome of payload_b [n_b, words]
+    (u32 [n_a, n_b]) through the tensor-core pipeline of the dense sweep (genomes of 1024..32768 bits)."""
+    a, b = _u32(payload_a), _u32(payload_b)
+    assert a.ndim == 2 and b.ndim == 2 and a.shape[1] == b.shape[1]
+    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.uint32)
+    p = make_params(0, a.shape[1], device, 0)
+    check(lib().apt_distance_matrix(ctypes.byref(p), a.shape[0], _ptr(a), b.shape[0], _ptr(b), _ptr(out)))
+    return out
+
+
 def pairwise(kind, payload, idx_a, idx_b, device=0):
     payload = _u32(payload)
     n, words = payload.shape

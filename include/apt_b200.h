@@ -219,6 +219,17 @@ int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_pa
                             uint32_t *d_out_best_species, float *d_out_best_score,
                             uint32_t *d_out_first_accept, uint32_t *d_out_n_accept, void *stream);
 
+/* Long bit-string genomes (1024..32768 bits, exact compatibility table): apt_classify_dense* run the distances on the
+ * 5th-generation tensor cores -- Hamming distance as an exact int8 GEMM over genomes expanded to +-1 bytes,
+ * (L - a.b) / 2, tcgen05.mma with the accumulators in tensor memory -- with the reference's arithmetic per
+ * (birth, species) unchanged in the epilogue; results are bit-identical to the popcount sweep (environment
+ * variable APT_DENSE_TC=0 selects that one).  The pool is expanded once, on the first sweep.
+ *
+ * apt_distance_matrix: the births x members distance kernel on its own (north_star (1)): out[i * n_b + j] =
+ * Hamming distance of genome i of payload_a and genome j of payload_b, through the same tensor-core pipeline. */
+int apt_distance_matrix (const apt_params *params, uint32_t n_a, const uint32_t *payload_a, uint32_t n_b,
+                         const uint32_t *payload_b, uint32_t *out);
+
 /* Species-sharded dense sweep (north_star (5)): this rank's pool holds the species
  * [species_offset, species_offset + n_species) of `world` <= 8 shards with increasing ranges.  The sweep
  * kernel writes one 16-byte record per birth {best species (pool-wide index), score bits, first

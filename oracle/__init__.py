@@ -70,6 +70,9 @@ def lib() -> ctypes.CDLL:
         L.apto_score.restype = ctypes.c_float
         L.apto_score.argtypes = [ctypes.c_uint32] * 3 + [ctypes.c_int] + [ctypes.c_double] * 3 + \
             [_u32p, _f32p, _u32p, _f32p, _f32p]
+        L.apto_score_dense.restype = None
+        L.apto_score_dense.argtypes = [ctypes.c_uint32] * 3 + [ctypes.c_int] + [ctypes.c_double] * 3 + \
+            [ctypes.c_uint32, _u32p, _f32p, ctypes.c_uint32, _u32p, _f32p, _u32p, ctypes.c_uint32, _u32p, _f32p, _u32p, _u32p]
         L.apto_env_contribution.restype = ctypes.c_int
         L.apto_env_contribution.argtypes = [ctypes.c_int, ctypes.c_uint32, _f32p, _f32p, _u32p, _f32p]
         _lib = L
@@ -189,6 +192,27 @@ def score(kind, birth, birth_compat, reps, rep_compat, full_continuous=True,
     s = lib().apto_score(kind, birth.size, k, int(full_continuous), compat_thr, sim_thr, avg_thr,
                          _p(birth, _u32p), _p(bc, _f32p), _p(reps, _u32p), _p(rc, _f32p), _p(d, _f32p))
     return float(s), d
+
+
+def score_dense(kind, births, birth_compat, reps, rep_compat, fill, full_continuous=True,
+                compat_thr=.1, sim_thr=.5, avg_thr=.25, threads=0):
+    """Every birth [B, words] against every species (reps [S, K, words], rep_compat [S, K, 3], fill [S]) with the
+    reference's arithmetic -> (best species, best score, first accepting species, accept count), the winners the
+    CUDA dense sweep reports.  Threaded over births."""
+    births = np.ascontiguousarray(births, dtype=np.uint32)
+    reps = np.ascontiguousarray(reps, dtype=np.uint32)
+    B, words = births.shape
+    S, K = reps.shape[0], reps.shape[1]
+    bc = np.ascontiguousarray(birth_compat, dtype=np.float32).reshape(B, 3)
+    rc = np.ascontiguousarray(rep_compat, dtype=np.float32).reshape(S, K, 3)
+    fill = np.ascontiguousarray(fill, dtype=np.uint32)
+    best, first, count = (np.zeros(B, dtype=np.uint32) for _ in range(3))
+    best_score = np.zeros(B, dtype=np.float32)
+    lib().apto_score_dense(kind, words, K, int(full_continuous), compat_thr, sim_thr, avg_thr, B, _p(births, _u32p),
+                           _p(bc, _f32p), S, _p(reps, _u32p), _p(rc, _f32p), _p(fill, _u32p),
+                           threads or (os.cpu_count() or 1), _p(best, _u32p), _p(best_score, _f32p), _p(first, _u32p),
+                           _p(count, _u32p))
+    return best, best_score, first, count
 
 
 def env_contribution(crit, edist, gdist):

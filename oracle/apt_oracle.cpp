@@ -26,6 +26,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "trace.h"
@@ -784,6 +785,74 @@ float apto_score (uint32_t kind, uint32_t words, uint32_t k, int fullContinuous,
     if (outD) outD[i] = float(d);
   }
   return matable - simThr * k;
+}
+
+/// Dense sweep checker: every birth against every species (apto_score per pair, i.e. phylogenetictree.hpp:430-478),
+/// folded into the per-birth winners the CUDA sweep reports -- species with the strictly greatest score (lowest
+/// index on ties), lowest species with score > 0 (or INVALID), number of species with score > 0.  Species with an
+/// empty enveloppe are skipped.  Split over `threads` host threads by birth (every pair is independent).  For
+/// bit-strings the two exp() per pair are taken from per-triple tables filled by the same compatibility() call
+/// for every integer distance: identical doubles, 100x fewer libm calls (1e9 pairs stay a matter of seconds).
+void apto_score_dense (uint32_t kind, uint32_t words, uint32_t K, int fullContinuous,
+                       double compatThr, double simThr, double avgThr,
+                       uint32_t nBirths, const uint32_t *births, const float *birthCompat,
+                       uint32_t nSpecies, const uint32_t *reps, const float *repCompat, const uint32_t *fill,
+                       uint32_t threads, uint32_t *outBest, float *outBestScore, uint32_t *outFirst, uint32_t *outCount) {
+  struct Triple { float a, b, c; bool operator< (const Triple &o) const { return a != o.a ? a < o.a : b != o.b ? b < o.b : c < o.c; } };
+  std::map<Triple, uint32_t> ids;
+  std::vector<std::vector<double>> tables;
+  std::vector<uint32_t> bcls (nBirths), rcls (size_t(nSpecies) * K, 0);
+  const uint32_t maxD = 32 * words;
+  auto classOf = [&] (const float *t) {
+    const Triple key { t[0], t[1], t[2] };
+    auto it = ids.find(key);
+    if (it != ids.end()) return it->second;
+    const uint32_t id = uint32_t(tables.size());
+    ids.emplace(key, id);
+    tables.emplace_back();
+    if (kind == 0) {
+      tables.back().resize(maxD + 1);
+      for (uint32_t d = 0; d <= maxD; d++) tables.back()[d] = compatibility(t[0], t[1], t[2], double(d));
+    }
+    return id;
+  };
+  for (uint32_t b = 0; b < nBirths; b++) bcls[b] = classOf(birthCompat + 3 * size_t(b));
+  for (uint32_t s = 0; s < nSpecies; s++)
+    for (uint32_t r = 0; r < std::min(fill[s], K); r++) rcls[size_t(s) * K + r] = classOf(repCompat + 3 * (size_t(s) * K + r));
+  auto work = [&] (uint32_t lo, uint32_t hi) {
+    for (uint32_t b = lo; b < hi; b++) {
+      uint32_t best = INVALID, first = INVALID, count = 0;
+      float bestScore = -std::numeric_limits<float>::infinity();
+      const uint32_t *g = births + size_t(b) * words;
+      const float *gc = birthCompat + 3 * size_t(b);
+      for (uint32_t s = 0; s < nSpecies; s++) {
+        const uint32_t k = std::min(fill[s], K);
+        if (!k) continue;
+        float score;
+        if (kind == 0) {
+          float avg = 0;
+          uint32_t matable = 0;
+          for (uint32_t i = 0; i < k; i++) {
+            const double d = distanceOf(kind, words, g, reps + (size_t(s) * K + i) * words);
+            const double c = std::min(tables[bcls[b]][uint32_t(d)], tables[rcls[size_t(s) * K + i]][uint32_t(d)]);
+            if (fullContinuous) avg += c; else if (c >= compatThr) matable++;
+          }
+          score = fullContinuous ? float(avg / float(k) - avgThr) : float(matable - simThr * k);
+        } else
+          score = apto_score(kind, words, k, fullContinuous, compatThr, simThr, avgThr, g, gc,
+                             reps + size_t(s) * K * words, repCompat + 3 * size_t(s) * K, nullptr);
+        if (best == INVALID || bestScore < score) { best = s; bestScore = score; }
+        if (score > 0) { count++; if (first == INVALID) first = s; }
+      }
+      outBest[b] = best;  outBestScore[b] = bestScore;  outFirst[b] = first;  outCount[b] = count;
+    }
+  };
+  const uint32_t T = std::max(1u, std::min(threads, nBirths));
+  std::vector<std::thread> pool;
+  const uint32_t per = (nBirths + T - 1) / T;
+  for (uint32_t t = 1; t < T; t++) pool.emplace_back(work, std::min(nBirths, t * per), std::min(nBirths, (t + 1) * per));
+  work(0, std::min(nBirths, per));
+  for (auto &th: pool) th.join();
 }
 
 /// Enveloppe criterion (enveloppecriteria.cpp:275-289) on a full k x k symmetric matrix

@@ -260,5 +260,14 @@ void launch_classify_dense_tiled (const PoolView&, const ScoreCfg&, const uint32
                                   uint32_t*, uint32_t*, cudaStream_t, const ShardSink*) {}
 void launch_publish_records (const uint32_t*, const float*, const uint32_t*, const uint32_t*, uint32_t, const ShardSink&, cudaStream_t) {}
 void launch_combine_shards (const uint4*, uint32_t, uint32_t, uint32_t*, float*, uint32_t*, uint32_t*, cudaStream_t) {}
+// tensor-core sweep: never selected under the stub
+bool dense_tc_supports (const ScoreCfg&, uint32_t, uint32_t) { return false; }
+size_t tc_pool_image_bytes (uint32_t, uint32_t, uint32_t) { return 16; }
+size_t tc_pool_meta_bytes (uint32_t, uint32_t) { return 16; }
+size_t tc_births_image_bytes (uint32_t, uint32_t) { return 16; }
+void launch_tc_expand_pool (const PoolView&, uint8_t*, uint32_t*, cudaStream_t) {}
+void launch_tc_expand_births (const uint32_t*, uint32_t, uint32_t, uint8_t*, cudaStream_t) {}
+void launch_classify_dense_tc (const PoolView&, const ScoreCfg&, const uint8_t*, const uint8_t*, const uint32_t*, const float4*, uint32_t,
+                               uint32_t*, float*, uint32_t*, uint32_t*, uint32_t*, cudaStream_t, const ShardSink*, uint32_t, uint32_t) {}
 
 } // namespace apt
