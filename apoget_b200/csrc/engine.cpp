@@ -140,6 +140,7 @@ Engine::Engine (const apt_params &p) : p_(p) {
     if (const char *e = getenv("APT_STAGE_MIN")) stageMin_ = size_t(std::max(1, atoi(e)));
     profile_ = getenv("APT_PROFILE") != nullptr;
     if (const char *e = getenv("APT_STREAM_PROF")) streamProf_ = e;
+    if (const char *e = getenv("APT_LUT_MAX_BYTES")) lutMaxBytes_ = size_t(std::max(0ll, atoll(e)));
     if (nt > 1) pool_.reset(new WorkerPool(nt));
   }
   streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
@@ -377,9 +378,14 @@ uint32_t Engine::classOf (float mu, float sin, float sout) {
     if (lutMode_) {
       // one table row per class, filled by the HOST libm: the device reads back the very doubles
       // the reference would compute (crossover.h:89-92)
-      if (size_t(id + 1) * lutStride_ * sizeof(double) > (size_t(256) << 20)) {
-        lutMode_ = false;     // too many distinct triples for a table: fall back to device exp() + guard band
+      if (size_t(id + 1) * lutStride_ * sizeof(double) > lutMaxBytes_) {
+        // too many distinct triples for a table: device exp() + guard band from here on.  Vote-count scoring has no
+        // guard band (a flipped vote cannot be seen from the score): without the exact table neither the stream
+        // kernel nor the sub-species kernel may decide such births any more -- the host does, with libm.
+        lutMode_ = false;
         hLut_.clear();  hLut_.shrink_to_fit();
+        streamOk_ = streamOk_ && p_.full_continuous;
+        childKernel_ = childKernel_ && p_.full_continuous;
       } else {
         hLut_.resize(size_t(id + 1) * lutStride_);
         for (uint32_t d = 0; d < lutStride_; d++) {

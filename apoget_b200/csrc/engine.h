@@ -211,6 +211,7 @@ private:
   uint32_t K_, W_, wp_;
   bool lutMode_;
   uint32_t lutStride_;
+  size_t lutMaxBytes_ = size_t(256) << 20;   // largest compatibility table kept (APT_LUT_MAX_BYTES); beyond it: generic mode
 
   // ---- tree state (phylogenetictree.hpp:370-389) ----
   uint32_t nextNodeID_ = 0, stillborns_ = 0, step_ = 0;

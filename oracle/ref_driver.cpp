@@ -253,7 +253,9 @@ int dispatch (const apt_trace::Trace &t, const Options &o) {
   switch (t.h.words) {
   case 1:   return run<1, IS_F32>(t, o);
   case 2:   return run<2, IS_F32>(t, o);
+  case 3:   return run<3, IS_F32>(t, o);
   case 4:   return run<4, IS_F32>(t, o);
+  case 5:   return run<5, IS_F32>(t, o);
   case 8:   return run<8, IS_F32>(t, o);
   case 16:  return run<16, IS_F32>(t, o);
   case 32:  return run<32, IS_F32>(t, o);

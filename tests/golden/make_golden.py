@@ -48,8 +48,12 @@ CASES = {
     "c5_speciation_trimming": (dict(kind=B, words=8, pop=60, gens=260, seed=45, flips=3, sigma=6.0,
                                     hybrid=0.1),
                                dict(K=8, trim_period=50, trim_min_delay=20, trim_delay=1.0, trim_thr=0.5)),
-    "ragged_b96_k3": (dict(kind=B, words=4, pop=37, gens=20, seed=12, flips=1, sigma=3.0, hybrid=0.5,
+    # 96-bit payloads: three words per genome, padded to four on the device
+    "ragged_b96_k3": (dict(kind=B, words=3, pop=37, gens=20, seed=12, flips=1, sigma=3.0, hybrid=0.5,
                            survive=0.5), dict(K=3)),
+    # vote-count scoring with four compatibility classes on 160-bit payloads (five words, padded to eight)
+    "semi_classes_b160_k5": (dict(kind=B, words=5, pop=100, gens=30, seed=14, flips=2, sigma=6.0, founders=4,
+                                  hybrid=0.2, compat_classes=4), dict(K=5, full_continuous=False)),
     "k1_b64": (dict(kind=B, words=2, pop=40, gens=20, seed=13, flips=1, sigma=2.0), dict(K=1)),
 }
 

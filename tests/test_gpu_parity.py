@@ -68,6 +68,14 @@ def test_tree_generic_compat_path(name):
     _compare(name, flags=4)
 
 
+@pytest.mark.parametrize("name,cap", [("semi_classes_b160_k5", 3000), ("founders_orphans_classes", 5000)])
+def test_tree_compat_table_overflow(name, cap, monkeypatch):
+    """The compatibility table overflows mid-run (APT_LUT_MAX_BYTES stands in for the 256 MiB limit): device exp()
+    from then on; vote-count scoring then leaves the device kernels (no guard band can protect a vote)."""
+    monkeypatch.setenv("APT_LUT_MAX_BYTES", str(cap))
+    _compare(name)
+
+
 def _random_pool(rng, kind, words, S, K, sigma):
     if kind == synth.BITS:
         base = rng.integers(0, 2**32, size=(S, 1, words), dtype=np.uint32)

@@ -80,6 +80,22 @@ def test_host_resolution_logic_generic_compat(hostsim, name):
     _compare(hostsim, name, flags=4)
 
 
+@pytest.mark.parametrize("name,cap", [("semi_classes_b160_k5", 3000), ("semi_classes_b160_k5", 1), ("founders_orphans_classes", 5000)])
+def test_compat_table_overflow_keeps_parity(hostsim, name, cap, monkeypatch):
+    """More distinct (mu, sigma_in, sigma_out) triples than the compatibility table may hold (APT_LUT_MAX_BYTES
+    stands in for the 256 MiB limit): the engine drops to device exp() mid-run.  With vote-count scoring no guard
+    band protects a decision, so the stream and sub-species kernels must stop deciding births from that point on
+    (the stub perturbs exp() by an ulp, as a real device does)."""
+    monkeypatch.setenv("APT_LUT_MAX_BYTES", str(cap))
+    tree = _compare(hostsim, name)
+    c = tree.counters()
+    assert c["host_scores"] > 0
+    if cap == 1:        # no table from the first genome on: vote counting never reaches the stream kernel
+        assert c["stream_births"] == 0
+    if name == "founders_orphans_classes":      # continuous scoring keeps it (guard band)
+        assert c["stream_births"] > 0
+
+
 def test_one_birth_per_call_equals_batches(hostsim):
     name = "hybrids_b256_k5"
     cfg = golden_cases()[name]["cfg"]

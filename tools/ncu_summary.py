@@ -17,6 +17,8 @@ gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed lts__t_sector_hit_rate.pc
 smsp__issue_active.avg.pct_of_peak_sustained_active sm__throughput.avg.pct_of_peak_sustained_elapsed
 sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active
 sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active
+lts__throughput.avg.pct_of_peak_sustained_elapsed l1tex__throughput.avg.pct_of_peak_sustained_elapsed
 l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum
 smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio
 smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio
