@@ -1,7 +1,9 @@
 // extern "C" boundary of libapt_b200.so (declarations and contracts: include/apt_b200.h).
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
 
 #include "engine.h"
@@ -85,15 +87,22 @@ struct apt_pool {
     cudaCheck(cudaGetLastError(), "tensor-core sweep launch");
     cudaCheck(cudaFreeAsync(img, st), "cudaFreeAsync");
   }
+  std::map<std::array<float, 3>, uint32_t> classIds;
   uint32_t classOf (float mu, float sin, float sout) {
-    for (size_t i = 0; i < classes.size(); i += 3)
-      if (classes[i] == mu && classes[i + 1] == sin && classes[i + 2] == sout) return uint32_t(i / 3);
+    const std::array<float, 3> key { mu, sin, sout };
+    auto it = classIds.find(key);
+    if (it != classIds.end()) return it->second;
+    const uint32_t id = uint32_t(classes.size() / 3);
+    classIds.emplace(key, id);
     classes.push_back(mu);  classes.push_back(sin);  classes.push_back(sout);
-    return uint32_t(classes.size() / 3 - 1);
+    return id;
   }
   void uploadLut (void) {
     if (!lut) return;
     const size_t n = classes.size() / 3;
+    // same bound as the tree engine: beyond 256 MiB of table the caller has to ask for the generic path
+    if (n * lutStride * sizeof(double) > (size_t(256) << 20))
+      throw ApiError(APT_ERR_ARGUMENT, "too many distinct compatibility triples for the table (use APT_FLAG_FORCE_GENERIC)");
     std::vector<double> h (n * lutStride);
     for (size_t c = 0; c < n; c++)
       for (uint32_t d = 0; d < lutStride; d++) {
@@ -223,15 +232,20 @@ uint32_t apt_tree_events (apt_tree *t, apt_event *out, uint32_t cap, int drain) 
   auto &ev = t->engine.events();
   const uint32_t n = uint32_t(std::min<size_t>(cap, ev.size()));
   if (out && n) memcpy(out, ev.data(), n * sizeof(apt_event));
-  if (drain) ev.erase(ev.begin(), ev.begin() + n);
+  if (drain) ev.erase(ev.begin(), ev.begin() + n);        // (moves trivially copyable elements down: cannot throw)
   return n;
 }
 
 uint64_t apt_tree_to_json (apt_tree *t, char *out, uint64_t cap) {
-  if (!t) return 0;
-  const std::string s = t->engine.toJson();
-  if (out && cap) memcpy(out, s.data(), std::min<uint64_t>(cap, s.size()));
-  return s.size();
+  // 0 = failure (an empty tree still dumps a non-empty object); the message is in apt_last_error()
+  uint64_t size = 0;
+  guarded([&] {
+    need(t, "null tree");
+    const std::string s = t->engine.toJson();
+    if (out && cap) memcpy(out, s.data(), std::min<uint64_t>(cap, s.size()));
+    size = s.size();
+  });
+  return size;
 }
 
 int apt_tree_from_json (apt_tree *t, const char *text, uint64_t len) {

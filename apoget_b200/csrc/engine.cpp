@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <limits>
 
 namespace apt {
@@ -56,7 +57,7 @@ void WorkerPool::loop (unsigned t) {
       if (gen_.load(std::memory_order_acquire) == seen) continue;     // woken ahead of the work (wake()): spin for it
     }
     seen = gen_.load(std::memory_order_acquire);
-    (*fn_)(t);
+    try { (*fn_)(t); } catch (...) { workerFailed_.store(true, std::memory_order_release); }
     if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
       std::lock_guard<std::mutex> lk (m_);
       done_.notify_one();
@@ -81,13 +82,20 @@ void WorkerPool::run (const std::function<void(unsigned)> &fn) {
     gen_.fetch_add(1, std::memory_order_acq_rel);
   }
   wake_.notify_all();
-  fn(0);
-  for (int spin = 0; spin < 20000; spin++) {
-    if (pending_.load(std::memory_order_acquire) == 0) return;
-    if (spin < 4096) __builtin_ia32_pause(); else sched_yield();
+  // the workers run *fn_ = the caller's function object: it must outlive them even when the caller's own share throws
+  std::exception_ptr failed;
+  try { fn(0); } catch (...) { failed = std::current_exception(); }
+  bool done = false;
+  for (int spin = 0; spin < 20000 && !done; spin++) {
+    done = pending_.load(std::memory_order_acquire) == 0;
+    if (!done) { if (spin < 4096) __builtin_ia32_pause(); else sched_yield(); }
   }
-  std::unique_lock<std::mutex> lk (m_);
-  done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+  if (!done) {
+    std::unique_lock<std::mutex> lk (m_);
+    done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+  }
+  if (failed) std::rethrow_exception(failed);
+  if (workerFailed_.exchange(false)) throw ApiError(APT_ERR_STATE, "a worker thread failed");
 }
 
 double allocClock (void) { return now(); }
@@ -1287,6 +1295,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
                        uint32_t *outReplaced, uint32_t &done) {
   double t0 = now();
   chunkEpoch_++;
+  curBirth_ = 0;              // (the error path settles the streams at the birth being committed)
   // APT_PROFILE: named time marks of this chunk, printed as successive differences at its end
   std::vector<std::pair<const char*, double>> marks;
   auto mark = [&] (const char *name) { if (profile_) marks.emplace_back(name, now()); };
@@ -1733,6 +1742,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       run++;
     }
     if (run < entryParMin) return 0;
+    curBirth_ = slow_[from];
     const unsigned T = pool_->size();
     const bool wantEvents = !(p_.flags & APT_FLAG_NO_EVENTS);
     struct Local { uint64_t comparisons = 0, n = 0; std::string error; };
@@ -2174,14 +2184,33 @@ void Engine::fromJson (const std::string &text) {
   if (envSize != K_)
     throw ApiError(APT_ERR_ARGUMENT, "Current configuration file specifies an enveloppe size of " + std::to_string(K_)
                    + " whereas the provided PTree was built with " + std::to_string(envSize));     // :949-954
+  // nothing of the input is trusted: ids are bounded by the dump's own nextSID (a later makeNode must not land on
+  // an existing node) and by what a tree can hold, and a dump that fails half-way leaves the tree empty again
+  const uint32_t nextSID = j.at("nextSID").u32();
+  if (nextSID > (1u << 28)) throw ApiError(APT_ERR_ARGUMENT, "JSON: nextSID out of range");
+  struct Rollback {
+    Engine &e;  bool armed = true;
+    ~Rollback (void) {
+      if (!armed) return;
+      for (Species *n: e.nodes_) delete n;
+      e.nodes_.clear();  e.root_ = nullptr;  e.width_ = 0;  e.nextNodeID_ = 0;  e.step_ = 0;  e.stillborns_ = 0;
+      e.aliveSpecies_.clear();  e.refresh_.clear();  e.fillUpdates_.clear();  e.freeSlots_.clear();
+      for (uint32_t s = e.nSlots_; s-- > 0; ) e.freeSlots_.push_back(s);       // every slot is free again
+      std::fill(e.sidSlot_.begin(), e.sidSlot_.end(), INV);
+    }
+  } rollback { *this };
   step_ = j.at("_step").u32();
   stillborns_ = j.at("_stillborns").u32();
 
   struct Rec {
-    Engine &e;
+    Engine &e;  const uint32_t nextSID;
     Species* node (const JVal &jn) {                                        // rebuildHierarchy, :908-927
-      Species *n = new Species;
-      n->sid = jn.at("id").u32();
+      const uint32_t id = jn.at("id").u32();
+      if (id >= nextSID) throw ApiError(APT_ERR_ARGUMENT, "JSON: species id not below nextSID");
+      if (id < e.nodes_.size() && e.nodes_[id]) throw ApiError(APT_ERR_ARGUMENT, "JSON: duplicate species id");
+      std::unique_ptr<Species> holder (new Species);
+      Species *n = holder.get();
+      n->sid = id;
       n->slot = e.allocSlot();
       n->reps.resize(e.K_);
       n->dist.assign(size_t(e.K_) * e.K_, 0.f);
@@ -2215,20 +2244,19 @@ void Engine::fromJson (const std::string &text) {
         n->dist[a * e.K_ + b] = n->dist[b * e.K_ + a] = float(dd.idx(2).num);
       }
       if (e.nodes_.size() <= n->sid) e.nodes_.resize(std::max<size_t>(n->sid + 1, e.nodes_.size() * 2), nullptr);
-      if (e.nodes_[n->sid]) throw ApiError(APT_ERR_ARGUMENT, "JSON: duplicate species id");
-      e.nodes_[n->sid] = n;
+      e.nodes_[n->sid] = holder.release();
       e.width_++;
       n->full_upload = true;
       e.queueRefresh(n);
       for (const JVal &c: jn.at("children").arr) node(c);
       return n;
     }
-  } rec { *this };
+  } rec { *this, nextSID };
   const JVal &jt = j.at("tree");
   if (jt.type == JVal::OBJ) root_ = rec.node(jt);
   aliveSpecies_.clear();
   for (const JVal &a: j.at("alive").arr) aliveSpecies_.insert(a.u32());
-  nextNodeID_ = j.at("nextSID").u32();
+  nextNodeID_ = nextSID;
 
   // Ensure correct parenting (:960-962): contributors.update({}) = stable_sort + currentMain on stored flags
   for (Species *n: nodes_) {
@@ -2238,6 +2266,7 @@ void Engine::fromJson (const std::string &text) {
     Species *newMC = updateParent(n, currentMain(n));
     if (newMC) newMC->children.push_back(n);
   }
+  rollback.armed = false;
 }
 
 } // namespace apt

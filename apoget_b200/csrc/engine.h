@@ -110,6 +110,7 @@ private:
   const std::function<void(unsigned)> *fn_ = nullptr;
   std::atomic<uint64_t> gen_ { 0 };
   std::atomic<unsigned> pending_ { 0 };
+  std::atomic<bool> workerFailed_ { false };
   bool stop_ = false;
   uint64_t hint_ = 0;
 };

@@ -264,6 +264,36 @@ def test_json_load_refuses_other_enveloppe_size(hostsim):
     assert "enveloppe size" in str(e.value)
 
 
+def test_json_load_is_validated_and_transactional(hostsim):
+    """A dump that fails half-way (species id not below nextSID, a duplicate id, a child that is not a node) must
+    leave the tree EMPTY, so that a good dump can still be loaded into it afterwards."""
+    import copy
+    name = "c2_b256_k10"
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    good = golden_json(name)
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+
+    def deepest(node):
+        while node["children"]:
+            node = node["children"][-1]
+        return node
+    bad1 = copy.deepcopy(good)
+    deepest(bad1["tree"])["id"] = good["nextSID"] + 5             # a later makeNode would land on it
+    bad2 = copy.deepcopy(good)
+    deepest(bad2["tree"])["id"] = bad2["tree"]["id"]              # duplicate
+    bad3 = copy.deepcopy(good)
+    deepest(bad3["tree"])["children"] = [{"id": 1}]               # truncated node
+    bad4 = copy.deepcopy(good)
+    bad4["nextSID"] = 2**31                                        # would size the node table by it
+    for bad in (bad1, bad2, bad3, bad4):
+        with pytest.raises(_lib.AptError):
+            tree.from_json(bad)
+        assert tree.stats()["width"] == 0 and tree.stats()["next_sid"] == 0
+    tree.from_json(good)
+    assert tree.to_json() == golden_roundtrip_json(name)
+
+
 def test_round_to_float_matches_the_hardware_conversion(tmp_path):
     """apt::round_to_float (csrc/round24.h) is what the dense sweep uses instead of the two conversions of the
     reference's `float avg += double c` (phylogenetictree.hpp:465-472): it must equal double(float(s)) bit for bit."""
