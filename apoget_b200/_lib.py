@@ -73,6 +73,7 @@ SYMBOLS = {
     "apt_classify_dense_shard_dev": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, ctypes.c_uint32, ctypes.c_uint32,
                                                     ctypes.c_uint32, u64p, vp]),
     "apt_combine_shards_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp, vp, vp]),
+    "apt_pool_uses_tensor_cores": (ctypes.c_int, [vp]),
     "apt_distance_matrix": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, ctypes.c_uint32, vp, vp]),
     "apt_env_contribution": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, vp, vp, vp, vp]),
     "apt_mate_compat": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, vp, ctypes.c_uint32, vp, vp, vp, vp]),

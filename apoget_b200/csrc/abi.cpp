@@ -417,6 +417,8 @@ int apt_classify_dense (apt_pool *p, uint32_t n_births, const uint32_t *payload,
   });
 }
 
+int apt_pool_uses_tensor_cores (apt_pool *p) { return p && p->tcWanted() ? 1 : 0; }
+
 int apt_classify_dense_shard_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_payload, const float *d_compat,
                                   uint32_t species_offset, uint32_t rank, uint32_t world,
                                   const uint64_t *peer_records, void *stream) {

@@ -31,6 +31,10 @@ class Pool:
 
     __del__ = close
 
+    def uses_tensor_cores(self) -> bool:
+        """True when the dense sweeps of this pool run as an int8 GEMM on the tensor cores (tc_dense.cu)."""
+        return bool(lib().apt_pool_uses_tensor_cores(self._h))
+
     def score_pairs(self, payload, compat, pair_birth, pair_species):
         payload = _u32(payload).reshape(-1, self.words)
         n = payload.shape[0]

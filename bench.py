@@ -48,6 +48,7 @@ WORKLOAD = dict(kind=synth.BITS, words=8, flips=0.5, sigma=12.0, hybrid=0.05, bu
 TREE_CFG = dict(K=10)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/)
 TRAFFIC = {"score_pairs_kernel": 6.10e6, "resolve_streams_kernel": 6.14e6}
+TRAFFIC_SOURCE = "ncu --set full capture of an earlier run of this workload (profiles/r01h_resolve_streams_ncu.txt), not measured in this run"
 METRIC = "births classified/sec (species assignment, reference-exact)"
 UNIT = "births/s"
 
@@ -127,7 +128,9 @@ def main() -> None:
     ap.add_argument("--pop", type=int, default=100_000, help="births per step (C2: 100 000)")
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-dense", action="store_true", help="skip the dense-sweep side measurement")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-sweep measurement")
+    ap.add_argument("--dense-births", type=int, default=1_000_000, help="births of the dense sweep (configs[3]: 1 M)")
+    ap.add_argument("--dense-check", type=int, default=10240, help="births of the dense sweep verified against the oracle (x all species)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                    # timing rule: W >= 3
@@ -397,7 +400,7 @@ def main() -> None:
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(n_launches[0]),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": TRAFFIC.get(kname), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": TRAFFIC.get(kname), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                      "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "births_per_launch": units, "evals_per_s_kernel": units * K / (kernel_ms * 1e-3) if kernel_ms else 0,
                      "births_per_s_kernel": units / (kernel_ms * 1e-3) if kernel_ms else 0,
@@ -419,24 +422,37 @@ def main() -> None:
         "species": width, "host_cores": os.cpu_count(), "host_threads_per_tree": os.environ.get("APT_HOST_THREADS", "default (12 on >= 16 cores)"),
     }
 
-    if rank == 0 and world == 1 and not args.no_dense:
-        # second headline of BASELINE.json ("genome-distance evals/sec vs int-pipe roofline"): the dense
-        # sweep of configs[3] (4096-bit genomes, 100 k enveloppe members) on a 131 072-birth slice
+    if not args.no_dense:
+        # second headline of BASELINE.json ("genome-distance evals/sec vs ... roofline", north_star target): the dense
+        # sweep of configs[3] at its FULL size -- 1 M births x 100 000 enveloppe members of 4096 bits -- on the tensor
+        # cores; with N > 1 GPUs the species are sharded over the ranks, every rank sweeps all births against its shard
+        # and the per-birth records are exchanged by peer-memory stores from the sweep kernel itself (NVLink), rank 0
+        # also timing the unsharded sweep for the speed-up.  `check` births are verified against the oracle, each
+        # against ALL species.
         import argparse as _ap
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_dense
-        d = bench_dense.run(_ap.Namespace(config="c4", births=131072, species=0, iters=2, check=8, exchange="p2p"))
-        line["dense_sweep"] = {
-            "workload": "C4: 4096-bit Hamming genomes, every birth x 10 000 species x K=10 (131 072-birth slice of the 1 M batch)",
-            "evals_per_s": d["evals_per_s"], "births_per_s": d["births_per_s"], "ms": d["ms"],
-            "roofline": {"bound": "int_pipe (popc32)", "achieved": d["pipe_ops_per_s"], "peak": d["pipe_peak_measured"],
-                         "unit": "popc32/s", "frac": d["frac_of_pipe_peak"],
-                         "peak_source": "measured on this GPU by apt_microbench (XOR+POPC chains)",
-                         "note": "achieved = ALGORITHMIC popc32 (one per genome word per eval); the kernel's carry-save "
-                                 "accumulation issues only 2 hardware POPC per 4 words and moves the rest to LOP3 on the "
-                                 "ALU pipe, so this fraction can exceed 1; int_pipe_model is the two-pipe bound",
-                         "int_pipe_model": d["int_pipe_model"]},
-            "oracle_checked_births": d["oracle_checked_births"], "oracle_mismatches": d["oracle_mismatches"]}
+        gc.enable()
+        d = bench_dense.run(_ap.Namespace(config="c4", births=args.dense_births, species=0, iters=2, check=args.dense_check,
+                                          exchange="p2p", also_single=True))
+        if rank == 0:
+            dense = {
+                "workload": f"C4: 4096-bit Hamming genomes, {d['births']} births x 10 000 species x K=10 = 100 000 enveloppe members"
+                            + (f", species sharded over {world} GPUs" if world > 1 else ""),
+                "path": d["path"], "exchange": d["exchange"], "n_gpus": world,
+                "ms": d["ms"], "evals_per_s": d["evals_per_s"], "births_per_s": d["births_per_s"],
+                "roofline": d["tensor_roofline"] or {
+                    "bound": "int_pipe (popc32)", "achieved": d["pipe_ops_per_s"], "peak": d["pipe_peak_measured"], "unit": "popc32/s",
+                    "frac": d["frac_of_pipe_peak"], "int_pipe_model": d["int_pipe_model"]},
+                "popc32_equivalent": {"achieved": d["pipe_ops_per_s"], "peak_measured": d["pipe_peak_measured"],
+                                      "frac": d["frac_of_pipe_peak"],
+                                      "note": "algorithmic popc32 (one per genome word per eval) against the measured POPC-pipe "
+                                              "peak: what a popcount kernel at 100 % of the integer pipe would reach is 1.0"},
+                "oracle_checked_births": d["oracle_checked_births"], "oracle_checked_pairs": d["oracle_checked_pairs"],
+                "oracle_mismatches": d["oracle_mismatches"]}
+            if "speedup_vs_1gpu" in d:
+                dense["single_gpu_ms"] = d["single_gpu_ms"]
+                dense["speedup_vs_1gpu"] = d["speedup_vs_1gpu"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
         synth.write_trace(path, trace)
@@ -446,7 +462,16 @@ def main() -> None:
                                 "sample": f"first {n} timed steps ({n * pop} births) of the same trace after the same "
                                           f"{SETUP_GENS}+{args.warmup} untimed generations; addGenome loop only; "
                                           f"1 thread (the reference is single-threaded); host has {os.cpu_count()} cores"}
+        rc = run_reference_arm(path, pop, args.warmup, n, cref=True)
+        if rc["kind"] == "reference":
+            line["cpu_baseline_cref"] = {
+                "value": rc["value"], "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": "same sample; the reference with ONE token changed -- std::cref(nodes) in the eligibility binder "
+                          "(src/core/tree/node.hpp:177), which otherwise copies the whole species map on every insertion; "
+                          "identical output (tests/test_oracle.py).  The honest CPU figure for a speed-up"}
     if rank == 0:
+        if not args.no_dense:
+            line["dense_sweep"] = dense          # last: the north-star numbers survive a `tail` of the line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -227,6 +227,8 @@ int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_pa
  *
  * apt_distance_matrix: the births x members distance kernel on its own (north_star (1)): out[i * n_b + j] =
  * Hamming distance of genome i of payload_a and genome j of payload_b, through the same tensor-core pipeline. */
+/* 1 when apt_classify_dense* take the tensor-core path for this pool (see above), else 0. */
+int apt_pool_uses_tensor_cores (apt_pool *p);
 int apt_distance_matrix (const apt_params *params, uint32_t n_a, const uint32_t *payload_a, uint32_t n_b,
                          const uint32_t *payload_b, uint32_t *out);
 

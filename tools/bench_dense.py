@@ -73,15 +73,6 @@ def run(args):
     bc = np.zeros((B, 3), dtype=np.float32)
     bc[:, 1:] = sigma
 
-    # species shard of this rank
-    s_lo, s_hi = shard.shard_range(S, rank, world)
-    pool = Pool(kind, words, reps[s_lo:s_hi], rc[s_lo:s_hi], fill[s_lo:s_hi], device=local, K=K)
-
-    peaks = np.zeros(4, dtype=np.float64)
-    _lib.check(_lib.lib().apt_microbench(local, peaks.ctypes.data_as(_lib.f64p)))
-    cvt = np.zeros(1, dtype=np.float64)
-    _lib.check(_lib.lib().apt_microbench_cvt(local, cvt.ctypes.data_as(_lib.f64p)))
-
     d_births = torch.from_numpy(births.view(np.int32)).cuda()
     d_compat = torch.from_numpy(bc).cuda()
     d_best = torch.empty(B, dtype=torch.int32, device="cuda")
@@ -90,6 +81,37 @@ def run(args):
     d_count = torch.empty(B, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream()
     vp = ctypes.c_void_p
+
+    # N > 1: rank 0 first sweeps the WHOLE pool alone (the other ranks wait), so that the line carries the sharded
+    # sweep's speed-up over one GPU measured in the same run on the same inputs
+    single_ms = None
+    if world > 1 and getattr(args, "also_single", False):
+        if rank == 0:
+            whole = Pool(kind, words, reps, rc, fill, device=local, K=K)
+            ts = []
+            for it in range(3):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                whole.classify_dense_dev(B, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), vp(d_best.data_ptr()),
+                                         vp(d_score.data_ptr()), vp(d_first.data_ptr()), vp(d_count.data_ptr()), vp(stream.cuda_stream))
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if it:
+                    ts.append(e0.elapsed_time(e1))
+            single_ms = min(ts)
+            whole.close()
+            del whole
+        dist.barrier()
+
+    # species shard of this rank
+    s_lo, s_hi = shard.shard_range(S, rank, world)
+    pool = Pool(kind, words, reps[s_lo:s_hi], rc[s_lo:s_hi], fill[s_lo:s_hi], device=local, K=K)
+
+    peaks = np.zeros(4, dtype=np.float64)
+    _lib.check(_lib.lib().apt_microbench(local, peaks.ctypes.data_as(_lib.f64p)))
+    cvt = np.zeros(1, dtype=np.float64)
+    _lib.check(_lib.lib().apt_microbench_cvt(local, cvt.ctypes.data_as(_lib.f64p)))
 
     def sweep():
         pool.classify_dense_dev(B, vp(d_births.data_ptr()), vp(d_compat.data_ptr()), vp(d_best.data_ptr()),
@@ -134,19 +156,19 @@ def run(args):
         ms = float(t[0])
 
     best, score, first, count = [x.cpu().numpy() for x in res]
-    # ---- verification against the CPU oracle on a sample of births (all species) ----
-    bad = 0
+    # ---- verification against the CPU oracle: `check` births x ALL species (threaded scorer of oracle/) ----
+    bad, checked = 0, 0
     if rank == 0 and args.check:
         import oracle
-        for b in rng.choice(B, size=min(args.check, B), replace=False):
-            sc = np.array([oracle.score(kind, births[b], bc[b], reps[s], rc[s])[0] for s in range(S)], dtype=np.float32)
-            if kind == 0:
-                ok = (int(best[b]) == int(np.argmax(sc)) and np.float32(score[b]) == sc.max()
-                      and int(count[b]) == int((sc > 0).sum())
-                      and int(first[b]) == (int(np.nonzero(sc > 0)[0][0]) if (sc > 0).any() else -1))
-            else:
-                ok = abs(float(score[b]) - float(sc.max())) <= 1e-5
-            bad += (not ok)
+        idx = np.sort(rng.choice(B, size=min(args.check, B), replace=False))
+        checked = int(idx.size)
+        ob, os_, of, oc = oracle.score_dense(kind, births[idx], bc[idx], reps, rc, fill)
+        if kind == 0:
+            ok = (best[idx].view(np.uint32) == ob) & (score[idx] == os_) & (first[idx].view(np.uint32) == of) \
+                & (count[idx].view(np.uint32) == oc)
+        else:
+            ok = np.abs(score[idx] - os_) <= 1e-5
+        bad = int((~ok).sum())
     evals = float(B) * S * K
     ops = evals * (words if kind == 0 else 3 * words)
     peak = peaks[0] if kind == 0 else peaks[3] * 2
@@ -161,21 +183,42 @@ def run(args):
         t_popc, t_alu = 2 * steps / peaks[0], 8 * steps / peaks[1]
         model = {"popc_per_step": 2, "alu_ops_per_step": 8, "bound": "alu (lop3)" if t_alu >= t_popc else "popc",
                  "min_ms": 1e3 * max(t_popc, t_alu) / world, "frac": max(t_popc, t_alu) / world / (ms * 1e-3)}
+    tc = pool.uses_tensor_cores()
+    tensor = None
+    if tc:
+        # tensor-core sweep: the distances are an int8 GEMM of 2 * births * members * bits operations.  Denominator:
+        # twice the bf16 rate the driver measured on this pool (int8 runs at twice the bf16 rate on sm_100; nominal
+        # 4.5 vs 2.25 PFLOP/s dense) -- the sustained figure for sweeps of a second, the burst one for short ones.
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                mp = json.load(f)
+            bf16 = float(mp["bf16_tflops_sustained" if ms > 100 else "bf16_tflops"])
+            src = "2 x measured cuBLAS bf16 (MEASURED_PEAKS.json, %s)" % ("sustained" if ms > 100 else "burst")
+        except Exception:
+            bf16, src = 1590.0, "2 x fallback bf16 (B200_PROFILING.md)"
+        tops = 2.0 * evals * words * 32 / (ms * 1e-3) / 1e12
+        tensor = {"bound": "tensor", "achieved": tops, "peak": 2 * bf16 * world, "unit": "TOP/s (int8)",
+                  "frac": tops / (2 * bf16 * world), "peak_source": src}
     out = None
     if rank == 0:
         out = ({
             "bench": "dense sweep", "config": args.config, "n_gpus": world,
+            "path": ("tensor cores: int8 tcgen05 GEMM, (L - a.b)/2, scoring epilogue on TMEM accumulators" if tc
+                     else "integer pipes: carry-save popcount tile"),
             "exchange": ("peer-memory stores from the sweep kernel + device barrier + combine kernel" if p2p is not None
                          else ("NCCL all-gather + torch reduction" if world > 1 else "none")), "births": B, "species": S, "K": K,
             "genome_words": words, "kind": "bits/hamming" if kind == 0 else "f32/l2", "ms": ms,
             "births_per_s": B / (ms * 1e-3), "evals_per_s": evals / (ms * 1e-3),
             "pipe_ops_per_s": ops / (ms * 1e-3), "pipe": "popc32 (+xor)" if kind == 0 else "fp32 flop (sub, fma)",
             "pipe_peak_measured": peak, "frac_of_pipe_peak": ops / (ms * 1e-3) / (peak * world),
-            "int_pipe_model": model,
+            "int_pipe_model": None if tc else model, "tensor_roofline": tensor,
             "microbench": {"popc32_per_s": peaks[0], "lop3_per_s": peaks[1], "dfma_per_s": peaks[2], "ffma_per_s": peaks[3],
                            "f2f_cvt_per_s": cvt[0]},
-            "accepting_births_frac": float((count > 0).mean()), "oracle_checked_births": int(min(args.check, B)),
-            "oracle_mismatches": int(bad)})
+            "accepting_births_frac": float((count > 0).mean()), "oracle_checked_births": checked,
+            "oracle_checked_pairs": checked * S, "oracle_mismatches": int(bad)})
+        if single_ms is not None:
+            out["single_gpu_ms"] = single_ms
+            out["speedup_vs_1gpu"] = single_ms / ms
     if own_group:
         dist.destroy_process_group()
     return out
@@ -187,7 +230,8 @@ def main():
     ap.add_argument("--births", type=int, default=0)
     ap.add_argument("--species", type=int, default=0)
     ap.add_argument("--iters", type=int, default=3)
-    ap.add_argument("--check", type=int, default=24, help="births verified against the CPU oracle")
+    ap.add_argument("--check", type=int, default=10240, help="births verified against the CPU oracle, each against ALL species")
+    ap.add_argument("--also-single", action="store_true", help="N > 1: rank 0 also times the unsharded sweep (speedup_vs_1gpu)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: records stored into the peers' buffers by the sweep kernel (p2p) or NCCL all-gather")
     out = run(ap.parse_args())
