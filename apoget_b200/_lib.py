@@ -56,6 +56,8 @@ SYMBOLS = {
     "apt_tree_events": (ctypes.c_uint32, [vp, vp, ctypes.c_uint32, ctypes.c_int]),
     "apt_tree_to_json": (ctypes.c_uint64, [vp, ctypes.c_char_p, ctypes.c_uint64]),
     "apt_tree_from_json": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_uint64]),
+    "apt_tree_clone": (ctypes.c_int, [vp, ctypes.POINTER(vp)]),
+    "apt_tree_trimmed": (ctypes.c_uint32, [vp, vp, ctypes.c_uint32, ctypes.c_int]),
     "apt_tree_node_info": (ctypes.c_int, [vp, ctypes.c_uint32, ctypes.POINTER(AptNodeInfo)]),
     "apt_tree_node_children": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.c_uint32]),
     "apt_tree_node_contributors": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.c_uint32]),

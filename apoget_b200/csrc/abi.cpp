@@ -255,6 +255,24 @@ int apt_tree_from_json (apt_tree *t, const char *text, uint64_t len) {
   });
 }
 
+int apt_tree_clone (apt_tree *src, apt_tree **out) {
+  return guarded([&] {
+    need(src && out, "null argument");
+    std::unique_ptr<apt_tree> t (new apt_tree(src->engine.params()));
+    t->engine.cloneFrom(src->engine);
+    *out = t.release();
+  });
+}
+
+uint32_t apt_tree_trimmed (apt_tree *t, uint32_t *out, uint32_t cap, int drain) {
+  if (!t) return 0;
+  auto &v = t->engine.trimmedSpecies();
+  const uint32_t n = uint32_t(std::min<size_t>(cap, v.size()));
+  if (out && n) memcpy(out, v.data(), n * sizeof(uint32_t));
+  if (drain) v.erase(v.begin(), v.begin() + n);
+  return out ? n : uint32_t(v.size());
+}
+
 int apt_tree_node_info (apt_tree *t, uint32_t sid, apt_node_info *out) {
   return guarded([&] {
     need(t && out, "null argument");

@@ -323,6 +323,7 @@ void Engine::performStillbornTrimming (void) {
       width_--;
       freeSlots_.push_back(s->slot);
       fillUpdates_.push_back(s->slot);  fillUpdates_.push_back(0);
+      trimmedSids_.push_back(s->sid);
       s->trimmed = true;  s->stale_mask = 0;                // nothing left to refresh
       graveyard_.push_back(s);                              // `root_` may still point at it, as in the reference
     }
@@ -2010,6 +2011,45 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
     throw;
   }
   if (nDone) *nDone = done;
+}
+
+/// Copy construction of the reference (phylogenetictree.hpp:98-109 with deepcopy :123-136), into an EMPTY tree: the
+/// nodes reachable from `that`'s root are copied (data, enveloppe, distances, contributors; children in their order),
+/// then eligibilities and parents are recomputed tree-wide (:103).  As in the reference, the set of alive species
+/// and the statistics are NOT copied, and species that are in nobody's children list (same-step orphans) are lost.
+void Engine::cloneFrom (const Engine &that) {
+  if (root_ || nextNodeID_ || width_) throw ApiError(APT_ERR_STATE, "cloning needs an empty tree");
+  if (that.K_ != K_ || that.W_ != W_ || that.p_.kind != p_.kind) throw ApiError(APT_ERR_ARGUMENT, "cloning between trees of different shapes");
+  nextNodeID_ = that.nextNodeID_;  stillborns_ = that.stillborns_;  step_ = that.step_;
+  struct Rec {
+    Engine &e;  const Engine &o;
+    Species* node (const Species *src) {
+      Species *n = new Species;
+      n->sid = src->sid;
+      n->slot = e.allocSlot();
+      n->first = src->first;  n->last = src->last;  n->count = src->count;  n->alive = src->alive;  n->pending = src->pending;
+      n->contribs = src->contribs;
+      n->k = src->k;  n->reps = src->reps;  n->dist = src->dist;
+      for (uint32_t r = 0; r < n->k; r++) {
+        RepMeta &m = n->reps[r];
+        m.cls = e.classOf(m.mu, m.sin, m.sout);
+        memcpy(&e.hPayload_[(size_t(n->slot) * e.K_ + r) * e.wp_], o.repPayload(src, r), e.wp_ * sizeof(uint32_t));
+      }
+      if (e.nodes_.size() <= n->sid) e.nodes_.resize(std::max<size_t>(n->sid + 1, e.nodes_.size() * 2), nullptr);
+      e.nodes_[n->sid] = n;
+      e.width_++;
+      n->full_upload = true;
+      e.queueRefresh(n);
+      for (const Species *c: src->children) {
+        Species *cc = node(c);
+        n->children.push_back(cc);
+      }
+      return n;
+    }
+  } rec { *this, that };
+  // (`that.root_` may point at a trimmed node, as in the reference; it is copied all the same, :101)
+  if (that.root_) root_ = rec.node(that.root_);
+  updateElligibilities();
 }
 
 // ---- JSON dump (layout of phylogenetictree.hpp:887-941) ---------------------

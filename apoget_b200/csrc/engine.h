@@ -200,6 +200,9 @@ public:
   std::vector<apt_event>& events (void) { return events_; }
   std::string toJson (void) const;
   void fromJson (const std::string &text);
+  void cloneFrom (const Engine &that);
+  std::vector<uint32_t>& trimmedSpecies (void) { return trimmedSids_; }
+  uint32_t stillborns (void) const { return stillborns_; }
   Species* nodeAt (uint32_t sid) const;
   Species* root (void) const { return root_; }
   const std::set<uint32_t>& aliveSpecies (void) const { return aliveSpecies_; }
@@ -223,6 +226,7 @@ private:
   std::set<uint32_t> aliveSpecies_;
   uint32_t insertions_ = 0, deletions_ = 0, comparisons_ = 0, branching_ = 0;
   std::vector<apt_event> events_;
+  std::vector<uint32_t> trimmedSids_;     // species removed by stillborn trimming since the binding last asked
 
   // ---- host mirror of the pool ----
   std::vector<uint32_t> hPayload_;        // [slot][K][wp]

@@ -2,13 +2,14 @@
 // (reference: src/core/tree/phylogenetictree.hpp) whose species-assignment hot path runs on a
 // B200 through libapt_b200.so (C ABI: include/apt_b200.h).
 //
-// Same class name, member names, argument meaning and callback order as the reference; the types
-// below mirror src/core/tree/treetypes.h (GID, SID, PID, Genealogy, InsertionResult),
-// callbacks.hpp (Callbacks_t) and ptreeconfig.h (config::PTree).  A host program switches by
-// including this header, using namespace `apt` instead of `phylogeny`, and describing how its
-// genome is laid out on the device:
+// Same namespaces, class names, member names, argument meaning and callback order as the reference: the types
+// below mirror src/core/tree/treetypes.h (GID, SID, PID, Genealogy, InsertionResult), node.hpp (Node, Node::Ptr,
+// Representative), speciesdata.hpp, speciescontributors.h (the read-only part), callbacks.hpp (Callbacks_t) in
+// namespace `phylogeny`, and ptreeconfig.h (::config::PTree).  A host program switches by including this header
+// instead of "kgd/apt/core/tree/phylogenetictree.hpp" and describing how its genome is laid out on the device
+// (tests/cpp/test_dropin.cpp compiles unchanged against either header); `apt` is an alias of `phylogeny`:
 //
-//   template <> struct apt::DeviceEncoding<MyGenome> {
+//   template <> struct phylogeny::DeviceEncoding<MyGenome> {
 //     static constexpr apt_kind kind = APT_BITS;      // or APT_F32
 //     static constexpr uint32_t words = 8;            // 32-bit payload words
 //     static void encode (const MyGenome &g, uint32_t *payload, float compat[3]);
@@ -18,14 +19,18 @@
 // (Hamming or L2 over the payload; the two-sided gaussian of src/core/crossover.h:76-92 with
 // compat = {optimalDistance, inbreedTolerance, outbreedTolerance}).  New with respect to the
 // reference: addGenomes(first, last, out), whose result is defined as that of calling addGenome on
-// every element in order.  Not provided ("out of scope"): copy construction /
-// assignment (:98-118; trees are movable) and logTo (:874-879).
+// every element in order; trees are movable as well as copyable.
+// nodeAt() / root() / Node::children() / Node::parent() hand out Node::Ptr handles like the reference's; a handle's
+// public fields (data, contributors, distances; rset is always live) are brought up to date whenever it is obtained
+// through one of those accessors -- fetch it again after mutating the tree instead of keeping it across mutations.
 // toJson / saveTo / fromJson / readFrom need nlohmann::json: define APT_WITH_JSON before including.
 #ifndef APT_PHYLOGENETICTREE_HPP
 #define APT_PHYLOGENETICTREE_HPP
 
+#include <algorithm>
 #include <cstdint>
 #include <deque>
+#include <fstream>
 #ifdef APT_DROPIN_PROFILE
 #include <chrono>
 #include <cstdio>
@@ -46,13 +51,38 @@
 #include "../apt_b200.h"
 
 #ifdef APT_WITH_JSON
-#include <fstream>
 #include <nlohmann/json.hpp>
 #endif
 
-namespace apt {
+namespace config {
+/// ptreeconfig.h:17-69 with the defaults of ptreeconfig.cpp:7-19, in the reference's own (global) namespace `config`.
+/// Values are read when a tree is constructed (the reference latches rsetSize there too, phylogenetictree.hpp:90);
+/// every accessor returns a reference that can be assigned to (the reference reads them from a config file).
+struct PTree {
+  using uint = unsigned int;
+#define APT_PARAM(TYPE, NAME, VALUE) static TYPE& NAME (void) { static TYPE v = VALUE; return v; }
+  APT_PARAM(double, compatibilityThreshold, .1)
+  APT_PARAM(double, similarityThreshold, .5)
+  APT_PARAM(double, avgCompatibilityThreshold, .25)
+  APT_PARAM(uint, rsetSize, 5)
+  APT_PARAM(bool, simpleNewSpecies, true)
+  APT_PARAM(uint, stillbornTrimmingPeriod, 100)
+  APT_PARAM(float, stillbornTrimmingThreshold, .25f)
+  APT_PARAM(float, stillbornTrimmingDelay, 4.f)
+  APT_PARAM(uint, stillbornTrimmingMinDelay, 200)
+  APT_PARAM(bool, DEBUG_FULL_CONTINUOUS, true)
+  APT_PARAM(int, DEBUG_ENV_CRIT, 1)
+#undef APT_PARAM
+};
+} // namespace config
 
+namespace phylogeny {
+
+namespace config = ::config;
 using uint = unsigned int;
+#ifdef APT_WITH_JSON
+using json = nlohmann::json;
+#endif
 
 // ---- treetypes.h ----------------------------------------------------------------------------
 enum class GID : uint { INVALID = uint(-1) };                        // treetypes.h:24-26
@@ -96,7 +126,18 @@ struct Genealogy {
     generation = std::max(mo.generation, fa.generation) + 1;
   }
   void setAsPrimordial (GIDManager &m) { self = PID(m()); mother = PID(); father = PID(); generation = 0; }
+  friend bool operator== (const Genealogy &l, const Genealogy &r) {
+    return l.mother == r.mother && l.father == r.father && l.self == r.self && l.generation == r.generation;
+  }
 };
+
+#ifdef APT_WITH_JSON
+// treetypes.h:104-107, 158-169 (the generation is not serialised by the reference either)
+inline void to_json (json &j, const PID &p) { j["g"] = uint(p.gid); j["s"] = uint(p.sid); }
+inline void from_json (const json &j, PID &p) { p.gid = GID(j["g"].get<uint>()); p.sid = SID(j["s"].get<uint>()); }
+inline void to_json (json &j, const Genealogy &g) { j["m"] = g.mother; j["f"] = g.father; j["s"] = g.self; }
+inline void from_json (const json &j, Genealogy &g) { from_json(j["m"], g.mother); from_json(j["f"], g.father); from_json(j["s"], g.self); }
+#endif
 
 /// treetypes.h:191-195
 template <typename UserData>
@@ -110,6 +151,11 @@ struct NoUserData {
   NoUserData (void) {}
   NoUserData (GID) {}
   void removedFromEnveloppe (void) const {}
+#ifdef APT_WITH_JSON
+  friend void to_json (json &j, const NoUserData&) { j = nullptr; }
+  friend void from_json (const json&, NoUserData&) {}
+#endif
+  friend void assertEqual (const NoUserData&, const NoUserData&, bool) {}
 };
 
 /// callbacks.hpp:16-45 -- specialise for your tree type to receive the events
@@ -122,25 +168,157 @@ struct Callbacks_t {
   void onMajorContributorChanged (SID, SID, SID) {}
 };
 
-namespace config {
-/// ptreeconfig.h:17-69 with the defaults of ptreeconfig.cpp:7-19.  Values are read when a tree is
-/// constructed (the reference latches rsetSize there too, phylogenetictree.hpp:90).
-struct PTree {
-#define APT_PARAM(TYPE, NAME, VALUE) static TYPE& NAME (void) { static TYPE v = VALUE; return v; }
-  APT_PARAM(double, compatibilityThreshold, .1)
-  APT_PARAM(double, similarityThreshold, .5)
-  APT_PARAM(double, avgCompatibilityThreshold, .25)
-  APT_PARAM(uint, rsetSize, 5)
-  APT_PARAM(bool, simpleNewSpecies, true)
-  APT_PARAM(uint, stillbornTrimmingPeriod, 100)
-  APT_PARAM(float, stillbornTrimmingThreshold, .25f)
-  APT_PARAM(float, stillbornTrimmingDelay, 4.f)
-  APT_PARAM(uint, stillbornTrimmingMinDelay, 200)
-  APT_PARAM(bool, DEBUG_FULL_CONTINUOUS, true)
-  APT_PARAM(int, DEBUG_ENV_CRIT, 1)
-#undef APT_PARAM
+/// speciesdata.hpp:15-31
+struct SpeciesData {
+  uint firstAppearance, lastAppearance, count, currentlyAlive, pendingCandidates;
 };
-} // namespace config
+
+/// speciescontributors.h:16-86, the read-only part (the engine maintains the collection)
+class Contributor {
+  SID _speciesID;  uint _count;  bool _elligible;
+public:
+  Contributor (void) : Contributor(SID::INVALID, uint(-1), false) {}
+  Contributor (SID sid, uint initialCount, bool elligible) : _speciesID(sid), _count(initialCount), _elligible(elligible) {}
+  SID speciesID (void) const { return _speciesID; }
+  uint count (void) const { return _count; }
+  bool elligible (void) const { return _elligible; }
+};
+
+/// speciescontributors.h:118-206, the read-only part
+class Contributors {
+  SID nodeID;
+  std::vector<Contributor> vec;
+public:
+  Contributors (void) : Contributors(SID::INVALID) {}
+  Contributors (SID id) : nodeID(id) {}
+  Contributors (SID id, std::vector<Contributor> &&v) : nodeID(id), vec(std::move(v)) {}
+  SID getNodeID (void) const { return nodeID; }
+  const std::vector<Contributor>& data (void) const { return vec; }
+  auto begin (void) const { return vec.begin(); }
+  auto end (void) const { return vec.end(); }
+};
+
+namespace _details {
+/// treetypes.h:233-259
+template <typename T>
+struct ordered_pair {
+  T first, second;
+  ordered_pair (T a, T b) : first(std::min(a, b)), second(std::max(a, b)) {}
+  friend bool operator< (const ordered_pair &l, const ordered_pair &r) { return l.first != r.first ? l.first < r.first : l.second < r.second; }
+};
+using DistanceMap = std::map<ordered_pair<uint>, float>;
+
+/// What the reference's utils::assertEqual does on a mismatch is Tools' business (not vendored); here: std::logic_error
+[[noreturn]] inline void unequal (const std::string &what) { throw std::logic_error("assertEqual: " + what + " differ"); }
+template <typename T> void same (const T &l, const T &r, const char *what) { if (!(l == r)) unequal(what); }
+} // namespace _details
+
+template <typename GENOME, typename UDATA> class PhylogeneticTree;
+
+/// node.hpp:16-243.  Handles to the species of a tree: obtained from PhylogeneticTree::nodeAt / root and from
+/// children() / parent(); `rset` holds the host-side genome and user-data objects of the enveloppe (always live),
+/// the other public fields mirror the engine's state as of the moment the handle was obtained.
+template <typename GENOME, typename UDATA>
+struct Node {
+  using Ptr = std::shared_ptr<Node>;
+  using Collection = std::map<SID, Ptr>;
+
+  /// node.hpp:25-85
+  struct Representative {
+    uint timestamp = 0;
+    GENOME genome;
+    std::unique_ptr<UDATA> userData;
+    Representative (void) = default;
+    Representative (const Representative &that) : genome(that.genome), userData(std::make_unique<UDATA>(*that.userData)) {}   // :34-36
+    Representative (Representative &&) = default;
+    Representative& operator= (Representative that) { std::swap(genome, that.genome); std::swap(userData, that.userData); return *this; }
+    static Representative make (const GENOME &g) {
+      Representative r;
+      r.genome = g;
+      r.userData = std::make_unique<UDATA>(g.genealogy().self.gid);
+      return r;
+    }
+#ifdef APT_WITH_JSON
+    friend void to_json (json &j, const Representative &p) { j = { p.genome, *p.userData }; }
+    friend void from_json (const json &j, Representative &p) {
+      p.genome = j[0].get<GENOME>();
+      p.userData = std::make_unique<UDATA>(GID::INVALID);
+      *p.userData = j[1].get<UDATA>();
+    }
+#endif
+    friend void assertEqual (const Representative &l, const Representative &r, bool deepcopy) {
+      assertEqual(l.genome, r.genome, deepcopy);                     // the user's, found by ADL as in the reference
+      if (bool(l.userData) != bool(r.userData)) _details::unequal("user data");
+      if (l.userData) {
+        if (deepcopy && l.userData.get() == r.userData.get()) _details::unequal("user data addresses (shallow copy)");
+        assertEqual(*l.userData, *r.userData, deepcopy);
+      }
+    }
+  };
+
+  SpeciesData data {};
+  Contributors contributors;
+  std::vector<Representative> rset;
+  _details::DistanceMap distances;
+
+  explicit Node (SID id) : contributors(id) {}
+  SID id (void) const { return contributors.getNodeID(); }
+  Node* parent (void) { return linked(), _parent; }
+  const Node* parent (void) const { return linked(), _parent; }
+  const std::vector<Ptr>& children (void) const { return linked(), _children; }
+  Ptr& child (size_t i) { return linked(), _children[i]; }
+  auto representativeGenome (uint i) const { return rset[i].genome; }
+  auto representativeId (uint i) const { return representativeGenome(i).genealogy().self.gid; }
+  bool extinct (void) const { return data.currentlyAlive == 0 && data.pendingCandidates == 0; }
+
+  /// node.hpp:212-219: this node and its sub-species, in dot format
+  void logTo (std::ostream &os) const {
+    os << "\t" << id() << ";\n";
+    for (const Ptr &n: children()) {
+      os << "\t" << id() << " -> " << n->id() << ";\n";
+      n->logTo(os);
+    }
+  }
+
+  /// node.hpp:222-235
+  friend void assertEqual (const Node &l, const Node &r, bool deepcopy) {
+    using _details::same;
+    const Node *lp = l.parent(), *rp = r.parent();
+    same(bool(lp), bool(rp), "parents");
+    if (lp && rp) same(lp->id(), rp->id(), "parent ids");
+    same(l.id(), r.id(), "species ids");
+    same(l.data.firstAppearance, r.data.firstAppearance, "first appearances");
+    same(l.data.lastAppearance, r.data.lastAppearance, "last appearances");
+    same(l.data.count, r.data.count, "counts");
+    same(l.data.currentlyAlive, r.data.currentlyAlive, "live counts");
+    same(l.data.pendingCandidates, r.data.pendingCandidates, "pending candidates");
+    same(l.contributors.data().size(), r.contributors.data().size(), "contributor counts");
+    for (size_t i = 0; i < l.contributors.data().size(); i++) {
+      const Contributor &a = l.contributors.data()[i], &b = r.contributors.data()[i];
+      if (a.speciesID() != b.speciesID() || a.count() != b.count() || a.elligible() != b.elligible()) _details::unequal("contributors");
+    }
+    same(l.rset.size(), r.rset.size(), "enveloppe sizes");
+    for (size_t i = 0; i < l.rset.size(); i++) assertEqual(l.rset[i], r.rset[i], deepcopy);
+    same(l.distances.size(), r.distances.size(), "distance map sizes");
+    for (auto a = l.distances.begin(), b = r.distances.begin(); a != l.distances.end(); ++a, ++b)
+      if (a->first.first != b->first.first || a->first.second != b->first.second || a->second != b->second) _details::unequal("distances");
+    const auto &lc = l.children(), &rc = r.children();
+    same(lc.size(), rc.size(), "sub-species counts");
+    for (size_t i = 0; i < lc.size(); i++) {
+      if (deepcopy && lc[i].get() == rc[i].get()) _details::unequal("node addresses (shallow copy)");
+      assertEqual(*lc[i], *rc[i], deepcopy);
+    }
+  }
+
+private:
+  friend class PhylogeneticTree<GENOME, UDATA>;
+  const PhylogeneticTree<GENOME, UDATA> *_owner = nullptr;
+  mutable Node *_parent = nullptr;
+  mutable std::vector<Ptr> _children;
+  mutable uint64_t _epoch = 0;          ///< tree modification count the scalar fields were read at
+  mutable uint64_t _linkEpoch = 0;      ///< ... and the one parent / children were resolved (and refreshed) at
+  void linked (void) const;             // defined below the tree
+};
 
 /// How a genome is laid out for the device; specialise per genome type (see the file header).
 /// Allocator of the staging arrays handed to the engine (encoded genomes, results): page-locked memory
@@ -176,23 +354,13 @@ public:
   using UserData = UDATA;
   using Callbacks = Callbacks_t<PhylogeneticTree<Genome, UserData>>;
   using Config = config::PTree;
-  using InsertionResult = apt::InsertionResult<UserData>;
+  using InsertionResult = phylogeny::InsertionResult<UserData>;
   using Encoding = DeviceEncoding<GENOME>;
 
-  /// node.hpp:25-85
-  struct Representative {
-    uint timestamp;
-    Genome genome;
-    std::unique_ptr<UserData> userData;
-  };
-
-  /// What the reference exposes through nodeAt(sid)-> : id, parent, children, data, rset
-  struct Node {
-    SID id, parent;                                  ///< parent == SID::INVALID for parentless nodes
-    struct { uint firstAppearance, lastAppearance, count, currentlyAlive, pendingCandidates; } data;
-    std::vector<SID> children;
-    const std::vector<Representative> *rset;
-  };
+  using Node = phylogeny::Node<Genome, UserData>;
+  using Node_ptr = typename Node::Ptr;
+  using Nodes = typename Node::Collection;
+  using Representative = typename Node::Representative;
 
   /// phylogenetictree.hpp:343-355
   struct Stats {
@@ -224,11 +392,35 @@ public:
   }
 
   ~PhylogeneticTree (void) { if (_tree) apt_tree_destroy(_tree); }
-  PhylogeneticTree (const PhylogeneticTree&) = delete;
-  PhylogeneticTree& operator= (const PhylogeneticTree&) = delete;
+
+  /// Constructs a deep copy of that PTree (:98-109): the nodes reachable from its root, eligibilities recomputed;
+  /// as in the reference the copy has no callbacks, no alive-species set and zeroed statistics
+  PhylogeneticTree (const PhylogeneticTree &that) : _rsetSize(that._rsetSize), _callbacks(nullptr) {
+    check(apt_tree_clone(that._tree, &_tree));
+    for (const Node_ptr &tn: that._nodes) {
+      if (!tn) continue;
+      apt_node_info i;
+      if (apt_tree_node_info(_tree, uint32_t(tn->id()), &i) != APT_OK) continue;     // not reachable from the root: not copied (:123-136)
+      nodeFor(tn->id())->rset = tn->rset;
+    }
+  }
+  /// Assigns that PTree to this one (:112-115)
+  PhylogeneticTree& operator= (PhylogeneticTree that) { swap(*this, that); return *this; }
   PhylogeneticTree (PhylogeneticTree &&that) noexcept
     : _tree(that._tree), _rsetSize(that._rsetSize), _aliveSpecies(std::move(that._aliveSpecies)),
-      _callbacks(nullptr), _rsets(std::move(that._rsets)) { that._tree = nullptr; }
+      _callbacks(that._callbacks), _nodes(std::move(that._nodes)), _root(std::move(that._root)), _epoch(that._epoch + 1) {
+    that._tree = nullptr;  that._callbacks = nullptr;
+    for (const Node_ptr &n: _nodes) if (n) n->_owner = this;
+  }
+  /// :138-147 (alive species and statistics travel with the engine here; the reference forgets to swap them)
+  friend void swap (PhylogeneticTree &l, PhylogeneticTree &r) {
+    using std::swap;
+    swap(l._tree, r._tree);  swap(l._rsetSize, r._rsetSize);  swap(l._aliveSpecies, r._aliveSpecies);
+    swap(l._callbacks, r._callbacks);  swap(l._nodes, r._nodes);  swap(l._root, r._root);
+    l._epoch = r._epoch = std::max(l._epoch, r._epoch) + 1;
+    for (const Node_ptr &n: l._nodes) if (n) n->_owner = &l;
+    for (const Node_ptr &n: r._nodes) if (n) n->_owner = &r;
+  }
 
   // == Accessors (:155-202) ==
   Callbacks* callbacks (void) { return _callbacks; }
@@ -236,41 +428,37 @@ public:
   uint step (void) const { return st(6); }
   SID nextNodeID (void) const { return SID(st(4)); }
   const LivingSet& aliveSpecies (void) const { return _aliveSpecies; }
-  SID root (void) const { uint32_t r; check(apt_tree_root(_tree, &r)); return SID(r); }
 
-  /// \return a view of the node with \p sid (throws like :168-177 when it does not exist)
-  Node nodeAt (SID sid) const {
-    apt_node_info i;
-    check(apt_tree_node_info(_tree, uint32_t(sid), &i));
-    Node n;
-    n.id = SID(i.sid);  n.parent = SID(i.parent_sid);
-    n.data = { i.data[0], i.data[1], i.data[2], i.data[3], i.data[4] };
-    std::vector<uint32_t> c (i.n_children);
-    if (!c.empty()) check(apt_tree_node_children(_tree, uint32_t(sid), c.data(), uint32_t(c.size())));
-    for (uint32_t s: c) n.children.push_back(SID(s));
-    static const std::vector<Representative> empty;
-    const auto *rs = rsetOf(sid);
-    n.rset = rs ? rs : &empty;
-    return n;
+  /// \return a smart pointer to the root (can be null), :158-160
+  const Node_ptr& root (void) const {
+    uint32_t r;
+    check(apt_tree_root(_tree, &r));
+    _root = (r == APT_INVALID) ? Node_ptr() : synced(SID(r), true);
+    return _root;
   }
+
+  /// \return the node with \p sid (throws like :168-177 when it does not exist)
+  const Node_ptr& nodeAt (SID sid) const { return synced(sid, true); }
 
   /// :181-187
   UserData* getUserData (const PID &pid) const {
-    nodeAt(pid.sid);                                           // throws for unknown species
-    if (const auto *rs = rsetOf(pid.sid))
-      for (const Representative &ep: *rs)
+    apt_node_info i;
+    check(apt_tree_node_info(_tree, uint32_t(pid.sid), &i));   // throws for unknown species
+    if (const Node *n = nodeOf(pid.sid))
+      for (const Representative &ep: n->rset)
         if (ep.genome.genealogy().self.gid == pid.gid) return ep.userData.get();
     return nullptr;
   }
 
   // == Modifiers (:216-221) ==
   void setCallbacks (Callbacks *c) const { _callbacks = c; }
-  void setStep (uint step) { check(apt_tree_set_step(_tree, step)); }
+  void setStep (uint step) { _epoch++; check(apt_tree_set_step(_tree, step)); }
 
   // == Core API ==
   /// :245-262
   template <typename IT, typename F>
   void step (uint step, IT begin, IT end, F sidExtractor) {
+    _epoch++;
     _aliveSpecies.clear();
     std::vector<uint32_t> sids;
     for (IT it = begin; it != end; ++it) {
@@ -303,6 +491,7 @@ public:
     for (IT it = first; it != last; ++it) gs.push_back(&*it);
     const size_t n = gs.size();
     if (!n) return;
+    _epoch++;
     _pl.resize(n * Encoding::words);  _cp.resize(n * 3);  _ids.resize(n * 5);
     _sid.resize(n);  _slot.resize(n);  _rep.resize(n);
     // genome objects -> staging arrays, on the engine's worker threads for large batches: DeviceEncoding::encode is
@@ -346,11 +535,11 @@ public:
   }
 
   /// :305-317
-  void delGenome (const Genome &g) { check(apt_tree_del_genome(_tree, uint32_t(g.genealogy().self.sid))); }
+  void delGenome (const Genome &g) { _epoch++; check(apt_tree_del_genome(_tree, uint32_t(g.genealogy().self.sid))); }
 
   /// :320-329
-  void registerCandidate (const Genealogy &g) { check(apt_tree_register_candidate(_tree, uint32_t(g.mother.sid), uint32_t(g.father.sid), +1)); }
-  void unregisterCandidate (const Genealogy &g) { check(apt_tree_register_candidate(_tree, uint32_t(g.mother.sid), uint32_t(g.father.sid), -1)); }
+  void registerCandidate (const Genealogy &g) { _epoch++; check(apt_tree_register_candidate(_tree, uint32_t(g.mother.sid), uint32_t(g.father.sid), +1)); }
+  void unregisterCandidate (const Genealogy &g) { _epoch++; check(apt_tree_register_candidate(_tree, uint32_t(g.mother.sid), uint32_t(g.father.sid), -1)); }
 
   // == Stats (:335-365) ==
   void resetStats (void) { check(apt_tree_reset_stats(_tree)); }
@@ -363,6 +552,48 @@ public:
 
   /// The engine behind this tree (counters, timers, node accessors of apt_b200.h)
   apt_tree* handle (void) const { return _tree; }
+
+protected:
+  /// Dump this PTree into dot file \p filename (:874-879; protected there too)
+  void logTo (const std::string &filename) const {
+    std::ofstream ofs (filename);
+    ofs << "digraph {\n";
+    if (const Node_ptr &r = root()) r->logTo(ofs);      // (the reference dereferences a null root here)
+    ofs << "}\n";
+  }
+public:
+
+  /// Asserts that two phylogenetic trees are equal (:970-981): root and nodes (recursively: parents, data, contributors,
+  /// enveloppes through the genome's and user data's own assertEqual, distances, sub-species), alive species, next
+  /// species id, enveloppe size, stillborns, step.  \p deepcopy additionally requires distinct objects.
+  /// Throws std::logic_error on the first difference.
+  friend void assertEqual (const PhylogeneticTree &lhs, const PhylogeneticTree &rhs, bool deepcopy) {
+    using _details::same;
+    const Node_ptr lr = lhs.root(), rr = rhs.root();
+    same(bool(lr), bool(rr), "roots");
+    if (lr) {
+      if (deepcopy && lr.get() == rr.get()) _details::unequal("root addresses (shallow copy)");
+      assertEqual(*lr, *rr, deepcopy);
+    }
+    same(lhs.width(), rhs.width(), "node counts");
+    uint32_t ls[8], rs[8];
+    check(apt_tree_stats(lhs._tree, ls));  check(apt_tree_stats(rhs._tree, rs));
+    for (uint32_t sid = 0, seen = 0; sid < ls[4] && seen < ls[5]; sid++) {       // _nodes: also the species no list holds
+      apt_node_info li, ri;
+      const bool lin = apt_tree_node_info(lhs._tree, sid, &li) == APT_OK, rin = apt_tree_node_info(rhs._tree, sid, &ri) == APT_OK;
+      same(lin, rin, "node sets");
+      if (!lin) continue;
+      seen++;
+      const Node_ptr ln = lhs.nodeAt(SID(sid)), rn = rhs.nodeAt(SID(sid));
+      if (deepcopy && ln.get() == rn.get()) _details::unequal("node addresses (shallow copy)");
+      assertEqual(*ln, *rn, deepcopy);
+    }
+    same(lhs._aliveSpecies, rhs._aliveSpecies, "alive species");
+    same(ls[4], rs[4], "next species ids");
+    same(lhs._rsetSize, rhs._rsetSize, "enveloppe sizes");
+    same(ls[7], rs[7], "stillborn counts");
+    same(ls[6], rs[6], "steps");
+  }
 
 #ifdef APT_WITH_JSON
   using json = nlohmann::json;
@@ -377,8 +608,9 @@ public:
     json alive = json::array();
     for (SID a: pt._aliveSpecies) alive.push_back(uint(a));
     j["alive"] = alive;
-    const SID r = pt.root();
-    j["tree"] = r == SID::INVALID ? json() : pt.nodeJson(r);
+    uint32_t r;
+    check(apt_tree_root(pt._tree, &r));
+    j["tree"] = r == APT_INVALID ? json() : pt.nodeJson(SID(r));
     j["nextSID"] = s[4];
   }
 
@@ -402,7 +634,9 @@ public:
     if (!ifs) throw std::invalid_argument("Unable to open '" + filename + "' for reading");
     PhylogeneticTree pt (device);
     fromJson(json::parse(ifs), pt);
-    return pt;
+    // the reference's tree leaves readFrom through its COPY constructor (no move constructor exists there), which
+    // drops the set of alive species (:98-109): programs written against it see an empty set after loading
+    return PhylogeneticTree(static_cast<const PhylogeneticTree&>(pt));
   }
 
   /// :984-1001
@@ -425,16 +659,56 @@ private:
   LivingSet _aliveSpecies;
   mutable Callbacks *_callbacks;
   mutable Stats _stats;
-  /// host-side genome objects per enveloppe slot, indexed by species id (ids are handed out densely, :195); a deque:
-  /// element addresses survive growth (Node views point at them) and a look-up is two hops instead of a hash chain
-  std::deque<std::vector<Representative>> _rsets;
+  /// handles = host-side objects of the species, indexed by species id (ids are handed out densely, :195): the
+  /// enveloppe's genome / user-data objects live in their `rset`
+  mutable std::deque<Node_ptr> _nodes;
+  mutable Node_ptr _root;
+  mutable uint64_t _epoch = 1;            ///< bumped by every mutating call: handles refresh their fields when it moved
+  const Node* nodeOf (SID sid) const { return uint32_t(sid) < _nodes.size() ? _nodes[uint32_t(sid)].get() : nullptr; }
+  const Node_ptr& nodeFor (SID sid) const {
+    if (uint32_t(sid) >= _nodes.size()) _nodes.resize(size_t(uint32_t(sid)) + 1);
+    Node_ptr &n = _nodes[uint32_t(sid)];
+    if (!n) { n = std::make_shared<Node>(sid);  n->_owner = this; }
+    return n;
+  }
+  std::vector<Representative>& rsetFor (SID sid) { return nodeFor(sid)->rset; }
   const std::vector<Representative>* rsetOf (SID sid) const {
-    return (uint32_t(sid) < _rsets.size() && !_rsets[uint32_t(sid)].empty()) ? &_rsets[uint32_t(sid)] : nullptr;
+    const Node *n = nodeOf(sid);
+    return (n && !n->rset.empty()) ? &n->rset : nullptr;
   }
-  std::vector<Representative>& rsetFor (SID sid) {
-    if (uint32_t(sid) >= _rsets.size()) _rsets.resize(size_t(uint32_t(sid)) + 1);
-    return _rsets[uint32_t(sid)];
+
+  /// The handle of species \p sid with its scalar fields (data, contributors, distances) as the engine holds them now;
+  /// \p links: parent and sub-species handles resolved (and refreshed the same way) too.  Throws for unknown species.
+  const Node_ptr& synced (SID sid, bool links) const {
+    apt_node_info i;
+    check(apt_tree_node_info(_tree, uint32_t(sid), &i));
+    const Node_ptr &n = nodeFor(sid);
+    if (n->_epoch != _epoch) {
+      n->data = { i.data[0], i.data[1], i.data[2], i.data[3], i.data[4] };
+      std::vector<uint32_t> ct (size_t(i.n_contributors) * 3);
+      if (!ct.empty()) check(apt_tree_node_contributors(_tree, uint32_t(sid), ct.data(), i.n_contributors));
+      std::vector<Contributor> cv;
+      for (uint32_t c = 0; c < i.n_contributors; c++) cv.emplace_back(SID(ct[3 * c]), ct[3 * c + 1], ct[3 * c + 2] != 0);
+      n->contributors = Contributors(sid, std::move(cv));
+      std::vector<float> d (size_t(_rsetSize) * _rsetSize);
+      check(apt_tree_node_distances(_tree, uint32_t(sid), d.data()));
+      n->distances.clear();
+      for (uint32_t a = 0; a < i.fill; a++)
+        for (uint32_t b = a + 1; b < i.fill; b++) n->distances.emplace(_details::ordered_pair<uint>(a, b), d[a * _rsetSize + b]);
+      n->_epoch = _epoch;
+    }
+    if (links && n->_linkEpoch != _epoch) {
+      n->_linkEpoch = _epoch;
+      n->_parent = i.parent_sid == APT_INVALID ? nullptr : synced(SID(i.parent_sid), false).get();
+      std::vector<uint32_t> ch (i.n_children);
+      if (!ch.empty()) check(apt_tree_node_children(_tree, uint32_t(sid), ch.data(), i.n_children));
+      n->_children.clear();
+      for (uint32_t c: ch) n->_children.push_back(synced(SID(c), false));
+    }
+    return n;
   }
+  friend struct phylogeny::Node<Genome, UserData>;
+
   PinnedVector<uint32_t> _pl, _sid, _rep, _ids;
   PinnedVector<float> _cp;
   PinnedVector<int32_t> _slot;
@@ -448,13 +722,14 @@ private:
 
   uint st (int i) const { uint32_t s[8]; check(apt_tree_stats(_tree, s)); return s[i]; }
 
-  /// Forget the genome objects of species removed by stillborn trimming (:816-860)
+  /// Forget the objects of species removed by stillborn trimming (:816-860): the engine lists them
   void dropTrimmed (void) {
-    for (size_t sid = 0; sid < _rsets.size(); sid++) {
-      if (_rsets[sid].empty()) continue;
-      apt_node_info i;
-      if (apt_tree_node_info(_tree, uint32_t(sid), &i) != APT_OK) std::vector<Representative>().swap(_rsets[sid]);
-    }
+    uint32_t n = apt_tree_trimmed(_tree, nullptr, 0, 0);
+    if (!n) return;
+    std::vector<uint32_t> sids (n);
+    n = apt_tree_trimmed(_tree, sids.data(), n, 1);
+    for (uint32_t k = 0; k < n; k++)
+      if (sids[k] < _nodes.size()) _nodes[sids[k]].reset();
   }
 
   /// Fires the recorded callbacks in the reference's order and mirrors enveloppe changes into the
@@ -590,6 +865,14 @@ private:
 #endif
 };
 
-} // namespace apt
+/// parent / sub-species handles of a node, resolved against the tree as it is now
+template <typename GENOME, typename UDATA>
+void Node<GENOME, UDATA>::linked (void) const {
+  if (_owner && _linkEpoch != _owner->_epoch) _owner->synced(id(), true);
+}
+
+} // namespace phylogeny
+
+namespace apt = phylogeny;
 
 #endif // APT_PHYLOGENETICTREE_HPP

@@ -156,6 +156,15 @@ uint64_t apt_tree_to_json (apt_tree *t, char *out, uint64_t cap);
  * the whole pool for upload.  A dump built with another rsetSize is refused like at :949-954. */
 int apt_tree_from_json (apt_tree *t, const char *text, uint64_t len);
 
+/* Copy construction (:98-109, deepcopy :123-136): a new tree holding deep copies of the nodes reachable from the
+ * root of `src` (children in their order), eligibilities and parents recomputed (:103).  Like the reference's, the
+ * copy has no alive-species set, zeroed Stats and no recorded events. */
+int apt_tree_clone (apt_tree *src, apt_tree **out);
+
+/* Species removed by stillborn trimming (:816-860) since the last drain: copies min(cap, count) ids (and removes them
+ * when `drain` is non-zero); with out == NULL returns the number pending.  For bindings that keep per-species objects. */
+uint32_t apt_tree_trimmed (apt_tree *t, uint32_t *out_sids, uint32_t cap, int drain);
+
 /* Node accessors used by the C++ binding (include/apt/phylogenetictree.hpp). */
 typedef struct apt_node_info {
   uint32_t sid, parent_sid;           /* parent_sid = APT_INVALID for parentless nodes */

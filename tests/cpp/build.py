@@ -21,3 +21,25 @@ def build(lib_path: str, tag: str) -> str:
            "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir]
     subprocess.run(cmd, check=True)
     return out
+
+
+REF = "/root/reference"
+
+
+def build_reference() -> str | None:
+    """The SAME test source against the reference's own header (+ the Tools stand-in of oracle/shim and the reference's
+    four translation units, compiled where they lie).  Only where /root/reference exists; outputs under _build/."""
+    if not os.path.isdir(os.path.join(REF, "src", "core")):
+        return None
+    out = os.path.join(HERE, "_build", "test_dropin_reference")
+    src = os.path.join(HERE, "test_dropin.cpp")
+    if os.path.exists(out) and os.path.getmtime(src) < os.path.getmtime(out):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json_inc = os.path.join(sysconfig.get_paths()["purelib"], "include", "cudnn_frontend", "thirdparty")
+    tus = [os.path.join(REF, "src", "core", "ptreeconfig.cpp")] + \
+          [os.path.join(REF, "src", "core", "tree", f) for f in ("treetypes.cpp", "enveloppecriteria.cpp", "speciescontributors.cpp")]
+    cmd = ["g++", "-std=c++17", "-O2", "-DNDEBUG", "-mpopcnt", "-DAPT_TEST_REFERENCE", "-I", os.path.join(ROOT, "oracle", "shim"),
+           "-I", json_inc, "-I", os.path.join(REF, "src"), "-o", out, src] + tus
+    subprocess.run(cmd, check=True)
+    return out

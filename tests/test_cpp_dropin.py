@@ -31,7 +31,54 @@ def _run(exe, name, extra, tmp_path, f32=False, env=None):
     jb = json.loads(gzip.open(os.path.join(GOLDEN, name + ".json.gz")).read())
     if not f32:
         assert ja == jb
-        assert json.load(open(prefix + ".rt.json")) == golden_roundtrip_json(name), "readFrom differs from the reference's"
+        # readFrom hands the tree out through the copy constructor, which drops the alive set (:98-109, :1004-1016)
+        want = dict(golden_roundtrip_json(name), alive=[])
+        assert json.load(open(prefix + ".rt.json")) == want, "readFrom differs from the reference's"
+
+
+@pytest.mark.parametrize("name,extra", CASES)
+def test_dropin_source_is_a_reference_program(name, extra, tmp_path):
+    """tests/cpp/test_dropin.cpp compiled UNCHANGED against the reference's own header (-DAPT_TEST_REFERENCE: the
+    reference's phylogenetictree.hpp over the Tools stand-in) and against ours must behave the same: results, callbacks,
+    dumps, the node-handle walk (root / nodeAt / children / parent), copy construction + assignment + assertEqual, and
+    the dot file of logTo.  Needs /root/reference (build container only)."""
+    from hostsim import build as hb
+    from cpp import build as cb
+    ref = cb.build_reference()
+    if ref is None:
+        pytest.skip("/root/reference is not present on this box")
+    ours = cb.build(hb.build(), "hostsim")
+    extra = [e for e in extra if e != "--one-by-one"]
+    cfg = golden_cases()[name]["cfg"]
+    out = {}
+    for tag, exe in (("ref", ref), ("ours", ours)):
+        prefix = str(tmp_path / (name + "_" + tag))
+        r = subprocess.run([exe, os.path.join(GOLDEN, name + ".trace"), prefix, str(cfg.get("K", 5))] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, tag + ": " + r.stdout + r.stderr
+        out[tag] = prefix
+    a, b = oracle.read_res(out["ref"] + ".res"), oracle.read_res(out["ours"] + ".res")
+    assert np.array_equal(a["sids"], b["sids"]) and np.array_equal(a["entered"], b["entered"])
+    assert np.array_equal(a["events"], b["events"]) and a["stats"] == b["stats"]
+    for ext in (".json", ".rt.json"):
+        assert json.load(open(out["ref"] + ext)) == json.load(open(out["ours"] + ext)), ext
+    assert open(out["ref"] + ".dot").read() == open(out["ours"] + ".dot").read(), "logTo"
+    assert open(out["ref"] + ".walk").read() == open(out["ours"] + ".walk").read(), "node walk / copy construction"
+
+
+def test_dropin_deep_copy_is_compared_somewhere(tmp_path):
+    """At least one case has every species below the root, so that copy construction + assertEqual(.., deepcopy) runs."""
+    from hostsim import build as hb
+    from cpp import build as cb
+    exe = cb.build(hb.build(), "hostsim")
+    ran = 0
+    for name, extra in CASES:
+        cfg = golden_cases()[name]["cfg"]
+        prefix = str(tmp_path / name)
+        r = subprocess.run([exe, os.path.join(GOLDEN, name + ".trace"), prefix, str(cfg.get("K", 5))] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        ran += int(open(prefix + ".walk").read().split()[3])
+    assert ran > 0
 
 
 @pytest.mark.parametrize("name,extra", CASES)
