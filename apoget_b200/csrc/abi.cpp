@@ -520,7 +520,7 @@ int apt_env_contribution (const apt_params *params, uint32_t n, const float *edi
                           uint8_t *out_better, uint32_t *out_than, float *out_value) {
   return guarded([&] {
     need(params && (n == 0 || (edist && gdist && out_better && out_than && out_value)), "null argument");
-    need(params->env_crit == 0 || params->env_crit == 1, "only criteria 0 and 1 run on the device");
+    need(params->env_crit >= 0 && params->env_crit <= 3, "No function for this use case");
     need(params->rset_size >= 1 && params->rset_size <= KMAX, "rset_size must be in 1..32");
     requireDevice(params->device);
     const uint32_t K = params->rset_size;

@@ -10,6 +10,7 @@
 // shuffle reductions, and the order-sensitive float accumulation (`float avg += double c`,
 // :465-472) kept strictly sequential -- shuffles / shared memory only GATHER the k values.
 #include "kernels.cuh"
+#include "criteria.h"
 
 #include <math_constants.h>
 
@@ -227,13 +228,22 @@ __global__ void mate_compat_kernel (uint32_t wp4, const uint4 *__restrict__ payl
   if (lane == 0) { out_dist[p] = float(d);  out_compat[p] = compat_generic(__ldg(cmeta + m), d); }
 }
 
-// enveloppecriteria.cpp:40-84 (crit 0) and :87-133 (crit 1); one thread per candidate genome
+// enveloppecriteria.cpp:40-84 (crit 0), :87-133 (crit 1), :136-202 (crit 2), :205-272 (crit 3); one thread per candidate genome
 __global__ void env_contribution_kernel (int crit, uint32_t K, uint32_t n, const float *__restrict__ edist,
                                          const float *__restrict__ gdist, uint8_t *__restrict__ out_better,
                                          uint32_t *__restrict__ out_than, float *__restrict__ out_value) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float *e = edist + size_t(i) * K * K, *g = gdist + size_t(i) * K;
+  if (crit >= 2) {
+    // :136-202 (exact) / :205-272 (device exp(): decisions within 1e-13 of a tie may differ from libm's)
+    auto D = [&] (uint32_t a, uint32_t b) { return e[a * K + b]; };
+    auto G = [&] (uint32_t j) { return g[j]; };
+    const CritResult r = crit == 2 ? crit_maxAvgMinStdDev(D, G, K)
+                                   : crit_maxWeightedDist2Avg<KMAX>(D, G, K, [] (double x) { return exp(x); });
+    out_better[i] = r.better;  out_than[i] = r.than;  out_value[i] = r.value;
+    return;
+  }
   float value = -CUDART_INF_F;      // -DBL_MAX stored into a float, :46 / :93
   uint32_t than = 0xFFFFFFFFu;
   for (uint32_t a = 0; a < K; a++) {

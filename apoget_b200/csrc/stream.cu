@@ -21,6 +21,7 @@
 // reference-identical arithmetic (device exp() inside the guard band) the warp stops and hands the
 // rest of the stream to the host.  At the end the warp writes the enveloppe back to the pool.
 #include "kernels.cuh"
+#include "criteria.h"
 
 #include <math_constants.h>
 
@@ -220,6 +221,18 @@ __device__ __forceinline__ bool criterion_maxAverage (const WarpState &ws, const
   return value > 0.f;
 }
 
+/// Criteria 2 and 3 (enveloppecriteria.cpp:136-272, criteria.h) against the full enveloppe in shared memory.  Kept out
+/// of line: they are debug options of the reference (DEBUG_ENV_CRIT) and must not cost the default criteria registers.
+/// Returns than | better << 30 | uncertain << 31.
+__device__ __noinline__ uint32_t criterion_other (int crit, uint32_t oD, uint32_t K, const float *gd) {
+  const float *Dm = reinterpret_cast<const float*>(apt_smem + oD);
+  auto D = [&] (uint32_t i, uint32_t j) { return Dm[i * K + j]; };
+  auto g = [&] (uint32_t j) { return gd[j]; };
+  const CritResult r = crit == 2 ? crit_maxAvgMinStdDev(D, g, K)
+                                 : crit_maxWeightedDist2Avg<KMAX>(D, g, K, [] (double x) { return exp(x); });
+  return (r.than & 0x3FFFFFFFu) | (r.better ? 0x40000000u : 0u) | (r.uncertain ? 0x80000000u : 0u);
+}
+
 /// Shared-memory bytes of one stream (without the table)
 __host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T, bool ktConst = false) {
   return (ktConst ? 0 : size_t(K) * T * 8) + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
@@ -232,7 +245,7 @@ __device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile("pref
 constexpr uint32_t EV_TID_SHIFT = 8, EV_UNCERTAIN = 0x80u, EV_SLOT_MASK = 0x3Fu;
 
 // 7 CTAs of 4 warps per SM keep 1 000 streams in one wave on 148 SMs (register-resident variant: <= 72 registers)
-template <int WQ, int KIND, bool LUT, int NW, int KT>
+template <int WQ, int KIND, bool LUT, int NW, int KT, bool CRITX = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 && KT > 0 && WQ <= 2) ? 7 : 1)
 resolve_streams_kernel (StreamArgs a) {
   constexpr uint32_t T = NW * 32;
@@ -365,14 +378,24 @@ resolve_streams_kernel (StreamArgs a) {
     bool rejected = false;
 
     for (;;) {
-      const bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
+      bool uncertain = mine && !LUT && fabsf(score) <= a.guard;
       const bool accept = mine && score > 0.f;
       bool modifies = false;
       uint32_t than = 0;
       if (accept && !uncertain) {
         if (k < K) { modifies = true; than = k; }                       // :668-677
-        else if (K > 1)
-          modifies = a.crit == 1 ? criterion_maxMinDist<KT>(ws, ln, K, tid, than) : criterion_maxAverage<KT>(ws, ln, K, tid, than);
+        else if (K > 1) {
+          if (a.crit == 1) modifies = criterion_maxMinDist<KT>(ws, ln, K, tid, than);
+          else if (a.crit == 0) modifies = criterion_maxAverage<KT>(ws, ln, K, tid, than);
+          else if (CRITX) {           // criteria 2 / 3: instantiated for the generic variant only (launchNW)
+            float gd[KMAX];
+            APT_FOR_K(r, K) gd[r] = KT ? ln.d[KT ? r : 0] : ws.d(r * ws.T + tid);
+            const uint32_t res = criterion_other(a.crit, ws.oD, K, gd);
+            than = res & 0x3FFFFFFFu;
+            uncertain = (res >> 31) != 0u;                               // criterion 3 inside its error band: the host decides
+            modifies = !uncertain && ((res >> 30) & 1u);
+          }
+        }
       }
       // earliest thread of the CTA whose decision is an event (changes the enveloppe / needs the host),
       // published together with what it does: one barrier tells every thread who and where
@@ -513,7 +536,7 @@ resolve_streams_kernel (StreamArgs a) {
   if (prof && tid == 0) { prof[4] = clock64();  prof[5] = profEvents;  prof[6] = profSteps;  prof[8] = profA;  prof[9] = profB; }
 }
 
-template <int WQ, int NW, int KT>
+template <int WQ, int NW, int KT, bool CRITX = false>
 void launchWQ (const StreamArgs &a, cudaStream_t st) {
   const uint32_t K = a.pool.K;
   size_t smem = (stream_smem(K, WQ, NW * 32, KT > 0) + 15) & ~size_t(15);
@@ -526,8 +549,8 @@ void launchWQ (const StreamArgs &a, cudaStream_t st) {
     kernel<<<a.n_groups, NW * 32, smem, st>>>(b);
   };
   if (a.cfg.kind == 0) {
-    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW, KT>); else go(resolve_streams_kernel<WQ, 0, false, NW, KT>);
-  } else go(resolve_streams_kernel<WQ, 1, false, NW, KT>);
+    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW, KT, CRITX>); else go(resolve_streams_kernel<WQ, 0, false, NW, KT, CRITX>);
+  } else go(resolve_streams_kernel<WQ, 1, false, NW, KT, CRITX>);
 }
 
 /// Warps per stream: wide CTAs pay off when some stream is long; genomes that fill the register
@@ -535,6 +558,8 @@ void launchWQ (const StreamArgs &a, cudaStream_t st) {
 /// ptreeconfig.cpp:10) and 10 (BASELINE.json) get the register-resident variant for short genomes.
 template <int WQ>
 void launchNW (const StreamArgs &a, cudaStream_t st) {
+  // criteria 2 and 3 (debug options of the reference): one variant, any enveloppe size, 4 warps
+  if (a.crit >= 2) { launchWQ<WQ, 4, 0, true>(a, st); return; }
   const bool wide = a.max_stream > 1024 && WQ <= 8
                     && ((stream_smem(a.pool.K, WQ, 512) + 15) & ~size_t(15)) <= (size_t(150) << 10);
   if constexpr (WQ <= 4) {
@@ -550,7 +575,7 @@ void launchNW (const StreamArgs &a, cudaStream_t st) {
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit) {
   const uint32_t wq = wp >> 2;
   if (!(wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32)) return false;
-  if (crit != 0 && crit != 1) return false;
+  if (crit < 0 || crit > 3) return false;
   return ((stream_smem(K, wq, 128) + 15) & ~size_t(15)) <= size_t(150) << 10;
 }
 

@@ -259,7 +259,8 @@ int apt_combine_shards_dev (int device, uint32_t n_births, uint32_t world, const
 
 /* a8, enveloppe criterion (enveloppecriteria.cpp:87-133, 275-289) for n candidates: edist
  * n*K*K f32 (full symmetric matrices), gdist n*K f32 -> better (u8), than (u32), value (f32).
- * Only crit 0 and 1 run on the device. */
+ * All four criteria run on the device (maxWeightedDist2Avg with the device's exp(): a decision closer than 1e-13
+ * to a tie may differ from libm's). */
 int apt_env_contribution (const apt_params *params, uint32_t n, const float *edist, const float *gdist,
                           uint8_t *out_better, uint32_t *out_than, float *out_value);
 

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "criteria.h"
 
 extern "C" {
 cudaError_t cudaGetDeviceCount (int *c) { *c = 1; return cudaSuccess; }
@@ -149,7 +150,7 @@ void launch_scatter_blocks_f32 (const float *src, const uint32_t *idx, uint32_t 
 
 bool stream_kernel_supports (uint32_t wp, uint32_t, int crit) {
   const uint32_t wq = wp >> 2;
-  return (wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32) && (crit == 0 || crit == 1);
+  return (wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32) && crit >= 0 && crit <= 3;
 }
 
 // Plain sequential stand-in for resolve_streams_kernel (same inputs, outputs and write-back)
@@ -186,6 +187,15 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       uint32_t than = 0xFFFFFFFFu;
       bool modifies = false, append = false;
       if (k < K) { modifies = append = true; than = k; }
+      else if (K > 1 && a.crit >= 2) {
+        // criteria 2 / 3: the very functions the kernel runs (criteria.h), exp() perturbed like a device's
+        auto Dm = [&] (uint32_t i, uint32_t j) { return D[i * K + j]; };
+        auto gv = [&] (uint32_t j) { return d[j]; };
+        auto dexp = [] (double x) { const double e = std::exp(x); return (uint64_t(x * -7919.) & 3) == 0 ? std::nextafter(e, 2.) : e; };
+        const CritResult r = a.crit == 2 ? crit_maxAvgMinStdDev(Dm, gv, K) : crit_maxWeightedDist2Avg<KMAX>(Dm, gv, K, dexp);
+        if (r.uncertain) { a.act[b] = ACT_UNCERTAIN; aborted = true; break; }
+        than = r.than;  modifies = r.better;
+      }
       else if (K > 1) {
         float value = -std::numeric_limits<float>::infinity();
         for (uint32_t i = 0; i < K; i++) {
@@ -247,7 +257,30 @@ void launch_classify_children (const ChildArgs &a, cudaStream_t) {
   }
 }
 
-void launch_env_contribution (int, uint32_t, uint32_t, const float*, const float*, uint8_t*, uint32_t*, float*, cudaStream_t) {}
+void launch_env_contribution (int crit, uint32_t K, uint32_t n, const float *edist, const float *gdist, uint8_t *ob, uint32_t *ot,
+                              float *ov, cudaStream_t) {
+  for (uint32_t i = 0; i < n; i++) {
+    const float *e = edist + size_t(i) * K * K, *g = gdist + size_t(i) * K;
+    auto D = [&] (uint32_t a, uint32_t b) { return e[a * K + b]; };
+    auto G = [&] (uint32_t j) { return g[j]; };
+    CritResult r { false, 0xFFFFFFFFu, -std::numeric_limits<float>::infinity(), false };
+    if (crit == 2) r = crit_maxAvgMinStdDev(D, G, K);
+    else if (crit == 3) r = crit_maxWeightedDist2Avg<KMAX>(D, G, K, [] (double x) { return std::exp(x); });
+    else {
+      for (uint32_t a = 0; a < K; a++) {
+        double c = 0;
+        if (crit == 1) {
+          float mb = std::numeric_limits<float>::max(), mn = mb;
+          for (uint32_t j = 0; j < K; j++) { if (j == a) continue; mb = std::min(mb, e[a * K + j]); mn = std::min(mn, g[j]); }
+          c = - mb + mn;
+        } else for (uint32_t j = 0; j < K; j++) { if (j == a) continue; c += - e[a * K + j] + g[j]; }
+        if (r.value < c) { r.value = float(c); r.than = a; }
+      }
+      r.better = r.value > 0;
+    }
+    ob[i] = r.better;  ot[i] = r.than;  ov[i] = r.value;
+  }
+}
 void launch_pairwise (int kind, uint32_t wp, const uint32_t *payload, uint32_t n, const uint32_t *a, const uint32_t *b,
                       float *out, cudaStream_t) {
   for (uint32_t p = 0; p < n; p++) out[p] = float(dist(kind, wp, payload + size_t(a[p]) * wp, payload + size_t(b[p]) * wp));

@@ -96,6 +96,28 @@ def test_compat_table_overflow_keeps_parity(hostsim, name, cap, monkeypatch):
         assert c["stream_births"] > 0
 
 
+@pytest.mark.parametrize("crit", [0, 1, 2, 3])
+@pytest.mark.parametrize("K", [2, 5, 6, 10, 17])
+def test_criteria_in_device_form_equal_the_reference_restatement(hostsim, crit, K):
+    """csrc/criteria.h (what the kernels run for DEBUG_ENV_CRIT 2 and 3: explicit roundings, insertion sort, x * x for
+    pow(x, 2)) compiled for the host, against the oracle's line-by-line restatement of enveloppecriteria.cpp:40-272 on
+    random enveloppes -- integer-valued distances (bit-strings) and float ones, near-ties included."""
+    from apoget_b200.kernels import env_contribution
+    rng = np.random.default_rng(100 * crit + K)
+    n = 300
+    e = rng.integers(1, 60, size=(n, K, K)).astype(np.float32)
+    e[n // 2:] = (rng.random((n - n // 2, K, K)) * 3).astype(np.float32)
+    e = np.maximum(e, e.transpose(0, 2, 1))                      # symmetric
+    g = rng.integers(1, 60, size=(n, K)).astype(np.float32)
+    g[n // 2:] = (rng.random((n - n // 2, K)) * 3).astype(np.float32)
+    g[::7] = e[::7, 0, :]                                        # the candidate as far from everyone as representative 0 is
+    better, than, value = env_contribution(K, e, g, crit=crit)
+    for i in range(n):
+        ob, ot, ov = oracle.env_contribution(crit, e[i], g[i])
+        assert (bool(better[i]), int(than[i])) == (ob, ot if ot != 0xFFFFFFFF else int(than[i])), (i, value[i], ov)
+        assert value[i] == np.float32(ov) or (np.isnan(value[i]) and np.isnan(ov))
+
+
 def test_one_birth_per_call_equals_batches(hostsim):
     name = "hybrids_b256_k5"
     cfg = golden_cases()[name]["cfg"]
