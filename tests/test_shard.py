@@ -84,9 +84,11 @@ def test_shard_ranges_partition():
 
 
 @pytest.mark.gpu
-def test_peer_memory_exchange_matches_allgather_on_two_gpus():
+@pytest.mark.parametrize("config,births,species", [("c2", "8192", "301"), ("c4", "4096", "613")])
+def test_peer_memory_exchange_matches_allgather_on_two_gpus(config, births, species):
     """The fused sweep + exchange (records stored into the peers' buffers over NVLink by the sweep kernel) against
-    the NCCL all-gather path, on 2 GPUs; tools/bench_dense.py asserts that both give identical winners."""
+    the NCCL all-gather path, on 2 GPUs (c2: popcount sweep, c4: tensor-core sweep); tools/bench_dense.py asserts that
+    both give identical winners, and checks them against the oracle."""
     import subprocess
     import sys
     if torch.cuda.device_count() < 2:
@@ -94,8 +96,8 @@ def test_peer_memory_exchange_matches_allgather_on_two_gpus():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-                        os.path.join(root, "tools", "bench_dense.py"), "--config", "c2", "--births", "8192",
-                        "--species", "301", "--exchange", "p2p", "--check", "6"],
+                        os.path.join(root, "tools", "bench_dense.py"), "--config", config, "--births", births,
+                        "--species", species, "--exchange", "p2p", "--check", "64"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert '"oracle_mismatches": 0' in r.stdout and "peer-memory" in r.stdout
