@@ -43,3 +43,19 @@ def golden_trace_path(name):
 @pytest.fixture(scope="session")
 def cases():
     return golden_cases()
+
+
+def json_close(a, b, rtol):
+    """Structural equality of two dumps with floats compared to a relative tolerance (float-vector genomes)."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and a.keys() == b.keys()
+        for k in a:
+            json_close(a[k], b[k], rtol)
+    elif isinstance(a, list):
+        assert isinstance(b, list) and len(a) == len(b)
+        for x, y in zip(a, b):
+            json_close(x, y, rtol)
+    elif isinstance(a, float) or isinstance(b, float):
+        assert abs(a - b) <= rtol * max(abs(a), abs(b)), (a, b)
+    else:
+        assert a == b, (a, b)

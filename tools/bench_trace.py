@@ -32,6 +32,14 @@ CONFIGS = {
                 burst_fanout=10, burst_bits=700), dict(K=10)),
     "c5": (dict(kind=B, words=8, pop=100_000, gens=30, seed=45, flips=2.0, sigma=6.0, hybrid=0.05, hybrid_far=0.1,
                 burst_levels=2, burst_fanout=10), dict(K=5)),
+    # BASELINE.json configs at their STATED sizes: 10 k species (four 10-way radiations: 11 111 species) for configs[2]
+    # (1 M births in calls of 65 536) and configs[3] (candidate mode; K = 10 -> 100 k enveloppe members), 10 M births for configs[4]
+    "c3full": (dict(kind=F, words=64, pop=65_536, gens=4 + 16, seed=43, sigma=0.35, noise=0.02, noise_coords=8, hybrid=0.05,
+                    burst_levels=4, burst_fanout=10, burst_scale=1.0), dict(K=10)),
+    "c4full": (dict(kind=B, words=128, pop=100_000, gens=4 + 10, seed=44, flips=4, sigma=100.0, hybrid=0.05, burst_levels=4,
+                    burst_fanout=10, burst_bits=700), dict(K=10)),
+    "c5full": (dict(kind=B, words=8, pop=100_000, gens=100, seed=45, flips=2.0, sigma=6.0, hybrid=0.05, hybrid_far=0.1,
+                    burst_levels=2, burst_fanout=10), dict(K=5)),
 }
 
 
@@ -40,7 +48,11 @@ def main():
     ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--gens", type=int, default=0)
     ap.add_argument("--pop", type=int, default=0)
-    ap.add_argument("--ref-births", type=int, default=400_000)
+    ap.add_argument("--ref-births", type=int, default=400_000, help="births replayed through the reference (-1: the whole stream, 0: none)")
+    ap.add_argument("--ref", default="unmodified", choices=["unmodified", "cref"],
+                    help="cref: the reference with std::cref(nodes) in its eligibility binder (node.hpp:177) -- identical "
+                         "output (tests/test_oracle.py), no O(#species) map copy per insertion: the one that can replay a whole stream")
+    ap.add_argument("--check-json", action="store_true", help="also compare the final tree dump with the reference's")
     ap.add_argument("--flags", type=int, default=1)
     args = ap.parse_args()
     gen, cfg = CONFIGS[args.config]
@@ -88,22 +100,43 @@ def main():
         import oracle
         path = os.path.join(tempfile.gettempdir(), "apt_bench_trace.trace")
         synth.write_trace(path, t)
-        nref = min(args.ref_births, t.n_births)
-        if oracle.have_reference():
+        nref = t.n_births if args.ref_births < 0 else min(args.ref_births, t.n_births)
+        cref = args.ref == "cref"
+        if oracle.have_reference(cref):
             prefix = os.path.join(tempfile.gettempdir(), "apt_bench_trace_ref")
-            r = oracle.run_reference(path, prefix, cfg, extra=["--no-json", "--no-events", "--max-births", str(nref)])
+            whole = nref == t.n_births
+            extra = ["--no-events", "--max-births", str(nref)] + ([] if (args.check_json and whole) else ["--no-json"])
+            r = oracle.run_reference(path, prefix, cfg, cref=cref, extra=extra)
             res = oracle.read_res(prefix + ".res")
             n = res["sids"].size
-            out.update(ref_kind="reference", ref_births=n, ref_births_per_s=r["births_per_s"],
-                       ref_last_gen_births_per_s=pop / r["gen_seconds"][-1],
-                       sid_parity=bool(np.array_equal(res["sids"], sid_of[:n])))
+            same = res["sids"] == sid_of[:n]
+            out.update(ref_kind="reference (std::cref in the eligibility binder)" if cref else "reference (unmodified)", ref_births=n,
+                       ref_births_per_s=r["births_per_s"], ref_last_gen_births_per_s=pop / r["gen_seconds"][-1],
+                       sid_parity=bool(same.all()), sid_mismatches=int((~same).sum()))
+            if whole:
+                out["stats_parity"] = all(res["stats"][k] == st[k] for k in ("insertions", "comparisons", "branching", "next_sid", "width"))
+                if args.check_json:
+                    ours, theirs = tree.to_json(), json.load(open(prefix + ".json"))
+                    if t.kind == B:
+                        out["json_parity"] = ours == theirs
+                    else:
+                        sys.path.insert(0, os.path.join(ROOT, "tests"))
+                        from conftest import json_close
+                        try:
+                            json_close(ours, theirs, 1e-5)
+                            out["json_parity"] = True
+                        except AssertionError as e:
+                            out["json_parity"] = False
+                            out["json_first_difference"] = str(e)[:200]
+                    out["json_tolerance"] = 0.0 if t.kind == B else 1e-5
         else:
             o = oracle.Oracle(t.kind, t.words, **cfg)
             o.log_events(False)
             osid, _, sec = o.replay(path, max_births=nref)
+            same = osid == sid_of[:osid.size]
             out.update(ref_kind="port", ref_births=int(osid.size), ref_births_per_s=osid.size / sec,
-                       sid_parity=bool(np.array_equal(osid, sid_of[:osid.size])))
-        g_ref = out["ref_births"] // pop
+                       sid_parity=bool(same.all()), sid_mismatches=int((~same).sum()))
+        g_ref = max(1, out["ref_births"] // pop)
         out["cuda_births_per_s_same_prefix"] = out["ref_births"] / sum(per_gen[:g_ref])
         out["speedup_same_prefix"] = out["cuda_births_per_s_same_prefix"] / out["ref_births_per_s"]
     print(json.dumps(out))
