@@ -35,7 +35,7 @@ def _json_close(a, b, rtol):
         assert a == b, (a, b)
 
 
-def _compare(name, flags=0):
+def _compare(name, flags=0, device_scores=True):
     from apoget_b200.tree import PhylogeneticTree
     cfg = golden_cases()[name]["cfg"]
     t = synth.read_trace(golden_trace_path(name))
@@ -53,7 +53,7 @@ def _compare(name, flags=0):
     else:
         _json_close(tree.to_json(), golden_json(name), F32_RTOL)
     c = tree.counters()
-    assert c["kernel_launches"] > 0 and c["device_scores"] > 0, "the CUDA path did not run"
+    assert c["kernel_launches"] > 0 and (c["device_scores"] > 0 or not device_scores), "the CUDA path did not run"
     return tree
 
 
@@ -73,7 +73,8 @@ def test_tree_compat_table_overflow(name, cap, monkeypatch):
     """The compatibility table overflows mid-run (APT_LUT_MAX_BYTES stands in for the 256 MiB limit): device exp()
     from then on; vote-count scoring then leaves the device kernels (no guard band can protect a vote)."""
     monkeypatch.setenv("APT_LUT_MAX_BYTES", str(cap))
-    _compare(name)
+    # (vote counting without the table: every device score is re-taken on the host -- none may be trusted)
+    _compare(name, device_scores=not name.startswith("semi"))
 
 
 def _random_pool(rng, kind, words, S, K, sigma):
