@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libapt_b200.so")
-SOURCES = ["kernels.cu", "stream.cu", "dense.cu", "tc_dense.cu", "microbench.cu", "engine.cpp", "abi.cpp"]
+SOURCES = ["kernels.cu", "stream.cu", "family.cu", "dense.cu", "tc_dense.cu", "microbench.cu", "engine.cpp", "abi.cpp"]
 HEADERS = ["kernels.cuh", "engine.h", os.path.join(ROOT, "include", "apt_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

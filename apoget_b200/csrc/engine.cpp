@@ -153,6 +153,7 @@ Engine::Engine (const apt_params &p) : p_(p) {
   }
   streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
               && (p.full_continuous || lutMode_);
+  famOk_ = streamOk_ && childKernel_ && !(p.flags & APT_FLAG_NO_FAMILY_KERNEL) && family_kernel_supports(wp_, K_, p.env_crit);
 }
 
 Engine::~Engine (void) {
@@ -260,6 +261,7 @@ void Engine::setStreamable (const Species *s, bool on) {
 
 uint32_t Engine::allocSlot (void) {
   uint32_t slot;
+  if (forcedSlot_ != INV) { slot = forcedSlot_; forcedSlot_ = INV; return slot; }      // (a slot of the block the family pass reserved)
   if (!freeSlots_.empty()) { slot = freeSlots_.back(); freeSlots_.pop_back(); }
   else {
     slot = nSlots_++;
@@ -395,6 +397,7 @@ uint32_t Engine::classOf (float mu, float sin, float sout) {
         hLut_.clear();  hLut_.shrink_to_fit();
         streamOk_ = streamOk_ && p_.full_continuous;
         childKernel_ = childKernel_ && p_.full_continuous;
+        famOk_ = famOk_ && p_.full_continuous;
       } else {
         hLut_.resize(size_t(id + 1) * lutStride_);
         for (uint32_t d = 0; d < lutStride_; d++) {
@@ -791,7 +794,7 @@ void Engine::resolveBelowStream (const uint32_t *w, const RepMeta &g, Species *s
     if (dev && idx < snapN) {
       const uint32_t rank = uint32_t(snapN - 1 - idx);
       const bool known = rank < firstRank || (rank == firstRank && !firstUnsure);
-      if (known && sub->stale_mask == 0 && !sub->full_upload && sub->div_epoch != chunkEpoch_ &&
+      if (known && sub->stale_mask == 0 && !sub->full_upload && sub->div_epoch != chunkEpoch_ && sub->fam_epoch != chunkEpoch_ &&
           (sub->grp_epoch != chunkEpoch_ || grpState_[sub->grp_index].lastEnter < int64_t(curBirth_))) {
         touchSnap(sub);
         comparisons_ += sub->k;
@@ -959,11 +962,117 @@ void Engine::walkStream (const uint32_t *w, RepMeta &g, Species *s0, uint32_t ac
   insertions_++;
 }
 
+/// Contributors::update (speciescontributors.cpp:15-65) for n1 births contributing (from, 1) and n2 contributing
+/// (from, 2) to species c, none of which changes its enveloppe: the same entry grows by n1 + 2 n2, and a stable sort
+/// after every single increment leaves it where one sort after the sum does (it only ever passes strictly smaller
+/// counts).  `from` is c's major contributor (c is one of its sub-species), so the parent cannot change.
+void Engine::bulkContribution (Species *c, Species *from, uint32_t n1, uint32_t n2) {
+  auto &v = c->contribs;
+  size_t i = 0;
+  while (i < v.size() && v[i].sid != from->sid) i++;
+  if (i == v.size() || c->parent != from) {           // not the situation described above: one update per birth, as the reference
+    for (uint32_t q = 0; q < n1; q++) updateContributions(c, { { from->sid, 1u } });
+    for (uint32_t q = 0; q < n2; q++) updateContributions(c, { { from->sid, 2u } });
+    return;
+  }
+  v[i].count += n1 + 2 * n2;
+  while (i > 0 && v[i - 1].count < v[i].count) { std::swap(v[i - 1], v[i]); i--; }
+}
+
+/// One birth the family pass (K3) decided with an effect on the tree: it entered a sub-species' enveloppe (append
+/// :668-677 / replacement :694-718) or founded a species (:637-643, :398-426).  The host mirrors the decision --
+/// the new species gets its id here, in birth order (:225-230) -- exactly as insertInto + updateContributions would;
+/// counters shared by all the births the family decided are booked per family (settleFamilies).
+void Engine::walkFamily (uint32_t i, const uint32_t *w, RepMeta &g, Species *s0, uint32_t fact, uint32_t &sid, int32_t &slot,
+                         uint32_t &replaced) {
+  Family &F = fams_[size_t(grpFam_[s0->grp_index])];
+  const uint32_t code = fact & FAM_CODE_MASK, child = fact >> FAM_CHILD_SHIFT, r = (fact >> FAM_SLOT_SHIFT) & 31u;
+  const Contributions contrib { { g.msid, 1u + (g.msid == g.fsid) } };
+  replaced = INV;
+  Species *c;
+  RepMeta m = g;
+  m.timestamp = step_;
+  if (code == FAM_FOUNDED) {
+    const uint32_t f = uint32_t(grpFam_[s0->grp_index]), j = child - F.snapN;
+    if (j != F.founded.size()) throw ApiError(APT_ERR_STATE, "family pass: species founded out of order");
+    forcedSlot_ = hNewFounder_.p[size_t(fams_.size()) * famMaxNew_ + size_t(f) * famMaxNew_ + j];
+    c = makeNode(contrib);                                    // simpleNewSpecies, :637-643
+    if (c->parent != s0) throw ApiError(APT_ERR_STATE, "family pass: a founded species did not become a sub-species");
+    F.founded.push_back(c);
+    m.udata = g.gid;
+    c->reps[0] = m;
+    memcpy(&hPayload_[(size_t(c->slot) * K_) * wp_], w, W_ * sizeof(uint32_t));
+    c->k = 1;
+    emit(APT_EV_ENTERS_ENVELOPPE, c->sid, g.gid, 0);
+    c->count++;  c->alive++;  c->last = step_;
+    // (:639-643: the founder is inserted with an empty contribution)
+  } else {
+    c = child < F.snapN ? s0->children[F.snapN - 1 - child] : F.founded.at(child - F.snapN);
+    const uint32_t k = c->k;
+    const float *d = hRows_.p + size_t(hFamRow_.p[i]) * K_;
+    if (fact & FAM_REPLACED) {
+      const uint32_t epId = c->reps[r].gid;
+      emit(APT_EV_LEAVES_ENVELOPPE, c->sid, epId, 0);
+      emit(APT_EV_ENTERS_ENVELOPPE, c->sid, g.gid, 0);
+      m.udata = epId;                                         // :710
+      replaced = epId;
+    } else {
+      if (r != k) throw ApiError(APT_ERR_STATE, "device/host enveloppe fill mismatch (family pass)");
+      emit(APT_EV_ENTERS_ENVELOPPE, c->sid, g.gid, 0);
+      m.udata = g.gid;
+      c->k = k + 1;
+    }
+    c->reps[r] = m;
+    memcpy(&hPayload_[(size_t(c->slot) * K_ + r) * wp_], w, W_ * sizeof(uint32_t));
+    for (uint32_t q = 0; q < k; q++)
+      if (q != r) c->dist[q * K_ + r] = c->dist[r * K_ + q] = d[q];
+    c->count++;  c->alive++;  c->last = step_;
+    bulkContribution(c, s0, g.msid == g.fsid ? 0u : 1u, g.msid == g.fsid ? 1u : 0u);
+  }
+  // the kernel wrote the same change to the pool
+  c->fam_epoch = chunkEpoch_;
+  touchSnap(c);
+  c->snap_mask |= (1u << r);
+  c->dev_fill = c->k;
+  setStreamable(c, true);
+  sid = c->sid;
+  slot = int32_t(r);
+  counters[14]++;
+}
+
+/// Books what the family pass decided without the host looking at the births one by one: per family the births'
+/// share of the statistics and of their species' pending counter (:293, :298, :444, :470, :526), per sub-species the
+/// births that joined it leaving its enveloppe alone (:721-723 counters, :741-769 contribution of the parent species).
+void Engine::settleFamilies (void) {
+  for (size_t f = 0; f < fams_.size(); f++) {
+    const Family &F = fams_[f];
+    const uint4 info = hFamInfo_.p[f];
+    if (!info.x) continue;
+    Species *S = grpSpecies_[F.g];
+    S->pending = S->pending > info.x ? S->pending - info.x : 0;
+    insertions_ += info.x;
+    branching_ += uint32_t(hFamStats_.p[2 * f]);
+    comparisons_ += uint32_t(hFamStats_.p[2 * f + 1]);
+    counters[0] += info.x;  counters[1] += info.x;  counters[15] += info.x;
+    if (info.y != F.founded.size()) throw ApiError(APT_ERR_STATE, "family pass: founded species were not all committed");
+    const uint32_t C = F.snapN + info.y;
+    for (uint32_t c = 0; c < C; c++) {
+      const uint32_t n1 = hChildJoin_.p[F.joinOff + 2 * c], n2 = hChildJoin_.p[F.joinOff + 2 * c + 1];
+      if (!(n1 + n2)) continue;
+      Species *sp = c < F.snapN ? S->children[F.snapN - 1 - c] : F.founded[c - F.snapN];
+      sp->count += n1 + n2;  sp->alive += n1 + n2;  sp->last = step_;
+      bulkContribution(sp, S, n1, n2);
+    }
+  }
+}
+
 /// Device-resident births: genome of a birth the stream kernel put into an enveloppe (it came back with the
 /// birth's distance row), or null when the birth is not such an entry
 const uint32_t* Engine::entryRowOf (uint32_t i) const {
   if (birthGroup_[i] < 0) return nullptr;
   const uint32_t act = hAct_.p[i];
+  if (famResults_ && act == ACT_FALLTHROUGH && (hFamAct_.p[i] & FAM_CODE_MASK) >= FAM_ENTERED)
+    return hRowPayload_.p + size_t(hFamRow_.p[i]) * wp_;       // entered a sub-species / founded one in the family pass
   if ((act & (ACT_CODE_MASK | ACT_UNCERTAIN)) != ACT_ENTERED) return nullptr;
   return hRowPayload_.p + size_t(act >> ACT_ROW_SHIFT) * wp_;
 }
@@ -1134,6 +1243,8 @@ void Engine::groupSerial (uint32_t n, const uint32_t *msid, const uint32_t *fsid
       continue;
     }
     birthGroup_[i] = -1;
+    if (s0) s0->pair_epoch = chunkEpoch_;                 // walked by the host: nobody else may own these species' families
+    if (s1) s1->pair_epoch = chunkEpoch_;
     PairRef pr { i, -1, -1 };
     if (s0 && s0->dev_fill) { pr.p0 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
     if (s1 && s1->dev_fill) { pr.p1 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
@@ -1279,6 +1390,8 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
       if (m == INV && f == INV) s0 = root_;
       else if (f == INV || m == f) s0 = lookup(m);
       else { s0 = lookup(m); s1 = lookup(f); }
+      if (s0) s0->pair_epoch = chunkEpoch_;
+      if (s1) s1->pair_epoch = chunkEpoch_;
       PairRef pr { i, -1, -1 };
       auto touch = [&] (Species *s) {
         if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
@@ -1297,6 +1410,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   double t0 = now();
   chunkEpoch_++;
   curBirth_ = 0;              // (the error path settles the streams at the birth being committed)
+  famResults_ = false;  famSlotsUsed_ = 0;
   // APT_PROFILE: named time marks of this chunk, printed as successive differences at its end
   std::vector<std::pair<const char*, double>> marks;
   auto mark = [&] (const char *name) { if (profile_) marks.emplace_back(name, now()); };
@@ -1403,16 +1517,45 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     size_t total = 0;
     for (uint32_t g = 0; g < G; g++) total += grpSpecies_[g]->children.size();
     hChildOff_.reserve(G + 1);  hChildSlot_.reserve(total + 1);
+    if (famOk_) {
+      hChildSid_.reserve(total + 1);
+      uploadLut();                                         // (the table's size decides how many sub-species fit)
+      famCap_ = family_capacity(wp_, K_, scoreCfg());
+    }
+    fams_.clear();
+    grpFam_.assign(G, -1);
+    // A family -- the births a stream's species rejects at top level and that species' sub-species -- is resolved on the
+    // device (K3) when nothing else in this pass can touch it: the species and its parent are named by no birth outside
+    // the streams, the parent has no stream (its rejected births would walk into this species), no sub-species has a
+    // stream or a two-parent birth of its own, all of them are current on the device, and a species founded now becomes
+    // a sub-species (strictly older parent, speciescontributors.h:177-197).
+    uint32_t joinOff = 0, maxSnap = 0;
     for (uint32_t g = 0; g < G; g++) {
       hChildOff_.p[g] = uint32_t(nChild);
-      const auto &ch = grpSpecies_[g]->children;
+      Species *S = grpSpecies_[g];
+      const auto &ch = S->children;
+      bool ok = famOk_ && S->pair_epoch != chunkEpoch_ && S->first < step_ && ch.size() + 8 <= famCap_
+                && (!S->parent || (S->parent->grp_epoch != chunkEpoch_ && S->parent->pair_epoch != chunkEpoch_));
       for (size_t idx = ch.size(); idx-- > 0; ) {
         const Species *c = ch[idx];
-        hChildSlot_.p[nChild++] = (c->dev_fill && c->dev_fill == c->k && !c->stale_mask && !c->full_upload) ? c->slot : INV;
+        const bool current = c->dev_fill && c->dev_fill == c->k && !c->stale_mask && !c->full_upload;
+        if (famOk_) hChildSid_.p[nChild] = c->sid;
+        hChildSlot_.p[nChild++] = current ? c->slot : INV;
+        ok = ok && current && c->grp_epoch != chunkEpoch_ && c->pair_epoch != chunkEpoch_;
+      }
+      if (ok) {
+        grpFam_[g] = int32_t(fams_.size());
+        fams_.push_back(Family{ g, uint32_t(ch.size()), joinOff, {} });
+        maxSnap = std::max<uint32_t>(maxSnap, uint32_t(ch.size()));
       }
     }
     hChildOff_.p[G] = uint32_t(nChild);
-  }
+    if (!fams_.empty()) {
+      // species a family may found before it hands the rest of its births back; the counters of family f start at joinOff_f
+      famMaxNew_ = std::min<uint32_t>(famCap_ - maxSnap, std::max<uint32_t>(16u, std::min<uint32_t>(256u, uint32_t(65536 / fams_.size()))));
+      for (Family &F: fams_) { F.joinOff = joinOff; joinOff += 2 * (F.snapN + famMaxNew_); }
+    }
+  } else { fams_.clear(); grpFam_.assign(G, -1); }
   uploadLut();
   mark("children");
   timers[0] += now() - t0;
@@ -1475,7 +1618,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
     // few, larger transfers: every call below costs the host ~3 us before the kernel can start
     dOrder_.reserve(nStream);  dGrpAll_.reserve(3 * size_t(G) + 1);  hGrpAll_.reserve(3 * size_t(G) + 1);  dAct_.reserve(n);
-    dCtr_.reserve(2);  hCtr_.reserve(2);  dRows_.reserve((size_t(nStream) + 8 * size_t(G)) * K_);
+    dCtr_.reserve(2);  hCtr_.reserve(4);  dRows_.reserve((size_t(nStream) + 8 * size_t(G)) * K_);
     dOut2_.reserve(2 * size_t(n));  dGrpSum_.reserve(G);
     hAct_.reserve(n);  hOutSid_.reserve(n);  hOutSlot_.reserve(n);  hGrpSum_.reserve(G);
     uint32_t *dGrpSlot = dGrpAll_.p, *dGrpSid = dGrpAll_.p + G, *dGrpOff = dGrpAll_.p + 2 * size_t(G);
@@ -1501,6 +1644,11 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (!payload) { dRowPayload_.reserve(size_t(nStream) * wp_ + 4); a.row_payload = dRowPayload_.p; }
     a.grp_sid = dGrpSid;  a.out_sid = dOutSid;  a.out_slot = dOutSlot;  a.grp_sum = dGrpSum_.p;
     a.ft_list = nullptr;  a.ft_counter = nullptr;
+    const uint32_t nFam = uint32_t(fams_.size());
+    if (nFam) {
+      dRejOrder_.reserve(nStream);  dRejFill_.reserve(nStream);  dRejCount_.reserve(G);
+      a.rej_order = dRejOrder_.p;  a.rej_fill = dRejFill_.p;  a.rej_count = dRejCount_.p;
+    }
     if (useChildKernel) {
       dFtList_.reserve(2 * nStream);
       // everything the sub-species pass may need is allocated with the first stream pass, not on the step in which the
@@ -1533,6 +1681,57 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       launch_classify_children(c, stream_);
       counters[4]++;
       cudaCheck(cudaGetLastError(), "classify_children launch");
+    }
+    if (nFam) {
+      // K3: the rejected births of every eligible family walk its sub-species on the device, in order, founding included
+      // (family.cu).  Species founded there take consecutive pool slots behind the ones in use; the host makes them
+      // real when it commits the founding births.
+      const uint32_t reserve = uint32_t(std::min<size_t>(nStream, size_t(1) << 16));
+      famSlotBase_ = nSlots_;
+      const size_t slots = size_t(nSlots_) + reserve;
+      dPool_.reserve(slots * K_ * wp_, true, stream_);  dMeta_.reserve(slots * K_, true, stream_);
+      dPoolDist_.reserve(slots * K_ * K_, true, stream_);
+      { const size_t oldCap = dFill_.cap;
+        dFill_.reserve(slots, true, stream_);
+        if (dFill_.cap != oldCap) cudaCheck(cudaMemsetAsync(dFill_.p + oldCap, 0, (dFill_.cap - oldCap) * 4, stream_), "fill clear"); }
+      size_t joinWords = 0;
+      for (const Family &F: fams_) joinWords = std::max<size_t>(joinWords, F.joinOff + 2 * (size_t(F.snapN) + famMaxNew_));
+      hFamTab_.reserve(2 * size_t(nFam));  dFamTab_.reserve(2 * size_t(nFam));
+      for (uint32_t f = 0; f < nFam; f++) { hFamTab_.p[f] = fams_[f].g;  hFamTab_.p[nFam + f] = fams_[f].joinOff; }
+      dChildSid_.reserve(nChild + 1);  dFamAct_.reserve(n);  dFamRow_.reserve(n);  dChildJoin_.reserve(joinWords + 1);
+      dNewFounder_.reserve(size_t(nFam) * famMaxNew_ * 2);  dFamInfo_.reserve(nFam);  dFamStats_.reserve(2 * size_t(nFam));
+      dFamSlotCtr_.reserve(1);
+      if (!(useChildKernel && nChild)) {        // (the sub-species lists usually went up for K2 just above)
+        dChildOff_.reserve(G + 1);  dChildSlot_.reserve(nChild + 1);
+        cudaCheck(cudaMemcpyAsync(dChildOff_.p, hChildOff_.p, (G + 1) * 4, cudaMemcpyHostToDevice, stream_), "children");
+        if (nChild) cudaCheck(cudaMemcpyAsync(dChildSlot_.p, hChildSlot_.p, nChild * 4, cudaMemcpyHostToDevice, stream_), "children");
+      }
+      if (nChild) cudaCheck(cudaMemcpyAsync(dChildSid_.p, hChildSid_.p, nChild * 4, cudaMemcpyHostToDevice, stream_), "children");
+      cudaCheck(cudaMemcpyAsync(dFamTab_.p, hFamTab_.p, 2 * size_t(nFam) * 4, cudaMemcpyHostToDevice, stream_), "families");
+      cudaCheck(cudaMemsetAsync(dFamAct_.p, 0, size_t(n) * 4, stream_), "family results clear");
+      cudaCheck(cudaMemsetAsync(dFamSlotCtr_.p, 0, 4, stream_), "family slot counter clear");
+      FamilyArgs fa;
+      fa.pool = poolView();  fa.pool.n_slots = uint32_t(slots);
+      fa.pool_payload_w = dPool_.p;  fa.pool_cmeta_w = dMeta_.p;  fa.pool_fill_w = dFill_.p;  fa.pool_dist = dPoolDist_.p;
+      fa.cfg = scoreCfg();  fa.crit = p_.env_crit;  fa.guard = GUARD;
+      fa.b_payload = dBirthRows;  fa.b_cmeta = dBMeta_.p;
+      fa.n_fam = nFam;  fa.fam_group = dFamTab_.p;  fa.fam_join_off = dFamTab_.p + nFam;
+      fa.grp_off = dGrpOff;  fa.rej_order = dRejOrder_.p;  fa.rej_fill = dRejFill_.p;  fa.rej_count = dRejCount_.p;
+      fa.child_off = dChildOff_.p;  fa.child_slot = dChildSlot_.p;  fa.child_sid = dChildSid_.p;
+      fa.slot_counter = dFamSlotCtr_.p;  fa.slot_base = famSlotBase_;  fa.slot_limit = reserve;
+      fa.max_new = famMaxNew_;
+      uint32_t maxSnap = 0;
+      for (const Family &F: fams_) maxSnap = std::max(maxSnap, F.snapN);
+      fa.cap = std::min<uint32_t>(famCap_, (maxSnap + famMaxNew_ + 31u) & ~31u);
+      fa.fam_act = dFamAct_.p;  fa.fam_row = dFamRow_.p;  fa.out_sid = dOutSid;  fa.out_slot = dOutSlot;
+      fa.rows = dRows_.p;  fa.row_payload = a.row_payload;  fa.row_counter = dCtr_.p;
+      fa.fam_info = dFamInfo_.p;  fa.fam_stats = dFamStats_.p;  fa.child_join = dChildJoin_.p;
+      fa.new_founder = dNewFounder_.p;  fa.new_slot = dNewFounder_.p + size_t(nFam) * famMaxNew_;
+      launch_resolve_families(fa, stream_);
+      counters[4]++;
+      cudaCheck(cudaGetLastError(), "resolve_families launch");
+      hFamInfo_.reserve(nFam);
+      cudaCheck(cudaMemcpyAsync(hFamInfo_.p, dFamInfo_.p, size_t(nFam) * sizeof(uint4), cudaMemcpyDeviceToHost, stream_), "family info");
     }
     if (!payload && useChildKernel) {
       // device-resident births: the host will want the genomes of the births the streams rejected (it walks the
@@ -1633,7 +1832,36 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           cudaCheck(cudaMemcpyAsync(hFtList_.p, dFtList_.p, 2 * size_t(nFtRows_) * 4, cudaMemcpyDeviceToHost, stream_), "ft list");
         }
       }
-      if (nRows > specRows || nFt_ || nFtRows_ > specFt) cudaCheck(cudaStreamSynchronize(stream_), "rows");
+      // what the family pass decided comes back only when it decided anything (a second round trip, radiations only)
+      famResults_ = false;
+      famSlotsUsed_ = 0;
+      if (!fams_.empty()) {
+        const uint32_t nFam = uint32_t(fams_.size());
+        uint64_t decided = 0;
+        for (uint32_t f = 0; f < nFam; f++) decided += hFamInfo_.p[f].x;
+        if (decided) {
+          size_t joinWords = 0;
+          for (const Family &F: fams_) joinWords = std::max<size_t>(joinWords, F.joinOff + 2 * (size_t(F.snapN) + famMaxNew_));
+          hFamAct_.reserve(n);  hFamRow_.reserve(n);  hChildJoin_.reserve(joinWords + 1);
+          hNewFounder_.reserve(size_t(nFam) * famMaxNew_ * 2 + 1);  hFamStats_.reserve(2 * size_t(nFam));
+          cudaCheck(cudaMemcpyAsync(hFamAct_.p, dFamAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "family results");
+          cudaCheck(cudaMemcpyAsync(hFamRow_.p, dFamRow_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "family rows");
+          cudaCheck(cudaMemcpyAsync(hChildJoin_.p, dChildJoin_.p, joinWords * 4, cudaMemcpyDeviceToHost, stream_), "family counters");
+          cudaCheck(cudaMemcpyAsync(hNewFounder_.p, dNewFounder_.p, size_t(nFam) * famMaxNew_ * 2 * 4, cudaMemcpyDeviceToHost, stream_), "family founders");
+          cudaCheck(cudaMemcpyAsync(hFamStats_.p, dFamStats_.p, 2 * size_t(nFam) * 8, cudaMemcpyDeviceToHost, stream_), "family stats");
+          cudaCheck(cudaMemcpyAsync(hCtr_.p + 2, dFamSlotCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "family slots");
+          famResults_ = true;
+        }
+      }
+      if (nRows > specRows || nFt_ || nFtRows_ > specFt || famResults_) cudaCheck(cudaStreamSynchronize(stream_), "rows");
+      if (famResults_) {
+        famSlotsUsed_ = std::min<uint32_t>(hCtr_.p[2], uint32_t(std::min<size_t>(nStream, size_t(1) << 16)));
+        if (famSlotsUsed_) {
+          // the species founded on the device live in pool slots [famSlotBase_, +used): they become real now
+          nSlots_ = famSlotBase_ + famSlotsUsed_;
+          hPayload_.resize(size_t(nSlots_) * K_ * wp_, 0u);
+        }
+      }
       estRows_ = nRows + nRows / 4 + 64;
       estFt_ = ftRows ? nFtRows_ + nFtRows_ / 2 + 256 : estFt_;     // (few, and their number varies more)
     }
@@ -1667,7 +1895,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       for (uint32_t i = lo; i < hi; i++) {
         const int32_t bg = birthGroup_[i];
         const uint32_t act = hAct_.p[i];
-        if (!(bg >= 0 && act == ACT_ACCEPTED)) { rest.push_back(i);  rest.push_back(uint32_t(bg));  rest.push_back(act); }
+        // settled on the device: accepted with the enveloppe left alone -- at top level, or (family pass) by a sub-species
+        const bool settled = bg >= 0 && (act == ACT_ACCEPTED ||
+                                         (famResults_ && act == ACT_FALLTHROUGH && (hFamAct_.p[i] & FAM_CODE_MASK) == FAM_JOINED));
+        if (!settled) { rest.push_back(i);  rest.push_back(uint32_t(bg));  rest.push_back(act); }
       }
     };
     mark("commit-init");
@@ -1886,7 +2117,11 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       const uint32_t *w = payloadOf(i);
       const double p0t = profile_ ? now() : 0.;
       int pcat = 0;                       // 0 plain entry, 1 rejected at top level (stream), 2 everything else
-      if (s0) { pcat = (act & ACT_CODE_MASK) == ACT_FALLTHROUGH ? 1 : 0; walkStream(w, g, s0, act, sid, slot, replaced); }
+      if (s0 && famResults_ && act == ACT_FALLTHROUGH && hFamAct_.p[i] != FAM_UNPROCESSED) {
+        pcat = 1;
+        walkFamily(i, w, g, s0, hFamAct_.p[i], sid, slot, replaced);
+      }
+      else if (s0) { pcat = (act & ACT_CODE_MASK) == ACT_FALLTHROUGH ? 1 : 0; walkStream(w, g, s0, act, sid, slot, replaced); }
       else {
         pcat = 2;
         int64_t p0 = -1, p1 = -1;
@@ -1911,6 +2146,21 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       if (g + 4 < G) __builtin_prefetch(grpSpecies_[g + 4]->contribs.data(), 1);
       if (grpSpecies_[g]->div_epoch != chunkEpoch_) settleStream(g, false, 0, nullptr);
     }
+    if (famResults_) {
+      settleFamilies();
+      // births placed in a species founded in this pass carry a placeholder: the ids were handed out by the walk above
+      if (outSid && famSlotsUsed_) {
+        const uint32_t nFam = uint32_t(fams_.size());
+        for (uint32_t i = 0; i < n; i++) {
+          const uint32_t v = outSid[i];
+          if (v != INV && (v & FAM_NEW_SID)) {
+            const uint32_t f = (v & ~FAM_NEW_SID) / famMaxNew_, j = (v & ~FAM_NEW_SID) % famMaxNew_;
+            if (f >= nFam || j >= fams_[f].founded.size()) throw ApiError(APT_ERR_STATE, "family pass: unknown founded species");
+            outSid[i] = fams_[f].founded[j]->sid;
+          }
+        }
+      }
+    }
     mark("settle");
     if (profile_ && n >= parMin_) {
       fprintf(stderr, "chunk:");
@@ -1923,6 +2173,27 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     // reference throws out of addGenome; streams are settled up to that birth
     const uint32_t failed = curBirth_;
     curBirth_ = failed;
+    if (famResults_) {
+      // the family pass decided births beyond the failing one too: its sub-species are rewritten from the host state, and
+      // the births before the failure that joined one without changing it are booked one by one (their share of
+      // Stats::comparisons / branching is only known per family and is not added)
+      for (uint32_t i = 0; i < failed && i < n; i++) {
+        if (birthGroup_[i] < 0 || hAct_.p[i] != ACT_FALLTHROUGH || (hFamAct_.p[i] & FAM_CODE_MASK) != FAM_JOINED) continue;
+        Species *S = grpSpecies_[size_t(birthGroup_[i])];
+        const Family &F = fams_[size_t(grpFam_[S->grp_index])];
+        const uint32_t child = hFamAct_.p[i] >> FAM_CHILD_SHIFT;
+        if (child >= F.snapN + F.founded.size()) continue;
+        Species *sp = child < F.snapN ? S->children[F.snapN - 1 - child] : F.founded[child - F.snapN];
+        if (S->pending > 0) S->pending--;
+        sp->count++;  sp->alive++;  sp->last = step_;  insertions_++;
+        bulkContribution(sp, S, msid[i] == fsid[i] ? 0u : 1u, msid[i] == fsid[i] ? 1u : 0u);
+      }
+      for (const Family &F: fams_) {
+        Species *S = grpSpecies_[F.g];
+        for (Species *sp: S->children) { sp->full_upload = true; queueRefresh(sp); }
+      }
+      // (slots of species the device founded behind the failing birth stay unused)
+    }
     for (uint32_t g = 0; g < G; g++)
       if (grpSpecies_[g]->div_epoch != chunkEpoch_) {
         grpSpecies_[g]->div_epoch = chunkEpoch_;  grpSpecies_[g]->full_upload = true;  queueRefresh(grpSpecies_[g]);

@@ -169,6 +169,8 @@ struct Species {
   uint32_t child_change_epoch = 0;        // chunk in which a sub-species was moved into / out of this node
   bool full_upload = false;               // the device copy (rows, matrix, fill) must be rewritten entirely
   uint32_t touch_epoch = 0;               // last scoring launch that read this enveloppe
+  uint32_t pair_epoch = 0;                // chunk in which a birth outside the streams names this species as a parent
+  uint32_t fam_epoch = 0;                 // chunk in which the family pass (K3) changed this enveloppe
   bool extinct (void) const { return alive == 0 && pending == 0; }   // node.hpp:157-159
 };
 
@@ -304,6 +306,26 @@ private:
   uint32_t estRows_ = 0, estFt_ = 0;     // enveloppe entries / rejected births of the last device pass (+25 %): fetched speculatively with the results
   DevBuf<uint32_t> dFtRows_;  PinBuf<uint32_t> hFtRows_;
   int64_t curFt_ = -1;                    // sub-species result entry of the birth being committed
+  // sub-species resolution on the device (K3, family.cu): the rejected births of a stream against its species'
+  // sub-species, in order, founding included
+  bool famOk_ = false;                    // the family kernel can serve this tree's configuration
+  uint32_t famCap_ = 0;                   // sub-species (at submission + founded) one family may hold
+  struct Family {
+    uint32_t g, snapN, joinOff;           // stream index, sub-species at submission, offset of its counters
+    std::vector<Species*> founded;        // species the family founded in this pass, in founding order
+  };
+  std::vector<Family> fams_;
+  std::vector<int32_t> grpFam_;           // stream -> family, -1 = none
+  uint32_t famMaxNew_ = 0, famSlotBase_ = 0, famSlotsUsed_ = 0;
+  bool famResults_ = false;               // the pass produced family results (fetched)
+  uint32_t forcedSlot_ = 0xFFFFFFFFu;     // pool slot the next makeNode takes (a species the device founded lives there already)
+  DevBuf<uint32_t> dRejOrder_, dRejFill_, dRejCount_, dFamTab_, dChildSid_, dFamAct_, dFamRow_, dChildJoin_, dNewFounder_, dFamSlotCtr_;
+  DevBuf<uint4> dFamInfo_;  DevBuf<unsigned long long> dFamStats_;
+  PinBuf<uint32_t> hFamTab_, hChildSid_, hFamAct_, hFamRow_, hChildJoin_, hNewFounder_;
+  PinBuf<uint4> hFamInfo_;  PinBuf<unsigned long long> hFamStats_;
+  void walkFamily (uint32_t i, const uint32_t *w, RepMeta &g, Species *s0, uint32_t fact, uint32_t &sid, int32_t &slot, uint32_t &replaced);
+  void settleFamilies (void);
+  void bulkContribution (Species *c, Species *from, uint32_t n1, uint32_t n2);
   uint32_t chunkEpoch_ = 0;
   bool chunkUniform_ = false;             // every birth of the chunk carries the same compatibility triple
   const float4 *fillPtr_ = nullptr;  uint32_t fillN_ = 0;  float4 fillValue_ {};   // what the births' device meta array was last filled with (uniform chunks)

@@ -118,11 +118,75 @@ struct StreamArgs {
   uint32_t *ft_list;          ///< births rejected at top level, appended as (birth, stream) pairs ...
   uint32_t *ft_counter;       ///< ... counted here (zero-initialised)
   uint32_t *row_counter;      ///< zero-initialised; a stream claims the rows of a step (its enveloppe entries) with one add
+  uint32_t *rej_order = nullptr;  ///< optional [n stream births]: per stream, at grp_off[g], its births rejected at top level in ARRIVAL
+                              ///< order (order words) -- the input of the sub-species resolution on the device (family.cu)
+  uint32_t *rej_fill = nullptr;   ///< same layout: the enveloppe fill each one's top-level score saw (Stats::comparisons)
+  uint32_t *rej_count = nullptr;  ///< [n_groups] how many
   int lut_in_smem = 0;        ///< set by the launcher
   unsigned long long *prof = nullptr;   ///< optional [n_groups][12] per-stream timeline (APT_STREAM_PROF), see stream.cu
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t stream);
+
+/// Result word of the family kernel (family.cu) per birth rejected at top level; zero = not processed (the host walks it)
+enum : uint32_t {
+  FAM_UNPROCESSED = 0u,
+  FAM_JOINED = 1u,            ///< accepted by a sub-species whose enveloppe it leaves alone
+  FAM_ENTERED = 2u,           ///< accepted by a sub-species and now one of its representatives
+  FAM_FOUNDED = 3u,           ///< no sub-species accepted it: founds a new one (:637-643)
+  FAM_CODE_MASK = 3u,
+  FAM_REPLACED = 4u,          ///< (with FAM_ENTERED) took the place of an older representative
+  FAM_SLOT_SHIFT = 3u,        ///< 5 bits: enveloppe slot
+  FAM_CHILD_SHIFT = 8u        ///< 24 bits: the sub-species: rank in the family's snapshot list (visiting order), or
+                              ///< snapshot count + j for the j-th species founded in this pass
+};
+/// out_sid of a birth placed in a species founded in this pass: FAM_NEW_SID | family * max_new + j (the id is given out
+/// by the host's ordered commit, :225-230)
+constexpr uint32_t FAM_NEW_SID = 0x80000000u;
+
+/// K3 -- findBestDerived + insertInto + makeNode (phylogenetictree.hpp:493-548, :657-726, :637-643) on the device for
+/// whole "families": the births one stream's species rejected at top level, IN ORDER, against that species' direct
+/// sub-species -- those it had at submission and those founded inside this very pass -- with every enveloppe change
+/// (append, replacement, a new species) visible to the next birth, exactly as the reference's sequential walk.
+/// One CTA per family; the sub-species' enveloppes live in shared memory.  A family is only submitted when nothing
+/// else in the pass can touch its sub-species (engine.cpp: no stream or two-parent birth of their own).
+struct FamilyArgs {
+  PoolView pool;
+  uint32_t *pool_payload_w;  float4 *pool_cmeta_w;  uint32_t *pool_fill_w;  float *pool_dist;
+  ScoreCfg cfg;
+  int crit;                   ///< 0 maxAverage, 1 maxMinDist
+  float guard;
+  const uint32_t *b_payload;  const float4 *b_cmeta;
+  uint32_t n_fam;
+  const uint32_t *fam_group;  ///< [n_fam] stream index of the family
+  const uint32_t *grp_off;    ///< [n_groups+1] stream extents = where its ordered reject list starts in rej_order
+  const uint32_t *rej_order, *rej_fill, *rej_count;     ///< written by the stream kernel (StreamArgs)
+  const uint32_t *child_off;  ///< [n_groups+1] offsets into child_slot / child_sid
+  const uint32_t *child_slot; ///< sub-species at submission, visiting order (newest first, :506): pool slots ...
+  const uint32_t *child_sid;  ///< ... and species ids
+  uint32_t *slot_counter;     ///< zero-initialised: species founded in this pass take the pool slots slot_base + 0, 1, 2 ...
+  uint32_t slot_base, slot_limit;   ///< ... up to slot_limit of them (the pool arrays are sized for it)
+  uint32_t max_new;           ///< species a family may found before it hands the rest of its births back
+  uint32_t cap;               ///< sub-species (at submission + founded) that fit in shared memory
+  uint32_t *fam_act;          ///< [n_births] result words (zero-initialised)
+  uint32_t *fam_row;          ///< [n_births] index into rows / row_payload (FAM_ENTERED, FAM_FOUNDED)
+  uint32_t *out_sid;  int32_t *out_slot;
+  float *rows;                ///< [n_rows][K] cached distances of the births that entered an enveloppe
+  uint32_t *row_payload;      ///< [n_rows][wp] their genomes, or null
+  uint32_t *row_counter;      ///< zero-initialised
+  uint4 *fam_info;            ///< [n_fam] {births decided, species founded, 1 = handed the rest back, sub-species in the end}
+  unsigned long long *fam_stats;  ///< [n_fam][2] Stats::branching (:526) and Stats::comparisons (:444 / :470) of the births
+                              ///< decided here (their top-level scores included)
+  const uint32_t *fam_join_off;   ///< [n_fam] where the family's per-sub-species counters start in child_join
+  uint32_t *child_join;       ///< per sub-species (snapshot ranks, then founded): FAM_JOINED births contributing 1 / 2 (:576-577)
+  uint32_t *new_founder;      ///< [n_fam][max_new] birth that founded the j-th new species
+  uint32_t *new_slot;         ///< [n_fam][max_new] the pool slot it lives in
+  int lut_in_smem = 0;
+};
+bool family_kernel_supports (uint32_t wp, uint32_t K, int crit);
+/// sub-species capacity of one family for this shape (0 = unsupported)
+uint32_t family_capacity (uint32_t wp, uint32_t K, const ScoreCfg &cfg);
+void launch_resolve_families (const FamilyArgs &a, cudaStream_t stream);
 
 /// K2 -- findBestDerived (phylogenetictree.hpp:493-548) for the births a stream rejected at top level:
 /// one warp per rejected birth walks the sub-species of its species in the reference's visiting

@@ -330,6 +330,7 @@ resolve_streams_kernel (StreamArgs a) {
   Lane<KT> ln;
 
   uint32_t changed = 0;         // slots to write back (uniform)
+  uint32_t nRej = 0;            // births rejected at top level so far (uniform)
   bool aborted = false;
   uint32_t nAcc0 = 0, nAcc1 = 0, nAcc2 = 0;     // per thread: accepted, enveloppe unchanged, by contribution class
 
@@ -374,7 +375,7 @@ resolve_streams_kernel (StreamArgs a) {
     // Nothing leaves the chip inside the event loop: scattered global stores ahead of the shared-memory
     // traffic of the next event cost ~1.3 us per event (measured with APT_STREAM_PROF; the LDS queue up
     // behind them).  Each thread keeps its verdict in registers and the step's results are written once.
-    uint32_t myAct = ACT_UNPROCESSED, myEv = 0, nEv = 0;
+    uint32_t myAct = ACT_UNPROCESSED, myEv = 0, nEv = 0, myK = 0;
     bool rejected = false;
 
     for (;;) {
@@ -415,6 +416,7 @@ resolve_streams_kernel (StreamArgs a) {
       if (mine && uint32_t(tid) < stop) {           // final: every earlier decision stands
         myAct = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
         rejected = !accept;
+        myK = k;                                    // the enveloppe fill this birth's top-level score saw
         mine = false;
       }
       if (event == NONE) break;
@@ -482,6 +484,9 @@ resolve_streams_kernel (StreamArgs a) {
     //      and the births rejected at top level queue up for the sub-species kernel ----
     if (nEv && tid == 0) ws.ctl(33) = atomicAdd(a.row_counter, nEv);
     const uint32_t ftm = __ballot_sync(0xffffffffu, rejected);
+    // ... and, for the sub-species resolution on the device (family.cu), line up per stream IN ARRIVAL ORDER:
+    // the warps' counts meet in shared memory across the barrier below
+    if (a.rej_order && lane == 0) ws.ctl(40 + warp) = uint32_t(__popc(ftm));
     if (ftm && a.ft_list) {
       uint32_t fbase = 0;
       if (lane == 0) fbase = atomicAdd(a.ft_counter, uint32_t(__popc(ftm)));
@@ -492,6 +497,17 @@ resolve_streams_kernel (StreamArgs a) {
       }
     }
     __syncthreads();
+    if (a.rej_order) {
+      uint32_t before = 0, all = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) { const uint32_t c = ws.ctl(40 + w); all += c; before += (w < warp) ? c : 0u; }
+      if (rejected) {
+        const uint32_t at = g0 + nRej + before + __popc(ftm & ((1u << lane) - 1u));
+        a.rej_order[at] = ord;
+        a.rej_fill[at] = myK;                     // the enveloppe fill its top-level score saw (Stats::comparisons, :444 / :470)
+      }
+      nRej += all;
+    }
     const uint32_t rowBase = nEv ? ws.ctl(33) : 0u;
     if (active) {
       const uint32_t code = myAct & ACT_CODE_MASK;
@@ -518,7 +534,10 @@ resolve_streams_kernel (StreamArgs a) {
   // ---- per-stream totals ----
   atomicAdd(&ws.ctl(36), nAcc0);  atomicAdd(&ws.ctl(37), nAcc1);  atomicAdd(&ws.ctl(38), nAcc2);
   __syncthreads();
-  if (tid == 0) a.grp_sum[g] = make_uint4(ws.ctl(36), ws.ctl(37), ws.ctl(38), aborted ? 1u : 0u);
+  if (tid == 0) {
+    a.grp_sum[g] = make_uint4(ws.ctl(36), ws.ctl(37), ws.ctl(38), aborted ? 1u : 0u);
+    if (a.rej_order) a.rej_count[g] = nRej;
+  }
 
   // ---- write the enveloppe back (the host mirrors the same changes from act/rows) ----
   if (changed && !aborted) {

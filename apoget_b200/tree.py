@@ -17,7 +17,7 @@ from ._lib import AptParams, check, lib
 
 INVALID = 0xFFFFFFFF
 BITS, F32 = 0, 1
-FLAG_NO_EVENTS, FLAG_NO_CHILD_KERNEL, FLAG_FORCE_GENERIC, FLAG_NO_STREAM_KERNEL = 1, 2, 4, 8
+FLAG_NO_EVENTS, FLAG_NO_CHILD_KERNEL, FLAG_FORCE_GENERIC, FLAG_NO_STREAM_KERNEL, FLAG_NO_FAMILY_KERNEL = 1, 2, 4, 8, 16
 
 # config::PTree defaults, src/core/ptreeconfig.cpp:7-19
 DEFAULTS = dict(K=5, full_continuous=True, env_crit=1, compat_thr=.1, sim_thr=.5, avg_thr=.25,
@@ -144,7 +144,7 @@ class PhylogeneticTree:
         keys = ["births", "device_scores", "patched_scores", "host_scores", "kernel_launches",
                 "host_distance_evals", "guard_rechecks", "device_pairs", "device_reps_read",
                 "score_launches", "refresh_rows", "streams_taken_over", "stream_launches", "stream_births",
-                "stream_entries"]
+                "stream_entries", "family_births"]
         return dict(zip(keys, (int(x) for x in out)))
 
     def timers(self) -> dict:

@@ -74,7 +74,8 @@ enum apt_flags {
   APT_FLAG_NO_EVENTS = 1u,       /* do not record the event stream */
   APT_FLAG_NO_CHILD_KERNEL = 2u, /* debug: sub-species candidates are scored by the host repair path only */
   APT_FLAG_FORCE_GENERIC = 4u,   /* debug: never use the compatibility look-up table */
-  APT_FLAG_NO_STREAM_KERNEL = 8u /* debug: single-parent births are resolved by the host walk over speculative scores */
+  APT_FLAG_NO_STREAM_KERNEL = 8u,/* debug: single-parent births are resolved by the host walk over speculative scores */
+  APT_FLAG_NO_FAMILY_KERNEL = 16u /* debug: births rejected at top level always walk the sub-species on the host */
 };
 
 /* Fills *p with the reference's compiled-in defaults (ptreeconfig.cpp:7-19). */
@@ -189,7 +190,8 @@ int apt_tree_del_genomes (apt_tree *t, uint32_t n, const uint32_t *sids);
  * [6] guard-band rechecks, [7] device pairs submitted to the scoring kernel, [8] representatives
  * those pairs read (distinct enveloppe rows per launch, summed), [9] scoring-kernel launches,
  * [10] rows uploaded by pool refreshes, [11] streams the host had to take over, [12] stream-kernel
- * launches, [13] births submitted to it, [14] enveloppe entries it decided, [15] reserved. */
+ * launches, [13] births submitted to it, [14] enveloppe entries the device decided, [15] births rejected at top level
+ * whose sub-species walk was decided on the device (family pass). */
 int apt_tree_counters (apt_tree *t, uint64_t out[16]);
 
 /* Time spent (cumulative): out[0] host prepare (s), [1] device H2D+kernels+D2H as waited for by the

@@ -163,7 +163,7 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
     std::vector<uint32_t> reps (a.pool.payload + size_t(slot) * K * wp, a.pool.payload + size_t(slot + 1) * K * wp);
     std::vector<float4> meta (a.pool.cmeta + size_t(slot) * K, a.pool.cmeta + size_t(slot + 1) * K);
     std::vector<float> D (a.pool_dist + size_t(slot) * K * K, a.pool_dist + size_t(slot + 1) * K * K);
-    uint32_t changed = 0, nAcc[3] = {0, 0, 0};
+    uint32_t changed = 0, nAcc[3] = {0, 0, 0}, nRej = 0;
     bool aborted = false;
     for (uint32_t t = a.grp_off[g]; t < a.grp_off[g + 1]; t++) {
       const uint32_t b = a.order[t] & ORDER_INDEX_MASK, ccls = a.order[t] >> ORDER_CLASS_SHIFT;
@@ -182,6 +182,7 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       if (!(score > 0)) {
         a.act[b] = ACT_FALLTHROUGH;
         if (a.ft_list) { const uint32_t at = (*a.ft_counter)++; a.ft_list[2 * at] = b; a.ft_list[2 * at + 1] = g; }
+        if (a.rej_order) { a.rej_order[a.grp_off[g] + nRej] = a.order[t]; a.rej_fill[a.grp_off[g] + nRej] = k; nRej++; }
         continue;
       }
       uint32_t than = 0xFFFFFFFFu;
@@ -228,6 +229,7 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       changed |= 1u << than;
     }
     a.grp_sum[g] = make_uint4(nAcc[0], nAcc[1], nAcc[2], aborted ? 1u : 0u);
+    if (a.rej_order) a.rej_count[g] = nRej;
     if (changed && !aborted) {
       for (uint32_t r = 0; r < k; r++) {
         if (!((changed >> r) & 1u)) continue;
@@ -236,6 +238,138 @@ void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
       }
       memcpy(a.pool_dist + size_t(slot) * K * K, D.data(), size_t(K) * K * sizeof(float));
       a.pool_fill_w[slot] = k;
+    }
+  }
+}
+
+bool family_kernel_supports (uint32_t wp, uint32_t K, int crit) {
+  const uint32_t wq = wp >> 2;
+  return (wq == 1 || wq == 2 || wq == 4 || wq == 8 || wq == 16 || wq == 32) && (crit == 0 || crit == 1) && K >= 1 && K <= KMAX;
+}
+uint32_t family_capacity (uint32_t, uint32_t, const ScoreCfg&) { return 96; }     // small on purpose: tests reach the hand-back paths
+
+// Plain sequential stand-in for resolve_families_kernel (same inputs, outputs and write-back): the reference's
+// findBestDerived / insertInto / makeNode for the rejected births of a family, in order, on local copies.
+void launch_resolve_families (const FamilyArgs &a, cudaStream_t) {
+  const uint32_t K = a.pool.K, wp = a.pool.wp;
+  const float FMAX = std::numeric_limits<float>::max();
+  struct Child { std::vector<uint32_t> reps; std::vector<float4> meta; std::vector<float> D; uint32_t k, sid, changed, join[2]; };
+  for (uint32_t f = 0; f < a.n_fam; f++) {
+    const uint32_t g = a.fam_group[f], g0 = a.grp_off[g], nRej = a.rej_count[g];
+    const uint32_t c0 = a.child_off[g], Cs = a.child_off[g + 1] - c0;
+    std::vector<Child> ch;
+    for (uint32_t c = 0; c < Cs; c++) {
+      const uint32_t slot = a.child_slot[c0 + c];
+      Child x;
+      x.reps.assign(a.pool.payload + size_t(slot) * K * wp, a.pool.payload + size_t(slot + 1) * K * wp);
+      x.meta.assign(a.pool.cmeta + size_t(slot) * K, a.pool.cmeta + size_t(slot + 1) * K);
+      x.D.assign(a.pool_dist + size_t(slot) * K * K, a.pool_dist + size_t(slot + 1) * K * K);
+      x.k = a.pool.fill[slot] < K ? a.pool.fill[slot] : K;
+      x.sid = a.child_sid[c0 + c];  x.changed = 0;  x.join[0] = x.join[1] = 0;
+      ch.push_back(std::move(x));
+    }
+    uint32_t nNew = 0, nDone = 0;
+    bool handedBack = false;
+    unsigned long long branching = 0, comparisons = 0;
+    auto scoreOf = [&] (const Child &x, const uint32_t *bw, float4 bm, float *d) {
+      float avg = 0;  uint32_t matable = 0;
+      for (uint32_t r = 0; r < x.k; r++) {
+        const double dd = dist(a.cfg.kind, wp, bw, &x.reps[size_t(r) * wp]);
+        const double ca = compat(a.cfg, bm, dd), cb = compat(a.cfg, x.meta[r], dd), c = cb < ca ? cb : ca;
+        avg += c;  matable += (c >= a.cfg.compat_thr);
+        d[r] = float(dd);
+      }
+      return a.cfg.full_continuous ? float(avg / float(x.k) - a.cfg.avg_thr) : float(matable - a.cfg.sim_thr * x.k);
+    };
+    for (uint32_t t = 0; t < nRej && !handedBack; t++) {
+      const uint32_t ord = a.rej_order[g0 + t], b = ord & ORDER_INDEX_MASK, ccls = ord >> ORDER_CLASS_SHIFT;
+      const uint32_t *bw = a.b_payload + size_t(b) * wp;
+      const float4 bm = a.b_cmeta[b];
+      // visiting order: founded here newest first, then the snapshot list
+      std::vector<uint32_t> visit;
+      for (uint32_t c = uint32_t(ch.size()); c-- > Cs; ) visit.push_back(c);
+      for (uint32_t c = 0; c < Cs; c++) visit.push_back(c);
+      uint32_t j = 0xFFFFFFFFu, vb = 0, vc = 0;
+      float d[KMAX];
+      bool uncertain = false;
+      for (uint32_t c: visit) {
+        vb++;  vc += ch[c].k;
+        const float sc = scoreOf(ch[c], bw, bm, d);
+        if (!a.cfg.use_lut && std::fabs(sc) <= a.guard) { uncertain = true; break; }
+        if (sc > 0) { j = c; break; }
+      }
+      if (uncertain) { handedBack = true; break; }
+      uint32_t act, slot = 0, kOld = 0;
+      if (j == 0xFFFFFFFFu) {
+        if (nNew == a.max_new || ch.size() == a.cap) { handedBack = true; break; }
+        const uint32_t ps = (*a.slot_counter)++;
+        if (ps >= a.slot_limit) { handedBack = true; break; }
+        a.new_slot[size_t(f) * a.max_new + nNew] = a.slot_base + ps;
+        Child x;
+        x.reps.assign(size_t(K) * wp, 0u);  x.meta.assign(K, make_float4(0, 1, 1, 0));  x.D.assign(size_t(K) * K, 0.f);
+        x.k = 0;  x.sid = FAM_NEW_SID | (f * a.max_new + nNew);  x.changed = 0;  x.join[0] = x.join[1] = 0;
+        a.new_founder[size_t(f) * a.max_new + nNew] = b;
+        j = uint32_t(ch.size());
+        ch.push_back(std::move(x));
+        nNew++;
+        act = FAM_FOUNDED;
+      } else {
+        Child &x = ch[j];
+        kOld = x.k;
+        if (x.k < K) { slot = x.k; act = FAM_ENTERED; }
+        else {
+          act = FAM_JOINED;
+          if (K > 1) {
+            float value = -std::numeric_limits<float>::infinity();
+            uint32_t than = 0xFFFFFFFFu;
+            for (uint32_t i = 0; i < K; i++) {
+              double c;
+              if (a.crit == 1) {
+                float minBase = FMAX, minNew = FMAX;
+                for (uint32_t q = 0; q < K; q++) { if (i == q) continue; minBase = std::min(minBase, x.D[i * K + q]); minNew = std::min(minNew, d[q]); }
+                c = - minBase + minNew;
+              } else {
+                c = 0;
+                for (uint32_t q = 0; q < K; q++) { if (i == q) continue; c += - x.D[i * K + q] + d[q]; }
+              }
+              if (value < c) { value = float(c); than = i; }
+            }
+            if (value > 0) { act = FAM_ENTERED | FAM_REPLACED; slot = than; }
+          }
+        }
+      }
+      branching += vb;  comparisons += vc + a.rej_fill[g0 + t];
+      Child &x = ch[j];
+      a.out_sid[b] = x.sid;
+      if ((act & FAM_CODE_MASK) == FAM_JOINED) { x.join[ccls == 2 ? 1 : 0]++; a.fam_act[b] = act | (j << FAM_CHILD_SHIFT); nDone++; continue; }
+      const uint32_t row = (*a.row_counter)++;
+      for (uint32_t r = 0; r < kOld; r++) {
+        a.rows[size_t(row) * K + r] = d[r];
+        if (r != slot) x.D[r * K + slot] = x.D[slot * K + r] = d[r];
+      }
+      memcpy(&x.reps[size_t(slot) * wp], bw, wp * 4);
+      if (a.row_payload) memcpy(a.row_payload + size_t(row) * wp, bw, wp * 4);
+      x.meta[slot] = bm;
+      if (slot == x.k) x.k++;
+      x.changed |= 1u << slot;
+      a.out_slot[b] = int32_t(slot);
+      a.fam_row[b] = row;
+      a.fam_act[b] = act | (slot << FAM_SLOT_SHIFT) | (j << FAM_CHILD_SHIFT);
+      nDone++;
+    }
+    a.fam_info[f] = make_uint4(nDone, nNew, handedBack ? 1u : 0u, uint32_t(ch.size()));
+    a.fam_stats[2 * size_t(f)] = branching;  a.fam_stats[2 * size_t(f) + 1] = comparisons;
+    for (uint32_t c = 0; c < ch.size(); c++) {
+      a.child_join[a.fam_join_off[f] + 2 * c] = ch[c].join[0];  a.child_join[a.fam_join_off[f] + 2 * c + 1] = ch[c].join[1];
+      if (!ch[c].changed) continue;
+      const uint32_t slot = c < Cs ? a.child_slot[c0 + c] : a.new_slot[size_t(f) * a.max_new + (c - Cs)];
+      for (uint32_t r = 0; r < ch[c].k; r++) {
+        if (!((ch[c].changed >> r) & 1u)) continue;
+        memcpy(a.pool_payload_w + (size_t(slot) * K + r) * wp, &ch[c].reps[size_t(r) * wp], wp * 4);
+        a.pool_cmeta_w[size_t(slot) * K + r] = ch[c].meta[r];
+      }
+      memcpy(a.pool_dist + size_t(slot) * K * K, ch[c].D.data(), size_t(K) * K * sizeof(float));
+      a.pool_fill_w[slot] = ch[c].k;
     }
   }
 }

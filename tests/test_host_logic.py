@@ -179,6 +179,50 @@ def test_randomised_traces_against_oracle(hostsim, seed, tmp_path):
     assert tree.to_json() == o.to_json()
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_radiations_resolved_by_the_family_pass(hostsim, seed, tmp_path, monkeypatch):
+    """Adaptive radiations (every child jumps to one of a few niches, generation after generation): all births are
+    rejected at top level and join or found sub-species in order.  The family pass (K3; the stub runs its sequential
+    stand-in with a small capacity, so the hand-back paths are reached too) must reproduce the oracle: species ids,
+    enveloppe entries, callback order, Stats (comparisons / branching of the walks) and the dump -- for whole
+    generations per call, for a few births per call, device-resident births, and with the worker-pool host paths."""
+    rng = np.random.default_rng(7000 + seed)
+    K = int(rng.choice([1, 2, 3, 5, 10]))
+    kind = synth.F32 if seed % 5 == 4 else synth.BITS
+    words = int(rng.choice([4, 8, 16])) if kind == synth.BITS else 16
+    gen = dict(kind=kind, words=words, pop=int(rng.integers(150, 600)), gens=int(rng.integers(5, 9)), seed=seed,
+               hybrid=float(rng.choice([0.0, 0.0, 0.05])), burst_levels=int(rng.integers(2, 5)),
+               burst_fanout=int(rng.choice([3, 10, 40, 120])), compat_classes=int(rng.integers(1, 3)))
+    if kind == synth.BITS:
+        gen.update(flips=float(rng.uniform(0.3, 2.0)), sigma=float(rng.uniform(0.05, 0.12)) * words * 32, burst_bits=max(8, words * 6))
+    else:
+        gen.update(sigma=0.35, noise=0.02, noise_coords=4, burst_scale=1.0)
+    t = synth.generate(**gen)
+    cfg = dict(K=K, full_continuous=bool(seed % 4), env_crit=int(seed % 2))
+    if seed % 3 == 1:
+        monkeypatch.setenv("APT_PAR_MIN", "1")
+        monkeypatch.setenv("APT_HOST_THREADS", "3")
+    path = str(tmp_path / "t.trace")
+    synth.write_trace(path, t)
+    o = oracle.Oracle(t.kind, t.words, **cfg)
+    osid, oent, _ = o.replay(path, n_births=t.n_births)
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, slots = tree.replay(t, to_device=(lambda a: (a, a.ctypes.data, 0)) if seed % 2 else None)
+    assert np.array_equal(sids, osid)
+    assert np.array_equal(slots >= 0, oent > 0)
+    assert tree.stats() == o.stats()
+    assert np.array_equal(tree.events(), o.events())
+    if kind == synth.BITS:
+        assert tree.to_json() == o.to_json()
+    if kind == synth.BITS or cfg["full_continuous"]:      # (vote counting needs the exact table: bit-strings only)
+        assert tree.counters()["family_births"] > 0, "the family pass never ran"
+    # the same trace with the family pass switched off gives the same tree (and is what ran before it existed)
+    from apoget_b200.tree import FLAG_NO_FAMILY_KERNEL
+    ref = hostsim.PhylogeneticTree(t.kind, t.words, flags=FLAG_NO_FAMILY_KERNEL, **cfg)
+    rs, _ = ref.replay(t)
+    assert np.array_equal(rs, osid) and ref.counters()["family_births"] == 0
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "ragged_b96_k3", "c5_speciation_trimming"])
 def test_device_resident_payload_entry_point(hostsim, name):
     """apt_tree_add_genomes_dev (payload rows fetched lazily for the births the host looks at); in the
