@@ -77,6 +77,48 @@ def test_tree_compat_table_overflow(name, cap, monkeypatch):
     _compare(name, device_scores=not name.startswith("semi"))
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_radiations_resolved_by_the_family_kernel(seed, tmp_path):
+    """Adaptive radiations: every birth is rejected at top level and joins or founds a sub-species, in order
+    (findBestDerived :493-548, insertInto :657-726, makeNode :398-426).  resolve_families_kernel must reproduce the oracle
+    bit for bit -- species ids, enveloppe entries, callback order, Stats and the dump."""
+    from apoget_b200.tree import PhylogeneticTree
+    rng = np.random.default_rng(7000 + seed)
+    K = int(rng.choice([1, 3, 5, 10]))
+    kind = synth.F32 if seed % 5 == 4 else synth.BITS
+    words = int(rng.choice([4, 8, 16, 128])) if kind == synth.BITS else 64
+    gen = dict(kind=kind, words=words, pop=int(rng.integers(300, 3000)), gens=int(rng.integers(5, 8)), seed=seed,
+               hybrid=float(rng.choice([0.0, 0.0, 0.05])), burst_levels=int(rng.integers(2, 5)),
+               burst_fanout=int(rng.choice([3, 10, 40, 300])), compat_classes=int(rng.integers(1, 3)))
+    if kind == synth.BITS:
+        gen.update(flips=float(rng.uniform(0.3, 2.0)), sigma=float(rng.uniform(0.05, 0.12)) * words * 32, burst_bits=max(8, words * 6))
+    else:
+        gen.update(sigma=0.35, noise=0.02, noise_coords=4, burst_scale=1.0)
+    t = synth.generate(**gen)
+    cfg = dict(K=K, full_continuous=bool(seed % 4) or kind == synth.F32, env_crit=int(seed % 2))
+    path = str(tmp_path / "t.trace")
+    synth.write_trace(path, t)
+    o = oracle.Oracle(t.kind, t.words, **cfg)
+    osid, oent, _ = o.replay(path, n_births=t.n_births)
+    tree = PhylogeneticTree(t.kind, t.words, **cfg)
+    to_dev = None
+    if seed % 2:
+        import torch
+        def to_dev(a):
+            d = torch.from_numpy(a.view(np.int32)).cuda()
+            return d, d.data_ptr(), torch.cuda.current_stream().cuda_stream
+    sids, slots = tree.replay(t, to_device=to_dev)
+    assert np.array_equal(sids, osid), "per-birth species ids"
+    assert np.array_equal(slots >= 0, oent > 0), "enveloppe entries"
+    assert tree.stats() == o.stats()
+    assert np.array_equal(tree.events(), o.events()), "callback stream"
+    if kind == synth.BITS:
+        assert tree.to_json() == o.to_json()
+    else:
+        _json_close(tree.to_json(), o.to_json(), F32_RTOL)
+    assert tree.counters()["family_births"] > 0, "the family kernel never ran"
+
+
 def _random_pool(rng, kind, words, S, K, sigma):
     if kind == synth.BITS:
         base = rng.integers(0, 2**32, size=(S, 1, words), dtype=np.uint32)
