@@ -135,6 +135,8 @@ Engine::Engine (const apt_params &p) : p_(p) {
   cudaCheck(cudaEventCreate(&evK1_), "cudaEventCreate");
   cudaCheck(cudaEventCreate(&evS0_), "cudaEventCreate");
   cudaCheck(cudaEventCreate(&evS1_), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&evF0_), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&evF1_), "cudaEventCreate");
   // the device resolves streams for the default criteria; vote-count scoring needs the exact table
   // (a flipped vote cannot be seen from the score, so no guard band protects it)
   childKernel_ = !(p.flags & APT_FLAG_NO_CHILD_KERNEL);
@@ -168,6 +170,8 @@ Engine::~Engine (void) {
   if (evK1_) cudaEventDestroy(evK1_);
   if (evS0_) cudaEventDestroy(evS0_);
   if (evS1_) cudaEventDestroy(evS1_);
+  if (evF0_) cudaEventDestroy(evF0_);
+  if (evF1_) cudaEventDestroy(evF1_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -1534,7 +1538,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       hChildOff_.p[g] = uint32_t(nChild);
       Species *S = grpSpecies_[g];
       const auto &ch = S->children;
-      bool ok = famOk_ && S->pair_epoch != chunkEpoch_ && S->first < step_ && ch.size() + 8 <= famCap_
+      bool ok = famOk_ && S->pair_epoch != chunkEpoch_ && S->first < step_ && ch.size() + 4 <= famCap_
                 && (!S->parent || (S->parent->grp_epoch != chunkEpoch_ && S->parent->pair_epoch != chunkEpoch_));
       for (size_t idx = ch.size(); idx-- > 0; ) {
         const Species *c = ch[idx];
@@ -1553,6 +1557,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (!fams_.empty()) {
       // species a family may found before it hands the rest of its births back; the counters of family f start at joinOff_f
       famMaxNew_ = std::min<uint32_t>(famCap_ - maxSnap, std::max<uint32_t>(16u, std::min<uint32_t>(256u, uint32_t(65536 / fams_.size()))));
+      famMaxNew_ = std::max<uint32_t>(famMaxNew_, 1u);
       for (Family &F: fams_) { F.joinOff = joinOff; joinOff += 2 * (F.snapN + famMaxNew_); }
     }
   } else { fams_.clear(); grpFam_.assign(G, -1); }
@@ -1686,7 +1691,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       // K3: the rejected births of every eligible family walk its sub-species on the device, in order, founding included
       // (family.cu).  Species founded there take consecutive pool slots behind the ones in use; the host makes them
       // real when it commits the founding births.
-      const uint32_t reserve = uint32_t(std::min<size_t>(nStream, size_t(1) << 16));
+      const uint32_t reserve = famReserve(nStream);
       famSlotBase_ = nSlots_;
       const size_t slots = size_t(nSlots_) + reserve;
       dPool_.reserve(slots * K_ * wp_, true, stream_);  dMeta_.reserve(slots * K_, true, stream_);
@@ -1722,12 +1727,14 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       fa.max_new = famMaxNew_;
       uint32_t maxSnap = 0;
       for (const Family &F: fams_) maxSnap = std::max(maxSnap, F.snapN);
-      fa.cap = std::min<uint32_t>(famCap_, (maxSnap + famMaxNew_ + 31u) & ~31u);
+      fa.cap = std::min<uint32_t>(famCap_, (maxSnap + famMaxNew_ + 3u) & ~3u);
       fa.fam_act = dFamAct_.p;  fa.fam_row = dFamRow_.p;  fa.out_sid = dOutSid;  fa.out_slot = dOutSlot;
       fa.rows = dRows_.p;  fa.row_payload = a.row_payload;  fa.row_counter = dCtr_.p;
       fa.fam_info = dFamInfo_.p;  fa.fam_stats = dFamStats_.p;  fa.child_join = dChildJoin_.p;
       fa.new_founder = dNewFounder_.p;  fa.new_slot = dNewFounder_.p + size_t(nFam) * famMaxNew_;
+      cudaCheck(cudaEventRecord(evF0_, stream_), "event record");
       launch_resolve_families(fa, stream_);
+      cudaCheck(cudaEventRecord(evF1_, stream_), "event record");
       counters[4]++;
       cudaCheck(cudaGetLastError(), "resolve_families launch");
       hFamInfo_.reserve(nFam);
@@ -1791,6 +1798,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (P) { cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed"); timers[4] += ms; }
     if (G) {
       cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
+      if (!fams_.empty()) { float fm = 0.f; cudaCheck(cudaEventElapsedTime(&fm, evF0_, evF1_), "event elapsed"); timers[6] += fm; }
       if (const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str()) {
         // development aid: one text line per stream {launch, stream, births, kernel ms, 10 timeline words}, appended
         std::vector<unsigned long long> hp (size_t(G) * 16);
@@ -1855,7 +1863,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       if (nRows > specRows || nFt_ || nFtRows_ > specFt || famResults_) cudaCheck(cudaStreamSynchronize(stream_), "rows");
       if (famResults_) {
-        famSlotsUsed_ = std::min<uint32_t>(hCtr_.p[2], uint32_t(std::min<size_t>(nStream, size_t(1) << 16)));
+        famSlotsUsed_ = std::min<uint32_t>(hCtr_.p[2], famReserve(nStream));
         if (famSlotsUsed_) {
           // the species founded on the device live in pool slots [famSlotBase_, +used): they become real now
           nSlots_ = famSlotBase_ + famSlotsUsed_;
@@ -2274,7 +2282,8 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
                outReplaced ? outReplaced + i0 : nullptr, done);
       i0 += m;
       const uint64_t hostScores = counters[3] - hostScores0;
-      if (hostScores > m && m > CHUNK_MIN) adaptChunk_ = std::max(CHUNK_MIN, m / 2);
+      if (hostScores > 8 * uint64_t(m) && m > CHUNK_MIN) adaptChunk_ = std::max(CHUNK_MIN, m / 16);
+      else if (hostScores > m && m > CHUNK_MIN) adaptChunk_ = std::max(CHUNK_MIN, m / 2);
       else if (hostScores < m / 8 && m == adaptChunk_) adaptChunk_ = std::min(CHUNK_MAX, adaptChunk_ * 2);
     }
   } catch (...) {

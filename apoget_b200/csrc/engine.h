@@ -325,13 +325,15 @@ private:
   PinBuf<uint4> hFamInfo_;  PinBuf<unsigned long long> hFamStats_;
   void walkFamily (uint32_t i, const uint32_t *w, RepMeta &g, Species *s0, uint32_t fact, uint32_t &sid, int32_t &slot, uint32_t &replaced);
   void settleFamilies (void);
+  /// pool slots kept ready behind the ones in use for species the family pass founds in one device pass
+  static uint32_t famReserve (size_t nStream) { return uint32_t(std::min<size_t>(nStream / 4 + 1024, size_t(1) << 16)); }
   void bulkContribution (Species *c, Species *from, uint32_t n1, uint32_t n2);
   uint32_t chunkEpoch_ = 0;
   bool chunkUniform_ = false;             // every birth of the chunk carries the same compatibility triple
   const float4 *fillPtr_ = nullptr;  uint32_t fillN_ = 0;  float4 fillValue_ {};   // what the births' device meta array was last filled with (uniform chunks)
   uint32_t chunkCls_ = 0;
   bool streamOk_ = false;                 // the stream kernel can serve this tree's configuration
-  cudaEvent_t evS0_ = nullptr, evS1_ = nullptr;
+  cudaEvent_t evS0_ = nullptr, evS1_ = nullptr, evF0_ = nullptr, evF1_ = nullptr;
   static constexpr uint32_t CHUNK_MIN = 1024, CHUNK_MAX = 1u << 20;
   uint32_t adaptChunk_ = 4096;          // births per device pass, adapted to how much of the last pass fell back to the host
   double profWalk_[3] = {0, 0, 0};  uint64_t profWalkN_[3] = {0, 0, 0};   // APT_PROFILE: serial commit by category

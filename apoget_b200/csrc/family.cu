@@ -444,8 +444,8 @@ uint32_t family_capacity (uint32_t wp, uint32_t K, const ScoreCfg &cfg) {
   const uint32_t wq = wp >> 2;
   const size_t budget = (size_t(200) << 10) - fam_lut_bytes(cfg);
   uint32_t cap = 1024;
-  while (cap >= 32 && fam_child_bytes(K, wq) * cap + fam_fixed_bytes(K, cap) > budget) cap -= 32;
-  return cap >= 32 ? cap : 0u;
+  while (cap >= 12 && fam_child_bytes(K, wq) * cap + fam_fixed_bytes(K, cap) > budget) cap -= 4;
+  return cap >= 12 ? cap : 0u;           // (4096-bit genomes, K = 10: 28 sub-species)
 }
 
 void launch_resolve_families (const FamilyArgs &a, cudaStream_t st) {
