@@ -150,6 +150,10 @@ resolve_families_kernel (FamilyArgs a) {
 
   const uint32_t g0 = a.grp_off[g];
   const uint32_t nRej = a.rej_count[g];
+  if (nRej == 0) {                        // nothing was rejected: the usual case outside radiations
+    if (threadIdx.x == 0) { a.fam_info[f] = make_uint4(0u, 0u, 0u, 0u); a.fam_stats[2 * size_t(f)] = 0ull; a.fam_stats[2 * size_t(f) + 1] = 0ull; }
+    return;
+  }
   const uint32_t c0 = a.child_off[g], Cs = a.child_off[g + 1] - c0;     // sub-species at submission (host: Cs < cap)
   const uint4 *birthRows = reinterpret_cast<const uint4*>(a.b_payload);
 

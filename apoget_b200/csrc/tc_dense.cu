@@ -27,6 +27,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace apt {
@@ -72,6 +73,34 @@ __device__ __forceinline__ void tc_mma_i8 (uint32_t d_tmem, uint64_t a_desc, uin
                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
                :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- CTA pair (cta_group::2): the two SMs of a TPC multiply one 256 x 256 tile, each holding half of either operand ----
+__device__ __forceinline__ uint32_t cluster_rank (void) { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all (void) {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+/// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote (uint32_t bar, uint32_t rank) {
+  asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" :: "r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster (uint32_t bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAITC_%=:\n"
+               "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra DONEC_%=;\nbra WAITC_%=;\nDONEC_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+/// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair (uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               :: "r"(bar), "h"(uint16_t(3)) : "memory");
+}
+/// D[tmem of both CTAs] (+)= A . B^T, M = 256 (128 rows per CTA), N = 256 (128 rows of B in either CTA's shared memory), K = 32
+__device__ __forceinline__ void tc_mma_i8_pair (uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+               :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t TC_IDESC_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
 /// K-major operand without swizzle: core matrices (8 rows x 16 B, rows 16 B apart) 128 B apart along K
 /// (leading byte offset) and 1 KB apart along M/N (stride byte offset); descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t tc_smem_desc (uint32_t saddr) {
@@ -151,25 +180,32 @@ struct TcArgs {
 
 namespace {
 
-template <int KT, bool CONT>
+/// CG = 1: one CTA per 128-birth tile.  CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 births -- either
+/// CTA stages its own 128 births and HALF of the representative tile, the leader issues M = 256 MMAs that read both shared
+/// memories: a third less shared-memory and L2 traffic per MAC (32 KB instead of 48 KB per CTA and K block).
+template <int KT, bool CONT, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 classify_dense_tc_kernel (TcArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t K = KT ? uint32_t(KT) : a.K;
   const uint32_t S = uint32_t(a.stages);
-  // [stages x (A 16 KB | B 32 KB)][table][winner exchange 4 x 32 x 16 B][barriers][tmem base]
+  constexpr uint32_t B_PART = B_STAGE / CG, STG = A_STAGE + B_PART;      // this CTA's share of a stage
+  const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+  const uint32_t firstTile = (blockIdx.x / CG) * CG + rank, tileStep = gridDim.x;
+  // [stages x (A 16 KB | B 32 or 16 KB)][table][winner exchange 4 x 32 x 16 B][barriers][tmem base]
   unsigned char *stage0 = tc_smem;
   const uint32_t lutBytes = a.lut_in_smem ? ((a.cfg.lut_classes * a.cfg.lut_stride * 8u + 15u) & ~15u) : 0u;
-  double *lut_s = reinterpret_cast<double*>(tc_smem + size_t(S) * STAGE);
-  Winners *xw = reinterpret_cast<Winners*>(tc_smem + size_t(S) * STAGE + lutBytes);
+  double *lut_s = reinterpret_cast<double*>(tc_smem + size_t(S) * STG);
+  Winners *xw = reinterpret_cast<Winners*>(tc_smem + size_t(S) * STG + lutBytes);
   uint64_t *bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(xw) + 4 * 32 * sizeof(Winners));
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * 8 + 4);
-  const uint32_t barFull = smem_u32(bars), barEmpty = smem_u32(bars + 8), barTFull = smem_u32(bars + 16), barTEmpty = smem_u32(bars + 18);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * 8 + 4);
+  const uint32_t barFull = smem_u32(bars), barEmpty = smem_u32(bars + 8), barPeer = smem_u32(bars + 16),
+                 barTFull = smem_u32(bars + 24), barTEmpty = smem_u32(bars + 26);
 
   if (tid == 0) {
-    for (uint32_t s = 0; s < S; s++) { mbar_init(barFull + 8 * s, 1); mbar_init(barEmpty + 8 * s, 1); }
-    for (uint32_t b = 0; b < 2; b++) { mbar_init(barTFull + 8 * b, 1); mbar_init(barTEmpty + 8 * b, EPI_WARPS); }
+    for (uint32_t s = 0; s < S; s++) { mbar_init(barFull + 8 * s, 1); mbar_init(barEmpty + 8 * s, 1); mbar_init(barPeer + 8 * s, 1); }
+    for (uint32_t b = 0; b < 2; b++) { mbar_init(barTFull + 8 * b, 1); mbar_init(barTEmpty + 8 * b, EPI_WARPS * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (a.lut_in_smem) {
@@ -177,11 +213,17 @@ classify_dense_tc_kernel (TcArgs a) {
     for (uint32_t i = tid; i < nd; i += TC_THREADS) lut_s[i] = __ldg(a.cfg.lut + i);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t nkb = a.nkb;
@@ -190,40 +232,55 @@ classify_dense_tc_kernel (TcArgs a) {
     // ===== producer: one bulk copy per operand and stage =====
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (uint32_t mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x)
+      for (uint32_t mt = firstTile; mt < a.m_tiles; mt += tileStep)
         for (uint32_t nt = 0; nt < a.n_tiles; nt++)
           for (uint32_t kb = 0; kb < nkb; kb++) {
             mbar_wait(barEmpty + 8 * s, ph ^ 1u);
-            mbar_expect_tx(barFull + 8 * s, STAGE);
-            const uint32_t dst = smem_u32(stage0 + size_t(s) * STAGE);
+            mbar_expect_tx(barFull + 8 * s, STG);
+            const uint32_t dst = smem_u32(stage0 + size_t(s) * STG);
             bulk_g2s(dst, a.a_img + (size_t(mt) * nkb + kb) * A_STAGE, A_STAGE, barFull + 8 * s);
-            bulk_g2s(dst + A_STAGE, a.b_img + (size_t(nt) * nkb + kb) * B_STAGE, B_STAGE, barFull + 8 * s);
+            bulk_g2s(dst + A_STAGE, a.b_img + (size_t(nt) * nkb + kb) * B_STAGE + size_t(rank) * B_PART, B_PART, barFull + 8 * s);
             if (++s == S) { s = 0; ph ^= 1u; }
           }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread =====
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t s = 0, ph = 0, it = 0;
-      for (uint32_t mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x)
+      for (uint32_t mt = firstTile; mt < a.m_tiles; mt += tileStep)
         for (uint32_t nt = 0; nt < a.n_tiles; nt++, it++) {
           const uint32_t buf = it & 1u;
-          mbar_wait(barTEmpty + 8 * buf, ((it >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+          // the epilogue (of both CTAs) has drained this accumulator
+          if (CG == 2) mbar_wait_cluster(barTEmpty + 8 * buf, ((it >> 1) & 1u) ^ 1u); else mbar_wait(barTEmpty + 8 * buf, ((it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem + buf * TN;
           for (uint32_t kb = 0; kb < nkb; kb++) {
             mbar_wait(barFull + 8 * s, ph);
+            if (CG == 2) mbar_wait_cluster(barPeer + 8 * s, ph);              // ... and the peer's half of the stage has landed
             tc_fence_after();
-            const uint32_t sa = smem_u32(stage0 + size_t(s) * STAGE);
+            const uint32_t sa = smem_u32(stage0 + size_t(s) * STG);
             const uint64_t da = tc_smem_desc(sa), db = tc_smem_desc(sa + A_STAGE);
 #pragma unroll
-            for (uint32_t k = 0; k < KBYTES / UMMA_K; k++)      // two core matrices (256 B) further along K per step
-              tc_mma_i8(d_tmem, da + uint64_t(k * 16u), db + uint64_t(k * 16u), TC_IDESC, (kb | k) != 0u);
-            tc_commit(barEmpty + 8 * s);                          // stage free once these MMAs have read it
+            for (uint32_t k = 0; k < KBYTES / UMMA_K; k++) {    // two core matrices (256 B) further along K per step
+              if (CG == 2) tc_mma_i8_pair(d_tmem, da + uint64_t(k * 16u), db + uint64_t(k * 16u), TC_IDESC_PAIR, (kb | k) != 0u);
+              else tc_mma_i8(d_tmem, da + uint64_t(k * 16u), db + uint64_t(k * 16u), TC_IDESC, (kb | k) != 0u);
+            }
+            // stage free (in both CTAs) once these MMAs have read it
+            if (CG == 2) tc_commit_pair(barEmpty + 8 * s); else tc_commit(barEmpty + 8 * s);
             if (++s == S) { s = 0; ph ^= 1u; }
           }
-          tc_commit(barTFull + 8 * buf);                          // accumulator complete
+          if (CG == 2) tc_commit_pair(barTFull + 8 * buf); else tc_commit(barTFull + 8 * buf);      // accumulator complete
         }
+    } else if (CG == 2 && lane == 0) {
+      // the peer: tells the leader when ITS half of every stage has landed (bulk copies complete on local barriers only)
+      uint32_t s = 0, ph = 0;
+      for (uint32_t mt = firstTile; mt < a.m_tiles; mt += tileStep)
+        for (uint32_t nt = 0; nt < a.n_tiles; nt++)
+          for (uint32_t kb = 0; kb < nkb; kb++) {
+            mbar_wait(barFull + 8 * s, ph);
+            mbar_arrive_remote(barPeer + 8 * s, 0u);
+            if (++s == S) { s = 0; ph ^= 1u; }
+          }
     }
   } else {
     // ===== epilogue: thread = birth (TMEM lane); the two warps of a lane quarter take alternate species pairs =====
@@ -233,7 +290,7 @@ classify_dense_tc_kernel (TcArgs a) {
     const double *lutAny = a.lut_in_smem ? lut_s : a.cfg.lut;
     const int L = int(a.lbits);
     uint32_t it = 0;
-    for (uint32_t mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+    for (uint32_t mt = firstTile; mt < a.m_tiles; mt += tileStep) {
       const uint32_t b = mt * TM + row;
       const bool live = b < a.n_births;
       const float4 bm = live ? __ldg(a.b_cmeta + b) : make_float4(0.f, 1.f, 1.f, 0.f);
@@ -330,7 +387,7 @@ classify_dense_tc_kernel (TcArgs a) {
         // accumulator drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(barTEmpty + 8 * buf);
+        if (lane == 0) { if (CG == 2) mbar_arrive_remote(barTEmpty + 8 * buf, 0u); else mbar_arrive(barTEmpty + 8 * buf); }
       }
       // ---- the two halves of every birth's species are merged and the winners leave the chip ----
       if (h == 1) xw[q * 32 + lane] = win;
@@ -355,9 +412,11 @@ classify_dense_tc_kernel (TcArgs a) {
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its tensor memory
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -442,7 +501,7 @@ uint32_t tc_nkb (uint32_t wp) { return (wp * 32u + KBYTES - 1) / KBYTES; }
 uint32_t tc_spc (uint32_t K) { return TN / K; }
 uint32_t tc_pool_tiles (uint32_t n_species, uint32_t K) { const uint32_t spc = tc_spc(K); return (n_species + spc - 1) / spc; }
 size_t tc_pool_image_bytes (uint32_t n_species, uint32_t K, uint32_t wp) { return size_t(tc_pool_tiles(n_species, K)) * tc_nkb(wp) * B_STAGE; }
-size_t tc_births_image_bytes (uint32_t n_births, uint32_t wp) { return size_t((n_births + TM - 1) / TM) * tc_nkb(wp) * A_STAGE; }
+size_t tc_births_image_bytes (uint32_t n_births, uint32_t wp) { return size_t(((n_births + TM - 1) / TM + 1) & ~1u) * tc_nkb(wp) * A_STAGE; }
 size_t tc_pool_meta_bytes (uint32_t n_species, uint32_t K) { return size_t(tc_pool_tiles(n_species, K)) * TC_META_WORDS * 4; }
 
 void launch_tc_expand_pool (const PoolView &pool, uint8_t *img, uint32_t *meta, cudaStream_t st) {
@@ -456,7 +515,7 @@ void launch_tc_expand_pool (const PoolView &pool, uint8_t *img, uint32_t *meta, 
 
 void launch_tc_expand_births (const uint32_t *b_payload, uint32_t n_births, uint32_t wp, uint8_t *img, cudaStream_t st) {
   const uint32_t nkb = tc_nkb(wp);
-  const uint64_t rows = uint64_t((n_births + TM - 1) / TM) * TM, threads = rows / 8 * nkb * 64;
+  const uint64_t rows = uint64_t(((n_births + TM - 1) / TM + 1) & ~1u) * TM, threads = rows / 8 * nkb * 64;     // (an even number of tiles: CTA pairs)
   if (!threads) return;
   tc_expand_kernel<<<unsigned((threads + 255) / 256), 256, 0, st>>>(b_payload, n_births, wp, nkb, TM, 1, 0, nullptr, uint32_t(rows), img);
 }
@@ -477,26 +536,39 @@ void launch_classify_dense_tc (const PoolView &pool, const ScoreCfg &cfg, const 
   a.out_matrix = out_matrix;
   a.sink = sink ? *sink : ShardSink{};
   a.rec_stride = rec_stride ? rec_stride : n_births;  a.rec_offset = rec_offset;
-  // shared memory: as many 48 KB stages as fit next to the table (4 without it, 3-4 with it)
-  const size_t fixed = 4 * 32 * sizeof(Winners) + (2 * 8 + 4) * 8 + 16;
+  // CTA pairs (cta_group::2) unless asked otherwise (APT_TC_CG=1) or there is a single birth tile
+  const char *cgEnv = getenv("APT_TC_CG");
+  const int CGv = (cgEnv && cgEnv[0] == '1') || a.m_tiles < 2 ? 1 : 2;
+  // shared memory: as many stages (48 KB; 32 KB per CTA of a pair) as fit next to the table
+  const size_t stg = A_STAGE + B_STAGE / CGv;
+  const size_t fixed = 4 * 32 * sizeof(Winners) + (3 * 8 + 4) * 8 + 16;
   const size_t lutBytes = (size_t(cfg.lut_classes) * cfg.lut_stride * 8 + 15) & ~size_t(15);
   const size_t cap = size_t(227) << 10;
-  a.lut_in_smem = cfg.use_lut && lutBytes > 0 && 3 * size_t(STAGE) + lutBytes + fixed <= cap;
+  a.lut_in_smem = cfg.use_lut && lutBytes > 0 && 3 * stg + lutBytes + fixed <= cap;
   size_t avail = cap - fixed - (a.lut_in_smem ? lutBytes : 0);
-  a.stages = int(std::min<size_t>(4, avail / STAGE));
-  const size_t smem = size_t(a.stages) * STAGE + (a.lut_in_smem ? lutBytes : 0) + fixed;
+  a.stages = int(std::min<size_t>(8, avail / stg));
+  const size_t smem = size_t(a.stages) * stg + (a.lut_in_smem ? lutBytes : 0) + fixed;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t grid = std::min<uint32_t>(a.m_tiles, uint32_t(sms));
+  // with pairs the births' image holds an even number of tiles (launch_tc_expand_births pads): either CTA has its own
+  if (CGv == 2) a.m_tiles = (a.m_tiles + 1u) & ~1u;
+  const uint32_t grid = CGv == 2 ? 2u * std::min<uint32_t>(a.m_tiles / 2u, uint32_t(sms) / 2u) : std::min<uint32_t>(a.m_tiles, uint32_t(sms));
   auto go = [&] (auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kernel<<<grid, TC_THREADS, smem, stream>>>(a);
+    cudaLaunchConfig_t lc {};
+    lc.gridDim = dim3(grid);  lc.blockDim = dim3(TC_THREADS);  lc.dynamicSmemBytes = smem;  lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = unsigned(CGv);  at[0].val.clusterDim.y = 1;  at[0].val.clusterDim.z = 1;
+    lc.attrs = at;  lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, kernel, a);
   };
   const bool cont = cfg.full_continuous != 0;
   auto pick = [&] (auto kt) {
     constexpr int KT = decltype(kt)::value;
-    if (cont) go(classify_dense_tc_kernel<KT, true>); else go(classify_dense_tc_kernel<KT, false>);
+    if (CGv == 2) { if (cont) go(classify_dense_tc_kernel<KT, true, 2>); else go(classify_dense_tc_kernel<KT, false, 2>); }
+    else { if (cont) go(classify_dense_tc_kernel<KT, true, 1>); else go(classify_dense_tc_kernel<KT, false, 1>); }
   };
   if (pool.K == 10) pick(std::integral_constant<int, 10>{});
   else if (pool.K == 5) pick(std::integral_constant<int, 5>{});
