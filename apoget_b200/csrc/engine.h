@@ -53,8 +53,10 @@ struct DevBuf {
   ~DevBuf (void) { if (p) cudaFree(p); }
   void reserve (size_t n, bool keep = false, cudaStream_t st = nullptr) {
     if (n <= cap) return;
-    size_t ncap = cap ? cap : 1024;
-    while (ncap < n) ncap *= 2;
+    // few, generous steps: every growth is a cudaMalloc + cudaFree (a device-wide synchronisation each; measured at 5-30 ms
+    // apiece inside a speciating run, 300 of them over seven generations when buffers doubled from 1 024 elements)
+    size_t ncap = cap ? cap : (size_t(1) << 16);
+    while (ncap < n) ncap *= 4;
     T *q = nullptr;
     const double t0 = allocClock();
     cudaCheck(cudaMalloc(&q, ncap * sizeof(T)), "cudaMalloc");
@@ -80,8 +82,8 @@ struct PinBuf {
     if (n <= cap) return;
     // at least 25 % of headroom: page-locking is slow (1.5 ms per call in a process that sees several GPUs) and
     // result sizes creep up from step to step
-    size_t ncap = cap ? cap : 1024;
-    while (ncap < n + n / 4) ncap *= 2;
+    size_t ncap = cap ? cap : (size_t(1) << 14);
+    while (ncap < n + n / 4) ncap *= 4;
     T *q = nullptr;
     const double t0 = allocClock();
     cudaCheck(cudaMallocHost(&q, ncap * sizeof(T)), "cudaMallocHost");

@@ -83,11 +83,6 @@ __device__ __forceinline__ void mbar_arrive_remote (uint32_t bar, uint32_t rank)
   asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
                "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" :: "r"(bar), "r"(rank) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster (uint32_t bar, uint32_t parity) {
-  asm volatile("{\n.reg .pred p;\nWAITC_%=:\n"
-               "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-               "@p bra DONEC_%=;\nbra WAITC_%=;\nDONEC_%=:\n}\n" :: "r"(bar), "r"(parity) : "memory");
-}
 /// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit_pair (uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
@@ -251,12 +246,12 @@ classify_dense_tc_kernel (TcArgs a) {
         for (uint32_t nt = 0; nt < a.n_tiles; nt++, it++) {
           const uint32_t buf = it & 1u;
           // the epilogue (of both CTAs) has drained this accumulator
-          if (CG == 2) mbar_wait_cluster(barTEmpty + 8 * buf, ((it >> 1) & 1u) ^ 1u); else mbar_wait(barTEmpty + 8 * buf, ((it >> 1) & 1u) ^ 1u);
+          mbar_wait(barTEmpty + 8 * buf, ((it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem + buf * TN;
           for (uint32_t kb = 0; kb < nkb; kb++) {
             mbar_wait(barFull + 8 * s, ph);
-            if (CG == 2) mbar_wait_cluster(barPeer + 8 * s, ph);              // ... and the peer's half of the stage has landed
+            if (CG == 2) mbar_wait(barPeer + 8 * s, ph);                      // ... and the peer's half of the stage has landed
             tc_fence_after();
             const uint32_t sa = smem_u32(stage0 + size_t(s) * STG);
             const uint64_t da = tc_smem_desc(sa), db = tc_smem_desc(sa + A_STAGE);
