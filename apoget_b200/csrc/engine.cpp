@@ -1618,6 +1618,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   bool ftRows = false;
   uint32_t specRows = 0, specFt = 0;        // rows / rejected births fetched ahead of knowing their number
   bool directOut = false;
+  std::function<void(void)> launchFamilies;     // K3 is only launched once the pass is known to have rejected births (below)
   if (G) {
     // the ordered resolution of the single-parent births, one warp per species stream; it runs
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
@@ -1687,7 +1688,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       counters[4]++;
       cudaCheck(cudaGetLastError(), "classify_children launch");
     }
-    if (nFam) {
+    if (nFam) launchFamilies = [&, nFam, dGrpOff, dOutSid, dOutSlot, famRowPayload = a.row_payload] (void) {
       // K3: the rejected births of every eligible family walk its sub-species on the device, in order, founding included
       // (family.cu).  Species founded there take consecutive pool slots behind the ones in use; the host makes them
       // real when it commits the founding births.
@@ -1729,7 +1730,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       for (const Family &F: fams_) maxSnap = std::max(maxSnap, F.snapN);
       fa.cap = std::min<uint32_t>(famCap_, (maxSnap + famMaxNew_ + 3u) & ~3u);
       fa.fam_act = dFamAct_.p;  fa.fam_row = dFamRow_.p;  fa.out_sid = dOutSid;  fa.out_slot = dOutSlot;
-      fa.rows = dRows_.p;  fa.row_payload = a.row_payload;  fa.row_counter = dCtr_.p;
+      fa.rows = dRows_.p;  fa.row_payload = famRowPayload;  fa.row_counter = dCtr_.p;
       fa.fam_info = dFamInfo_.p;  fa.fam_stats = dFamStats_.p;  fa.child_join = dChildJoin_.p;
       fa.new_founder = dNewFounder_.p;  fa.new_slot = dNewFounder_.p + size_t(nFam) * famMaxNew_;
       cudaCheck(cudaEventRecord(evF0_, stream_), "event record");
@@ -1739,7 +1740,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       cudaCheck(cudaGetLastError(), "resolve_families launch");
       hFamInfo_.reserve(nFam);
       cudaCheck(cudaMemcpyAsync(hFamInfo_.p, dFamInfo_.p, size_t(nFam) * sizeof(uint4), cudaMemcpyDeviceToHost, stream_), "family info");
-    }
+    };
     if (!payload && useChildKernel) {
       // device-resident births: the host will want the genomes of the births the streams rejected (it walks the
       // sub-species for them); they are gathered from the device-side list right away, so that they come back
@@ -1798,7 +1799,6 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (P) { cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed"); timers[4] += ms; }
     if (G) {
       cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
-      if (!fams_.empty()) { float fm = 0.f; cudaCheck(cudaEventElapsedTime(&fm, evF0_, evF1_), "event elapsed"); timers[6] += fm; }
       if (const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str()) {
         // development aid: one text line per stream {launch, stream, births, kernel ms, 10 timeline words}, appended
         std::vector<unsigned long long> hp (size_t(G) * 16);
@@ -1812,6 +1812,21 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           fclose(f);
         }
       }
+      // The family pass runs only when the streams rejected a fair share of their births (a radiation): a steady pass does
+      // not pay for it.  It appends its rows behind the streams' and is awaited here.
+      if (launchFamilies && hCtr_.p[1] >= std::max<uint32_t>(32u, n / 64u)) {
+        launchFamilies();
+        cudaCheck(cudaMemcpyAsync(hCtr_.p, dCtr_.p, 8, cudaMemcpyDeviceToHost, stream_), "counters");
+        // (the species ids / slots of the births it decided: fetched again)
+        cudaCheck(cudaMemcpyAsync(directOut ? outSid : hOutSid_.p, dOut2_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
+        cudaCheck(cudaMemcpyAsync(directOut ? reinterpret_cast<uint32_t*>(outSlot) : reinterpret_cast<uint32_t*>(hOutSlot_.p), dOut2_.p + n,
+                                  size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "slots");
+        cudaCheck(cudaStreamSynchronize(stream_), "family pass");
+        float fm = 0.f;
+        cudaCheck(cudaEventElapsedTime(&fm, evF0_, evF1_), "event elapsed");
+        timers[6] += fm;
+        specRows = 0;               // rows fetched ahead of the family pass do not hold its entries yet: fetched again below
+      } else fams_.clear();
       nRows = hCtr_.p[0];
       nFt_ = (useChildKernel && nChild) ? hCtr_.p[1] : 0u;
       if (nRows > specRows) {

@@ -531,9 +531,11 @@ void launch_classify_dense_tc (const PoolView &pool, const ScoreCfg &cfg, const 
   a.out_matrix = out_matrix;
   a.sink = sink ? *sink : ShardSink{};
   a.rec_stride = rec_stride ? rec_stride : n_births;  a.rec_offset = rec_offset;
-  // CTA pairs (cta_group::2) unless asked otherwise (APT_TC_CG=1) or there is a single birth tile
+  // One CTA per birth tile by default.  CTA pairs (tcgen05 cta_group::2, APT_TC_CG=2) stage a third less per CTA but measured
+  // 6-12 % SLOWER on B200 (131 072 x 100 000 x 4096 bits: 72 vs 63-68 ms): bulk copies complete on barriers of their own
+  // CTA only, so the peer's half of every stage is announced to the leader by a relay thread, one more hop per stage.
   const char *cgEnv = getenv("APT_TC_CG");
-  const int CGv = (cgEnv && cgEnv[0] == '1') || a.m_tiles < 2 ? 1 : 2;
+  const int CGv = (cgEnv && cgEnv[0] == '2' && a.m_tiles >= 2) ? 2 : 1;
   // shared memory: as many stages (48 KB; 32 KB per CTA of a pair) as fit next to the table
   const size_t stg = A_STAGE + B_STAGE / CGv;
   const size_t fixed = 4 * 32 * sizeof(Winners) + (3 * 8 + 4) * 8 + 16;
