@@ -989,7 +989,8 @@ void Engine::bulkContribution (Species *c, Species *from, uint32_t n1, uint32_t 
 /// counters shared by all the births the family decided are booked per family (settleFamilies).
 void Engine::walkFamily (uint32_t i, const uint32_t *w, RepMeta &g, Species *s0, uint32_t fact, uint32_t &sid, int32_t &slot,
                          uint32_t &replaced) {
-  Family &F = fams_[size_t(grpFam_[s0->grp_index])];
+  const Family &F = fams_[size_t(grpFam_[s0->grp_index])];
+  std::vector<Species*> &founded = famFounded_[size_t(grpFam_[s0->grp_index])];
   const uint32_t code = fact & FAM_CODE_MASK, child = fact >> FAM_CHILD_SHIFT, r = (fact >> FAM_SLOT_SHIFT) & 31u;
   const Contributions contrib { { g.msid, 1u + (g.msid == g.fsid) } };
   replaced = INV;
@@ -998,11 +999,11 @@ void Engine::walkFamily (uint32_t i, const uint32_t *w, RepMeta &g, Species *s0,
   m.timestamp = step_;
   if (code == FAM_FOUNDED) {
     const uint32_t f = uint32_t(grpFam_[s0->grp_index]), j = child - F.snapN;
-    if (j != F.founded.size()) throw ApiError(APT_ERR_STATE, "family pass: species founded out of order");
+    if (j != founded.size()) throw ApiError(APT_ERR_STATE, "family pass: species founded out of order");
     forcedSlot_ = hNewFounder_.p[size_t(fams_.size()) * famMaxNew_ + size_t(f) * famMaxNew_ + j];
     c = makeNode(contrib);                                    // simpleNewSpecies, :637-643
     if (c->parent != s0) throw ApiError(APT_ERR_STATE, "family pass: a founded species did not become a sub-species");
-    F.founded.push_back(c);
+    founded.push_back(c);
     m.udata = g.gid;
     c->reps[0] = m;
     memcpy(&hPayload_[(size_t(c->slot) * K_) * wp_], w, W_ * sizeof(uint32_t));
@@ -1011,7 +1012,7 @@ void Engine::walkFamily (uint32_t i, const uint32_t *w, RepMeta &g, Species *s0,
     c->count++;  c->alive++;  c->last = step_;
     // (:639-643: the founder is inserted with an empty contribution)
   } else {
-    c = child < F.snapN ? s0->children[F.snapN - 1 - child] : F.founded.at(child - F.snapN);
+    c = child < F.snapN ? s0->children[F.snapN - 1 - child] : founded.at(child - F.snapN);
     const uint32_t k = c->k;
     const float *d = hRows_.p + size_t(hFamRow_.p[i]) * K_;
     if (fact & FAM_REPLACED) {
@@ -1058,12 +1059,12 @@ void Engine::settleFamilies (void) {
     branching_ += uint32_t(hFamStats_.p[2 * f]);
     comparisons_ += uint32_t(hFamStats_.p[2 * f + 1]);
     counters[0] += info.x;  counters[1] += info.x;  counters[15] += info.x;
-    if (info.y != F.founded.size()) throw ApiError(APT_ERR_STATE, "family pass: founded species were not all committed");
+    if (info.y != famFounded_[f].size()) throw ApiError(APT_ERR_STATE, "family pass: founded species were not all committed");
     const uint32_t C = F.snapN + info.y;
     for (uint32_t c = 0; c < C; c++) {
       const uint32_t n1 = hChildJoin_.p[F.joinOff + 2 * c], n2 = hChildJoin_.p[F.joinOff + 2 * c + 1];
       if (!(n1 + n2)) continue;
-      Species *sp = c < F.snapN ? S->children[F.snapN - 1 - c] : F.founded[c - F.snapN];
+      Species *sp = c < F.snapN ? S->children[F.snapN - 1 - c] : famFounded_[f][c - F.snapN];
       sp->count += n1 + n2;  sp->alive += n1 + n2;  sp->last = step_;
       bulkContribution(sp, S, n1, n2);
     }
@@ -1549,7 +1550,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       if (ok) {
         grpFam_[g] = int32_t(fams_.size());
-        fams_.push_back(Family{ g, uint32_t(ch.size()), joinOff, {} });
+        fams_.push_back(Family{ g, uint32_t(ch.size()), joinOff });
         maxSnap = std::max<uint32_t>(maxSnap, uint32_t(ch.size()));
       }
     }
@@ -1816,6 +1817,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       // not pay for it.  It appends its rows behind the streams' and is awaited here.
       if (launchFamilies && hCtr_.p[1] >= std::max<uint32_t>(32u, n / 64u)) {
         launchFamilies();
+        famFounded_.resize(std::max(famFounded_.size(), fams_.size()));
+        for (size_t f = 0; f < fams_.size(); f++) famFounded_[f].clear();
         cudaCheck(cudaMemcpyAsync(hCtr_.p, dCtr_.p, 8, cudaMemcpyDeviceToHost, stream_), "counters");
         // (the species ids / slots of the births it decided: fetched again)
         cudaCheck(cudaMemcpyAsync(directOut ? outSid : hOutSid_.p, dOut2_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
@@ -2178,8 +2181,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           const uint32_t v = outSid[i];
           if (v != INV && (v & FAM_NEW_SID)) {
             const uint32_t f = (v & ~FAM_NEW_SID) / famMaxNew_, j = (v & ~FAM_NEW_SID) % famMaxNew_;
-            if (f >= nFam || j >= fams_[f].founded.size()) throw ApiError(APT_ERR_STATE, "family pass: unknown founded species");
-            outSid[i] = fams_[f].founded[j]->sid;
+            if (f >= nFam || j >= famFounded_[f].size()) throw ApiError(APT_ERR_STATE, "family pass: unknown founded species");
+            outSid[i] = famFounded_[f][j]->sid;
           }
         }
       }
@@ -2204,9 +2207,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         if (birthGroup_[i] < 0 || hAct_.p[i] != ACT_FALLTHROUGH || (hFamAct_.p[i] & FAM_CODE_MASK) != FAM_JOINED) continue;
         Species *S = grpSpecies_[size_t(birthGroup_[i])];
         const Family &F = fams_[size_t(grpFam_[S->grp_index])];
+        const auto &founded = famFounded_[size_t(grpFam_[S->grp_index])];
         const uint32_t child = hFamAct_.p[i] >> FAM_CHILD_SHIFT;
-        if (child >= F.snapN + F.founded.size()) continue;
-        Species *sp = child < F.snapN ? S->children[F.snapN - 1 - child] : F.founded[child - F.snapN];
+        if (child >= F.snapN + founded.size()) continue;
+        Species *sp = child < F.snapN ? S->children[F.snapN - 1 - child] : founded[child - F.snapN];
         if (S->pending > 0) S->pending--;
         sp->count++;  sp->alive++;  sp->last = step_;  insertions_++;
         bulkContribution(sp, S, msid[i] == fsid[i] ? 0u : 1u, msid[i] == fsid[i] ? 1u : 0u);

@@ -312,11 +312,9 @@ private:
   // sub-species, in order, founding included
   bool famOk_ = false;                    // the family kernel can serve this tree's configuration
   uint32_t famCap_ = 0;                   // sub-species (at submission + founded) one family may hold
-  struct Family {
-    uint32_t g, snapN, joinOff;           // stream index, sub-species at submission, offset of its counters
-    std::vector<Species*> founded;        // species the family founded in this pass, in founding order
-  };
+  struct Family { uint32_t g, snapN, joinOff; };    // stream index, sub-species at submission, offset of its counters
   std::vector<Family> fams_;
+  std::vector<std::vector<Species*>> famFounded_;   // per family: the species it founded in this pass, in founding order
   std::vector<int32_t> grpFam_;           // stream -> family, -1 = none
   uint32_t famMaxNew_ = 0, famSlotBase_ = 0, famSlotsUsed_ = 0;
   bool famResults_ = false;               // the pass produced family results (fetched)
