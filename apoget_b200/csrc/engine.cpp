@@ -100,9 +100,15 @@ void WorkerPool::run (const std::function<void(unsigned)> &fn) {
 
 double allocClock (void) { return now(); }
 
+static std::atomic<double> g_allocSeconds { 0. };
+double allocSeconds (void) { return g_allocSeconds.load(std::memory_order_relaxed); }
+
 void noteAlloc (const char *kind, size_t bytes, double t0) {
   static const bool on = getenv("APT_PROFILE") != nullptr;
-  if (on) fprintf(stderr, "alloc: %s %zu bytes in %.3f ms\n", kind, bytes, 1e3 * (now() - t0));
+  const double dt = now() - t0;
+  double cur = g_allocSeconds.load(std::memory_order_relaxed);
+  while (!g_allocSeconds.compare_exchange_weak(cur, cur + dt, std::memory_order_relaxed)) {}
+  if (on) fprintf(stderr, "alloc: %s %zu bytes in %.3f ms\n", kind, bytes, 1e3 * dt);
 }
 
 void cudaCheck (cudaError_t e, const char *what) {
@@ -2245,6 +2251,11 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
   if (!n) return;
   if (pool_ && n >= parMin_) pool_->wake();
   cudaCheck(cudaSetDevice(p_.device), "cudaSetDevice");
+  struct AllocTime {          // timers[7]: buffer growth inside this call (process-wide clock: one host thread per tree)
+    double &out, a0;
+    explicit AllocTime (double &o) : out(o), a0(allocSeconds()) {}
+    ~AllocTime (void) { out += allocSeconds() - a0; }
+  } allocTime (timers[7]);
   payloadPinned_ = false;
   if (!onDevice && size_t(n) * W_ * 4 >= stageMin_) {
     cudaPointerAttributes a;

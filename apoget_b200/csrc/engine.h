@@ -44,6 +44,8 @@ void cudaCheck (cudaError_t e, const char *what);
 /// APT_PROFILE: every (re)allocation of a grow-only buffer is reported on stderr with the time it took
 void noteAlloc (const char *kind, size_t bytes, double t0);
 double allocClock (void);
+/// seconds this process spent growing those buffers (cudaMalloc / cudaMallocHost and the frees that go with them)
+double allocSeconds (void);
 
 /// Grow-only device buffer
 template <typename T>

@@ -31,7 +31,7 @@ namespace {
 
 constexpr float FMAX = 3.402823466e+38f;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int FT = 128;                 // threads = births per step
+constexpr int FT = 256;                 // most threads (= births per step) a family CTA runs with; 128 when there are many families
 
 __device__ __forceinline__ uint32_t popc4 (uint4 a, uint4 b) {
   return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
@@ -55,7 +55,7 @@ extern __shared__ __align__(16) unsigned char fam_smem[];
 /// Byte offsets of the family's state in shared memory
 struct FamState {
   uint32_t oReps, oMeta, oD, oMinB, oFill, oSid, oChanged, oJoin, oAcc, oUnc, oDc, oEv, oCtl, oLut;
-  uint32_t K, cap, MW;
+  uint32_t K, cap, MW, T;
   const double *lutG;
   bool lutS;
   __device__ __forceinline__ uint4& reps (uint32_t c, uint32_t r, uint32_t v, uint32_t WQ) const { return reinterpret_cast<uint4*>(fam_smem + oReps)[(c * K + r) * WQ + v]; }
@@ -66,9 +66,9 @@ struct FamState {
   __device__ __forceinline__ uint32_t& sid (uint32_t c) const { return reinterpret_cast<uint32_t*>(fam_smem + oSid)[c]; }
   __device__ __forceinline__ uint32_t& changed (uint32_t c) const { return reinterpret_cast<uint32_t*>(fam_smem + oChanged)[c]; }
   __device__ __forceinline__ uint32_t& join (uint32_t i) const { return reinterpret_cast<uint32_t*>(fam_smem + oJoin)[i]; }
-  __device__ __forceinline__ uint32_t& acc (uint32_t w, uint32_t t) const { return reinterpret_cast<uint32_t*>(fam_smem + oAcc)[w * FT + t]; }
-  __device__ __forceinline__ uint32_t& unc (uint32_t w, uint32_t t) const { return reinterpret_cast<uint32_t*>(fam_smem + oUnc)[w * FT + t]; }
-  __device__ __forceinline__ float& dc (uint32_t r, uint32_t t) const { return reinterpret_cast<float*>(fam_smem + oDc)[r * FT + t]; }
+  __device__ __forceinline__ uint32_t& acc (uint32_t w, uint32_t t) const { return reinterpret_cast<uint32_t*>(fam_smem + oAcc)[w * T + t]; }
+  __device__ __forceinline__ uint32_t& unc (uint32_t w, uint32_t t) const { return reinterpret_cast<uint32_t*>(fam_smem + oUnc)[w * T + t]; }
+  __device__ __forceinline__ float& dc (uint32_t r, uint32_t t) const { return reinterpret_cast<float*>(fam_smem + oDc)[r * T + t]; }
   __device__ __forceinline__ uint32_t& ev (uint32_t i) const { return reinterpret_cast<uint32_t*>(fam_smem + oEv)[i]; }
   __device__ __forceinline__ uint32_t& ctl (uint32_t i) const { return reinterpret_cast<uint32_t*>(fam_smem + oCtl)[i]; }
   __device__ __forceinline__ double lut (size_t i) const { return lutS ? reinterpret_cast<const double*>(fam_smem + oLut)[i] : __ldg(lutG + i); }
@@ -121,14 +121,15 @@ __device__ __forceinline__ float fam_score (const ScoreCfg &cfg, const FamState 
 // event kinds (the word every warp publishes: thread << 8 | kind; smaller = earlier)
 constexpr uint32_t EVK_FOUND = 1, EVK_ENTER = 2, EVK_STOP = 3;
 
-template <int WQ, int KIND, bool LUT>
-__global__ void __launch_bounds__(FT, 1)
+template <int WQ, int KIND, bool LUT, int NT>
+__global__ void __launch_bounds__(NT, 1)
 resolve_families_kernel (FamilyArgs a) {
+  constexpr int FT = NT;                  // (shadows the sizing constant: everything below is per launch width)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t f = blockIdx.x, g = a.fam_group[f];
   const uint32_t K = a.pool.K, cap = a.cap, MW = (cap + 31) / 32;
   FamState fs;
-  fs.K = K;  fs.cap = cap;  fs.MW = MW;
+  fs.K = K;  fs.cap = cap;  fs.MW = MW;  fs.T = FT;
   uint32_t base = 0;
   fs.oReps = base;     base += cap * K * WQ * 16;
   fs.oMeta = base;     base += cap * K * 16;
@@ -460,14 +461,21 @@ void launch_resolve_families (const FamilyArgs &a, cudaStream_t st) {
   size_t smem = ((fam_child_bytes(a.pool.K, wq) * a.cap + fam_fixed_bytes(a.pool.K, a.cap)) + 15) & ~size_t(15);
   b.lut_in_smem = lutBytes > 0;
   smem += lutBytes;
-  auto go = [&] (auto kernel) {
+  // few families (the first generations of a radiation: ONE family of 100 000 births) get 256 threads each
+  const bool wide = a.n_fam <= 74;
+  auto go = [&] (auto kernel, int threads) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kernel<<<a.n_fam, FT, smem, st>>>(b);
+    kernel<<<a.n_fam, threads, smem, st>>>(b);
   };
   auto pick = [&] (auto wqc) {
     constexpr int WQ = decltype(wqc)::value;
-    if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true>); else go(resolve_families_kernel<WQ, 0, false>); }
-    else go(resolve_families_kernel<WQ, 1, false>);
+    if (wide) {
+      if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true, 256>, 256); else go(resolve_families_kernel<WQ, 0, false, 256>, 256); }
+      else go(resolve_families_kernel<WQ, 1, false, 256>, 256);
+    } else {
+      if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true, 128>, 128); else go(resolve_families_kernel<WQ, 0, false, 128>, 128); }
+      else go(resolve_families_kernel<WQ, 1, false, 128>, 128);
+    }
   };
   switch (wq) {
   case 1: pick(std::integral_constant<int, 1>{}); break;

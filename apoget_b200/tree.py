@@ -150,7 +150,7 @@ class PhylogeneticTree:
     def timers(self) -> dict:
         out = np.zeros(8, dtype=np.float64)
         check(lib().apt_tree_timers(self._h, out.ctypes.data_as(_lib.f64p)))
-        return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s", "score_kernel_ms", "stream_kernel_ms", "family_kernel_ms"],
+        return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s", "score_kernel_ms", "stream_kernel_ms", "family_kernel_ms", "alloc_s"],
                         (float(x) for x in out)))
 
     def node_info(self, sid: int) -> dict:

@@ -197,7 +197,7 @@ int apt_tree_counters (apt_tree *t, uint64_t out[16]);
 /* Time spent (cumulative): out[0] host prepare (s), [1] device H2D+kernels+D2H as waited for by the
  * host (s), [2] ordered resolution walk (s), [3] pool refresh (s), [4] scoring kernel alone,
  * CUDA events on the engine stream (ms), [5] stream-resolution kernel alone (ms), [6] family kernel alone (ms),
- * [7] reserved. */
+ * [7] growth of the engine's device and pinned buffers inside add_genomes calls (s; part of [0]-[3]: first-use cost). */
 int apt_tree_timers (apt_tree *t, double out[8]);
 
 /* ------------------------------------------------------------------------------------------------

@@ -84,6 +84,7 @@ def main():
         gen_rows.append([round(1e3 * per_gen[-1], 3)] +
                         [round(1e3 * (tm1[k] - tm0[k]), 3) for k in ("prepare_s", "device_s", "walk_s", "refresh_s")] +
                         [round(tm1["stream_kernel_ms"] - tm0["stream_kernel_ms"], 3)] +
+                        [round(tm1["family_kernel_ms"] - tm0["family_kernel_ms"], 3), round(1e3 * (tm1["alloc_s"] - tm0["alloc_s"]), 3)] +
                         [cn1[k] - cn0[k] for k in ("stream_launches", "host_scores", "stream_entries")])
         sid_of[b0:b1] = s
         tree.del_genomes(sid_of[t.deaths_of(g)])
@@ -94,7 +95,7 @@ def main():
            "cuda_seconds": sum(per_gen), "cuda_births_per_s": t.n_births / sum(per_gen),
            "cuda_births_per_s_last_gen": pop / per_gen[-1], "counters": tree.counters(), "timers": tree.timers(),
            "per_gen": {"columns": ["call_ms", "prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms", "stream_kernel_ms",
-                                   "device_passes", "host_scores", "stream_entries"], "rows": gen_rows}}
+                                   "family_kernel_ms", "alloc_ms", "device_passes", "host_scores", "stream_entries"], "rows": gen_rows}}
 
     if args.ref_births:
         import oracle
