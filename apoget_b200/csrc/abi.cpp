@@ -54,7 +54,12 @@ struct apt_pool {
   std::vector<float> classes;       // triples, class id = index
   // tensor-core sweep (tc_dense.cu): the pool expanded into tile images + per-tile metadata, built on first use
   uint8_t *tcImg = nullptr;  uint32_t *tcMeta = nullptr;
-  ~apt_pool (void) { cudaFree(payload); cudaFree(meta); cudaFree(fill); cudaFree(dlut); cudaFree(tcImg); cudaFree(tcMeta); }
+  // ... and the expanded births of the sweep in flight: kept between calls (a stream-ordered allocation of 2 GiB per call
+  // went back to the driver at every synchronisation; eight ranks allocating at once queue up behind each other)
+  uint8_t *tcBirths = nullptr;  size_t tcBirthsBytes = 0;
+  ~apt_pool (void) {
+    cudaFree(payload); cudaFree(meta); cudaFree(fill); cudaFree(dlut); cudaFree(tcImg); cudaFree(tcMeta); cudaFree(tcBirths);
+  }
   /// long bit-string genomes with the exact table go through the tensor cores (APT_DENSE_TC=0: popcount sweep)
   bool tcWanted (void) const {
     const char *e = getenv("APT_DENSE_TC");
@@ -75,8 +80,14 @@ struct apt_pool {
     tcEnsure(st);
     const size_t perBirth = tc_births_image_bytes(128, wp) / 128;
     uint32_t slab = uint32_t(std::min<size_t>(n, std::max<size_t>(128, ((size_t(2) << 30) / perBirth) / (148 * 128) * (148 * 128))));
-    uint8_t *img = nullptr;
-    cudaCheck(cudaMallocAsync(&img, tc_births_image_bytes(slab, wp), st), "cudaMallocAsync (expanded births)");
+    const size_t imgBytes = tc_births_image_bytes(slab, wp);
+    if (imgBytes > tcBirthsBytes) {
+      // (cudaFree waits for the device: no sweep of an earlier call still reads the old image)
+      cudaFree(tcBirths);  tcBirths = nullptr;  tcBirthsBytes = 0;
+      cudaCheck(cudaMalloc(&tcBirths, imgBytes), "cudaMalloc (expanded births)");
+      tcBirthsBytes = imgBytes;
+    }
+    uint8_t *img = tcBirths;
     for (uint32_t b0 = 0; b0 < n; b0 += slab) {
       const uint32_t m = std::min(slab, n - b0);
       launch_tc_expand_births(dB + size_t(b0) * wp, m, wp, img, st);
@@ -85,7 +96,6 @@ struct apt_pool {
                                matrix ? matrix + size_t(b0) * matrixLd : nullptr, st, sink, n, b0);
     }
     cudaCheck(cudaGetLastError(), "tensor-core sweep launch");
-    cudaCheck(cudaFreeAsync(img, st), "cudaFreeAsync");
   }
   std::map<std::array<float, 3>, uint32_t> classIds;
   uint32_t classOf (float mu, float sin, float sout) {

@@ -453,6 +453,8 @@ def main() -> None:
             if "speedup_vs_1gpu" in d:
                 dense["single_gpu_ms"] = d["single_gpu_ms"]
                 dense["speedup_vs_1gpu"] = d["speedup_vs_1gpu"]
+            if "per_rank_shard_sweep_ms" in d:
+                dense["per_rank_shard_sweep_ms"] = d["per_rank_shard_sweep_ms"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         path = os.path.join(tempfile.gettempdir(), "apt_bench_c2.trace")
         synth.write_trace(path, trace)

@@ -235,7 +235,9 @@ int apt_classify_dense_dev (apt_pool *p, uint32_t n_births, const uint32_t *d_pa
  * 5th-generation tensor cores -- Hamming distance as an exact int8 GEMM over genomes expanded to +-1 bytes,
  * (L - a.b) / 2, tcgen05.mma with the accumulators in tensor memory -- with the reference's arithmetic per
  * (birth, species) unchanged in the epilogue; results are bit-identical to the popcount sweep (environment
- * variable APT_DENSE_TC=0 selects that one).  The pool is expanded once, on the first sweep.
+ * variable APT_DENSE_TC=0 selects that one).  The pool is expanded once, on the first sweep, and keeps the scratch
+ * image of the births being swept (up to 2 GiB) between calls: sweeps of ONE pool must not overlap (issue them on one
+ * stream, or order the streams); different pools are independent.
  *
  * apt_distance_matrix: the births x members distance kernel on its own (north_star (1)): out[i * n_b + j] =
  * Hamming distance of genome i of payload_a and genome j of payload_b, through the same tensor-core pipeline. */

@@ -155,6 +155,22 @@ def run(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
 
+    # where the sharded time goes: every rank's sweep of its own shard alone (no exchange, no cross-rank wait), all ranks
+    # sweeping at the same time as in the measurement above
+    per_rank_ms = None
+    if world > 1 and p2p is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        _sweep()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [round(float(x[0]), 3) for x in allt]
+
     best, score, first, count = [x.cpu().numpy() for x in res]
     # ---- verification against the CPU oracle: `check` births x ALL species (threaded scorer of oracle/) ----
     bad, checked = 0, 0
@@ -219,6 +235,8 @@ def run(args):
         if single_ms is not None:
             out["single_gpu_ms"] = single_ms
             out["speedup_vs_1gpu"] = single_ms / ms
+        if per_rank_ms is not None:
+            out["per_rank_shard_sweep_ms"] = per_rank_ms
     if own_group:
         dist.destroy_process_group()
     return out
