@@ -93,7 +93,7 @@ struct WarpState {
   __device__ __forceinline__ float& D (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + oD)[i]; }              // [K][K]
   __device__ __forceinline__ float& minBase (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + oMinBase)[i]; }  // [K]
   __device__ __forceinline__ float& d (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + od)[i]; }              // [K][T] distance of thread t to representative r at r*T + t
-  __device__ __forceinline__ double& c (uint32_t i) const { return reinterpret_cast<double*>(apt_smem + oc)[i]; }            // [K][T] compatibilities (only when K is not a compile-time constant)
+  __device__ __forceinline__ double& c (uint32_t i) const { return reinterpret_cast<double*>(apt_smem + oc)[i]; }            // [K][T] compatibilities
   __device__ __forceinline__ float& pre (uint32_t i) const { return reinterpret_cast<float*>(apt_smem + oPre)[i]; }          // [K+1][T] running average BEFORE representative r is added (pre[k] = the total)
   __device__ __forceinline__ uint32_t& ev (uint32_t i) const { return reinterpret_cast<uint32_t*>(apt_smem + oEv)[i]; }      // [T] per event of a step: thread << 8 | distances
   __device__ __forceinline__ uint32_t& ctl (uint32_t i) const { return reinterpret_cast<uint32_t*>(apt_smem + oCtl)[i]; }    // [64] exchange words
@@ -102,14 +102,14 @@ struct WarpState {
   }
 };
 
-/// A thread's distances and compatibilities to the k representatives.  With the enveloppe size known
-/// at compile time (KT > 0) they live in registers and every loop over them is unrolled -- the
-/// per-event critical path (criterion, re-sum) then has no shared-memory round trips in it; the
-/// distances are mirrored to shared memory because the OTHER threads need the entering birth's row.
+/// A thread's distances to the k representatives.  With the enveloppe size known at compile time (KT > 0)
+/// they live in registers and every loop over them is unrolled -- the criterion on the per-event critical
+/// path then has no shared-memory round trips in it; they are mirrored to shared memory because the OTHER
+/// threads need the entering birth's row.  The compatibilities stay in shared memory: the decisions only
+/// need their sum (decision_score), the exact chain reads them when a score is too close to call.
 template <int KT>
 struct Lane {
   float d[KT ? KT : 1];
-  double c[KT ? KT : 1];
 };
 
 #define APT_FOR_K(r, k) _Pragma("unroll") for (uint32_t r = 0; r < (KT ? uint32_t(KT) : (k)); r++) if (KT == 0 || r < (k))
@@ -146,18 +146,23 @@ __device__ __forceinline__ void measure_one (const ScoreCfg &cfg, const uint4 (&
   c = pair_compat<LUT>(cfg, ws, bm, ws.rmeta(r), d);
 }
 
-/// (re-)measures representative r and stores the result in the lane's column
+/// (re-)measures representative r and stores the result in the lane's column; returns by how much the lane's
+/// compatibility to slot r changed (`replaces`: the slot held a representative before; else it is new)
 template <int WQ, int KIND, bool LUT, int KT>
-__device__ __forceinline__ void measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
-                                         const WarpState &ws, Lane<KT> &ln, uint32_t r, int lane) {
-  float df;  double c;
+__device__ __forceinline__ double measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
+                                           const WarpState &ws, Lane<KT> &ln, uint32_t r, int lane, bool replaces) {
+  float df;  double c, old;
   measure_one<WQ, KIND, LUT>(cfg, bw, bm, ws, r, df, c);
   ws.d(r * ws.T + lane) = df;
   if (KT > 0) {
 #pragma unroll
-    for (int q = 0; q < (KT ? KT : 1); q++) if (uint32_t(q) == r) { ln.d[q] = df; ln.c[q] = c; }
-  } else ws.c(r * ws.T + lane) = c;
+    for (int q = 0; q < (KT ? KT : 1); q++) if (uint32_t(q) == r) ln.d[q] = df;
+  }
+  old = ws.c(r * ws.T + lane);
+  ws.c(r * ws.T + lane) = c;
+  return replaces ? c - old : c;
 }
+
 
 /// phylogenetictree.hpp:465-477 / :439-451 over this lane's cached compatibilities.  The float
 /// accumulation is order sensitive, so it stays sequential -- but representatives before `from` are
@@ -170,15 +175,38 @@ __device__ __forceinline__ float resum (const ScoreCfg &cfg, const WarpState &ws
     APT_FOR_K(r, k) {
       if (r >= from) {
         ws.pre(r * ws.T + lane) = avg;
-        avg = float(__dadd_rn(double(avg), KT ? ln.c[KT ? r : 0] : ws.c(r * ws.T + lane)));
+        avg = float(__dadd_rn(double(avg), ws.c(r * ws.T + lane)));
       }
     }
     ws.pre(k * ws.T + lane) = avg;
     return float(__dsub_rn(double(__fdiv_rn(avg, float(k))), cfg.avg_thr));
   }
   uint32_t matable = 0;
-  APT_FOR_K(r, k) matable += ((KT ? ln.c[KT ? r : 0] : ws.c(r * ws.T + lane)) >= cfg.compat_thr);
+  APT_FOR_K(r, k) matable += (ws.c(r * ws.T + lane) >= cfg.compat_thr);
   return float(__dsub_rn(double(matable), __dmul_rn(cfg.sim_thr, double(k))));
+}
+
+/// The score as far as the decisions need it (its sign; in the guarded mode also whether it is inside the guard band).
+/// Continuous mode: the reference's float accumulation (resum) is a chain of k dependent F2F / DADD / F2F triples on the
+/// critical path of every event.  A plain double sum of the same compatibilities, sumC / k - threshold, differs from it
+/// by less than 2^-24 * 1.001 * ((k + 1) / 2 + 1) -- every partial sum is <= k and picks up one float rounding, the
+/// quotient one more -- so outside a band eight times that wide (plus the guard) the two agree in sign and in the guard
+/// test, and the exact chain only runs for the rare birth inside it (from the first representative whose compatibility
+/// changed since the chain last ran: dirtyFrom).  No score leaves this kernel, only the decisions.
+template <int KT>
+__device__ __forceinline__ float decision_score (const ScoreCfg &cfg, const WarpState &ws, const Lane<KT> &ln, uint32_t k,
+                                                 int lane, double sumC, float guard, uint32_t &dirtyFrom) {
+  if (cfg.full_continuous) {
+    // (k is uniform; a full enveloppe of compile-time size needs no division)
+    const double invK = (KT > 0 && k == uint32_t(KT)) ? 1. / double(KT ? KT : 1) : 1. / double(k);
+    const double approx = __dsub_rn(__dmul_rn(sumC, invK), cfg.avg_thr);
+    const float band = guard + float(k + 8u) * 2.4e-7f;            // 4 * 2^-24 * (k + 8) >= 8 x the error bound
+    if (fabs(approx) > double(band)) return approx > 0. ? 1.f : -1.f;
+    const float exact = resum<KT>(cfg, ws, ln, k, lane, dirtyFrom);
+    dirtyFrom = k;
+    return exact;
+  }
+  return resum<KT>(cfg, ws, ln, k, lane, 0);
 }
 
 /// maxMinDist (enveloppecriteria.cpp:87-133) for this lane's distances against a FULL enveloppe.
@@ -202,6 +230,35 @@ __device__ __forceinline__ bool criterion_maxMinDist (const WarpState &ws, const
     if (value < c) { value = c; than = i; }                      // :125-128, first index wins ties
   }
   return value > 0.f;                                            // :131
+}
+
+/// The same criterion for bit-string genomes, where every distance is a small integer held exactly by a float: the
+/// differences of :117 are exact, so max_i (minNew_i - minBase_i) is reached either at i1 (the representative nearest
+/// to the birth, whose minNew is the second smallest distance m2) or at the row with the smallest minBase among the
+/// others (minNew = m1 for all of them; smallest minBase, first index on ties, = first index of the largest
+/// difference).  The two smallest (minBase, index) pairs of the enveloppe are found once per event by the warp that
+/// updates the matrix (keys below) instead of by every thread: key = minBase << 5 | row, FLT_MAX as 0xFFFFFFE0 | row.
+__device__ __forceinline__ uint32_t minbase_key (float m, uint32_t row) {
+  return (m >= 16777216.f ? 0xFFFFFFE0u : (uint32_t(m) << 5)) | row;
+}
+template <int KT>
+__device__ __forceinline__ bool criterion_maxMinDist_int (const WarpState &ws, const Lane<KT> &ln, uint32_t K, int lane,
+                                                          uint32_t key1, uint32_t key2, uint32_t &than) {
+  float m1 = FMAX, m2 = FMAX;
+  uint32_t i1 = 0xFFFFFFFFu;
+  APT_FOR_K(r, K) {
+    const float x = KT ? ln.d[KT ? r : 0] : ws.d(r * ws.T + lane);
+    if (x < m1) { m2 = m1; m1 = x; i1 = r; }
+    else if (x < m2) m2 = x;
+  }
+  const uint32_t keyA = (key1 & 31u) == i1 ? key2 : key1;            // smallest minBase over the rows other than i1
+  const uint32_t iA = keyA & 31u;
+  const float cA = __fadd_rn(-float(keyA >> 5), m1);                 // :117 for every i != i1 collapses to this one
+  const float cB = __fadd_rn(-ws.minBase(i1), m2);                   // ... and i1 itself
+  // :125-128: the first index reaching the maximum wins
+  const bool takeB = cB > cA || (cB == cA && i1 < iA);
+  than = takeB ? i1 : iA;
+  return (takeB ? cB : cA) > 0.f;                                    // :131
 }
 
 /// maxAverage (enveloppecriteria.cpp:40-84)
@@ -235,7 +292,8 @@ __device__ __noinline__ uint32_t criterion_other (int crit, uint32_t oD, uint32_
 
 /// Shared-memory bytes of one stream (without the table)
 __host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T, bool ktConst = false) {
-  return (ktConst ? 0 : size_t(K) * T * 8) + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
+  (void) ktConst;
+  return size_t(K) * T * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
        + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + size_t(T) * 4 + 64 * 4;
 }
 
@@ -256,7 +314,7 @@ resolve_streams_kernel (StreamArgs a) {
   uint32_t base = 0;
   WarpState ws;
   ws.T = T;
-  ws.oc = base;        if (KT == 0) base += K * T * 8;
+  ws.oc = base;        base += K * T * 8;
   ws.oReps = base;     base += K * WQ * 16;
   ws.oRmeta = base;    base += K * 16;
   ws.oD = base;        base += K * K * 4;
@@ -326,8 +384,16 @@ resolve_streams_kernel (StreamArgs a) {
     ws.minBase(r) = m;
   }
   __syncthreads();
+  if (KIND == 0 && warp == 0) {                 // criterion_maxMinDist_int's keys (rows past k: FLT_MAX)
+    const uint32_t key = (uint32_t(lane) < K) ? minbase_key(uint32_t(lane) < k ? ws.minBase(lane) : FMAX, lane) : 0xFFFFFFFFu;
+    const uint32_t k1 = __reduce_min_sync(0xffffffffu, key);
+    const uint32_t k2 = __reduce_min_sync(0xffffffffu, key == k1 ? 0xFFFFFFFFu : key);
+    if (lane == 0) { ws.ctl(34) = k1;  ws.ctl(35) = k2; }
+  }
+  __syncthreads();
   if (prof && tid == 0) prof[2] = clock64();
   Lane<KT> ln;
+  const float bandGuard = LUT ? 0.f : a.guard;      // decision_score: the exact table needs no guard band
 
   uint32_t changed = 0;         // slots to write back (uniform)
   uint32_t nRej = 0;            // births rejected at top level so far (uniform)
@@ -359,14 +425,18 @@ resolve_streams_kernel (StreamArgs a) {
       prefetch_l2(a.b_cmeta + (ordNext & ORDER_INDEX_MASK));
     }
     float score = 0.f;
+    double sumC = 0.;               // sum of this birth's compatibilities (decision_score)
+    uint32_t dirtyFrom = 0;         // the exact chain's partial sums are valid up to here
     if (active) {
       APT_FOR_K(r, k) {
         float df;  double c;
         measure_one<WQ, KIND, LUT>(a.cfg, bw, bm, ws, r, df, c);
         ws.d(r * T + tid) = df;
-        if (KT > 0) { ln.d[KT ? r : 0] = df; ln.c[KT ? r : 0] = c; } else ws.c(r * T + tid) = c;
+        if (KT > 0) ln.d[KT ? r : 0] = df;
+        ws.c(r * T + tid) = c;
+        sumC += c;
       }
-      score = resum<KT>(a.cfg, ws, ln, k, tid, 0);
+      score = decision_score<KT>(a.cfg, ws, ln, k, tid, sumC, bandGuard, dirtyFrom);
     }
     if (prof && tid == 0 && cb == g0) prof[3] = clock64();
     profSteps++;
@@ -386,7 +456,10 @@ resolve_streams_kernel (StreamArgs a) {
       if (accept && !uncertain) {
         if (k < K) { modifies = true; than = k; }                       // :668-677
         else if (K > 1) {
-          if (a.crit == 1) modifies = criterion_maxMinDist<KT>(ws, ln, K, tid, than);
+          if (a.crit == 1) {
+            if (KIND == 0) modifies = criterion_maxMinDist_int<KT>(ws, ln, K, tid, ws.ctl(34), ws.ctl(35), than);
+            else modifies = criterion_maxMinDist<KT>(ws, ln, K, tid, than);
+          }
           else if (a.crit == 0) modifies = criterion_maxAverage<KT>(ws, ln, K, tid, than);
           else if (CRITX) {           // criteria 2 / 3: instantiated for the generic variant only (launchNW)
             float gd[KMAX];
@@ -444,7 +517,31 @@ resolve_streams_kernel (StreamArgs a) {
       // Lane r of warp 0 owns row r (only its column sl changes), one lane of warp 1 owns row sl (the birth's
       // own distances): no thread needs another's writes for its new minimum.  Straight-line code, loads
       // unconditional -- this sits on the critical path of every event.
-      {
+      if (KIND == 0) {
+        // bit strings: warp 0 does all rows in one instruction stream (lane sl: the birth's own row), because the
+        // rows' minima meet in a warp reduction right after (criterion_maxMinDist_int's keys)
+        if (warp == 0) {
+          const uint32_t aEnt = ws.sb + ws.od + stop * 4;
+          const uint32_t r = min(uint32_t(tid), K - 1u), aRow = ws.sb + ws.oD + r * K * 4;
+          const bool row = uint32_t(tid) < k, own = uint32_t(tid) == sl;
+          const float dr = lds_f32(aEnt + r * T * 4);
+          float m = FMAX;
+#pragma unroll (KT ? KT : 1)
+          for (uint32_t j = 0; j < K; j++) {
+            const float e = lds_f32(aEnt + j * T * 4);          // columns past kOld hold stale values: masked
+            const float w = lds_f32(aRow + j * 4);
+            const float v = own ? ((j == sl || j >= kOld) ? FMAX : e) : (j == sl ? dr : w);
+            if (own) ws.D(sl * K + j) = v;
+            m = fminf(m, v);
+          }
+          if (row && !own) ws.D(r * K + sl) = dr;
+          if (row) ws.minBase(r) = m;
+          const uint32_t key = (uint32_t(tid) < K) ? minbase_key(row ? m : FMAX, tid) : 0xFFFFFFFFu;
+          const uint32_t k1 = __reduce_min_sync(0xffffffffu, key);
+          const uint32_t k2 = __reduce_min_sync(0xffffffffu, key == k1 ? 0xFFFFFFFFu : key);
+          if (lane == 0) { ws.ctl(34) = k1;  ws.ctl(35) = k2; }
+        }
+      } else {
         const uint32_t aEnt = ws.sb + ws.od + stop * 4;
         if (uint32_t(tid) < k && uint32_t(tid) != sl) {
           const uint32_t r = tid, aRow = ws.sb + ws.oD + r * K * 4;
@@ -474,8 +571,9 @@ resolve_streams_kernel (StreamArgs a) {
       changed |= 1u << sl;
       // later births see the new representative: re-measure that slot only, re-sum from there in order
       if (mine) {
-        measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, sl, tid);
-        score = resum<KT>(a.cfg, ws, ln, k, tid, sl);
+        sumC += measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, sl, tid, !append);
+        dirtyFrom = min(dirtyFrom, sl);
+        score = decision_score<KT>(a.cfg, ws, ln, k, tid, sumC, bandGuard, dirtyFrom);
       }
     }
 
