@@ -146,13 +146,13 @@ __device__ __forceinline__ void measure_one (const ScoreCfg &cfg, const uint4 (&
   c = pair_compat<LUT>(cfg, ws, bm, ws.rmeta(r), d);
 }
 
-/// (re-)measures representative r and stores the result in the lane's column; returns by how much the lane's
+/// (re-)measures representative r (read from row src) and stores the result in the lane's column; returns by how much the lane's
 /// compatibility to slot r changed (`replaces`: the slot held a representative before; else it is new)
 template <int WQ, int KIND, bool LUT, int KT>
 __device__ __forceinline__ double measure (const ScoreCfg &cfg, const uint4 (&bw)[WQ], float4 bm,
-                                           const WarpState &ws, Lane<KT> &ln, uint32_t r, int lane, bool replaces) {
+                                           const WarpState &ws, Lane<KT> &ln, uint32_t src, uint32_t r, int lane, bool replaces) {
   float df;  double c, old;
-  measure_one<WQ, KIND, LUT>(cfg, bw, bm, ws, r, df, c);
+  measure_one<WQ, KIND, LUT>(cfg, bw, bm, ws, src, df, c);        // src: the row that holds slot r's new genome (staging row)
   ws.d(r * ws.T + lane) = df;
   if (KT > 0) {
 #pragma unroll
@@ -293,7 +293,7 @@ __device__ __noinline__ uint32_t criterion_other (int crit, uint32_t oD, uint32_
 /// Shared-memory bytes of one stream (without the table)
 __host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T, bool ktConst = false) {
   (void) ktConst;
-  return size_t(K) * T * 8 + size_t(K) * wq * 16 + size_t(K) * 16 + size_t(K) * K * 4 + size_t(K) * 4
+  return size_t(K) * T * 8 + size_t(K + T / 32) * wq * 16 + size_t(K + T / 32) * 16 + size_t(K) * K * 4 + size_t(K) * 4
        + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + size_t(T) * 4 + 64 * 4;
 }
 
@@ -315,8 +315,8 @@ resolve_streams_kernel (StreamArgs a) {
   WarpState ws;
   ws.T = T;
   ws.oc = base;        base += K * T * 8;
-  ws.oReps = base;     base += K * WQ * 16;
-  ws.oRmeta = base;    base += K * 16;
+  ws.oReps = base;     base += (K + NW) * WQ * 16;        // rows K ...: one staging row per warp (the genome its candidate
+  ws.oRmeta = base;    base += (K + NW) * 16;             // would put into the enveloppe, visible to all at the event barrier)
   ws.oD = base;        base += K * K * 4;
   ws.oMinBase = base;  base += K * 4;
   ws.od = base;        base += K * T * 4;
@@ -479,6 +479,13 @@ resolve_streams_kernel (StreamArgs a) {
         const uint32_t word = (uint32_t(tid) << EV_TID_SHIFT) | (uncertain ? EV_UNCERTAIN : (than & EV_SLOT_MASK));
         const uint32_t w0 = __shfl_sync(0xffffffffu, word, first);
         if (lane == 0) ws.ctl(warp) = w0;
+        // the warp's candidate shows its genome before the barrier: should it be the event, the later births measure
+        // it at once, while warp 0 updates the matrix (nobody waits for the owner to publish it after the barrier)
+        if (lane == first && !uncertain) {
+#pragma unroll
+          for (int v = 0; v < WQ; v++) ws.reps((K + warp) * WQ + v) = bw[v];
+          ws.rmeta(K + warp) = bm;
+        }
       } else if (lane == 0) ws.ctl(warp) = NONE;
       __syncthreads();
       if (prof) { const long long t = clock64(); profA += t - profT; profT = t; }
@@ -566,15 +573,16 @@ resolve_streams_kernel (StreamArgs a) {
           ws.minBase(sl) = m;
         }
       }
-      __syncthreads();
-      if (prof) { const long long t = clock64(); profB += t - profT; profT = t; }
-      changed |= 1u << sl;
-      // later births see the new representative: re-measure that slot only, re-sum from there in order
+      // later births see the new representative: re-measure that slot only (from the winner's staging row: the matrix
+      // update above and this run side by side), the score follows from the change of that one compatibility
       if (mine) {
-        sumC += measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, sl, tid, !append);
+        sumC += measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, K + (stop >> 5), sl, tid, !append);
         dirtyFrom = min(dirtyFrom, sl);
         score = decision_score<KT>(a.cfg, ws, ln, k, tid, sumC, bandGuard, dirtyFrom);
       }
+      __syncthreads();            // the criterion at the top of the loop reads the matrix' row minima
+      if (prof) { const long long t = clock64(); profB += t - profT; profT = t; }
+      changed |= 1u << sl;
     }
 
     // ---- the step's results leave the chip: one row claim for all its enveloppe entries, one result
