@@ -156,6 +156,7 @@ Engine::Engine (const apt_params &p) : p_(p) {
     if (const char *e = getenv("APT_STAGE_MIN")) stageMin_ = size_t(std::max(1, atoi(e)));
     profile_ = getenv("APT_PROFILE") != nullptr;
     if (const char *e = getenv("APT_STREAM_PROF")) streamProf_ = e;
+    if (const char *e = getenv("APT_DEVLIST_MIN")) devListMin_ = uint32_t(std::max(1, atoi(e)));
     if (const char *e = getenv("APT_LUT_MAX_BYTES")) lutMaxBytes_ = size_t(std::max(0ll, atoll(e)));
     if (nt > 1) pool_.reset(new WorkerPool(nt));
   }
@@ -1624,6 +1625,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   nFt_ = 0;  nFtRows_ = 0;
   bool ftRows = false;
   uint32_t specRows = 0, specFt = 0;        // rows / rejected births fetched ahead of knowing their number
+  uint32_t specSlow = 0, nSlow = 0;
+  const bool devList = streamOk_ && n >= devListMin_;      // (small passes: the host scans the result words itself)
   bool directOut = false;
   std::function<void(void)> launchFamilies;     // K3 is only launched once the pass is known to have rejected births (below)
   if (G) {
@@ -1760,6 +1763,20 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       counters[4]++;
       ftRows = true;
     }
+    if (devList) {
+      // the births the host will have to look at, in arrival order (it reads this list instead of every result word)
+      dSlowBlk_.reserve(list_unsettled_blocks(n));  dSlowList_.reserve(2 * size_t(n));  dSlowCtr_.reserve(1);
+      launch_list_unsettled(dAct_.p, nullptr, n, dSlowBlk_.p, dSlowList_.p, dSlowCtr_.p, stream_);
+      counters[4] += 2;
+      cudaCheck(cudaGetLastError(), "list_unsettled launch");
+      cudaCheck(cudaMemcpyAsync(hCtr_.p + 3, dSlowCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "listed births");
+      hSlowList_.reserve(2 * std::max<size_t>(2048, nStream / 4));
+      if (estSlow_) {
+        specSlow = uint32_t(std::min<size_t>(estSlow_, n));
+        hSlowList_.reserve(2 * size_t(specSlow));
+        cudaCheck(cudaMemcpyAsync(hSlowList_.p, dSlowList_.p, 2 * size_t(specSlow) * 4, cudaMemcpyDeviceToHost, stream_), "list");
+      }
+    }
     cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
     cudaCheck(cudaMemcpyAsync(hCtr_.p, dCtr_.p, 8, cudaMemcpyDeviceToHost, stream_), "counters");
     // results go straight into the caller's arrays when those are pinned (no staging copy on the host)
@@ -1830,6 +1847,13 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         cudaCheck(cudaMemcpyAsync(directOut ? outSid : hOutSid_.p, dOut2_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
         cudaCheck(cudaMemcpyAsync(directOut ? reinterpret_cast<uint32_t*>(outSlot) : reinterpret_cast<uint32_t*>(hOutSlot_.p), dOut2_.p + n,
                                   size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "slots");
+        if (devList) {              // (births that joined a sub-species there are settled now: listed again)
+          launch_list_unsettled(dAct_.p, dFamAct_.p, n, dSlowBlk_.p, dSlowList_.p, dSlowCtr_.p, stream_);
+          counters[4] += 2;
+          cudaCheck(cudaGetLastError(), "list_unsettled launch");
+          cudaCheck(cudaMemcpyAsync(hCtr_.p + 3, dSlowCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "listed births");
+          specSlow = 0;
+        }
         cudaCheck(cudaStreamSynchronize(stream_), "family pass");
         float fm = 0.f;
         cudaCheck(cudaEventElapsedTime(&fm, evF0_, evF1_), "event elapsed");
@@ -1885,7 +1909,15 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           famResults_ = true;
         }
       }
-      if (nRows > specRows || nFt_ || nFtRows_ > specFt || famResults_) cudaCheck(cudaStreamSynchronize(stream_), "rows");
+      if (devList) {
+        nSlow = std::min(hCtr_.p[3], n);
+        if (nSlow > specSlow) {
+          hSlowList_.reserve(2 * size_t(nSlow));
+          cudaCheck(cudaMemcpyAsync(hSlowList_.p, dSlowList_.p, 2 * size_t(nSlow) * 4, cudaMemcpyDeviceToHost, stream_), "list");
+        }
+        estSlow_ = nSlow + nSlow / 4 + 64;
+      }
+      if (nRows > specRows || nFt_ || nFtRows_ > specFt || famResults_ || nSlow > specSlow) cudaCheck(cudaStreamSynchronize(stream_), "rows");
       if (famResults_) {
         famSlotsUsed_ = std::min<uint32_t>(hCtr_.p[2], famReserve(nStream));
         if (famSlotsUsed_) {
@@ -1908,7 +1940,32 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   //      top level, two-parent births, streams handed back -- is committed here in arrival order. ----
   curPayload_ = payload;
   slow_.clear();  slowGrp_.clear();  slowAct_.clear();  requeue_.clear();  grpOwner_.clear();
-  if (G) {
+  if (G && devList) {
+    // the device listed the births the host has to look at (arrival order); the outputs of the others are in place
+    const unsigned T = (pool_ && n >= parMin_) ? pool_->size() : 1u;
+    if (!directOut) {
+      const uint32_t per = (n + T - 1) / T;
+      auto copyOut = [&] (unsigned t) {
+        const uint32_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+        if (outSid) memcpy(outSid + lo, hOutSid_.p + lo, size_t(hi - lo) * 4);
+        if (outSlot) memcpy(outSlot + lo, hOutSlot_.p + lo, size_t(hi - lo) * 4);
+      };
+      if (T > 1) pool_->run(copyOut); else copyOut(0);
+    }
+    mark("commit-init");
+    mark("scan");
+    const size_t total = nSlow;
+    slow_.resize(total);  slowGrp_.resize(total);  slowAct_.resize(total);
+    const uint32_t *list = hSlowList_.p;
+    for (size_t q = 0; q < total; q++) {
+      if (q + 16 < total) __builtin_prefetch(&birthGroup_[list[2 * (q + 16)]]);
+      const uint32_t i = list[2 * q];
+      if (i >= n) throw ApiError(APT_ERR_STATE, "device list of unsettled births is corrupt");
+      const int32_t bg = birthGroup_[i];
+      slow_[q] = i;  slowGrp_[q] = bg;  slowAct_[q] = list[2 * q + 1];
+      if (bg >= 0 && (list[2 * q + 1] & ACT_CODE_MASK) == ACT_ENTERED) grpState_[size_t(bg)].lastEnter = i;
+    }
+  } else if (G) {
     // outputs of the births the device settled + the list of births the host has to look at
     // (one pass over the result words; split over the worker pool for large chunks)
     const unsigned T = (pool_ && n >= parMin_) ? pool_->size() : 1u;

@@ -221,6 +221,7 @@ private:
   uint32_t K_, W_, wp_;
   bool lutMode_;
   uint32_t lutStride_;
+  uint32_t devListMin_ = 4096;               // passes of at least this many births get their list of unsettled births from the device (APT_DEVLIST_MIN)
   size_t lutMaxBytes_ = size_t(256) << 20;   // largest compatibility table kept (APT_LUT_MAX_BYTES); beyond it: generic mode
 
   // ---- tree state (phylogenetictree.hpp:370-389) ----
@@ -307,6 +308,9 @@ private:
   uint32_t nFtRows_ = 0;                 // device-resident births: genomes of the rejected births fetched with the rows
   std::vector<int32_t> ftRowOfSlow_;
   int64_t curFtRow_ = -1;
+  // the births of a pass the host has to look at, listed in arrival order by the device (launch_list_unsettled)
+  DevBuf<uint32_t> dSlowBlk_, dSlowList_, dSlowCtr_;  PinBuf<uint32_t> hSlowList_;
+  uint32_t estSlow_ = 0;
   uint32_t estRows_ = 0, estFt_ = 0;     // enveloppe entries / rejected births of the last device pass (+25 %): fetched speculatively with the results
   DevBuf<uint32_t> dFtRows_;  PinBuf<uint32_t> hFtRows_;
   int64_t curFt_ = -1;                    // sub-species result entry of the birth being committed

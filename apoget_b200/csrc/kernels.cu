@@ -481,6 +481,90 @@ __global__ void gather_listed_rows_kernel (const uint32_t *__restrict__ src, con
   }
 }
 
+// ---- the births of a pass the host has to look at, in arrival order ------------------------------------------------
+// A birth is settled on the device when it was accepted with the enveloppe left alone -- at top level (stream kernel) or
+// by a sub-species (family pass).  Everything else (enveloppe entries, rejected births, births outside the streams whose
+// result word is still clear, streams handed back) is listed as {birth, result word}: the host reads this list instead of
+// scanning one result word per birth.  Two small launches: per-block counts, then the ordered write.
+constexpr uint32_t LIST_THREADS = 256, LIST_PER_THREAD = 8, LIST_PER_BLOCK = LIST_THREADS * LIST_PER_THREAD;
+
+__device__ __forceinline__ bool birth_unsettled (uint32_t act, const uint32_t *fam_act, uint32_t i) {
+  if (act == ACT_ACCEPTED) return false;
+  return !(fam_act && act == ACT_FALLTHROUGH && (fam_act[i] & FAM_CODE_MASK) == FAM_JOINED);
+}
+
+__device__ __forceinline__ uint32_t block_sum (uint32_t v, uint32_t *warpSums) {      // every thread gets the total
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) warpSums[warp] = v;
+  __syncthreads();
+  uint32_t t = 0;
+  for (uint32_t w = 0; w < LIST_THREADS / 32; w++) t += warpSums[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(LIST_THREADS)
+unsettled_count_kernel (const uint32_t *act, const uint32_t *fam_act, uint32_t n, uint32_t *block_count) {
+  __shared__ uint32_t warpSums[LIST_THREADS / 32];
+  const uint32_t i0 = blockIdx.x * LIST_PER_BLOCK + threadIdx.x * LIST_PER_THREAD;
+  uint32_t c = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < LIST_PER_THREAD; j++)
+    if (i0 + j < n) c += birth_unsettled(act[i0 + j], fam_act, i0 + j);
+  const uint32_t t = block_sum(c, warpSums);
+  if (threadIdx.x == 0) block_count[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(LIST_THREADS)
+unsettled_list_kernel (const uint32_t *act, const uint32_t *fam_act, uint32_t n, const uint32_t *block_count,
+                       uint32_t *list, uint32_t *total) {
+  __shared__ uint32_t warpSums[LIST_THREADS / 32];
+  __shared__ uint32_t warpOff[LIST_THREADS / 32];
+  // entries of the blocks in front of this one
+  uint32_t before = 0;
+  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += LIST_THREADS) before += block_count[b];
+  before = block_sum(before, warpSums);
+  const uint32_t i0 = blockIdx.x * LIST_PER_BLOCK + threadIdx.x * LIST_PER_THREAD;
+  uint32_t a[LIST_PER_THREAD], flags = 0, c = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < LIST_PER_THREAD; j++) {
+    a[j] = 0;
+    if (i0 + j < n) {
+      a[j] = act[i0 + j];
+      if (birth_unsettled(a[j], fam_act, i0 + j)) { flags |= 1u << j; c++; }
+    }
+  }
+  // exclusive scan of the threads' counts: inside the warp, then across the warps
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= uint32_t(o)) incl += v; }
+  if (lane == 31) warpSums[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t w = 0; w < LIST_THREADS / 32; w++) { warpOff[w] = run; run += warpSums[w]; }
+    if (blockIdx.x == gridDim.x - 1) *total = before + run;
+  }
+  __syncthreads();
+  uint32_t at = before + warpOff[warp] + incl - c;
+#pragma unroll
+  for (uint32_t j = 0; j < LIST_PER_THREAD; j++)
+    if ((flags >> j) & 1u) { list[2 * size_t(at)] = i0 + j;  list[2 * size_t(at) + 1] = a[j];  at++; }
+}
+
+uint32_t list_unsettled_blocks (uint32_t n) { return (n + LIST_PER_BLOCK - 1) / LIST_PER_BLOCK; }
+
+void launch_list_unsettled (const uint32_t *act, const uint32_t *fam_act, uint32_t n, uint32_t *block_count,
+                            uint32_t *list, uint32_t *total, cudaStream_t stream) {
+  if (!n) return;
+  const uint32_t blocks = list_unsettled_blocks(n);
+  unsettled_count_kernel<<<blocks, LIST_THREADS, 0, stream>>>(act, fam_act, n, block_count);
+  unsettled_list_kernel<<<blocks, LIST_THREADS, 0, stream>>>(act, fam_act, n, block_count, list, total);
+}
+
 void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
                                 uint32_t words, uint32_t *dst, cudaStream_t stream) {
   if (!max_entries) return;

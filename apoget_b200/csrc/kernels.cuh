@@ -59,6 +59,12 @@ void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, u
                          cudaStream_t stream);
 
 /// dst[e][0..words) = src[list[2e]][0..words) for e < min(*count, max_entries), `count` being a device counter
+/// The births of a pass that are not settled on the device, in arrival order: list[2 e] = birth, list[2 e + 1] = its result
+/// word; *total = their number.  block_count: scratch of list_unsettled_blocks(n) words.  fam_act: the family pass'
+/// verdicts (births that joined a sub-species without changing it are settled too) or null.
+uint32_t list_unsettled_blocks (uint32_t n);
+void launch_list_unsettled (const uint32_t *act, const uint32_t *fam_act, uint32_t n, uint32_t *block_count,
+                            uint32_t *list, uint32_t *total, cudaStream_t stream);
 void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
                                 uint32_t words, uint32_t *dst, cudaStream_t stream);
 

@@ -126,6 +126,18 @@ void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, u
   for (uint32_t i = 0; i < n; i++) memcpy(dst + size_t(i) * words, src + size_t(idx[i]) * words, words * 4);
 }
 
+uint32_t list_unsettled_blocks (uint32_t n) { return (n + 2047) / 2048; }
+void launch_list_unsettled (const uint32_t *act, const uint32_t *fam_act, uint32_t n, uint32_t *, uint32_t *list,
+                            uint32_t *total, cudaStream_t) {
+  uint32_t at = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const bool settled = act[i] == ACT_ACCEPTED
+                         || (fam_act && act[i] == ACT_FALLTHROUGH && (fam_act[i] & FAM_CODE_MASK) == FAM_JOINED);
+    if (!settled) { list[2 * size_t(at)] = i;  list[2 * size_t(at) + 1] = act[i];  at++; }
+  }
+  if (n) *total = at;
+}
+
 void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
                                 uint32_t words, uint32_t *dst, cudaStream_t) {
   const uint32_t n = *count < max_entries ? *count : max_entries;

@@ -62,6 +62,14 @@ def test_tree_matches_unmodified_reference(name):
     _compare(name)
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_tree_with_the_device_made_list_of_unsettled_births(name, monkeypatch):
+    """Large batches read the births the host has to look at from a list the device compacts in arrival order
+    (launch_list_unsettled) instead of scanning every result word; forced on for the golden cases' small batches."""
+    monkeypatch.setenv("APT_DEVLIST_MIN", "1")
+    _compare(name)
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c4_b4096_k10"])
 def test_tree_generic_compat_path(name):
     """Device exp() instead of the libm-built table: decisions must still be identical."""

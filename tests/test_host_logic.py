@@ -153,9 +153,12 @@ def test_unknown_species_is_an_error_and_commits_the_prefix(hostsim):
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_randomised_traces_against_oracle(hostsim, seed, tmp_path):
+def test_randomised_traces_against_oracle(hostsim, seed, tmp_path, monkeypatch):
     """Fresh seeded traces with many far hybrids, overlapping generations and small enveloppes: the
-    regime where streams get taken over, contributions interleave and parents change."""
+    regime where streams get taken over, contributions interleave and parents change.  (Odd seeds: the
+    list of births the host looks at comes from the device-side pass, as it does for large batches.)"""
+    if seed % 2:
+        monkeypatch.setenv("APT_DEVLIST_MIN", "1")
     rng = np.random.default_rng(1000 + seed)
     K = int(rng.integers(1, 7))
     t = synth.generate(kind=synth.BITS, words=int(rng.choice([1, 2, 4, 8])), pop=int(rng.integers(30, 160)),
@@ -202,6 +205,8 @@ def test_radiations_resolved_by_the_family_pass(hostsim, seed, tmp_path, monkeyp
     if seed % 3 == 1:
         monkeypatch.setenv("APT_PAR_MIN", "1")
         monkeypatch.setenv("APT_HOST_THREADS", "3")
+    if seed % 2 == 0:
+        monkeypatch.setenv("APT_DEVLIST_MIN", "1")      # device-made list of unsettled births, re-made after the family pass
     path = str(tmp_path / "t.trace")
     synth.write_trace(path, t)
     o = oracle.Oracle(t.kind, t.words, **cfg)
@@ -259,6 +264,8 @@ def test_parallel_host_paths(hostsim, name, monkeypatch):
     enveloppe entries) forced on for small chunks: results, callback order and dump must not change."""
     monkeypatch.setenv("APT_PAR_MIN", "1")
     monkeypatch.setenv("APT_HOST_THREADS", "4")
+    _compare(hostsim, name)
+    monkeypatch.setenv("APT_DEVLIST_MIN", "1")
     _compare(hostsim, name)
 
 
