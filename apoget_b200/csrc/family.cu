@@ -15,14 +15,23 @@
 // sub-species, so "the first accepting sub-species in visiting order" is a bit scan.  Births that join a full
 // enveloppe without changing it (the bulk, once the niches are populated) cost no event at all.
 //
+// A family with very many births (the first generations of a radiation: ONE family of 100 000) is spread over a thread
+// block CLUSTER: every CTA keeps its own copy of the family's state, a step decides 256 births per CTA -- position in
+// the step = CTA rank * 256 + thread -- the earliest event is elected across the cluster through distributed shared
+// memory, its CTA applies it and pushes the changed sub-species into the other copies.  Scoring a step's births against
+// all sub-species, the bulk of the work when events are rare, then runs on up to 16 SMs instead of one.
+//
 // The host only commits what changed -- new species (it hands out the ids in birth order, :225-230), enveloppe
 // entries -- and books the rest per sub-species from the kernel's counters (engine.cpp).  A family whose state stops
 // fitting (sub-species capacity, reserved pool slots), or whose next decision needs exact arithmetic (scores inside
 // the guard band without the compatibility table), hands the REST of its births back to the host's walk.
 #include "kernels.cuh"
 
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace apt {
@@ -79,7 +88,7 @@ __host__ __device__ inline size_t fam_child_bytes (uint32_t K, uint32_t wq) {
 }
 __host__ __device__ inline size_t fam_fixed_bytes (uint32_t K, uint32_t cap) {
   const size_t MW = (cap + 31) / 32;
-  return 2 * MW * FT * 4 + size_t(K) * FT * 4 + size_t(FT) * 4 + 64 * 4 + 64;
+  return 2 * MW * FT * 4 + size_t(K) * FT * 4 + size_t(FT) * 4 + 96 * 4 + 64;
 }
 
 /// speciesMatchingScore (:456-478 / :430-452) of this thread's birth against sub-species c, representatives in order;
@@ -121,12 +130,17 @@ __device__ __forceinline__ float fam_score (const ScoreCfg &cfg, const FamState 
 // event kinds (the word every warp publishes: thread << 8 | kind; smaller = earlier)
 constexpr uint32_t EVK_FOUND = 1, EVK_ENTER = 2, EVK_STOP = 3;
 
-template <int WQ, int KIND, bool LUT, int NT>
+template <int WQ, int KIND, bool LUT, int NT, bool CLUSTER>
 __global__ void __launch_bounds__(NT, 1)
 resolve_families_kernel (FamilyArgs a) {
+  namespace cg = cooperative_groups;
   constexpr int FT = NT;                  // (shadows the sizing constant: everything below is per launch width)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t f = blockIdx.x, g = a.fam_group[f];
+  uint32_t crank = 0, csize = 1;          // this CTA's rank in the family's cluster, CTAs per family
+  if (CLUSTER) { cg::cluster_group cl = cg::this_cluster();  crank = cl.block_rank();  csize = cl.num_blocks(); }
+  auto cluster_sync = [&] (void) { if (CLUSTER) cg::this_cluster().sync(); else __syncthreads(); };
+  const uint32_t f = blockIdx.x / csize, g = a.fam_group[f];
+  const uint32_t gpos = crank * FT + uint32_t(tid);           // this thread's position among the births of a step
   const uint32_t K = a.pool.K, cap = a.cap, MW = (cap + 31) / 32;
   FamState fs;
   fs.K = K;  fs.cap = cap;  fs.MW = MW;  fs.T = FT;
@@ -144,7 +158,7 @@ resolve_families_kernel (FamilyArgs a) {
   fs.oDc = base;       base += K * FT * 4;
   fs.oEv = base;       base += FT * 4;
   base = (base + 7u) & ~7u;        // (64-bit totals live in the control words)
-  fs.oCtl = base;      base += 64 * 4;
+  fs.oCtl = base;      base += 96 * 4;      // 0..7 warps' events, 8..11 the event, 16 new slot, 20 births done, 32..35 totals, 40..71 the cluster's events (two sets)
   fs.oLut = (base + 15u) & ~15u;
   fs.lutG = a.cfg.lut;
   fs.lutS = LUT && a.lut_in_smem;
@@ -152,7 +166,7 @@ resolve_families_kernel (FamilyArgs a) {
   const uint32_t g0 = a.grp_off[g];
   const uint32_t nRej = a.rej_count[g];
   if (nRej == 0) {                        // nothing was rejected: the usual case outside radiations
-    if (threadIdx.x == 0) { a.fam_info[f] = make_uint4(0u, 0u, 0u, 0u); a.fam_stats[2 * size_t(f)] = 0ull; a.fam_stats[2 * size_t(f) + 1] = 0ull; }
+    if (threadIdx.x == 0 && crank == 0) { a.fam_info[f] = make_uint4(0u, 0u, 0u, 0u); a.fam_stats[2 * size_t(f)] = 0ull; a.fam_stats[2 * size_t(f) + 1] = 0ull; }
     return;
   }
   const uint32_t c0 = a.child_off[g], Cs = a.child_off[g + 1] - c0;     // sub-species at submission (host: Cs < cap)
@@ -200,6 +214,7 @@ resolve_families_kernel (FamilyArgs a) {
   __syncthreads();
 
   uint32_t C = Cs, nNew = 0, nDone = 0;           // uniform: sub-species now, founded here, births decided
+  uint32_t elect = 0;                             // which set of election words the next event uses (cluster)
   bool handedBack = false;
   unsigned long long branching = 0, comparisons = 0;        // this thread's births
   const uint32_t newSidBase = FAM_NEW_SID | (f * a.max_new);
@@ -212,11 +227,11 @@ resolve_families_kernel (FamilyArgs a) {
     for (uint32_t c = 0; c < Cs; c++) { nb++; nc += fs.fill(c); if (c == j) return; }
   };
 
-  for (uint32_t cb = 0; cb < nRej && !handedBack; cb += FT) {
-    const uint32_t nb = min(uint32_t(FT), nRej - cb);
-    const bool active = uint32_t(tid) < nb;
-    const uint32_t ord = active ? __ldg(a.rej_order + g0 + cb + tid) : 0u;
-    const uint32_t topFill = active ? __ldg(a.rej_fill + g0 + cb + tid) : 0u;
+  for (uint32_t cb = 0; cb < nRej && !handedBack; cb += FT * csize) {
+    const uint32_t nb = min(uint32_t(FT) * csize, nRej - cb);
+    const bool active = gpos < nb;
+    const uint32_t ord = active ? __ldg(a.rej_order + g0 + cb + gpos) : 0u;
+    const uint32_t topFill = active ? __ldg(a.rej_fill + g0 + cb + gpos) : 0u;
     const uint32_t b = ord & ORDER_INDEX_MASK, ccls = ord >> ORDER_CLASS_SHIFT;
     uint4 bw[WQ];
     float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
@@ -293,14 +308,23 @@ resolve_families_kernel (FamilyArgs a) {
       const uint32_t em = __ballot_sync(0xffffffffu, kind != 0u);
       const int first = em ? __ffs(em) - 1 : 0;
       const uint32_t firstKind = __shfl_sync(0xffffffffu, kind, first);
-      if (lane == 0) fs.ctl(warp) = em ? (((uint32_t(warp) * 32u + uint32_t(first)) << 8) | firstKind) : NONE;
+      if (lane == 0) fs.ctl(warp) = em ? (((crank * FT + uint32_t(warp) * 32u + uint32_t(first)) << 8) | firstKind) : NONE;
       __syncthreads();
       uint32_t event = NONE;
 #pragma unroll
       for (int w = 0; w < FT / 32; w++) event = min(event, fs.ctl(w));
+      if (CLUSTER) {
+        // the CTAs' earliest events meet in everybody's control words (40 + rank), one remote store per peer
+        // (two sets of words, used in turn: a CTA that runs ahead must not overwrite what a slower one still reads)
+        if (uint32_t(tid) < csize) *cg::this_cluster().map_shared_rank(&fs.ctl(40 + 16 * elect + crank), tid) = event;
+        cg::this_cluster().sync();
+        event = NONE;
+        for (uint32_t r = 0; r < csize; r++) event = min(event, fs.ctl(40 + 16 * elect + r));
+        elect ^= 1u;
+      }
       const uint32_t stop = event == NONE ? NONE : event >> 8;
       uint32_t evKind = event == NONE ? 0u : (event & 0xFFu);
-      if (mine && uint32_t(tid) < stop) {
+      if (mine && gpos < stop) {
         // final: joins sub-species j and leaves its enveloppe alone (:687-691)
         myAct = FAM_JOINED | (j << FAM_CHILD_SHIFT);
         uint32_t vb, vc;
@@ -311,9 +335,9 @@ resolve_families_kernel (FamilyArgs a) {
         mine = false;
       }
       if (event == NONE) break;
-      __syncthreads();                 // the final births above read the state the event below is about to change
+      cluster_sync();                  // the final births above read the state the event below is about to change
       // ---- the event: applied by its own thread, published through shared memory ----
-      if (uint32_t(tid) == stop) {
+      if (gpos == stop) {
         uint32_t jj = j, slot = than;
         if (evKind == EVK_FOUND && (nNew == a.max_new || C == cap)) evKind = EVK_STOP;     // no room: hand the rest back
         if (evKind == EVK_FOUND) {
@@ -361,13 +385,38 @@ resolve_families_kernel (FamilyArgs a) {
           a.out_slot[b] = int32_t(slot);
           mine = false;
         }
-        fs.ctl(8) = evKind;  fs.ctl(9) = jj;
+        fs.ctl(8) = evKind;  fs.ctl(9) = jj;  fs.ctl(11) = slot;
       }
-      __syncthreads();
+      const bool ownEvent = stop / FT == crank;               // (uniform in the CTA)
+      if (CLUSTER) {
+        // the event's CTA pushes what changed -- the sub-species' matrix, row minima, the new representative, fill, id --
+        // into the other CTAs' copies of the family
+        if (ownEvent) {
+          __syncthreads();
+          const uint32_t ek = fs.ctl(8), ej = fs.ctl(9), es = fs.ctl(11);
+          for (uint32_t r = 0; r < csize; r++) {
+            if (r == crank) continue;
+            unsigned char *peer = cg::this_cluster().map_shared_rank(fam_smem, r);
+            if (ek != EVK_STOP) {
+              for (uint32_t i = tid; i < K * K; i += FT) reinterpret_cast<float*>(peer + fs.oD)[ej * K * K + i] = fs.D(ej, i);
+              for (uint32_t i = tid; i < K; i += FT) reinterpret_cast<float*>(peer + fs.oMinB)[ej * K + i] = fs.minB(ej, i);
+              for (uint32_t v = tid; v < uint32_t(WQ); v += FT) reinterpret_cast<uint4*>(peer + fs.oReps)[(ej * K + es) * WQ + v] = fs.reps(ej, es, v, WQ);
+              if (tid == 0) {
+                reinterpret_cast<float4*>(peer + fs.oMeta)[ej * K + es] = fs.meta(ej, es);
+                reinterpret_cast<uint32_t*>(peer + fs.oFill)[ej] = fs.fill(ej);
+                reinterpret_cast<uint32_t*>(peer + fs.oSid)[ej] = fs.sid(ej);
+                reinterpret_cast<uint32_t*>(peer + fs.oChanged)[ej] = fs.changed(ej);
+              }
+            }
+            if (tid == 0) { reinterpret_cast<uint32_t*>(peer + fs.oCtl)[8] = ek;  reinterpret_cast<uint32_t*>(peer + fs.oCtl)[9] = ej; }
+          }
+        }
+        cg::this_cluster().sync();
+      } else __syncthreads();
       evKind = fs.ctl(8);
       const uint32_t jj = fs.ctl(9);
       if (evKind == EVK_STOP) { handedBack = true; break; }
-      nEv++;
+      if (ownEvent) nEv++;
       if (evKind == EVK_FOUND) { C++; nNew++; }
       // later births see the change: re-score that sub-species only
       if (mine) {
@@ -406,14 +455,43 @@ resolve_families_kernel (FamilyArgs a) {
   // ---- totals, per-sub-species counters, and the enveloppes go back to the pool ----
   atomicAdd(reinterpret_cast<unsigned long long*>(&fs.ctl(32)), branching);
   atomicAdd(reinterpret_cast<unsigned long long*>(&fs.ctl(34)), comparisons);
-  __syncthreads();
-  if (tid == 0) {
-    a.fam_info[f] = make_uint4(nDone, nNew, handedBack ? 1u : 0u, C);
-    a.fam_stats[2 * size_t(f)] = *reinterpret_cast<unsigned long long*>(&fs.ctl(32));
-    a.fam_stats[2 * size_t(f) + 1] = *reinterpret_cast<unsigned long long*>(&fs.ctl(34));
-  }
+  if (tid == 0) fs.ctl(20) = nDone;
+  cluster_sync();
   const uint32_t jo = a.fam_join_off[f];
-  for (uint32_t i = tid; i < 2 * C; i += FT) a.child_join[jo + i] = fs.join(i);
+  if (CLUSTER) {
+    // the CTAs' totals and per-sub-species counters are summed by rank 0, which also writes the enveloppes back (the copies
+    // are identical); the others stay until it has read them
+    if (crank == 0) {
+      cg::cluster_group cl = cg::this_cluster();
+      if (tid == 0) {
+        unsigned long long br = 0, cmp = 0;
+        uint32_t done = 0;
+        for (uint32_t r = 0; r < csize; r++) {
+          const uint32_t *pc = cl.map_shared_rank(&fs.ctl(0), r);
+          done += pc[20];
+          br += *reinterpret_cast<const unsigned long long*>(pc + 32);
+          cmp += *reinterpret_cast<const unsigned long long*>(pc + 34);
+        }
+        a.fam_info[f] = make_uint4(done, nNew, handedBack ? 1u : 0u, C);
+        a.fam_stats[2 * size_t(f)] = br;
+        a.fam_stats[2 * size_t(f) + 1] = cmp;
+      }
+      for (uint32_t i = tid; i < 2 * C; i += FT) {
+        uint32_t sum = 0;
+        for (uint32_t r = 0; r < csize; r++) sum += cl.map_shared_rank(&fs.join(0), r)[i];
+        a.child_join[jo + i] = sum;
+      }
+    }
+    cg::this_cluster().sync();
+    if (crank != 0) return;
+  } else {
+    if (tid == 0) {
+      a.fam_info[f] = make_uint4(nDone, nNew, handedBack ? 1u : 0u, C);
+      a.fam_stats[2 * size_t(f)] = *reinterpret_cast<unsigned long long*>(&fs.ctl(32));
+      a.fam_stats[2 * size_t(f) + 1] = *reinterpret_cast<unsigned long long*>(&fs.ctl(34));
+    }
+    for (uint32_t i = tid; i < 2 * C; i += FT) a.child_join[jo + i] = fs.join(i);
+  }
   for (uint32_t c = 0; c < C; c++) {
     const uint32_t ch = fs.changed(c);
     if (!ch) continue;
@@ -461,20 +539,45 @@ void launch_resolve_families (const FamilyArgs &a, cudaStream_t st) {
   size_t smem = ((fam_child_bytes(a.pool.K, wq) * a.cap + fam_fixed_bytes(a.pool.K, a.cap)) + 15) & ~size_t(15);
   b.lut_in_smem = lutBytes > 0;
   smem += lutBytes;
-  // few families (the first generations of a radiation: ONE family of 100 000 births) get 256 threads each
+  // few families (the first generations of a radiation: ONE family of 100 000 births) get 256 threads per CTA and a
+  // cluster of CTAs each: 16 (more than the portable 8: opted into, and checked against what the device can place), 8,
+  // 4 or 2 CTAs, as many as keep the clusters of all families on the chip at once
   const bool wide = a.n_fam <= 74;
-  auto go = [&] (auto kernel, int threads) {
+  static const int maxCluster = getenv("APT_FAMILY_CLUSTER") ? atoi(getenv("APT_FAMILY_CLUSTER")) : 16;
+  uint32_t want = 1;
+  if (wide) for (uint32_t c = 2; c <= uint32_t(std::max(1, maxCluster)) && c <= 16 && a.n_fam * c <= 148; c *= 2) want = c;
+  auto go = [&] (auto kernel, auto clustered, int threads) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kernel<<<a.n_fam, threads, smem, st>>>(b);
+    cudaFuncSetAttribute(clustered, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    uint32_t cl = want;
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute at[1];
+    lc.blockDim = dim3(threads);  lc.dynamicSmemBytes = smem;  lc.stream = st;  lc.attrs = at;  lc.numAttrs = 1;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    if (cl > 8) cudaFuncSetAttribute(clustered, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (; cl > 1; cl /= 2) {             // the largest cluster the device can schedule with this much shared memory
+      lc.gridDim = dim3(a.n_fam * cl);
+      at[0].val.clusterDim.x = cl;  at[0].val.clusterDim.y = 1;  at[0].val.clusterDim.z = 1;
+      int nClusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nClusters, clustered, &lc) == cudaSuccess && nClusters >= 1) break;
+      cudaGetLastError();
+    }
+    if (cl > 1) cudaLaunchKernelEx(&lc, clustered, b);
+    else kernel<<<a.n_fam, threads, smem, st>>>(b);
   };
   auto pick = [&] (auto wqc) {
     constexpr int WQ = decltype(wqc)::value;
     if (wide) {
-      if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true, 256>, 256); else go(resolve_families_kernel<WQ, 0, false, 256>, 256); }
-      else go(resolve_families_kernel<WQ, 1, false, 256>, 256);
+      if (a.cfg.kind == 0) {
+        if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true, 256, false>, resolve_families_kernel<WQ, 0, true, 256, true>, 256);
+        else go(resolve_families_kernel<WQ, 0, false, 256, false>, resolve_families_kernel<WQ, 0, false, 256, true>, 256);
+      } else go(resolve_families_kernel<WQ, 1, false, 256, false>, resolve_families_kernel<WQ, 1, false, 256, true>, 256);
     } else {
-      if (a.cfg.kind == 0) { if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true, 128>, 128); else go(resolve_families_kernel<WQ, 0, false, 128>, 128); }
-      else go(resolve_families_kernel<WQ, 1, false, 128>, 128);
+      want = 1;
+      if (a.cfg.kind == 0) {
+        if (a.cfg.use_lut) go(resolve_families_kernel<WQ, 0, true, 128, false>, resolve_families_kernel<WQ, 0, true, 128, false>, 128);
+        else go(resolve_families_kernel<WQ, 0, false, 128, false>, resolve_families_kernel<WQ, 0, false, 128, false>, 128);
+      } else go(resolve_families_kernel<WQ, 1, false, 128, false>, resolve_families_kernel<WQ, 1, false, 128, false>, 128);
     }
   };
   switch (wq) {

@@ -45,6 +45,21 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+def pinned_array(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (apt_host_alloc): what a host program keeps its encoded genomes and
+    result arrays in (INTEGRATION.md; the header binding's apt::PinnedVector) -- add_genomes then reads / writes it by
+    DMA, no staging copy.  Freed with the array."""
+    import weakref
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    check(lib().apt_host_alloc(max(n, 1), ctypes.byref(p)))
+    buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib().apt_host_free, p)
+    return arr
+
+
 class PhylogeneticTree:
     def __init__(self, kind: int, words: int, device: int = 0, flags: int = 0, **cfg):
         self.kind, self.words = kind, words

@@ -54,6 +54,9 @@ def main():
                          "output (tests/test_oracle.py), no O(#species) map copy per insertion: the one that can replay a whole stream")
     ap.add_argument("--check-json", action="store_true", help="also compare the final tree dump with the reference's")
     ap.add_argument("--flags", type=int, default=1)
+    ap.add_argument("--pageable", action="store_true",
+                    help="feed the genomes from ordinary (pageable) memory: the engine then stages them through its own page-locked "
+                         "buffer.  Default: the trace's genomes sit in page-locked memory (apt_host_alloc), as a host program's do")
     args = ap.parse_args()
     gen, cfg = CONFIGS[args.config]
     gen = dict(gen)
@@ -64,8 +67,12 @@ def main():
     t = synth.generate(**gen)
     pop = gen["pop"]
 
-    from apoget_b200.tree import PhylogeneticTree, INVALID
+    from apoget_b200.tree import PhylogeneticTree, INVALID, pinned_array
     tree = PhylogeneticTree(t.kind, t.words, flags=args.flags, **cfg)
+    payload, compat = t.payload, t.compat
+    if not args.pageable:
+        payload = pinned_array(t.payload.shape, t.payload.dtype);  payload[...] = t.payload
+        compat = pinned_array(t.compat.shape, t.compat.dtype);  compat[...] = t.compat
     sid_of = np.full(t.n_births, INVALID, dtype=np.uint32)
     per_gen, gen_rows = [], []
     for g in range(t.n_gens):
@@ -78,7 +85,7 @@ def main():
                np.where(hf, sid_of[np.where(hf, f, 0)], INVALID).astype(np.uint32)]
         tm0, cn0 = tree.timers(), tree.counters()
         t0 = time.perf_counter()
-        s, _, _ = tree.add_genomes(t.payload[b0:b1], t.compat[b0:b1], *ids)
+        s, _, _ = tree.add_genomes(payload[b0:b1], compat[b0:b1], *ids)
         per_gen.append(time.perf_counter() - t0)
         tm1, cn1 = tree.timers(), tree.counters()
         gen_rows.append([round(1e3 * per_gen[-1], 3)] +
@@ -91,7 +98,7 @@ def main():
         tree.step(g + 1, sid_of[t.alive_of(g)])
     st = tree.stats()
     out = {"config": args.config, "births": t.n_births, "gens": t.n_gens, "pop": pop, "species": st["next_sid"],
-           "width": st["width"], "comparisons": st["comparisons"], "branching": st["branching"],
+           "genomes_in": "pageable memory" if args.pageable else "page-locked memory", "width": st["width"], "comparisons": st["comparisons"], "branching": st["branching"],
            "cuda_seconds": sum(per_gen), "cuda_births_per_s": t.n_births / sum(per_gen),
            "cuda_births_per_s_last_gen": pop / per_gen[-1], "counters": tree.counters(), "timers": tree.timers(),
            "per_gen": {"columns": ["call_ms", "prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms", "stream_kernel_ms",
