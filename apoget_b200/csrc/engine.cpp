@@ -163,6 +163,21 @@ Engine::Engine (const apt_params &p) : p_(p) {
   streamOk_ = !(p.flags & APT_FLAG_NO_STREAM_KERNEL) && stream_kernel_supports(wp_, K_, p.env_crit)
               && (p.full_continuous || lutMode_);
   famOk_ = streamOk_ && childKernel_ && !(p.flags & APT_FLAG_NO_FAMILY_KERNEL) && family_kernel_supports(wp_, K_, p.env_crit);
+  // The runtime loads a kernel when it is first used (milliseconds for the big ones): the variants this tree's
+  // configuration selects are loaded now, not inside the first generations' passes.
+  if (streamOk_) {
+    StreamArgs a {};
+    a.pool = poolView();  a.cfg = scoreCfg();  a.crit = p.env_crit;  a.preload = 1;
+    a.max_stream = 0;     launch_resolve_streams(a, stream_);
+    a.max_stream = 4096;  launch_resolve_streams(a, stream_);          // (the wide variant of long streams)
+  }
+  if (famOk_) {
+    FamilyArgs f {};
+    f.pool = poolView();  f.cfg = scoreCfg();  f.crit = p.env_crit;  f.preload = 1;  f.cap = 12;
+    f.n_fam = 1;     launch_resolve_families(f, stream_);               // (few families: 256 threads, clusters)
+    f.n_fam = 1000;  launch_resolve_families(f, stream_);
+  }
+  cudaGetLastError();
 }
 
 Engine::~Engine (void) {

@@ -549,6 +549,7 @@ void launch_resolve_families (const FamilyArgs &a, cudaStream_t st) {
   auto go = [&] (auto kernel, auto clustered, int threads) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaFuncSetAttribute(clustered, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (a.preload) { cudaFuncAttributes fa;  cudaFuncGetAttributes(&fa, kernel);  cudaFuncGetAttributes(&fa, clustered);  return; }
     uint32_t cl = want;
     cudaLaunchConfig_t lc = {};
     cudaLaunchAttribute at[1];

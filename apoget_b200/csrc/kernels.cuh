@@ -129,6 +129,7 @@ struct StreamArgs {
   uint32_t *rej_fill = nullptr;   ///< same layout: the enveloppe fill each one's top-level score saw (Stats::comparisons)
   uint32_t *rej_count = nullptr;  ///< [n_groups] how many
   int lut_in_smem = 0;        ///< set by the launcher
+  int preload = 0;            ///< the launcher only makes the runtime load the kernel variant these arguments select (no launch)
   unsigned long long *prof = nullptr;   ///< optional [n_groups][12] per-stream timeline (APT_STREAM_PROF), see stream.cu
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);
@@ -188,6 +189,7 @@ struct FamilyArgs {
   uint32_t *new_founder;      ///< [n_fam][max_new] birth that founded the j-th new species
   uint32_t *new_slot;         ///< [n_fam][max_new] the pool slot it lives in
   int lut_in_smem = 0;
+  int preload = 0;            ///< as StreamArgs::preload
 };
 bool family_kernel_supports (uint32_t wp, uint32_t K, int crit);
 /// sub-species capacity of one family for this shape (0 = unsupported)

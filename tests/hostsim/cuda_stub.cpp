@@ -167,6 +167,7 @@ bool stream_kernel_supports (uint32_t wp, uint32_t, int crit) {
 
 // Plain sequential stand-in for resolve_streams_kernel (same inputs, outputs and write-back)
 void launch_resolve_streams (const StreamArgs &a, cudaStream_t) {
+  if (a.preload) return;
   const uint32_t K = a.pool.K, wp = a.pool.wp;
   const float FMAX = std::numeric_limits<float>::max();
   for (uint32_t g = 0; g < a.n_groups; g++) {
@@ -263,6 +264,7 @@ uint32_t family_capacity (uint32_t, uint32_t, const ScoreCfg&) { return 96; }   
 // Plain sequential stand-in for resolve_families_kernel (same inputs, outputs and write-back): the reference's
 // findBestDerived / insertInto / makeNode for the rejected births of a family, in order, on local copies.
 void launch_resolve_families (const FamilyArgs &a, cudaStream_t) {
+  if (a.preload) return;
   const uint32_t K = a.pool.K, wp = a.pool.wp;
   const float FMAX = std::numeric_limits<float>::max();
   struct Child { std::vector<uint32_t> reps; std::vector<float4> meta; std::vector<float> D; uint32_t k, sid, changed, join[2]; };
