@@ -291,7 +291,7 @@ uint32_t Engine::allocSlot (void) {
   if (!freeSlots_.empty()) { slot = freeSlots_.back(); freeSlots_.pop_back(); }
   else {
     slot = nSlots_++;
-    hPayload_.resize(size_t(nSlots_) * K_ * wp_, 0u);
+    hPayload_.resize(size_t(nSlots_) * K_ * wp_, true);
   }
   return slot;
 }
@@ -1938,7 +1938,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         if (famSlotsUsed_) {
           // the species founded on the device live in pool slots [famSlotBase_, +used): they become real now
           nSlots_ = famSlotBase_ + famSlotsUsed_;
-          hPayload_.resize(size_t(nSlots_) * K_ * wp_, 0u);
+          hPayload_.resize(size_t(nSlots_) * K_ * wp_, true);
         }
       }
       estRows_ = nRows + nRows / 4 + 64;

@@ -16,14 +16,18 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <initializer_list>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <set>
 #include <stdexcept>
@@ -93,6 +97,32 @@ struct PinBuf {
     p = q;  cap = ncap;
     noteAlloc("pinned", ncap * sizeof(T), t0);
   }
+};
+
+/// Host mirror of the pool's genome rows.  Grows by realloc: the C library remaps large blocks instead of copying them (a
+/// std::vector moves the old rows into a new block every time 10 000 species are founded in one pass).  New rows are
+/// zeroed in one sweep -- leaving them untouched was measured slower: the first touches then happen scattered in the walk.
+struct HostRows {
+  uint32_t *p = nullptr;
+  size_t n = 0, cap = 0;
+  HostRows (void) = default;
+  HostRows (const HostRows&) = delete;
+  HostRows& operator= (const HostRows&) = delete;
+  ~HostRows (void) { free(p); }
+  void resize (size_t m, bool zeroNew) {
+    if (m > cap) {
+      const size_t ncap = std::max<size_t>(std::max<size_t>(m, cap + cap / 2), size_t(1) << 16);
+      void *q = realloc(p, ncap * sizeof(uint32_t));
+      if (!q) throw std::bad_alloc();
+      p = static_cast<uint32_t*>(q);
+      if (zeroNew) memset(p + cap, 0, (ncap - cap) * sizeof(uint32_t));
+      cap = ncap;
+    }
+    n = m;
+  }
+  size_t size (void) const { return n; }
+  uint32_t& operator[] (size_t i) { return p[i]; }
+  const uint32_t& operator[] (size_t i) const { return p[i]; }
 };
 
 /// Fixed set of worker threads for the O(n) host loops of large chunks (grouping births into
@@ -236,7 +266,7 @@ private:
   std::vector<uint32_t> trimmedSids_;     // species removed by stillborn trimming since the binding last asked
 
   // ---- host mirror of the pool ----
-  std::vector<uint32_t> hPayload_;        // [slot][K][wp]
+  HostRows hPayload_;                     // [slot][K][wp]
   std::vector<uint32_t> freeSlots_;
   uint32_t nSlots_ = 0;
   std::vector<Species*> refresh_;         // species with stale device rows
