@@ -143,6 +143,8 @@ Engine::Engine (const apt_params &p) : p_(p) {
   cudaCheck(cudaEventCreate(&evS1_), "cudaEventCreate");
   cudaCheck(cudaEventCreate(&evF0_), "cudaEventCreate");
   cudaCheck(cudaEventCreate(&evF1_), "cudaEventCreate");
+  cudaCheck(cudaEventCreateWithFlags(&evG_, cudaEventDisableTiming), "cudaEventCreate");
+  cudaCheck(cudaStreamCreateWithFlags(&streamG_, cudaStreamNonBlocking), "cudaStreamCreate");
   // the device resolves streams for the default criteria; vote-count scoring needs the exact table
   // (a flipped vote cannot be seen from the score, so no guard band protects it)
   childKernel_ = !(p.flags & APT_FLAG_NO_CHILD_KERNEL);
@@ -157,6 +159,8 @@ Engine::Engine (const apt_params &p) : p_(p) {
     profile_ = getenv("APT_PROFILE") != nullptr;
     if (const char *e = getenv("APT_STREAM_PROF")) streamProf_ = e;
     if (const char *e = getenv("APT_DEVLIST_MIN")) devListMin_ = uint32_t(std::max(1, atoi(e)));
+    if (const char *e = getenv("APT_DEVGROUP_MIN")) devGroupMin_ = uint32_t(std::max(1, atoi(e)));
+    devGroupPageable_ = getenv("APT_DEVGROUP_PAGEABLE") != nullptr;
     if (const char *e = getenv("APT_LUT_MAX_BYTES")) lutMaxBytes_ = size_t(std::max(0ll, atoll(e)));
     if (nt > 1) pool_.reset(new WorkerPool(nt));
   }
@@ -194,6 +198,8 @@ Engine::~Engine (void) {
   if (evS1_) cudaEventDestroy(evS1_);
   if (evF0_) cudaEventDestroy(evF0_);
   if (evF1_) cudaEventDestroy(evF1_);
+  if (evG_) cudaEventDestroy(evG_);
+  if (streamG_) cudaStreamDestroy(streamG_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -282,7 +288,8 @@ void Engine::updateElligibilities (void) {
 /// sidSlot_ mirrors "the device holds a current copy of this species" (dev_fill > 0)
 void Engine::setStreamable (const Species *s, bool on) {
   if (sidSlot_.size() <= s->sid) sidSlot_.resize(std::max<size_t>(s->sid + 1, sidSlot_.size() * 2), INV);
-  sidSlot_[s->sid] = on ? s->slot : INV;
+  const uint32_t v = on ? s->slot : INV;
+  if (sidSlot_[s->sid] != v) { sidSlot_[s->sid] = v;  sidSlotDirty_ = true; }
 }
 
 uint32_t Engine::allocSlot (void) {
@@ -1096,7 +1103,7 @@ void Engine::settleFamilies (void) {
 /// Device-resident births: genome of a birth the stream kernel put into an enveloppe (it came back with the
 /// birth's distance row), or null when the birth is not such an entry
 const uint32_t* Engine::entryRowOf (uint32_t i) const {
-  if (birthGroup_[i] < 0) return nullptr;
+  if (bg_[i] < 0) return nullptr;
   const uint32_t act = hAct_.p[i];
   if (famResults_ && act == ACT_FALLTHROUGH && (hFamAct_.p[i] & FAM_CODE_MASK) >= FAM_ENTERED)
     return hRowPayload_.p + size_t(hFamRow_.p[i]) * wp_;       // entered a sub-species / founded one in the family pass
@@ -1430,6 +1437,120 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
 }
 
 
+/// The same grouping done by the device (launch_group_births): the id arrays go up, the per-species totals, the births
+/// outside the streams and (later, with the results) the birth -> stream table and the order list come back; the host
+/// only walks the species that have births.  Returns false when the pass has to be grouped on the host after all (a
+/// stream too long for the device-side sort).
+bool Engine::groupDevice (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream) {
+  const size_t NS = nodes_.size();
+  if (sidSlot_.size() < NS) { sidSlot_.resize(NS, INV);  sidSlotDirty_ = true; }
+  dSidSlot_.reserve(NS);
+  if (sidSlotDirty_ || dSidSlotN_ != NS) {
+    cudaCheck(cudaMemcpyAsync(dSidSlot_.p, sidSlot_.data(), NS * 4, cudaMemcpyHostToDevice, streamG_), "species table");
+    sidSlotDirty_ = false;  dSidSlotN_ = NS;
+  }
+  const double pg0 = profile_ ? now() : 0.;
+  if (profile_) cudaEventRecord(evK0_, streamG_);
+  dGrpKey_.reserve(n);  dOrder_.reserve(n);  dRestList_.reserve(n);
+  dSidStart_.reserve(NS);  dSidCursor_.reserve(NS);  dSidGidx_.reserve(NS);  dGrpInfo_.reserve(16);
+  hSidTotal_.reserve(NS);  hGrpInfo_.reserve(8);  hBirthGroup_.reserve(n);  hOrder_.reserve(n);  hRestList_.reserve(n);
+  // two sets of per-species counters (and of summary words) used in turn: the scan of one pass clears the set of the next,
+  // so that a steady pass needs no clearing launch; a set is cleared here when it is new or the species table grew
+  const uint32_t cur = grpFlip_, nxt = cur ^ 1u;
+  for (uint32_t q = 0; q < 2; q++) {
+    dSidTotal_[q].reserve(NS);
+    if (grpZeroedPtr_[q] != dSidTotal_[q].p) { grpZeroedPtr_[q] = dSidTotal_[q].p;  grpZeroed_[q] = 0; }
+  }
+  if (grpZeroed_[cur] < NS) {
+    cudaCheck(cudaMemsetAsync(dSidTotal_[cur].p, 0, NS * 4, streamG_), "stream counters clear");
+    grpZeroed_[cur] = NS;
+  }
+  if (!grpInfoReady_) { cudaCheck(cudaMemsetAsync(dGrpInfo_.p, 0, 16 * 4, streamG_), "grouping summary clear");  grpInfoReady_ = true; }
+  // page-locked id arrays are read by the kernel where they are; others (tests) go through a device copy
+  const uint32_t *kMsid = msid, *kFsid = fsid;
+  if (!idsPinned_) {
+    dMsid_.reserve(n);  dFsid_.reserve(n);
+    cudaCheck(cudaMemcpyAsync(dMsid_.p, msid, size_t(n) * 4, cudaMemcpyHostToDevice, streamG_), "mother species ids");
+    cudaCheck(cudaMemcpyAsync(dFsid_.p, fsid, size_t(n) * 4, cudaMemcpyHostToDevice, streamG_), "father species ids");
+    kMsid = dMsid_.p;  kFsid = dFsid_.p;
+  }
+  const uint32_t rootSid = (root_ && root_->sid < NS && nodes_[root_->sid] == root_ && sidSlot_[root_->sid] != INV) ? root_->sid : INV;
+  uint32_t *dInfo = dGrpInfo_.p + 8 * cur, *dInfoNext = dGrpInfo_.p + 8 * nxt;
+  hGrpInfo_.p[3] = 1u;  hGrpInfo_.p[0] = hGrpInfo_.p[2] = hGrpInfo_.p[4] = 0u;        // (a launch that fails leaves "group on the host")
+  launch_group_births(kMsid, kFsid, n, dSidSlot_.p, uint32_t(NS), rootSid, dGrpKey_.p, dSidTotal_[cur].p, dSidTotal_[nxt].p,
+                      dSidStart_.p, dSidCursor_.p, dSidGidx_.p, dInfo, dInfoNext, dOrder_.p, dRestList_.p, hSidTotal_.p, hGrpInfo_.p,
+                      hRestList_.p, hOrder_.p, hBirthGroup_.p, streamG_);
+  if (cudaGetLastError() != cudaSuccess) {      // (a cooperative launch the device cannot place: the host groups, now and later)
+    grpZeroed_[0] = grpZeroed_[1] = 0;  grpInfoReady_ = false;
+    devGroupMin_ = 0xFFFFFFFFu;
+    return false;
+  }
+  grpZeroed_[cur] = 0;  grpZeroed_[nxt] = NS;  grpFlip_ = nxt;
+  counters[4] += 1;
+  if (profile_) cudaEventRecord(evK1_, streamG_);
+  cudaCheck(cudaEventRecord(evG_, streamG_), "event record");
+  const double pg1 = profile_ ? now() : 0.;
+  cudaCheck(cudaEventSynchronize(evG_), "grouping");
+  if (profile_ && n >= parMin_) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, evK0_, evK1_);
+    fprintf(stderr, "group (device): enqueue %.3f wait %.3f ms; on the device %.3f ms\n", 1e3 * (pg1 - pg0), 1e3 * (now() - pg1), double(ms));
+  }
+  if (hGrpInfo_.p[3]) return false;
+  // streams in ascending species id (as groupParallel)
+  uint32_t off = 0;
+  for (size_t sid = 0; sid < NS; sid++) {
+    const uint32_t total = hSidTotal_.p[sid];
+    if (sid + 8 < NS && hSidTotal_.p[sid + 8] && nodes_[sid + 8]) {
+      __builtin_prefetch(nodes_[sid + 8], 1);  __builtin_prefetch(reinterpret_cast<const char*>(nodes_[sid + 8]) + 128, 1);
+    }
+    if (!total) continue;
+    Species *sp = nodes_[sid];
+    if (!sp) throw ApiError(APT_ERR_STATE, "device grouping: a stream of a species that does not exist");
+    sp->grp_epoch = chunkEpoch_;
+    sp->grp_index = uint32_t(grpSpecies_.size());
+    grpSpecies_.push_back(sp);  grpCount_.push_back(total);
+    if (sp->touch_epoch != touchEpoch_) { sp->touch_epoch = touchEpoch_; counters[8] += sp->dev_fill; }
+    sidGroup_[sid] = int32_t(sp->grp_index);
+    sidTouched_.push_back(uint32_t(sid));
+    off += total;
+    maxStream = std::max(maxStream, total);
+  }
+  nStream = off;
+  const uint32_t G = uint32_t(grpSpecies_.size());
+  if (G != hGrpInfo_.p[0] || off != hGrpInfo_.p[2]) throw ApiError(APT_ERR_STATE, "device grouping: inconsistent summary");
+  hGrpSlot_.reserve(G);  hGrpOff_.reserve(G + 1);  hGrpSid_.reserve(G);
+  uint32_t o2 = 0;
+  for (uint32_t g = 0; g < G; g++) {
+    hGrpSlot_.p[g] = grpSpecies_[g]->slot;  hGrpSid_.p[g] = grpSpecies_[g]->sid;
+    hGrpOff_.p[g] = o2;  o2 += grpCount_[g];
+  }
+  hGrpOff_.p[G] = o2;
+  // the rest (two parent species, unknown ids, species without a device copy): speculative pairs, in arrival order
+  const uint32_t nRest = std::min(hGrpInfo_.p[4], n);
+  std::sort(hRestList_.p, hRestList_.p + nRest);              // (appended with atomics on the device: any order)
+  for (uint32_t e = 0; e < nRest; e++) {
+    const uint32_t i = hRestList_.p[e];
+    if (i >= n) throw ApiError(APT_ERR_STATE, "device grouping: corrupt list");
+    const uint32_t m = msid[i], f = fsid[i];
+    Species *s0 = nullptr, *s1 = nullptr;
+    auto lookup = [&] (uint32_t sid) -> Species* { return (sid != INV && sid < NS) ? nodes_[sid] : nullptr; };
+    if (m == INV && f == INV) s0 = root_;
+    else if (f == INV || m == f) s0 = lookup(m);
+    else { s0 = lookup(m); s1 = lookup(f); }
+    if (s0) s0->pair_epoch = chunkEpoch_;
+    if (s1) s1->pair_epoch = chunkEpoch_;
+    PairRef pr { i, -1, -1 };
+    auto touch = [&] (Species *s) {
+      if (s->touch_epoch != touchEpoch_) { s->touch_epoch = touchEpoch_; counters[8] += s->dev_fill; }
+    };
+    if (s0 && s0->dev_fill) { pr.p0 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s0->slot; P++; touch(s0); }
+    if (s1 && s1->dev_fill) { pr.p1 = int64_t(P); hPairBirth_.p[P] = i; hPairSlot_.p[P] = s1->slot; P++; touch(s1); }
+    if (pr.p0 >= 0 || pr.p1 >= 0) pairOf_.push_back(pr);
+  }
+  return true;
+}
+
 void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat, const uint32_t *dPayload,
                        const uint32_t *gid, const uint32_t *mgid, const uint32_t *msid,
                        const uint32_t *fgid, const uint32_t *fsid, uint32_t *outSid, int32_t *outSlot,
@@ -1482,7 +1603,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     }
     birthsUploaded = true;
   };
-  if (!dPayload && n >= 4096 && nSlots_ > freeSlots_.size()) uploadBirths();
+  const bool tryDevGroup = streamOk_ && n >= devGroupMin_ && (idsPinned_ || devGroupPageable_) && nSlots_ > freeSlots_.size()
+                           && nodes_.size() <= std::min<size_t>(size_t(2) * n, 32768);
+  const bool earlyUpload = !dPayload && n >= 4096 && nSlots_ > freeSlots_.size();
+  if (earlyUpload) uploadBirths();
   // ... and so do the clears of the result arrays (they depend on n only): the device runs them under the grouping
   bool earlyClears = false;
   auto clearResults = [&] (void) {
@@ -1491,7 +1615,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     cudaCheck(cudaMemsetAsync(dAct_.p, 0, size_t(n) * 4, stream_), "act clear");
     earlyClears = true;
   };
-  if (streamOk_ && n >= 4096 && nSlots_ > freeSlots_.size()) clearResults();
+  const bool earlyClear = streamOk_ && n >= 4096 && nSlots_ > freeSlots_.size();
+  if (earlyClear) clearResults();
   mark("upload");
   // ---- prepare: classes; births with a single parent species join that species' stream, the
   //      others get (birth, species) pairs for the speculative scoring kernel ----
@@ -1531,10 +1656,23 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   }
   mark("classes");
   uint32_t maxStream = 0;
-  if (pool_ && n >= parMin_ && streamOk_ && nodes_.size() <= size_t(2) * n)
+  devGrouped_ = false;
+  bg_ = nullptr;
+  if (tryDevGroup) {
+    devGrouped_ = groupDevice(n, msid, fsid, P, nStream, maxStream);
+    if (devGrouped_) bg_ = hBirthGroup_.p;
+    else {                        // (handed back: whatever it booked is dropped)
+      P = 0;  nStream = 0;  maxStream = 0;  pairOf_.clear();  grpSpecies_.clear();  grpCount_.clear();
+      for (uint32_t sid: sidTouched_) if (sid < sidGroup_.size()) sidGroup_[sid] = -2;
+      sidTouched_.clear();
+    }
+  }
+  if (devGrouped_) {}
+  else if (pool_ && n >= parMin_ && streamOk_ && nodes_.size() <= size_t(2) * n)
     groupParallel(n, msid, fsid, P, nStream, maxStream);
   else
     groupSerial(n, msid, fsid, P, nStream, maxStream);
+  if (!bg_) bg_ = birthGroup_.data();
   mark("group");
   const uint32_t G = uint32_t(grpSpecies_.size());
   // sub-species of every stream's species, in the reference's visiting order (newest first, :506)
@@ -1659,7 +1797,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     memcpy(hGrpAll_.p + G, hGrpSid_.p, size_t(G) * 4);
     memcpy(hGrpAll_.p + 2 * size_t(G), hGrpOff_.p, (size_t(G) + 1) * 4);
     cudaCheck(cudaMemcpyAsync(dGrpAll_.p, hGrpAll_.p, (3 * size_t(G) + 1) * 4, cudaMemcpyHostToDevice, stream_), "groups");
-    cudaCheck(cudaMemcpyAsync(dOrder_.p, hOrder_.p, nStream * 4, cudaMemcpyHostToDevice, stream_), "order");
+    if (!devGrouped_) cudaCheck(cudaMemcpyAsync(dOrder_.p, hOrder_.p, nStream * 4, cudaMemcpyHostToDevice, stream_), "order");
     if (!earlyClears) clearResults();
     // (kept behind the copies on purpose: the copy-engine -> SM hand-over then sits in front of this 8-byte clear and
     // not between the two events that time the kernel)
@@ -1973,10 +2111,10 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     slow_.resize(total);  slowGrp_.resize(total);  slowAct_.resize(total);
     const uint32_t *list = hSlowList_.p;
     for (size_t q = 0; q < total; q++) {
-      if (q + 16 < total) __builtin_prefetch(&birthGroup_[list[2 * (q + 16)]]);
+      if (q + 16 < total) __builtin_prefetch(&bg_[list[2 * (q + 16)]]);
       const uint32_t i = list[2 * q];
       if (i >= n) throw ApiError(APT_ERR_STATE, "device list of unsettled births is corrupt");
-      const int32_t bg = birthGroup_[i];
+      const int32_t bg = bg_[i];
       slow_[q] = i;  slowGrp_[q] = bg;  slowAct_[q] = list[2 * q + 1];
       if (bg >= 0 && (list[2 * q + 1] & ACT_CODE_MASK) == ACT_ENTERED) grpState_[size_t(bg)].lastEnter = i;
     }
@@ -1997,7 +2135,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       auto &rest = parRest_[t];
       rest.clear();
       for (uint32_t i = lo; i < hi; i++) {
-        const int32_t bg = birthGroup_[i];
+        const int32_t bg = bg_[i];
         const uint32_t act = hAct_.p[i];
         // settled on the device: accepted with the enveloppe left alone -- at top level, or (family pass) by a sub-species
         const bool settled = bg >= 0 && (act == ACT_ACCEPTED ||
@@ -2182,13 +2320,13 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       // the births looked at are sparse: pull what the next ones touch into the cache ahead of time
       if (si + 12 < slow_.size()) {
         const uint32_t j = slow_[si + 12];
-        __builtin_prefetch(&birthGroup_[j]);  __builtin_prefetch(&hAct_.p[j]);
+        __builtin_prefetch(&bg_[j]);  __builtin_prefetch(&hAct_.p[j]);
         __builtin_prefetch(&gid[j]);  __builtin_prefetch(&mgid[j]);  __builtin_prefetch(&msid[j]);
         __builtin_prefetch(&fgid[j]);  __builtin_prefetch(&fsid[j]);  __builtin_prefetch(&compat[3 * size_t(j)]);
         if (payload) __builtin_prefetch(payload + size_t(j) * W_);
       }
       if (si + 6 < slow_.size()) {
-        const int32_t bg = birthGroup_[slow_[si + 6]];
+        const int32_t bg = bg_[slow_[si + 6]];
         if (bg >= 0) {
           const Species *sp = grpSpecies_[size_t(bg)];
           __builtin_prefetch(sp);  __builtin_prefetch(reinterpret_cast<const char*>(sp) + 64);
@@ -2196,7 +2334,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
         }
       }
       if (si + 3 < slow_.size()) {
-        const int32_t bg = birthGroup_[slow_[si + 3]];
+        const int32_t bg = bg_[slow_[si + 3]];
         if (bg >= 0) {
           const Species *sp = grpSpecies_[size_t(bg)];
           __builtin_prefetch(sp->reps.data(), 1);  __builtin_prefetch(sp->dist.data(), 1);
@@ -2206,8 +2344,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       Species *s0 = nullptr;
       uint32_t act = 0;
-      if (birthGroup_[i] >= 0) {
-        s0 = grpSpecies_[size_t(birthGroup_[i])];
+      if (bg_[i] >= 0) {
+        s0 = grpSpecies_[size_t(bg_[i])];
         if (s0->div_epoch == chunkEpoch_) s0 = nullptr;
         else {
           act = hAct_.p[i];
@@ -2282,8 +2420,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       // the births before the failure that joined one without changing it are booked one by one (their share of
       // Stats::comparisons / branching is only known per family and is not added)
       for (uint32_t i = 0; i < failed && i < n; i++) {
-        if (birthGroup_[i] < 0 || hAct_.p[i] != ACT_FALLTHROUGH || (hFamAct_.p[i] & FAM_CODE_MASK) != FAM_JOINED) continue;
-        Species *S = grpSpecies_[size_t(birthGroup_[i])];
+        if (bg_[i] < 0 || hAct_.p[i] != ACT_FALLTHROUGH || (hFamAct_.p[i] & FAM_CODE_MASK) != FAM_JOINED) continue;
+        Species *S = grpSpecies_[size_t(bg_[i])];
         const Family &F = fams_[size_t(grpFam_[S->grp_index])];
         const auto &founded = famFounded_[size_t(grpFam_[S->grp_index])];
         const uint32_t child = hFamAct_.p[i] >> FAM_CHILD_SHIFT;
@@ -2332,6 +2470,13 @@ void Engine::addGenomes (uint32_t n, const uint32_t *payload, const float *compa
   if (!onDevice && size_t(n) * W_ * 4 >= stageMin_) {
     cudaPointerAttributes a;
     payloadPinned_ = cudaPointerGetAttributes(&a, payload) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+  }
+  idsPinned_ = false;
+  if (n >= devGroupMin_ && streamOk_) {
+    cudaPointerAttributes a0, a1;
+    idsPinned_ = cudaPointerGetAttributes(&a0, msid) == cudaSuccess && a0.type == cudaMemoryTypeHost
+              && cudaPointerGetAttributes(&a1, fsid) == cudaSuccess && a1.type == cudaMemoryTypeHost;
     cudaGetLastError();
   }
   outPinned_ = false;
@@ -2619,6 +2764,7 @@ void Engine::fromJson (const std::string &text) {
       e.aliveSpecies_.clear();  e.refresh_.clear();  e.fillUpdates_.clear();  e.freeSlots_.clear();
       for (uint32_t s = e.nSlots_; s-- > 0; ) e.freeSlots_.push_back(s);       // every slot is free again
       std::fill(e.sidSlot_.begin(), e.sidSlot_.end(), INV);
+      e.sidSlotDirty_ = true;
     }
   } rollback { *this };
   step_ = j.at("_step").u32();

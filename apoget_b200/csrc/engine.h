@@ -338,6 +338,24 @@ private:
   uint32_t nFtRows_ = 0;                 // device-resident births: genomes of the rejected births fetched with the rows
   std::vector<int32_t> ftRowOfSlow_;
   int64_t curFtRow_ = -1;
+  // grouping of a pass's births on the device (launch_group_births): for callers whose id arrays are page-locked
+  DevBuf<uint32_t> dMsid_, dFsid_, dSidSlot_, dGrpKey_, dSidTotal_[2], dSidStart_, dSidCursor_, dSidGidx_, dGrpInfo_, dRestList_;
+  uint32_t grpFlip_ = 0;                     // which of the two counter sets the next grouping uses (its scan clears the other one)
+  size_t grpZeroed_[2] = { 0, 0 };           // leading entries of each set known to be zero
+  const uint32_t *grpZeroedPtr_[2] = { nullptr, nullptr };
+  bool grpInfoReady_ = false;
+  PinBuf<uint32_t> hSidTotal_, hGrpInfo_, hRestList_;
+  PinBuf<int32_t> hBirthGroup_;
+  cudaEvent_t evG_ = nullptr;
+  cudaStream_t streamG_ = nullptr;          // the grouping kernel runs beside the genomes' upload
+  bool sidSlotDirty_ = true;                 // sidSlot_ changed since it was last uploaded
+  size_t dSidSlotN_ = 0;
+  uint32_t devGroupMin_ = 4096;              // passes of at least this many births are grouped on the device (APT_DEVGROUP_MIN)
+  bool devGroupPageable_ = false;            // (tests) also when the id arrays are not page-locked (APT_DEVGROUP_PAGEABLE)
+  bool idsPinned_ = false, devGrouped_ = false;
+  uint32_t estRest_ = 0;
+  const int32_t *bg_ = nullptr;              // the pass's birth -> stream table: birthGroup_ (host grouping) or hBirthGroup_ (device)
+  bool groupDevice (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
   // the births of a pass the host has to look at, listed in arrival order by the device (launch_list_unsettled)
   DevBuf<uint32_t> dSlowBlk_, dSlowList_, dSlowCtr_;  PinBuf<uint32_t> hSlowList_;
   uint32_t estSlow_ = 0;

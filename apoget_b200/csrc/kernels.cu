@@ -10,6 +10,8 @@
 // shuffle reductions, and the order-sensitive float accumulation (`float avg += double c`,
 // :465-472) kept strictly sequential -- shuffles / shared memory only GATHER the k values.
 #include "kernels.cuh"
+
+#include <cooperative_groups.h>
 #include "criteria.h"
 
 #include <math_constants.h>
@@ -488,7 +490,9 @@ __global__ void gather_listed_rows_kernel (const uint32_t *__restrict__ src, con
 // scanning one result word per birth.  Two small launches: per-block counts, then the ordered write.
 constexpr uint32_t LIST_THREADS = 256, LIST_PER_THREAD = 8, LIST_PER_BLOCK = LIST_THREADS * LIST_PER_THREAD;
 
+template <int MODE>
 __device__ __forceinline__ bool birth_unsettled (uint32_t act, const uint32_t *fam_act, uint32_t i) {
+  if (MODE == 1) return act == 0xFFFFFFFFu;           // (grouping: `act` is the birth's stream key; none = outside the streams)
   if (act == ACT_ACCEPTED) return false;
   return !(fam_act && act == ACT_FALLTHROUGH && (fam_act[i] & FAM_CODE_MASK) == FAM_JOINED);
 }
@@ -505,6 +509,7 @@ __device__ __forceinline__ uint32_t block_sum (uint32_t v, uint32_t *warpSums) {
   return t;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(LIST_THREADS)
 unsettled_count_kernel (const uint32_t *act, const uint32_t *fam_act, uint32_t n, uint32_t *block_count) {
   __shared__ uint32_t warpSums[LIST_THREADS / 32];
@@ -512,11 +517,12 @@ unsettled_count_kernel (const uint32_t *act, const uint32_t *fam_act, uint32_t n
   uint32_t c = 0;
 #pragma unroll
   for (uint32_t j = 0; j < LIST_PER_THREAD; j++)
-    if (i0 + j < n) c += birth_unsettled(act[i0 + j], fam_act, i0 + j);
+    if (i0 + j < n) c += birth_unsettled<MODE>(act[i0 + j], fam_act, i0 + j);
   const uint32_t t = block_sum(c, warpSums);
   if (threadIdx.x == 0) block_count[blockIdx.x] = t;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(LIST_THREADS)
 unsettled_list_kernel (const uint32_t *act, const uint32_t *fam_act, uint32_t n, const uint32_t *block_count,
                        uint32_t *list, uint32_t *total) {
@@ -533,7 +539,7 @@ unsettled_list_kernel (const uint32_t *act, const uint32_t *fam_act, uint32_t n,
     a[j] = 0;
     if (i0 + j < n) {
       a[j] = act[i0 + j];
-      if (birth_unsettled(a[j], fam_act, i0 + j)) { flags |= 1u << j; c++; }
+      if (birth_unsettled<MODE>(a[j], fam_act, i0 + j)) { flags |= 1u << j; c++; }
     }
   }
   // exclusive scan of the threads' counts: inside the warp, then across the warps
@@ -561,8 +567,161 @@ void launch_list_unsettled (const uint32_t *act, const uint32_t *fam_act, uint32
                             uint32_t *list, uint32_t *total, cudaStream_t stream) {
   if (!n) return;
   const uint32_t blocks = list_unsettled_blocks(n);
-  unsettled_count_kernel<<<blocks, LIST_THREADS, 0, stream>>>(act, fam_act, n, block_count);
-  unsettled_list_kernel<<<blocks, LIST_THREADS, 0, stream>>>(act, fam_act, n, block_count, list, total);
+  unsettled_count_kernel<0><<<blocks, LIST_THREADS, 0, stream>>>(act, fam_act, n, block_count);
+  unsettled_list_kernel<0><<<blocks, LIST_THREADS, 0, stream>>>(act, fam_act, n, block_count, list, total);
+}
+
+// ---- grouping the births of a pass into per-species streams on the device -------------------------------------------
+// What Engine::groupParallel does on the host (a stable counting sort of the single-parent births by species id), for
+// callers whose id arrays sit in page-locked memory.  ONE cooperative launch, phases separated by grid barriers (separate
+// launches and copies cost more in gaps than the work itself: 90 us for 30 us of work):
+//   0. keys + per-species totals (global atomics); births outside the streams are appended to a list; the id arrays are
+//      read where they are (page-locked host memory, or a device copy)
+//   1. block 0 scans the species: where each stream starts, its rank among the streams, the summary -- written to the
+//      host directly -- and clears the counters of the NEXT call (two sets, used in turn)
+//   2. scatter through per-species cursors (order inside a stream arbitrary); totals and the rest list go to the host
+//   3. every stream is put back into arrival order (a block sorts one by birth index in shared memory; a stream too long
+//      for that makes the host group the pass instead) and written out for the stream kernel and for the host
+constexpr uint32_t GROUP_SORT_MAX = 2048, GROUP_THREADS = 256;
+
+struct GroupArgs {
+  const uint32_t *msid, *fsid;      ///< [n] (device-accessible)
+  uint32_t n;
+  const uint32_t *sid_slot;         ///< [ns]
+  uint32_t ns, root_sid;
+  uint32_t *key;                    ///< [n] scratch
+  uint32_t *total, *total_next;     ///< [ns] counters of this call (zero on entry) / of the next one (cleared here)
+  uint32_t *start, *cursor, *gidx;  ///< [ns]
+  uint32_t *info, *info_next;       ///< [8]
+  uint32_t *order;                  ///< [n] device: what the stream kernel reads
+  uint32_t *rest;                   ///< [n] device scratch: births outside the streams
+  // results for the host, written in place (page-locked memory)
+  uint32_t *h_total, *h_info, *h_rest, *h_order;
+  int32_t *h_birth_group;
+};
+
+__global__ void __launch_bounds__(GROUP_THREADS)
+group_births_kernel (GroupArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t sm[GROUP_SORT_MAX];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t gsize = gridDim.x * GROUP_THREADS, gtid = blockIdx.x * GROUP_THREADS + tid;
+
+  // ---- 0: keys, totals, rest list ----
+  for (uint32_t i = gtid; i < a.n; i += gsize) {
+    const uint32_t m = a.msid[i], f = a.fsid[i];
+    uint32_t k = 0xFFFFFFFFu;
+    if (f == 0xFFFFFFFFu || m == f) {
+      if (m == 0xFFFFFFFFu) k = a.root_sid;                               // primordial: the root's stream, contributes nothing
+      else if (m < a.ns && __ldg(a.sid_slot + m) != 0xFFFFFFFFu) k = m | ((m == f ? 2u : 1u) << ORDER_CLASS_SHIFT);
+    }
+    a.key[i] = k;
+    if (k != 0xFFFFFFFFu) atomicAdd(a.total + (k & ORDER_INDEX_MASK), 1u);
+    else a.rest[atomicAdd(a.info + 4, 1u)] = i;                           // (few: the host puts them back into arrival order)
+  }
+  grid.sync();
+
+  // ---- 1: block 0 scans the species ----
+  if (blockIdx.x == 0) {
+    uint32_t *wsum = sm, *wcnt = sm + 8, *wmax = sm + 16, *carry = sm + 24;      // carry: sum, count, max
+    if (tid < 3) carry[tid] = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < a.ns; base += GROUP_THREADS) {
+      const uint32_t sid = base + tid;
+      const uint32_t t = sid < a.ns ? a.total[sid] : 0u, nz = t ? 1u : 0u;
+      uint32_t is = t, ic = nz, mx = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, is, o), y = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= uint32_t(o)) { is += x; ic += y; }
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 31) { wsum[warp] = is; wcnt[warp] = ic; }
+      if (lane == 0) wmax[warp] = mx;
+      __syncthreads();
+      uint32_t os = carry[0], oc = carry[1];
+      for (uint32_t w = 0; w < warp; w++) { os += wsum[w]; oc += wcnt[w]; }
+      if (sid < a.ns) {
+        const uint32_t st = os + is - t;
+        a.start[sid] = st;  a.cursor[sid] = st;  a.gidx[sid] = oc + ic - nz;
+        a.total_next[sid] = 0u;                 // the NEXT call's counters: no clearing launch
+      }
+      __syncthreads();
+      if (tid == GROUP_THREADS - 1) { carry[0] = os + is; carry[1] = oc + ic; }
+      if (tid == 0) { uint32_t m = carry[2]; for (uint32_t w = 0; w < GROUP_THREADS / 32; w++) m = max(m, wmax[w]); carry[2] = m; }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const uint32_t over = carry[2] > GROUP_SORT_MAX ? 1u : 0u, nrest = a.info[4];
+      a.info[0] = carry[1];  a.info[1] = carry[2];  a.info[2] = carry[0];  a.info[3] = over;
+      a.h_info[0] = carry[1];  a.h_info[1] = carry[2];  a.h_info[2] = carry[0];  a.h_info[3] = over;  a.h_info[4] = nrest;
+    }
+    if (tid < 8) a.info_next[tid] = 0u;
+  }
+  grid.sync();
+
+  // ---- 2: scatter; totals and the rest list to the host ----
+  for (uint32_t i = gtid; i < a.n; i += gsize) {
+    const uint32_t k = a.key[i];
+    if (k == 0xFFFFFFFFu) { a.h_birth_group[i] = -1; continue; }
+    const uint32_t sid = k & ORDER_INDEX_MASK;
+    a.order[atomicAdd(a.cursor + sid, 1u)] = i | (k & ~ORDER_INDEX_MASK);
+    a.h_birth_group[i] = int32_t(a.gidx[sid]);
+  }
+  for (uint32_t sid = gtid; sid < a.ns; sid += gsize) a.h_total[sid] = a.total[sid];
+  { const uint32_t nrest = a.info[4];  for (uint32_t e = gtid; e < nrest; e += gsize) a.h_rest[e] = a.rest[e]; }
+  if (a.info[3]) return;                        // (uniform: the host groups this pass itself)
+  grid.sync();
+
+  // ---- 3: every stream back into arrival order ----
+  for (uint32_t sid = blockIdx.x; sid < a.ns; sid += gridDim.x) {
+    const uint32_t t = a.total[sid];
+    if (!t) continue;
+    uint32_t *o = a.order + a.start[sid], *ho = a.h_order + a.start[sid];
+    if (t == 1) { if (tid == 0) ho[0] = o[0]; continue; }
+    uint32_t p2 = 2;
+    while (p2 < t) p2 <<= 1;
+    for (uint32_t i = tid; i < p2; i += GROUP_THREADS) sm[i] = i < t ? o[i] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint32_t k = 2; k <= p2; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = tid; i < p2; i += GROUP_THREADS) {
+          const uint32_t x = i ^ j;
+          if (x > i) {
+            const uint32_t u = sm[i], v = sm[x];
+            // (padding entries are all ones: larger than any index; real entries compare by birth index)
+            const uint32_t ku = u == 0xFFFFFFFFu ? u : (u & ORDER_INDEX_MASK), kv = v == 0xFFFFFFFFu ? v : (v & ORDER_INDEX_MASK);
+            if ((ku > kv) == ((i & k) == 0)) { sm[i] = v; sm[x] = u; }
+          }
+        }
+        __syncthreads();
+      }
+    for (uint32_t i = tid; i < t; i += GROUP_THREADS) { const uint32_t v = sm[i];  o[i] = v;  ho[i] = v; }
+    __syncthreads();
+  }
+}
+
+void launch_group_births (const uint32_t *msid, const uint32_t *fsid, uint32_t n, const uint32_t *sid_slot, uint32_t ns,
+                          uint32_t root_sid, uint32_t *key, uint32_t *total, uint32_t *total_next, uint32_t *start, uint32_t *cursor,
+                          uint32_t *gidx, uint32_t *info, uint32_t *info_next, uint32_t *order, uint32_t *rest, uint32_t *h_total,
+                          uint32_t *h_info, uint32_t *h_rest, uint32_t *h_order, int32_t *h_birth_group, cudaStream_t stream) {
+  if (!n || !ns) return;
+  static int perSm = 0, sms = 0;
+  if (!perSm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, group_births_kernel, int(GROUP_THREADS), 0);
+    if (perSm < 1) perSm = 1;
+  }
+  GroupArgs a { msid, fsid, n, sid_slot, ns, root_sid, key, total, total_next, start, cursor, gidx, info, info_next, order, rest,
+                h_total, h_info, h_rest, h_order, h_birth_group };
+  // every block must be resident at once (grid barriers): at most what the device holds, at least enough for the births
+  const uint32_t want = std::max<uint32_t>((n + GROUP_THREADS * 4 - 1) / (GROUP_THREADS * 4), std::min<uint32_t>(ns, 1024u));
+  const uint32_t grid = std::max(1u, std::min<uint32_t>(want, uint32_t(sms) * uint32_t(std::min(perSm, 4))));
+  void *args[] = { &a };
+  cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(group_births_kernel), dim3(grid), dim3(GROUP_THREADS), args, 0, stream);
 }
 
 void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,

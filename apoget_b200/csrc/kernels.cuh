@@ -65,6 +65,19 @@ void launch_gather_rows (const uint32_t *src, const uint32_t *idx, uint32_t n, u
 uint32_t list_unsettled_blocks (uint32_t n);
 void launch_list_unsettled (const uint32_t *act, const uint32_t *fam_act, uint32_t n, uint32_t *block_count,
                             uint32_t *list, uint32_t *total, cudaStream_t stream);
+/// The births of a pass grouped into per-species streams on the device (what Engine::groupParallel does on the host), one
+/// cooperative launch.  msid / fsid: device-accessible (page-locked host memory is read in place).  key[n], start / cursor /
+/// gidx [ns], rest[n]: device scratch.  total[ns], info[8]: this call's counters, zero on entry; the kernel clears
+/// total_next / info_next, the sets the NEXT call passes as total / info.  order[n] (device): the streams, species in
+/// ascending id, births in arrival order, as the stream kernel reads them.  Written to page-locked host memory directly:
+/// h_total[sid] births per species, h_info = {streams, longest, births in streams, 1 when a stream was too long to be put
+/// back into arrival order here (nothing below is valid then), births outside the streams}, h_rest those births (in no
+/// particular order), h_order a copy of order, h_birth_group[i] the birth's stream (rank of its species among the
+/// species with births) or -1.
+void launch_group_births (const uint32_t *msid, const uint32_t *fsid, uint32_t n, const uint32_t *sid_slot, uint32_t ns,
+                          uint32_t root_sid, uint32_t *key, uint32_t *total, uint32_t *total_next, uint32_t *start, uint32_t *cursor,
+                          uint32_t *gidx, uint32_t *info, uint32_t *info_next, uint32_t *order, uint32_t *rest, uint32_t *h_total,
+                          uint32_t *h_info, uint32_t *h_rest, uint32_t *h_order, int32_t *h_birth_group, cudaStream_t stream);
 void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,
                                 uint32_t words, uint32_t *dst, cudaStream_t stream);
 

@@ -244,6 +244,12 @@ def main() -> None:
         pin_sid = torch.empty(pop, dtype=torch.int32).pin_memory()
         pin_slot = torch.empty(pop, dtype=torch.int32).pin_memory()
         pin_rep = torch.empty(pop, dtype=torch.int32).pin_memory()
+        pin_ids = [torch.empty(pop, dtype=torch.int32).pin_memory() for _ in range(5)]      # gid, mother gid / sid, father gid / sid
+
+        def pinned_ids(ids):
+            for dst, src in zip(pin_ids, ids):
+                dst.numpy()[:] = src.view(np.int32)
+            return [vp(x.data_ptr()) for x in pin_ids]
         dev_payload = torch.empty((pop, W), dtype=torch.int32, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         vp = ctypes.c_void_p
@@ -255,8 +261,7 @@ def main() -> None:
             # --- e2e: host buffers through the public C ABI -------------------------------------------
             pin_payload.numpy()[:] = trace.payload[b0:b1].view(np.int32)
             pin_compat.numpy()[:] = trace.compat[b0:b1]
-            ids = ids_for(g, sid_h)
-            args_h = (pop, vp(pin_payload.data_ptr()), vp(pin_compat.data_ptr()), [vp(x.ctypes.data) for x in ids],
+            args_h = (pop, vp(pin_payload.data_ptr()), vp(pin_compat.data_ptr()), pinned_ids(ids_for(g, sid_h)),
                       vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))      # marshalled outside the timed region
             flush.fill_(g & 0xFF)
             if world > 1 and step_barrier:
@@ -280,9 +285,8 @@ def main() -> None:
             finish_gen(tree_h, g, sid_h)
             # --- value: payloads already resident in HBM ------------------------------------------------
             dev_payload.copy_(pin_payload, non_blocking=True)
-            ids = ids_for(g, sid_d)
             args_d = (pop, vp(dev_payload.data_ptr()), vp(pin_compat.data_ptr()), vp(stream.cuda_stream),
-                      [vp(x.ctypes.data) for x in ids], vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
+                      pinned_ids(ids_for(g, sid_d)), vp(pin_sid.data_ptr()), vp(pin_slot.data_ptr()), vp(pin_rep.data_ptr()))
             flush.fill_((g + 1) & 0xFF)
             if world > 1 and step_barrier:
                 dist.barrier()
@@ -380,8 +384,13 @@ def main() -> None:
     # come back; two-parent births add their pair lists / scores
     n_streams = int(dc["stream_launches"] and width)
     ent = int(dc["stream_entries"] / args.steps)
-    h2d = pop * G + pop * 4 + (3 * n_streams + 1) * 4 + int(pairs) * 8
-    d2h = 3 * pop * 4 + n_streams * 16 + 8 + (ent + ent // 4 + 64) * 4 * K + int(pairs) * (4 + 4 * K)
+    # (id arrays in page-locked memory: the births are grouped into streams on the device -- the two species-id arrays go up
+    # instead of the order list; the per-species stream lengths, the birth -> stream table and the order list come back,
+    # and so does the list of the births the host has to look at: 8 bytes each, last step's count + 25 % + 64)
+    listed = ent + int(pairs)
+    h2d = pop * G + 2 * pop * 4 + (3 * n_streams + 1) * 4 + int(pairs) * 8
+    d2h = (3 * pop * 4 + n_streams * 16 + 8 + (ent + ent // 4 + 64) * 4 * K + int(pairs) * (4 + 4 * K)
+           + 2 * pop * 4 + int(width) * 4 + 24 + (listed + listed // 4 + 64) * 8)
     line = {
         "metric": METRIC, "value": births / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,

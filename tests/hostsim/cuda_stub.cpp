@@ -28,6 +28,7 @@ cudaError_t cudaEventDestroy (cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventCreate (cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
 cudaError_t cudaEventElapsedTime (float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 cudaError_t cudaEventRecord (cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize (cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaMalloc (void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocAsync (void **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
@@ -136,6 +137,45 @@ void launch_list_unsettled (const uint32_t *act, const uint32_t *fam_act, uint32
     if (!settled) { list[2 * size_t(at)] = i;  list[2 * size_t(at) + 1] = act[i];  at++; }
   }
   if (n) *total = at;
+}
+
+void launch_group_births (const uint32_t *msid, const uint32_t *fsid, uint32_t n, const uint32_t *sid_slot, uint32_t ns,
+                          uint32_t root_sid, uint32_t *key, uint32_t *total, uint32_t *total_next, uint32_t *start, uint32_t *cursor,
+                          uint32_t *gidx, uint32_t *info, uint32_t *info_next, uint32_t *order, uint32_t *rest, uint32_t *h_total,
+                          uint32_t *h_info, uint32_t *h_rest, uint32_t *h_order, int32_t *h_birth_group, cudaStream_t) {
+  if (!n || !ns) return;
+  uint32_t nr = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t m = msid[i], f = fsid[i];
+    uint32_t k = 0xFFFFFFFFu;
+    if (f == 0xFFFFFFFFu || m == f) {
+      if (m == 0xFFFFFFFFu) k = root_sid;
+      else if (m < ns && sid_slot[m] != 0xFFFFFFFFu) k = m | ((m == f ? 2u : 1u) << ORDER_CLASS_SHIFT);
+    }
+    key[i] = k;
+    if (k != 0xFFFFFFFFu) total[k & ORDER_INDEX_MASK]++;
+    else rest[nr++] = i;
+  }
+  // (the device appends with atomics: any order.  Reversed here, so that the host's sort is exercised)
+  for (uint32_t e = 0; e < nr; e++) h_rest[e] = rest[nr - 1 - e];
+  uint32_t run = 0, cnt = 0, mx = 0;
+  for (uint32_t s = 0; s < ns; s++) {
+    start[s] = cursor[s] = run;  gidx[s] = cnt;  h_total[s] = total[s];
+    run += total[s];  cnt += total[s] ? 1u : 0u;  mx = total[s] > mx ? total[s] : mx;
+    total_next[s] = 0;
+  }
+  info[0] = cnt;  info[1] = mx;  info[2] = run;  info[3] = mx > 2048 ? 1u : 0u;      // (the device kernel's sorting limit, so that the hand-back is exercised)
+  info[4] = nr;
+  for (int q = 0; q < 5; q++) h_info[q] = info[q];
+  for (int q = 0; q < 8; q++) info_next[q] = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t k = key[i];
+    if (k == 0xFFFFFFFFu) { h_birth_group[i] = -1;  continue; }
+    const uint32_t sid = k & ORDER_INDEX_MASK;
+    const uint32_t at = cursor[sid]++;
+    order[at] = h_order[at] = i | (k & ~ORDER_INDEX_MASK);
+    h_birth_group[i] = int32_t(gidx[sid]);
+  }
 }
 
 void launch_gather_listed_rows (const uint32_t *src, const uint32_t *list, const uint32_t *count, uint32_t max_entries,

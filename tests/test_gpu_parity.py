@@ -70,6 +70,17 @@ def test_tree_with_the_device_made_list_of_unsettled_births(name, monkeypatch):
     _compare(name)
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_tree_with_births_grouped_on_the_device(name, monkeypatch):
+    """Large batches whose id arrays are page-locked are grouped into per-species streams by the device
+    (launch_group_births: keys, scan, scatter, per-stream sort) instead of the host's counting sort; forced on for the
+    golden cases' small batches and ordinary arrays."""
+    monkeypatch.setenv("APT_DEVGROUP_MIN", "1")
+    monkeypatch.setenv("APT_DEVGROUP_PAGEABLE", "1")
+    monkeypatch.setenv("APT_DEVLIST_MIN", "1")
+    _compare(name)
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c4_b4096_k10"])
 def test_tree_generic_compat_path(name):
     """Device exp() instead of the libm-built table: decisions must still be identical."""

@@ -159,6 +159,9 @@ def test_randomised_traces_against_oracle(hostsim, seed, tmp_path, monkeypatch):
     list of births the host looks at comes from the device-side pass, as it does for large batches.)"""
     if seed % 2:
         monkeypatch.setenv("APT_DEVLIST_MIN", "1")
+    if seed % 4 >= 2:
+        monkeypatch.setenv("APT_DEVGROUP_MIN", "1")         # births grouped into streams by the device-side pass
+        monkeypatch.setenv("APT_DEVGROUP_PAGEABLE", "1")
     rng = np.random.default_rng(1000 + seed)
     K = int(rng.integers(1, 7))
     t = synth.generate(kind=synth.BITS, words=int(rng.choice([1, 2, 4, 8])), pop=int(rng.integers(30, 160)),
@@ -207,6 +210,9 @@ def test_radiations_resolved_by_the_family_pass(hostsim, seed, tmp_path, monkeyp
         monkeypatch.setenv("APT_HOST_THREADS", "3")
     if seed % 2 == 0:
         monkeypatch.setenv("APT_DEVLIST_MIN", "1")      # device-made list of unsettled births, re-made after the family pass
+    if seed % 4 == 1:
+        monkeypatch.setenv("APT_DEVGROUP_MIN", "1")
+        monkeypatch.setenv("APT_DEVGROUP_PAGEABLE", "1")
     path = str(tmp_path / "t.trace")
     synth.write_trace(path, t)
     o = oracle.Oracle(t.kind, t.words, **cfg)
@@ -267,6 +273,12 @@ def test_parallel_host_paths(hostsim, name, monkeypatch):
     _compare(hostsim, name)
     monkeypatch.setenv("APT_DEVLIST_MIN", "1")
     _compare(hostsim, name)
+    # ... and with the births grouped into streams by the device-side pass (launch_group_births; page-locked id arrays
+    # in production, any arrays under this test switch)
+    monkeypatch.setenv("APT_DEVGROUP_MIN", "1")
+    monkeypatch.setenv("APT_DEVGROUP_PAGEABLE", "1")
+    t = _compare(hostsim, name)
+    assert t.counters()["kernel_launches"] > 0
 
 
 @pytest.mark.parametrize("name", ["c2_b256_k10", "ragged_b96_k3", "c3_f32x64_k10"])
