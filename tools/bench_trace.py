@@ -100,7 +100,11 @@ def main():
     out = {"config": args.config, "births": t.n_births, "gens": t.n_gens, "pop": pop, "species": st["next_sid"],
            "genomes_in": "pageable memory" if args.pageable else "page-locked memory", "width": st["width"], "comparisons": st["comparisons"], "branching": st["branching"],
            "cuda_seconds": sum(per_gen), "cuda_births_per_s": t.n_births / sum(per_gen),
-           "cuda_births_per_s_last_gen": pop / per_gen[-1], "counters": tree.counters(), "timers": tree.timers(),
+           "cuda_births_per_s_last_gen": pop / per_gen[-1],
+           # first-use cost: growth of the engine's device / page-locked buffers inside the calls (a long simulation pays it once)
+           "buffer_growth_seconds": tree.timers()["alloc_s"],
+           "cuda_births_per_s_excl_buffer_growth": t.n_births / max(1e-9, sum(per_gen) - tree.timers()["alloc_s"]),
+           "counters": tree.counters(), "timers": tree.timers(),
            "per_gen": {"columns": ["call_ms", "prepare_ms", "device_wait_ms", "commit_ms", "refresh_ms", "stream_kernel_ms",
                                    "family_kernel_ms", "alloc_ms", "device_passes", "host_scores", "stream_entries"], "rows": gen_rows}}
 
