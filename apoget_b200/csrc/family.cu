@@ -543,7 +543,8 @@ void launch_resolve_families (const FamilyArgs &a, cudaStream_t st) {
   // cluster of CTAs each: 16 (more than the portable 8: opted into, and checked against what the device can place), 8,
   // 4 or 2 CTAs, as many as keep the clusters of all families on the chip at once
   const bool wide = a.n_fam <= 74;
-  static const int maxCluster = getenv("APT_FAMILY_CLUSTER") ? atoi(getenv("APT_FAMILY_CLUSTER")) : 16;
+  const char *env = getenv("APT_FAMILY_CLUSTER");                // (read per launch: tests switch it)
+  const int maxCluster = env ? atoi(env) : 16;
   uint32_t want = 1;
   if (wide) for (uint32_t c = 2; c <= uint32_t(std::max(1, maxCluster)) && c <= 16 && a.n_fam * c <= 148; c *= 2) want = c;
   auto go = [&] (auto kernel, auto clustered, int threads) {

@@ -23,7 +23,10 @@
 #include "kernels.cuh"
 #include "criteria.h"
 
+#include <cooperative_groups.h>
 #include <math_constants.h>
+#include <algorithm>
+#include <cstdlib>
 
 namespace apt {
 
@@ -294,7 +297,7 @@ __device__ __noinline__ uint32_t criterion_other (int crit, uint32_t oD, uint32_
 __host__ __device__ inline size_t stream_smem (uint32_t K, uint32_t wq, uint32_t T, bool ktConst = false) {
   (void) ktConst;
   return size_t(K) * T * 8 + size_t(K + T / 32) * wq * 16 + size_t(K + T / 32) * 16 + size_t(K) * K * 4 + size_t(K) * 4
-       + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + size_t(T) * 4 + 64 * 4;
+       + size_t(K) * T * 4 + size_t(K + 1) * T * 4 + size_t(T) * 4 + 160 * 4;
 }
 
 __device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
@@ -303,13 +306,24 @@ __device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile("pref
 constexpr uint32_t EV_TID_SHIFT = 8, EV_UNCERTAIN = 0x80u, EV_SLOT_MASK = 0x3Fu;
 
 // 7 CTAs of 4 warps per SM keep 1 000 streams in one wave on 148 SMs (register-resident variant: <= 72 registers)
-template <int WQ, int KIND, bool LUT, int NW, int KT, bool CRITX = false>
+//
+// CLUSTER: one very long stream (a species that holds all the births of a pass) spread over the CTAs of a thread-block
+// cluster, as resolve_families_kernel does (family.cu): every CTA keeps its own copy of the enveloppe, a step decides
+// T births per CTA (position in the step = CTA rank * T + thread), the earliest event is elected across the cluster
+// through distributed shared memory, and its CTA pushes the new representative and the entering birth's distances
+// into the other copies.
+template <int WQ, int KIND, bool LUT, int NW, int KT, bool CRITX = false, bool CLUSTER = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 && KT > 0 && WQ <= 2) ? 7 : 1)
 resolve_streams_kernel (StreamArgs a) {
+  namespace cg = cooperative_groups;
   constexpr uint32_t T = NW * 32;
   constexpr uint32_t NONE = 0xFFFFFFFFu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t g = blockIdx.x;
+  uint32_t crank = 0, csize = 1;
+  if (CLUSTER) { cg::cluster_group cl = cg::this_cluster();  crank = cl.block_rank();  csize = cl.num_blocks(); }
+  const uint32_t g = blockIdx.x / csize;
+  const uint32_t gpos = crank * T + uint32_t(tid);            // this thread's position among the births of a step
+  const uint32_t TS = T * csize;                               // births per step
   const uint32_t K = KT ? uint32_t(KT) : a.pool.K;
   uint32_t base = 0;
   WarpState ws;
@@ -322,8 +336,9 @@ resolve_streams_kernel (StreamArgs a) {
   ws.od = base;        base += K * T * 4;
   ws.oPre = base;      base += (K + 1) * T * 4;
   ws.oEv = base;       base += T * 4;
-  ws.oCtl = base;      base += 64 * 4;
-  // ws.ctl(0..NW): event word per warp; ws.ctl(33): first output row of the step; ws.ctl(36..39): counters
+  ws.oCtl = base;      base += 160 * 4;
+  // ws.ctl(0..NW): event word per warp; ws.ctl(33): first output row of the step; ws.ctl(36..39): counters;
+  // cluster: ws.ctl(64..95) the CTAs' events (two sets), ws.ctl(96..111) their rejected births, ws.ctl(112..143) the entering birth's distances
   ws.oLut = (base + 15u) & ~15u;
   ws.lutG = a.cfg.lut;
   ws.lutS = LUT && a.lut_in_smem;
@@ -335,7 +350,7 @@ resolve_streams_kernel (StreamArgs a) {
   // optional timeline of this stream (development aid, APT_STREAM_PROF): {globaltimer ns at start, SM clock at
   // start, after the enveloppe is loaded, after the first births are scored, at the end, events, steps, SM id,
   // cycles between barriers on the score/decide side, on the enveloppe-update side}
-  unsigned long long *prof = a.prof ? a.prof + size_t(g) * 16 : nullptr;
+  unsigned long long *prof = (a.prof && crank == 0) ? a.prof + size_t(g) * 16 : nullptr;
   uint32_t profEvents = 0, profSteps = 0;
   long long profA = 0, profB = 0, profT = 0;     // cycles between barriers: score/decide side, enveloppe update side
   if (prof && tid == 0) {
@@ -348,7 +363,7 @@ resolve_streams_kernel (StreamArgs a) {
   const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
   const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
   const uint4 *birthRows = reinterpret_cast<const uint4*>(a.b_payload);
-  uint32_t ordNext = (g0 + tid < g1) ? __ldg(a.order + g0 + tid) : 0u;
+  uint32_t ordNext = (g0 + gpos < g1) ? __ldg(a.order + g0 + gpos) : 0u;
   uint32_t k = min(__ldg(a.pool.fill + slot), K);
   for (uint32_t i = tid; i < K * WQ; i += T) ws.reps(i) = poolRows[i];          // rows past the fill are never read
   for (uint32_t i = tid; i < K; i += T) ws.rmeta(i) = a.pool.cmeta[size_t(slot) * K + i];
@@ -367,7 +382,7 @@ resolve_streams_kernel (StreamArgs a) {
   if (tid < 4) ws.ctl(36 + tid) = 0;
   uint4 bw[WQ];
   float4 bm = make_float4(0.f, 1.f, 1.f, 0.f);
-  if (g0 + tid < g1) {
+  if (g0 + gpos < g1) {
     const uint32_t b = ordNext & ORDER_INDEX_MASK;
 #pragma unroll
     for (int v = 0; v < WQ; v++) bw[v] = __ldg(birthRows + size_t(b) * WQ + v);
@@ -400,9 +415,10 @@ resolve_streams_kernel (StreamArgs a) {
   bool aborted = false;
   uint32_t nAcc0 = 0, nAcc1 = 0, nAcc2 = 0;     // per thread: accepted, enveloppe unchanged, by contribution class
 
-  for (uint32_t cb = g0; cb < g1 && !aborted; cb += T) {
-    const uint32_t nb = min(T, g1 - cb);
-    const bool active = uint32_t(tid) < nb;
+  uint32_t elect = 0;           // which set of election words the next event uses (cluster)
+  for (uint32_t cb = g0; cb < g1 && !aborted; cb += TS) {
+    const uint32_t nb = min(TS, g1 - cb);
+    const bool active = gpos < nb;
     const uint32_t ord = ordNext;
     const uint32_t b = ord & ORDER_INDEX_MASK, ccls = ord >> ORDER_CLASS_SHIFT;
     if (cb != g0) {
@@ -417,8 +433,8 @@ resolve_streams_kernel (StreamArgs a) {
     }
     // the next step's births start their way up from HBM while this step is resolved
     ordNext = 0u;
-    if (cb + T + tid < g1) {
-      ordNext = __ldg(a.order + cb + T + tid);
+    if (cb + TS + gpos < g1) {
+      ordNext = __ldg(a.order + cb + TS + gpos);
       const char *nx = reinterpret_cast<const char*>(birthRows + size_t(ordNext & ORDER_INDEX_MASK) * WQ);
 #pragma unroll
       for (int o = 0; o < WQ * 16; o += 128) prefetch_l2(nx + o);
@@ -476,12 +492,12 @@ resolve_streams_kernel (StreamArgs a) {
       const uint32_t em = __ballot_sync(0xffffffffu, uncertain || modifies);
       if (em) {
         const int first = __ffs(em) - 1;
-        const uint32_t word = (uint32_t(tid) << EV_TID_SHIFT) | (uncertain ? EV_UNCERTAIN : (than & EV_SLOT_MASK));
+        const uint32_t word = (gpos << EV_TID_SHIFT) | (uncertain ? EV_UNCERTAIN : (than & EV_SLOT_MASK));
         const uint32_t w0 = __shfl_sync(0xffffffffu, word, first);
         if (lane == 0) ws.ctl(warp) = w0;
         // the warp's candidate shows its genome before the barrier: should it be the event, the later births measure
         // it at once, while warp 0 updates the matrix (nobody waits for the owner to publish it after the barrier)
-        if (lane == first && !uncertain) {
+        if (!CLUSTER && lane == first && !uncertain) {
 #pragma unroll
           for (int v = 0; v < WQ; v++) ws.reps((K + warp) * WQ + v) = bw[v];
           ws.rmeta(K + warp) = bm;
@@ -492,8 +508,17 @@ resolve_streams_kernel (StreamArgs a) {
       uint32_t event = NONE;
 #pragma unroll
       for (int w = 0; w < NW; w++) event = min(event, ws.ctl(w));
+      if (CLUSTER) {
+        // the CTAs' earliest events meet in everybody's control words (two sets used in turn: a CTA that runs ahead
+        // must not overwrite what a slower one still reads)
+        if (uint32_t(tid) < csize) *cg::this_cluster().map_shared_rank(&ws.ctl(64 + 16 * elect + crank), tid) = event;
+        cg::this_cluster().sync();
+        event = NONE;
+        for (uint32_t r = 0; r < csize; r++) event = min(event, ws.ctl(64 + 16 * elect + r));
+        elect ^= 1u;
+      }
       const uint32_t stop = event == NONE ? NONE : event >> EV_TID_SHIFT;
-      if (mine && uint32_t(tid) < stop) {           // final: every earlier decision stands
+      if (mine && gpos < stop) {                    // final: every earlier decision stands
         myAct = accept ? ACT_ACCEPTED : ACT_FALLTHROUGH;
         rejected = !accept;
         myK = k;                                    // the enveloppe fill this birth's top-level score saw
@@ -501,7 +526,7 @@ resolve_streams_kernel (StreamArgs a) {
       }
       if (event == NONE) break;
       if (event & EV_UNCERTAIN) {                     // the host takes the stream over from here
-        if (uint32_t(tid) == stop) myAct = ACT_UNCERTAIN;
+        if (gpos == stop) myAct = ACT_UNCERTAIN;
         aborted = true;
         break;
       }
@@ -510,16 +535,34 @@ resolve_streams_kernel (StreamArgs a) {
       const bool append = (k < K);
       const uint32_t kOld = k;
       if (append) k++;
-      if (uint32_t(tid) == stop) {
+      const bool ownEvent = !CLUSTER || stop / T == crank;       // (uniform in the CTA)
+      if (gpos == stop) {
 #pragma unroll
         for (int v = 0; v < WQ; v++) ws.reps(sl * WQ + v) = bw[v];
         ws.rmeta(sl) = bm;
         myAct = ACT_ENTERED | (append ? 0u : ACT_REPLACED) | (sl << ACT_SLOT_SHIFT);
         myEv = nEv;
-        ws.ev(nEv) = (stop << 8) | kOld;             // whose distances are the row, and how many
+        ws.ev(nEv) = (uint32_t(tid) << 8) | kOld;    // whose distances are the row, and how many
         mine = false;
       }
-      nEv++;
+      if (ownEvent) nEv++;
+      if (CLUSTER) {
+        // the event's CTA pushes the new representative into the other copies of the enveloppe, and the entering birth's
+        // distances (the new row / column of the matrix) into everybody's, its own included
+        if (ownEvent) {
+          __syncthreads();
+          const uint32_t ls = stop - crank * T;
+          for (uint32_t r = 0; r < csize; r++) {
+            unsigned char *peer = cg::this_cluster().map_shared_rank(apt_smem, r);
+            if (r != crank) {
+              for (uint32_t v = tid; v < uint32_t(WQ); v += T) reinterpret_cast<uint4*>(peer + ws.oReps)[sl * WQ + v] = ws.reps(sl * WQ + v);
+              if (tid == 0) reinterpret_cast<float4*>(peer + ws.oRmeta)[sl] = ws.rmeta(sl);
+            }
+            for (uint32_t j = tid; j < K; j += T) reinterpret_cast<float*>(peer + ws.oCtl)[112 + j] = ws.d(j * T + ls);
+          }
+        }
+        cg::this_cluster().sync();
+      }
       // the entering birth's distances are the new row / column sl of the matrix (:676-677 / :712-715).
       // Lane r of warp 0 owns row r (only its column sl changes), one lane of warp 1 owns row sl (the birth's
       // own distances): no thread needs another's writes for its new minimum.  Straight-line code, loads
@@ -528,14 +571,15 @@ resolve_streams_kernel (StreamArgs a) {
         // bit strings: warp 0 does all rows in one instruction stream (lane sl: the birth's own row), because the
         // rows' minima meet in a warp reduction right after (criterion_maxMinDist_int's keys)
         if (warp == 0) {
-          const uint32_t aEnt = ws.sb + ws.od + stop * 4;
+          // (cluster: the entering birth's distances were pushed into the control words; else they are its thread's column)
+          const uint32_t aEnt = CLUSTER ? ws.sb + ws.oCtl + 112 * 4 : ws.sb + ws.od + stop * 4, sEnt = CLUSTER ? 4u : T * 4u;
           const uint32_t r = min(uint32_t(tid), K - 1u), aRow = ws.sb + ws.oD + r * K * 4;
           const bool row = uint32_t(tid) < k, own = uint32_t(tid) == sl;
-          const float dr = lds_f32(aEnt + r * T * 4);
+          const float dr = lds_f32(aEnt + r * sEnt);
           float m = FMAX;
 #pragma unroll (KT ? KT : 1)
           for (uint32_t j = 0; j < K; j++) {
-            const float e = lds_f32(aEnt + j * T * 4);          // columns past kOld hold stale values: masked
+            const float e = lds_f32(aEnt + j * sEnt);           // columns past kOld hold stale values: masked
             const float w = lds_f32(aRow + j * 4);
             const float v = own ? ((j == sl || j >= kOld) ? FMAX : e) : (j == sl ? dr : w);
             if (own) ws.D(sl * K + j) = v;
@@ -549,10 +593,10 @@ resolve_streams_kernel (StreamArgs a) {
           if (lane == 0) { ws.ctl(34) = k1;  ws.ctl(35) = k2; }
         }
       } else {
-        const uint32_t aEnt = ws.sb + ws.od + stop * 4;
+        const uint32_t aEnt = CLUSTER ? ws.sb + ws.oCtl + 112 * 4 : ws.sb + ws.od + stop * 4, sEnt = CLUSTER ? 4u : T * 4u;
         if (uint32_t(tid) < k && uint32_t(tid) != sl) {
           const uint32_t r = tid, aRow = ws.sb + ws.oD + r * K * 4;
-          const float dr = lds_f32(aEnt + r * T * 4);
+          const float dr = lds_f32(aEnt + r * sEnt);
           float m = FMAX;
 #pragma unroll (KT ? KT : 1)
           for (uint32_t j = 0; j < K; j++) {
@@ -565,7 +609,7 @@ resolve_streams_kernel (StreamArgs a) {
           float m = FMAX;
 #pragma unroll (KT ? KT : 1)
           for (uint32_t j = 0; j < K; j++) {
-            const float e = lds_f32(aEnt + j * T * 4);          // columns past kOld hold stale values: masked
+            const float e = lds_f32(aEnt + j * sEnt);           // columns past kOld hold stale values: masked
             const float v = (j == sl || j >= kOld) ? FMAX : e;
             ws.D(sl * K + j) = v;
             m = fminf(m, v);
@@ -576,7 +620,7 @@ resolve_streams_kernel (StreamArgs a) {
       // later births see the new representative: re-measure that slot only (from the winner's staging row: the matrix
       // update above and this run side by side), the score follows from the change of that one compatibility
       if (mine) {
-        sumC += measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, K + (stop >> 5), sl, tid, !append);
+        sumC += measure<WQ, KIND, LUT, KT>(a.cfg, bw, bm, ws, ln, CLUSTER ? sl : K + (stop >> 5), sl, tid, !append);
         dirtyFrom = min(dirtyFrom, sl);
         score = decision_score<KT>(a.cfg, ws, ln, k, tid, sumC, bandGuard, dirtyFrom);
       }
@@ -607,6 +651,13 @@ resolve_streams_kernel (StreamArgs a) {
       uint32_t before = 0, all = 0;
 #pragma unroll
       for (int w = 0; w < NW; w++) { const uint32_t c = ws.ctl(40 + w); all += c; before += (w < warp) ? c : 0u; }
+      if (CLUSTER) {
+        // arrival order across the cluster: the CTAs of lower rank come first
+        if (uint32_t(tid) < csize) *cg::this_cluster().map_shared_rank(&ws.ctl(96 + crank), tid) = all;
+        cg::this_cluster().sync();
+        all = 0;
+        for (uint32_t r = 0; r < csize; r++) { const uint32_t c = ws.ctl(96 + r); all += c; before += (r < crank) ? c : 0u; }
+      }
       if (rejected) {
         const uint32_t at = g0 + nRej + before + __popc(ftm & ((1u << lane) - 1u));
         a.rej_order[at] = ord;
@@ -640,7 +691,21 @@ resolve_streams_kernel (StreamArgs a) {
   // ---- per-stream totals ----
   atomicAdd(&ws.ctl(36), nAcc0);  atomicAdd(&ws.ctl(37), nAcc1);  atomicAdd(&ws.ctl(38), nAcc2);
   __syncthreads();
-  if (tid == 0) {
+  if (CLUSTER) {
+    // rank 0 sums the CTAs' counters and writes the enveloppe back (the copies are identical); the others stay until it has
+    cg::this_cluster().sync();
+    if (crank == 0 && tid == 0) {
+      uint32_t s0 = 0, s1 = 0, s2 = 0;
+      for (uint32_t r = 0; r < csize; r++) {
+        const uint32_t *pc = cg::this_cluster().map_shared_rank(&ws.ctl(0), r);
+        s0 += pc[36];  s1 += pc[37];  s2 += pc[38];
+      }
+      a.grp_sum[g] = make_uint4(s0, s1, s2, aborted ? 1u : 0u);
+      if (a.rej_order) a.rej_count[g] = nRej;
+    }
+    cg::this_cluster().sync();
+    if (crank != 0) return;
+  } else if (tid == 0) {
     a.grp_sum[g] = make_uint4(ws.ctl(36), ws.ctl(37), ws.ctl(38), aborted ? 1u : 0u);
     if (a.rej_order) a.rej_count[g] = nRej;
   }
@@ -661,23 +726,40 @@ resolve_streams_kernel (StreamArgs a) {
   if (prof && tid == 0) { prof[4] = clock64();  prof[5] = profEvents;  prof[6] = profSteps;  prof[8] = profA;  prof[9] = profB; }
 }
 
-template <int WQ, int NW, int KT, bool CRITX = false>
-void launchWQ (const StreamArgs &a, cudaStream_t st) {
+/// `cluster` > 1: CTAs per stream (the CLUSTER instantiation); returns false when the device cannot place such clusters
+template <int WQ, int NW, int KT, bool CRITX = false, bool CLUSTER = false>
+bool launchWQ (const StreamArgs &a, cudaStream_t st, uint32_t cluster = 1) {
   const uint32_t K = a.pool.K;
   size_t smem = (stream_smem(K, WQ, NW * 32, KT > 0) + 15) & ~size_t(15);
   StreamArgs b = a;
   const size_t lutBytes = size_t(a.cfg.lut_classes) * a.cfg.lut_stride * sizeof(double);
   b.lut_in_smem = a.cfg.use_lut && lutBytes > 0 && lutBytes <= (size_t(48) << 10) && smem + lutBytes <= (size_t(200) << 10);
   if (b.lut_in_smem) smem += lutBytes;
+  bool ok = true;
   auto go = [&] (auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     // (preload: the runtime loads a kernel on its first use -- milliseconds that would otherwise land in the first pass)
     if (a.preload) { cudaFuncAttributes fa;  cudaFuncGetAttributes(&fa, kernel);  return; }
-    kernel<<<a.n_groups, NW * 32, smem, st>>>(b);
+    if (!CLUSTER) { kernel<<<a.n_groups, NW * 32, smem, st>>>(b);  return; }
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute at[1];
+    lc.blockDim = dim3(NW * 32);  lc.dynamicSmemBytes = smem;  lc.stream = st;  lc.attrs = at;  lc.numAttrs = 1;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    if (cluster > 8) cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    uint32_t cl = cluster;
+    for (; cl > 1; cl /= 2) {             // the largest cluster the device can schedule
+      lc.gridDim = dim3(a.n_groups * cl);
+      at[0].val.clusterDim.x = cl;  at[0].val.clusterDim.y = 1;  at[0].val.clusterDim.z = 1;
+      int nClusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nClusters, kernel, &lc) == cudaSuccess && nClusters >= 1) break;
+      cudaGetLastError();
+    }
+    if (cl > 1) cudaLaunchKernelEx(&lc, kernel, b); else ok = false;
   };
   if (a.cfg.kind == 0) {
-    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW, KT, CRITX>); else go(resolve_streams_kernel<WQ, 0, false, NW, KT, CRITX>);
-  } else go(resolve_streams_kernel<WQ, 1, false, NW, KT, CRITX>);
+    if (a.cfg.use_lut) go(resolve_streams_kernel<WQ, 0, true, NW, KT, CRITX, CLUSTER>); else go(resolve_streams_kernel<WQ, 0, false, NW, KT, CRITX, CLUSTER>);
+  } else go(resolve_streams_kernel<WQ, 1, false, NW, KT, CRITX, CLUSTER>);
+  return ok;
 }
 
 /// Warps per stream: wide CTAs pay off when some stream is long; genomes that fill the register
@@ -687,6 +769,16 @@ template <int WQ>
 void launchNW (const StreamArgs &a, cudaStream_t st) {
   // criteria 2 and 3 (debug options of the reference): one variant, any enveloppe size, 4 warps
   if (a.crit >= 2) { launchWQ<WQ, 4, 0, true>(a, st); return; }
+  // a pass of few streams one of which is very long (one species holds the births: the first generations of a
+  // radiation): that many CTAs of 4 warps per stream as keep all streams on the chip at once, 16 at most
+  const char *env = getenv("APT_STREAM_CLUSTER_MIN");          // (read per launch: tests switch it)
+  const uint32_t clusterMin = env ? uint32_t(std::max(1, atoi(env))) : 2048u;
+  if (a.preload) launchWQ<WQ, 4, 0, false, true>(a, st);
+  else if (a.max_stream >= clusterMin && a.n_groups * 2 <= 148) {
+    uint32_t cl = 2;
+    while (cl < 16 && a.n_groups * cl * 2 <= 148 && cl * 128 < a.max_stream) cl *= 2;
+    if (launchWQ<WQ, 4, 0, false, true>(a, st, cl)) return;
+  }
   const bool wide = a.max_stream > 1024 && WQ <= 8
                     && ((stream_smem(a.pool.K, WQ, 512) + 15) & ~size_t(15)) <= (size_t(150) << 10);
   if constexpr (WQ <= 4) {

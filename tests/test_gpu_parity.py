@@ -81,6 +81,43 @@ def test_tree_with_births_grouped_on_the_device(name, monkeypatch):
     _compare(name)
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_tree_with_streams_on_thread_block_clusters(name, monkeypatch):
+    """A pass of few streams one of which is very long runs every stream on a cluster of CTAs (replicated enveloppe,
+    events elected through distributed shared memory); forced on for the golden cases' short streams, whenever a pass
+    has few enough streams for clusters to fit."""
+    monkeypatch.setenv("APT_STREAM_CLUSTER_MIN", "1")
+    _compare(name)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_long_streams_on_clusters_equal_single_cta_streams(seed, monkeypatch):
+    """One species holding thousands of births per call (the start of a simulation): the clustered stream kernel against
+    the single-CTA one on the same trace -- ids, entries, callback stream, Stats and dump must be identical."""
+    from apoget_b200.tree import PhylogeneticTree
+    rng = np.random.default_rng(300 + seed)
+    kind = synth.F32 if seed == 3 else synth.BITS
+    gen = dict(kind=kind, words=[8, 128, 4, 16][seed], pop=int(rng.integers(3000, 9000)), gens=3, seed=seed, hybrid=0.02)
+    if kind == synth.BITS:
+        gen.update(flips=1.5, sigma=[12.0, 100.0, 6.0, 0.0][seed])
+    else:
+        gen.update(sigma=0.35, noise=0.02, noise_coords=4)
+    t = synth.generate(**gen)
+    cfg = dict(K=[10, 10, 5, 10][seed])
+    out = []
+    for cluster_min in ("1000000000", "1"):
+        monkeypatch.setenv("APT_STREAM_CLUSTER_MIN", cluster_min)
+        tree = PhylogeneticTree(t.kind, t.words, **cfg)
+        sids, slots = tree.replay(t)
+        out.append((sids, slots, tree.stats(), tree.events(), tree.to_json()))
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[2] == b[2]
+    assert np.array_equal(a[3], b[3])
+    assert a[4] == b[4]
+    assert int(np.bincount(a[0]).max()) >= 2048, "the trace has no long stream"
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c4_b4096_k10"])
 def test_tree_generic_compat_path(name):
     """Device exp() instead of the libm-built table: decisions must still be identical."""
