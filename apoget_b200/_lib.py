@@ -67,6 +67,7 @@ SYMBOLS = {
     "apt_tree_alive_species": (ctypes.c_int, [vp, vp, ctypes.c_uint32, u32p]),
     "apt_tree_counters": (ctypes.c_int, [vp, u64p]),
     "apt_tree_timers": (ctypes.c_int, [vp, f64p]),
+    "apt_tree_kernel_span": (ctypes.c_int, [vp, f64p]),
     "apt_pool_create": (ctypes.c_int, [ctypes.POINTER(AptParams), ctypes.c_uint32, vp, vp, vp, ctypes.POINTER(vp)]),
     "apt_pool_destroy": (None, [vp]),
     "apt_score_pairs": (ctypes.c_int, [vp, ctypes.c_uint32, vp, vp, ctypes.c_uint32, vp, vp, vp, vp]),

@@ -352,6 +352,10 @@ int apt_tree_timers (apt_tree *t, double out[8]) {
   return guarded([&] { need(t && out, "null argument"); memcpy(out, t->engine.timers, sizeof t->engine.timers); });
 }
 
+int apt_tree_kernel_span (apt_tree *t, double out[2]) {
+  return guarded([&] { need(t && out, "null argument"); out[0] = t->engine.streamSpanMs_; out[1] = double(t->engine.streamSpanN_); });
+}
+
 // ---- stateless kernels ----------------------------------------------------------------------------
 
 int apt_pool_create (const apt_params *params, uint32_t n_species, const uint32_t *rep_payload,

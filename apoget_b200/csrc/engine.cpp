@@ -1610,7 +1610,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   // ... and so do the clears of the result arrays (they depend on n only): the device runs them under the grouping
   bool earlyClears = false;
   auto clearResults = [&] (void) {
-    dOut2_.reserve(2 * size_t(n));  dAct_.reserve(n);  dCtr_.reserve(2);
+    dOut2_.reserve(2 * size_t(n));  dAct_.reserve(n);  dCtr_.reserve(8);
     cudaCheck(cudaMemsetAsync(dOut2_.p, 0xFF, 2 * size_t(n) * 4, stream_), "sid / slot clear");
     cudaCheck(cudaMemsetAsync(dAct_.p, 0, size_t(n) * 4, stream_), "act clear");
     earlyClears = true;
@@ -1787,7 +1787,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     // AFTER the speculative kernel, which must see the pool as it was when the chunk was submitted
     // few, larger transfers: every call below costs the host ~3 us before the kernel can start
     dOrder_.reserve(nStream);  dGrpAll_.reserve(3 * size_t(G) + 1);  hGrpAll_.reserve(3 * size_t(G) + 1);  dAct_.reserve(n);
-    dCtr_.reserve(2);  hCtr_.reserve(4);  dRows_.reserve((size_t(nStream) + 8 * size_t(G)) * K_);
+    dCtr_.reserve(8);  hCtr_.reserve(16);  dRows_.reserve((size_t(nStream) + 8 * size_t(G)) * K_);
     dOut2_.reserve(2 * size_t(n));  dGrpSum_.reserve(G);
     hAct_.reserve(n);  hOutSid_.reserve(n);  hOutSlot_.reserve(n);  hGrpSum_.reserve(G);
     uint32_t *dGrpSlot = dGrpAll_.p, *dGrpSid = dGrpAll_.p + G, *dGrpOff = dGrpAll_.p + 2 * size_t(G);
@@ -1801,7 +1801,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     if (!earlyClears) clearResults();
     // (kept behind the copies on purpose: the copy-engine -> SM hand-over then sits in front of this 8-byte clear and
     // not between the two events that time the kernel)
-    cudaCheck(cudaMemsetAsync(dCtr_.p, 0, 8, stream_), "counter clear");        // [0] rows claimed, [1] births rejected at top level
+    // [0] rows claimed, [1] births rejected at top level, [2..5] the stream kernel's time span (two 64-bit words)
+    cudaCheck(cudaMemsetAsync(dCtr_.p, 0, 24, stream_), "counter clear");
     StreamArgs a;
     a.pool = poolView();
     a.pool_payload_w = dPool_.p;  a.pool_cmeta_w = dMeta_.p;  a.pool_fill_w = dFill_.p;  a.pool_dist = dPoolDist_.p;
@@ -1809,6 +1810,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     a.b_payload = dBirthRows;  a.b_cmeta = dBMeta_.p;
     a.n_groups = G;  a.max_stream = maxStream;  a.grp_slot = dGrpSlot;  a.grp_off = dGrpOff;  a.order = dOrder_.p;
     a.act = dAct_.p;  a.rows = dRows_.p;  a.row_counter = dCtr_.p;
+    a.span = reinterpret_cast<unsigned long long*>(dCtr_.p + 2);
     a.row_payload = nullptr;
     if (!payload) { dRowPayload_.reserve(size_t(nStream) * wp_ + 4); a.row_payload = dRowPayload_.p; }
     a.grp_sid = dGrpSid;  a.out_sid = dOutSid;  a.out_slot = dOutSlot;  a.grp_sum = dGrpSum_.p;
@@ -1830,7 +1832,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     }
     const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str();
     if (profPath) { dProf_.reserve(size_t(G) * 16); a.prof = dProf_.p; }
-    cudaCheck(cudaEventRecord(evS0_, stream_), "event record");
+    a.ev_before = evS0_;                     // (recorded by the launcher, immediately in front of the launch)
     launch_resolve_streams(a, stream_);
     cudaCheck(cudaEventRecord(evS1_, stream_), "event record");
     counters[4]++;  counters[12]++;  counters[13] += nStream;
@@ -1922,7 +1924,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       launch_list_unsettled(dAct_.p, nullptr, n, dSlowBlk_.p, dSlowList_.p, dSlowCtr_.p, stream_);
       counters[4] += 2;
       cudaCheck(cudaGetLastError(), "list_unsettled launch");
-      cudaCheck(cudaMemcpyAsync(hCtr_.p + 3, dSlowCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "listed births");
+      cudaCheck(cudaMemcpyAsync(hCtr_.p + 9, dSlowCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "listed births");
       hSlowList_.reserve(2 * std::max<size_t>(2048, nStream / 4));
       if (estSlow_) {
         specSlow = uint32_t(std::min<size_t>(estSlow_, n));
@@ -1931,7 +1933,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
     }
     cudaCheck(cudaMemcpyAsync(hAct_.p, dAct_.p, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "act");
-    cudaCheck(cudaMemcpyAsync(hCtr_.p, dCtr_.p, 8, cudaMemcpyDeviceToHost, stream_), "counters");
+    cudaCheck(cudaMemcpyAsync(hCtr_.p, dCtr_.p, 24, cudaMemcpyDeviceToHost, stream_), "counters");
     // results go straight into the caller's arrays when those are pinned (no staging copy on the host)
     directOut = outSid && outSlot && outPinned_;
     cudaCheck(cudaMemcpyAsync(directOut ? outSid : hOutSid_.p, dOutSid, size_t(n) * 4, cudaMemcpyDeviceToHost, stream_), "sids");
@@ -1975,7 +1977,17 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
     float ms = 0.f;
     if (P) { cudaCheck(cudaEventElapsedTime(&ms, evK0_, evK1_), "event elapsed"); timers[4] += ms; }
     if (G) {
-      cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");  timers[5] += ms;
+      cudaCheck(cudaEventElapsedTime(&ms, evS0_, evS1_), "event elapsed");
+      {
+        // the kernel's own span -- first CTA in to last CTA out, by the device's nanosecond timer -- kept beside the event
+        // time (apt_tree_kernel_span): the events also see the gap between the host's record call and its launch call
+        // whenever the stream is idle at that point (it is, since the grouping moved to the device), ~5 us of no kernel
+        unsigned long long sp[2];
+        memcpy(sp, hCtr_.p + 2, sizeof sp);
+        const unsigned long long t0 = ~sp[0], t1 = sp[1];
+        if (sp[0] && t1 > t0) { streamSpanMs_ += double(t1 - t0) * 1e-6;  streamSpanN_++; }
+      }
+      timers[5] += ms;
       if (const char *profPath = streamProf_.empty() ? nullptr : streamProf_.c_str()) {
         // development aid: one text line per stream {launch, stream, births, kernel ms, 10 timeline words}, appended
         std::vector<unsigned long long> hp (size_t(G) * 16);
@@ -2004,7 +2016,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           launch_list_unsettled(dAct_.p, dFamAct_.p, n, dSlowBlk_.p, dSlowList_.p, dSlowCtr_.p, stream_);
           counters[4] += 2;
           cudaCheck(cudaGetLastError(), "list_unsettled launch");
-          cudaCheck(cudaMemcpyAsync(hCtr_.p + 3, dSlowCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "listed births");
+          cudaCheck(cudaMemcpyAsync(hCtr_.p + 9, dSlowCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "listed births");
           specSlow = 0;
         }
         cudaCheck(cudaStreamSynchronize(stream_), "family pass");
@@ -2058,12 +2070,12 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           cudaCheck(cudaMemcpyAsync(hChildJoin_.p, dChildJoin_.p, joinWords * 4, cudaMemcpyDeviceToHost, stream_), "family counters");
           cudaCheck(cudaMemcpyAsync(hNewFounder_.p, dNewFounder_.p, size_t(nFam) * famMaxNew_ * 2 * 4, cudaMemcpyDeviceToHost, stream_), "family founders");
           cudaCheck(cudaMemcpyAsync(hFamStats_.p, dFamStats_.p, 2 * size_t(nFam) * 8, cudaMemcpyDeviceToHost, stream_), "family stats");
-          cudaCheck(cudaMemcpyAsync(hCtr_.p + 2, dFamSlotCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "family slots");
+          cudaCheck(cudaMemcpyAsync(hCtr_.p + 8, dFamSlotCtr_.p, 4, cudaMemcpyDeviceToHost, stream_), "family slots");
           famResults_ = true;
         }
       }
       if (devList) {
-        nSlow = std::min(hCtr_.p[3], n);
+        nSlow = std::min(hCtr_.p[9], n);
         if (nSlow > specSlow) {
           hSlowList_.reserve(2 * size_t(nSlow));
           cudaCheck(cudaMemcpyAsync(hSlowList_.p, dSlowList_.p, 2 * size_t(nSlow) * 4, cudaMemcpyDeviceToHost, stream_), "list");
@@ -2072,7 +2084,7 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
       }
       if (nRows > specRows || nFt_ || nFtRows_ > specFt || famResults_ || nSlow > specSlow) cudaCheck(cudaStreamSynchronize(stream_), "rows");
       if (famResults_) {
-        famSlotsUsed_ = std::min<uint32_t>(hCtr_.p[2], famReserve(nStream));
+        famSlotsUsed_ = std::min<uint32_t>(hCtr_.p[8], famReserve(nStream));
         if (famSlotsUsed_) {
           // the species founded on the device live in pool slots [famSlotBase_, +used): they become real now
           nSlots_ = famSlotBase_ + famSlotsUsed_;

@@ -245,6 +245,7 @@ public:
   const apt_params& params (void) const { return p_; }
   uint64_t counters[16] = {};
   double timers[8] = {};
+  double streamSpanMs_ = 0.;  uint64_t streamSpanN_ = 0;     // stream kernel: first CTA in to last CTA out, summed over its launches
 
 private:
   apt_params p_;

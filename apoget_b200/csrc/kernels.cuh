@@ -137,12 +137,14 @@ struct StreamArgs {
   uint32_t *ft_list;          ///< births rejected at top level, appended as (birth, stream) pairs ...
   uint32_t *ft_counter;       ///< ... counted here (zero-initialised)
   uint32_t *row_counter;      ///< zero-initialised; a stream claims the rows of a step (its enveloppe entries) with one add
+  unsigned long long *span = nullptr;   ///< optional, zero-initialised: [0] max over the CTAs of ~(global timer at entry), [1] max of the timer at exit
   uint32_t *rej_order = nullptr;  ///< optional [n stream births]: per stream, at grp_off[g], its births rejected at top level in ARRIVAL
                               ///< order (order words) -- the input of the sub-species resolution on the device (family.cu)
   uint32_t *rej_fill = nullptr;   ///< same layout: the enveloppe fill each one's top-level score saw (Stats::comparisons)
   uint32_t *rej_count = nullptr;  ///< [n_groups] how many
   int lut_in_smem = 0;        ///< set by the launcher
   int preload = 0;            ///< the launcher only makes the runtime load the kernel variant these arguments select (no launch)
+  cudaEvent_t ev_before = nullptr;   ///< host side: recorded on the stream by the launcher immediately in front of the launch
   unsigned long long *prof = nullptr;   ///< optional [n_groups][12] per-stream timeline (APT_STREAM_PROF), see stream.cu
 };
 bool stream_kernel_supports (uint32_t wp, uint32_t K, int crit);

@@ -359,6 +359,11 @@ resolve_streams_kernel (StreamArgs a) {
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     prof[0] = gt;  prof[1] = clock64();  prof[7] = smid;
   }
+  if (a.span && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    atomicMax(a.span, ~gt);
+  }
   const uint32_t slot = a.grp_slot[g], sid = a.grp_sid[g];
   const uint32_t g0 = a.grp_off[g], g1 = a.grp_off[g + 1];
   const uint4 *poolRows = reinterpret_cast<const uint4*>(a.pool.payload) + size_t(slot) * K * WQ;
@@ -724,6 +729,11 @@ resolve_streams_kernel (StreamArgs a) {
     if (tid == 0) a.pool_fill_w[slot] = k;
   }
   if (prof && tid == 0) { prof[4] = clock64();  prof[5] = profEvents;  prof[6] = profSteps;  prof[8] = profA;  prof[9] = profB; }
+  if (a.span && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    atomicMax(a.span + 1, gt);
+  }
 }
 
 /// `cluster` > 1: CTAs per stream (the CLUSTER instantiation); returns false when the device cannot place such clusters
@@ -737,9 +747,19 @@ bool launchWQ (const StreamArgs &a, cudaStream_t st, uint32_t cluster = 1) {
   if (b.lut_in_smem) smem += lutBytes;
   bool ok = true;
   auto go = [&] (auto kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    // (the attribute call costs microseconds: made when the size changes, not per launch.  One entry per instantiation
+    // of this lambda, i.e. per kernel variant; a tree is driven by one host thread)
+    static size_t smemSet = ~size_t(0);
+    static int devSet = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smemSet != smem || devSet != dev) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      smemSet = smem;  devSet = dev;
+    }
     // (preload: the runtime loads a kernel on its first use -- milliseconds that would otherwise land in the first pass)
     if (a.preload) { cudaFuncAttributes fa;  cudaFuncGetAttributes(&fa, kernel);  return; }
+    if (a.ev_before) cudaEventRecord(a.ev_before, st);
     if (!CLUSTER) { kernel<<<a.n_groups, NW * 32, smem, st>>>(b);  return; }
     cudaLaunchConfig_t lc = {};
     cudaLaunchAttribute at[1];

@@ -168,6 +168,12 @@ class PhylogeneticTree:
         return dict(zip(["prepare_s", "device_s", "walk_s", "refresh_s", "score_kernel_ms", "stream_kernel_ms", "family_kernel_ms", "alloc_s"],
                         (float(x) for x in out)))
 
+    def kernel_span(self) -> tuple[float, int]:
+        """Stream kernel as timed on the device: (ms summed over its launches: first CTA in to last CTA out, launches)."""
+        out = np.zeros(2, dtype=np.float64)
+        check(lib().apt_tree_kernel_span(self._h, out.ctypes.data_as(_lib.f64p)))
+        return float(out[0]), int(out[1])
+
     def node_info(self, sid: int) -> dict:
         info = _lib.AptNodeInfo()
         check(lib().apt_tree_node_info(self._h, sid, ctypes.byref(info)))

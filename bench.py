@@ -202,7 +202,7 @@ def main() -> None:
     # reduction behind the last one, not in front of every timed call (BENCH_STEP_BARRIER=1 does that: it lines up the
     # host-side bursts of all ranks on the shared cores -- 631 M instead of 765 M births/s on 8 GPUs / 32 cores)
     step_barrier = os.environ.get("BENCH_STEP_BARRIER", "0") == "1"
-    dc, dt, dtd, n_launches, per_step = {}, {}, {}, [0], []
+    dc, dt, dtd, n_launches, per_step, span = {}, {}, {}, [0], [], [0.0, 0.0]
     sampler = ClockSampler(local_rank)
 
     def run_epoch(e, n_warm, n_timed):
@@ -313,6 +313,7 @@ def main() -> None:
 
         c0, t0 = tree_h.counters(), tree_h.timers()
         cd0, td0 = tree_d.counters(), tree_d.timers()
+        sp0 = tree_h.kernel_span()
         steps_here = []
         for k in range(n_timed):
             steps_here.append(timed_step(SETUP_GENS + n_warm + k, True))
@@ -320,6 +321,8 @@ def main() -> None:
                 sampler.sample()
         c1, t1 = tree_h.counters(), tree_h.timers()
         cd1, td1 = tree_d.counters(), tree_d.timers()
+        sp1 = tree_h.kernel_span()
+        span[0] += sp1[0] - sp0[0];  span[1] += sp1[1] - sp0[1]
         for k in td1:
             dtd[k] = dtd.get(k, 0.0) + td1[k] - td0[k]
         for k in c1:
@@ -410,7 +413,11 @@ def main() -> None:
         "gpu_launches": int(n_launches[0]),
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC.get(kname), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
-                     "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel_ms_per_launch": kernel_ms, "kernel_ms_timed_by": "CUDA events on the engine's stream, around the launch",
+                     # the same launches as the kernel itself sees them (global nanosecond timer, first CTA in to last CTA out): the
+                     # events also contain the host's gap between recording and launching when the stream is idle at that point
+                     "kernel_span_ms_per_launch_on_device": (span[0] / span[1]) if (span[1] and kname == "resolve_streams_kernel") else None,
+                     "algorithmic_bytes_per_launch": alg_bytes,
                      "births_per_launch": units, "evals_per_s_kernel": units * K / (kernel_ms * 1e-3) if kernel_ms else 0,
                      "births_per_s_kernel": units / (kernel_ms * 1e-3) if kernel_ms else 0,
                      "note": "latency-bound by construction: one CTA per species stream, the launch lasts as long as the stream with most "

@@ -200,6 +200,11 @@ int apt_tree_counters (apt_tree *t, uint64_t out[16]);
  * [7] growth of the engine's device and pinned buffers inside add_genomes calls (s; part of [0]-[3]: first-use cost). */
 int apt_tree_timers (apt_tree *t, double out[8]);
 
+/* The stream-resolution kernel as the device itself timed it: out[0] = sum over its launches of (last CTA out - first
+ * CTA in) by the global nanosecond timer (ms), out[1] = launches so timed.  ([5] of apt_tree_timers is the CUDA-event
+ * time of the same launches, which also contains the host's gap between recording the event and launching.) */
+int apt_tree_kernel_span (apt_tree *t, double out[2]);
+
 /* ------------------------------------------------------------------------------------------------
  * Stateless kernels (the pieces of the hot path, individually testable against the oracle).
  * A pool holds `n_species` enveloppes of up to K representatives; all pointers below are DEVICE
