@@ -421,7 +421,7 @@ def main() -> None:
                      "births_per_launch": units, "evals_per_s_kernel": units * K / (kernel_ms * 1e-3) if kernel_ms else 0,
                      "births_per_s_kernel": units / (kernel_ms * 1e-3) if kernel_ms else 0,
                      "note": "latency-bound by construction: one CTA per species stream, the launch lasts as long as the stream with most "
-                             "enveloppe entries (~8 us fixed + ~1.5 us per entry, up to 13 per step; DESIGN.md 4.1) and moves 9 MB, 1.4 us worth "
+                             "enveloppe entries (~8 us fixed + ~1.0 us per entry, up to 13 per step; DESIGN.md 4.1) and moves 9 MB, 1.4 us worth "
                              "of HBM time; the throughput kernel of this path is the dense sweep (dense_sweep.roofline)"},
         "clocks": clocks,
         "breakdown_e2e_ms_per_step": {
