@@ -58,6 +58,42 @@ def test_c2_full_size_tree_equals_oracle_and_is_batch_invariant(tmp_path):
     assert np.array_equal(sid_of, sids), "result depends on the batch boundaries"
     assert cut.to_json() == whole.to_json(), "tree depends on the batch boundaries"
 
+    # the same generations with everything a host program hands over in page-locked memory (apt_host_alloc): the births
+    # are then grouped into streams by the device (one cooperative kernel reading the id arrays in place), the unsettled
+    # births are listed by it, and the results land in the caller's arrays directly
+    from apoget_b200.tree import pinned_array
+    pop = 100_000
+    pin = PhylogeneticTree(t.kind, t.words, K=10)
+    p_payload = pinned_array((pop, t.words), np.uint32)
+    p_compat = pinned_array((pop, 3), np.float32)
+    p_ids = [pinned_array((pop,), np.uint32) for _ in range(5)]
+    p_out = [pinned_array((pop,), np.uint32), pinned_array((pop,), np.int32), pinned_array((pop,), np.uint32)]
+    vp = ctypes.c_void_p
+    psid = np.full(t.n_births, INVALID, dtype=np.uint32)
+    launches_before_steady = None
+    for g in range(t.n_gens):
+        b0, b1 = int(t.gen_birth_off[g]), int(t.gen_birth_off[g + 1])
+        assert b1 - b0 == pop
+        m, f = t.mother[b0:b1], t.father[b0:b1]
+        hm, hf = m != INVALID, f != INVALID
+        p_payload[...] = t.payload[b0:b1]
+        p_compat[...] = t.compat[b0:b1]
+        for dst, src in zip(p_ids, (np.arange(b0 + 1, b1 + 1, dtype=np.uint32), np.where(hm, m + 1, INVALID),
+                                    np.where(hm, psid[np.where(hm, m, 0)], INVALID), np.where(hf, f + 1, INVALID),
+                                    np.where(hf, psid[np.where(hf, f, 0)], INVALID))):
+            dst[...] = src.astype(np.uint32)
+        if g == t.n_gens - 1:
+            launches_before_steady = pin.counters()["kernel_launches"]
+        pin.add_genomes_raw(pop, vp(p_payload.ctypes.data), vp(p_compat.ctypes.data), [vp(x.ctypes.data) for x in p_ids],
+                            vp(p_out[0].ctypes.data), vp(p_out[1].ctypes.data), vp(p_out[2].ctypes.data))
+        psid[b0:b1] = p_out[0]
+        pin.del_genomes(psid[t.deaths_of(g)])
+        pin.step(g + 1, psid[t.alive_of(g)])
+    assert np.array_equal(psid, sids), "page-locked inputs (device-side grouping) change the result"
+    assert pin.to_json() == whole.to_json(), "page-locked inputs (device-side grouping) change the tree"
+    # the last (steady) generation: grouping kernel + stream kernel + the two list kernels + the fill of the class table at most
+    assert pin.counters()["kernel_launches"] - launches_before_steady <= 8
+
 
 @pytest.mark.parametrize("words,sigma", [(8, 12.0), (128, 60.0)])
 def test_dense_sweep_full_size_properties(words, sigma):
