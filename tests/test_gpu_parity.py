@@ -118,6 +118,27 @@ def test_long_streams_on_clusters_equal_single_cta_streams(seed, monkeypatch):
     assert int(np.bincount(a[0]).max()) >= 2048, "the trace has no long stream"
 
 
+@pytest.mark.parametrize("seed", range(1000, 1012))
+def test_randomised_trees_with_random_device_paths(seed):
+    """tools/fuzz_gpu.py's cases (random genome kind / width / enveloppe size / criterion / hybrids / radiations, a random
+    subset of the device-side paths forced on for small batches) against the oracle; profiles/fuzz_r02e.json is a run of
+    250 larger ones (30 M births)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_gpu", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "fuzz_gpu.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    saved = {k: os.environ.get(k) for k in ("APT_STREAM_CLUSTER_MIN", "APT_DEVLIST_MIN", "APT_DEVGROUP_MIN", "APT_DEVGROUP_PAGEABLE")}
+    try:
+        row = fuzz.one(seed, 5000)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert not row["bad"], row
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "c4_b4096_k10"])
 def test_tree_generic_compat_path(name):
     """Device exp() instead of the libm-built table: decisions must still be identical."""
