@@ -1441,7 +1441,7 @@ void Engine::groupParallel (uint32_t n, const uint32_t *msid, const uint32_t *fs
 /// outside the streams and (later, with the results) the birth -> stream table and the order list come back; the host
 /// only walks the species that have births.  Returns false when the pass has to be grouped on the host after all (a
 /// stream too long for the device-side sort).
-bool Engine::groupDevice (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream) {
+bool Engine::groupDeviceLaunch (uint32_t n, const uint32_t *msid, const uint32_t *fsid) {
   const size_t NS = nodes_.size();
   if (sidSlot_.size() < NS) { sidSlot_.resize(NS, INV);  sidSlotDirty_ = true; }
   dSidSlot_.reserve(NS);
@@ -1489,12 +1489,20 @@ bool Engine::groupDevice (uint32_t n, const uint32_t *msid, const uint32_t *fsid
   counters[4] += 1;
   if (profile_) cudaEventRecord(evK1_, streamG_);
   cudaCheck(cudaEventRecord(evG_, streamG_), "event record");
+  if (profile_) grpProf_[0] = now() - pg0;
+  return true;
+}
+
+/// ... and its second half, once the host has done what does not depend on the grouping: waits for the kernel and books
+/// the streams.  Returns false when the pass has to be grouped on the host after all.
+bool Engine::groupDeviceFinish (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream) {
+  const size_t NS = nodes_.size();
   const double pg1 = profile_ ? now() : 0.;
   cudaCheck(cudaEventSynchronize(evG_), "grouping");
   if (profile_ && n >= parMin_) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, evK0_, evK1_);
-    fprintf(stderr, "group (device): enqueue %.3f wait %.3f ms; on the device %.3f ms\n", 1e3 * (pg1 - pg0), 1e3 * (now() - pg1), double(ms));
+    fprintf(stderr, "group (device): enqueue %.3f wait %.3f ms; on the device %.3f ms\n", 1e3 * grpProf_[0], 1e3 * (now() - pg1), double(ms));
   }
   if (hGrpInfo_.p[3]) return false;
   // streams in ascending species id (as groupParallel)
@@ -1631,6 +1639,8 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   for (uint32_t sid: sidTouched_) if (sid < sidGroup_.size()) sidGroup_[sid] = -2;
   sidTouched_.clear();
   if (sidGroup_.size() < nodes_.size()) sidGroup_.resize(nodes_.size(), -2);
+  // (the device starts grouping the births while the host looks at their compatibility classes)
+  const bool devLaunched = tryDevGroup && groupDeviceLaunch(n, msid, fsid);
   // compatibility classes: one triple for the whole chunk is the common case (array == itself shifted by one triple)
   if (pool_ && n >= parMin_) {
     const unsigned T = pool_->size();
@@ -1658,8 +1668,9 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
   uint32_t maxStream = 0;
   devGrouped_ = false;
   bg_ = nullptr;
-  if (tryDevGroup) {
-    devGrouped_ = groupDevice(n, msid, fsid, P, nStream, maxStream);
+  if (devLaunched && !streamOk_) cudaCheck(cudaEventSynchronize(evG_), "grouping");      // (the classes just switched the streams off)
+  else if (devLaunched) {
+    devGrouped_ = groupDeviceFinish(n, msid, fsid, P, nStream, maxStream);
     if (devGrouped_) bg_ = hBirthGroup_.p;
     else {                        // (handed back: whatever it booked is dropped)
       P = 0;  nStream = 0;  maxStream = 0;  pairOf_.clear();  grpSpecies_.clear();  grpCount_.clear();

@@ -356,7 +356,9 @@ private:
   bool idsPinned_ = false, devGrouped_ = false;
   uint32_t estRest_ = 0;
   const int32_t *bg_ = nullptr;              // the pass's birth -> stream table: birthGroup_ (host grouping) or hBirthGroup_ (device)
-  bool groupDevice (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
+  bool groupDeviceLaunch (uint32_t n, const uint32_t *msid, const uint32_t *fsid);
+  bool groupDeviceFinish (uint32_t n, const uint32_t *msid, const uint32_t *fsid, size_t &P, size_t &nStream, uint32_t &maxStream);
+  double grpProf_[2] = { 0., 0. };
   // the births of a pass the host has to look at, listed in arrival order by the device (launch_list_unsettled)
   DevBuf<uint32_t> dSlowBlk_, dSlowList_, dSlowCtr_;  PinBuf<uint32_t> hSlowList_;
   uint32_t estSlow_ = 0;
