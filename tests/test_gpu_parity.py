@@ -324,11 +324,16 @@ def test_pairwise_kernel(kind, words):
         assert np.allclose(out, exp, rtol=F32_RTOL, atol=0)
 
 
-@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "ragged_b96_k3", "c4_b4096_k10"])
-def test_tree_device_resident_payloads(name):
-    """apt_tree_add_genomes_dev: payloads stay in HBM, the host fetches only the rows it needs."""
+@pytest.mark.parametrize("device_passes", [False, True])
+@pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "ragged_b96_k3", "c4_b4096_k10", "c5_speciation_trimming"])
+def test_tree_device_resident_payloads(name, device_passes, monkeypatch):
+    """apt_tree_add_genomes_dev: payloads stay in HBM, the host fetches only the rows it needs.  (device_passes: with
+    the device-side grouping, list and clustered streams forced on for these small batches as well.)"""
     import torch
     from apoget_b200.tree import PhylogeneticTree
+    if device_passes:
+        for var in ("APT_DEVGROUP_MIN", "APT_DEVGROUP_PAGEABLE", "APT_DEVLIST_MIN", "APT_STREAM_CLUSTER_MIN"):
+            monkeypatch.setenv(var, "1")
     cfg = golden_cases()[name]["cfg"]
     t = synth.read_trace(golden_trace_path(name))
     tree = PhylogeneticTree(t.kind, t.words, **cfg)
