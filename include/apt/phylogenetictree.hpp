@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <deque>
 #include <fstream>
 #ifdef APT_DROPIN_PROFILE
@@ -485,13 +486,14 @@ public:
 #ifdef APT_DROPIN_PROFILE
     const auto p0 = std::chrono::steady_clock::now();
 #endif
-    _pl.clear();  _cp.clear();  _ids.clear();
     std::vector<const Genome*> gs;
     gs.reserve(size_t(std::distance(first, last)));
     for (IT it = first; it != last; ++it) gs.push_back(&*it);
     const size_t n = gs.size();
     if (!n) return;
     _epoch++;
+    // (no clear() in front of these: a vector re-initialises every element it grows by, 7 MB per 100 000 births on one
+    // thread; every element is written below -- payload rows are zeroed by the slice that encodes them)
     _pl.resize(n * Encoding::words);  _cp.resize(n * 3);  _ids.resize(n * 5);
     _sid.resize(n);  _slot.resize(n);  _rep.resize(n);
     // genome objects -> staging arrays, on the engine's worker threads for large batches: DeviceEncoding::encode is
@@ -501,6 +503,7 @@ public:
       EncodeCtx &x = *static_cast<EncodeCtx*>(c);
       PhylogeneticTree &t = *x.self;
       const size_t n = x.n;
+      std::memset(&t._pl[size_t(lo) * Encoding::words], 0, size_t(hi - lo) * Encoding::words * sizeof(uint32_t));
       for (size_t i = lo; i < hi; i++) {
         Encoding::encode(*x.gs[i], &t._pl[i * Encoding::words], &t._cp[i * 3]);
         const Genealogy &ge = x.gs[i]->genealogy();

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
-def build(lib_path: str, tag: str) -> str:
+def build(lib_path: str, tag: str, defines=()) -> str:
     out = os.path.join(HERE, "_build", f"test_dropin_{tag}")
     src = os.path.join(HERE, "test_dropin.cpp")
     deps = [src, lib_path, os.path.join(ROOT, "include", "apt", "phylogenetictree.hpp"),
@@ -18,7 +18,7 @@ def build(lib_path: str, tag: str) -> str:
     json_inc = os.path.join(sysconfig.get_paths()["purelib"], "include", "cudnn_frontend", "thirdparty")
     libdir, libname = os.path.split(lib_path)
     cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", json_inc, "-o", out, src,
-           "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir]
+           "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir] + ["-D" + d for d in defines]
     subprocess.run(cmd, check=True)
     return out
 

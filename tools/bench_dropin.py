@@ -25,16 +25,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pop", type=int, default=100_000)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--profile", action="store_true", help="per-call split on stderr: encode / engine / event replay (APT_DROPIN_PROFILE)")
     args = ap.parse_args()
     warm = 3
     trace = bench.make_trace(args.pop, warm + args.steps, 42)
     path = os.path.join(tempfile.gettempdir(), "apt_dropin_c2.trace")
     synth.write_trace(path, trace)
-    exe = cb.build(apt_build.build(), "cuda")
+    exe = cb.build(apt_build.build(), "cuda_prof" if args.profile else "cuda", ("APT_DROPIN_PROFILE",) if args.profile else ())
     r = subprocess.run([exe, path, os.path.join(tempfile.gettempdir(), "apt_dropin_c2"), str(bench.TREE_CFG["K"])],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise SystemExit(r.stdout + r.stderr)
+    if args.profile:
+        sys.stderr.write(r.stderr)
     out = json.loads(r.stdout.strip().splitlines()[-1])
     ms = out["add_ms_per_generation"][bench.SETUP_GENS + warm:]
     print(json.dumps({"workload": "C2 through apt::PhylogeneticTree<GENOME,UDATA>::addGenomes (C++ drop-in, callbacks on)",
