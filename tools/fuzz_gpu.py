@@ -52,7 +52,16 @@ def one(seed, pop_max):
     o = oracle.Oracle(t.kind, t.words, **cfg)
     osid, oent, _ = o.replay(path, n_births=t.n_births)
     tree = PhylogeneticTree(t.kind, t.words, **cfg)
-    sids, slots = tree.replay(t)
+    to_device = None
+    if rng.random() < 0.3:                      # genomes resident in HBM (apt_tree_add_genomes_dev)
+        import torch
+
+        def to_device(a):
+            d = torch.from_numpy(a.view(np.int32)).cuda()
+            torch.cuda.synchronize()
+            return d, d.data_ptr(), torch.cuda.current_stream().cuda_stream
+        forced["device-resident genomes"] = "1"
+    sids, slots = tree.replay(t, to_device=to_device)
     bad = []
     if not np.array_equal(sids, osid): bad.append("sids")
     if not np.array_equal(slots >= 0, oent > 0): bad.append("entries")
