@@ -827,8 +827,11 @@ void Engine::resolveBelowStream (const uint32_t *w, const RepMeta &g, Species *s
     if (dev && idx < snapN) {
       const uint32_t rank = uint32_t(snapN - 1 - idx);
       const bool known = rank < firstRank || (rank == firstRank && !firstUnsure);
+      // (a sub-species with a stream of its own: the kernel saw it as that stream left it -- all its entries applied.  A
+      // stream the device handed back in the middle never wrote its enveloppe back: the verdict then rests on the state
+      // BEFORE the pass although the host has committed that stream's earlier entries, and must not be used)
       if (known && sub->stale_mask == 0 && !sub->full_upload && sub->div_epoch != chunkEpoch_ && sub->fam_epoch != chunkEpoch_ &&
-          (sub->grp_epoch != chunkEpoch_ || grpState_[sub->grp_index].lastEnter < int64_t(curBirth_))) {
+          (sub->grp_epoch != chunkEpoch_ || (grpState_[sub->grp_index].lastEnter < int64_t(curBirth_) && !hGrpSum_.p[sub->grp_index].w))) {
         touchSnap(sub);
         comparisons_ += sub->k;
         counters[1]++;

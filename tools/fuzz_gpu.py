@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 from apoget_b200 import synth  # noqa: E402
 
 
-def one(seed, pop_max):
+def one(seed, pop_max, allow_device_payload=True):
     import oracle
     from apoget_b200.tree import PhylogeneticTree
     rng = np.random.default_rng(90_000 + seed)
@@ -38,7 +38,9 @@ def one(seed, pop_max):
     else:
         gen.update(sigma=0.35, noise=0.02, noise_coords=4, burst_scale=1.0)
     t = synth.generate(**gen)
-    cfg = dict(K=K, full_continuous=bool(rng.random() < 0.75), env_crit=int(rng.choice([0, 1, 1, 1])))
+    cfg = dict(K=K, full_continuous=bool(rng.random() < 0.75), env_crit=int(rng.choice([0, 1, 1, 1, 1, 2, 3])))
+    if rng.random() < 0.3:                      # stillborn trimming at work (step(), slot recycling)
+        cfg.update(trim_period=int(rng.integers(2, 6)), trim_min_delay=int(rng.integers(1, 4)), trim_delay=1.0, trim_thr=float(rng.choice([0.3, 0.6])))
     forced = {}
     for var, p in (("APT_STREAM_CLUSTER_MIN", 0.5), ("APT_DEVLIST_MIN", 0.5), ("APT_DEVGROUP_MIN", 0.5)):
         os.environ.pop(var, None)
@@ -51,9 +53,13 @@ def one(seed, pop_max):
     synth.write_trace(path, t)
     o = oracle.Oracle(t.kind, t.words, **cfg)
     osid, oent, _ = o.replay(path, n_births=t.n_births)
-    tree = PhylogeneticTree(t.kind, t.words, **cfg)
+    flags = 0
+    if rng.random() < 0.2:                      # device exp() instead of the table: streams stop inside the guard band
+        flags = 4
+        forced["generic compatibility (flag 4)"] = "1"
+    tree = PhylogeneticTree(t.kind, t.words, flags=flags, **cfg)
     to_device = None
-    if rng.random() < 0.3:                      # genomes resident in HBM (apt_tree_add_genomes_dev)
+    if allow_device_payload and rng.random() < 0.3:                      # genomes resident in HBM (apt_tree_add_genomes_dev)
         import torch
 
         def to_device(a):
