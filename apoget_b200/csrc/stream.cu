@@ -747,15 +747,17 @@ bool launchWQ (const StreamArgs &a, cudaStream_t st, uint32_t cluster = 1) {
   if (b.lut_in_smem) smem += lutBytes;
   bool ok = true;
   auto go = [&] (auto kernel) {
-    // (the attribute call costs microseconds: made when the size changes, not per launch.  One entry per instantiation
-    // of this lambda, i.e. per kernel variant; a tree is driven by one host thread)
-    static size_t smemSet = ~size_t(0);
-    static int devSet = -1;
+    // (the attribute call costs microseconds: made when the size changes, not per launch.  Keyed by the kernel: every
+    // variant has the same pointer TYPE, so this lambda -- and a plain static in it -- is shared by all of them)
+    struct Set { const void *fn; size_t smem; int dev; };
+    static Set sets[4] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (smemSet != smem || devSet != dev) {
+    Set *e = nullptr;
+    for (Set &q: sets) if (q.fn == reinterpret_cast<const void*>(kernel) || (!q.fn && !e)) { e = &q; if (q.fn) break; }
+    if (!e || e->fn != reinterpret_cast<const void*>(kernel) || e->smem != smem || e->dev != dev) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      smemSet = smem;  devSet = dev;
+      if (e) { e->fn = reinterpret_cast<const void*>(kernel);  e->smem = smem;  e->dev = dev; }
     }
     // (preload: the runtime loads a kernel on its first use -- milliseconds that would otherwise land in the first pass)
     if (a.preload) { cudaFuncAttributes fa;  cudaFuncGetAttributes(&fa, kernel);  return; }

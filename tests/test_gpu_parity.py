@@ -118,6 +118,23 @@ def test_long_streams_on_clusters_equal_single_cta_streams(seed, monkeypatch):
     assert int(np.bincount(a[0]).max()) >= 2048, "the trace has no long stream"
 
 
+def test_table_and_generic_variants_of_the_wide_stream_kernel_in_one_process(monkeypatch):
+    """The variants of a stream kernel that need more than 48 KB of shared memory (long streams) each need their own
+    opt-in before the first launch: a process that runs the table variant and then the generic one (device exp()) with the
+    same shared-memory size once skipped the second opt-in (launch: invalid argument).  Same trace through both: same
+    tree."""
+    from apoget_b200.tree import PhylogeneticTree
+    monkeypatch.setenv("APT_STREAM_CLUSTER_MIN", "1000000000")         # the 16-warp single-CTA variant, not clusters
+    t = synth.generate(kind=synth.BITS, words=4, pop=5000, gens=4, seed=77, flips=1.0, sigma=9.0, hybrid=0.02)
+    out = []
+    for flags in (0, 4, 0, 4):
+        tree = PhylogeneticTree(t.kind, t.words, flags=flags, K=10)
+        sids, slots = tree.replay(t)
+        out.append((sids, slots, tree.to_json()))
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and np.array_equal(o[1], out[0][1]) and o[2] == out[0][2]
+
+
 @pytest.mark.parametrize("seed", range(1000, 1012))
 def test_randomised_trees_with_random_device_paths(seed):
     """tools/fuzz_gpu.py's cases (random genome kind / width / enveloppe size / criterion / hybrids / radiations, a random

@@ -87,7 +87,13 @@ def main():
     ap.add_argument("--pop-max", type=int, default=20000)
     args = ap.parse_args()
     t0 = time.time()
-    rows = [one(s, args.pop_max) for s in range(args.first, args.first + args.seeds)]
+    rows = []
+    for s in range(args.first, args.first + args.seeds):
+        try:
+            rows.append(one(s, args.pop_max))
+        except Exception as e:                   # an engine error is a failed case too
+            rows.append(dict(seed=s, births=0, family_births=0, stream_births=0, bad=["exception: " + str(e)[:300]],
+                             env={k: v for k, v in os.environ.items() if k.startswith("APT_")}))
     failed = [r for r in rows if r["bad"]]
     print(json.dumps({"seeds": args.seeds, "first": args.first, "births": sum(r["births"] for r in rows),
                       "family_births": sum(r["family_births"] for r in rows), "stream_births": sum(r["stream_births"] for r in rows),
