@@ -181,15 +181,25 @@ class PhylogeneticTree:
                     n_children=info.n_children, n_contributors=info.n_contributors)
 
     # -- trace replay (same loop as oracle/ref_driver.cpp) -----------------------------------------
-    def replay(self, trace, max_gens: int | None = None, to_device=None):
-        """Feeds a synth.Trace generation by generation: one add_genomes batch per generation, then
+    def replay(self, trace, max_gens: int | None = None, to_device=None, cuts=None):
+        """Feeds a synth.Trace generation by generation: one add_genomes batch per generation (or, with
+        ``cuts(g, n) -> increasing offsets inside (0, n)``, several calls per generation), then
         the deaths, then step().  Returns (sid per birth, slot per birth)."""
         B = trace.n_births
         sid_of = np.full(B, INVALID, dtype=np.uint32)
         slot_of = np.full(B, -1, dtype=np.int32)
         gens = trace.n_gens if max_gens is None else min(max_gens, trace.n_gens)
         for g in range(gens):
-            b0, b1 = int(trace.gen_birth_off[g]), int(trace.gen_birth_off[g + 1])
+            g0, g1 = int(trace.gen_birth_off[g]), int(trace.gen_birth_off[g + 1])
+            edges = [g0] + ([g0 + int(c) for c in cuts(g, g1 - g0) if 0 < int(c) < g1 - g0] if cuts else []) + [g1]
+            for b0, b1 in zip(edges[:-1], edges[1:]):
+                self._replay_call(trace, b0, b1, sid_of, slot_of, to_device)
+            self.del_genomes(sid_of[trace.deaths_of(g)])
+            self.step(g + 1, sid_of[trace.alive_of(g)])
+        return sid_of, slot_of
+
+    def _replay_call(self, trace, b0, b1, sid_of, slot_of, to_device):
+        if True:
             m, f = trace.mother[b0:b1], trace.father[b0:b1]
             hm, hf = m != INVALID, f != INVALID
             mgid = np.where(hm, m + 1, INVALID).astype(np.uint32)
@@ -210,6 +220,3 @@ class PhylogeneticTree:
                                      [_ptr(x) for x in (gid, mgid, msid, fgid, fsid)], _ptr(s), _ptr(sl), _ptr(rp))
                 del keep
             sid_of[b0:b1], slot_of[b0:b1] = s, sl
-            self.del_genomes(sid_of[trace.deaths_of(g)])
-            self.step(g + 1, sid_of[trace.alive_of(g)])
-        return sid_of, slot_of

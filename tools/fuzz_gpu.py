@@ -33,6 +33,11 @@ def one(seed, pop_max, allow_device_payload=True):
                hybrid=float(rng.choice([0.0, 0.02, 0.1])), hybrid_far=float(rng.choice([0.0, 0.1, 1.0])),
                burst_levels=int(rng.integers(0, 4)), burst_fanout=int(rng.choice([3, 10, 40])),
                compat_classes=int(rng.integers(1, 4)), survive=float(rng.choice([0.0, 0.3])))
+    # (dimensions added later: seeds from 10 000 on, drawn from a second generator -- a lower seed keeps the case it had,
+    # two of them are regression tests)
+    rng2 = np.random.default_rng(123_000 + seed)
+    if seed >= 10_000:
+        gen.update(founders=int(rng2.choice([1, 1, 2, 3])), parent_skew=float(rng2.choice([0.0, 0.0, 1.5])))
     if kind == synth.BITS:
         gen.update(flips=float(rng.uniform(0.3, 2.5)), sigma=float(rng.uniform(0.03, 0.12)) * words * 32, burst_bits=max(8, words * 6))
     else:
@@ -67,7 +72,12 @@ def one(seed, pop_max, allow_device_payload=True):
             torch.cuda.synchronize()
             return d, d.data_ptr(), torch.cuda.current_stream().cuda_stream
         forced["device-resident genomes"] = "1"
-    sids, slots = tree.replay(t, to_device=to_device)
+    cuts = None
+    if seed >= 10_000 and rng2.random() < 0.3:  # a generation handed over in several calls of random sizes (the result may not depend on it)
+        crng = np.random.default_rng(seed)
+        cuts = lambda g, n: sorted(set(int(x) for x in crng.integers(1, max(2, n), size=int(crng.integers(1, 5)))))   # noqa: E731
+        forced["random batch boundaries"] = "1"
+    sids, slots = tree.replay(t, to_device=to_device, cuts=cuts)
     bad = []
     if not np.array_equal(sids, osid): bad.append("sids")
     if not np.array_equal(slots >= 0, oent > 0): bad.append("entries")
