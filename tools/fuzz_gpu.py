@@ -51,6 +51,9 @@ def one(seed, pop_max, allow_device_payload=True):
         os.environ.pop(var, None)
         if rng.random() < p:
             os.environ[var] = forced[var] = "1"
+    os.environ.pop("APT_LUT_MAX_BYTES", None)
+    if seed >= 20_000 and rng2.random() < 0.15:  # the compatibility table overflows somewhere in the run: generic path from there
+        os.environ["APT_LUT_MAX_BYTES"] = forced["APT_LUT_MAX_BYTES"] = str(int(rng2.choice([1, 3000, 20000])))
     os.environ.pop("APT_DEVGROUP_PAGEABLE", None)
     if "APT_DEVGROUP_MIN" in forced:
         os.environ["APT_DEVGROUP_PAGEABLE"] = "1"
