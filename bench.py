@@ -47,8 +47,8 @@ SETUP_GENS = 4          # generations 0..3: root + three 10-way radiations -> 1 
 WORKLOAD = dict(kind=synth.BITS, words=8, flips=0.5, sigma=12.0, hybrid=0.05, burst_levels=3, burst_fanout=10)
 TREE_CFG = dict(K=10)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/)
-TRAFFIC = {"score_pairs_kernel": 6.10e6, "resolve_streams_kernel": 6.14e6}
-TRAFFIC_SOURCE = "ncu --set full capture of an earlier run of this workload (profiles/r01h_resolve_streams_ncu.txt), not measured in this run"
+TRAFFIC = {"score_pairs_kernel": 6.10e6, "resolve_streams_kernel": 6.15e6}
+TRAFFIC_SOURCE = "ncu --set full capture of an earlier run of this workload (profiles/r02c_resolve_streams_ncu.txt: dram read 6.15 MB, written 0), not measured in this run"
 METRIC = "births classified/sec (species assignment, reference-exact)"
 UNIT = "births/s"
 
