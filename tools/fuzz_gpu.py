@@ -29,6 +29,8 @@ def one(seed, pop_max, allow_device_payload=True):
     kind = synth.F32 if rng.random() < 0.2 else synth.BITS
     words = int(rng.choice([4, 8, 16, 32, 128])) if kind == synth.BITS else int(rng.choice([16, 64]))
     K = int(rng.choice([1, 2, 3, 5, 5, 10, 10]))
+    if seed >= 30_000:                          # (drawn from the same stream position: lower seeds keep their cases) other enveloppe sizes, up to the largest supported
+        K = int([4, 7, 17, 32][K % 4])
     gen = dict(kind=kind, words=words, pop=int(rng.integers(300, pop_max)), gens=int(rng.integers(4, 9)), seed=seed,
                hybrid=float(rng.choice([0.0, 0.02, 0.1])), hybrid_far=float(rng.choice([0.0, 0.1, 1.0])),
                burst_levels=int(rng.integers(0, 4)), burst_fanout=int(rng.choice([3, 10, 40])),
