@@ -70,6 +70,48 @@ def test_dropin_source_is_a_reference_program(name, extra, tmp_path):
     assert open(out["ref"] + ".walk").read() == open(out["ours"] + ".walk").read(), "node walk / copy construction"
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_dropin_random_traces_against_the_reference_program(seed, tmp_path):
+    """Fresh random simulations (genome width, enveloppe size, criterion, scoring mode, hybrids, radiations, founders)
+    through the SAME test program built against the reference's header and against ours: results, callbacks, dumps,
+    read-back, node walk, copies and dot files must be identical.  Needs /root/reference (build container only)."""
+    from apoget_b200 import synth
+    from hostsim import build as hb
+    from cpp import build as cb
+    ref = cb.build_reference()
+    if ref is None:
+        pytest.skip("/root/reference is not present on this box")
+    ours = cb.build(hb.build(), "hostsim")
+    rng = np.random.default_rng(4200 + seed)
+    words = int(rng.choice([8, 8, 8, 128]))                     # (the genome widths test_dropin.cpp instantiates)
+    K = int(rng.choice([2, 3, 5, 10]))
+    t = synth.generate(kind=synth.BITS, words=words, pop=int(rng.integers(60, 300)), gens=int(rng.integers(5, 12)), seed=seed,
+                       flips=float(rng.uniform(0.3, 2.5)), sigma=float(rng.uniform(0.03, 0.1)) * words * 32,
+                       hybrid=float(rng.choice([0.0, 0.05, 0.3])), hybrid_far=float(rng.choice([0.0, 0.2, 1.0])),
+                       burst_levels=int(rng.integers(0, 3)), burst_fanout=int(rng.choice([3, 10])), burst_bits=max(8, words * 6),
+                       founders=int(rng.choice([1, 1, 2])), survive=float(rng.choice([0.0, 0.4])))
+    trace = str(tmp_path / "t.trace")
+    synth.write_trace(trace, t)
+    extra = (["--semi"] if seed % 4 == 3 else []) + (["--crit", str(int(rng.choice([0, 2, 3])))] if seed % 2 else [])
+    out, verdict = {}, {}
+    for tag, exe in (("ref", ref), ("ours", ours)):
+        prefix = str(tmp_path / tag)
+        r = subprocess.run([exe, trace, prefix, str(K)] + extra, capture_output=True, text=True)
+        # (the program's own consistency checks are written for the default configuration: under the reference's debug
+        # options some do not hold for the reference either -- what matters here is that both builds say the same)
+        assert r.returncode in (0, 3), tag + ": " + r.stdout + r.stderr
+        verdict[tag] = (r.returncode, json.loads(r.stdout.strip().splitlines()[-1])["bad"])
+        out[tag] = prefix
+    assert verdict["ref"] == verdict["ours"], verdict
+    a, b = oracle.read_res(out["ref"] + ".res"), oracle.read_res(out["ours"] + ".res")
+    assert np.array_equal(a["sids"], b["sids"]) and np.array_equal(a["entered"], b["entered"])
+    assert np.array_equal(a["events"], b["events"]) and a["stats"] == b["stats"]
+    for ext in (".json", ".rt.json"):
+        assert json.load(open(out["ref"] + ext)) == json.load(open(out["ours"] + ext)), ext
+    assert open(out["ref"] + ".dot").read() == open(out["ours"] + ".dot").read(), "logTo"
+    assert open(out["ref"] + ".walk").read() == open(out["ours"] + ".walk").read(), "node walk / copy construction"
+
+
 def test_dropin_deep_copy_is_compared_somewhere(tmp_path):
     """At least one case has every species below the root, so that copy construction + assertEqual(.., deepcopy) runs."""
     from hostsim import build as hb
