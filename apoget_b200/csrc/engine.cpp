@@ -157,6 +157,7 @@ Engine::Engine (const apt_params &p) : p_(p) {
     if (const char *e = getenv("APT_PAR_MIN")) parMin_ = uint32_t(std::max(1, atoi(e)));
     if (const char *e = getenv("APT_STAGE_MIN")) stageMin_ = size_t(std::max(1, atoi(e)));
     profile_ = getenv("APT_PROFILE") != nullptr;
+    if (getenv("APT_SUBTREE_WALK")) ageOrdered_ = false;     // (tests: keep the reference's walk in elligibile())
     if (const char *e = getenv("APT_STREAM_PROF")) streamProf_ = e;
     if (const char *e = getenv("APT_DEVLIST_MIN")) devListMin_ = uint32_t(std::max(1, atoi(e)));
     if (const char *e = getenv("APT_DEVGROUP_MIN")) devGroupMin_ = uint32_t(std::max(1, atoi(e)));
@@ -219,6 +220,12 @@ bool Engine::elligibile (uint32_t lhs, uint32_t rhs) const {
   if (rhs >= nodes_.size() || !nodes_[rhs]) return false;      // removed species are ignored
   const Species *q = nodes_[rhs];
   if (n->first <= q->first) return false;                       // no younger (or same-age) parent
+  // The walk below cannot find n while every contributor flagged eligible is older than its species (ageOrdered_):
+  // parents are picked among those (currentMain), so `first` strictly decreases along q's ancestors, all of them older
+  // than q, which is older than n.  Flags come from this function or from a JSON dump (checked on load), `first` never
+  // changes.  A species that is being created has no subtree either way.  The walk is a chain of cold cache lines as long
+  // as the lineage is deep -- the cost of founding a species grew with the age of the simulation.
+  if (ageOrdered_ || n == freshNode_) return true;
   while (q && q != n) q = q->parent;                            // not inside n's subtree
   return q != n;
 }
@@ -315,7 +322,9 @@ Species* Engine::makeNode (const Contributions &contrib) {
   if (nodes_.size() <= n->sid) nodes_.resize(std::max<size_t>(n->sid + 1, nodes_.size() * 2), nullptr);
   nodes_[n->sid] = n;
   width_++;
+  freshNode_ = n;
   nodeUpdate(n, contrib);
+  freshNode_ = nullptr;
   if (n->parent) n->parent->children.push_back(n);
   emit(APT_EV_NEW_SPECIES, n->parent ? n->parent->sid : INV, n->sid, 0);
   return n;
@@ -2574,6 +2583,7 @@ void Engine::cloneFrom (const Engine &that) {
   if (root_ || nextNodeID_ || width_) throw ApiError(APT_ERR_STATE, "cloning needs an empty tree");
   if (that.K_ != K_ || that.W_ != W_ || that.p_.kind != p_.kind) throw ApiError(APT_ERR_ARGUMENT, "cloning between trees of different shapes");
   nextNodeID_ = that.nextNodeID_;  stillborns_ = that.stillborns_;  step_ = that.step_;
+  ageOrdered_ = that.ageOrdered_;
   struct Rec {
     Engine &e;  const Engine &o;
     Species* node (const Species *src) {
@@ -2787,6 +2797,7 @@ void Engine::fromJson (const std::string &text) {
       if (!armed) return;
       for (Species *n: e.nodes_) delete n;
       e.nodes_.clear();  e.root_ = nullptr;  e.width_ = 0;  e.nextNodeID_ = 0;  e.step_ = 0;  e.stillborns_ = 0;
+      e.ageOrdered_ = true;
       e.aliveSpecies_.clear();  e.refresh_.clear();  e.fillUpdates_.clear();  e.freeSlots_.clear();
       for (uint32_t s = e.nSlots_; s-- > 0; ) e.freeSlots_.push_back(s);       // every slot is free again
       std::fill(e.sidSlot_.begin(), e.sidSlot_.end(), INV);
@@ -2859,6 +2870,12 @@ void Engine::fromJson (const std::string &text) {
                      [] (const Contributor &l, const Contributor &r) { return l.count > r.count; });
     Species *newMC = updateParent(n, currentMain(n));
     if (newMC) newMC->children.push_back(n);
+  }
+  // a dump written by hand may flag a younger (or missing) contributor as eligible: elligibile() then keeps its subtree walk
+  for (const Species *n: nodes_) {
+    if (!n) continue;
+    for (const Contributor &c: n->contribs)
+      if (c.elligible && (c.sid >= nodes_.size() || !nodes_[c.sid] || nodes_[c.sid]->first >= n->first)) ageOrdered_ = false;
   }
   rollback.armed = false;
 }

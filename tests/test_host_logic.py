@@ -74,6 +74,49 @@ def test_host_resolution_logic_matches_reference(hostsim, name):
     _compare(hostsim, name)
 
 
+@pytest.mark.parametrize("name", ["hybrids_b256_k5", "founders_orphans_classes", "c5_speciation_trimming", "ragged_b96_k3"])
+def test_eligibility_with_the_reference_walk_kept(hostsim, name, monkeypatch):
+    """speciescontributors.h:177-197: the engine concludes from the species' ages that a candidate's ancestors cannot
+    contain the species; with the reference's walk up the ancestors kept, the trees (and their dumps) are the same."""
+    monkeypatch.setenv("APT_SUBTREE_WALK", "1")
+    _compare(hostsim, name)
+
+
+def test_hand_written_dump_with_a_younger_eligible_contributor_loads(hostsim):
+    """A dump may flag a contributor as eligible that the engine itself never would (younger than the species): it loads
+    and dumps back what it was given (the ancestor walk of elligibile() is kept for such a tree)."""
+    import json
+    name = "hybrids_b256_k5"
+    cfg = golden_cases()[name]["cfg"]
+    t = synth.read_trace(golden_trace_path(name))
+    j = golden_json(name)
+
+    def nodes(n):
+        yield n
+        for c in n["children"] or []:
+            yield from nodes(c)
+    all_nodes = list(nodes(j["tree"]))
+    first = {n["id"]: n["data"][0] if isinstance(n["data"], list) else n["data"]["firstAppearance"] for n in all_nodes}
+    # a contributor behind the current major one (the parent stays what it is), younger than the species or as old
+    def late_younger(n):
+        seen_main = False
+        for c in n["contribs"]:
+            if seen_main and not c[2] and c[0] in first and c[0] != n["id"] and first[c[0]] >= first[n["id"]]:
+                return c
+            seen_main = seen_main or c[2]
+        return None
+    victim = next(n for n in all_nodes if late_younger(n))
+    late_younger(victim)[2] = True
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    tree.from_json(j)
+    d1 = tree.to_json()
+    again = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    again.from_json(d1)
+    assert again.to_json() == d1
+    flagged = [c for n in nodes(d1["tree"]) if n["id"] == victim["id"] for c in n["contribs"] if c[2] and first[c[0]] >= first[n["id"]]]
+    assert flagged, "the hand-set flag is kept as stored (phylogenetictree.hpp:960-962 sorts and re-parents, nothing else)"
+
+
 @pytest.mark.parametrize("name", ["c2_b256_k10", "hybrids_b256_k5", "founders_orphans_classes"])
 def test_host_resolution_logic_generic_compat(hostsim, name):
     """Device exp() path (stub perturbs it by an ulp): the guard band must hide it."""
