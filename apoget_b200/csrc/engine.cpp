@@ -285,11 +285,18 @@ Species* Engine::nodeUpdate (Species *n, const Contributions &c) { return update
 
 // phylogenetictree.hpp:773-783 with node.hpp:191-194 and speciescontributors.cpp:85-90
 void Engine::updateElligibilities (void) {
+  // With ageOrdered_ (see elligibile) a flag is "the contributor exists and is older than the species": the ages never
+  // change, every flag was computed by that rule when its entry was made, and every contributors update re-derives the
+  // parent (nodeUpdate).  Until a species is REMOVED (stillborn trimming leaves flags naming it behind, as in the
+  // reference) or flags arrive from a dump, this pass over every species of the tree would rewrite what is there -- at
+  // a million species it was 75 ms per change of a major contributor.
+  if (ageOrdered_ && !eligStale_) return;
   for (Species *n: nodes_) {
     if (!n) continue;
     for (Contributor &c: n->contribs) c.elligible = elligibile(n->sid, c.sid);
     updateParent(n, currentMain(n));
   }
+  eligStale_ = false;
 }
 
 /// sidSlot_ mirrors "the device holds a current copy of this species" (dev_fill > 0)
@@ -363,6 +370,7 @@ void Engine::performStillbornTrimming (void) {
       }
       stillborns_++;
       nodes_[i] = nullptr;
+      eligStale_ = true;
       setStreamable(s, false);
       width_--;
       freeSlots_.push_back(s->slot);
@@ -2612,6 +2620,7 @@ void Engine::cloneFrom (const Engine &that) {
   } rec { *this, that };
   // (`that.root_` may point at a trimmed node, as in the reference; it is copied all the same, :101)
   if (that.root_) root_ = rec.node(that.root_);
+  eligStale_ = true;                      // (species outside the root's subtree are lost in a copy: flags naming them go)
   updateElligibilities();
 }
 
@@ -2797,7 +2806,7 @@ void Engine::fromJson (const std::string &text) {
       if (!armed) return;
       for (Species *n: e.nodes_) delete n;
       e.nodes_.clear();  e.root_ = nullptr;  e.width_ = 0;  e.nextNodeID_ = 0;  e.step_ = 0;  e.stillborns_ = 0;
-      e.ageOrdered_ = true;
+      e.ageOrdered_ = true;  e.eligStale_ = false;
       e.aliveSpecies_.clear();  e.refresh_.clear();  e.fillUpdates_.clear();  e.freeSlots_.clear();
       for (uint32_t s = e.nSlots_; s-- > 0; ) e.freeSlots_.push_back(s);       // every slot is free again
       std::fill(e.sidSlot_.begin(), e.sidSlot_.end(), INV);
@@ -2877,6 +2886,7 @@ void Engine::fromJson (const std::string &text) {
     for (const Contributor &c: n->contribs)
       if (c.elligible && (c.sid >= nodes_.size() || !nodes_[c.sid] || nodes_[c.sid]->first >= n->first)) ageOrdered_ = false;
   }
+  eligStale_ = true;                      // flags as stored: the next eligibility pass recomputes them all
   rollback.armed = false;
 }
 

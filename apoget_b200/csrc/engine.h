@@ -394,6 +394,7 @@ private:
   static constexpr uint32_t CHUNK_MIN = 1024, CHUNK_MAX = 1u << 20;
   uint32_t adaptChunk_ = 4096;          // births per device pass, adapted to how much of the last pass fell back to the host
   bool ageOrdered_ = true;                // every contributor flagged eligible is older than its species (elligibile)
+  bool eligStale_ = false;                // a species was removed, or flags came from a dump, since the last tree-wide eligibility pass
   const Species *freshNode_ = nullptr;    // the node makeNode is linking into the tree (elligibile: it has no subtree)
   double profWalk_[3] = {0, 0, 0};  uint64_t profWalkN_[3] = {0, 0, 0};   // APT_PROFILE: serial commit by category
   bool profile_ = false;                // APT_PROFILE: per-phase host timings on stderr
