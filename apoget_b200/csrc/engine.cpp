@@ -2383,6 +2383,20 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
           __builtin_prefetch(sp->reps.data(), 1);  __builtin_prefetch(sp->dist.data(), 1);
           __builtin_prefetch(sp->contribs.data(), 1);
           __builtin_prefetch(&hPayload_[size_t(sp->slot) * K_ * wp_], 1);
+          if (!sp->children.empty()) __builtin_prefetch(&sp->children.back());
+        }
+      }
+      // a birth its stream rejected walks the species' sub-species, newest first: their records are cold too
+      if (si + 2 < slow_.size()) {
+        const uint32_t j = slow_[si + 2];
+        const int32_t bg = bg_[j];
+        if (bg >= 0 && (hAct_.p[j] & ACT_CODE_MASK) == ACT_FALLTHROUGH) {
+          const Species *sp = grpSpecies_[size_t(bg)];
+          const size_t nc = sp->children.size();
+          for (size_t c = 0; c < std::min<size_t>(nc, 2); c++) {
+            const char *cp = reinterpret_cast<const char*>(sp->children[nc - 1 - c]);
+            __builtin_prefetch(cp, 1);  __builtin_prefetch(cp + 64, 1);  __builtin_prefetch(cp + 128, 1);
+          }
         }
       }
       Species *s0 = nullptr;
