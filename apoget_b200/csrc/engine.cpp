@@ -839,6 +839,18 @@ void Engine::resolveBelowStream (const uint32_t *w, const RepMeta &g, Species *s
   size_t idx = s0->children.size();
   while (idx-- > 0) {
     Species *sub = s0->children[idx];
+    // (the walk is a chain of cold records: the next two sub-species' are requested while this one is looked at, and
+    // the stream state of the next one)
+    if (idx >= 2) {
+      const char *cp = reinterpret_cast<const char*>(s0->children[idx - 2]);
+      __builtin_prefetch(cp);  __builtin_prefetch(cp + 64);  __builtin_prefetch(cp + 128);
+    }
+    if (idx >= 1) {
+      const Species *nx = s0->children[idx - 1];
+      if (nx->grp_epoch == chunkEpoch_ && nx->grp_index < grpState_.size()) {
+        __builtin_prefetch(&grpState_[nx->grp_index]);  __builtin_prefetch(&hGrpSum_.p[nx->grp_index]);
+      }
+    }
     branching_++;
     bool decided = false;
     if (dev && idx < snapN) {
@@ -2398,6 +2410,60 @@ void Engine::runChunk (uint32_t n, const uint32_t *payload, const float *compat,
             __builtin_prefetch(cp, 1);  __builtin_prefetch(cp + 64, 1);  __builtin_prefetch(cp + 128, 1);
           }
         }
+      }
+      // a birth outside the streams (two parent species, mostly) is scored on the host against both species and their
+      // sub-species: a chain of dependent cold lines (id -> record -> list of sub-species -> their records -> their
+      // genomes), requested stage by stage over the births in front of it
+      auto parentsOf = [&] (uint32_t j, const Species *out[2]) {
+        out[0] = msid[j] < nodes_.size() ? nodes_[msid[j]] : nullptr;
+        out[1] = (fsid[j] != msid[j] && fsid[j] < nodes_.size()) ? nodes_[fsid[j]] : nullptr;
+      };
+      if (si + 9 < slow_.size()) {
+        const uint32_t j = slow_[si + 9];
+        if (bg_[j] < 0) {
+          if (msid[j] < nodes_.size()) __builtin_prefetch(&nodes_[msid[j]]);
+          if (fsid[j] < nodes_.size()) __builtin_prefetch(&nodes_[fsid[j]]);
+        }
+      }
+      if (si + 7 < slow_.size() && bg_[slow_[si + 7]] < 0) {
+        const Species *ps[2];
+        parentsOf(slow_[si + 7], ps);
+        for (const Species *sp: ps)
+          if (sp) {
+            const char *cp = reinterpret_cast<const char*>(sp);
+            __builtin_prefetch(cp);  __builtin_prefetch(cp + 64);  __builtin_prefetch(cp + 128);
+          }
+      }
+      if (si + 5 < slow_.size() && bg_[slow_[si + 5]] < 0) {
+        const Species *ps[2];
+        parentsOf(slow_[si + 5], ps);
+        for (const Species *sp: ps)
+          if (sp) {
+            __builtin_prefetch(sp->reps.data());  __builtin_prefetch(sp->contribs.data(), 1);
+            __builtin_prefetch(&hPayload_[size_t(sp->slot) * K_ * wp_]);
+            if (!sp->children.empty()) __builtin_prefetch(&sp->children.back());
+          }
+      }
+      if (si + 3 < slow_.size() && bg_[slow_[si + 3]] < 0) {
+        const Species *ps[2];
+        parentsOf(slow_[si + 3], ps);
+        for (const Species *sp: ps)
+          if (sp) {
+            const size_t nc = sp->children.size();
+            for (size_t c = 0; c < std::min<size_t>(nc, 2); c++) {
+              const char *cp = reinterpret_cast<const char*>(sp->children[nc - 1 - c]);
+              __builtin_prefetch(cp, 1);  __builtin_prefetch(cp + 64, 1);  __builtin_prefetch(cp + 128, 1);
+            }
+          }
+      }
+      if (si + 1 < slow_.size() && bg_[slow_[si + 1]] < 0) {
+        const Species *ps[2];
+        parentsOf(slow_[si + 1], ps);
+        for (const Species *sp: ps)
+          if (sp && !sp->children.empty()) {
+            const Species *c = sp->children.back();
+            __builtin_prefetch(c->reps.data());  __builtin_prefetch(&hPayload_[size_t(c->slot) * K_ * wp_]);
+          }
       }
       Species *s0 = nullptr;
       uint32_t act = 0;
