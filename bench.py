@@ -422,7 +422,11 @@ def main() -> None:
                      "births_per_s_kernel": units / (kernel_ms * 1e-3) if kernel_ms else 0,
                      "note": "latency-bound by construction: one CTA per species stream, the launch lasts as long as the stream with most "
                              "enveloppe entries (~8 us fixed + ~1.0 us per entry, up to 13 per step; DESIGN.md 4.1) and moves 9 MB, 1.4 us worth "
-                             "of HBM time; the throughput kernel of this path is the dense sweep (dense_sweep.roofline)"},
+                             "of HBM time; the throughput kernel of this path is the dense sweep (dense_sweep.roofline)",
+                     "other_kernels_of_the_step": "group_births_kernel (one cooperative launch on the upload stream, beside the genomes' H2D copy) lasts "
+                                                  "58 us under ncu (profiles/r02g_launches_summary.txt) -- longer than this kernel -- but is PCIe-bound, not "
+                                                  "HBM-bound: it reads the 0.8 MB of parent species ids in place from page-locked host memory and writes "
+                                                  "0.8 MB of tables back (DESIGN.md 2.2, 4); unsettled_count/list 4 + 5 us"},
         "clocks": clocks,
         "breakdown_e2e_ms_per_step": {
             "prepare": 1e3 * dt["prepare_s"] / args.steps,
